@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 ray-tracing backend (BASELINE.json metric).
+
+A "step" is one C3 pass (BASELINE config 2): 1024x1024 primary rays generated on the device ->
+closest hit against the 10,008,338-triangle displaced grid -> shadow rays to the point light (any-hit) and
+cosine-bounce rays (incoherent closest hit) spawned from the hits -> both traced.  3 x 1,048,576 rays per step.
+
+  value     = rays traced / device time, inputs resident in HBM (CUDA events on the launching stream)
+  e2e       = the same three batches through the host-buffer C ABI (pb2_intersect / pb2_intersect_p) from pinned host
+              memory, H2D + D2H inside the timed region
+  roofline  = algorithmic bytes of the incoherent closest-hit launch (oracle-counted nodes/triangles in reference order,
+              SURVEY §8d) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference = the CPU restatement of the reference (oracle/, all host threads) on a bounded sample
+
+Launch: `python bench.py --gpus 1` or `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`.
+With N > 1 every rank traces its own full pass from a camera rotated about the y axis (weak scaling, BVH replicated,
+no data-path collective for ray casting).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid-n", type=int, default=2237, help="quads per side of the C3 grid (2237 -> 10,008,338 triangles)")
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-stride", type=int, default=4, help="cpu sample = every k-th ray of each ray set")
+    return ap.parse_args()
+
+
+def rank_info():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def camera_for_rank(scenes, rank, res):
+    cam = dict(scenes.C3_CAMERA, res=(res, res))
+    if rank:
+        a = 2.0 * np.pi * rank / 8.0
+        x, y, z = cam["pos"]
+        cam["pos"] = (float(x * np.cos(a) - z * np.sin(a)), y, float(x * np.sin(a) + z * np.cos(a)))
+    return cam
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(n_rays, nodes, tris, hit_bytes):
+    # B(r) = 32 (ray in) + 16 or 4 (hit / any-hit out) + 32 N_nodes(r) + 36 N_tris(r)
+    return n_rays * (32 + hit_bytes) + 32 * int(nodes) + 36 * int(tris)
+
+
+def host_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return os.cpu_count() or 1, model
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference hot path (oracle/; the Rust crate cannot be built —
+    no rustc/cargo in the image), all host threads, on a bounded sample of the C3 pass."""
+    rank, _, world = rank_info()
+    if rank != 0:
+        return
+    scenes, orc = ge.load_scenes(), ge.load_oracle()
+    verts, idx = scenes.scene_c3(args.grid_n)
+    cam = camera_for_rank(scenes, 0, args.res)
+    ref = orc.BVHAccel(verts, idx, 4)
+    rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    hits, b0, _ = ref.intersect(rays, want_b0=True)
+    srays = orc.spawn_shadow_rays(ref, hits, b0, scenes.C3_POINT_LIGHT)
+    brays = orc.spawn_bounce_rays(ref, rays, hits, b0)
+    k = max(1, args.cpu_stride)
+    sample = [np.ascontiguousarray(rays[::k]), np.ascontiguousarray(srays[::k]), np.ascontiguousarray(brays[::k])]
+    n_sample = sum(len(s) for s in sample)
+    cores, model = host_info()
+
+    def step():
+        return ref.intersect(sample[0])[-1] + ref.intersect_p(sample[1])[-1] + ref.intersect(sample[2])[-1]
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = float(sum(times))
+    value = n_sample * args.steps / total / 1e6
+    line = {
+        "impl": "reference", "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C3: {len(idx)}-triangle displaced grid, {args.res}x{args.res} primary closest-hit + shadow any-hit + "
+                               "incoherent bounce closest-hit, SAH BVH max_prims_in_node=4"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
+                         "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays per step), traversal time only"},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of pbrt-rs BVHAccel/Triangle (oracle/); the Rust reference itself is not compilable here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    rank, local_rank, world = rank_info()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pb2, scenes = ge.load_package(), ge.load_scenes()
+    pb2.init(local_rank)                    # raises if the extension or the GPU is missing: no fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    t0 = time.time()
+    verts, idx = scenes.scene_c3(args.grid_n)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    accel = pb2.BVHAccel(verts, idx, max_prims_in_node=4)
+    t_build = time.time() - t0
+    n_nodes, n_prims, depth = accel.info()
+    cam = camera_for_rank(scenes, rank, args.res)
+    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    n = args.res * args.res
+
+    def dbuf(nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    d_rays, d_hits, d_b0 = dbuf(n * 32), dbuf(n * 16), dbuf(n * 4)
+    d_srays, d_brays, d_occ, d_bhits = dbuf(n * 32), dbuf(n * 32), dbuf(n), dbuf(n * 16)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    names = ["raygen", "closest_primary", "spawn", "any_shadow", "closest_bounce"]
+
+    def device_step(events=None):
+        def mark(i):
+            if events is not None:
+                events[i].record()
+        mark(0)
+        camera.primary_rays_device(d_rays.data_ptr(), stream)
+        mark(1)
+        accel.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), d_b0.data_ptr(), stream)
+        mark(2)
+        accel.spawn_shadow_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, scenes.C3_POINT_LIGHT, d_srays.data_ptr(), stream)
+        accel.spawn_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_brays.data_ptr(), stream)
+        mark(3)
+        accel.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), stream)
+        mark(4)
+        accel.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
+        mark(5)
+    launches_per_step = 6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+        flush.zero_()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    all_events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        device_step(all_events[s])
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pairs)
+    barrier()
+    step_ms = [ev[0].elapsed_time(ev[5]) for ev in all_events]
+    kernel_ms = {names[i]: float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in all_events])) for i in range(5)}
+    total_ms = float(sum(step_ms))
+
+    # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region ----
+    h_rays = torch.empty(n * 8, dtype=torch.float32).pin_memory()
+    h_srays, h_brays = torch.empty_like(h_rays).pin_memory(), torch.empty_like(h_rays).pin_memory()
+    h_hits, h_bhits = torch.empty(n * 4, dtype=torch.int32).pin_memory(), torch.empty(n * 4, dtype=torch.int32).pin_memory()
+    h_occ = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_rays.copy_(d_rays.view(torch.float32))
+    h_srays.copy_(d_srays.view(torch.float32))
+    h_brays.copy_(d_brays.view(torch.float32))
+    torch.cuda.synchronize()
+    L = pb2.lib()
+
+    def e2e_step():
+        pb2.check(L.pb2_intersect(accel.h, h_rays.data_ptr(), n, h_hits.data_ptr(), None))
+        pb2.check(L.pb2_intersect_p(accel.h, h_srays.data_ptr(), n, h_occ.data_ptr()))
+        pb2.check(L.pb2_intersect(accel.h, h_brays.data_ptr(), n, h_bhits.data_ptr(), None))
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clock_rec = clocks.stop()
+    e2e_parity = bool(np.array_equal(h_hits.numpy(), d_hits.view(torch.int32).cpu().numpy())
+                      and np.array_equal(h_occ.numpy(), d_occ.cpu().numpy())
+                      and np.array_equal(h_bhits.numpy(), d_bhits.view(torch.int32).cpu().numpy()))
+
+    # ---- max over ranks ----
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    rays_per_step = 3 * n
+    value = world * rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    e2e_value = world * rays_per_step * args.steps / e2e_s / 1e6
+
+    # ---- roofline + cpu baseline (rank 0, after the GPU timing so host threads do not perturb it) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roofline, cpu_baseline, parity = None, None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        orc = ge.load_oracle()
+        ref = orc.BVHAccel(verts, idx, 4)
+        g_rays = d_rays.view(torch.float32).cpu().numpy().reshape(-1, 8)
+        g_srays = d_srays.view(torch.float32).cpu().numpy().reshape(-1, 8)
+        g_brays = d_brays.view(torch.float32).cpu().numpy().reshape(-1, 8)
+        rh, rb0, c_prim, _ = ref.intersect(g_rays, counters=True, want_b0=True)
+        ro, c_shadow, _ = ref.intersect_p(g_srays, counters=True)
+        rbh, c_bounce, _ = ref.intersect(g_brays, counters=True)
+        g_hits = d_hits.cpu().numpy().view(pb2.HIT_DTYPE)
+        g_bhits = d_bhits.cpu().numpy().view(pb2.HIT_DTYPE)
+        mism = int((g_hits["prim_id"] != rh["prim_id"]).sum() + (g_hits["t"].view(np.uint32) != rh["t"].view(np.uint32)).sum()
+                   + (d_occ.cpu().numpy() != ro).sum() + (g_bhits["prim_id"] != rbh["prim_id"]).sum()
+                   + (g_bhits["t"].view(np.uint32) != rbh["t"].view(np.uint32)).sum())
+        parity = {"rays_checked": 3 * n, "mismatches": mism, "checked_against": "oracle (CPU restatement), same ray batch",
+                  "e2e_equals_device": e2e_parity}
+        per_kernel = {}
+        for name, cnt, hb in (("closest_primary", c_prim, 16), ("any_shadow", c_shadow, 4), ("closest_bounce", c_bounce, 16)):
+            bts = algorithmic_bytes(n, cnt[0], cnt[1], hb)
+            per_kernel[name] = {"ms": kernel_ms[name], "algorithmic_bytes": bts, "gbs": bts / (kernel_ms[name] * 1e-3) / 1e9,
+                                "nodes_per_ray": float(cnt[0]) / n, "tris_per_ray": float(cnt[1]) / n,
+                                "mrays_s": n / (kernel_ms[name] * 1e-3) / 1e6}
+        dom = max(("closest_primary", "any_shadow", "closest_bounce"), key=lambda k: kernel_ms[k])
+        roofline = {"bound": "hbm", "kernel": f"k_closest_hit/k_any_hit [{dom}]", "achieved": per_kernel[dom]["gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": per_kernel[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "per_kernel": per_kernel}
+        k = max(1, args.cpu_stride)
+        sample = [np.ascontiguousarray(g_rays[::k]), np.ascontiguousarray(g_srays[::k]), np.ascontiguousarray(g_brays[::k])]
+        n_sample = sum(len(s) for s in sample)
+        ref.intersect(sample[0])
+        cpu_s = ref.intersect(sample[0])[-1] + ref.intersect_p(sample[1])[-1] + ref.intersect(sample[2])[-1]
+        cores, model = host_info()
+        cpu_baseline = {"value": n_sample / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
+                        "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays), traversal time only"}
+    if rank == 0:
+        line = {
+            "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3: {n_prims}-triangle displaced grid, {args.res}x{args.res} primary closest-hit + shadow any-hit + "
+                                   "incoherent bounce closest-hit, SAH BVH max_prims_in_node=4",
+                       "rays_per_step_per_gpu": rays_per_step, "bvh_nodes": n_nodes, "bvh_depth": depth,
+                       "l2": "BVH+triangles (~1 GB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",
+                       "scene_gen_s": t_gen, "bvh_build_upload_s": t_build},
+            "kernel_ms": kernel_ms,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
+                    "api": "pb2_intersect / pb2_intersect_p with pinned host buffers"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

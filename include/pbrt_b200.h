@@ -1,0 +1,200 @@
+/* pbrt_b200.h — C ABI of the B200-native ray-tracing backend for the pbrt-rs hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / POD structs and returns an int status
+ * (0 = PB2_OK, <0 = error; message via pb2_last_error()).  Nothing aborts; there is NO CPU fallback — a missing
+ * GPU or CUDA failure is an error.  Each function names the reference interface (file:line under
+ * /root/reference) it replaces.  The Rust-side binding is shown in INTEGRATION.md and rust_shim/.
+ *
+ * Buffers: "host" pointers are caller-owned host memory (copied in/out synchronously).  "_device" variants take
+ * device pointers plus a CUDA stream (cudaStream_t passed as void*) and are asynchronous on that stream.
+ */
+#ifndef PBRT_B200_H
+#define PBRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_OK 0
+#define PB2_ERR_INVALID -1   /* bad argument */
+#define PB2_ERR_CUDA -2      /* CUDA runtime failure / no device */
+#define PB2_ERR_STATE -3     /* call order (e.g. intersect before build_bvh) */
+#define PB2_ERR_NCCL -4
+#define PB2_ERR_LIMIT -5     /* BVH deeper than the 64-entry traversal stack (bvh.rs:839) */
+
+#define PB2_MISS 0xFFFFFFFFu
+
+/* src/core/geometry.rs:756-763 `Ray {o, d, t_max, time}` — 32 bytes, two float4 loads on the device. */
+typedef struct pb2_ray {
+    float o[3];
+    float t_max;
+    float d[3];
+    float time;
+} pb2_ray;
+
+/* What `Primitive::intersect` leaves behind (src/core/primitive.rs:65-78, src/shapes/triangle.rs:182-316):
+ * prim_id = index into the caller's triangle list (PB2_MISS when nothing was hit), t = the shrunk ray.t_max,
+ * (b1, b2) = barycentrics e1*inv_det, e2*inv_det.  16 bytes. */
+typedef struct pb2_hit {
+    uint32_t prim_id;
+    float t;
+    float b1;
+    float b2;
+} pb2_hit;
+
+/* pbrt-v3 matte / plastic / glass (the reference's src/materials/{matte,plastic,glass}.rs are empty files;
+ * SURVEY.md Appendix B).  */
+enum { PB2_MAT_MATTE = 0, PB2_MAT_PLASTIC = 1, PB2_MAT_GLASS = 2 };
+typedef struct pb2_material {
+    int32_t type;
+    float kd[3];        /* matte, plastic: diffuse reflectance */
+    float ks[3];        /* plastic: glossy reflectance */
+    float roughness;    /* plastic */
+    int32_t remap_roughness;
+    float kr[3];        /* glass */
+    float kt[3];        /* glass */
+    float eta;          /* glass index of refraction */
+} pb2_material;
+
+/* src/lights/point.rs PointLight; src/lights/diffuse.rs DiffuseAreaLight (one per emissive triangle). */
+enum { PB2_LIGHT_POINT = 0, PB2_LIGHT_AREA = 1 };
+typedef struct pb2_light {
+    int32_t type;
+    float p[3];         /* point: position */
+    float i[3];         /* point: intensity I; area: emitted radiance L_emit */
+    uint32_t prim_id;   /* area: the emissive triangle */
+    int32_t two_sided;  /* area */
+} pb2_light;
+
+/* src/cameras/perspective.rs:34-82 PerspectiveCamera (pinhole: lens_radius = 0) + Transform::look_at. */
+typedef struct pb2_camera {
+    float pos[3];
+    float look[3];
+    float up[3];
+    float fov;          /* degrees, applies to the shorter image axis */
+    int32_t res_x, res_y;
+} pb2_camera;
+
+enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1 };
+/* src/core/film.rs:31-75 Film::new + src/filters/{boxf,gaussian}.rs */
+typedef struct pb2_film_desc {
+    int32_t res_x, res_y;
+    int32_t filter;     /* PB2_FILTER_* */
+    float radius_x, radius_y;
+    float gaussian_alpha;
+} pb2_film_desc;
+
+enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1 };
+/* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
+typedef struct pb2_path_desc {
+    int32_t max_depth;
+    float rr_threshold;
+    int32_t light_strategy;     /* PB2_LIGHTS_* (src/core/lightdistrib.rs:222-232) */
+    int32_t spp;                /* samples per pixel of the whole frame */
+    int32_t sample_begin;       /* this call renders sample indices [sample_begin, sample_end) of every pixel */
+    int32_t sample_end;
+} pb2_path_desc;
+
+typedef struct pb2_scene pb2_scene;
+typedef struct pb2_film pb2_film;
+
+/* ---- runtime ------------------------------------------------------------------------------------------ */
+int pb2_init(int device);                 /* cudaSetDevice + capability check (sm_100 required) */
+int pb2_shutdown(void);
+const char* pb2_last_error(void);         /* thread-local message of the last failing call */
+int pb2_device_count(int* out);
+/* Pinned host memory for the host-buffer entry points (lets their H2D / D2H copies overlap the kernels), raw
+ * device memory + blocking copies for callers of the *_device entry points that have no CUDA binding of their own. */
+int pb2_host_alloc(uint64_t bytes, void** out);
+int pb2_host_free(void* p);
+int pb2_device_alloc(uint64_t bytes, void** out);
+int pb2_device_free(void* p);
+int pb2_memcpy_h2d(void* dst_device, const void* src_host, uint64_t bytes);
+int pb2_memcpy_d2h(void* dst_host, const void* src_device, uint64_t bytes);
+int pb2_device_synchronize(void);
+
+/* ---- scene + BVHAccel (src/accelerators/bvh.rs:216-271 BVHAccel::new) ---------------------------------- */
+/* Copies the mesh.  tri_material (index into mats) / tri_light (index into lights or -1) may be NULL for pure
+ * ray casting.  Replaces the Vec<PrimitiveDt> of GeometricPrimitive(Triangle) handed to BVHAccel::new. */
+int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
+                     const uint32_t* tri_material, const pb2_material* mats, uint32_t n_mats,
+                     const pb2_light* lights, uint32_t n_lights, pb2_scene** out);
+int pb2_scene_destroy(pb2_scene* scene);
+/* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
+ * node layout + 48-byte triangles, upload to the current device.  split_method: 0 = SAH (only one built). */
+int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_method);
+/* Host half only (no device needed): the flattened array can then be inspected with pb2_bvh_info / pb2_bvh_export. */
+int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_method);
+/* bvh.rs:819-826 BVHAccel::world_bound -> {min.xyz, max.xyz} */
+int pb2_world_bound(const pb2_scene* scene, float out[6]);
+/* Parity hooks: the flattened LinearBVHNode array (bvh.rs:129-135 as 32-byte nodes {bounds[6], offset u32,
+ * n_prims u16, axis u8, pad}) and the ordered primitive list. */
+int pb2_bvh_info(const pb2_scene* scene, uint64_t* n_nodes, uint64_t* n_prims, int* max_depth);
+int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prims);
+
+/* ---- Primitive::intersect / intersect_p, batched (bvh.rs:828-879, :881-932) ---------------------------- */
+/* Closest hit for n rays.  hits[i].t is the value Primitive::intersect would leave in ray.t_max.  b0 may be NULL. */
+int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0);
+/* Any hit: out[i] = 1 if Primitive::intersect_p would return true. */
+int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out);
+/* Device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`). */
+int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream);
+int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream);
+
+/* ---- Camera::generate_ray (src/cameras/perspective.rs:90-112), batched -------------------------------- */
+/* One ray per film point p_film[i] = {x, y} in raster space. */
+int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, uint64_t n, pb2_ray* rays);
+/* One ray through every pixel centre (x+0.5, y+0.5), row-major; device output. */
+int pb2_camera_primary_rays_device(const pb2_camera* cam, void* d_rays, void* stream);
+/* Host-side matrices for parity checks: raster_to_camera, camera_to_world (row-major 4x4 each). */
+int pb2_camera_matrices(const pb2_camera* cam, float r2c[16], float c2w[16]);
+
+/* ---- secondary-ray builders used by the C3 workload (src/core/interaction.rs:132-153) ------------------ */
+/* From each closest hit: Interaction::spawn_ray_to(point) shadow rays (t_max = 1 - SHADOW_EPSILON); misses get
+ * a degenerate ray with t_max = -1 that hits nothing. */
+int pb2_spawn_shadow_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n,
+                                 const float light_pos[3], void* d_out_rays, void* stream);
+/* From each closest hit: Interaction::spawn_ray(wi), wi = cosine_sample_hemisphere about the geometric normal
+ * (src/core/sampling.rs:289-294) drawn from PCG32 stream `i` (src/core/rng.rs). */
+int pb2_spawn_bounce_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n,
+                                 void* d_out_rays, void* stream);
+
+/* ---- RNG (src/core/rng.rs:14-48) — parity hook --------------------------------------------------------- */
+/* out[s*n_per + k] = k-th uniform_float() of RNG::new(first_sequence + s). */
+int pb2_rng_uniform_floats(uint64_t first_sequence, uint32_t n_sequences, uint32_t n_per, float* out);
+
+/* ---- Film (src/core/film.rs) ---------------------------------------------------------------------------- */
+int pb2_film_create(const pb2_film_desc* desc, pb2_film** out);     /* Film::new :31-75 */
+int pb2_film_destroy(pb2_film* film);
+int pb2_film_clear(pb2_film* film);
+/* FilmTile::add_sample (:252-295) + Film::merge_film_tile (:111-123), batched: n samples, host arrays. */
+int pb2_film_add_samples(pb2_film* film, const float* p_film, const float* L_rgb, const float* weight, uint64_t n);
+/* Raw accumulators: float4 {X, Y, Z, filter_weight_sum} per pixel, row-major. */
+int pb2_film_read_xyzw(pb2_film* film, float* out);
+/* Film::write_image (:153-178): XYZ -> RGB, / weight, clamp >= 0, * scale. */
+int pb2_film_resolve_rgb(pb2_film* film, float scale, float* rgb);
+int pb2_film_device_ptr(pb2_film* film, void** d_xyzw, uint64_t* n_floats);
+
+/* ---- Integrator::render / PathIntegrator::li (src/core/integrator.rs:399-480, src/integrators/path.rs) -- */
+/* Wavefront path tracer: renders sample indices [sample_begin, sample_end) of every pixel into `film`
+ * (accumulating).  Sampler stream of (pixel x,y; sample s) = RNG::new((y*res_x + x)*spp + s). */
+int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, pb2_film* film, void* stream);
+/* Per-sample radiance of PathIntegrator::li for explicit (pixel, sample) pairs — parity hook.  host arrays. */
+int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, const uint32_t* pixel_xy,
+                const uint32_t* sample_index, uint64_t n, float* L_rgb, float* p_film);
+/* Counters of the last pb2_render_path call: {camera_samples, extend_rays, shadow_rays, mis_rays, kernel_launches}. */
+int pb2_render_counters(pb2_scene* scene, uint64_t out[8]);
+
+/* ---- multi-GPU film reduce (one process per GPU; NCCL over NVLink) -------------------------------------- */
+int pb2_nccl_unique_id(char id[128]);
+int pb2_nccl_init(const char id[128], int rank, int n_ranks);
+int pb2_nccl_shutdown(void);
+/* ncclReduce(sum, float32, 4*W*H, root) of the film accumulators. */
+int pb2_film_reduce(pb2_film* film, int root, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRT_B200_H */

@@ -217,3 +217,20 @@ def camera_rays(pos, look, up, fov, res, pfilm):
     rays = np.empty((len(pfilm), 8), dtype=np.float32)
     lib().orc_camera_rays(_p(_cam9(pos, look, up)), fov, res[0], res[1], _p(pfilm), len(pfilm), _p(rays))
     return rays
+
+
+def spawn_shadow_rays(bvh, hits, b0, light_pos):
+    L = lib()
+    L.orc_spawn_shadow_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    out = np.empty((len(hits), 8), dtype=np.float32)
+    lp = np.asarray(light_pos, dtype=np.float32)
+    L.orc_spawn_shadow_rays(bvh.h, _p(np.ascontiguousarray(hits)), _p(_f32(b0)), len(hits), _p(lp), _p(out))
+    return out
+
+
+def spawn_bounce_rays(bvh, rays, hits, b0):
+    L = lib()
+    L.orc_spawn_bounce_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    out = np.empty((len(hits), 8), dtype=np.float32)
+    L.orc_spawn_bounce_rays(bvh.h, _p(_f32(rays)), _p(np.ascontiguousarray(hits)), _p(_f32(b0)), len(hits), _p(out))
+    return out

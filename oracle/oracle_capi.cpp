@@ -160,6 +160,51 @@ void orc_brute_force(void* h, const float* rays8, uint64_t n, void* hits16, int 
     for (auto& t : pool) t.join();
 }
 
+// ---- secondary rays of the C3 workload -------------------------------------------------------------
+static bool hit_interaction(const BVHAccel* bvh, const Hit& h, Float b0, Interaction* it) {
+    if (h.prim_id == 0xFFFFFFFFu) return false;
+    V3 p0, p1, p2;
+    bvh->tri(h.prim_id, &p0, &p1, &p2);
+    *it = triangle_interaction(p0, p1, p2, b0, h.b1, h.b2);
+    return true;
+}
+static void dead_ray(float* out8) {
+    const float r[8] = {0, 0, 0, -1.0f, 0, 0, 1.0f, 0};
+    std::memcpy(out8, r, 32);
+}
+// interaction.rs:138-144 spawn_ray_to(light position) from every closest hit; misses -> t_max = -1
+void orc_spawn_shadow_rays(void* h, const void* hits16, const float* b0, uint64_t n, const float* light3, float* out8) {
+    const BVHAccel* bvh = (const BVHAccel*)h;
+    for (uint64_t i = 0; i < n; ++i) {
+        Interaction it;
+        if (!hit_interaction(bvh, ((const Hit*)hits16)[i], b0[i], &it)) { dead_ray(out8 + 8 * i); continue; }
+        Ray r = spawn_ray_to(it, V3{light3[0], light3[1], light3[2]});
+        std::memcpy(out8 + 8 * i, &r, 32);
+    }
+}
+// interaction.rs:132-135 spawn_ray(wi), wi cosine-distributed about the geometric normal facing the incoming side,
+// (u0,u1) = first two floats of RNG::new(i)
+void orc_spawn_bounce_rays(void* h, const float* rays8, const void* hits16, const float* b0, uint64_t n, float* out8) {
+    const BVHAccel* bvh = (const BVHAccel*)h;
+    for (uint64_t i = 0; i < n; ++i) {
+        Interaction it;
+        if (!hit_interaction(bvh, ((const Hit*)hits16)[i], b0[i], &it)) { dead_ray(out8 + 8 * i); continue; }
+        V3 d_in{rays8[8 * i + 4], rays8[8 * i + 5], rays8[8 * i + 6]};
+        V3 n_face = it.n;
+        if (dot(n_face, d_in) > 0.0f) n_face = -n_face;
+        RNG rng;
+        rng.set_sequence(i);
+        Float u0 = rng.uniform_float();
+        Float u1 = rng.uniform_float();
+        V3 l = cosine_sample_hemisphere(u0, u1);
+        V3 s, t;
+        coordinate_system(n_face, &s, &t);
+        V3 wi = (s * l.x + t * l.y) + n_face * l.z;
+        Ray r = spawn_ray(it, wi);
+        std::memcpy(out8 + 8 * i, &r, 32);
+    }
+}
+
 // ---- camera ----------------------------------------------------------------------------------
 // cam9 = {pos, look, up}; out: raster_to_camera (16), camera_to_world (16)
 void orc_camera_matrices(const float* cam9, float fov, int rx, int ry, float* r2c16, float* c2w16) {

@@ -539,6 +539,80 @@ struct RNG {
     }
 };
 
+// ---------------------------------------------------------------- sin / cos
+// The reference calls f32::sin / f32::cos (platform libm; last-bit results are platform dependent).  The numerics
+// contract of this project fixes one definition shared by oracle and kernels: Cody-Waite reduction by
+// pi/2 in three f32 steps + Cephes sinf/cosf minimax polynomials, every op separately rounded (<= 2 ulp).
+inline void sincos_contract(Float x, Float* s_out, Float* c_out) {
+    const Float q = std::rint(x * 0.636619772367581343f);
+    const int k = (int)q;
+    Float r = x - q * 1.5703125f;
+    r = r - q * 4.837512969970703125e-4f;
+    r = r - q * 7.549789948768648e-8f;
+    const Float z = r * r;
+    const Float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    const Float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    switch (k & 3) {
+        case 0: *s_out = sp; *c_out = cp; break;
+        case 1: *s_out = cp; *c_out = -sp; break;
+        case 2: *s_out = -sp; *c_out = -cp; break;
+        default: *s_out = -cp; *c_out = sp; break;
+    }
+}
+inline Float sin_c(Float x) { Float s, c; sincos_contract(x, &s, &c); return s; }
+inline Float cos_c(Float x) { Float s, c; sincos_contract(x, &s, &c); return c; }
+
+// ---------------------------------------------------------------- geometry.rs:1139-1154, interaction.rs:132-153
+inline V3 offset_ray_origin(V3 p, V3 p_error, V3 n, V3 w) {
+    Float d = dot(vabs(n), p_error);
+    V3 offset = n * d;
+    if (dot(w, n) < 0.0f) offset = -offset;
+    V3 po = p + offset;
+    for (int i = 0; i < 3; ++i) {
+        if (offset[i] > 0.0f) po[i] = next_float_up(po[i]);
+        else if (offset[i] < 0.0f) po[i] = next_float_down(po[i]);
+    }
+    return po;
+}
+struct Interaction {          // interaction.rs:100-123 BaseInteraction subset
+    V3 p, error, n;
+};
+inline Ray spawn_ray(const Interaction& it, V3 d) {                       // :132-135
+    return Ray{offset_ray_origin(it.p, it.error, it.n, d), kInfinity, d, 0.0f};
+}
+inline Ray spawn_ray_to(const Interaction& it, V3 p2) {                   // :138-144
+    V3 d = p2 - it.p;
+    return Ray{offset_ray_origin(it.p, it.error, it.n, d), 1.0f - kShadowEpsilon, d, 0.0f};
+}
+// triangle.rs:217-250: p_hit, p_error, geometric normal of an accepted hit
+inline Interaction triangle_interaction(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2) {
+    Interaction it;
+    Float xs = (std::fabs(b0 * p0.x) + std::fabs(b1 * p1.x)) + std::fabs(b2 * p2.x);
+    Float ys = (std::fabs(b0 * p0.y) + std::fabs(b1 * p1.y)) + std::fabs(b2 * p2.y);
+    Float zs = (std::fabs(b0 * p0.z) + std::fabs(b1 * p1.z)) + std::fabs(b2 * p2.z);
+    it.error = V3{xs, ys, zs} * gamma(7.0f);
+    it.p = (p0 * b0 + p1 * b1) + p2 * b2;
+    it.n = normalize(cross(p0 - p2, p1 - p2));
+    return it;
+}
+
+// ---------------------------------------------------------------- sampling.rs:258-273, :289-294
+inline void concentric_sample_disk(Float u0, Float u1, Float* x, Float* y) {
+    Float ox = u0 * 2.0f - 1.0f, oy = u1 * 2.0f - 1.0f;
+    if (ox == 0.0f && oy == 0.0f) { *x = 0; *y = 0; return; }
+    Float r, theta;
+    if (std::fabs(ox) > std::fabs(oy)) { r = ox; theta = (kPi / 4.0f) * (oy / ox); }
+    else { r = oy; theta = (kPi / 2.0f) - (kPi / 4.0f) * (ox / oy); }
+    *x = cos_c(theta) * r;
+    *y = sin_c(theta) * r;
+}
+inline V3 cosine_sample_hemisphere(Float u0, Float u1) {                  // D30 FIX: sqrt
+    Float x, y;
+    concentric_sample_disk(u0, u1, &x, &y);
+    Float z = std::sqrt(fmax_(0.0f, (1.0f - x * x) - y * y));
+    return {x, y, z};
+}
+
 // ---------------------------------------------------------------- transform.rs + cameras/perspective.rs
 struct M4 { Float m[4][4]; };
 inline M4 m4_identity() { M4 r{}; for (int i = 0; i < 4; ++i) r.m[i][i] = 1.0f; return r; }

@@ -1,0 +1,324 @@
+"""pbrt_rs_b200 — thin ctypes binding over libpbrt_b200.so (include/pbrt_b200.h).
+
+This is the Python-side stand-in for the Rust shim (rust_shim/): it mirrors the reference's trait surface
+(`BVHAccel::{world_bound, intersect, intersect_p}`, `PerspectiveCamera::generate_ray`, `PathIntegrator::render`,
+`Film::add_sample`) one to one over the C ABI so tests and bench.py exercise exactly what the FFI would bind.
+There is no CPU fallback: a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbrt_b200.so")
+_LIB = None
+
+PB2_MISS = 0xFFFFFFFF
+HIT_DTYPE = np.dtype([("prim_id", np.uint32), ("t", np.float32), ("b1", np.float32), ("b2", np.float32)])
+NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_prims", np.uint16), ("axis", np.uint8),
+                       ("pad", np.uint8)])
+
+MAT_MATTE, MAT_PLASTIC, MAT_GLASS = 0, 1, 2
+LIGHT_POINT, LIGHT_AREA = 0, 1
+FILTER_BOX, FILTER_GAUSSIAN = 0, 1
+LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
+
+
+class Pb2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pb2 error {code}: {msg}")
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("roughness", C.c_float),
+                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("p", C.c_float * 3), ("i", C.c_float * 3), ("prim_id", C.c_uint32),
+                ("two_sided", C.c_int32)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
+                ("res_x", C.c_int32), ("res_y", C.c_int32)]
+
+
+class FilmDesc(C.Structure):
+    _fields_ = [("res_x", C.c_int32), ("res_y", C.c_int32), ("filter", C.c_int32), ("radius_x", C.c_float),
+                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float)]
+
+
+class PathDesc(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32)]
+
+
+def matte(kd):
+    m = Material()
+    m.type = MAT_MATTE
+    m.kd[:] = kd
+    return m
+
+
+def plastic(kd, ks, roughness=0.1, remap=True):
+    m = Material()
+    m.type = MAT_PLASTIC
+    m.kd[:] = kd
+    m.ks[:] = ks
+    m.roughness = roughness
+    m.remap_roughness = int(remap)
+    return m
+
+
+def glass(kr=(1, 1, 1), kt=(1, 1, 1), eta=1.5):
+    m = Material()
+    m.type = MAT_GLASS
+    m.kr[:] = kr
+    m.kt[:] = kt
+    m.eta = eta
+    return m
+
+
+def point_light(p, intensity):
+    l = Light()
+    l.type = LIGHT_POINT
+    l.p[:] = p
+    l.i[:] = intensity
+    return l
+
+
+def area_light(prim_id, radiance, two_sided=False):
+    l = Light()
+    l.type = LIGHT_AREA
+    l.i[:] = radiance
+    l.prim_id = prim_id
+    l.two_sided = int(two_sided)
+    return l
+
+
+def header_symbols():
+    """Every pb2_* function include/pbrt_b200.h declares."""
+    import re
+    text = open(os.path.join(_HERE, "..", "include", "pbrt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Load libpbrt_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise Pb2Error(-2, f"{LIB_PATH} is missing: run `make -C pbrt-rs_b200` (or __graft_entry__.build()); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, u64, i32, u32, f32 = C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_float
+    L.pb2_last_error.restype = C.c_char_p
+    sig = {
+        "pb2_init": [i32], "pb2_shutdown": [], "pb2_device_count": [vp],
+        "pb2_host_alloc": [u64, vp], "pb2_host_free": [vp], "pb2_device_alloc": [u64, vp], "pb2_device_free": [vp],
+        "pb2_memcpy_h2d": [vp, vp, u64], "pb2_memcpy_d2h": [vp, vp, u64], "pb2_device_synchronize": [],
+        "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
+        "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
+        "pb2_bvh_export": [vp, vp, vp],
+        "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
+        "pb2_intersect_device": [vp, vp, u64, vp, vp, vp], "pb2_intersect_p_device": [vp, vp, u64, vp, vp],
+        "pb2_camera_generate_rays": [vp, vp, u64, vp], "pb2_camera_primary_rays_device": [vp, vp, vp],
+        "pb2_camera_matrices": [vp, vp, vp],
+        "pb2_spawn_shadow_rays_device": [vp, vp, vp, u64, vp, vp, vp],
+        "pb2_spawn_bounce_rays_device": [vp, vp, vp, u64, vp, vp],
+        "pb2_rng_uniform_floats": [u64, u32, u32, vp],
+        "pb2_film_create": [vp, vp], "pb2_film_destroy": [vp], "pb2_film_clear": [vp],
+        "pb2_film_add_samples": [vp, vp, vp, vp, u64], "pb2_film_read_xyzw": [vp, vp],
+        "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_device_ptr": [vp, vp, vp],
+        "pb2_render_path": [vp, vp, vp, vp, vp], "pb2_path_li": [vp, vp, vp, vp, vp, u64, vp, vp],
+        "pb2_render_counters": [vp, vp],
+        "pb2_nccl_unique_id": [vp], "pb2_nccl_init": [vp, i32, i32], "pb2_nccl_shutdown": [],
+        "pb2_film_reduce": [vp, i32, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise Pb2Error(rc, lib().pb2_last_error().decode())
+
+
+def init(device=0):
+    check(lib().pb2_init(device))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def camera_desc(pos, look, up, fov, res):
+    c = CameraDesc()
+    c.pos[:] = pos
+    c.look[:] = look
+    c.up[:] = up
+    c.fov = fov
+    c.res_x, c.res_y = res
+    return c
+
+
+class DeviceBuffer:
+    """Raw device allocation (pb2_device_alloc) for the device-resident entry points."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        self.nbytes = int(nbytes)
+        check(lib().pb2_device_alloc(self.nbytes, C.byref(self.ptr)))
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(lib().pb2_memcpy_h2d(self.ptr, _p(arr), arr.nbytes))
+        return self
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib().pb2_memcpy_d2h(_p(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().pb2_device_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Triangle list + materials + lights handed to BVHAccel::new (pb2_scene_create)."""
+
+    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None):
+        verts = _f32(verts).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
+        self.n_tris = len(idx)
+        tm = None if tri_material is None else np.ascontiguousarray(tri_material, dtype=np.uint32)
+        mats = (Material * len(materials))(*materials) if materials else None
+        lts = (Light * len(lights))(*lights) if lights else None
+        self.h = C.c_void_p()
+        check(lib().pb2_scene_create(_p(verts), len(verts), _p(idx), len(idx), _p(tm),
+                                     C.cast(mats, C.c_void_p) if mats else None, len(materials) if materials else 0,
+                                     C.cast(lts, C.c_void_p) if lts else None, len(lights) if lights else 0,
+                                     C.byref(self.h)))
+
+    def destroy(self):
+        if self.h:
+            lib().pb2_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class BVHAccel:
+    """Mirror of src/accelerators/bvh.rs BVHAccel behind the Primitive trait (world_bound / intersect / intersect_p)."""
+
+    SAH = 0
+
+    def __init__(self, scene_or_verts, idx=None, max_prims_in_node=4, split_method=0, host_only=False):
+        self.scene = scene_or_verts if isinstance(scene_or_verts, Scene) else Scene(scene_or_verts, idx)
+        build = lib().pb2_scene_build_bvh_host if host_only else lib().pb2_scene_build_bvh
+        check(build(self.scene.h, max_prims_in_node, split_method))
+
+    @property
+    def h(self):
+        return self.scene.h
+
+    def world_bound(self):
+        out = np.empty(6, dtype=np.float32)
+        check(lib().pb2_world_bound(self.h, _p(out)))
+        return out
+
+    def info(self):
+        n_nodes, n_prims, depth = C.c_uint64(), C.c_uint64(), C.c_int()
+        check(lib().pb2_bvh_info(self.h, C.byref(n_nodes), C.byref(n_prims), C.byref(depth)))
+        return n_nodes.value, n_prims.value, depth.value
+
+    def export(self):
+        n_nodes, n_prims, _ = self.info()
+        nodes = np.empty(n_nodes, dtype=NODE_DTYPE)
+        prims = np.empty(n_prims, dtype=np.uint32)
+        check(lib().pb2_bvh_export(self.h, _p(nodes), _p(prims)))
+        return nodes, prims
+
+    def intersect(self, rays, want_b0=False):
+        """Closest hit per ray -> structured array (prim_id, t, b1, b2) [+ b0]."""
+        rays = _f32(rays).reshape(-1, 8)
+        hits = np.empty(len(rays), dtype=HIT_DTYPE)
+        b0 = np.empty(len(rays), dtype=np.float32) if want_b0 else None
+        check(lib().pb2_intersect(self.h, _p(rays), len(rays), _p(hits), _p(b0)))
+        return (hits, b0) if want_b0 else hits
+
+    def intersect_p(self, rays):
+        rays = _f32(rays).reshape(-1, 8)
+        out = np.empty(len(rays), dtype=np.uint8)
+        check(lib().pb2_intersect_p(self.h, _p(rays), len(rays), _p(out)))
+        return out
+
+    # device-resident variants (pointers are ints / c_void_p; stream is a cudaStream_t value)
+    def intersect_device(self, d_rays, n, d_hits, d_b0=None, stream=None):
+        check(lib().pb2_intersect_device(self.h, d_rays, n, d_hits, d_b0, stream))
+
+    def intersect_p_device(self, d_rays, n, d_out, stream=None):
+        check(lib().pb2_intersect_p_device(self.h, d_rays, n, d_out, stream))
+
+    def spawn_shadow_rays_device(self, d_rays, d_hits, n, light_pos, d_out, stream=None):
+        lp = np.asarray(light_pos, dtype=np.float32)
+        check(lib().pb2_spawn_shadow_rays_device(self.h, d_rays, d_hits, n, _p(lp), d_out, stream))
+
+    def spawn_bounce_rays_device(self, d_rays, d_hits, n, d_out, stream=None):
+        check(lib().pb2_spawn_bounce_rays_device(self.h, d_rays, d_hits, n, d_out, stream))
+
+
+class PerspectiveCamera:
+    """Mirror of src/cameras/perspective.rs (pinhole)."""
+
+    def __init__(self, pos, look, up, fov, res):
+        self.desc = camera_desc(pos, look, up, fov, res)
+        self.res = tuple(res)
+
+    def matrices(self):
+        r2c = np.empty((4, 4), dtype=np.float32)
+        c2w = np.empty((4, 4), dtype=np.float32)
+        check(lib().pb2_camera_matrices(C.byref(self.desc), _p(r2c), _p(c2w)))
+        return r2c, c2w
+
+    def generate_rays(self, p_film):
+        p_film = _f32(p_film).reshape(-1, 2)
+        rays = np.empty((len(p_film), 8), dtype=np.float32)
+        check(lib().pb2_camera_generate_rays(C.byref(self.desc), _p(p_film), len(p_film), _p(rays)))
+        return rays
+
+    def primary_rays_device(self, d_rays, stream=None):
+        check(lib().pb2_camera_primary_rays_device(C.byref(self.desc), d_rays, stream))
+
+
+def rng_uniform_floats(first_sequence, n_sequences, n_per):
+    out = np.empty((n_sequences, n_per), dtype=np.float32)
+    check(lib().pb2_rng_uniform_floats(first_sequence, n_sequences, n_per, _p(out)))
+    return out

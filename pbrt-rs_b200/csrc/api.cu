@@ -1,0 +1,410 @@
+// api.cu — the C ABI of include/pbrt_b200.h: scene handles, BVH upload, batched intersect / intersect_p,
+// camera rays, RNG parity hook.  (Film / path tracer / NCCL entry points live in api_path.cu.)
+#include "api_internal.hpp"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+
+namespace pb2 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    return set_error(PB2_ERR_CUDA, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+}
+
+void camera_setup(const float pos[3], const float look[3], const float up[3], float fov, int res_x, int res_y, CameraView* out);
+
+int make_camera_view(const pb2_camera* cam, CameraView* out) {
+    if (!cam || cam->res_x <= 0 || cam->res_y <= 0 || !(cam->fov > 0.0f && cam->fov < 180.0f))
+        return set_error(PB2_ERR_INVALID, "invalid camera description");
+    camera_setup(cam->pos, cam->look, cam->up, cam->fov, cam->res_x, cam->res_y, out);
+    return PB2_OK;
+}
+
+}  // namespace pb2
+
+using namespace pb2;
+
+void pb2_scene::free_device() {
+    if (d_pairs) cudaFree(d_pairs);
+    if (d_tris) cudaFree(d_tris);
+    if (d_slot_of_prim) cudaFree(d_slot_of_prim);
+    if (d_tri_material) cudaFree(d_tri_material);
+    if (d_tri_light) cudaFree(d_tri_light);
+    if (d_materials) cudaFree(d_materials);
+    if (d_lights) cudaFree(d_lights);
+    if (d_light_cdf) cudaFree(d_light_cdf);
+    d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i].d_in) cudaFree(stage[i].d_in);
+        if (stage[i].d_out) cudaFree(stage[i].d_out);
+        if (stage[i].d_aux) cudaFree(stage[i].d_aux);
+        if (stage[i].stream) cudaStreamDestroy(stage[i].stream);
+        stage[i] = Stage();
+    }
+    if (wf) { wavefront_destroy(wf); wf = nullptr; }
+}
+
+extern "C" {
+
+const char* pb2_last_error(void) { return g_err; }
+
+int pb2_device_count(int* out) {
+    if (!out) return set_error(PB2_ERR_INVALID, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    *out = n;
+    return PB2_OK;
+}
+
+int pb2_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(PB2_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_error(PB2_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    PB2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PB2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_error(PB2_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    PB2_CUDA(cudaFree(0));
+    return PB2_OK;
+}
+
+int pb2_shutdown(void) {
+    pb2_nccl_shutdown();
+    return PB2_OK;
+}
+
+int pb2_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return set_error(PB2_ERR_INVALID, "null out");
+    PB2_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return PB2_OK;
+}
+int pb2_host_free(void* p) {
+    if (p) PB2_CUDA(cudaFreeHost(p));
+    return PB2_OK;
+}
+int pb2_device_alloc(uint64_t bytes, void** out) {
+    if (!out) return set_error(PB2_ERR_INVALID, "null out");
+    PB2_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return PB2_OK;
+}
+int pb2_device_free(void* p) {
+    if (p) PB2_CUDA(cudaFree(p));
+    return PB2_OK;
+}
+int pb2_memcpy_h2d(void* dst, const void* src, uint64_t bytes) {
+    PB2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return PB2_OK;
+}
+int pb2_memcpy_d2h(void* dst, const void* src, uint64_t bytes) {
+    PB2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return PB2_OK;
+}
+int pb2_device_synchronize(void) {
+    PB2_CUDA(cudaDeviceSynchronize());
+    return PB2_OK;
+}
+
+int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
+                     const uint32_t* tri_material, const pb2_material* mats, uint32_t n_mats,
+                     const pb2_light* lights, uint32_t n_lights, pb2_scene** out) {
+    if (!out) return set_error(PB2_ERR_INVALID, "null out");
+    *out = nullptr;
+    if ((n_verts && !verts) || (n_tris && !indices)) return set_error(PB2_ERR_INVALID, "null mesh arrays");
+    if (n_tris >= 0x7FFFFFFFull) return set_error(PB2_ERR_LIMIT, "at most 2^31-1 triangles");
+    for (uint64_t i = 0; i < 3 * n_verts; ++i)
+        if (!std::isfinite(verts[i])) return set_error(PB2_ERR_INVALID, "vertex %llu has a non-finite coordinate", (unsigned long long)(i / 3));
+    for (uint64_t i = 0; i < 3 * n_tris; ++i)
+        if (indices[i] >= n_verts) return set_error(PB2_ERR_INVALID, "triangle %llu references vertex %u >= %llu", (unsigned long long)(i / 3), indices[i], (unsigned long long)n_verts);
+    if (tri_material) {
+        if (!mats || n_mats == 0) return set_error(PB2_ERR_INVALID, "tri_material given without materials");
+        for (uint64_t i = 0; i < n_tris; ++i)
+            if (tri_material[i] >= n_mats) return set_error(PB2_ERR_INVALID, "triangle %llu references material %u >= %u", (unsigned long long)i, tri_material[i], n_mats);
+    }
+    for (uint32_t i = 0; i < n_lights; ++i) {
+        if (lights[i].type == PB2_LIGHT_AREA && lights[i].prim_id >= n_tris)
+            return set_error(PB2_ERR_INVALID, "area light %u references triangle %u >= %llu", i, lights[i].prim_id, (unsigned long long)n_tris);
+        if (lights[i].type != PB2_LIGHT_AREA && lights[i].type != PB2_LIGHT_POINT) return set_error(PB2_ERR_INVALID, "light %u has unknown type %d", i, lights[i].type);
+    }
+    pb2_scene* s = new pb2_scene();
+    s->verts.assign(verts, verts + 3 * n_verts);
+    s->indices.assign(indices, indices + 3 * n_tris);
+    if (tri_material) s->tri_material.assign(tri_material, tri_material + n_tris);
+    if (mats) s->materials.assign(mats, mats + n_mats);
+    if (lights) s->lights.assign(lights, lights + n_lights);
+    *out = s;
+    return PB2_OK;
+}
+
+int pb2_scene_destroy(pb2_scene* scene) {
+    if (!scene) return PB2_OK;
+    scene->free_device();
+    delete scene;
+    return PB2_OK;
+}
+
+static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_method) {
+    if (split_method != 0) return set_error(PB2_ERR_INVALID, "only SplitMethod::SAH (0) is built");
+    if (max_prims_in_node < 1) return set_error(PB2_ERR_INVALID, "max_prims_in_node must be >= 1");
+    scene->built = false;
+    scene->built_host = false;
+    const uint64_t n_tris = scene->indices.size() / 3;
+    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
+    if (scene->bvh.max_depth > kStackDepth)
+        return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
+    scene->built_host = true;
+    return PB2_OK;
+}
+
+int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_method) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    return build_host_locked(scene, max_prims_in_node, split_method);
+}
+
+int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_method) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    scene->free_device();
+    int rc = build_host_locked(scene, max_prims_in_node, split_method);
+    if (rc != PB2_OK) return rc;
+    const uint64_t n_tris = scene->indices.size() / 3;
+    HostBVH& b = scene->bvh;
+    PB2_CUDA(cudaGetDevice(&scene->device));
+    SceneView v;
+    memset(&v, 0, sizeof v);
+    v.n_tris = (uint32_t)n_tris;
+    if (n_tris) {
+        PB2_CUDA(cudaMalloc(&scene->d_pairs, std::max<size_t>(64, b.pairs.size() * sizeof(PairNode))));
+        PB2_CUDA(cudaMalloc(&scene->d_tris, b.tris.size() * sizeof(PackedTri)));
+        PB2_CUDA(cudaMalloc(&scene->d_slot_of_prim, n_tris * 4));
+        if (!b.pairs.empty()) PB2_CUDA(cudaMemcpy(scene->d_pairs, b.pairs.data(), b.pairs.size() * sizeof(PairNode), cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
+        std::vector<uint32_t> slot(n_tris);
+        for (uint64_t i = 0; i < n_tris; ++i) slot[b.ordered_prims[i]] = (uint32_t)i;
+        PB2_CUDA(cudaMemcpy(scene->d_slot_of_prim, slot.data(), n_tris * 4, cudaMemcpyHostToDevice));
+        v.pairs = (const float4*)scene->d_pairs;
+        v.tris = (const float4*)scene->d_tris;
+        v.slot_of_prim = (const uint32_t*)scene->d_slot_of_prim;
+        v.root_ref = b.root_ref;
+        for (int k = 0; k < 3; ++k) { v.root_lo[k] = b.root_bounds[k]; v.root_hi[k] = b.root_bounds[3 + k]; }
+    }
+    scene->view = v;
+    rc = upload_shading_tables(scene);
+    if (rc != PB2_OK) return rc;
+    // the device copies are authoritative from here on; drop the host-side device-layout mirrors
+    std::vector<PairNode>().swap(b.pairs);
+    std::vector<PackedTri>().swap(b.tris);
+    scene->built = true;
+    return PB2_OK;
+}
+
+int pb2_world_bound(const pb2_scene* scene, float out[6]) {
+    if (!scene || !out) return set_error(PB2_ERR_INVALID, "null argument");
+    if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (scene->bvh.nodes.empty()) {          // Bounds3f::default(): bvh.rs:825
+        out[0] = out[1] = out[2] = 3.402823466e+38f;
+        out[3] = out[4] = out[5] = -3.402823466e+38f;
+        return PB2_OK;
+    }
+    for (int k = 0; k < 3; ++k) { out[k] = scene->bvh.nodes[0].bmin[k]; out[3 + k] = scene->bvh.nodes[0].bmax[k]; }
+    return PB2_OK;
+}
+
+int pb2_bvh_info(const pb2_scene* scene, uint64_t* n_nodes, uint64_t* n_prims, int* max_depth) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (n_nodes) *n_nodes = scene->bvh.nodes.size();
+    if (n_prims) *n_prims = scene->bvh.ordered_prims.size();
+    if (max_depth) *max_depth = scene->bvh.max_depth;
+    return PB2_OK;
+}
+
+int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prims) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (nodes32) memcpy(nodes32, scene->bvh.nodes.data(), scene->bvh.nodes.size() * sizeof(LinearNode));
+    if (ordered_prims) memcpy(ordered_prims, scene->bvh.ordered_prims.data(), scene->bvh.ordered_prims.size() * 4);
+    return PB2_OK;
+}
+
+// ---- batched intersect ------------------------------------------------------------------------------------
+static int ensure_stage(pb2_scene* s, size_t chunk) {
+    for (int i = 0; i < 2; ++i) {
+        Stage& st = s->stage[i];
+        if (!st.stream) PB2_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        if (st.cap < chunk) {
+            if (st.d_in) cudaFree(st.d_in);
+            if (st.d_out) cudaFree(st.d_out);
+            if (st.d_aux) cudaFree(st.d_aux);
+            st.d_in = st.d_out = st.d_aux = nullptr;
+            PB2_CUDA(cudaMalloc(&st.d_in, chunk * 32));
+            PB2_CUDA(cudaMalloc(&st.d_out, chunk * 16));
+            PB2_CUDA(cudaMalloc(&st.d_aux, chunk * 4));
+            st.cap = chunk;
+        }
+    }
+    return PB2_OK;
+}
+
+static int check_ready(const pb2_scene* scene) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    if (!scene->built) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    return PB2_OK;
+}
+
+// Host-buffer entry points stream the batch through two device staging buffers so that the H2D copy of chunk k+1,
+// the traversal of chunk k and the D2H copy of chunk k-1 overlap (pinned caller memory: pb2_host_alloc).
+static const size_t kChunk = 1u << 18;
+
+int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    if (n && (!rays || !hits)) return set_error(PB2_ERR_INVALID, "null ray/hit buffer");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    PB2_CUDA(cudaSetDevice(scene->device));
+    rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
+    if (rc) return rc;
+    int k = 0;
+    for (uint64_t off = 0; off < n; off += kChunk, k ^= 1) {
+        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
+        Stage& st = scene->stage[k];
+        PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
+        launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, st.stream);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaMemcpyAsync(hits + off, st.d_out, m * 16, cudaMemcpyDeviceToHost, st.stream));
+        if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, st.stream));
+    }
+    PB2_CUDA(cudaStreamSynchronize(scene->stage[0].stream));
+    PB2_CUDA(cudaStreamSynchronize(scene->stage[1].stream));
+    return PB2_OK;
+}
+
+int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    if (n && (!rays || !out)) return set_error(PB2_ERR_INVALID, "null ray/output buffer");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    PB2_CUDA(cudaSetDevice(scene->device));
+    rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
+    if (rc) return rc;
+    int k = 0;
+    for (uint64_t off = 0; off < n; off += kChunk, k ^= 1) {
+        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
+        Stage& st = scene->stage[k];
+        PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
+        launch_any_hit(scene->view, st.d_in, m, st.d_out, st.stream);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaMemcpyAsync(out + off, st.d_out, m, cudaMemcpyDeviceToHost, st.stream));
+    }
+    PB2_CUDA(cudaStreamSynchronize(scene->stage[0].stream));
+    PB2_CUDA(cudaStreamSynchronize(scene->stage[1].stream));
+    return PB2_OK;
+}
+
+int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    launch_closest_hit(scene->view, d_rays, n, d_hits, d_b0, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    launch_any_hit(scene->view, d_rays, n, d_out, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+// ---- camera -------------------------------------------------------------------------------------------------
+int pb2_camera_matrices(const pb2_camera* cam, float r2c[16], float c2w[16]) {
+    CameraView v;
+    int rc = make_camera_view(cam, &v);
+    if (rc) return rc;
+    if (r2c) memcpy(r2c, v.raster_to_camera.m, 64);
+    if (c2w) memcpy(c2w, v.camera_to_world.m, 64);
+    return PB2_OK;
+}
+
+int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, uint64_t n, pb2_ray* rays) {
+    CameraView v;
+    int rc = make_camera_view(cam, &v);
+    if (rc) return rc;
+    if (n == 0) return PB2_OK;
+    if (!p_film || !rays) return set_error(PB2_ERR_INVALID, "null buffer");
+    void *d_p = nullptr, *d_r = nullptr;
+    PB2_CUDA(cudaMalloc(&d_p, n * 8));
+    cudaError_t e = cudaMalloc(&d_r, n * 32);
+    if (e != cudaSuccess) { cudaFree(d_p); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    e = cudaMemcpy(d_p, p_film, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch_camera_rays(v, d_p, n, d_r, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(rays, d_r, n * 32, cudaMemcpyDeviceToHost);
+    cudaFree(d_p);
+    cudaFree(d_r);
+    if (e != cudaSuccess) return cuda_fail(e, "camera ray generation", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_camera_primary_rays_device(const pb2_camera* cam, void* d_rays, void* stream) {
+    CameraView v;
+    int rc = make_camera_view(cam, &v);
+    if (rc) return rc;
+    if (!d_rays) return set_error(PB2_ERR_INVALID, "null buffer");
+    launch_camera_rays(v, nullptr, (uint64_t)v.res_x * (uint64_t)v.res_y, d_rays, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+// ---- secondary-ray builders -----------------------------------------------------------------------------------
+int pb2_spawn_shadow_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n,
+                                 const float light_pos[3], void* d_out_rays, void* stream) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    if (!light_pos) return set_error(PB2_ERR_INVALID, "null light position");
+    launch_spawn_shadow(scene->view, d_rays, d_hits, n, light_pos, d_out_rays, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+int pb2_spawn_bounce_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n,
+                                 void* d_out_rays, void* stream) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    launch_spawn_bounce(scene->view, d_rays, d_hits, n, d_out_rays, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+// ---- RNG parity hook ----------------------------------------------------------------------------------------
+int pb2_rng_uniform_floats(uint64_t first_sequence, uint32_t n_sequences, uint32_t n_per, float* out) {
+    const uint64_t total = (uint64_t)n_sequences * n_per;
+    if (total == 0) return PB2_OK;
+    if (!out) return set_error(PB2_ERR_INVALID, "null out");
+    float* d = nullptr;
+    PB2_CUDA(cudaMalloc(&d, total * 4));
+    launch_rng_floats(first_sequence, n_sequences, n_per, d, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, total * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "rng kernel", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// api_internal.hpp — state behind the opaque handles of include/pbrt_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/pbrt_b200.h"
+#include "bvh_build.hpp"
+#include "kernels.hpp"
+#include "traverse.cuh"
+
+namespace pb2 {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int make_camera_view(const pb2_camera* cam, CameraView* out);
+
+#define PB2_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t pb2_e_ = (call);                                                    \
+        if (pb2_e_ != cudaSuccess) return pb2::cuda_fail(pb2_e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+struct Stage {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* d_aux = nullptr;
+    size_t cap = 0;
+};
+
+struct Wavefront;
+void wavefront_destroy(Wavefront* wf);
+
+}  // namespace pb2
+
+struct pb2_scene {
+    std::vector<float> verts;
+    std::vector<uint32_t> indices;
+    std::vector<uint32_t> tri_material;
+    std::vector<pb2_material> materials;
+    std::vector<pb2_light> lights;
+    pb2::HostBVH bvh;
+    bool built_host = false;   // LinearNode array + ordered prims valid
+    bool built = false;        // device copies valid
+    int device = 0;
+    std::mutex mu;
+    // device copies
+    void* d_pairs = nullptr;
+    void* d_tris = nullptr;
+    void* d_slot_of_prim = nullptr;
+    void* d_tri_material = nullptr;
+    void* d_tri_light = nullptr;
+    void* d_materials = nullptr;
+    void* d_lights = nullptr;
+    void* d_light_cdf = nullptr;
+    pb2::SceneView view;
+    pb2::Stage stage[2];
+    pb2::Wavefront* wf = nullptr;
+    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void free_device();
+};
+
+namespace pb2 {
+int upload_shading_tables(pb2_scene* scene);
+}

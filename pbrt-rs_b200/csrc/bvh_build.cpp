@@ -1,0 +1,399 @@
+// bvh_build.cpp — host SAH build; see bvh_build.hpp.  Compiled with -ffp-contract=off.
+//
+// Arithmetic that decides the tree (centroids, bucket index, SAH cost, split choice, partition order) follows
+// src/accelerators/bvh.rs:273-473 with the Appendix-A fixes D12-D17 (pbrt-v3 semantics), so the flattened array
+// equals what the reference algorithm produces for the same primitive list.
+#include "bvh_build.hpp"
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cfloat>
+#include <cstring>
+#include <thread>
+
+namespace pb2 {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        lo[0] = lo[1] = lo[2] = FLT_MAX;            // Bounds3::new(): geometry.rs:439-448
+        hi[0] = hi[1] = hi[2] = -FLT_MAX;
+    }
+    void grow(const float* blo, const float* bhi) {
+        for (int k = 0; k < 3; ++k) {
+            if (blo[k] < lo[k]) lo[k] = blo[k];
+            if (bhi[k] > hi[k]) hi[k] = bhi[k];
+        }
+    }
+    void grow_point(const float* p) { grow(p, p); }
+    void merge(const Box& o) { grow(o.lo, o.hi); }
+    float area() const {                            // geometry.rs:667-670
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return 2.0f * ((dx * dy + dx * dz) + dy * dz);
+    }
+    int widest() const {                            // geometry.rs:482-485 + :91-93
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return (dx > dy && dx > dz) ? 0 : ((dy > dz) ? 1 : 2);
+    }
+};
+
+struct PrimRef {            // BVHPrimitiveInfo, bvh.rs:26-41
+    float lo[3], hi[3];
+    float c[3];
+    uint32_t id;
+    uint32_t bucket;        // scratch: SAH bucket of the current split
+};
+
+constexpr int kBuckets = 12;
+constexpr int kMaxThreads = 64;
+
+struct Split {
+    Box bounds;
+    int dim = 0;
+    size_t mid = 0;
+    bool leaf = false;
+};
+
+class Builder {
+public:
+    Builder(std::vector<PrimRef>& refs, int max_prims, int threads) : refs_(refs), max_prims_(max_prims), threads_(threads) {}
+
+    // Decide what happens to [start, end): leaf, or partition about `mid` along `dim`.
+    Split split_range(size_t start, size_t end, bool parallel) {
+        Split s;
+        const size_t n = end - start;
+        Box cb;
+        range_bounds(start, end, parallel, &s.bounds, &cb);
+        if (n == 1) { s.leaf = true; return s; }
+        s.dim = cb.widest();
+        const int dim = s.dim;
+        if (cb.hi[dim] == cb.lo[dim]) { s.leaf = true; return s; }
+        if (n <= 2) {
+            // bvh.rs:361-371: nth_element about the middle by centroid[dim]
+            if (refs_[start + 1].c[dim] < refs_[start].c[dim]) std::swap(refs_[start], refs_[start + 1]);
+            s.mid = (start + end) / 2;
+            return s;
+        }
+        int count[kBuckets];
+        Box bb[kBuckets];
+        bucket_pass(start, end, parallel, cb, dim, count, bb);
+        float cost[kBuckets - 1];
+        const float total_area = s.bounds.area();
+        for (int i = 0; i < kBuckets - 1; ++i) {
+            Box b0, b1;
+            b0.reset();
+            b1.reset();
+            int c0 = 0, c1 = 0;
+            for (int j = 0; j <= i; ++j) { b0.merge(bb[j]); c0 += count[j]; }
+            for (int j = i + 1; j < kBuckets; ++j) { b1.merge(bb[j]); c1 += count[j]; }
+            cost[i] = 1.0f + ((float)c0 * b0.area() + (float)c1 * b1.area()) / total_area;    // bvh.rs:403
+        }
+        float min_cost = FLT_MAX;
+        int min_bucket = 0;
+        for (int i = 0; i < kBuckets - 1; ++i)
+            if (cost[i] < min_cost) { min_cost = cost[i]; min_bucket = i; }
+        const float leaf_cost = (float)n;
+        if (!((int)n > max_prims_ || min_cost < leaf_cost)) { s.leaf = true; return s; }
+        // Unstable two-pointer partition (Rust partition_in_place == libstdc++ bidirectional std::partition):
+        // first element failing the predicate from the front is swapped with the last one passing it from the back.
+        size_t lo = start, hi = end;
+        const uint32_t mb = (uint32_t)min_bucket;
+        for (;;) {
+            while (lo < hi && refs_[lo].bucket <= mb) ++lo;
+            if (lo == hi) break;
+            do { --hi; } while (lo < hi && refs_[hi].bucket > mb);
+            if (lo == hi) break;
+            std::swap(refs_[lo], refs_[hi]);
+            ++lo;
+        }
+        s.mid = lo;
+        return s;
+    }
+
+    // Sequential subtree build, appending to `out` in depth-first order with indices local to `out`.
+    void build_subtree(size_t start, size_t end, std::vector<LinearNode>& out, int depth, int* max_depth) {
+        Split s = split_range(start, end, false);
+        const uint32_t me = (uint32_t)out.size();
+        out.emplace_back();
+        write_bounds(out[me], s.bounds);
+        if (depth > *max_depth) *max_depth = depth;
+        if (s.leaf) {
+            out[me].offset = (uint32_t)start;      // leaves are emitted in order, so first_prim_offset == start
+            out[me].n_prims = (uint16_t)(end - start);
+            out[me].axis = 0;
+            out[me].pad = 0;
+            return;
+        }
+        out[me].n_prims = 0;
+        out[me].axis = (uint8_t)s.dim;
+        out[me].pad = 0;
+        build_subtree(start, s.mid, out, depth + 1, max_depth);
+        out[me].offset = (uint32_t)out.size();
+        build_subtree(s.mid, end, out, depth + 1, max_depth);
+    }
+
+    struct TopNode {
+        LinearNode node;
+        int child[2] = {-1, -1};
+        int task = -1;
+    };
+    struct Task {
+        size_t start, end;
+        int depth;
+        std::vector<LinearNode> nodes;
+        int max_depth = 0;
+    };
+
+    int build_top(size_t start, size_t end, int depth, size_t grain) {
+        if (end - start <= grain) return make_task(start, end, depth);
+        Split s = split_range(start, end, true);
+        if (s.leaf) {
+            // oversized leaf (coincident centroids): the task re-derives it
+            return make_task(start, end, depth);
+        }
+        int me = (int)top_.size();
+        top_.emplace_back();
+        write_bounds(top_[me].node, s.bounds);
+        top_[me].node.n_prims = 0;
+        top_[me].node.axis = (uint8_t)s.dim;
+        top_[me].node.pad = 0;
+        int c0 = build_top(start, s.mid, depth + 1, grain);
+        int c1 = build_top(s.mid, end, depth + 1, grain);
+        top_[me].child[0] = c0;
+        top_[me].child[1] = c1;
+        return me;
+    }
+
+    void run(HostBVH* out) {
+        const size_t n = refs_.size();
+        const size_t grain = std::max<size_t>(4096, n / (size_t)(threads_ * 8));
+        int root = build_top(0, n, 1, threads_ > 1 ? grain : n);
+        // phase 2: subtrees in parallel
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t t = next.fetch_add(1);
+                if (t >= tasks_.size()) break;
+                Task& tk = tasks_[t];
+                tk.nodes.reserve(2 * (tk.end - tk.start));
+                tk.max_depth = tk.depth;
+                build_subtree(tk.start, tk.end, tk.nodes, tk.depth, &tk.max_depth);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int i = 1; i < threads_; ++i) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        // phase 3: concatenate in depth-first order
+        size_t total = top_.size() - tasks_.size();
+        for (auto& t : tasks_) total += t.nodes.size();
+        out->nodes.clear();
+        out->nodes.reserve(total);
+        out->max_depth = 0;
+        for (auto& t : tasks_) out->max_depth = std::max(out->max_depth, t.max_depth);
+        emit(root, out->nodes);
+        out->ordered_prims.resize(n);
+        for (size_t i = 0; i < n; ++i) out->ordered_prims[i] = refs_[i].id;
+    }
+
+private:
+    std::vector<PrimRef>& refs_;
+    int max_prims_;
+    int threads_;
+    std::vector<TopNode> top_;
+    std::vector<Task> tasks_;
+
+    static void write_bounds(LinearNode& n, const Box& b) {
+        for (int k = 0; k < 3; ++k) { n.bmin[k] = b.lo[k]; n.bmax[k] = b.hi[k]; }
+    }
+
+    int make_task(size_t start, size_t end, int depth) {
+        int me = (int)top_.size();
+        top_.emplace_back();
+        top_[me].task = (int)tasks_.size();
+        tasks_.push_back(Task{start, end, depth, {}, 0});
+        return me;
+    }
+
+    void emit(int t, std::vector<LinearNode>& out) {
+        const TopNode& tn = top_[t];
+        if (tn.task >= 0) {
+            const Task& tk = tasks_[tn.task];
+            const uint32_t base = (uint32_t)out.size();
+            for (const LinearNode& ln : tk.nodes) {
+                LinearNode c = ln;
+                if (c.n_prims == 0) c.offset += base;
+                out.push_back(c);
+            }
+            return;
+        }
+        const uint32_t me = (uint32_t)out.size();
+        out.push_back(tn.node);
+        emit(tn.child[0], out);
+        out[me].offset = (uint32_t)out.size();
+        emit(tn.child[1], out);
+    }
+
+    int slots_for(size_t n, bool parallel) const { return (parallel && n > (1u << 18)) ? threads_ : 1; }
+
+    template <class F>
+    void for_chunks(size_t start, size_t end, int nt, F&& fn) {
+        const size_t n = end - start;
+        if (nt <= 1) { fn(0, start, end); return; }
+        std::vector<std::thread> pool;
+        const size_t per = (n + nt - 1) / nt;
+        for (int i = 0; i < nt; ++i) {
+            size_t s = start + per * i, e = std::min(end, s + per);
+            if (s >= e) break;
+            pool.emplace_back([&fn, i, s, e]() { fn(i, s, e); });
+        }
+        for (auto& t : pool) t.join();
+    }
+
+    // union of primitive bounds (bvh.rs:283-286) and of centroids (bvh.rs:305-308, D12)
+    void range_bounds(size_t start, size_t end, bool parallel, Box* bounds, Box* cbounds) {
+        const int nt = slots_for(end - start, parallel);
+        Box pb[kMaxThreads], pc[kMaxThreads];
+        for (int i = 0; i < nt; ++i) { pb[i].reset(); pc[i].reset(); }
+        for_chunks(start, end, nt, [&](int slot, size_t s, size_t e) {
+            Box b, c;
+            b.reset();
+            c.reset();
+            for (size_t i = s; i < e; ++i) {
+                b.grow(refs_[i].lo, refs_[i].hi);
+                c.grow_point(refs_[i].c);
+            }
+            pb[slot] = b;
+            pc[slot] = c;
+        });
+        *bounds = pb[0];
+        *cbounds = pc[0];
+        for (int i = 1; i < nt; ++i) { bounds->merge(pb[i]); cbounds->merge(pc[i]); }
+    }
+
+    // bvh.rs:373-386 with D14: b = (int)(nBuckets * offset[dim]); offset = (c - min) / (max - min)  (geometry.rs:460-467)
+    void bucket_pass(size_t start, size_t end, bool parallel, const Box& cb, int dim, int* count, Box* bb) {
+        const int nt = slots_for(end - start, parallel);
+        const float lo = cb.lo[dim], extent = cb.hi[dim] - cb.lo[dim];
+        auto pass = [&](size_t s, size_t e, int* cnt, Box* bx) {
+            for (int j = 0; j < kBuckets; ++j) { cnt[j] = 0; bx[j].reset(); }
+            for (size_t i = s; i < e; ++i) {
+                float o = refs_[i].c[dim] - lo;
+                o /= extent;                              // cb.hi > cb.lo on this axis (checked by caller)
+                int b = (int)((float)kBuckets * o);
+                if (b == kBuckets) b = kBuckets - 1;
+                refs_[i].bucket = (uint32_t)b;
+                cnt[b]++;
+                bx[b].grow(refs_[i].lo, refs_[i].hi);
+            }
+        };
+        if (nt <= 1) { pass(start, end, count, bb); return; }
+        std::vector<int> pcnt((size_t)nt * kBuckets);
+        std::vector<Box> pbb((size_t)nt * kBuckets);
+        for (auto& b : pbb) b.reset();
+        for_chunks(start, end, nt, [&](int slot, size_t s, size_t e) { pass(s, e, &pcnt[(size_t)slot * kBuckets], &pbb[(size_t)slot * kBuckets]); });
+        for (int j = 0; j < kBuckets; ++j) {
+            count[j] = 0;
+            bb[j].reset();
+            for (int t = 0; t < nt; ++t) { count[j] += pcnt[(size_t)t * kBuckets + j]; bb[j].merge(pbb[(size_t)t * kBuckets + j]); }
+        }
+    }
+};
+
+}  // namespace
+
+void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
+                   int max_prims_in_node, int threads, HostBVH* out) {
+    (void)n_verts;
+    *out = HostBVH();
+    if (n_tris == 0) return;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > kMaxThreads) threads = kMaxThreads;
+    const int max_prims = std::min(max_prims_in_node, 255);      // bvh.rs:222
+    std::vector<PrimRef> refs(n_tris);
+    {
+        // Triangle::world_bound (triangle.rs:175-180) and centroid = min*0.5 + max*0.5 (bvh.rs:38)
+        std::atomic<uint64_t> next{0};
+        auto work = [&]() {
+            const uint64_t chunk = 1 << 16;
+            for (;;) {
+                uint64_t s = next.fetch_add(chunk);
+                if (s >= n_tris) break;
+                uint64_t e = std::min<uint64_t>(n_tris, s + chunk);
+                for (uint64_t t = s; t < e; ++t) {
+                    const float* p0 = verts + 3ull * indices[3 * t];
+                    const float* p1 = verts + 3ull * indices[3 * t + 1];
+                    const float* p2 = verts + 3ull * indices[3 * t + 2];
+                    PrimRef& r = refs[t];
+                    for (int k = 0; k < 3; ++k) {
+                        float lo = p0[k] < p1[k] ? p0[k] : p1[k];
+                        float hi = p0[k] > p1[k] ? p0[k] : p1[k];
+                        if (p2[k] < lo) lo = p2[k];
+                        if (p2[k] > hi) hi = p2[k];
+                        r.lo[k] = lo;
+                        r.hi[k] = hi;
+                        r.c[k] = lo * 0.5f + hi * 0.5f;
+                    }
+                    r.id = (uint32_t)t;
+                    r.bucket = 0;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int i = 1; i < threads; ++i) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+    }
+    Builder b(refs, max_prims, threads);
+    b.run(out);
+
+    // ---- repack into the device layout ----
+    const size_t n_nodes = out->nodes.size();
+    std::vector<uint32_t> pair_of(n_nodes, 0);
+    uint32_t n_pairs = 0;
+    for (size_t i = 0; i < n_nodes; ++i)
+        if (out->nodes[i].n_prims == 0) pair_of[i] = n_pairs++;
+    out->pairs.resize(n_pairs);
+    auto ref_of = [&](uint32_t node) -> uint32_t {
+        const LinearNode& ln = out->nodes[node];
+        return ln.n_prims > 0 ? (kLeafBit | ln.offset) : pair_of[node];
+    };
+    for (size_t i = 0; i < n_nodes; ++i) {
+        const LinearNode& ln = out->nodes[i];
+        if (ln.n_prims != 0) continue;
+        const LinearNode& L = out->nodes[i + 1];
+        const LinearNode& R = out->nodes[ln.offset];
+        PairNode& p = out->pairs[pair_of[i]];
+        p.a[0] = L.bmin[0]; p.a[1] = L.bmin[1]; p.a[2] = L.bmin[2]; p.a[3] = L.bmax[0];
+        p.b[0] = L.bmax[1]; p.b[1] = L.bmax[2]; p.b[2] = R.bmin[0]; p.b[3] = R.bmin[1];
+        p.c[0] = R.bmin[2]; p.c[1] = R.bmax[0]; p.c[2] = R.bmax[1]; p.c[3] = R.bmax[2];
+        p.left = ref_of((uint32_t)i + 1);
+        p.right = ref_of(ln.offset);
+        p.axis = ln.axis;
+        p.pad = 0;
+    }
+    out->root_ref = ref_of(0);
+    for (int k = 0; k < 3; ++k) { out->root_bounds[k] = out->nodes[0].bmin[k]; out->root_bounds[3 + k] = out->nodes[0].bmax[k]; }
+
+    out->tris.resize(n_tris);
+    for (size_t i = 0; i < n_tris; ++i) {
+        const uint32_t t = out->ordered_prims[i];
+        PackedTri& pt = out->tris[i];
+        const float* p0 = verts + 3ull * indices[3ull * t];
+        const float* p1 = verts + 3ull * indices[3ull * t + 1];
+        const float* p2 = verts + 3ull * indices[3ull * t + 2];
+        for (int k = 0; k < 3; ++k) { pt.v0[k] = p0[k]; pt.v1[k] = p1[k]; pt.v2[k] = p2[k]; }
+        pt.prim_id = t;
+        pt.last = 0;
+        pt.pad = 0;
+    }
+    for (size_t i = 0; i < n_nodes; ++i) {
+        const LinearNode& ln = out->nodes[i];
+        if (ln.n_prims > 0) out->tris[(size_t)ln.offset + ln.n_prims - 1].last = 1;
+    }
+}
+
+}  // namespace pb2

@@ -1,0 +1,66 @@
+// bvh_build.hpp — host-side SAH BVH build for the B200 backend.
+//
+// Replaces BVHAccel::new / recursive_build / flatten_bvh_tree (src/accelerators/bvh.rs:216-473, :774-811) for
+// SplitMethod::SAH.  The build stays on the host (north-star); it emits the flattened depth-first node array
+// directly (first child at i+1, second-child offset patched after the first subtree), runs independent
+// subtrees on worker threads, and then repacks into the device layout:
+//   * PairNode (64 B): one record per INTERIOR node holding both children's boxes, so one 64-byte fetch feeds
+//     two slab tests and leaves need no node record at all;
+//   * PackedTri (48 B): triangles gathered in BVH leaf order as three float4, w-lanes carry the caller's
+//     primitive id and an end-of-leaf flag.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace pb2 {
+
+// The reference's LinearBVHNode (bvh.rs:129-135) narrowed to pbrt-v3's 32 bytes.
+struct LinearNode {
+    float bmin[3];
+    float bmax[3];
+    uint32_t offset;      // leaf: first index into ordered prims; interior: second child
+    uint16_t n_prims;     // 0 = interior
+    uint8_t axis;
+    uint8_t pad;
+};
+static_assert(sizeof(LinearNode) == 32, "LinearNode must be 32 bytes");
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+
+// Device node: boxes of the left (i+1) and right (second child) children of one interior node.
+//   a = {L.min.x, L.min.y, L.min.z, L.max.x}
+//   b = {L.max.y, L.max.z, R.min.x, R.min.y}
+//   c = {R.min.z, R.max.x, R.max.y, R.max.z}
+//   d = {L.ref, R.ref, axis, 0}      ref = pair index, or kLeafBit | first triangle slot
+struct alignas(64) PairNode {
+    float a[4], b[4], c[4];
+    uint32_t left, right, axis, pad;
+};
+static_assert(sizeof(PairNode) == 64, "PairNode must be 64 bytes");
+
+struct alignas(16) PackedTri {
+    float v0[3];
+    uint32_t prim_id;     // index into the caller's triangle list
+    float v1[3];
+    uint32_t last;        // 1 = last triangle of its leaf
+    float v2[3];
+    uint32_t pad;
+};
+static_assert(sizeof(PackedTri) == 48, "PackedTri must be 48 bytes");
+
+struct HostBVH {
+    std::vector<LinearNode> nodes;          // reference layout (parity export)
+    std::vector<uint32_t> ordered_prims;    // leaf order -> caller triangle id
+    int max_depth = 0;                      // nodes on the longest root-to-leaf path
+    // device layout
+    std::vector<PairNode> pairs;
+    std::vector<PackedTri> tris;
+    uint32_t root_ref = 0;
+    float root_bounds[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// verts: 3 floats per vertex; indices: 3 per triangle.  threads <= 0 -> hardware concurrency.
+void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
+                   int max_prims_in_node, int threads, HostBVH* out);
+
+}  // namespace pb2

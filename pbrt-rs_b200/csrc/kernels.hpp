@@ -1,0 +1,28 @@
+// kernels.hpp — host-visible launchers of the device kernels (internal; the public surface is include/pbrt_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+struct SceneView;
+
+// PerspectiveCamera state (perspective.rs:23-31): raster_to_camera and camera_to_world, computed on the host.
+struct CameraView {
+    mat4 raster_to_camera;
+    mat4 camera_to_world;
+    int res_x, res_y;
+};
+
+void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, cudaStream_t st);
+void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, cudaStream_t st);
+void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, void* d_rays, cudaStream_t st);
+void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
+                         void* d_out, cudaStream_t st);
+void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st);
+void launch_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* d_out, cudaStream_t st);
+
+}  // namespace pb2

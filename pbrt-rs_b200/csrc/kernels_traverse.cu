@@ -1,0 +1,238 @@
+// kernels_traverse.cu — batched Primitive::intersect / intersect_p kernels and the ray builders of the
+// ray-casting workloads (sm_100a; compile with -fmad=false).
+#include "kernels.hpp"
+#include "traverse.cuh"
+
+namespace pb2 {
+
+// ---------------------------------------------------------------------------------------------------------
+// k_closest_hit: bvh.rs:828-879.  One ray per thread; rays are 2 x float4 (o,t_max | d,time), hits one uint4.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_closest_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                      uint4* __restrict__ hits, float* __restrict__ b0_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = __ldg(rays + 2 * i);
+    const float4 rd = __ldg(rays + 2 * i + 1);
+    HitRec h;
+    h.prim = 0xFFFFFFFFu; h.slot = 0; h.t = ro.w; h.b0 = 0.0f; h.b1 = 0.0f; h.b2 = 0.0f;
+    traverse<false>(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, &h);
+    hits[i] = make_uint4(h.prim, __float_as_uint(h.t), __float_as_uint(h.b1), __float_as_uint(h.b2));
+    if (b0_out) b0_out[i] = h.b0;
+}
+
+// k_any_hit: bvh.rs:881-932.
+__global__ void __launch_bounds__(128) k_any_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                  uint8_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = __ldg(rays + 2 * i);
+    const float4 rd = __ldg(rays + 2 * i + 1);
+    HitRec h;
+    const bool occluded = traverse<true>(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, &h);
+    out[i] = occluded ? 1 : 0;
+}
+
+void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, cudaStream_t st) {
+    if (n == 0) return;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    k_closest_hit<<<blocks, 128, 0, st>>>(s, (const float4*)d_rays, n, (uint4*)d_hits, (float*)d_b0);
+}
+
+void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    k_any_hit<<<blocks, 128, 0, st>>>(s, (const float4*)d_rays, n, (uint8_t*)d_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Camera::generate_ray (perspective.rs:90-112) + Ray transform (geometry.rs:865-881)
+// ---------------------------------------------------------------------------------------------------------
+PB2_D vec3 xf_point(const mat4& m, vec3 p) {                                  // transform.rs:351-369
+    const float xp = ((m.m[0][0] * p.x + m.m[0][1] * p.y) + m.m[0][2] * p.z) + m.m[0][3];
+    const float yp = ((m.m[1][0] * p.x + m.m[1][1] * p.y) + m.m[1][2] * p.z) + m.m[1][3];
+    const float zp = ((m.m[2][0] * p.x + m.m[2][1] * p.y) + m.m[2][2] * p.z) + m.m[2][3];
+    const float wp = ((m.m[3][0] * p.x + m.m[3][1] * p.y) + m.m[3][2] * p.z) + m.m[3][3];
+    if (wp == 1.0f) return mk(xp, yp, zp);
+    return mk(xp, yp, zp) / wp;
+}
+PB2_D vec3 xf_point_err(const mat4& m, vec3 p, vec3* err) {                   // geometry.rs:898-936
+    const float xp = ((m.m[0][0] * p.x + m.m[0][1] * p.y) + m.m[0][2] * p.z) + m.m[0][3];
+    const float yp = ((m.m[1][0] * p.x + m.m[1][1] * p.y) + m.m[1][2] * p.z) + m.m[1][3];
+    const float zp = ((m.m[2][0] * p.x + m.m[2][1] * p.y) + m.m[2][2] * p.z) + m.m[2][3];
+    const float wp = ((m.m[3][0] * p.x + m.m[3][1] * p.y) + m.m[3][2] * p.z) + m.m[3][3];
+    const float xs = ((fabsf(m.m[0][0] * p.x) + fabsf(m.m[0][1] * p.y)) + fabsf(m.m[0][2] * p.z)) + fabsf(m.m[0][3]);
+    const float ys = ((fabsf(m.m[1][0] * p.x) + fabsf(m.m[1][1] * p.y)) + fabsf(m.m[1][2] * p.z)) + fabsf(m.m[1][3]);
+    const float zs = ((fabsf(m.m[2][0] * p.x) + fabsf(m.m[2][1] * p.y)) + fabsf(m.m[2][2] * p.z)) + fabsf(m.m[2][3]);
+    *err = mk(xs, ys, zs) * gammaf_(3.0f);
+    if (wp == 1.0f) return mk(xp, yp, zp);
+    return mk(xp, yp, zp) / wp;
+}
+PB2_D vec3 xf_vector(const mat4& m, vec3 v) {                                 // transform.rs:371-386
+    return mk((m.m[0][0] * v.x + m.m[0][1] * v.y) + m.m[0][2] * v.z,
+              (m.m[1][0] * v.x + m.m[1][1] * v.y) + m.m[1][2] * v.z,
+              (m.m[2][0] * v.x + m.m[2][1] * v.y) + m.m[2][2] * v.z);
+}
+
+__device__ void camera_ray(const CameraView& cam, float fx, float fy, vec3* o_out, vec3* d_out, float* t_max_out) {
+    const vec3 p_camera = xf_point(cam.raster_to_camera, mk(fx, fy, 0.0f));
+    const vec3 d_cam = unit(p_camera);
+    vec3 o_err;
+    vec3 o = xf_point_err(cam.camera_to_world, mk(0.0f, 0.0f, 0.0f), &o_err);
+    const vec3 d = xf_vector(cam.camera_to_world, d_cam);
+    const float ls = len2(d);
+    float t_max = __int_as_float(0x7f800000);
+    if (ls > 0.0f) {
+        const float dt = dot3(abs3(d), o_err) / ls;
+        o = o + d * dt;
+        t_max = t_max - dt;
+    }
+    *o_out = o;
+    *d_out = d;
+    *t_max_out = t_max;
+}
+
+__global__ void __launch_bounds__(256) k_camera_rays(CameraView cam, const float2* __restrict__ p_film, uint64_t n,
+                                                      float4* __restrict__ rays) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx, fy;
+    if (p_film) {
+        const float2 p = p_film[i];
+        fx = p.x; fy = p.y;
+    } else {
+        fx = (float)(uint32_t)(i % (uint64_t)cam.res_x) + 0.5f;
+        fy = (float)(uint32_t)(i / (uint64_t)cam.res_x) + 0.5f;
+    }
+    vec3 o, d;
+    float t_max;
+    camera_ray(cam, fx, fy, &o, &d, &t_max);
+    rays[2 * i] = make_float4(o.x, o.y, o.z, t_max);
+    rays[2 * i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, void* d_rays, cudaStream_t st) {
+    if (n == 0) return;
+    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, (const float2*)d_pfilm, n, (float4*)d_rays);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Secondary rays of the C3 workload.  The interaction is rebuilt from the hit record as Triangle::intersect does
+// (triangle.rs:217-250): p_hit = b0*p0 + b1*p1 + b2*p2, p_error = gamma(7) * sum|b_i p_i|, n = normalize(dp02 x dp12).
+// ---------------------------------------------------------------------------------------------------------
+struct SurfPoint {
+    vec3 p, p_err, n;
+};
+
+PB2_D bool rebuild_hit(const SceneView& s, vec3 o, vec3 d, uint32_t slot, SurfPoint* sp) {
+    const float4 a = ldg4(s.tris + 3ull * slot), b = ldg4(s.tris + 3ull * slot + 1), c = ldg4(s.tris + 3ull * slot + 2);
+    const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
+    const RayCtx r = make_ray_ctx(o, d);
+    float t, b0, b1, b2;
+    if (!tri_test(r, __int_as_float(0x7f800000), p0, p1, p2, &t, &b0, &b1, &b2)) return false;
+    const float xs = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x)) + fabsf(b2 * p2.x);
+    const float ys = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y)) + fabsf(b2 * p2.y);
+    const float zs = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z)) + fabsf(b2 * p2.z);
+    sp->p_err = mk(xs, ys, zs) * gammaf_(7.0f);
+    sp->p = (p0 * b0 + p1 * b1) + p2 * b2;
+    sp->n = unit(cross3(p0 - p2, p1 - p2));
+    return true;
+}
+
+// interaction.rs:138-153 spawn_ray_to(point): o = offset_ray_origin(p, err, n, target - p), d = target - o,
+// t_max = 1 - SHADOW_EPSILON.
+__global__ void __launch_bounds__(256) k_spawn_shadow(SceneView s, const float4* __restrict__ rays, const uint4* __restrict__ hits,
+                                                       uint64_t n, float lx, float ly, float lz,
+                                                       float4* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 h = hits[i];
+    float4 o4 = make_float4(0.f, 0.f, 0.f, -1.0f), d4 = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (h.x != 0xFFFFFFFFu) {
+        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+        SurfPoint sp;
+        if (rebuild_hit(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), __ldg(s.slot_of_prim + h.x), &sp)) {
+            const vec3 target = mk(lx, ly, lz);
+            const vec3 d = target - sp.p;                       // interaction.rs:140: d = p2 - self.p
+            const vec3 o = offset_ray_origin(sp.p, sp.p_err, sp.n, d);
+            o4 = make_float4(o.x, o.y, o.z, 1.0f - PB2_SHADOW_EPS);
+            d4 = make_float4(d.x, d.y, d.z, 0.0f);
+        }
+    }
+    out[2 * i] = o4;
+    out[2 * i + 1] = d4;
+}
+
+// sampling.rs:258-273 concentric_sample_disk, :289-294 cosine_sample_hemisphere (D30 FIX: z = sqrt(max(0, 1-x^2-y^2)))
+PB2_D vec3 cosine_hemisphere(float u0, float u1) {
+    const float ox = 2.0f * u0 - 1.0f, oy = 2.0f * u1 - 1.0f;
+    float dx = 0.0f, dy = 0.0f;
+    if (!(ox == 0.0f && oy == 0.0f)) {
+        float r, theta;
+        if (fabsf(ox) > fabsf(oy)) { r = ox; theta = (PB2_PI / 4.0f) * (oy / ox); }
+        else { r = oy; theta = (PB2_PI / 2.0f) - (PB2_PI / 4.0f) * (ox / oy); }
+        dx = r * det_cos(theta);
+        dy = r * det_sin(theta);
+    }
+    const float z = sqrtf(fmaxf(0.0f, (1.0f - dx * dx) - dy * dy));
+    return mk(dx, dy, z);
+}
+
+// interaction.rs:132-135 spawn_ray(d): o = offset_ray_origin(p, err, n, d), t_max = inf.  Direction: cosine-weighted
+// about the geometric normal flipped towards the incoming side, frame from coordinate_system(n); PCG32 stream = ray index.
+__global__ void __launch_bounds__(256) k_spawn_bounce(SceneView s, const float4* __restrict__ rays, const uint4* __restrict__ hits,
+                                                       uint64_t n, float4* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 h = hits[i];
+    float4 o4 = make_float4(0.f, 0.f, 0.f, -1.0f), d4 = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (h.x != 0xFFFFFFFFu) {
+        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+        SurfPoint sp;
+        const vec3 d_in = mk(rd.x, rd.y, rd.z);
+        if (rebuild_hit(s, mk(ro.x, ro.y, ro.z), d_in, __ldg(s.slot_of_prim + h.x), &sp)) {
+            vec3 n = sp.n;
+            if (dot3(n, d_in) > 0.0f) n = -n;
+            Pcg32 rng;
+            rng.set_sequence(i);
+            const float u0 = rng.next_float();
+            const float u1 = rng.next_float();
+            const vec3 l = cosine_hemisphere(u0, u1);
+            vec3 sdir, tdir;
+            coord_system(n, &sdir, &tdir);
+            const vec3 wi = (sdir * l.x + tdir * l.y) + n * l.z;
+            const vec3 o = offset_ray_origin(sp.p, sp.p_err, sp.n, wi);
+            o4 = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+            d4 = make_float4(wi.x, wi.y, wi.z, 0.0f);
+        }
+    }
+    out[2 * i] = o4;
+    out[2 * i + 1] = d4;
+}
+
+void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
+                         void* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    k_spawn_shadow<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, (const float4*)d_rays, (const uint4*)d_hits, n, light[0], light[1],
+                                                                  light[2], (float4*)d_out);
+}
+
+void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    k_spawn_bounce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, (const float4*)d_rays, (const uint4*)d_hits, n, (float4*)d_out);
+}
+
+__global__ void __launch_bounds__(256) k_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    Pcg32 rng;
+    rng.set_sequence(first_seq + s);
+    for (uint32_t k = 0; k < n_per; ++k) out[(uint64_t)s * n_per + k] = rng.next_float();
+}
+
+void launch_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* d_out, cudaStream_t st) {
+    if (n_seq == 0 || n_per == 0) return;
+    k_rng_floats<<<(n_seq + 255) / 256, 256, 0, st>>>(first_seq, n_seq, n_per, d_out);
+}
+
+}  // namespace pb2

@@ -1,0 +1,213 @@
+"""GPU parity tests (B200): every result that comes back through the C ABI is compared bit for bit with the CPU
+oracle on the same inputs.  Integer / index / t-bit work: zero mismatches allowed."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def assert_hits_equal(got, ref, b0_got=None, b0_ref=None):
+    assert np.array_equal(got["prim_id"], ref["prim_id"]), f"{(got['prim_id'] != ref['prim_id']).sum()} prim_id mismatches"
+    assert np.array_equal(bits(got["t"]), bits(ref["t"])), "t bits differ"
+    assert np.array_equal(bits(got["b1"]), bits(ref["b1"])) and np.array_equal(bits(got["b2"]), bits(ref["b2"]))
+    if b0_got is not None:
+        assert np.array_equal(bits(b0_got), bits(b0_ref))
+
+
+def random_rays(n, seed, extent=12.0, finite_tmax=False):
+    rng = np.random.default_rng(seed)
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0:3] = rng.uniform(-extent, extent, (n, 3))
+    rays[:, 3] = rng.uniform(1.0, 30.0, n) if finite_tmax else np.inf
+    rays[:, 4:7] = rng.normal(size=(n, 3))
+    return rays
+
+
+def test_rng_streams_bit_exact(gpu, orc):
+    got = gpu.rng_uniform_floats(0, 300, 16)
+    for s in (0, 1, 17, 299):
+        assert np.array_equal(bits(got[s]), bits(orc.pcg32_float(s, 16)))
+    big = gpu.rng_uniform_floats(2 ** 40 + 5, 4, 8)
+    assert np.array_equal(bits(big[3]), bits(orc.pcg32_float(2 ** 40 + 8, 8)))
+
+
+def test_camera_rays_bit_exact(gpu, orc, scenes):
+    for cam in (scenes.C1_CAMERA, scenes.C3_CAMERA):
+        res = (256, 192)
+        camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], res)
+        rng = np.random.default_rng(3)
+        pf = rng.uniform(0, 1, (50000, 2)).astype(np.float32) * np.array(res, np.float32)
+        got = camera.generate_rays(pf)
+        ref = orc.camera_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], res, pf)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def c1(gpu, orc, scenes):
+    v, i = scenes.scene_c1()
+    cam = scenes.C1_CAMERA
+    rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    return dict(v=v, i=i, rays=rays, accel=gpu.BVHAccel(v, i, 4), ref=orc.BVHAccel(v, i, 4))
+
+
+def test_c1_closest_hit_bit_exact(c1):
+    """BASELINE config 0: 1024x1024 primary rays vs the 100,024-triangle sphere+ground, SAH BVH."""
+    hits, b0 = c1["accel"].intersect(c1["rays"], want_b0=True)
+    ref, ref_b0, _ = c1["ref"].intersect(c1["rays"], want_b0=True)
+    assert (ref["prim_id"] != 0xFFFFFFFF).mean() > 0.5
+    assert_hits_equal(hits, ref, b0, ref_b0)
+
+
+def test_c1_any_hit_bit_exact(c1):
+    occ = c1["accel"].intersect_p(c1["rays"])
+    ref = c1["ref"].intersect_p(c1["rays"])[0]
+    assert np.array_equal(occ, ref)
+
+
+def test_c1_bvh_export_equals_oracle(c1):
+    nodes, prims = c1["accel"].export()
+    ref_nodes = c1["ref"].nodes()
+    assert np.array_equal(prims, c1["ref"].ordered_prims())
+    for f in ("bounds", "offset", "n_prims", "axis"):
+        assert np.array_equal(nodes[f], ref_nodes[f])
+    assert np.array_equal(c1["accel"].world_bound(), c1["ref"].world_bound())
+
+
+@pytest.mark.parametrize("max_prims,n_tris", [(1, 3000), (4, 20000), (16, 20000), (255, 5000)])
+def test_random_soup_bit_exact(gpu, orc, scenes, max_prims, n_tris):
+    v, i = scenes.random_soup(n_tris, seed=max_prims)
+    accel = gpu.BVHAccel(v, i, max_prims)
+    ref = orc.BVHAccel(v, i, max_prims)
+    for finite in (False, True):
+        rays = random_rays(100003, seed=n_tris + finite, finite_tmax=finite)        # ragged batch size
+        # axis-aligned directions exercise inv_dir = +-inf and 0*inf = NaN in the slab test
+        rays[:3000, 4:7] = np.eye(3, dtype=np.float32)[np.arange(3000) % 3] * np.where(np.arange(3000) % 2, 1, -1)[:, None].astype(np.float32)
+        rays[3000:4000, 5] = -0.0
+        hits, b0 = accel.intersect(rays, want_b0=True)
+        rh, rb0, _ = ref.intersect(rays, want_b0=True)
+        assert (rh["prim_id"] != 0xFFFFFFFF).sum() > 1000
+        assert_hits_equal(hits, rh, b0, rb0)
+        assert np.array_equal(accel.intersect_p(rays), ref.intersect_p(rays)[0])
+
+
+def test_any_hit_equals_closest_hit_found(gpu, scenes):
+    v, i = scenes.random_soup(30000, seed=77)
+    accel = gpu.BVHAccel(v, i, 4)
+    rays = random_rays(200000, seed=5, finite_tmax=True)
+    hits = accel.intersect(rays)
+    assert np.array_equal(accel.intersect_p(rays).astype(bool), hits["prim_id"] != 0xFFFFFFFF)
+    assert (hits["t"][hits["prim_id"] != 0xFFFFFFFF] <= rays[hits["prim_id"] != 0xFFFFFFFF, 3]).all()
+    miss = hits["prim_id"] == 0xFFFFFFFF
+    assert np.array_equal(bits(hits["t"][miss]), bits(rays[miss, 3]))       # ray.t_max untouched on a miss
+
+
+def test_shared_edges_and_coplanar_ties(gpu, orc):
+    """Rays aimed exactly at shared vertices/edges of a fine grid: equal-t candidates -> last tested wins (tie order)."""
+    n = 64
+    xs = np.linspace(-1, 1, n + 1, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs)
+    v = np.stack([X.ravel(), Y.ravel(), np.zeros(X.size, np.float32)], axis=1)
+    a = (np.arange(n)[:, None] * (n + 1) + np.arange(n)[None, :]).ravel()
+    i = np.concatenate([np.stack([a, a + 1, a + n + 1], 1), np.stack([a + 1, a + n + 2, a + n + 1], 1)]).astype(np.uint32)
+    v = np.concatenate([v, v + np.array([0, 0, 1], np.float32)])            # second, parallel layer
+    i = np.concatenate([i, i + (n + 1) ** 2])
+    accel, ref = gpu.BVHAccel(v, i, 4), orc.BVHAccel(v, i, 4)
+    targets = v[: (n + 1) ** 2]
+    rays = np.zeros((len(targets), 8), np.float32)
+    rays[:, 0:3] = targets + np.array([0, 0, -2], np.float32)
+    rays[:, 3] = np.inf
+    rays[:, 6] = 1.0
+    hits = accel.intersect(rays)
+    rh = ref.intersect(rays)[0]
+    assert (rh["prim_id"] != 0xFFFFFFFF).all()
+    assert_hits_equal(hits, rh)
+
+
+def test_empty_single_and_zero_rays(gpu, orc):
+    e = gpu.BVHAccel(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    rays = np.array([orc.make_ray([0, 0, -1], [0, 0, 1])])
+    h = e.intersect(rays)
+    assert h["prim_id"][0] == 0xFFFFFFFF and np.isinf(h["t"][0]) and e.intersect_p(rays)[0] == 0
+    one = gpu.BVHAccel(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    rays = np.array([orc.make_ray([0.2, 0.2, -1], [0, 0, 1]), orc.make_ray([2, 2, -1], [0, 0, 1])])
+    h = one.intersect(rays)
+    assert h["prim_id"].tolist() == [0, 0xFFFFFFFF] and h["t"][0] == 1.0
+    assert one.intersect_p(rays).tolist() == [1, 0]
+    assert len(one.intersect(np.zeros((0, 8), np.float32))) == 0
+    assert len(one.intersect_p(np.zeros((0, 8), np.float32))) == 0
+
+
+def test_intersect_before_build_is_an_error(gpu):
+    s = gpu.Scene(np.zeros((3, 3), np.float32), np.array([[0, 1, 2]], np.uint32))
+    out = np.empty(1, dtype=gpu.HIT_DTYPE)
+    rays = np.zeros((1, 8), np.float32)
+    rc = gpu.lib().pb2_intersect(s.h, rays.ctypes.data, 1, out.ctypes.data, None)
+    assert rc == -3 and b"build_bvh" in gpu.lib().pb2_last_error()
+
+
+def _c3_pass(gpu, accel, camera, n, light):
+    """primary closest-hit -> shadow any-hit + incoherent bounce closest-hit, all device resident."""
+    d_rays, d_hits, d_b0 = gpu.DeviceBuffer(n * 32), gpu.DeviceBuffer(n * 16), gpu.DeviceBuffer(n * 4)
+    d_srays, d_brays = gpu.DeviceBuffer(n * 32), gpu.DeviceBuffer(n * 32)
+    d_occ, d_bhits = gpu.DeviceBuffer(n), gpu.DeviceBuffer(n * 16)
+    camera.primary_rays_device(d_rays.ptr)
+    accel.intersect_device(d_rays.ptr, n, d_hits.ptr, d_b0.ptr)
+    accel.spawn_shadow_rays_device(d_rays.ptr, d_hits.ptr, n, light, d_srays.ptr)
+    accel.spawn_bounce_rays_device(d_rays.ptr, d_hits.ptr, n, d_brays.ptr)
+    accel.intersect_p_device(d_srays.ptr, n, d_occ.ptr)
+    accel.intersect_device(d_brays.ptr, n, d_bhits.ptr)
+    gpu.check(gpu.lib().pb2_device_synchronize())
+    return dict(rays=d_rays.download(np.float32, n * 8).reshape(-1, 8), hits=d_hits.download(gpu.HIT_DTYPE, n),
+                b0=d_b0.download(np.float32, n), srays=d_srays.download(np.float32, n * 8).reshape(-1, 8),
+                brays=d_brays.download(np.float32, n * 8).reshape(-1, 8), occ=d_occ.download(np.uint8, n),
+                bhits=d_bhits.download(gpu.HIT_DTYPE, n))
+
+
+def _check_c3(gpu, orc, scenes, grid_n, res):
+    v, i = scenes.displaced_grid(n=grid_n)
+    cam = dict(scenes.C3_CAMERA, res=res)
+    accel = gpu.BVHAccel(v, i, 4)
+    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    n = res[0] * res[1]
+    got = _c3_pass(gpu, accel, camera, n, scenes.C3_POINT_LIGHT)
+    ref = orc.BVHAccel(v, i, 4)
+    ref_rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    assert np.array_equal(got["rays"].view(np.uint32), ref_rays.view(np.uint32))
+    rh, rb0, _ = ref.intersect(ref_rays, want_b0=True)
+    assert (rh["prim_id"] != 0xFFFFFFFF).mean() > 0.3
+    assert_hits_equal(got["hits"], rh, got["b0"], rb0)
+    srays = orc.spawn_shadow_rays(ref, rh, rb0, scenes.C3_POINT_LIGHT)
+    brays = orc.spawn_bounce_rays(ref, ref_rays, rh, rb0)
+    assert np.array_equal(got["srays"].view(np.uint32), srays.view(np.uint32)), "shadow rays differ"
+    assert np.array_equal(got["brays"].view(np.uint32), brays.view(np.uint32)), "bounce rays differ"
+    assert np.array_equal(got["occ"], ref.intersect_p(srays)[0])
+    assert_hits_equal(got["bhits"], ref.intersect(brays)[0])
+    occ_frac = got["occ"].mean()
+    assert 0.0 < occ_frac < 1.0
+    return accel, got
+
+
+def test_c3_reduced_all_ray_types_bit_exact(gpu, orc, scenes):
+    _check_c3(gpu, orc, scenes, grid_n=400, res=(256, 256))
+
+
+def test_c3_full_size_10m_triangles_bit_exact(gpu, orc, scenes):
+    """BASELINE config 2 at full size: 10,008,338 triangles, 1024x1024 primary + shadow + incoherent rays, every
+    result compared with the oracle (which builds its own BVH), plus the size-independent properties."""
+    accel, got = _check_c3(gpu, orc, scenes, grid_n=2237, res=(1024, 1024))
+    assert accel.info()[1] == 10008338
+    hit = got["hits"]["prim_id"] != 0xFFFFFFFF
+    # host-buffer path == device-resident path; any-hit == (closest hit found) on the incoherent batch
+    sub = slice(0, 300000)
+    assert np.array_equal(accel.intersect(got["brays"][sub]), got["bhits"][sub])
+    assert np.array_equal(accel.intersect_p(got["brays"][sub]).astype(bool), got["bhits"]["prim_id"][sub] != 0xFFFFFFFF)
+    # idempotence: re-tracing a ray clipped to its own hit distance returns the same primitive and t
+    clipped = got["rays"].copy()
+    clipped[:, 3] = got["hits"]["t"]
+    again = accel.intersect(clipped[hit][:200000])
+    assert np.array_equal(again["prim_id"], got["hits"]["prim_id"][hit][:200000])
+    assert np.array_equal(bits(again["t"]), bits(got["hits"]["t"][hit][:200000]))

@@ -1,0 +1,101 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol, the host SAH
+build equals the oracle's flattened array, camera matrices match, and error paths behave (no GPU calls)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol(pb2):
+    L = pb2.lib()
+    syms = pb2.header_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_product_does_not_link_or_import_the_oracle(pb2):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(pb2.LIB_PATH))
+    out = subprocess.run(["grep", "-rIl", "-i", "oracle", os.path.join(root, "pbrt-rs_b200", "csrc"),
+                          os.path.join(root, "pbrt-rs_b200", "__init__.py"), os.path.join(root, "include")],
+                         capture_output=True, text=True).stdout.strip()
+    assert out == "", f"product sources mention the oracle: {out}"
+    deps = subprocess.run(["ldd", pb2.LIB_PATH], capture_output=True, text=True).stdout
+    assert "liboracle" not in deps
+
+
+def test_last_error_and_invalid_arguments(pb2):
+    L = pb2.lib()
+    h = C.c_void_p()
+    v = np.zeros((3, 3), np.float32)
+    bad = np.array([[0, 1, 7]], np.uint32)
+    rc = L.pb2_scene_create(v.ctypes.data, 3, bad.ctypes.data, 1, None, None, 0, None, 0, C.byref(h))
+    assert rc == -1 and b"references vertex" in L.pb2_last_error()
+    v[0, 0] = np.nan
+    ok = np.array([[0, 1, 2]], np.uint32)
+    rc = L.pb2_scene_create(v.ctypes.data, 3, ok.ctypes.data, 1, None, None, 0, None, 0, C.byref(h))
+    assert rc == -1 and b"non-finite" in L.pb2_last_error()
+    assert L.pb2_world_bound(None, None) == -1
+    with pytest.raises(pb2.Pb2Error):
+        pb2.check(L.pb2_scene_build_bvh(None, 4, 0))
+
+
+def _same_nodes(a, b):
+    return (np.array_equal(a["bounds"], b["bounds"]) and np.array_equal(a["offset"], b["offset"])
+            and np.array_equal(a["n_prims"], b["n_prims"]) and np.array_equal(a["axis"], b["axis"]))
+
+
+@pytest.mark.parametrize("case", ["soup4", "soup1", "soup16", "sphere", "tiny", "coincident"])
+def test_host_sah_build_equals_oracle(pb2, orc, scenes, case):
+    if case.startswith("soup"):
+        mp = int(case[4:])
+        v, i = scenes.random_soup(20000, seed=mp)
+    elif case == "sphere":
+        mp = 4
+        v, i = scenes.merge(scenes.uv_sphere(n_theta=60, n_phi=120), scenes.ground_grid())
+    elif case == "tiny":
+        mp = 4
+        v, i = scenes.random_soup(3, seed=9)
+    else:  # nine triangles sharing one centroid -> one oversized leaf (bvh.rs:311)
+        mp = 4
+        tris = []
+        for k in range(9):
+            s = 1.0 + k
+            tris.append([[-s, -s, 0], [s, -s, 0], [0, 2 * s, 0]])
+        v = np.array(tris, np.float32).reshape(-1, 3)
+        i = np.arange(27, dtype=np.uint32).reshape(-1, 3)
+    mine = pb2.BVHAccel(v, i, max_prims_in_node=mp, host_only=True)
+    ref = orc.BVHAccel(v, i, mp)
+    nodes, prims = mine.export()
+    assert len(nodes) == ref.num_nodes
+    assert np.array_equal(prims, ref.ordered_prims())
+    assert _same_nodes(nodes, ref.nodes())
+    assert mine.info()[2] == ref.max_depth
+    assert np.array_equal(mine.world_bound(), ref.world_bound())
+
+
+def test_host_build_parallel_path_equals_oracle(pb2, orc, scenes):
+    # large enough that the builder splits the top of the tree across worker threads (grain = n / (8 * threads))
+    v, i = scenes.displaced_grid(n=300)
+    mine = pb2.BVHAccel(v, i, max_prims_in_node=4, host_only=True)
+    ref = orc.BVHAccel(v, i, 4)
+    nodes, prims = mine.export()
+    assert np.array_equal(prims, ref.ordered_prims())
+    assert _same_nodes(nodes, ref.nodes())
+
+
+def test_camera_matrices_equal_oracle(pb2, orc, scenes):
+    for cam in (scenes.C1_CAMERA, scenes.C3_CAMERA, dict(pos=(278, 273, -800), look=(278, 273, 0), up=(0, 1, 0), fov=39.3, res=(1920, 1080))):
+        r2c, c2w = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"]).matrices()
+        o_r2c, o_c2w = orc.camera_matrices(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+        assert np.array_equal(r2c.view(np.uint32), o_r2c.view(np.uint32))
+        assert np.array_equal(c2w.view(np.uint32), o_c2w.view(np.uint32))
+
+
+def test_empty_scene_host(pb2):
+    b = pb2.BVHAccel(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), host_only=True)
+    assert b.info() == (0, 0, 0)
+    wb = b.world_bound()
+    assert (wb[:3] > 1e38).all() and (wb[3:] < -1e38).all()
