@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbrt_b200.so")
+LIB_PATH = os.environ.get("PB2_LIB", os.path.join(_HERE, "libpbrt_b200.so"))   # PB2_LIB: tuning builds only
 _LIB = None
 
 PB2_MISS = 0xFFFFFFFF

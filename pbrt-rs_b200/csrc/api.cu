@@ -44,6 +44,8 @@ void pb2_scene::free_device() {
     if (d_materials) cudaFree(d_materials);
     if (d_lights) cudaFree(d_lights);
     if (d_light_cdf) cudaFree(d_light_cdf);
+    if (d_counters) cudaFree(d_counters);
+    d_counters = nullptr;
     d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
     for (int i = 0; i < 2; ++i) {
         if (stage[i].d_in) cudaFree(stage[i].d_in);
@@ -189,6 +191,8 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     SceneView v;
     memset(&v, 0, sizeof v);
     v.n_tris = (uint32_t)n_tris;
+    PB2_CUDA(cudaMalloc(&scene->d_counters, pb2_scene::kCounters * sizeof(unsigned long long)));
+    PB2_CUDA(cudaMemset(scene->d_counters, 0, pb2_scene::kCounters * sizeof(unsigned long long)));
     if (n_tris) {
         PB2_CUDA(cudaMalloc(&scene->d_pairs, std::max<size_t>(64, b.pairs.size() * sizeof(PairNode))));
         PB2_CUDA(cudaMalloc(&scene->d_tris, b.tris.size() * sizeof(PackedTri)));
@@ -285,7 +289,7 @@ int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hi
         const uint64_t m = std::min<uint64_t>(kChunk, n - off);
         Stage& st = scene->stage[k];
         PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
-        launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, st.stream);
+        launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, scene->next_counter(), st.stream);
         PB2_CUDA(cudaGetLastError());
         PB2_CUDA(cudaMemcpyAsync(hits + off, st.d_out, m * 16, cudaMemcpyDeviceToHost, st.stream));
         if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, st.stream));
@@ -308,7 +312,7 @@ int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* 
         const uint64_t m = std::min<uint64_t>(kChunk, n - off);
         Stage& st = scene->stage[k];
         PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
-        launch_any_hit(scene->view, st.d_in, m, st.d_out, st.stream);
+        launch_any_hit(scene->view, st.d_in, m, st.d_out, scene->next_counter(), st.stream);
         PB2_CUDA(cudaGetLastError());
         PB2_CUDA(cudaMemcpyAsync(out + off, st.d_out, m, cudaMemcpyDeviceToHost, st.stream));
     }
@@ -320,7 +324,7 @@ int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* 
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream) {
     int rc = check_ready(scene);
     if (rc) return rc;
-    launch_closest_hit(scene->view, d_rays, n, d_hits, d_b0, (cudaStream_t)stream);
+    launch_closest_hit(scene->view, d_rays, n, d_hits, d_b0, scene->next_counter(), (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;
 }
@@ -328,7 +332,7 @@ int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void*
 int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream) {
     int rc = check_ready(scene);
     if (rc) return rc;
-    launch_any_hit(scene->view, d_rays, n, d_out, (cudaStream_t)stream);
+    launch_any_hit(scene->view, d_rays, n, d_out, scene->next_counter(), (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;
 }

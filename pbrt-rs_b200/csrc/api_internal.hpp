@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -57,6 +58,11 @@ struct pb2_scene {
     void* d_materials = nullptr;
     void* d_lights = nullptr;
     void* d_light_cdf = nullptr;
+    // work counters of the persistent traversal kernels: one slot per launch, handed out round-robin
+    static constexpr unsigned kCounters = 256;
+    unsigned long long* d_counters = nullptr;
+    std::atomic<unsigned> counter_cursor{0};
+    unsigned long long* next_counter() { return d_counters + (counter_cursor.fetch_add(1) % kCounters); }
     pb2::SceneView view;
     pb2::Stage stage[2];
     pb2::Wavefront* wf = nullptr;

@@ -17,8 +17,9 @@ struct CameraView {
     int res_x, res_y;
 };
 
-void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, cudaStream_t st);
-void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, cudaStream_t st);
+void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, unsigned long long* d_counter,
+                        cudaStream_t st);
+void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, unsigned long long* d_counter, cudaStream_t st);
 void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, void* d_rays, cudaStream_t st);
 void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
                          void* d_out, cudaStream_t st);

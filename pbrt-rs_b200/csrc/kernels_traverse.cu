@@ -1,48 +1,94 @@
 // kernels_traverse.cu — batched Primitive::intersect / intersect_p kernels and the ray builders of the
 // ray-casting workloads (sm_100a; compile with -fmad=false).
 #include "kernels.hpp"
-#include "traverse.cuh"
+#include "trace_persistent.cuh"
+
+#include <cstdlib>
 
 namespace pb2 {
 
 // ---------------------------------------------------------------------------------------------------------
-// k_closest_hit: bvh.rs:828-879.  One ray per thread; rays are 2 x float4 (o,t_max | d,time), hits one uint4.
+// k_closest_hit / k_any_hit: bvh.rs:828-879 / :881-932 over a batch.  Rays are 2 x float4 (o,t_max | d,time), hits one
+// uint4 {prim_id, t, b1, b2}.  The walk itself is trace_persistent.cuh.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_closest_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
-                                                      uint4* __restrict__ hits, float* __restrict__ b0_out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = __ldg(rays + 2 * i);
-    const float4 rd = __ldg(rays + 2 * i + 1);
-    HitRec h;
-    h.prim = 0xFFFFFFFFu; h.slot = 0; h.t = ro.w; h.b0 = 0.0f; h.b1 = 0.0f; h.b2 = 0.0f;
-    traverse<false>(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, &h);
-    hits[i] = make_uint4(h.prim, __float_as_uint(h.t), __float_as_uint(h.b1), __float_as_uint(h.b2));
-    if (b0_out) b0_out[i] = h.b0;
+#ifndef PB2_MIN_BLOCKS
+#define PB2_MIN_BLOCKS 8   /* 64 registers: 8 CTAs of 4 warps per SM; 48 registers spill and run slower (profiles/r01_tuning.md) */
+#endif
+
+struct BatchSink {
+    const float4* __restrict__ rays;
+    uint4* __restrict__ hits;
+    float* __restrict__ b0_out;
+    uint8_t* __restrict__ occ_out;
+    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+        const float4 ro = __ldg(rays + 2 * i);
+        const float4 rd = __ldg(rays + 2 * i + 1);
+        *o = mk(ro.x, ro.y, ro.z);
+        *d = mk(rd.x, rd.y, rd.z);
+        *t_max = ro.w;
+        return true;
+    }
+    PB2_D void closest(uint64_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
+        hits[i] = make_uint4(prim, __float_as_uint(t), __float_as_uint(b1), __float_as_uint(b2));
+        if (b0_out) b0_out[i] = b0;
+    }
+    PB2_D void occluded(uint64_t i, bool occ) const { occ_out[i] = occ ? 1 : 0; }
+};
+
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_closest_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                      unsigned long long* __restrict__ counter, uint4* __restrict__ hits,
+                                                      float* __restrict__ b0_out, TraceTuning tune) {
+    const BatchSink sink{rays, hits, b0_out, nullptr};
+    trace_persistent<false>(s, n, counter, sink, tune);
 }
 
-// k_any_hit: bvh.rs:881-932.
-__global__ void __launch_bounds__(128) k_any_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
-                                                  uint8_t* __restrict__ out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = __ldg(rays + 2 * i);
-    const float4 rd = __ldg(rays + 2 * i + 1);
-    HitRec h;
-    const bool occluded = traverse<true>(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, &h);
-    out[i] = occluded ? 1 : 0;
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                  unsigned long long* __restrict__ counter, uint8_t* __restrict__ out,
+                                                  TraceTuning tune) {
+    const BatchSink sink{rays, nullptr, nullptr, out};
+    trace_persistent<true>(s, n, counter, sink, tune);
 }
 
-void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, cudaStream_t st) {
+// Scheduling knobs (results do not depend on them).  Defaults tuned on B200 with the C3 workload; the environment
+// variables exist for the tuning sweeps recorded in profiles/.
+TraceTuning trace_tuning() {
+    static TraceTuning t = [] {
+        TraceTuning v{16, 12, 33, 0};
+        if (const char* e = getenv("PB2_REFILL_BELOW")) v.refill_below = atoi(e);
+        if (const char* e = getenv("PB2_NODE_QUORUM")) v.node_quorum = atoi(e);
+        if (const char* e = getenv("PB2_LEAF_QUORUM")) v.leaf_quorum = atoi(e);
+        if (const char* e = getenv("PB2_PREFETCH")) v.prefetch = atoi(e);
+        return v;
+    }();
+    return t;
+}
+
+// Grid = every SM filled to the occupancy the kernel reaches (queried once), capped by the amount of work.
+static unsigned persistent_grid(const void* kernel, uint64_t n) {
+    static int sm_count = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t want = (n + 127) / 128;
+    const uint64_t full = (uint64_t)sm_count * (uint64_t)per_sm;
+    return (unsigned)(want < full ? want : full);
+}
+
+void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, unsigned long long* d_counter,
+                        cudaStream_t st) {
     if (n == 0) return;
-    const unsigned blocks = (unsigned)((n + 127) / 128);
-    k_closest_hit<<<blocks, 128, 0, st>>>(s, (const float4*)d_rays, n, (uint4*)d_hits, (float*)d_b0);
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
+    k_closest_hit<<<persistent_grid((const void*)k_closest_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, n, d_counter, (uint4*)d_hits,
+                                                                                 (float*)d_b0, trace_tuning());
 }
 
-void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, cudaStream_t st) {
+void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, unsigned long long* d_counter, cudaStream_t st) {
     if (n == 0) return;
-    const unsigned blocks = (unsigned)((n + 127) / 128);
-    k_any_hit<<<blocks, 128, 0, st>>>(s, (const float4*)d_rays, n, (uint8_t*)d_out);
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
+    k_any_hit<<<persistent_grid((const void*)k_any_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, n, d_counter, (uint8_t*)d_out, trace_tuning());
 }
 
 // ---------------------------------------------------------------------------------------------------------
