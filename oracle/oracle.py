@@ -64,15 +64,21 @@ def lib():
 
 
 def _bind_path(L):
-    if hasattr(L, "orc_render"):
-        L.orc_scene_create.restype = C.c_void_p
-        L.orc_scene_create.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
-                                       C.c_uint32, C.c_void_p, C.c_uint32, C.c_int]
-        L.orc_scene_free.argtypes = [C.c_void_p]
-        L.orc_render.restype = C.c_double
-        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.orc_scene_bvh.restype = C.c_void_p
-        L.orc_scene_bvh.argtypes = [C.c_void_p]
+    vp = C.c_void_p
+    L.orc_scene_create.restype = vp
+    L.orc_scene_create.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_int]
+    L.orc_scene_free.argtypes = [vp]
+    L.orc_scene_bvh.restype = vp
+    L.orc_scene_bvh.argtypes = [vp]
+    L.orc_render.restype = C.c_double
+    L.orc_render.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
+    L.orc_path_li.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp]
+    L.orc_resolve_rgb.argtypes = [vp, C.c_uint64, C.c_float, vp]
+    L.orc_film_add_samples.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
+    L.orc_roughness_to_alpha.restype = C.c_float
+    L.orc_roughness_to_alpha.argtypes = [C.c_float]
+    L.orc_sincos.argtypes = [C.c_float, vp, vp]
+    L.orc_film_table.argtypes = [vp, vp]
 
 
 def _p(a):

@@ -1,3 +1,769 @@
-// ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  (path tracer restatement: filled in below)
+// ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  PARITY UNPINNED (see oracle_core.hpp).
+//
+// CPU restatement of the PathIntegrator side of the hot path: PathIntegrator::li (src/integrators/path.rs:65-213),
+// uniform_sample_one_light / estimate_direct (src/core/integrator.rs:92-266), SamplerIntegrator::render (:399-480),
+// BSDF + Lambertian / MicrofacetReflection(Trowbridge-Reitz) / FresnelSpecular (src/core/reflection.rs,
+// src/core/microfacet.rs), DiffuseAreaLight / PointLight (src/lights/), Distribution1D (src/core/sampling.rs),
+// Film / FilmTile / Box+Gaussian filters (src/core/film.rs, src/filters/), RGB<->XYZ (src/core/spectrum.rs).
+// Defect decisions follow SURVEY.md Appendix A; matte / plastic / glass are restated from pbrt-v3 (Appendix B) because
+// src/materials/{matte,plastic,glass}.rs are empty files in the reference.
 #pragma once
 #include "oracle_core.hpp"
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+namespace orc {
+
+// ---------------------------------------------------------------- spectrum.rs (RGBSpectrum)
+struct RGB {
+    Float r, g, b;
+};
+inline RGB rgb(Float v) { return {v, v, v}; }
+inline RGB operator+(RGB a, RGB b) { return {a.r + b.r, a.g + b.g, a.b + b.b}; }
+inline RGB operator*(RGB a, RGB b) { return {a.r * b.r, a.g * b.g, a.b * b.b}; }
+inline RGB operator*(RGB a, Float s) { return {a.r * s, a.g * s, a.b * s}; }
+inline RGB operator/(RGB a, Float s) { return {a.r / s, a.g / s, a.b / s}; }
+inline bool is_black(RGB a) { return a.r == 0.0f && a.g == 0.0f && a.b == 0.0f; }        // spectrum.rs:176-183, D28 FIX
+inline Float y_value(RGB a) { return (0.212671f * a.r + 0.715160f * a.g) + 0.072169f * a.b; }   // :679-682
+inline Float max_component_value(RGB a) {                                                  // :161-165 (fold from f32::MIN)
+    Float m = -std::numeric_limits<Float>::max();
+    m = (m > a.r) ? m : a.r;
+    m = (m > a.g) ? m : a.g;
+    m = (m > a.b) ? m : a.b;
+    return m;
+}
+inline bool has_nans(RGB a) { return std::isnan(a.r) || std::isnan(a.g) || std::isnan(a.b); }
+inline void rgb_to_xyz(RGB c, Float xyz[3]) {                                              // :103-107
+    xyz[0] = (0.412453f * c.r + 0.357580f * c.g) + 0.180423f * c.b;
+    xyz[1] = (0.212671f * c.r + 0.715160f * c.g) + 0.072169f * c.b;
+    xyz[2] = (0.019334f * c.r + 0.119193f * c.g) + 0.950227f * c.b;
+}
+inline void xyz_to_rgb(const Float xyz[3], Float out[3]) {                                 // :96-100
+    out[0] = (3.240479f * xyz[0] - 1.537150f * xyz[1]) - 0.498535f * xyz[2];
+    out[1] = (-0.969256f * xyz[0] + 1.875991f * xyz[1]) + 0.041556f * xyz[2];
+    out[2] = (0.055648f * xyz[0] - 0.204043f * xyz[1]) + 1.057311f * xyz[2];
+}
+inline Float clampf(Float v, Float lo, Float hi) { return v < lo ? lo : (v > hi ? hi : v); }   // pbrt.rs:112-120
+
+// ---------------------------------------------------------------- scene description (same POD layout as the C ABI)
+enum { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_GLASS = 2 };
+struct MaterialDesc {
+    int32_t type;
+    Float kd[3], ks[3];
+    Float roughness;
+    int32_t remap_roughness;
+    Float kr[3], kt[3];
+    Float eta;
+};
+enum { LIGHT_POINT = 0, LIGHT_AREA = 1 };
+struct LightDesc {
+    int32_t type;
+    Float p[3];
+    Float i[3];
+    uint32_t prim_id;
+    int32_t two_sided;
+};
+struct CameraDesc {
+    Float pos[3], look[3], up[3];
+    Float fov;
+    int32_t res_x, res_y;
+};
+enum { FILTER_BOX = 0, FILTER_GAUSSIAN = 1 };
+struct FilmDesc {
+    int32_t res_x, res_y;
+    int32_t filter;
+    Float radius_x, radius_y;
+    Float gaussian_alpha;
+};
+enum { LIGHTS_UNIFORM = 0, LIGHTS_POWER = 1 };
+struct PathDesc {
+    int32_t max_depth;
+    Float rr_threshold;
+    int32_t light_strategy;
+    int32_t spp;
+    int32_t sample_begin, sample_end;
+};
+
+// ---------------------------------------------------------------- sampling.rs:68-154 Distribution1D (D29 FIX, D57 KEEP, D58)
+struct Distribution1D {
+    std::vector<Float> func, cdf;
+    Float func_int = 0;
+    void init(const std::vector<Float>& f) {
+        size_t n = f.size();
+        func = f;
+        cdf.assign(n + 1, 0.0f);
+        for (size_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / (Float)n;
+        func_int = cdf[n];
+        if (func_int == 0.0f) for (size_t i = 1; i < n + 1; ++i) cdf[i] = (Float)i / (Float)n;
+        else for (size_t i = 1; i < n + 1; ++i) cdf[i] /= func_int;
+    }
+    size_t count() const { return func.size(); }
+    // pbrt.rs:229-243 find_interval with pred = cdf[i] < u (D57), signed clamp (D58)
+    size_t sample_discrete(Float u, Float* pdf) const {
+        long first = 0, len = (long)cdf.size();
+        while (len > 0) {
+            long half = len >> 1, middle = first + half;
+            if (cdf[middle] < u) { first = middle + 1; len -= half + 1; }
+            else len = half;
+        }
+        long off = first - 1;
+        long hi = (long)cdf.size() - 2;
+        if (off < 0) off = 0; else if (off > hi) off = hi;
+        *pdf = func_int > 0.0f ? func[off] / (func_int * (Float)count()) : 0.0f;
+        return (size_t)off;
+    }
+};
+
+// ---------------------------------------------------------------- reflection.rs
+enum : uint8_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+
+inline Float fr_dielectric(Float cos_theta_i, Float eta_i, Float eta_t) {                  // :19-40
+    cos_theta_i = clampf(cos_theta_i, -1.0f, 1.0f);
+    bool entering = cos_theta_i > 0.0f;
+    if (!entering) { std::swap(eta_i, eta_t); cos_theta_i = std::fabs(cos_theta_i); }
+    Float sin_theta_i = std::sqrt(fmax_(1.0f - cos_theta_i * cos_theta_i, 0.0f));
+    Float sin_theta_t = eta_i / eta_t * sin_theta_i;
+    if (sin_theta_t >= 1.0f) return 1.0f;
+    Float cos_theta_t = std::sqrt(fmax_(1.0f - sin_theta_t * sin_theta_t, 0.0f));
+    Float r_parl = (eta_t * cos_theta_i - eta_i * cos_theta_t) / (eta_t * cos_theta_i + eta_i * cos_theta_t);
+    Float r_perp = (eta_i * cos_theta_i - eta_t * cos_theta_t) / (eta_i * cos_theta_i + eta_t * cos_theta_t);
+    return (r_parl * r_parl + r_perp * r_perp) / 2.0f;
+}
+inline Float cos_theta(V3 w) { return w.z; }                                               // :71-135
+inline Float cos2_theta(V3 w) { return w.z * w.z; }
+inline Float abs_cos_theta(V3 w) { return std::fabs(w.z); }
+inline Float sin2_theta(V3 w) { return fmax_(1.0f - cos2_theta(w), 0.0f); }
+inline Float sin_theta(V3 w) { return std::sqrt(sin2_theta(w)); }
+inline Float tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }
+inline Float tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+inline Float cos_phi(V3 w) { Float s = sin_theta(w); return s == 0.0f ? 1.0f : clampf(w.x / s, -1.0f, 1.0f); }
+inline Float sin_phi(V3 w) { Float s = sin_theta(w); return s == 0.0f ? 0.0f : clampf(w.y / s, -1.0f, 1.0f); }
+inline Float cos2_phi(V3 w) { return cos_phi(w) * cos_phi(w); }
+inline Float sin2_phi(V3 w) { return sin_phi(w) * sin_phi(w); }
+inline V3 reflect(V3 wo, V3 n) { return -wo + n * (2.0f * dot(wo, n)); }                   // :140-142
+inline bool refract(V3 wi, V3 n, Float eta, V3* wt) {                                      // :145-156, D35 FIX
+    Float cos_theta_i = dot(n, wi);
+    Float sin2_theta_i = fmax_(1.0f - cos_theta_i * cos_theta_i, 0.0f);
+    Float sin2_theta_t = eta * eta * sin2_theta_i;
+    if (sin2_theta_t >= 1.0f) return false;
+    Float cos_theta_t = std::sqrt(1.0f - sin2_theta_t);
+    *wt = -wi * eta + n * (eta * cos_theta_i - cos_theta_t);
+    return true;
+}
+inline bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0f; }
+inline V3 faceforward(V3 n, V3 v) { return dot(n, v) < 0.0f ? -n : n; }                    // pbrt Faceforward(n, v) (D6 FIX)
+
+// ---------------------------------------------------------------- microfacet.rs:145-248, 336-406 (Trowbridge-Reitz)
+inline Float roughness_to_alpha(Float roughness) {                                         // :160-168
+    roughness = fmax_(roughness, 1e-3f);
+    Float x = std::log(roughness);
+    return (((1.62142f + 0.819955f * x) + 0.1734f * x * x) + 0.0171201f * x * x * x) + 0.000640711f * x * x * x * x;
+}
+struct TrowbridgeReitz {
+    Float ax, ay;
+    Float d(V3 wh) const {                                                                  // :176-186
+        Float t2 = tan2_theta(wh);
+        if (std::isinf(t2)) return 0.0f;
+        Float cos4 = cos2_theta(wh) * cos2_theta(wh);
+        Float e = (cos2_phi(wh) / (ax * ax) + sin2_phi(wh) / (ay * ay)) * t2;
+        return 1.0f / (kPi * ax * ay * cos4 * (1.0f + e) * (1.0f + e));
+    }
+    Float lambda(V3 w) const {                                                              // :188-199
+        Float abs_tan = std::fabs(tan_theta(w));
+        if (std::isinf(abs_tan)) return 0.0f;
+        Float alpha = std::sqrt(cos2_phi(w) * ax * ax + sin2_phi(w) * ay * ay);
+        Float a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
+        return (-1.0f + std::sqrt(1.0f + a2t2)) / 2.0f;
+    }
+    Float g1(V3 w) const { return 1.0f / (1.0f + lambda(w)); }                              // :15-17
+    Float g(V3 wo, V3 wi) const { return 1.0f / ((1.0f + lambda(wo)) + lambda(wi)); }       // :18-20
+    Float pdf(V3 wo, V3 wh) const { return d(wh) * g1(wo) * std::fabs(dot(wo, wh)) / abs_cos_theta(wo); }   // :23-29 (visible area)
+    static void sample11(Float cos_t, Float u1, Float u2, Float* slope_x, Float* slope_y) {  // :336-384
+        if (cos_t > 0.9999f) {
+            Float r = std::sqrt(u1 / (1.0f - u1));
+            Float phi = 6.28318530718f * u2;
+            *slope_x = r * cos_c(phi);
+            *slope_y = r * sin_c(phi);
+            return;
+        }
+        Float sin_t = std::sqrt(fmax_(1.0f - cos_t * cos_t, 0.0f));
+        Float tan_t = sin_t / cos_t;
+        Float a = 1.0f / tan_t;
+        Float g1 = 2.0f / (1.0f + std::sqrt(1.0f + 1.0f / (a * a)));
+        a = 2.0f * u1 / g1 - 1.0f;
+        Float tmp = 1.0f / (a * a - 1.0f);
+        if (tmp > 1e10f) tmp = 1e10f;
+        Float b = tan_t;
+        Float dd = std::sqrt(fmax_(b * b * tmp * tmp - (a * a - b * b), 0.0f));
+        Float sx1 = b * tmp - dd, sx2 = b * tmp + dd;
+        *slope_x = (a < 0.0f || sx2 > 1.0f / tan_t) ? sx1 : sx2;
+        Float s;
+        if (u2 > 0.5f) { s = 1.0f; u2 = 2.0f * (u2 - 0.5f); }
+        else { s = -1.0f; u2 = 2.0f * (0.5f - u2); }
+        Float z = (u2 * (u2 * (u2 * 0.27385f - 0.73369f) + 0.46341f)) /
+                  (u2 * (u2 * (u2 * 0.093073f + 0.309420f) - 1.00000f) + 0.5979999f);
+        *slope_y = s * z * std::sqrt(1.0f + *slope_x * *slope_x);
+    }
+    static V3 sample(V3 wi, Float ax, Float ay, Float u1, Float u2) {                        // :386-406, D40 FIX
+        V3 ws = normalize(V3{ax * wi.x, ay * wi.y, wi.z});
+        Float sx, sy;
+        sample11(cos_theta(ws), u1, u2, &sx, &sy);
+        Float tmp = cos_phi(ws) * sx - sin_phi(ws) * sy;
+        sy = sin_phi(ws) * sx + cos_phi(ws) * sy;
+        sx = tmp;
+        sx = ax * sx;
+        sy = ay * sy;
+        return normalize(V3{-sx, -sy, 1.0f});
+    }
+    V3 sample_wh(V3 wo, Float u0, Float u1) const {                                         // :201-243 (sample_visible_area)
+        bool flip = wo.z < 0.0f;
+        V3 wh = sample(flip ? -wo : wo, ax, ay, u0, u1);
+        return flip ? -wh : wh;
+    }
+};
+
+// ---------------------------------------------------------------- BxDFs as tagged PODs
+enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR };
+struct Lobe {
+    LobeKind kind;
+    uint8_t type;       // BxDFType bits
+    RGB r, t;           // reflectance / transmittance
+    Float alpha;        // microfacet
+    Float eta_a, eta_b; // fresnel specular / dielectric
+    bool matches(uint8_t flags) const { return (type & flags) == type; }                    // :455-457, D33 FIX
+    RGB f(V3 wo, V3 wi) const {
+        switch (kind) {
+            case LOBE_LAMBERT: return r * (1.0f / kPi);                                     // :840-842 (r * INV_PI)
+            case LOBE_MICROFACET: {                                                          // :998-1017
+                Float co = abs_cos_theta(wo), ci = abs_cos_theta(wi);
+                V3 wh = wi + wo;
+                if (ci == 0.0f || co == 0.0f) return rgb(0);
+                if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return rgb(0);
+                wh = normalize(wh);
+                TrowbridgeReitz tr{alpha, alpha};
+                Float fr = fr_dielectric(dot(wi, faceforward(wh, V3{0, 0, 1})), eta_a, eta_b);   // D6 FIX
+                return r * tr.d(wh) * tr.g(wo, wi) * rgb(fr) / (4.0f * ci * co);
+            }
+            default: return rgb(0);                                                          // FresnelSpecular :761-763
+        }
+    }
+    Float pdf(V3 wo, V3 wi) const {
+        switch (kind) {
+            case LOBE_LAMBERT: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * (1.0f / kPi) : 0.0f;   // :501-507
+            case LOBE_MICROFACET: {                                                          // :1042-1048
+                if (!same_hemisphere(wo, wi)) return 0.0f;
+                V3 wh = normalize(wo + wi);
+                TrowbridgeReitz tr{alpha, alpha};
+                return tr.pdf(wo, wh) / (4.0f * dot(wo, wh));
+            }
+            default: return 0.0f;
+        }
+    }
+    RGB sample_f(V3 wo, V3* wi, Float u0, Float u1, Float* pdf_out, uint8_t* sampled_type) const {
+        switch (kind) {
+            case LOBE_LAMBERT: {                                                             // :459-472 BxDF default
+                *wi = cosine_sample_hemisphere(u0, u1);
+                if (wo.z < 0.0f) wi->z *= -1.0f;
+                *pdf_out = pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case LOBE_MICROFACET: {                                                          // :1019-1040, D36 FIX
+                if (wo.z == 0.0f) return rgb(0);
+                TrowbridgeReitz tr{alpha, alpha};
+                V3 wh = tr.sample_wh(wo, u0, u1);
+                if (dot(wo, wh) < 0.0f) return rgb(0);
+                *wi = reflect(wo, wh);
+                if (!same_hemisphere(wo, *wi)) return rgb(0);
+                *pdf_out = tr.pdf(wo, wh) / (4.0f * dot(wo, wh));
+                return f(wo, *wi);
+            }
+            default: {                                                                       // FresnelSpecular :765-811
+                Float fr = fr_dielectric(cos_theta(wo), eta_a, eta_b);
+                if (u0 < fr) {
+                    *wi = V3{-wo.x, -wo.y, wo.z};
+                    *sampled_type = BSDF_SPECULAR | BSDF_REFLECTION;
+                    *pdf_out = fr;
+                    return r * fr / abs_cos_theta(*wi);
+                }
+                bool entering = cos_theta(wo) > 0.0f;
+                Float eta_i = entering ? eta_a : eta_b, eta_t = entering ? eta_b : eta_a;
+                if (!refract(wo, faceforward(V3{0, 0, 1}, wo), eta_i / eta_t, wi)) return rgb(0);   // D6 FIX
+                RGB ft = t * (1.0f - fr);
+                ft = ft * ((eta_i * eta_i) / (eta_t * eta_t));                                // TransportMode::Radiance
+                *sampled_type = BSDF_SPECULAR | BSDF_TRANSMISSION;
+                *pdf_out = 1.0f - fr;
+                return ft / abs_cos_theta(*wi);
+            }
+        }
+    }
+};
+
+struct BSDF {                                                                                // :206-449
+    Float eta = 1.0f;
+    V3 ns, ng, ss, ts;
+    int n = 0;
+    Lobe lobes[2];
+    int num_components(uint8_t flags) const { int c = 0; for (int i = 0; i < n; ++i) c += lobes[i].matches(flags); return c; }
+    V3 world_to_local(V3 v) const { return {dot(v, ss), dot(v, ts), dot(v, ns)}; }
+    V3 local_to_world(V3 v) const {                                                          // :256-262, D34 FIX
+        return {(ss.x * v.x + ts.x * v.y) + ns.x * v.z, (ss.y * v.x + ts.y * v.y) + ns.y * v.z, (ss.z * v.x + ts.z * v.y) + ns.z * v.z};
+    }
+    RGB f(V3 wo_w, V3 wi_w, uint8_t flags) const {                                           // :265-284
+        V3 wi = world_to_local(wi_w), wo = world_to_local(wo_w);
+        if (wo.z == 0.0f) return rgb(0);
+        bool refl = dot(wi_w, ng) * dot(wo_w, ng) > 0.0f;
+        RGB sum = rgb(0);
+        for (int i = 0; i < n; ++i)
+            if (lobes[i].matches(flags) && ((refl && (lobes[i].type & BSDF_REFLECTION)) || (!refl && (lobes[i].type & BSDF_TRANSMISSION))))
+                sum = sum + lobes[i].f(wo, wi);
+        return sum;
+    }
+    Float pdf(V3 wo_w, V3 wi_w, uint8_t flags) const {                                       // :420-448
+        if (n == 0) return 0.0f;
+        V3 wo = world_to_local(wo_w), wi = world_to_local(wi_w);
+        if (wo.z == 0.0f) return 0.0f;
+        Float p = 0.0f;
+        int matching = 0;
+        for (int i = 0; i < n; ++i)
+            if (lobes[i].matches(flags)) { ++matching; p += lobes[i].pdf(wo, wi); }
+        return matching > 0 ? p / (Float)matching : 0.0f;
+    }
+    RGB sample_f(V3 wo_w, V3* wi_w, Float u0, Float u1, Float* pdf_out, uint8_t flags, uint8_t* sampled) const {   // :286-381
+        int matching = num_components(flags);
+        if (matching == 0) { *pdf_out = 0.0f; *sampled = 0; return rgb(0); }
+        int comp = std::min((int)std::floor(u0 * (Float)matching), matching - 1);
+        int count = comp, chosen = -1;
+        for (int i = 0; i < n; ++i)
+            if (lobes[i].matches(flags) && count-- == 0) { chosen = i; break; }
+        const Lobe& bx = lobes[chosen];
+        Float u0r = fmin_(kOneMinusEpsilon, u0 * (Float)matching - (Float)comp);
+        V3 wi{0, 0, 0};
+        V3 wo = world_to_local(wo_w);
+        if (wo.z == 0.0f) return rgb(0);
+        *pdf_out = 0.0f;
+        *sampled = bx.type;
+        RGB fv = bx.sample_f(wo, &wi, u0r, u1, pdf_out, sampled);
+        if (*pdf_out == 0.0f) { *sampled = 0; return rgb(0); }
+        *wi_w = local_to_world(wi);
+        if (!(bx.type & BSDF_SPECULAR) && matching > 1)
+            for (int i = 0; i < n; ++i)
+                if (i != chosen && lobes[i].matches(flags)) *pdf_out += lobes[i].pdf(wo, wi);
+        if (matching > 1) *pdf_out /= (Float)matching;
+        if (!(bx.type & BSDF_SPECULAR)) {
+            bool refl = dot(*wi_w, ng) * dot(wo_w, ng) > 0.0f;
+            fv = rgb(0);
+            for (int i = 0; i < n; ++i)
+                if (lobes[i].matches(flags) && ((refl && (lobes[i].type & BSDF_REFLECTION)) || (!refl && (lobes[i].type & BSDF_TRANSMISSION))))
+                    fv = fv + lobes[i].f(wo, wi);
+        }
+        return fv;
+    }
+};
+
+inline Float power_heuristic(Float f_pdf, Float g_pdf) {                                     // sampling.rs:306-313 (nf = ng = 1)
+    Float f = 1.0f * f_pdf, g = 1.0f * g_pdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// ---------------------------------------------------------------- interaction.rs SurfaceInteraction (subset)
+struct SurfaceInteraction {
+    V3 p, error, n, wo, dpdu;
+    uint32_t prim;
+};
+
+struct LightRt {
+    LightDesc d;
+    V3 p0, p1, p2;      // area: the emissive triangle
+    Float area;
+    RGB l() const { return {d.i[0], d.i[1], d.i[2]}; }
+    bool is_delta() const { return d.type == LIGHT_POINT; }                                  // light.rs:28-31, D24 FIX
+};
+
+struct MaterialRt {
+    MaterialDesc d;
+    Float alpha;        // plastic: roughness (remapped) — host-side, microfacet.rs:160-168
+};
+
+class Scene {
+public:
+    BVHAccel bvh;
+    std::vector<uint32_t> tri_material;
+    std::vector<MaterialRt> materials;
+    std::vector<LightRt> lights;
+    std::vector<int32_t> tri_light;
+    Distribution1D light_distrib;
+
+    void init(const Float* verts, uint64_t nv, const uint32_t* idx, uint64_t nt, const uint32_t* tri_mat, const MaterialDesc* mats,
+              uint32_t n_mats, const LightDesc* lts, uint32_t n_lights, int max_prims) {
+        bvh.build(verts, nv, idx, nt, max_prims);
+        tri_material.assign(tri_mat, tri_mat + nt);
+        materials.resize(n_mats);
+        for (uint32_t i = 0; i < n_mats; ++i) {
+            materials[i].d = mats[i];
+            materials[i].alpha = mats[i].remap_roughness ? roughness_to_alpha(mats[i].roughness) : mats[i].roughness;
+        }
+        tri_light.assign(nt, -1);
+        lights.resize(n_lights);
+        for (uint32_t i = 0; i < n_lights; ++i) {
+            lights[i].d = lts[i];
+            lights[i].area = 0;
+            if (lts[i].type == LIGHT_AREA) {
+                bvh.tri(lts[i].prim_id, &lights[i].p0, &lights[i].p1, &lights[i].p2);
+                lights[i].area = length(cross(lights[i].p1 - lights[i].p0, lights[i].p2 - lights[i].p0)) * 0.5f;   // triangle.rs:323-328
+                tri_light[lts[i].prim_id] = (int32_t)i;
+            }
+        }
+    }
+    // lightdistrib.rs:222-232 + integrator.rs:268-277
+    void set_light_strategy(int strategy) {
+        std::vector<Float> f(lights.size(), 1.0f);
+        if (strategy == LIGHTS_POWER && lights.size() != 1)
+            for (size_t i = 0; i < lights.size(); ++i) {
+                const LightRt& l = lights[i];
+                RGB power = l.is_delta() ? l.l() * (4.0f * kPi)                                              // point.rs:68-70
+                                         : l.l() * ((l.d.two_sided ? 2.0f : 1.0f) * l.area * kPi);            // diffuse.rs:83-85
+                f[i] = y_value(power);
+            }
+        light_distrib.init(f);
+    }
+
+    // Scene::intersect -> SurfaceInteraction (triangle.rs:182-250; D59: shading = geometric)
+    bool intersect(Ray& ray, SurfaceInteraction* si) const {
+        Hit h;
+        Float b0;
+        if (!bvh.intersect(ray, &h, &b0, nullptr)) return false;
+        V3 p0, p1, p2;
+        bvh.tri(h.prim_id, &p0, &p1, &p2);
+        Interaction it = triangle_interaction(p0, p1, p2, b0, h.b1, h.b2);
+        si->p = it.p; si->error = it.error; si->n = it.n;
+        si->wo = -ray.d;
+        V3 du, dv;
+        triangle_frame(p0, p1, p2, &du, &dv);
+        si->dpdu = du;
+        si->prim = h.prim_id;
+        return true;
+    }
+    RGB le(const SurfaceInteraction& si, V3 w) const {                                          // interaction.rs:387-395 + diffuse.rs:150-156
+        int32_t li = tri_light[si.prim];
+        if (li < 0) return rgb(0);
+        const LightRt& l = lights[li];
+        return (l.d.two_sided || dot(si.n, w) > 0.0f) ? l.l() : rgb(0);
+    }
+    // Appendix B: matte / plastic / glass -> BSDF
+    BSDF make_bsdf(const SurfaceInteraction& si) const {
+        const MaterialRt& m = materials[tri_material[si.prim]];
+        BSDF b;
+        b.eta = m.d.type == MAT_GLASS ? m.d.eta : 1.0f;
+        b.ns = si.n; b.ng = si.n;                                                               // reflection.rs:220-234
+        b.ss = normalize(si.dpdu);
+        b.ts = cross(b.ns, b.ss);
+        RGB kd{m.d.kd[0], m.d.kd[1], m.d.kd[2]}, ks{m.d.ks[0], m.d.ks[1], m.d.ks[2]};
+        RGB kr{m.d.kr[0], m.d.kr[1], m.d.kr[2]}, kt{m.d.kt[0], m.d.kt[1], m.d.kt[2]};
+        if (m.d.type == MAT_MATTE || m.d.type == MAT_PLASTIC) {
+            if (!is_black(kd)) b.lobes[b.n++] = Lobe{LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, kd, rgb(0), 0, 1, 1};
+            if (m.d.type == MAT_PLASTIC && !is_black(ks))
+                b.lobes[b.n++] = Lobe{LOBE_MICROFACET, BSDF_REFLECTION | BSDF_GLOSSY, ks, rgb(0), m.alpha, 1.5f, 1.0f};
+        } else if (!(is_black(kr) && is_black(kt))) {
+            b.lobes[b.n++] = Lobe{LOBE_FRESNEL_SPECULAR, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, kr, kt, 0, 1.0f, m.d.eta};
+        }
+        return b;
+    }
+};
+
+struct Sampler {          // RandomSampler (samplers/random.rs:29-56): every dimension straight from PCG32
+    RNG rng;
+    Float get_1d() { return rng.uniform_float(); }
+    void get_2d(Float* a, Float* b) { *a = rng.uniform_float(); *b = rng.uniform_float(); }   // x then y
+};
+
+// integrator.rs:136-266 (handle_media = false, specular = false)
+inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, const BSDF& bsdf, Float us0, Float us1, const LightRt& light,
+                           uint32_t light_index, Float ul0, Float ul1) {
+    const uint8_t flags = BSDF_ALL & ~BSDF_SPECULAR;                                            // D23 FIX
+    RGB ld = rgb(0);
+    V3 wi{0, 0, 0};
+    Float light_pdf = 0.0f, scattering_pdf = 0.0f;
+    RGB li = rgb(0);
+    Ray shadow{};
+    // ---- Light::sample_li ----
+    if (light.is_delta()) {                                                                    // point.rs:47-66
+        V3 pl{light.d.p[0], light.d.p[1], light.d.p[2]};
+        wi = normalize(pl - it.p);
+        light_pdf = 1.0f;
+        li = light.l() / length_squared(pl - it.p);
+        // VisibilityTester: spawn_ray_to(&BaseInteraction) with a bare point (interaction.rs:146-153)
+        V3 origin = offset_ray_origin(it.p, it.error, it.n, pl - it.p);
+        V3 target = offset_ray_origin(pl, V3{0, 0, 0}, V3{0, 0, 0}, origin - pl);
+        shadow = Ray{origin, 1.0f - kShadowEpsilon, target - origin, 0.0f};
+    } else {                                                                                   // diffuse.rs:60-81 + shape.rs:38-53 + triangle.rs:330-348
+        Float su0 = std::sqrt(ul0);
+        Float b0 = 1.0f - su0, b1 = ul1 * su0;                                                 // sampling.rs:275-278
+        V3 ps = (light.p0 * b0 + light.p1 * b1) + light.p2 * ((1.0f - b0) - b1);
+        V3 ns = normalize(cross(light.p1 - light.p0, light.p2 - light.p0));
+        V3 pe = ((vabs(light.p0 * b0) + vabs(light.p1 * b1)) + vabs(light.p2 * ((1.0f - b0) - b1))) * gamma(6.0f);
+        Float pdf = 1.0f / light.area;
+        V3 w = ps - it.p;
+        if (length_squared(w) == 0.0f) pdf = 0.0f;
+        else {
+            w = normalize(w);
+            pdf *= length_squared(it.p - ps) / std::fabs(dot(ns, -w));
+            if (std::isinf(pdf)) pdf = 0.0f;
+        }
+        light_pdf = pdf;
+        if (pdf == 0.0f || length_squared(ps - it.p) == 0.0f) { light_pdf = 0.0f; li = rgb(0); }
+        else {
+            wi = normalize(ps - it.p);
+            li = (light.d.two_sided || dot(ns, -wi) > 0.0f) ? light.l() : rgb(0);             // D55 FIX
+            V3 origin = offset_ray_origin(it.p, it.error, it.n, ps - it.p);
+            V3 target = offset_ray_origin(ps, pe, ns, origin - ps);
+            shadow = Ray{origin, 1.0f - kShadowEpsilon, target - origin, 0.0f};
+        }
+    }
+    if (light_pdf > 0.0f && !is_black(li)) {
+        scattering_pdf = bsdf.pdf(it.wo, wi, flags);
+        RGB f = bsdf.f(it.wo, wi, flags) * std::fabs(dot(wi, bsdf.ns));
+        if (!is_black(f)) {
+            if (scene.bvh.intersect_p(shadow, nullptr)) li = rgb(0);                           // light.rs:126-135, D25 FIX
+            if (!is_black(li)) {
+                if (light.is_delta()) ld = ld + li * f / light_pdf;
+                else ld = ld + li * f * power_heuristic(light_pdf, scattering_pdf) / light_pdf;
+            }
+        }
+    }
+    // ---- BSDF sampling with MIS ----
+    if (!light.is_delta()) {
+        uint8_t sampled = 0;
+        RGB f = bsdf.sample_f(it.wo, &wi, us0, us1, &scattering_pdf, flags, &sampled);
+        f = f * std::fabs(dot(wi, bsdf.ns));
+        bool sampled_specular = (sampled & BSDF_SPECULAR) != 0;
+        if (!is_black(f) && scattering_pdf > 0.0f) {
+            Float weight = 1.0f;
+            Interaction base{it.p, it.error, it.n};
+            if (!sampled_specular) {
+                // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): intersect the light's own triangle
+                Ray r = spawn_ray(base, wi);
+                TriHit th = triangle_intersect_test(light.p0, light.p1, light.p2, r);
+                V3 du, dv;
+                if (!th.hit || !triangle_frame(light.p0, light.p1, light.p2, &du, &dv)) return ld;
+                Interaction li_it = triangle_interaction(light.p0, light.p1, light.p2, th.b0, th.b1, th.b2);
+                Float lp = length_squared(it.p - li_it.p) / (std::fabs(dot(li_it.n, -wi)) * light.area);
+                if (std::isinf(lp)) lp = 0.0f;
+                light_pdf = lp;
+                if (light_pdf == 0.0f) return ld;
+                weight = power_heuristic(scattering_pdf, light_pdf);
+            }
+            Ray ray = spawn_ray(base, wi);
+            SurfaceInteraction light_isect;
+            RGB lmis = rgb(0);
+            if (scene.intersect(ray, &light_isect)) {
+                if (scene.tri_light[light_isect.prim] == (int32_t)light_index) lmis = scene.le(light_isect, -wi);   // D56 FIX
+            }
+            if (!is_black(lmis)) ld = ld + lmis * f * rgb(1.0f) * weight / scattering_pdf;
+        }
+    }
+    return ld;
+}
+
+// integrator.rs:92-134
+inline RGB uniform_sample_one_light(const Scene& scene, const SurfaceInteraction& it, const BSDF& bsdf, Sampler& s) {
+    if (scene.lights.empty()) return rgb(0);
+    Float light_pdf;
+    size_t num = scene.light_distrib.sample_discrete(s.get_1d(), &light_pdf);
+    if (light_pdf == 0.0f) return rgb(0);
+    Float ul0, ul1, us0, us1;
+    s.get_2d(&ul0, &ul1);
+    s.get_2d(&us0, &us1);
+    return estimate_direct(scene, it, bsdf, us0, us1, scene.lights[num], (uint32_t)num, ul0, ul1) / light_pdf;
+}
+
+struct PathCounters {
+    uint64_t camera_samples = 0, extend_rays = 0, shadow_rays = 0, mis_rays = 0;
+};
+
+// path.rs:65-213 (BSSRDF branch dead: no subsurface material exists)
+inline RGB path_li(const Scene& scene, Ray ray, Sampler& s, int max_depth, Float rr_threshold) {
+    RGB l = rgb(0), beta = rgb(1);
+    bool specular_bounce = false;
+    int bounces = 0;
+    Float eta_scale = 1.0f;
+    for (;;) {
+        SurfaceInteraction isect;
+        bool found = scene.intersect(ray, &isect);
+        if (bounces == 0 || specular_bounce)
+            if (found) l = l + beta * scene.le(isect, -ray.d);
+        if (!found || bounces >= max_depth) break;
+        BSDF bsdf = scene.make_bsdf(isect);
+        if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) l = l + beta * uniform_sample_one_light(scene, isect, bsdf, s);
+        V3 wo = -ray.d, wi{0, 0, 0};
+        Float pdf = 0.0f, u0, u1;
+        uint8_t flags = 0;
+        s.get_2d(&u0, &u1);
+        RGB f = bsdf.sample_f(wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
+        if (is_black(f) || pdf == 0.0f) break;
+        beta = beta * (f * (std::fabs(dot(wi, bsdf.ns)) / pdf));
+        specular_bounce = (flags & BSDF_SPECULAR) != 0;
+        if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+            Float eta = bsdf.eta;
+            eta_scale *= (dot(wo, isect.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta);
+        }
+        ray = spawn_ray(Interaction{isect.p, isect.error, isect.n}, wi);
+        RGB rr_beta = beta * eta_scale;
+        if (max_component_value(rr_beta) < rr_threshold && bounces > 3) {
+            Float q = fmin_(1.0f - max_component_value(rr_beta), 0.05f);                        // D27 KEEP
+            if (s.get_1d() < q) break;
+            beta = beta / (1.0f - q);
+        }
+        bounces += 1;
+    }
+    return l;
+}
+
+// ---------------------------------------------------------------- film.rs
+struct Film {
+    FilmDesc d;
+    Float table[16 * 16];
+    int sb_x0, sb_y0, sb_x1, sb_y1;          // sample bounds (D42 FIX)
+    void init(const FilmDesc& desc) {
+        d = desc;
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) {
+                Float px = ((Float)x + 0.5f) * d.radius_x / 16.0f, py = ((Float)y + 0.5f) * d.radius_y / 16.0f;   // film.rs:53-63
+                table[y * 16 + x] = evaluate(px, py);
+            }
+        sb_x0 = (int)std::floor(0.0f + 0.5f - d.radius_x);
+        sb_y0 = (int)std::floor(0.0f + 0.5f - d.radius_y);
+        sb_x1 = (int)std::ceil((Float)d.res_x - 0.5f + d.radius_x);
+        sb_y1 = (int)std::ceil((Float)d.res_y - 0.5f + d.radius_y);
+    }
+    Float gaussian(Float v, Float expv) const { return fmax_(std::exp(-d.gaussian_alpha * v * v) - expv, 0.0f); }   // gaussian.rs:29-31
+    Float evaluate(Float x, Float y) const {
+        if (d.filter == FILTER_BOX) return 1.0f;                                               // boxf.rs:26-28
+        Float ex = std::exp(-d.gaussian_alpha * d.radius_x * d.radius_x), ey = std::exp(-d.gaussian_alpha * d.radius_y * d.radius_y);
+        return gaussian(x, ex) * gaussian(y, ey);
+    }
+    // film.rs:252-295 FilmTile::add_sample footprint + weights (D43, D44 FIX); calls fn(px, py, filter_weight)
+    template <class F>
+    void footprint(Float pfx, Float pfy, F&& fn) const {
+        Float dx = pfx - 0.5f, dy = pfy - 0.5f;
+        int x0 = (int)std::ceil(dx - d.radius_x), y0 = (int)std::ceil(dy - d.radius_y);
+        int x1 = (int)std::floor(dx + d.radius_x) + 1, y1 = (int)std::floor(dy + d.radius_y) + 1;
+        x0 = std::max(x0, 0); y0 = std::max(y0, 0);
+        x1 = std::min(x1, d.res_x); y1 = std::min(y1, d.res_y);
+        for (int y = y0; y < y1; ++y) {
+            Float fy = std::fabs(((Float)y - dy) * (1.0f / d.radius_y) * 16.0f);
+            int iy = std::min(15, (int)std::floor(fy));
+            for (int x = x0; x < x1; ++x) {
+                Float fx = std::fabs(((Float)x - dx) * (1.0f / d.radius_x) * 16.0f);
+                int ix = std::min(15, (int)std::floor(fx));
+                fn(x, y, table[iy * 16 + ix]);
+            }
+        }
+    }
+};
+
+struct Stray {
+    uint64_t order;       // (source sample-bounds pixel index) * spp + sample
+    int x, y;
+    RGB c;
+    Float w;
+};
+
+// SamplerIntegrator::render (integrator.rs:399-480).
+//  mode 1 = per-(pixel,sample) sampler streams: RNG::new(((y-sb_y0)*W_sb + (x-sb_x0))*spp + s); film accumulation order
+//           per target pixel: its own samples in sample order, then contributions from other pixels' samples ordered
+//           by (source pixel, sample).  This is the mode the GPU implements.
+//  mode 0 = the reference's order: one sampler stream per 16x16 tile (seed = tile.y*n_tiles.x + tile.x), consumed
+//           sequentially over pixels, samples and path vertices.
+// out_xyzw: float4 {X, Y, Z, filter_weight_sum} per pixel, ADDED to the buffer.  Returns seconds.
+inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& fd, const PathDesc& pd, int mode, int threads, Float* out_xyzw) {
+    Camera cam;
+    cam.init({cd.pos[0], cd.pos[1], cd.pos[2]}, {cd.look[0], cd.look[1], cd.look[2]}, {cd.up[0], cd.up[1], cd.up[2]}, cd.fov, cd.res_x, cd.res_y);
+    Film film;
+    film.init(fd);
+    const int W = film.sb_x1 - film.sb_x0, H = film.sb_y1 - film.sb_y0;
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
+    const size_t npix = (size_t)fd.res_x * fd.res_y;
+    std::vector<RGB> acc(npix, rgb(0));
+    std::vector<Float> wsum(npix, 0.0f);
+    std::vector<std::vector<Stray>> strays(threads);
+    std::atomic<int> next{0};
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int tid) {
+        for (;;) {
+            int t = next.fetch_add(1);
+            if (t >= tiles_x * tiles_y) break;
+            int tx = t % tiles_x, ty = t / tiles_x;
+            Sampler tile_sampler;
+            tile_sampler.rng.set_sequence((uint64_t)(ty * tiles_x + tx));                       // integrator.rs:414-415
+            int x0 = film.sb_x0 + tx * 16, x1 = std::min(x0 + 16, film.sb_x1);
+            int y0 = film.sb_y0 + ty * 16, y1 = std::min(y0 + 16, film.sb_y1);
+            // mode 0 accumulates into a tile-local buffer first (FilmTile), merged below
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x)
+                    for (int s = pd.sample_begin; s < pd.sample_end; ++s) {
+                        Sampler own;
+                        uint64_t order = ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)) * (uint64_t)pd.spp + (uint64_t)s;
+                        if (mode == 1) own.rng.set_sequence(order);
+                        Sampler& smp = mode == 1 ? own : tile_sampler;
+                        Float u0, u1, ut, l0, l1;
+                        smp.get_2d(&u0, &u1);                                                   // sampler.rs:27-33
+                        ut = smp.get_1d();
+                        smp.get_2d(&l0, &l1);
+                        (void)ut; (void)l0; (void)l1;
+                        Float pfx = (Float)x + u0, pfy = (Float)y + u1;
+                        Ray ray = cam.generate_ray(pfx, pfy);
+                        RGB L = path_li(scene, ray, smp, pd.max_depth, pd.rr_threshold);
+                        if (has_nans(L) || y_value(L) < -1e-5f || std::isinf(y_value(L))) L = rgb(0);   // D22 FIX
+                        film.footprint(pfx, pfy, [&](int px, int py, Float fw) {
+                            RGB c = L * 1.0f * fw;                                              // l * sample_weight * filter_weight
+                            if (mode == 1 && !(px == x && py == y)) { strays[tid].push_back(Stray{order, px, py, c, fw}); return; }
+                            if (mode == 0 && (px < x0 || px >= x1 || py < y0 || py >= y1)) { strays[tid].push_back(Stray{order, px, py, c, fw}); return; }
+                            size_t o = (size_t)py * fd.res_x + px;
+                            acc[o] = acc[o] + c;
+                            wsum[o] += fw;
+                        });
+                    }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < threads; ++i) pool.emplace_back(work, i);
+    work(0);
+    for (auto& t : pool) t.join();
+    std::vector<Stray> all;
+    for (auto& v : strays) all.insert(all.end(), v.begin(), v.end());
+    std::sort(all.begin(), all.end(), [](const Stray& a, const Stray& b) {
+        if (a.order != b.order) return a.order < b.order;
+        if (a.y != b.y) return a.y < b.y;
+        return a.x < b.x;
+    });
+    for (const Stray& s : all) {
+        size_t o = (size_t)s.y * fd.res_x + s.x;
+        acc[o] = acc[o] + s.c;
+        wsum[o] += s.w;
+    }
+    for (size_t i = 0; i < npix; ++i) {                                                        // Film::merge_film_tile :111-123
+        Float xyz[3];
+        rgb_to_xyz(acc[i], xyz);
+        out_xyzw[4 * i] += xyz[0]; out_xyzw[4 * i + 1] += xyz[1]; out_xyzw[4 * i + 2] += xyz[2];
+        out_xyzw[4 * i + 3] += wsum[i];
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Film::write_image (film.rs:153-178): XYZ -> RGB, / weight, clamp >= 0, * scale
+inline void resolve_rgb(const Float* xyzw, size_t npix, Float scale, Float* out_rgb) {
+    for (size_t i = 0; i < npix; ++i) {
+        Float c[3];
+        xyz_to_rgb(xyzw + 4 * i, c);
+        Float w = xyzw[4 * i + 3];
+        if (w != 0.0f) {
+            Float inv = 1.0f / w;
+            c[0] = fmax_(c[0] * inv, 0.0f); c[1] = fmax_(c[1] * inv, 0.0f); c[2] = fmax_(c[2] * inv, 0.0f);
+        }
+        out_rgb[3 * i] = c[0] * scale; out_rgb[3 * i + 1] = c[1] * scale; out_rgb[3 * i + 2] = c[2] * scale;
+    }
+}
+
+}  // namespace orc

@@ -1,0 +1,173 @@
+"""ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes wrapper over the path-tracer half of oracle/liboracle.so (oracle_path.hpp): PathIntegrator::li, Film,
+SamplerIntegrator::render restated on the CPU.  Parity unpinned (see oracle_core.hpp).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import oracle as O
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("roughness", C.c_float),
+                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("p", C.c_float * 3), ("i", C.c_float * 3), ("prim_id", C.c_uint32),
+                ("two_sided", C.c_int32)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
+                ("res_x", C.c_int32), ("res_y", C.c_int32)]
+
+
+class FilmDesc(C.Structure):
+    _fields_ = [("res_x", C.c_int32), ("res_y", C.c_int32), ("filter", C.c_int32), ("radius_x", C.c_float),
+                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float)]
+
+
+class PathDesc(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32)]
+
+
+_MAT = {"matte": 0, "plastic": 1, "glass": 2}
+_STRAT = {"uniform": 0, "power": 1}
+_FILTER = {"box": 0, "gaussian": 1}
+
+
+def material(d):
+    m = Material()
+    m.type = _MAT[d["type"]]
+    m.kd[:] = d.get("kd", (0, 0, 0))
+    m.ks[:] = d.get("ks", (0, 0, 0))
+    m.roughness = d.get("roughness", 0.1)
+    m.remap_roughness = int(d.get("remap", True))
+    m.kr[:] = d.get("kr", (0, 0, 0))
+    m.kt[:] = d.get("kt", (0, 0, 0))
+    m.eta = d.get("eta", 1.5)
+    return m
+
+
+def light(d):
+    l = Light()
+    if d["type"] == "point":
+        l.type = 0
+        l.p[:] = d["p"]
+        l.i[:] = d["I"]
+    else:
+        l.type = 1
+        l.i[:] = d["L"]
+        l.prim_id = d["prim"]
+        l.two_sided = int(d.get("two_sided", False))
+    return l
+
+
+def camera_desc(cam):
+    c = CameraDesc()
+    c.pos[:] = cam["pos"]
+    c.look[:] = cam["look"]
+    c.up[:] = cam["up"]
+    c.fov = cam["fov"]
+    c.res_x, c.res_y = cam["res"]
+    return c
+
+
+def film_desc(res, filt="box", radius=(0.5, 0.5), alpha=2.0):
+    f = FilmDesc()
+    f.res_x, f.res_y = res
+    f.filter = _FILTER[filt]
+    f.radius_x, f.radius_y = radius
+    f.gaussian_alpha = alpha
+    return f
+
+
+def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None):
+    p = PathDesc()
+    p.max_depth = max_depth
+    p.rr_threshold = rr_threshold
+    p.light_strategy = _STRAT[light_strategy]
+    p.spp = spp
+    p.sample_begin = sample_begin
+    p.sample_end = spp if sample_end is None else sample_end
+    return p
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    def __init__(self, sc, max_prims_in_node=4):
+        L = O.lib()
+        self.verts = np.ascontiguousarray(sc["verts"], dtype=np.float32).reshape(-1, 3)
+        self.idx = np.ascontiguousarray(sc["idx"], dtype=np.uint32).reshape(-1, 3)
+        tm = np.ascontiguousarray(sc["tri_material"], dtype=np.uint32)
+        mats = (Material * len(sc["materials"]))(*[material(m) for m in sc["materials"]])
+        lts = (Light * max(1, len(sc["lights"])))(*[light(l) for l in sc["lights"]])
+        self.h = L.orc_scene_create(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), _p(tm),
+                                    C.cast(mats, C.c_void_p), len(sc["materials"]), C.cast(lts, C.c_void_p),
+                                    len(sc["lights"]), max_prims_in_node)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            O.lib().orc_scene_free(self.h)
+            self.h = None
+
+    def bvh(self):
+        return O.BVHAccel(None, None, _handle=O.lib().orc_scene_bvh(self.h))
+
+    def render(self, cam, film, path, mode=1, threads=0, out=None):
+        """Returns (xyzw [H,W,4] accumulators, seconds)."""
+        cd, fd = camera_desc(cam), film
+        if out is None:
+            out = np.zeros((fd.res_y, fd.res_x, 4), dtype=np.float32)
+        dt = O.lib().orc_render(self.h, C.byref(cd), C.byref(fd), C.byref(path), mode, threads, _p(out))
+        return out, dt
+
+    def path_li(self, cam, film, path, pixel_xy, sample_index):
+        pixel_xy = np.ascontiguousarray(pixel_xy, dtype=np.int32).reshape(-1, 2)
+        sample_index = np.ascontiguousarray(sample_index, dtype=np.uint32)
+        n = len(pixel_xy)
+        L_rgb = np.empty((n, 3), dtype=np.float32)
+        pf = np.empty((n, 2), dtype=np.float32)
+        cd = camera_desc(cam)
+        O.lib().orc_path_li(self.h, C.byref(cd), C.byref(film), C.byref(path), _p(pixel_xy), _p(sample_index), n,
+                            _p(L_rgb), _p(pf))
+        return L_rgb, pf
+
+
+def resolve_rgb(xyzw, scale=1.0):
+    xyzw = np.ascontiguousarray(xyzw, dtype=np.float32)
+    out = np.empty(xyzw.shape[:-1] + (3,), dtype=np.float32)
+    O.lib().orc_resolve_rgb(_p(xyzw), xyzw.size // 4, scale, _p(out))
+    return out
+
+
+def film_add_samples(film, p_film, L_rgb, weight):
+    p_film = np.ascontiguousarray(p_film, dtype=np.float32)
+    L_rgb = np.ascontiguousarray(L_rgb, dtype=np.float32)
+    weight = np.ascontiguousarray(weight, dtype=np.float32)
+    out = np.zeros((film.res_y, film.res_x, 4), dtype=np.float32)
+    O.lib().orc_film_add_samples(C.byref(film), _p(p_film), _p(L_rgb), _p(weight), len(weight), _p(out))
+    return out
+
+
+def roughness_to_alpha(r):
+    return np.float32(O.lib().orc_roughness_to_alpha(r))
+
+
+def sincos(x):
+    s, c = C.c_float(), C.c_float()
+    O.lib().orc_sincos(x, C.byref(s), C.byref(c))
+    return np.float32(s.value), np.float32(c.value)
+
+
+def film_table(film):
+    t = np.empty(256, dtype=np.float32)
+    O.lib().orc_film_table(C.byref(film), _p(t))
+    return t

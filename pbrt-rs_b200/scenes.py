@@ -138,3 +138,96 @@ def random_soup(n_tris, seed=0, extent=10.0, size=1.0):
     v = (c + rng.uniform(-size, size, size=(n_tris, 3, 3))).astype(np.float32).reshape(-1, 3)
     idx = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
     return v, idx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Path-traced scenes (BASELINE configs 1, 3, 4).  Materials / lights are plain dicts so that both the CUDA binding and
+# the oracle binding can build their own structs from them.
+# ---------------------------------------------------------------------------------------------------------------
+def _quad(a, b, c, d):
+    """Quad a,b,c,d -> two triangles (a,b,c), (a,c,d); geometric normal = normalize((a-c) x (b-c))."""
+    return np.array([a, b, c, d], dtype=np.float64), np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int64)
+
+
+def _append(meshes, mats, quad, mat):
+    meshes.append((quad[0].astype(np.float32), quad[1].astype(np.uint32)))
+    mats.extend([mat, mat])
+
+
+WHITE, RED, GREEN = (0.725, 0.71, 0.68), (0.63, 0.065, 0.05), (0.14, 0.45, 0.091)
+
+
+def cornell_box(light_y=548.3, blocks=True):
+    """Classic Cornell box data (555-unit room): 5 walls + ceiling light + short and tall block = 32 triangles."""
+    meshes, tm = [], []
+    W, R, G = 0, 1, 2
+    _append(meshes, tm, _quad((552.8, 0, 0), (0, 0, 0), (0, 0, 559.2), (549.6, 0, 559.2)), W)                    # floor
+    _append(meshes, tm, _quad((556, 548.8, 0), (556, 548.8, 559.2), (0, 548.8, 559.2), (0, 548.8, 0)), W)       # ceiling
+    _append(meshes, tm, _quad((549.6, 0, 559.2), (0, 0, 559.2), (0, 548.8, 559.2), (556, 548.8, 559.2)), W)     # back
+    _append(meshes, tm, _quad((0, 0, 559.2), (0, 0, 0), (0, 548.8, 0), (0, 548.8, 559.2)), G)                    # right
+    _append(meshes, tm, _quad((552.8, 0, 0), (549.6, 0, 559.2), (556, 548.8, 559.2), (556, 548.8, 0)), R)       # left
+    light_first = 2 * len(meshes)
+    _append(meshes, tm, _quad((343, light_y, 227), (343, light_y, 332), (213, light_y, 332), (213, light_y, 227)), W)
+    if blocks:
+        short = [((130, 165, 65), (82, 165, 225), (240, 165, 272), (290, 165, 114)),
+                 ((290, 0, 114), (290, 165, 114), (240, 165, 272), (240, 0, 272)),
+                 ((130, 0, 65), (130, 165, 65), (290, 165, 114), (290, 0, 114)),
+                 ((82, 0, 225), (82, 165, 225), (130, 165, 65), (130, 0, 65)),
+                 ((240, 0, 272), (240, 165, 272), (82, 165, 225), (82, 0, 225))]
+        tall = [((423, 330, 247), (265, 330, 296), (314, 330, 456), (472, 330, 406)),
+                ((423, 0, 247), (423, 330, 247), (472, 330, 406), (472, 0, 406)),
+                ((472, 0, 406), (472, 330, 406), (314, 330, 456), (314, 0, 456)),
+                ((314, 0, 456), (314, 330, 456), (265, 330, 296), (265, 0, 296)),
+                ((265, 0, 296), (265, 330, 296), (423, 330, 247), (423, 0, 247))]
+        for q in short + tall:
+            _append(meshes, tm, _quad(*q), W)
+    verts, idx = merge(*meshes)
+    materials = [dict(type="matte", kd=WHITE), dict(type="matte", kd=RED), dict(type="matte", kd=GREEN)]
+    lights = [dict(type="area", prim=light_first, L=(17.0, 12.0, 4.0), two_sided=False),
+              dict(type="area", prim=light_first + 1, L=(17.0, 12.0, 4.0), two_sided=False)]
+    return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=materials, lights=lights)
+
+
+C2_CAMERA = dict(pos=(278.0, 273.0, -800.0), look=(278.0, 273.0, 0.0), up=(0.0, 1.0, 0.0), fov=39.3, res=(512, 512))
+C2_PATH = dict(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=64)
+
+
+def scene_c2():
+    """C2: Cornell box, matte walls, diffuse quad light, PathIntegrator maxdepth=5, 512x512 @ 64 spp."""
+    return cornell_box()
+
+
+def scene_c4(n_theta=158, n_phi=316):
+    """C4: Cornell room + three tessellated spheres (matte / plastic / glass), ceiling area light + point light."""
+    room = cornell_box(blocks=False)
+    meshes = [(room["verts"], room["idx"])]
+    tm = list(room["tri_material"])
+    for k, (cx, mat) in enumerate(((140.0, 3), (278.0, 4), (416.0, 5))):
+        v, i = uv_sphere(radius=90.0, center=(cx, 90.0 + 40.0 * (k == 1), 280.0 - 60.0 * (k == 1)), n_theta=n_theta, n_phi=n_phi)
+        meshes.append((v, i))
+        tm.extend([mat] * len(i))
+    verts, idx = merge(*meshes)
+    materials = room["materials"] + [dict(type="matte", kd=(0.5, 0.5, 0.8)),
+                                     dict(type="plastic", kd=(0.25, 0.25, 0.25), ks=(0.25, 0.25, 0.25), roughness=0.1, remap=True),
+                                     dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5)]
+    lights = room["lights"] + [dict(type="point", p=(278.0, 400.0, 100.0), I=(40000.0, 40000.0, 40000.0))]
+    return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=materials, lights=lights)
+
+
+C4_CAMERA = dict(pos=(278.0, 273.0, -800.0), look=(278.0, 273.0, 0.0), up=(0.0, 1.0, 0.0), fov=39.3, res=(1920, 1080))
+C4_PATH = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", spp=256)
+C5_CAMERA = dict(C4_CAMERA, res=(3840, 2160))
+C5_PATH = dict(C4_PATH, spp=1024)
+
+
+def furnace_box(L=0.5, kd=0.5):
+    """White furnace: closed matte cube whose six walls all emit L (two-sided) -> radiance L / (1 - kd) everywhere."""
+    c = [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)]
+    faces = [(0, 1, 2, 3), (5, 4, 7, 6), (4, 0, 3, 7), (1, 5, 6, 2), (3, 2, 6, 7), (4, 5, 1, 0)]
+    meshes, tm = [], []
+    for f in faces:
+        _append(meshes, tm, _quad(*[c[k] for k in f]), 0)
+    verts, idx = merge(*meshes)
+    lights = [dict(type="area", prim=k, L=(L, L, L), two_sided=True) for k in range(len(idx))]
+    return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=[dict(type="matte", kd=(kd, kd, kd))],
+                lights=lights)
