@@ -318,6 +318,132 @@ class PerspectiveCamera:
         check(lib().pb2_camera_primary_rays_device(C.byref(self.desc), d_rays, stream))
 
 
+_MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS}
+_STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER}
+_FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN}
+
+
+def material_from_dict(d):
+    if d["type"] == "matte":
+        return matte(d["kd"])
+    if d["type"] == "plastic":
+        return plastic(d["kd"], d["ks"], d.get("roughness", 0.1), d.get("remap", True))
+    return glass(d.get("kr", (1, 1, 1)), d.get("kt", (1, 1, 1)), d.get("eta", 1.5))
+
+
+def light_from_dict(d):
+    if d["type"] == "point":
+        return point_light(d["p"], d["I"])
+    return area_light(d["prim"], d["L"], d.get("two_sided", False))
+
+
+def scene_from_dict(sc):
+    """Scene from the plain-dict description the generators in scenes.py return."""
+    return Scene(sc["verts"], sc["idx"], sc["tri_material"], [material_from_dict(m) for m in sc["materials"]],
+                 [light_from_dict(l) for l in sc["lights"]])
+
+
+class Film:
+    """Mirror of src/core/film.rs Film (+ FilmTile::add_sample), accumulators resident on the device."""
+
+    def __init__(self, res, filter="box", radius=(0.5, 0.5), alpha=2.0):
+        self.desc = FilmDesc()
+        self.desc.res_x, self.desc.res_y = res
+        self.desc.filter = _FILTER[filter]
+        self.desc.radius_x, self.desc.radius_y = radius
+        self.desc.gaussian_alpha = alpha
+        self.res = tuple(res)
+        self.h = C.c_void_p()
+        check(lib().pb2_film_create(C.byref(self.desc), C.byref(self.h)))
+
+    def destroy(self):
+        if self.h:
+            lib().pb2_film_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def clear(self):
+        check(lib().pb2_film_clear(self.h))
+
+    def add_samples(self, p_film, L_rgb, weight):
+        p_film, L_rgb, weight = _f32(p_film), _f32(L_rgb), _f32(weight)
+        check(lib().pb2_film_add_samples(self.h, _p(p_film), _p(L_rgb), _p(weight), len(weight)))
+
+    def read_xyzw(self):
+        out = np.empty((self.res[1], self.res[0], 4), dtype=np.float32)
+        check(lib().pb2_film_read_xyzw(self.h, _p(out)))
+        return out
+
+    def resolve_rgb(self, scale=1.0):
+        out = np.empty((self.res[1], self.res[0], 3), dtype=np.float32)
+        check(lib().pb2_film_resolve_rgb(self.h, scale, _p(out)))
+        return out
+
+    def device_ptr(self):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        check(lib().pb2_film_device_ptr(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def reduce(self, root=0, stream=None):
+        check(lib().pb2_film_reduce(self.h, root, stream))
+
+
+class PathIntegrator:
+    """Mirror of src/integrators/path.rs PathIntegrator + SamplerIntegrator::render (RandomSampler streams per sample)."""
+
+    def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1):
+        self.accel, self.camera = accel, camera
+        self.desc = PathDesc()
+        self.desc.max_depth = max_depth
+        self.desc.rr_threshold = rr_threshold
+        self.desc.light_strategy = _STRATEGY[light_strategy]
+        self.desc.spp = spp
+        self.desc.sample_begin, self.desc.sample_end = 0, spp
+
+    def render(self, film, sample_begin=0, sample_end=None, stream=None):
+        """Integrator::render: accumulates sample indices [sample_begin, sample_end) of every pixel into `film`."""
+        self.desc.sample_begin = sample_begin
+        self.desc.sample_end = self.desc.spp if sample_end is None else sample_end
+        check(lib().pb2_render_path(self.accel.h, C.byref(self.camera.desc), C.byref(self.desc), film.h, stream))
+
+    def li(self, pixel_xy, sample_index):
+        """PathIntegrator::li per explicit (pixel, sample) -> (L_rgb [n,3], p_film [n,2])."""
+        pixel_xy = np.ascontiguousarray(pixel_xy, dtype=np.uint32).reshape(-1, 2)
+        sample_index = np.ascontiguousarray(sample_index, dtype=np.uint32)
+        n = len(sample_index)
+        L = np.empty((n, 3), dtype=np.float32)
+        pf = np.empty((n, 2), dtype=np.float32)
+        self.desc.sample_begin, self.desc.sample_end = 0, self.desc.spp
+        check(lib().pb2_path_li(self.accel.h, C.byref(self.camera.desc), C.byref(self.desc), _p(pixel_xy), _p(sample_index), n,
+                                _p(L), _p(pf)))
+        return L, pf
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().pb2_render_counters(self.accel.h, _p(out)))
+        return dict(camera_samples=int(out[0]), extend_rays=int(out[1]), shadow_rays=int(out[2]), mis_rays=int(out[3]),
+                    kernel_launches=int(out[4]), stray_overflow=int(out[5]))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().pb2_nccl_unique_id(buf))
+    return buf.raw
+
+
+def nccl_init(unique_id, rank, n_ranks):
+    check(lib().pb2_nccl_init(C.create_string_buffer(unique_id, 128), rank, n_ranks))
+
+
+def nccl_shutdown():
+    check(lib().pb2_nccl_shutdown())
+
+
 def rng_uniform_floats(first_sequence, n_sequences, n_per):
     out = np.empty((n_sequences, n_per), dtype=np.float32)
     check(lib().pb2_rng_uniform_floats(first_sequence, n_sequences, n_per, _p(out)))

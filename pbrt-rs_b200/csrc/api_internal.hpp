@@ -63,6 +63,9 @@ struct pb2_scene {
     unsigned long long* d_counters = nullptr;
     std::atomic<unsigned> counter_cursor{0};
     unsigned long long* next_counter() { return d_counters + (counter_cursor.fetch_add(1) % kCounters); }
+    // Distribution1D of the light-selection strategies: [0] uniform, [1] power (lightdistrib.rs:26-69)
+    std::vector<float> light_func[2], light_cdf[2];
+    float light_func_int[2] = {0.0f, 0.0f};
     pb2::SceneView view;
     pb2::Stage stage[2];
     pb2::Wavefront* wf = nullptr;

@@ -1,28 +1,381 @@
 // api_path.cu — Film, wavefront PathIntegrator and NCCL entry points of include/pbrt_b200.h.
+#include <nccl.h>
+
+#include <cmath>
+
 #include "api_internal.hpp"
+#include "wavefront.cuh"
 
 namespace pb2 {
-struct Wavefront {};
-void wavefront_destroy(Wavefront* wf) { delete wf; }
-int upload_shading_tables(pb2_scene*) { return PB2_OK; }
+size_t film_sort_scratch_bytes(uint32_t capacity);
+}
+
+struct pb2_film {
+    pb2_film_desc desc;
+    float table[256];
+    float* d_table = nullptr;
+    float4* d_xyzw = nullptr;
+    float4* d_acc = nullptr;
+    void* d_stray = nullptr;
+    float4* d_stray_vals = nullptr;
+    uint32_t stray_capacity = 0;
+    unsigned long long* d_counters = nullptr;      // C_COUNT slots, used when the film is filled without a wavefront
+    int sb_x0, sb_y0, sb_x1, sb_y1;
+    int device = 0;
+};
+
+namespace pb2 {
+
+static FilmView film_view(const pb2_film* f) {
+    FilmView v;
+    v.res_x = f->desc.res_x; v.res_y = f->desc.res_y;
+    v.sb_x0 = f->sb_x0; v.sb_y0 = f->sb_y0; v.sb_w = f->sb_x1 - f->sb_x0; v.sb_h = f->sb_y1 - f->sb_y0;
+    v.radius_x = f->desc.radius_x; v.radius_y = f->desc.radius_y;
+    v.exact = (f->desc.filter == PB2_FILTER_BOX && f->desc.radius_x == 0.5f && f->desc.radius_y == 0.5f) ? 1 : 0;
+    v.table = f->d_table;
+    v.acc = f->d_acc;
+    v.xyzw = f->d_xyzw;
+    v.stray_keys = (unsigned long long*)f->d_stray;
+    v.stray_vals = f->d_stray_vals;
+    v.stray_capacity = f->stray_capacity;
+    return v;
+}
+
+// TrowbridgeReitzDistribution::roughness_to_alpha (microfacet.rs:160-168), evaluated once per material on the host
+static float roughness_to_alpha(float roughness) {
+    roughness = std::fmax(roughness, 1e-3f);
+    const float x = std::log(roughness);
+    return (((1.62142f + 0.819955f * x) + 0.1734f * x * x) + 0.0171201f * x * x * x) + 0.000640711f * x * x * x * x;
+}
+
+// Distribution1D::new (sampling.rs:76-98, D29 FIX)
+static void make_distribution(const std::vector<float>& func, std::vector<float>* cdf, float* func_int) {
+    const size_t n = func.size();
+    cdf->assign(n + 1, 0.0f);
+    for (size_t i = 1; i < n + 1; ++i) (*cdf)[i] = (*cdf)[i - 1] + func[i - 1] / (float)n;
+    *func_int = (*cdf)[n];
+    if (*func_int == 0.0f) for (size_t i = 1; i < n + 1; ++i) (*cdf)[i] = (float)i / (float)n;
+    else for (size_t i = 1; i < n + 1; ++i) (*cdf)[i] /= *func_int;
+}
+
+// Device tables for shading: per-primitive material / area-light ids, materials, lights and both light distributions
+// (lightdistrib.rs:222-232: "uniform" and "power"; integrator.rs:268-277).
+int upload_shading_tables(pb2_scene* scene) {
+    const size_t n_tris = scene->indices.size() / 3;
+    if (scene->tri_material.empty() || n_tris == 0) return PB2_OK;       // ray-casting-only scene
+    std::vector<DMaterial> mats(scene->materials.size());
+    for (size_t i = 0; i < mats.size(); ++i) {
+        const pb2_material& m = scene->materials[i];
+        if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_GLASS) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
+        DMaterial& d = mats[i];
+        d.type = m.type;
+        for (int k = 0; k < 3; ++k) { d.kd[k] = m.kd[k]; d.ks[k] = m.ks[k]; d.kr[k] = m.kr[k]; d.kt[k] = m.kt[k]; }
+        d.alpha = m.remap_roughness ? roughness_to_alpha(m.roughness) : m.roughness;
+        d.eta = m.eta;
+    }
+    const size_t n_lights = scene->lights.size();
+    std::vector<DLight> lights(std::max<size_t>(1, n_lights));
+    std::vector<int32_t> tri_light(n_tris, -1);
+    std::vector<float> power(n_lights), ones(n_lights, 1.0f);
+    for (size_t i = 0; i < n_lights; ++i) {
+        const pb2_light& l = scene->lights[i];
+        DLight& d = lights[i];
+        memset(&d, 0, sizeof d);
+        d.type = l.type;
+        for (int k = 0; k < 3; ++k) { d.p[k] = l.p[k]; d.l[k] = l.i[k]; }
+        d.prim = l.prim_id;
+        d.two_sided = l.two_sided;
+        rgb3 pw;
+        if (l.type == PB2_LIGHT_AREA) {
+            const uint32_t* ix = &scene->indices[3ull * l.prim_id];
+            const float* v = scene->verts.data();
+            const vec3 p0 = mk(v[3 * ix[0]], v[3 * ix[0] + 1], v[3 * ix[0] + 2]);
+            const vec3 p1 = mk(v[3 * ix[1]], v[3 * ix[1] + 1], v[3 * ix[1] + 2]);
+            const vec3 p2 = mk(v[3 * ix[2]], v[3 * ix[2] + 1], v[3 * ix[2] + 2]);
+            d.p0[0] = p0.x; d.p0[1] = p0.y; d.p0[2] = p0.z;
+            d.p1[0] = p1.x; d.p1[1] = p1.y; d.p1[2] = p1.z;
+            d.p2[0] = p2.x; d.p2[1] = p2.y; d.p2[2] = p2.z;
+            d.area = len(cross3(p1 - p0, p2 - p0)) * 0.5f;               // triangle.rs:323-328
+            tri_light[l.prim_id] = (int32_t)i;
+            pw = mkc(l.i[0], l.i[1], l.i[2]) * ((l.two_sided ? 2.0f : 1.0f) * d.area * PB2_PI);      // diffuse.rs:83-85
+        } else {
+            pw = mkc(l.i[0], l.i[1], l.i[2]) * (4.0f * PB2_PI);          // point.rs:68-70
+        }
+        power[i] = luminance(pw);
+    }
+    scene->light_func[0] = ones;
+    scene->light_func[1] = (n_lights == 1) ? ones : power;               // lightdistrib.rs:223: one light -> uniform
+    for (int k = 0; k < 2; ++k) make_distribution(scene->light_func[k], &scene->light_cdf[k], &scene->light_func_int[k]);
+    PB2_CUDA(cudaMalloc(&scene->d_tri_material, n_tris * 4));
+    PB2_CUDA(cudaMalloc(&scene->d_tri_light, n_tris * 4));
+    PB2_CUDA(cudaMalloc(&scene->d_materials, mats.size() * sizeof(DMaterial)));
+    PB2_CUDA(cudaMalloc(&scene->d_lights, lights.size() * sizeof(DLight)));
+    PB2_CUDA(cudaMalloc(&scene->d_light_cdf, (4 * n_lights + 4) * sizeof(float)));
+    PB2_CUDA(cudaMemcpy(scene->d_tri_material, scene->tri_material.data(), n_tris * 4, cudaMemcpyHostToDevice));
+    PB2_CUDA(cudaMemcpy(scene->d_tri_light, tri_light.data(), n_tris * 4, cudaMemcpyHostToDevice));
+    PB2_CUDA(cudaMemcpy(scene->d_materials, mats.data(), mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice));
+    PB2_CUDA(cudaMemcpy(scene->d_lights, lights.data(), lights.size() * sizeof(DLight), cudaMemcpyHostToDevice));
+    // layout: [func uniform | cdf uniform | func power | cdf power]
+    float* base = (float*)scene->d_light_cdf;
+    size_t off = 0;
+    for (int k = 0; k < 2; ++k) {
+        if (n_lights) PB2_CUDA(cudaMemcpy(base + off, scene->light_func[k].data(), n_lights * 4, cudaMemcpyHostToDevice));
+        off += n_lights;
+        PB2_CUDA(cudaMemcpy(base + off, scene->light_cdf[k].data(), (n_lights + 1) * 4, cudaMemcpyHostToDevice));
+        off += n_lights + 1;
+    }
+    return PB2_OK;
+}
+
+static ShadeView shade_view(const pb2_scene* s, int strategy) {
+    ShadeView v;
+    const size_t n = s->lights.size();
+    v.tri_material = (const uint32_t*)s->d_tri_material;
+    v.tri_light = (const int32_t*)s->d_tri_light;
+    v.mats = (const DMaterial*)s->d_materials;
+    v.lights = (const DLight*)s->d_lights;
+    v.n_lights = (int)n;
+    const float* base = (const float*)s->d_light_cdf;
+    const size_t off = strategy == PB2_LIGHTS_POWER ? (2 * n + 1) : 0;
+    v.light_func = base + off;
+    v.light_cdf = base + off + n;
+    v.light_func_int = s->light_func_int[strategy == PB2_LIGHTS_POWER ? 1 : 0];
+    return v;
+}
+
+static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, const pb2_film_desc* fd, CameraView* cv) {
+    if (!scene || !cam || !path) return set_error(PB2_ERR_INVALID, "null argument");
+    if (!scene->built) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (scene->tri_material.empty()) return set_error(PB2_ERR_STATE, "the scene was created without materials");
+    if (path->max_depth < 0 || path->max_depth > 65535) return set_error(PB2_ERR_INVALID, "max_depth out of range");
+    if (path->spp <= 0 || path->sample_begin < 0 || path->sample_end > path->spp || path->sample_begin > path->sample_end)
+        return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
+    if (path->light_strategy != PB2_LIGHTS_UNIFORM && path->light_strategy != PB2_LIGHTS_POWER)
+        return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
+    if (fd && (cam->res_x != fd->res_x || cam->res_y != fd->res_y)) return set_error(PB2_ERR_INVALID, "camera and film resolutions differ");
+    return make_camera_view(cam, cv);
+}
+
+static int ensure_wavefront(pb2_scene* scene, uint64_t min_capacity) {
+    const uint64_t want = std::max<uint64_t>(min_capacity, 1ull << 22);
+    if (scene->wf && scene->wf->capacity >= want) return PB2_OK;
+    if (scene->wf) { wavefront_destroy(scene->wf); scene->wf = nullptr; }
+    int rc = wavefront_create(want, &scene->wf);
+    if (rc != 0) return set_error(PB2_ERR_CUDA, "wavefront buffers for %llu paths: %s", (unsigned long long)want, cudaGetErrorString((cudaError_t)rc));
+    return PB2_OK;
+}
+
+static ncclComm_t g_comm = nullptr;
+static int g_rank = 0, g_nranks = 1;
+
 }  // namespace pb2
 
 using namespace pb2;
 
 extern "C" {
-#define PB2_TODO(name) return set_error(PB2_ERR_STATE, name " is not implemented yet")
-int pb2_film_create(const pb2_film_desc*, pb2_film**) { PB2_TODO("pb2_film_create"); }
-int pb2_film_destroy(pb2_film*) { return PB2_OK; }
-int pb2_film_clear(pb2_film*) { PB2_TODO("pb2_film_clear"); }
-int pb2_film_add_samples(pb2_film*, const float*, const float*, const float*, uint64_t) { PB2_TODO("pb2_film_add_samples"); }
-int pb2_film_read_xyzw(pb2_film*, float*) { PB2_TODO("pb2_film_read_xyzw"); }
-int pb2_film_resolve_rgb(pb2_film*, float, float*) { PB2_TODO("pb2_film_resolve_rgb"); }
-int pb2_film_device_ptr(pb2_film*, void**, uint64_t*) { PB2_TODO("pb2_film_device_ptr"); }
-int pb2_render_path(pb2_scene*, const pb2_camera*, const pb2_path_desc*, pb2_film*, void*) { PB2_TODO("pb2_render_path"); }
-int pb2_path_li(pb2_scene*, const pb2_camera*, const pb2_path_desc*, const uint32_t*, const uint32_t*, uint64_t, float*, float*) { PB2_TODO("pb2_path_li"); }
-int pb2_render_counters(pb2_scene*, uint64_t*) { PB2_TODO("pb2_render_counters"); }
-int pb2_nccl_unique_id(char*) { PB2_TODO("pb2_nccl_unique_id"); }
-int pb2_nccl_init(const char*, int, int) { PB2_TODO("pb2_nccl_init"); }
-int pb2_nccl_shutdown(void) { return PB2_OK; }
-int pb2_film_reduce(pb2_film*, int, void*) { PB2_TODO("pb2_film_reduce"); }
+
+// ---- Film ---------------------------------------------------------------------------------------------------------------------
+int pb2_film_create(const pb2_film_desc* desc, pb2_film** out) {
+    if (!desc || !out) return set_error(PB2_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->res_x <= 0 || desc->res_y <= 0 || !(desc->radius_x > 0.0f) || !(desc->radius_y > 0.0f))
+        return set_error(PB2_ERR_INVALID, "bad film description");
+    if (desc->filter != PB2_FILTER_BOX && desc->filter != PB2_FILTER_GAUSSIAN) return set_error(PB2_ERR_INVALID, "unknown filter %d", desc->filter);
+    pb2_film* f = new pb2_film();
+    f->desc = *desc;
+    // Film::new filter table (film.rs:53-63) with BoxFilter / GaussianFilter::evaluate (boxf.rs:26-28, gaussian.rs:17-39)
+    const float a = desc->gaussian_alpha;
+    const float ex = std::exp(-a * desc->radius_x * desc->radius_x), ey = std::exp(-a * desc->radius_y * desc->radius_y);
+    for (int y = 0; y < 16; ++y)
+        for (int x = 0; x < 16; ++x) {
+            const float px = ((float)x + 0.5f) * desc->radius_x / 16.0f, py = ((float)y + 0.5f) * desc->radius_y / 16.0f;
+            float w = 1.0f;
+            if (desc->filter == PB2_FILTER_GAUSSIAN) w = std::fmax(std::exp(-a * px * px) - ex, 0.0f) * std::fmax(std::exp(-a * py * py) - ey, 0.0f);
+            f->table[y * 16 + x] = w;
+        }
+    // Film::get_sample_bounds (film.rs:76-81, D42 FIX)
+    f->sb_x0 = (int)std::floor(0.0f + 0.5f - desc->radius_x);
+    f->sb_y0 = (int)std::floor(0.0f + 0.5f - desc->radius_y);
+    f->sb_x1 = (int)std::ceil((float)desc->res_x - 0.5f + desc->radius_x);
+    f->sb_y1 = (int)std::ceil((float)desc->res_y - 0.5f + desc->radius_y);
+    const size_t npix = (size_t)desc->res_x * desc->res_y;
+    f->stray_capacity = 1u << 20;
+    const size_t stray_bytes = (size_t)f->stray_capacity * (2 * 8 + 2 * 4) + film_sort_scratch_bytes(f->stray_capacity) + 1024;
+    cudaError_t e = cudaGetDevice(&f->device);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_table, sizeof f->table);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_xyzw, npix * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_acc, npix * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_stray, stray_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_stray_vals, (size_t)f->stray_capacity * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_counters, C_COUNT * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_table, f->table, sizeof f->table, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(f->d_xyzw, 0, npix * 16);
+    if (e == cudaSuccess) e = cudaMemset(f->d_acc, 0, npix * 16);
+    if (e == cudaSuccess) e = cudaMemset(f->d_counters, 0, C_COUNT * 8);
+    if (e != cudaSuccess) { pb2_film_destroy(f); return cuda_fail(e, "film allocation", __FILE__, __LINE__); }
+    *out = f;
+    return PB2_OK;
 }
+
+int pb2_film_destroy(pb2_film* f) {
+    if (!f) return PB2_OK;
+    cudaFree(f->d_table); cudaFree(f->d_xyzw); cudaFree(f->d_acc); cudaFree(f->d_stray); cudaFree(f->d_stray_vals); cudaFree(f->d_counters);
+    delete f;
+    return PB2_OK;
+}
+
+int pb2_film_clear(pb2_film* f) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    const size_t npix = (size_t)f->desc.res_x * f->desc.res_y;
+    PB2_CUDA(cudaMemset(f->d_xyzw, 0, npix * 16));
+    PB2_CUDA(cudaMemset(f->d_acc, 0, npix * 16));
+    return PB2_OK;
+}
+
+int pb2_film_add_samples(pb2_film* f, const float* p_film, const float* L_rgb, const float* weight, uint64_t n) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    if (n == 0) return PB2_OK;
+    if (!p_film || !L_rgb || !weight) return set_error(PB2_ERR_INVALID, "null sample arrays");
+    float *d_p = nullptr, *d_L = nullptr, *d_w = nullptr;
+    cudaError_t e = cudaMalloc(&d_p, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_L, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_w, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_p, p_film, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_L, L_rgb, n * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_w, weight, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { film_add_samples(film_view(f), d_p, d_L, d_w, n, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_p); cudaFree(d_L); cudaFree(d_w);
+    if (e != cudaSuccess) return cuda_fail(e, "film add_samples", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_film_read_xyzw(pb2_film* f, float* out) {
+    if (!f || !out) return set_error(PB2_ERR_INVALID, "null argument");
+    PB2_CUDA(cudaMemcpy(out, f->d_xyzw, (size_t)f->desc.res_x * f->desc.res_y * 16, cudaMemcpyDeviceToHost));
+    return PB2_OK;
+}
+
+int pb2_film_resolve_rgb(pb2_film* f, float scale, float* rgb) {
+    if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
+    const size_t npix = (size_t)f->desc.res_x * f->desc.res_y;
+    float* d = nullptr;
+    PB2_CUDA(cudaMalloc(&d, npix * 12));
+    film_resolve(film_view(f), scale, d, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(rgb, d, npix * 12, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "film resolve", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_film_device_ptr(pb2_film* f, void** d_xyzw, uint64_t* n_floats) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    if (d_xyzw) *d_xyzw = f->d_xyzw;
+    if (n_floats) *n_floats = (uint64_t)f->desc.res_x * f->desc.res_y * 4;
+    return PB2_OK;
+}
+
+// ---- Integrator::render ---------------------------------------------------------------------------------------------------------
+int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, pb2_film* film, void* stream) {
+    if (!film) return set_error(PB2_ERR_INVALID, "null film");
+    CameraView cv;
+    int rc = check_path_args(scene, cam, path, &film->desc, &cv);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(scene->mu);
+    const FilmView fv = film_view(film);
+    rc = ensure_wavefront(scene, (uint64_t)fv.sb_w * fv.sb_h);
+    if (rc) return rc;
+    const PathParams pp{path->max_depth, path->rr_threshold};
+    wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, path->spp, path->sample_begin,
+                     path->sample_end, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
+int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, const uint32_t* pixel_xy,
+                const uint32_t* sample_index, uint64_t n, float* L_rgb, float* p_film) {
+    CameraView cv;
+    int rc = check_path_args(scene, cam, path, nullptr, &cv);
+    if (rc) return rc;
+    if (n == 0) return PB2_OK;
+    if (!pixel_xy || !sample_index || !L_rgb || !p_film) return set_error(PB2_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    rc = ensure_wavefront(scene, n);
+    if (rc) return rc;
+    // box filter, r = 0.5 sample bounds: streams are indexed by image pixel
+    FilmView fv;
+    memset(&fv, 0, sizeof fv);
+    fv.res_x = cam->res_x; fv.res_y = cam->res_y; fv.sb_w = cam->res_x; fv.sb_h = cam->res_y; fv.radius_x = fv.radius_y = 0.5f;
+    int32_t* d_xy = nullptr;
+    uint32_t* d_s = nullptr;
+    float *d_L = nullptr, *d_pf = nullptr;
+    cudaError_t e = cudaMalloc(&d_xy, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_L, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pf, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_xy, pixel_xy, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_s, sample_index, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const PathParams pp{path->max_depth, path->rr_threshold};
+        wavefront_li(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, path->spp, d_xy, d_s, n, d_L, d_pf, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(L_rgb, d_L, n * 12, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(p_film, d_pf, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_xy); cudaFree(d_s); cudaFree(d_L); cudaFree(d_pf);
+    if (e != cudaSuccess) return cuda_fail(e, "pb2_path_li", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_render_counters(pb2_scene* scene, uint64_t out[8]) {
+    if (!scene || !out) return set_error(PB2_ERR_INVALID, "null argument");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!scene->wf) return PB2_OK;
+    unsigned long long c[C_COUNT];
+    PB2_CUDA(cudaDeviceSynchronize());
+    PB2_CUDA(cudaMemcpy(c, scene->wf->b.counters, sizeof c, cudaMemcpyDeviceToHost));
+    out[0] = c[T_CAMERA]; out[1] = c[T_EXTEND]; out[2] = c[T_SHADOW]; out[3] = c[T_MIS];
+    out[4] = scene->wf->totals[4];
+    out[5] = c[C_STRAY_OVERFLOW];
+    return PB2_OK;
+}
+
+// ---- NCCL film reduce -------------------------------------------------------------------------------------------------------------
+int pb2_nccl_unique_id(char id[128]) {
+    if (!id) return set_error(PB2_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    ncclResult_t r = ncclGetUniqueId(&u);
+    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+    memcpy(id, &u, 128);
+    return PB2_OK;
+}
+
+int pb2_nccl_init(const char id[128], int rank, int n_ranks) {
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(PB2_ERR_INVALID, "bad NCCL init arguments");
+    if (g_comm) return set_error(PB2_ERR_STATE, "NCCL communicator already initialised");
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclResult_t r = ncclCommInitRank(&g_comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { g_comm = nullptr; return set_error(PB2_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r)); }
+    g_rank = rank;
+    g_nranks = n_ranks;
+    return PB2_OK;
+}
+
+int pb2_nccl_shutdown(void) {
+    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    return PB2_OK;
+}
+
+int pb2_film_reduce(pb2_film* f, int root, void* stream) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    if (!g_comm) return set_error(PB2_ERR_STATE, "pb2_nccl_init has not been called");
+    const size_t count = (size_t)f->desc.res_x * f->desc.res_y * 4;
+    ncclResult_t r = ncclReduce(f->d_xyzw, f->d_xyzw, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
+    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclReduce: %s", ncclGetErrorString(r));
+    return PB2_OK;
+}
+
+}  // extern "C"

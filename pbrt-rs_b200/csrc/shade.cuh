@@ -1,0 +1,366 @@
+// shade.cuh — device-side scattering, light sampling and film math of the wavefront PathIntegrator (sm_100a).
+//
+// Replaces, per path vertex: BSDF::{f, pdf, sample_f} (src/core/reflection.rs:206-449) with the three lobes the
+// materials of the configs need — LambertianReflection (:821-855 + BxDF defaults :459-507), MicrofacetReflection with
+// TrowbridgeReitzDistribution (:977-1056, src/core/microfacet.rs:145-248,336-406) and FresnelSpecular (:733-819) —
+// fr_dielectric (:19-40), the shading-space helpers (:71-156), power_heuristic (src/core/sampling.rs:306-313),
+// Distribution1D::sample_discrete (:130-149), RGB<->XYZ / y_value (src/core/spectrum.rs:96-107,679-682) and the
+// FilmTile::add_sample footprint (src/core/film.rs:252-295).  matte / plastic / glass follow pbrt-v3 (the reference's
+// material files are empty).  Arithmetic order is the reference's, one rounded f32 op each
+// (-fmad=false); sin/cos are det_sincos (pb2_math.cuh).  Appendix-A fixes applied: D6 D22 D23 D28 D30 D33-D36 D40.
+#pragma once
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+struct rgb3 {
+    float r, g, b;
+};
+PB2_HD rgb3 mkc(float r, float g, float b) { rgb3 c; c.r = r; c.g = g; c.b = b; return c; }
+PB2_HD rgb3 gray(float v) { return mkc(v, v, v); }
+PB2_HD rgb3 operator+(rgb3 a, rgb3 b) { return mkc(a.r + b.r, a.g + b.g, a.b + b.b); }
+PB2_HD rgb3 operator*(rgb3 a, rgb3 b) { return mkc(a.r * b.r, a.g * b.g, a.b * b.b); }
+PB2_HD rgb3 operator*(rgb3 a, float s) { return mkc(a.r * s, a.g * s, a.b * s); }
+PB2_HD rgb3 operator/(rgb3 a, float s) { return mkc(a.r / s, a.g / s, a.b / s); }
+PB2_HD bool black(rgb3 a) { return a.r == 0.0f && a.g == 0.0f && a.b == 0.0f; }
+PB2_HD float luminance(rgb3 a) { return (0.212671f * a.r + 0.715160f * a.g) + 0.072169f * a.b; }
+PB2_HD float max_channel(rgb3 a) {          // spectrum.rs:161-165: fold from f32::MIN with `if max > v {max} else {v}`
+    float m = -3.402823466e+38f;
+    m = (m > a.r) ? m : a.r;
+    m = (m > a.g) ? m : a.g;
+    m = (m > a.b) ? m : a.b;
+    return m;
+}
+PB2_HD bool any_nan(rgb3 a) { return isnan(a.r) || isnan(a.g) || isnan(a.b); }
+PB2_HD void to_xyz(rgb3 c, float* x, float* y, float* z) {
+    *x = (0.412453f * c.r + 0.357580f * c.g) + 0.180423f * c.b;
+    *y = (0.212671f * c.r + 0.715160f * c.g) + 0.072169f * c.b;
+    *z = (0.019334f * c.r + 0.119193f * c.g) + 0.950227f * c.b;
+}
+PB2_HD rgb3 from_xyz(float x, float y, float z) {
+    return mkc((3.240479f * x - 1.537150f * y) - 0.498535f * z, (-0.969256f * x + 1.875991f * y) + 0.041556f * z,
+               (0.055648f * x - 0.204043f * y) + 1.057311f * z);
+}
+PB2_HD float clamp01s(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+enum : unsigned { kReflection = 1u, kTransmission = 2u, kDiffuse = 4u, kGlossy = 8u, kSpecular = 16u, kAllLobes = 31u };
+
+// ---- shading-space helpers (reflection.rs:71-156) --------------------------------------------------------------
+PB2_HD float cos_t(vec3 w) { return w.z; }
+PB2_HD float cos2_t(vec3 w) { return w.z * w.z; }
+PB2_HD float abs_cos_t(vec3 w) { return fabsf(w.z); }
+PB2_HD float sin2_t(vec3 w) { return fmaxf(1.0f - cos2_t(w), 0.0f); }
+PB2_HD float sin_t(vec3 w) { return sqrtf(sin2_t(w)); }
+PB2_HD float tan_t(vec3 w) { return sin_t(w) / cos_t(w); }
+PB2_HD float tan2_t(vec3 w) { return sin2_t(w) / cos2_t(w); }
+PB2_HD float cos_p(vec3 w) { const float s = sin_t(w); return s == 0.0f ? 1.0f : clamp01s(w.x / s, -1.0f, 1.0f); }
+PB2_HD float sin_p(vec3 w) { const float s = sin_t(w); return s == 0.0f ? 0.0f : clamp01s(w.y / s, -1.0f, 1.0f); }
+PB2_HD float cos2_p(vec3 w) { return cos_p(w) * cos_p(w); }
+PB2_HD float sin2_p(vec3 w) { return sin_p(w) * sin_p(w); }
+PB2_HD bool same_side(vec3 a, vec3 b) { return a.z * b.z > 0.0f; }
+PB2_HD vec3 mirror(vec3 wo, vec3 n) { return -wo + n * (2.0f * dot3(wo, n)); }
+PB2_HD vec3 face_toward(vec3 n, vec3 v) { return dot3(n, v) < 0.0f ? -n : n; }       // pbrt Faceforward(n, v)
+PB2_HD bool refract_dir(vec3 wi, vec3 n, float eta, vec3* wt) {
+    const float ci = dot3(n, wi);
+    const float s2i = fmaxf(1.0f - ci * ci, 0.0f);
+    const float s2t = eta * eta * s2i;
+    if (s2t >= 1.0f) return false;
+    const float ct = sqrtf(1.0f - s2t);
+    *wt = -wi * eta + n * (eta * ci - ct);
+    return true;
+}
+PB2_HD float fresnel_dielectric(float ci, float eta_i, float eta_t) {
+    ci = clamp01s(ci, -1.0f, 1.0f);
+    if (!(ci > 0.0f)) {
+        const float t = eta_i; eta_i = eta_t; eta_t = t;
+        ci = fabsf(ci);
+    }
+    const float si = sqrtf(fmaxf(1.0f - ci * ci, 0.0f));
+    const float st = eta_i / eta_t * si;
+    if (st >= 1.0f) return 1.0f;
+    const float ct = sqrtf(fmaxf(1.0f - st * st, 0.0f));
+    const float r_parl = (eta_t * ci - eta_i * ct) / (eta_t * ci + eta_i * ct);
+    const float r_perp = (eta_i * ci - eta_t * ct) / (eta_i * ci + eta_t * ct);
+    return (r_parl * r_parl + r_perp * r_perp) / 2.0f;
+}
+
+// ---- sampling.rs --------------------------------------------------------------------------------------------------
+PB2_HD vec3 cosine_hemisphere(float u0, float u1) {          // :258-273 concentric disk, :289-294 (D30 FIX)
+    const float ox = u0 * 2.0f - 1.0f, oy = u1 * 2.0f - 1.0f;
+    float dx = 0.0f, dy = 0.0f;
+    if (!(ox == 0.0f && oy == 0.0f)) {
+        float r, theta;
+        if (fabsf(ox) > fabsf(oy)) { r = ox; theta = (PB2_PI / 4.0f) * (oy / ox); }
+        else { r = oy; theta = (PB2_PI / 2.0f) - (PB2_PI / 4.0f) * (ox / oy); }
+        float s, c;
+        det_sincos(theta, &s, &c);
+        dx = c * r;
+        dy = s * r;
+    }
+    return mk(dx, dy, sqrtf(fmaxf(0.0f, (1.0f - dx * dx) - dy * dy)));
+}
+PB2_HD float power_heuristic(float f_pdf, float g_pdf) {
+    const float f = 1.0f * f_pdf, g = 1.0f * g_pdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// ---- Trowbridge-Reitz, isotropic alpha, visible-area sampling (microfacet.rs) ------------------------------------
+PB2_HD float tr_d(float a, vec3 wh) {
+    const float t2 = tan2_t(wh);
+    if (isinf(t2)) return 0.0f;
+    const float cos4 = cos2_t(wh) * cos2_t(wh);
+    const float e = (cos2_p(wh) / (a * a) + sin2_p(wh) / (a * a)) * t2;
+    return 1.0f / (PB2_PI * a * a * cos4 * (1.0f + e) * (1.0f + e));
+}
+PB2_HD float tr_lambda(float a, vec3 w) {
+    const float at = fabsf(tan_t(w));
+    if (isinf(at)) return 0.0f;
+    const float alpha = sqrtf(cos2_p(w) * a * a + sin2_p(w) * a * a);
+    const float a2t2 = (alpha * at) * (alpha * at);
+    return (-1.0f + sqrtf(1.0f + a2t2)) / 2.0f;
+}
+PB2_HD float tr_g1(float a, vec3 w) { return 1.0f / (1.0f + tr_lambda(a, w)); }
+PB2_HD float tr_g(float a, vec3 wo, vec3 wi) { return 1.0f / ((1.0f + tr_lambda(a, wo)) + tr_lambda(a, wi)); }
+PB2_HD float tr_pdf(float a, vec3 wo, vec3 wh) { return tr_d(a, wh) * tr_g1(a, wo) * fabsf(dot3(wo, wh)) / abs_cos_t(wo); }
+PB2_HD void tr_sample11(float cos_theta, float u1, float u2, float* slope_x, float* slope_y) {
+    if (cos_theta > 0.9999f) {
+        const float r = sqrtf(u1 / (1.0f - u1));
+        const float phi = 6.28318530718f * u2;
+        float s, c;
+        det_sincos(phi, &s, &c);
+        *slope_x = r * c;
+        *slope_y = r * s;
+        return;
+    }
+    const float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+    const float tan_theta = sin_theta / cos_theta;
+    float a = 1.0f / tan_theta;
+    const float g1 = 2.0f / (1.0f + sqrtf(1.0f + 1.0f / (a * a)));
+    a = 2.0f * u1 / g1 - 1.0f;
+    float tmp = 1.0f / (a * a - 1.0f);
+    if (tmp > 1e10f) tmp = 1e10f;
+    const float b = tan_theta;
+    const float d = sqrtf(fmaxf(b * b * tmp * tmp - (a * a - b * b), 0.0f));
+    const float sx1 = b * tmp - d, sx2 = b * tmp + d;
+    *slope_x = (a < 0.0f || sx2 > 1.0f / tan_theta) ? sx1 : sx2;
+    float s;
+    if (u2 > 0.5f) { s = 1.0f; u2 = 2.0f * (u2 - 0.5f); }
+    else { s = -1.0f; u2 = 2.0f * (0.5f - u2); }
+    const float z = (u2 * (u2 * (u2 * 0.27385f - 0.73369f) + 0.46341f)) /
+                    (u2 * (u2 * (u2 * 0.093073f + 0.309420f) - 1.00000f) + 0.5979999f);
+    *slope_y = s * z * sqrtf(1.0f + *slope_x * *slope_x);
+}
+PB2_HD vec3 tr_sample_wh(float a, vec3 wo, float u0, float u1) {
+    const bool flip = wo.z < 0.0f;
+    const vec3 wi = flip ? -wo : wo;
+    const vec3 ws = unit(mk(a * wi.x, a * wi.y, wi.z));
+    float sx, sy;
+    tr_sample11(cos_t(ws), u0, u1, &sx, &sy);
+    const float tmp = cos_p(ws) * sx - sin_p(ws) * sy;
+    sy = sin_p(ws) * sx + cos_p(ws) * sy;
+    sx = tmp;
+    sx = a * sx;                         // D40 FIX
+    sy = a * sy;
+    const vec3 wh = unit(mk(-sx, -sy, 1.0f));
+    return flip ? -wh : wh;
+}
+
+// ---- materials as device PODs -------------------------------------------------------------------------------------
+struct DMaterial {
+    int type;               // PB2_MAT_*
+    float kd[3], ks[3], kr[3], kt[3];
+    float alpha;            // plastic: Trowbridge-Reitz alpha (roughness_to_alpha applied on the host when remapping)
+    float eta;              // glass
+};
+
+struct DLight {
+    int type;               // PB2_LIGHT_*
+    float p[3];             // point
+    float l[3];             // I or L_emit
+    unsigned prim;          // area: emissive triangle
+    int two_sided;
+    float area;
+    float p0[3], p1[3], p2[3];
+};
+
+enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u };
+struct Lobe {
+    unsigned kind, type;
+    rgb3 r, t;
+    float alpha, eta_a, eta_b;
+};
+
+PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags) == l.type; }       // D33 FIX
+
+PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
+    if (l.kind == kLambert) return l.r * (1.0f / PB2_PI);
+    if (l.kind == kMicrofacet) {
+        const float co = abs_cos_t(wo), ci = abs_cos_t(wi);
+        vec3 wh = wi + wo;
+        if (ci == 0.0f || co == 0.0f) return gray(0.0f);
+        if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return gray(0.0f);
+        wh = unit(wh);
+        const float fr = fresnel_dielectric(dot3(wi, face_toward(wh, mk(0.0f, 0.0f, 1.0f))), l.eta_a, l.eta_b);   // D6 FIX
+        return l.r * tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi) * gray(fr) / (4.0f * ci * co);
+    }
+    return gray(0.0f);
+}
+PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
+    if (l.kind == kLambert) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
+    if (l.kind == kMicrofacet) {
+        if (!same_side(wo, wi)) return 0.0f;
+        const vec3 wh = unit(wo + wi);
+        return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+    }
+    return 0.0f;
+}
+PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, float* pdf, unsigned* sampled) {
+    if (l.kind == kLambert) {
+        *wi = cosine_hemisphere(u0, u1);
+        if (wo.z < 0.0f) wi->z = wi->z * -1.0f;
+        *pdf = lobe_pdf(l, wo, *wi);
+        return lobe_f(l, wo, *wi);
+    }
+    if (l.kind == kMicrofacet) {
+        if (wo.z == 0.0f) return gray(0.0f);
+        const vec3 wh = tr_sample_wh(l.alpha, wo, u0, u1);
+        if (dot3(wo, wh) < 0.0f) return gray(0.0f);
+        *wi = mirror(wo, wh);                                   // D36 FIX
+        if (!same_side(wo, *wi)) return gray(0.0f);
+        *pdf = tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+        return lobe_f(l, wo, *wi);
+    }
+    const float fr = fresnel_dielectric(cos_t(wo), l.eta_a, l.eta_b);
+    if (u0 < fr) {
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *sampled = kSpecular | kReflection;
+        *pdf = fr;
+        return l.r * fr / abs_cos_t(*wi);
+    }
+    const bool entering = cos_t(wo) > 0.0f;
+    const float eta_i = entering ? l.eta_a : l.eta_b, eta_t = entering ? l.eta_b : l.eta_a;
+    if (!refract_dir(wo, face_toward(mk(0.0f, 0.0f, 1.0f), wo), eta_i / eta_t, wi)) return gray(0.0f);
+    rgb3 ft = l.t * (1.0f - fr);
+    ft = ft * ((eta_i * eta_i) / (eta_t * eta_t));             // TransportMode::Radiance
+    *sampled = kSpecular | kTransmission;
+    *pdf = 1.0f - fr;
+    return ft / abs_cos_t(*wi);
+}
+
+struct Bsdf {
+    float eta;
+    vec3 ns, ng, ss, ts;
+    int n;
+    Lobe lobes[2];
+};
+
+PB2_HD int bsdf_count(const Bsdf& b, unsigned flags) {
+    int c = 0;
+    for (int i = 0; i < b.n; ++i) c += lobe_matches(b.lobes[i], flags) ? 1 : 0;
+    return c;
+}
+PB2_HD vec3 to_local(const Bsdf& b, vec3 v) { return mk(dot3(v, b.ss), dot3(v, b.ts), dot3(v, b.ns)); }
+PB2_HD vec3 to_world(const Bsdf& b, vec3 v) {                  // D34 FIX
+    return mk((b.ss.x * v.x + b.ts.x * v.y) + b.ns.x * v.z, (b.ss.y * v.x + b.ts.y * v.y) + b.ns.y * v.z,
+              (b.ss.z * v.x + b.ts.z * v.y) + b.ns.z * v.z);
+}
+PB2_HD rgb3 bsdf_sum_f(const Bsdf& b, vec3 wo, vec3 wi, bool refl, unsigned flags) {
+    rgb3 sum = gray(0.0f);
+    for (int i = 0; i < b.n; ++i) {
+        const Lobe& l = b.lobes[i];
+        if (lobe_matches(l, flags) && ((refl && (l.type & kReflection)) || (!refl && (l.type & kTransmission)))) sum = sum + lobe_f(l, wo, wi);
+    }
+    return sum;
+}
+PB2_HD rgb3 bsdf_f(const Bsdf& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+    const vec3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
+    if (wo.z == 0.0f) return gray(0.0f);
+    const bool refl = dot3(wi_w, b.ng) * dot3(wo_w, b.ng) > 0.0f;
+    return bsdf_sum_f(b, wo, wi, refl, flags);
+}
+PB2_HD float bsdf_pdf(const Bsdf& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+    if (b.n == 0) return 0.0f;
+    const vec3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
+    if (wo.z == 0.0f) return 0.0f;
+    float p = 0.0f;
+    int matching = 0;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags)) { ++matching; p += lobe_pdf(b.lobes[i], wo, wi); }
+    return matching > 0 ? p / (float)matching : 0.0f;
+}
+// BSDF::sample_f (:286-381).  *pdf must be pre-set by the caller (it is left untouched on the early exits, as in the reference).
+PB2_HD rgb3 bsdf_sample_f(const Bsdf& b, vec3 wo_w, vec3* wi_w, float u0, float u1, float* pdf, unsigned flags, unsigned* sampled) {
+    const int matching = bsdf_count(b, flags);
+    if (matching == 0) { *pdf = 0.0f; *sampled = 0u; return gray(0.0f); }
+    int comp = (int)floorf(u0 * (float)matching);
+    if (comp > matching - 1) comp = matching - 1;
+    int count = comp, chosen = 0;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags)) {
+            if (count == 0) { chosen = i; break; }
+            --count;
+        }
+    const Lobe& bx = b.lobes[chosen];
+    const float u0r = fminf(PB2_ONE_MINUS_EPS, u0 * (float)matching - (float)comp);
+    vec3 wi = mk(0.0f, 0.0f, 0.0f);
+    const vec3 wo = to_local(b, wo_w);
+    if (wo.z == 0.0f) return gray(0.0f);
+    *pdf = 0.0f;
+    *sampled = bx.type;
+    rgb3 fv = lobe_sample_f(bx, wo, &wi, u0r, u1, pdf, sampled);
+    if (*pdf == 0.0f) { *sampled = 0u; return gray(0.0f); }
+    *wi_w = to_world(b, wi);
+    if (!(bx.type & kSpecular) && matching > 1)
+        for (int i = 0; i < b.n; ++i)
+            if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    if (matching > 1) *pdf = *pdf / (float)matching;
+    if (!(bx.type & kSpecular)) {
+        const bool refl = dot3(*wi_w, b.ng) * dot3(wo_w, b.ng) > 0.0f;
+        fv = bsdf_sum_f(b, wo, wi, refl, flags);
+    }
+    return fv;
+}
+
+// Material::compute_scattering_functions for matte / plastic / glass (pbrt-v3; Appendix B).
+PB2_HD Bsdf make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
+    Bsdf b;
+    b.eta = m.type == 2 ? m.eta : 1.0f;
+    b.ns = n;
+    b.ng = n;
+    b.ss = unit(dpdu);                                         // reflection.rs:220-234 (D59: shading = geometric)
+    b.ts = cross3(b.ns, b.ss);
+    b.n = 0;
+    const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);
+    const rgb3 kr = mkc(m.kr[0], m.kr[1], m.kr[2]), kt = mkc(m.kt[0], m.kt[1], m.kt[2]);
+    if (m.type == 0 || m.type == 1) {
+        if (!black(kd)) {
+            Lobe& l = b.lobes[b.n++];
+            l.kind = kLambert; l.type = kReflection | kDiffuse; l.r = kd; l.t = gray(0.0f); l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f;
+        }
+        if (m.type == 1 && !black(ks)) {
+            Lobe& l = b.lobes[b.n++];
+            l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = gray(0.0f); l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f;
+        }
+    } else if (!(black(kr) && black(kt))) {
+        Lobe& l = b.lobes[b.n++];
+        l.kind = kFresnelSpecular; l.type = kReflection | kTransmission | kSpecular; l.r = kr; l.t = kt; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = m.eta;
+    }
+    return b;
+}
+
+// Distribution1D::sample_discrete (sampling.rs:130-149) over cdf[0..n], func[0..n) — D57 KEEP (cdf < u), D58 signed clamp.
+PB2_HD int sample_discrete(const float* cdf, const float* func, int n, float func_int, float u, float* pdf) {
+    int first = 0, len = n + 1;
+    while (len > 0) {
+        const int half = len >> 1, middle = first + half;
+        if (cdf[middle] < u) { first = middle + 1; len -= half + 1; }
+        else len = half;
+    }
+    int off = first - 1;
+    const int hi = n - 1;
+    if (off < 0) off = 0; else if (off > hi) off = hi;
+    *pdf = func_int > 0.0f ? func[off] / (func_int * (float)n) : 0.0f;
+    return off;
+}
+
+}  // namespace pb2

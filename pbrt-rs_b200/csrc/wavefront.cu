@@ -1,0 +1,691 @@
+// wavefront.cu — the wavefront PathIntegrator: ray-gen -> extend (closest hit) -> material-sorted shade ->
+// shadow (any hit) + MIS (closest hit) -> resolve -> next bounce, and the Film accumulation kernels (sm_100a).
+//
+// Replaces SamplerIntegrator::render (src/core/integrator.rs:399-480), PathIntegrator::li (src/integrators/path.rs:65-213),
+// uniform_sample_one_light / estimate_direct (src/core/integrator.rs:92-266), DiffuseAreaLight / PointLight sampling
+// (src/lights/diffuse.rs:60-90,150-156, src/lights/point.rs:47-74, src/core/shape.rs:38-69, src/shapes/triangle.rs:323-348),
+// Interaction::spawn_ray / spawn_ray_to (src/core/interaction.rs:132-153) and FilmTile::add_sample / merge_film_tile
+// (src/core/film.rs:252-295,111-123).  Each (pixel, sample) owns the sampler stream RNG::new(pixel_index*spp + sample)
+// and draws from it in the reference's order (5 camera dims; per vertex: light pick, u_light, u_scattering, BSDF sample,
+// Russian roulette), so a path's radiance does not depend on scheduling.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+
+#include "trace_persistent.cuh"
+#include "wavefront.cuh"
+
+namespace pb2 {
+
+TraceTuning trace_tuning();
+
+namespace {
+
+constexpr float kInf = __builtin_huge_valf();
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t queue_push(unsigned long long* counter, uint32_t* queue, uint32_t slot) {
+    const unsigned long long pos = atomicAdd(counter, 1ull);
+    queue[pos] = slot;
+    return (uint32_t)pos;
+}
+
+// ---- slot <-> (pixel, sample) -----------------------------------------------------------------------------------
+struct SlotInfo {
+    int x, y;                 // pixel in image coordinates (may lie outside the image for wide filters)
+    unsigned long long seq;   // sampler stream: ((y - sb_y0) * sb_w + (x - sb_x0)) * spp + sample
+};
+__device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& f, uint64_t slot) {
+    SlotInfo s;
+    uint32_t sample;
+    if (m.explicit_xy) {
+        s.x = m.explicit_xy[2 * slot];
+        s.y = m.explicit_xy[2 * slot + 1];
+        sample = m.explicit_s[slot];
+    } else {
+        const uint32_t pix = (uint32_t)(slot % m.n_pix);
+        sample = (uint32_t)m.sample0 + (uint32_t)(slot / m.n_pix);
+        s.x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w);
+        s.y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
+    }
+    s.seq = ((unsigned long long)(s.y - f.sb_y0) * (unsigned long long)f.sb_w + (unsigned long long)(s.x - f.sb_x0)) * (unsigned long long)m.spp + sample;
+    return s;
+}
+
+// ---- Camera::generate_ray (perspective.rs:90-112 + geometry.rs:865-881) ----------------------------------------------
+__device__ __forceinline__ vec3 cam_point(const mat4& m, vec3 p) {
+    const float xp = ((m.m[0][0] * p.x + m.m[0][1] * p.y) + m.m[0][2] * p.z) + m.m[0][3];
+    const float yp = ((m.m[1][0] * p.x + m.m[1][1] * p.y) + m.m[1][2] * p.z) + m.m[1][3];
+    const float zp = ((m.m[2][0] * p.x + m.m[2][1] * p.y) + m.m[2][2] * p.z) + m.m[2][3];
+    const float wp = ((m.m[3][0] * p.x + m.m[3][1] * p.y) + m.m[3][2] * p.z) + m.m[3][3];
+    if (wp == 1.0f) return mk(xp, yp, zp);
+    return mk(xp, yp, zp) / wp;
+}
+__device__ void gen_camera_ray(const CameraView& cam, float fx, float fy, vec3* o_out, vec3* d_out, float* t_max_out) {
+    const vec3 d_cam = unit(cam_point(cam.raster_to_camera, mk(fx, fy, 0.0f)));
+    const mat4& m = cam.camera_to_world;
+    // origin (0,0,0) through camera_to_world with its error bound (geometry.rs:898-936)
+    vec3 o = cam_point(m, mk(0.0f, 0.0f, 0.0f));
+    const float xs = ((fabsf(m.m[0][0] * 0.0f) + fabsf(m.m[0][1] * 0.0f)) + fabsf(m.m[0][2] * 0.0f)) + fabsf(m.m[0][3]);
+    const float ys = ((fabsf(m.m[1][0] * 0.0f) + fabsf(m.m[1][1] * 0.0f)) + fabsf(m.m[1][2] * 0.0f)) + fabsf(m.m[1][3]);
+    const float zs = ((fabsf(m.m[2][0] * 0.0f) + fabsf(m.m[2][1] * 0.0f)) + fabsf(m.m[2][2] * 0.0f)) + fabsf(m.m[2][3]);
+    const vec3 o_err = mk(xs, ys, zs) * gammaf_(3.0f);
+    const vec3 d = mk((m.m[0][0] * d_cam.x + m.m[0][1] * d_cam.y) + m.m[0][2] * d_cam.z,
+                      (m.m[1][0] * d_cam.x + m.m[1][1] * d_cam.y) + m.m[1][2] * d_cam.z,
+                      (m.m[2][0] * d_cam.x + m.m[2][1] * d_cam.y) + m.m[2][2] * d_cam.z);
+    const float ls = len2(d);
+    float t_max = kInf;
+    if (ls > 0.0f) {
+        const float dt = dot3(abs3(d), o_err) / ls;
+        o = o + d * dt;
+        t_max = t_max - dt;
+    }
+    *o_out = o;
+    *d_out = d;
+    *t_max_out = t_max;
+}
+
+// ---- k_raygen: integrator.rs:431-445 + sampler.rs:27-33 -------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, FilmView film, CameraView cam, PathBuffers b) {
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const SlotInfo si = slot_info(map, film, slot);
+        Pcg32 rng;
+        rng.set_sequence(si.seq);
+        const float u0 = rng.next_float(), u1 = rng.next_float();     // p_film offset (x then y)
+        (void)rng.next_float();                                       // time
+        (void)rng.next_float();                                       // p_lens
+        (void)rng.next_float();
+        vec3 o, d;
+        float t_max;
+        gen_camera_ray(cam, (float)si.x + u0, (float)si.y + u1, &o, &d, &t_max);
+        b.ray_o[slot] = make_float4(o.x, o.y, o.z, t_max);
+        b.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        b.L[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+        b.rng[slot] = rng.state;
+        b.q_active[0][slot] = (uint32_t)slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.counters[C_ACTIVE_A] = n;
+        b.counters[C_ACTIVE_B] = 0;
+        b.counters[T_CAMERA] += n;
+    }
+}
+
+// ---- per-iteration bookkeeping ------------------------------------------------------------------------------------------
+__global__ void k_iter_begin(PathBuffers b, int cur) {
+    if (threadIdx.x == 0) {
+        b.counters[T_EXTEND] += b.counters[C_ACTIVE_A + cur];
+        b.counters[C_ACTIVE_A + (cur ^ 1)] = 0;
+        b.counters[C_MAT0] = b.counters[C_MAT1] = b.counters[C_MAT2] = 0;
+        b.counters[C_SHADOW] = b.counters[C_MIS] = b.counters[C_NEE] = 0;
+        b.counters[C_WORK_EXTEND] = b.counters[C_WORK_SHADOW] = b.counters[C_WORK_MIS] = 0;
+    }
+}
+
+// ---- extend: closest hit over the active queue; hits are binned by material type (material-sorted shading) ---------------
+struct ExtendSink {
+    PathBuffers b;
+    ShadeView sh;
+    const uint32_t* queue;
+    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+        const uint32_t slot = queue[i];
+        const float4 ro = b.ray_o[slot], rd = b.ray_d[slot];
+        *o = mk(ro.x, ro.y, ro.z);
+        *d = mk(rd.x, rd.y, rd.z);
+        *t_max = ro.w;
+        return true;
+    }
+    PB2_D void closest(uint64_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
+        (void)t;
+        if (prim == 0xFFFFFFFFu) return;                 // escaped: no infinite lights in scope, the path is finished
+        const uint32_t slot = queue[i];
+        b.hit[slot] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
+        const int type = sh.mats[sh.tri_material[prim]].type;
+        queue_push(&b.counters[C_MAT0 + type], b.q_mat[type], slot);
+    }
+    PB2_D void occluded(uint64_t, bool) const {}
+};
+__global__ void __launch_bounds__(128, 8) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
+    const ExtendSink sink{b, sh, b.q_active[cur]};
+    trace_persistent<false>(s, (uint64_t)b.counters[C_ACTIVE_A + cur], &b.counters[C_WORK_EXTEND], sink, tune);
+}
+
+struct ShadowSink {
+    PathBuffers b;
+    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+        const uint32_t slot = b.q_shadow[i];
+        const float4 ro = b.sh_o[slot], rd = b.sh_d[slot];
+        *o = mk(ro.x, ro.y, ro.z);
+        *d = mk(rd.x, rd.y, rd.z);
+        *t_max = ro.w;
+        return true;
+    }
+    PB2_D void closest(uint64_t, uint32_t, float, float, float, float) const {}
+    PB2_D void occluded(uint64_t i, bool occ) const { b.occluded[b.q_shadow[i]] = occ ? 1 : 0; }
+};
+__global__ void __launch_bounds__(128, 8) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
+    const ShadowSink sink{b};
+    trace_persistent<true>(s, (uint64_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
+}
+
+struct MisSink {
+    PathBuffers b;
+    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+        const uint32_t slot = b.q_mis[i];
+        const float4 ro = b.mis_o[slot], rd = b.mis_d[slot];
+        *o = mk(ro.x, ro.y, ro.z);
+        *d = mk(rd.x, rd.y, rd.z);
+        *t_max = kInf;
+        return true;
+    }
+    PB2_D void closest(uint64_t i, uint32_t prim, float, float, float, float) const { b.mis_prim[b.q_mis[i]] = prim; }
+    PB2_D void occluded(uint64_t, bool) const {}
+};
+__global__ void __launch_bounds__(128, 8) k_mis(SceneView s, PathBuffers b, TraceTuning tune) {
+    const MisSink sink{b};
+    trace_persistent<false>(s, (uint64_t)b.counters[C_MIS], &b.counters[C_WORK_MIS], sink, tune);
+}
+
+// ---- shade -----------------------------------------------------------------------------------------------------------------
+struct Vertex {           // SurfaceInteraction subset rebuilt from the hit record (triangle.rs:193-250, D59)
+    vec3 p, err, n, dpdu;
+};
+__device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, uint32_t prim, float b0, float b1, float b2) {
+    const uint32_t slot = __ldg(s.slot_of_prim + prim);
+    const float4 a = ldg4(s.tris + 3ull * slot), b = ldg4(s.tris + 3ull * slot + 1), c = ldg4(s.tris + 3ull * slot + 2);
+    const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
+    Vertex v;
+    const float xs = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x)) + fabsf(b2 * p2.x);
+    const float ys = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y)) + fabsf(b2 * p2.y);
+    const float zs = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z)) + fabsf(b2 * p2.z);
+    v.err = mk(xs, ys, zs) * gammaf_(7.0f);
+    v.p = (p0 * b0 + p1 * b1) + p2 * b2;
+    v.n = unit(cross3(p0 - p2, p1 - p2));
+    vec3 dv;
+    tri_frame(p0, p1, p2, &v.dpdu, &dv);
+    return v;
+}
+__device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+
+// estimate_direct (integrator.rs:136-266) up to the two visibility queries: fills the NEE record of `slot`.
+__device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeView& sh, const PathBuffers& b, uint32_t slot, const Vertex& v, vec3 wo,
+                                                const Bsdf& bsdf, const DLight& light, float pick_pdf, float ul0, float ul1, float us0,
+                                                float us1, rgb3 beta) {
+    const unsigned flags = kAllLobes & ~kSpecular;                       // D23 FIX
+    const rgb3 l_emit = mkc(light.l[0], light.l[1], light.l[2]);
+    const bool delta = light.type == 0;                                  // light.rs:28-31, D24 FIX
+    vec3 wi = mk(0.f, 0.f, 0.f);
+    float light_pdf = 0.0f, scattering_pdf = 0.0f;
+    rgb3 li = gray(0.0f);
+    vec3 sh_o = mk(0.f, 0.f, 0.f), sh_d = mk(0.f, 0.f, 0.f);
+    const vec3 lp0 = ld3(light.p0), lp1 = ld3(light.p1), lp2 = ld3(light.p2);
+    if (delta) {                                                         // point.rs:47-66
+        const vec3 pl = ld3(light.p);
+        wi = unit(pl - v.p);
+        light_pdf = 1.0f;
+        li = l_emit / len2(pl - v.p);
+        sh_o = offset_ray_origin(v.p, v.err, v.n, pl - v.p);             // interaction.rs:146-153
+        const vec3 target = offset_ray_origin(pl, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), sh_o - pl);
+        sh_d = target - sh_o;
+    } else {                                                             // diffuse.rs:60-81, shape.rs:38-53, triangle.rs:330-348
+        const float su0 = sqrtf(ul0);
+        const float b0 = 1.0f - su0, b1 = ul1 * su0;                     // sampling.rs:275-278
+        const float b2 = (1.0f - b0) - b1;
+        const vec3 ps = (lp0 * b0 + lp1 * b1) + lp2 * b2;
+        const vec3 ns = unit(cross3(lp1 - lp0, lp2 - lp0));
+        const vec3 pe = ((abs3(lp0 * b0) + abs3(lp1 * b1)) + abs3(lp2 * b2)) * gammaf_(6.0f);
+        float pdf = 1.0f / light.area;
+        vec3 w = ps - v.p;
+        if (len2(w) == 0.0f) pdf = 0.0f;
+        else {
+            w = unit(w);
+            pdf = pdf * (len2(v.p - ps) / fabsf(dot3(ns, -w)));
+            if (isinf(pdf)) pdf = 0.0f;
+        }
+        if (pdf == 0.0f || len2(ps - v.p) == 0.0f) { light_pdf = 0.0f; }
+        else {
+            light_pdf = pdf;
+            wi = unit(ps - v.p);
+            li = (light.two_sided || dot3(ns, -wi) > 0.0f) ? l_emit : gray(0.0f);      // D55 FIX
+            sh_o = offset_ray_origin(v.p, v.err, v.n, ps - v.p);
+            const vec3 target = offset_ray_origin(ps, pe, ns, sh_o - ps);
+            sh_d = target - sh_o;
+        }
+    }
+    unsigned pending = 0u;
+    rgb3 t1 = gray(0.0f), t2 = gray(0.0f);
+    if (light_pdf > 0.0f && !black(li)) {
+        scattering_pdf = bsdf_pdf(bsdf, wo, wi, flags);
+        const rgb3 f = bsdf_f(bsdf, wo, wi, flags) * fabsf(dot3(wi, bsdf.ns));
+        if (!black(f)) {
+            pending |= 1u;                                               // VisibilityTester::un_occluded decides (D25 FIX)
+            t1 = delta ? li * f / light_pdf : li * f * power_heuristic(light_pdf, scattering_pdf) / light_pdf;
+        }
+    }
+    vec3 mis_o = mk(0.f, 0.f, 0.f), mis_d = mk(0.f, 0.f, 1.f);
+    if (!delta) {
+        unsigned sampled = 0u;
+        rgb3 f = bsdf_sample_f(bsdf, wo, &wi, us0, us1, &scattering_pdf, flags, &sampled);
+        f = f * fabsf(dot3(wi, bsdf.ns));
+        const bool sampled_specular = (sampled & kSpecular) != 0u;
+        if (!black(f) && scattering_pdf > 0.0f) {
+            float weight = 1.0f;
+            bool go = true;
+            const vec3 ro = offset_ray_origin(v.p, v.err, v.n, wi);      // it.spawn_ray(wi)
+            if (!sampled_specular) {
+                // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): the light's own triangle
+                const RayCtx rc = make_ray_ctx(ro, wi);
+                float t, lb0, lb1, lb2;
+                vec3 du, dv;
+                if (!tri_test(rc, kInf, lp0, lp1, lp2, &t, &lb0, &lb1, &lb2) || !tri_frame(lp0, lp1, lp2, &du, &dv)) go = false;
+                else {
+                    const vec3 p_l = (lp0 * lb0 + lp1 * lb1) + lp2 * lb2;
+                    const vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                    float lp = len2(v.p - p_l) / (fabsf(dot3(n_l, -wi)) * light.area);
+                    if (isinf(lp)) lp = 0.0f;
+                    if (lp == 0.0f) go = false;
+                    else weight = power_heuristic(scattering_pdf, lp);
+                }
+            }
+            if (go) {
+                // li = light_isect.le(-wi) if the closest hit is this light's triangle (D56 FIX); its normal is known here
+                const vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                const rgb3 lmis = (light.two_sided || dot3(n_l, -wi) > 0.0f) ? l_emit : gray(0.0f);
+                if (!black(lmis)) {
+                    pending |= 2u;
+                    t2 = lmis * f * gray(1.0f) * weight / scattering_pdf;
+                    mis_o = ro;
+                    mis_d = wi;
+                }
+            }
+        }
+    }
+    if (pending == 0u) return;
+    b.sh_o[slot] = make_float4(sh_o.x, sh_o.y, sh_o.z, 1.0f - PB2_SHADOW_EPS);
+    b.sh_d[slot] = make_float4(sh_d.x, sh_d.y, sh_d.z, pick_pdf);
+    b.t1[slot] = make_float4(t1.r, t1.g, t1.b, __uint_as_float(pending));
+    b.mis_o[slot] = make_float4(mis_o.x, mis_o.y, mis_o.z, 0.0f);
+    b.mis_d[slot] = make_float4(mis_d.x, mis_d.y, mis_d.z, 0.0f);
+    b.t2[slot] = make_float4(t2.r, t2.g, t2.b, __uint_as_float(light.prim));
+    b.beta_nee[slot] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+    queue_push(&b.counters[C_NEE], b.q_nee, slot);
+    if (pending & 1u) queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
+    if (pending & 2u) queue_push(&b.counters[C_MIS], b.q_mis, slot);
+    (void)s;
+}
+
+// One path vertex of PathIntegrator::li (path.rs:79-209) for every hit of material type `mat`.
+__global__ void __launch_bounds__(kThreads) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int mat, int cur) {
+    const uint64_t n = b.counters[C_MAT0 + mat];
+    const uint32_t* queue = b.q_mat[mat];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        const uint4 h = b.hit[slot];
+        const float4 rd = b.ray_d[slot];
+        float4 Lf = b.L[slot];
+        float4 bt = b.beta[slot];
+        rgb3 L = mkc(Lf.x, Lf.y, Lf.z), beta = mkc(bt.x, bt.y, bt.z);
+        float eta_scale = bt.w;
+        const unsigned state = __float_as_uint(Lf.w);
+        unsigned bounces = state & 0xFFFFu;
+        const bool specular_bounce = (state >> 16) & 1u;
+        const Vertex v = rebuild_vertex(s, h.x, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w));
+        const vec3 wo = -mk(rd.x, rd.y, rd.z);
+        if (bounces == 0u || specular_bounce) {                          // path.rs:80-82 + interaction.rs:387-395
+            const int li = sh.tri_light[h.x];
+            if (li >= 0) {
+                const DLight& lt = sh.lights[li];
+                const rgb3 le = (lt.two_sided || dot3(v.n, wo) > 0.0f) ? mkc(lt.l[0], lt.l[1], lt.l[2]) : gray(0.0f);
+                L = L + beta * le;
+            }
+        }
+        bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
+        if (alive) {
+            const Bsdf bsdf = make_bsdf(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
+            Pcg32 rng;
+            rng.state = b.rng[slot];
+            rng.inc = (slot_info(map, film, slot).seq << 1) | 1ull;
+            if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
+                float pick_pdf;
+                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next_float(), &pick_pdf);
+                if (pick_pdf != 0.0f) {
+                    const float ul0 = rng.next_float(), ul1 = rng.next_float();
+                    const float us0 = rng.next_float(), us1 = rng.next_float();
+                    direct_lighting(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
+                }
+            }
+            const float u0 = rng.next_float(), u1 = rng.next_float();                     // path.rs:123-134
+            vec3 wi = mk(0.f, 0.f, 0.f);
+            float pdf = 0.0f;
+            unsigned sampled = 0u;
+            const rgb3 f = bsdf_sample_f(bsdf, wo, &wi, u0, u1, &pdf, kAllLobes, &sampled);
+            if (black(f) || pdf == 0.0f) alive = false;
+            else {
+                beta = beta * (f * (fabsf(dot3(wi, bsdf.ns)) / pdf));
+                const bool spec = (sampled & kSpecular) != 0u;
+                if (spec && (sampled & kTransmission)) {
+                    const float eta = bsdf.eta;
+                    eta_scale = eta_scale * ((dot3(wo, v.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta));
+                }
+                const vec3 o = offset_ray_origin(v.p, v.err, v.n, wi);
+                const rgb3 rr_beta = beta * eta_scale;                                   // path.rs:200-207, D27 KEEP
+                if (max_channel(rr_beta) < pp.rr_threshold && bounces > 3u) {
+                    const float q = fminf(1.0f - max_channel(rr_beta), 0.05f);
+                    if (rng.next_float() < q) alive = false;
+                    else beta = beta / (1.0f - q);
+                }
+                if (alive) {
+                    bounces += 1u;
+                    b.ray_o[slot] = make_float4(o.x, o.y, o.z, kInf);
+                    b.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, 0.0f);
+                    b.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
+                    b.rng[slot] = rng.state;
+                    Lf.w = __uint_as_float(bounces | ((spec ? 1u : 0u) << 16));
+                    queue_push(&b.counters[C_ACTIVE_A + (cur ^ 1)], b.q_active[cur ^ 1], slot);
+                }
+            }
+        }
+        b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
+    }
+}
+
+// l += beta * (estimate_direct / light_pdf) once both visibility queries are back (integrator.rs:178-191,243-261,:133).
+__global__ void __launch_bounds__(kThreads) k_resolve(PathBuffers b) {
+    const uint64_t n = b.counters[C_NEE];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = b.q_nee[i];
+        const float4 t1 = b.t1[slot], t2 = b.t2[slot], bn = b.beta_nee[slot];
+        const unsigned pending = __float_as_uint(t1.w);
+        rgb3 ld = gray(0.0f);
+        if ((pending & 1u) && !b.occluded[slot]) ld = ld + mkc(t1.x, t1.y, t1.z);
+        if ((pending & 2u) && b.mis_prim[slot] == __float_as_uint(t2.w)) ld = ld + mkc(t2.x, t2.y, t2.z);
+        const float pick_pdf = b.sh_d[slot].w;
+        float4 Lf = b.L[slot];
+        const rgb3 L = mkc(Lf.x, Lf.y, Lf.z) + mkc(bn.x, bn.y, bn.z) * (ld / pick_pdf);
+        b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.counters[T_SHADOW] += b.counters[C_SHADOW];
+        b.counters[T_MIS] += b.counters[C_MIS];
+    }
+}
+
+// ---- Film ------------------------------------------------------------------------------------------------------------------
+// FilmTile::add_sample footprint (film.rs:259-294 with D43/D44): calls fn(px, py, filter_weight).
+template <class F>
+__device__ __forceinline__ void film_footprint(const FilmView& f, float pfx, float pfy, F&& fn) {
+    const float dx = pfx - 0.5f, dy = pfy - 0.5f;
+    int x0 = (int)ceilf(dx - f.radius_x), y0 = (int)ceilf(dy - f.radius_y);
+    int x1 = (int)floorf(dx + f.radius_x) + 1, y1 = (int)floorf(dy + f.radius_y) + 1;
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, f.res_x); y1 = min(y1, f.res_y);
+    const float inv_rx = 1.0f / f.radius_x, inv_ry = 1.0f / f.radius_y;
+    for (int y = y0; y < y1; ++y) {
+        const int iy = min(15, (int)floorf(fabsf(((float)y - dy) * inv_ry * 16.0f)));
+        for (int x = x0; x < x1; ++x) {
+            const int ix = min(15, (int)floorf(fabsf(((float)x - dx) * inv_rx * 16.0f)));
+            fn(x, y, f.table[iy * 16 + ix]);
+        }
+    }
+}
+__device__ __forceinline__ rgb3 guard_radiance(rgb3 L) {                  // integrator.rs:455-457, D22 FIX
+    if (any_nan(L) || luminance(L) < -1e-5f || isinf(luminance(L))) return gray(0.0f);
+    return L;
+}
+__device__ __forceinline__ void film_atomic_add(const FilmView& f, int px, int py, rgb3 c, float w) {
+    float* a = reinterpret_cast<float*>(f.acc + ((size_t)py * f.res_x + px));
+    atomicAdd(a, c.r); atomicAdd(a + 1, c.g); atomicAdd(a + 2, c.b); atomicAdd(a + 3, w);
+}
+__device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long* counters, unsigned long long order, int px, int py, rgb3 c, float w) {
+    const unsigned long long pos = atomicAdd(&counters[C_STRAYS], 1ull);
+    if (pos < f.stray_capacity) {
+        f.stray_keys[pos] = ((unsigned long long)((size_t)py * f.res_x + px) << 40) | (order & 0xFFFFFFFFFFull);
+        f.stray_vals[pos] = make_float4(c.r, c.g, c.b, w);
+    } else {
+        atomicAdd(&counters[C_STRAY_OVERFLOW], 1ull);                     // still accumulated, but in arrival order
+        film_atomic_add(f, px, py, c, w);
+    }
+}
+
+// Exact mode (box filter, r = 0.5): one thread per pixel adds that pixel's samples of the batch in sample order.
+__global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map, FilmView f, PathBuffers b, int n_samples) {
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < map.n_pix; pix += gridDim.x * blockDim.x) {
+        const int x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w), y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
+        const bool inside = x >= 0 && y >= 0 && x < f.res_x && y < f.res_y;
+        float4 acc = inside ? f.acc[(size_t)y * f.res_x + x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_samples; ++s) {
+            const uint64_t slot = (uint64_t)s * map.n_pix + pix;
+            const float4 Lf = b.L[slot];
+            const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
+            const SlotInfo si = slot_info(map, f, slot);
+            Pcg32 rng;
+            rng.set_sequence(si.seq);
+            const float pfx = (float)x + rng.next_float();
+            const float pfy = (float)y + rng.next_float();
+            film_footprint(f, pfx, pfy, [&](int px, int py, float fw) {
+                const rgb3 c = L * 1.0f * fw;                            // l * sample_weight * filter_weight
+                if (px == x && py == y) { acc.x += c.r; acc.y += c.g; acc.z += c.b; acc.w += fw; }
+                else film_stray(f, b.counters, si.seq, px, py, c, fw);
+            });
+        }
+        if (inside) f.acc[(size_t)y * f.res_x + x] = acc;
+    }
+}
+// General mode: one thread per path, atomics into the call's accumulators.
+__global__ void __launch_bounds__(kThreads) k_film_accumulate_atomic(uint64_t n, PathMap map, FilmView f, PathBuffers b) {
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 Lf = b.L[slot];
+        const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
+        const SlotInfo si = slot_info(map, f, slot);
+        Pcg32 rng;
+        rng.set_sequence(si.seq);
+        const float pfx = (float)si.x + rng.next_float();
+        const float pfy = (float)si.y + rng.next_float();
+        film_footprint(f, pfx, pfy, [&](int px, int py, float fw) { film_atomic_add(f, px, py, L * 1.0f * fw, fw); });
+    }
+}
+// Sorted strays: the first thread of each run of equal target pixels adds the whole run in key order.
+__global__ void __launch_bounds__(kThreads) k_apply_strays(FilmView f, const unsigned long long* keys, const uint32_t* index, const unsigned long long* counters) {
+    unsigned long long n = counters[C_STRAYS];
+    if (n > f.stray_capacity) n = f.stray_capacity;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long pixel = keys[j] >> 40;
+        if (j > 0 && (keys[j - 1] >> 40) == pixel) continue;
+        float4 acc = f.acc[pixel];
+        for (unsigned long long k = j; k < n && (keys[k] >> 40) == pixel; ++k) {
+            const float4 v = f.stray_vals[index[k]];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        f.acc[pixel] = acc;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_fill_index(uint32_t* idx, unsigned long long* keys, uint32_t cap, const unsigned long long* counters) {
+    unsigned long long n = counters[C_STRAYS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        idx[i] = i;
+        if (i >= n) keys[i] = ~0ull;
+    }
+}
+// Film::merge_film_tile (film.rs:111-123): XYZ of the call's RGB sums is added to the film; the call accumulators reset.
+__global__ void __launch_bounds__(kThreads) k_film_merge(FilmView f, unsigned long long* counters) {
+    const size_t n = (size_t)f.res_x * f.res_y;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = f.acc[i];
+        float x, y, z;
+        to_xyz(mkc(a.x, a.y, a.z), &x, &y, &z);
+        float4 p = f.xyzw[i];
+        p.x += x; p.y += y; p.z += z; p.w += a.w;
+        f.xyzw[i] = p;
+        f.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counters) counters[C_STRAYS] = 0;
+}
+// FilmTile::add_sample for explicit samples (pb2_film_add_samples): atomics, any filter.
+__global__ void __launch_bounds__(kThreads) k_film_add_samples(FilmView f, const float2* pf, const float* L, const float* w, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const rgb3 c = mkc(L[3 * i], L[3 * i + 1], L[3 * i + 2]);
+        const float sw = w[i];
+        film_footprint(f, pf[i].x, pf[i].y, [&](int px, int py, float fw) { film_atomic_add(f, px, py, c * sw * fw, fw); });
+    }
+}
+// Film::write_image (film.rs:153-178)
+__global__ void __launch_bounds__(kThreads) k_film_resolve(FilmView f, float scale, float* rgb) {
+    const size_t n = (size_t)f.res_x * f.res_y;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 p = f.xyzw[i];
+        rgb3 c = from_xyz(p.x, p.y, p.z);
+        if (p.w != 0.0f) {
+            const float inv = 1.0f / p.w;
+            c = mkc(fmaxf(c.r * inv, 0.0f), fmaxf(c.g * inv, 0.0f), fmaxf(c.b * inv, 0.0f));
+        }
+        rgb[3 * i] = c.r * scale; rgb[3 * i + 1] = c.g * scale; rgb[3 * i + 2] = c.b * scale;
+    }
+}
+__global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, float* L_out, float* pf_out) {
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 Lf = b.L[slot];
+        L_out[3 * slot] = Lf.x; L_out[3 * slot + 1] = Lf.y; L_out[3 * slot + 2] = Lf.z;
+        const SlotInfo si = slot_info(map, f, slot);
+        Pcg32 rng;
+        rng.set_sequence(si.seq);
+        pf_out[2 * slot] = (float)si.x + rng.next_float();
+        pf_out[2 * slot + 1] = (float)si.y + rng.next_float();
+    }
+}
+
+unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
+    const uint64_t want = (n + kThreads - 1) / kThreads;
+    const uint64_t cap = (uint64_t)wf->sm_count * per_sm;
+    return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+// All bounces of one batch of `n` path slots.
+void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film, const PathMap& map,
+                 const PathParams& pp, uint64_t n, cudaStream_t st) {
+    PathBuffers& b = wf->b;
+    const TraceTuning tune = trace_tuning();
+    const unsigned trace_grid = (unsigned)wf->sm_count * 8u;
+    k_raygen<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, cam, b);
+    int launches = 1;
+    for (int depth = 0; depth <= pp.max_depth; ++depth) {
+        const int cur = depth & 1;
+        k_iter_begin<<<1, 32, 0, st>>>(b, cur);
+        k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
+        for (int mat = 0; mat < 3; ++mat) k_shade<<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, mat, cur);
+        if (depth < pp.max_depth && sh.n_lights > 0) {
+            k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
+            k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);
+            k_resolve<<<grid_for(wf, n, 4), kThreads, 0, st>>>(b);
+            launches += 3;
+        }
+        launches += 5;
+    }
+    wf->totals[4] += (uint64_t)launches;
+}
+
+}  // namespace
+
+int wavefront_create(uint64_t capacity, Wavefront** out) {
+    Wavefront* wf = new Wavefront();
+    wf->capacity = capacity;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&wf->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    // one arena: 13 float4/uint4 arrays, rng, occluded, mis_prim, 8 queues, counters
+    const size_t f4 = capacity * 16;
+    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + capacity + 8 * capacity * 4 + C_COUNT * 8 + 4096;
+    cudaError_t e = cudaMalloc(&wf->arena, bytes);
+    if (e != cudaSuccess) { delete wf; *out = nullptr; return (int)e; }
+    char* p = (char*)wf->arena;
+    auto take = [&](size_t n) { char* r = p; p += (n + 255) & ~(size_t)255; return r; };
+    PathBuffers& b = wf->b;
+    b.ray_o = (float4*)take(f4); b.ray_d = (float4*)take(f4); b.beta = (float4*)take(f4); b.L = (float4*)take(f4);
+    b.hit = (uint4*)take(f4);
+    b.sh_o = (float4*)take(f4); b.sh_d = (float4*)take(f4); b.t1 = (float4*)take(f4);
+    b.mis_o = (float4*)take(f4); b.mis_d = (float4*)take(f4); b.t2 = (float4*)take(f4); b.beta_nee = (float4*)take(f4);
+    b.rng = (unsigned long long*)take(capacity * 8);
+    b.mis_prim = (uint32_t*)take(capacity * 4);
+    b.occluded = (uint8_t*)take(capacity);
+    for (int i = 0; i < 2; ++i) b.q_active[i] = (uint32_t*)take(capacity * 4);
+    for (int i = 0; i < 3; ++i) b.q_mat[i] = (uint32_t*)take(capacity * 4);
+    b.q_shadow = (uint32_t*)take(capacity * 4);
+    b.q_mis = (uint32_t*)take(capacity * 4);
+    b.q_nee = (uint32_t*)take(capacity * 4);
+    b.counters = (unsigned long long*)take(C_COUNT * 8);
+    cudaMemset(b.counters, 0, C_COUNT * 8);
+    *out = wf;
+    return 0;
+}
+
+void wavefront_destroy(Wavefront* wf) {
+    if (!wf) return;
+    if (wf->arena) cudaFree(wf->arena);
+    delete wf;
+}
+
+int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
+                     const PathParams& pp, int spp, int sample_begin, int sample_end, cudaStream_t st) {
+    const uint64_t n_pix = (uint64_t)film.sb_w * (uint64_t)film.sb_h;
+    if (n_pix == 0 || sample_end <= sample_begin) return 0;
+    const int per_batch = (int)std::max<uint64_t>(1, wf->capacity / n_pix);
+    for (int s0 = sample_begin; s0 < sample_end; s0 += per_batch) {
+        const int ns = std::min(per_batch, sample_end - s0);
+        PathMap map{(uint32_t)n_pix, spp, s0, nullptr, nullptr};
+        const uint64_t n = n_pix * (uint64_t)ns;
+        trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
+        if (film.exact) k_film_accumulate_exact<<<grid_for(wf, n_pix), kThreads, 0, st>>>(map, film, wf->b, ns);
+        else k_film_accumulate_atomic<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, wf->b);
+        wf->totals[4] += 1;
+    }
+    film_finish(film, wf->b.counters, st);
+    return 0;
+}
+
+int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
+                 const PathParams& pp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L, float* d_pfilm,
+                 cudaStream_t st) {
+    if (n == 0) return 0;
+    PathMap map{(uint32_t)std::max<uint64_t>(1, n), spp, 0, d_xy, d_s};
+    trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
+    k_copy_li<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, wf->b, d_L, d_pfilm);
+    return 0;
+}
+
+// Ordered application of the strays (exact mode), then merge of the call's sums into the film.
+void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st) {
+    const unsigned grid = 148 * 4;
+    if (film.exact && counters && film.stray_capacity) {
+        // scratch: sorted keys + index pairs live behind the primary arrays (allocated 2x by the film)
+        unsigned long long* keys_in = film.stray_keys;
+        unsigned long long* keys_out = film.stray_keys + film.stray_capacity;
+        uint32_t* idx_in = reinterpret_cast<uint32_t*>(film.stray_keys + 2ull * film.stray_capacity);
+        uint32_t* idx_out = idx_in + film.stray_capacity;
+        void* temp = idx_out + film.stray_capacity;
+        k_fill_index<<<grid, kThreads, 0, st>>>(idx_in, keys_in, film.stray_capacity, counters);
+        size_t temp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)film.stray_capacity, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)film.stray_capacity, 0, 64, st);
+        k_apply_strays<<<grid, kThreads, 0, st>>>(film, keys_out, idx_out, counters);
+    }
+    k_film_merge<<<grid, kThreads, 0, st>>>(film, counters);
+}
+
+size_t film_sort_scratch_bytes(uint32_t capacity) {
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)capacity, 0, 64, (cudaStream_t)0);
+    return temp_bytes + 256;
+}
+
+void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_film_add_samples<<<148 * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_L, d_w, n);
+    k_film_merge<<<148 * 4, kThreads, 0, st>>>(film, nullptr);
+}
+
+void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st) {
+    k_film_resolve<<<148 * 4, kThreads, 0, st>>>(film, scale, d_rgb);
+}
+
+}  // namespace pb2

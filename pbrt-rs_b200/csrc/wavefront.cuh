@@ -1,0 +1,106 @@
+// wavefront.cuh — data layout of the wavefront PathIntegrator (SoA path state + stage queues in HBM).
+//
+// One path slot per (pixel, sample) of the current batch; slot i = s_local * n_pixels + pixel, so a warp holds
+// neighbouring pixels of one sample index.  Every array below is indexed by slot (coalesced float4 / uint4 accesses);
+// stages talk to each other only through these arrays and the uint32 slot queues.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.hpp"
+#include "shade.cuh"
+#include "traverse.cuh"
+
+namespace pb2 {
+
+// Device-side scene tables for shading (indexed by the caller's primitive id).
+struct ShadeView {
+    const uint32_t* tri_material;
+    const int32_t* tri_light;
+    const DMaterial* mats;
+    const DLight* lights;
+    int n_lights;
+    const float* light_func;      // Distribution1D func[n_lights]
+    const float* light_cdf;       // cdf[n_lights + 1]
+    float light_func_int;
+};
+
+// Film geometry: image, sample bounds (film.rs:76-81 with D42), filter radius and its 16x16 table (film.rs:53-63).
+struct FilmView {
+    int res_x, res_y;
+    int sb_x0, sb_y0, sb_w, sb_h;
+    float radius_x, radius_y;
+    int exact;                    // box filter, r = 0.5: ordered accumulation (bit-reproducible)
+    const float* table;           // 256 floats
+    float4* acc;                  // per image pixel: RGB sum + filter weight sum of the current render call
+    float4* xyzw;                 // per image pixel: X, Y, Z, weight accumulators (the Film itself)
+    unsigned long long* stray_keys;
+    float4* stray_vals;
+    uint32_t stray_capacity;
+};
+
+// slot -> (pixel, sample index)
+struct PathMap {
+    uint32_t n_pix;               // sample-bounds pixels per sample index
+    int spp;
+    int sample0;
+    const int32_t* explicit_xy;   // pb2_path_li: explicit pixel coordinates, else null
+    const uint32_t* explicit_s;
+};
+
+enum Counter : int {
+    C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6, C_NEE = 7,
+    C_WORK_EXTEND = 8, C_WORK_SHADOW = 9, C_WORK_MIS = 10, C_STRAYS = 11, C_STRAY_OVERFLOW = 12,
+    T_CAMERA = 16, T_EXTEND = 17, T_SHADOW = 18, T_MIS = 19, T_LAUNCHES = 20, C_COUNT = 24
+};
+
+struct PathBuffers {
+    float4* ray_o;        // xyz origin, w = t_max
+    float4* ray_d;        // xyz direction
+    float4* beta;         // rgb throughput, w = eta_scale
+    float4* L;            // rgb radiance, w = bits: bounces | specular_bounce << 16
+    unsigned long long* rng;
+    uint4* hit;           // prim id, b0, b1, b2 (float bits)
+    // next-event estimation record of the current bounce
+    float4* sh_o;         // shadow ray origin, w = t_max
+    float4* sh_d;         // shadow ray direction, w = light pick pdf
+    float4* t1;           // light-sampling term (rgb), w = bits: 1 = shadow ray pending, 2 = MIS ray pending
+    float4* mis_o;        // MIS ray origin
+    float4* mis_d;        // MIS ray direction
+    float4* t2;           // BSDF-sampling term (rgb), w = light primitive id bits
+    float4* beta_nee;     // throughput before the bounce
+    uint8_t* occluded;
+    uint32_t* mis_prim;
+    uint32_t* q_active[2];
+    uint32_t* q_mat[3];
+    uint32_t* q_shadow;
+    uint32_t* q_mis;
+    uint32_t* q_nee;
+    unsigned long long* counters;
+};
+
+struct PathParams {
+    int max_depth;
+    float rr_threshold;
+};
+
+struct Wavefront {
+    uint64_t capacity = 0;
+    PathBuffers b{};
+    void* arena = nullptr;
+    int sm_count = 0;
+    uint64_t totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+int wavefront_create(uint64_t capacity, Wavefront** out);
+int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
+                     const PathParams& pp, int spp, int sample_begin, int sample_end, cudaStream_t st);
+int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
+                 const PathParams& pp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L, float* d_pfilm,
+                 cudaStream_t st);
+void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
+void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
+void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st);
+
+}  // namespace pb2
