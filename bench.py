@@ -120,6 +120,137 @@ def host_info():
     return os.cpu_count() or 1, model
 
 
+def path_steps(args):
+    return max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))
+
+
+def bench_path_c2(pb2, scenes, torch, args, dist, world):
+    """Path-traced Msamples/s on BASELINE config 1 (Cornell box, maxdepth 5, 512x512 @ 64 spp, box filter): one step = one
+    full frame (16.8 M camera samples) rendered into a device-resident Film.  e2e adds the film read-back to the host."""
+    sc = scenes.scene_c2()
+    cam = scenes.C2_CAMERA
+    pk = scenes.C2_PATH
+    accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4)
+    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    integ = pb2.PathIntegrator(accel, camera, **pk)
+    film = pb2.Film(cam["res"])
+    stream = torch.cuda.current_stream().cuda_stream
+    n_samples = cam["res"][0] * cam["res"][1] * pk["spp"]
+    steps, warmup = path_steps(args)
+    for _ in range(warmup):
+        integ.render(film, stream=stream)
+    torch.cuda.synchronize()
+    c0 = integ.counters()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        film.clear()
+        a.record()
+        integ.render(film, stream=stream)
+        b.record()
+    torch.cuda.synchronize()
+    c1 = integ.counters()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        film.clear()
+        integ.render(film, stream=stream)
+        xyzw = film.read_xyzw()
+    e2e_s = time.perf_counter() - t0
+    tot = float(sum(ms))
+    if world > 1:
+        t = torch.tensor([tot, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot, e2e_s = float(t[0]), float(t[1])
+    rays = {k: (c1[k] - c0[k]) / steps for k in ("extend_rays", "shadow_rays", "mis_rays")}
+    return {"workload": "C2: Cornell box (32 triangles, matte, quad area light), PathIntegrator maxdepth=5, 512x512 @ 64 spp, RandomSampler "
+                        "streams per (pixel, sample), box filter", "unit": "Msamples/s", "value": world * n_samples * steps / (tot * 1e-3) / 1e6,
+            "ms_per_frame": tot / steps, "samples_per_frame": n_samples,
+            "e2e": {"value": world * n_samples * steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 128,
+                    "d2h_bytes_per_step": int(xyzw.nbytes), "api": "pb2_render_path + pb2_film_read_xyzw"},
+            "rays_per_frame": rays, "mrays_per_s": sum(rays.values()) / (tot / steps * 1e-3) / 1e6,
+            "kernel_launches_per_frame": (c1["kernel_launches"] - c0["kernel_launches"]) / steps,
+            "mean_rgb": [float(v) for v in pb2_mean_rgb(film)]}, (accel, camera, integ, film, sc)
+
+
+def pb2_mean_rgb(film):
+    return film.resolve_rgb().mean(axis=(0, 1))
+
+
+def bench_path_cpu(orc_mod, scenes, sc, gpu_film_xyzw):
+    """CPU baseline for path tracing: the oracle's SamplerIntegrator::render on a bounded sample (2 of the 64 spp of C2)
+    with all host threads, and a parity check of that sample range against the GPU."""
+    from oracle import oracle_path as OP
+    cam = scenes.C2_CAMERA
+    pk = dict(scenes.C2_PATH)
+    ref = OP.Scene(sc, 4)
+    fd = OP.film_desc(cam["res"])
+    pd = OP.path_desc(sample_begin=0, sample_end=2, **pk)
+    xyzw, dt = ref.render(cam, fd, pd, mode=1)
+    n = cam["res"][0] * cam["res"][1] * 2
+    cores, model = host_info()
+    return {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": model,
+            "sample": "sample indices [0,2) of the 64 spp of every pixel (524,288 camera samples), render time only"}, xyzw
+
+
+def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
+    """BASELINE config 4 shape: the C4 scene (matte / plastic / glass spheres, area + point light, maxdepth 8, power light
+    distribution) at 3840x2160; every GPU renders its own `spp_per_gpu` sample indices of every pixel (weak scaling) and the
+    per-GPU films are summed with one ncclReduce to rank 0."""
+    sc = scenes.scene_c4()
+    cam = scenes.C5_CAMERA
+    spp_per_gpu = 4
+    pk = dict(scenes.C5_PATH, spp=spp_per_gpu * world)
+    accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4)
+    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    integ = pb2.PathIntegrator(accel, camera, **pk)
+    film = pb2.Film(cam["res"])
+    stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        uid = [pb2.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pb2.nccl_init(uid[0], rank, world)
+    steps, warmup = path_steps(args)
+    s0, s1 = rank * spp_per_gpu, (rank + 1) * spp_per_gpu
+
+    def frame(ev=None):
+        film.clear()
+        if ev:
+            ev[0].record()
+        integ.render(film, s0, s1, stream=stream)
+        if ev:
+            ev[1].record()
+        if world > 1:
+            film.reduce(0, stream=stream)
+        if ev:
+            ev[2].record()
+
+    for _ in range(warmup):
+        frame()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for ev in evs:
+        frame(ev)
+    torch.cuda.synchronize()
+    render_ms = float(sum(e[0].elapsed_time(e[1]) for e in evs))
+    reduce_ms = float(sum(e[1].elapsed_time(e[2]) for e in evs))
+    total_ms = float(sum(e[0].elapsed_time(e[2]) for e in evs))
+    if world > 1:
+        t = torch.tensor([render_ms, reduce_ms, total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        render_ms, reduce_ms, total_ms = (float(v) for v in t)
+    n_samples = cam["res"][0] * cam["res"][1] * spp_per_gpu * world
+    out = {"workload": f"C5 shape: {len(sc['idx'])}-triangle matte/plastic/glass room, maxdepth 8, 3840x2160, {spp_per_gpu} spp per GPU "
+                       f"({spp_per_gpu * world} spp total), one ncclReduce of the float4 film (132.7 MB) to rank 0",
+           "unit": "Msamples/s", "value": n_samples * steps / (total_ms * 1e-3) / 1e6, "ms_per_frame": total_ms / steps,
+           "render_ms": render_ms / steps, "film_reduce_ms": reduce_ms / steps, "film_reduce_frac_of_frame": reduce_ms / total_ms,
+           "film_reduce_frac_at_1024spp": (reduce_ms / steps) / ((render_ms / steps) * (1024.0 / world / spp_per_gpu) + reduce_ms / steps)}
+    if world > 1:
+        pb2.nccl_shutdown()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference hot path (oracle/; the Rust crate cannot be built —
     no rustc/cargo in the image), all host threads, on a bounded sample of the C3 pass."""
@@ -147,6 +278,7 @@ def run_reference(args):
     times = [step() for _ in range(args.steps)]
     total = float(sum(times))
     value = n_sample * args.steps / total / 1e6
+    path_cpu, _ = bench_path_cpu(orc, scenes, scenes.scene_c2(), None)
     line = {
         "impl": "reference", "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -156,7 +288,9 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
                          "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays per step), traversal time only"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of pbrt-rs BVHAccel/Triangle (oracle/); the Rust reference itself is not compilable here",
+        "path": {"workload": "C2: Cornell box, PathIntegrator maxdepth=5, 512x512, RandomSampler, box filter", "unit": "Msamples/s",
+                 "value": path_cpu["value"], "cpu_baseline": path_cpu},
+        "note": "CPU restatement of pbrt-rs BVHAccel/Triangle/PathIntegrator (oracle/); the Rust reference itself is not compilable here",
     }
     print(json.dumps(line), flush=True)
 
@@ -266,6 +400,12 @@ def main():
                       and np.array_equal(h_occ.numpy(), d_occ.cpu().numpy())
                       and np.array_equal(h_bhits.numpy(), d_bhits.view(torch.int32).cpu().numpy()))
 
+    # ---- path tracing (second half of the BASELINE metric) ----
+    dist_mod = dist if world > 1 else None
+    path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
+    path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world) if world > 1 else None
+    path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0])
+
     # ---- max over ranks ----
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -318,6 +458,16 @@ def main():
         cores, model = host_info()
         cpu_baseline = {"value": n_sample / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
                         "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays), traversal time only"}
+        # path tracing: oracle on sample indices [0,2) of C2, and the GPU film of the same range must equal it bit for bit
+        accel2, camera2, integ2, film2, sc2 = path_keep
+        path_cpu, ref_xyzw = bench_path_cpu(orc, scenes, sc2, None)
+        film2.clear()
+        integ2.render(film2, 0, 2)
+        g_xyzw = film2.read_xyzw()
+        path_c2["cpu_baseline"] = path_cpu
+        path_c2["parity"] = {"pixels_checked": int(g_xyzw.shape[0] * g_xyzw.shape[1]),
+                             "pixels_differing": int((g_xyzw.view(np.uint32) != ref_xyzw.view(np.uint32)).any(axis=2).sum()),
+                             "checked_against": "oracle SamplerIntegrator::render, per-(pixel,sample) sampler streams, samples [0,2)"}
     if rank == 0:
         line = {
             "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -331,8 +481,9 @@ def main():
             "kernel_ms": kernel_ms,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
                     "api": "pb2_intersect / pb2_intersect_p with pinned host buffers"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+            "path": path_c2, "path_multi_gpu": path_c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

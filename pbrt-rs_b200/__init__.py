@@ -115,7 +115,7 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise Pb2Error(-2, f"{LIB_PATH} is missing: run `make -C pbrt-rs_b200` (or __graft_entry__.build()); "
                            "there is no CPU fallback")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(LIB_PATH)
     vp, u64, i32, u32, f32 = C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_float
     L.pb2_last_error.restype = C.c_char_p
     sig = {
@@ -428,6 +428,17 @@ class PathIntegrator:
         check(lib().pb2_render_counters(self.accel.h, _p(out)))
         return dict(camera_samples=int(out[0]), extend_rays=int(out[1]), shadow_rays=int(out[2]), mis_rays=int(out[3]),
                     kernel_launches=int(out[4]), stray_overflow=int(out[5]))
+
+
+def partition_samples(spp, rank, world):
+    """Sample-index range of every pixel that GPU `rank` of `world` renders: contiguous, disjoint, covering
+    [0, spp); the first spp % world ranks take one extra index.  Every (pixel, sample) keeps its own sampler stream, so the
+    union over ranks draws exactly the random numbers a single GPU would."""
+    if world < 1 or not (0 <= rank < world) or spp < 0:
+        raise ValueError("bad partition arguments")
+    base, extra = divmod(spp, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
 
 
 def nccl_unique_id():

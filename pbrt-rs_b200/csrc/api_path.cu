@@ -1,4 +1,5 @@
 // api_path.cu — Film, wavefront PathIntegrator and NCCL entry points of include/pbrt_b200.h.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cmath>
@@ -165,8 +166,36 @@ static int ensure_wavefront(pb2_scene* scene, uint64_t min_capacity) {
     return PB2_OK;
 }
 
+// NCCL is bound at first use with dlopen instead of at link time: a process that also imports PyTorch must end up with
+// ONE libnccl.so.2 (PyTorch bundles a newer one than the system's, same SONAME), whichever side loads first.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
 static ncclComm_t g_comm = nullptr;
-static int g_rank = 0, g_nranks = 1;
+
+static int nccl_bind() {
+    if (g_nccl.lib) return PB2_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // already in the process (e.g. PyTorch's)?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return set_error(PB2_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    NcclApi a;
+    a.lib = h;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.Reduce = (decltype(a.Reduce))dlsym(h, "ncclReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Reduce || !a.GetErrorString)
+        return set_error(PB2_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return PB2_OK;
+}
 
 }  // namespace pb2
 
@@ -345,9 +374,11 @@ int pb2_render_counters(pb2_scene* scene, uint64_t out[8]) {
 int pb2_nccl_unique_id(char id[128]) {
     if (!id) return set_error(PB2_ERR_INVALID, "null id");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    int rc = nccl_bind();
+    if (rc) return rc;
     ncclUniqueId u;
-    ncclResult_t r = ncclGetUniqueId(&u);
-    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+    ncclResult_t r = g_nccl.GetUniqueId(&u);
+    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
     memcpy(id, &u, 128);
     return PB2_OK;
 }
@@ -355,17 +386,17 @@ int pb2_nccl_unique_id(char id[128]) {
 int pb2_nccl_init(const char id[128], int rank, int n_ranks) {
     if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(PB2_ERR_INVALID, "bad NCCL init arguments");
     if (g_comm) return set_error(PB2_ERR_STATE, "NCCL communicator already initialised");
+    int rc = nccl_bind();
+    if (rc) return rc;
     ncclUniqueId u;
     memcpy(&u, id, 128);
-    ncclResult_t r = ncclCommInitRank(&g_comm, n_ranks, u, rank);
-    if (r != ncclSuccess) { g_comm = nullptr; return set_error(PB2_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r)); }
-    g_rank = rank;
-    g_nranks = n_ranks;
+    ncclResult_t r = g_nccl.CommInitRank(&g_comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { g_comm = nullptr; return set_error(PB2_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     return PB2_OK;
 }
 
 int pb2_nccl_shutdown(void) {
-    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
     return PB2_OK;
 }
 
@@ -373,8 +404,8 @@ int pb2_film_reduce(pb2_film* f, int root, void* stream) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     if (!g_comm) return set_error(PB2_ERR_STATE, "pb2_nccl_init has not been called");
     const size_t count = (size_t)f->desc.res_x * f->desc.res_y * 4;
-    ncclResult_t r = ncclReduce(f->d_xyzw, f->d_xyzw, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
-    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclReduce: %s", ncclGetErrorString(r));
+    ncclResult_t r = g_nccl.Reduce(f->d_xyzw, f->d_xyzw, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
+    if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString(r));
     return PB2_OK;
 }
 
