@@ -396,6 +396,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clock_rec = clocks.stop()
+    import zlib
+    hits_crc = "%08x" % zlib.crc32(d_occ.cpu().numpy().tobytes(), zlib.crc32(d_bhits.cpu().numpy().tobytes(), zlib.crc32(d_hits.cpu().numpy().tobytes())))
     e2e_parity = bool(np.array_equal(h_hits.numpy(), d_hits.view(torch.int32).cpu().numpy())
                       and np.array_equal(h_occ.numpy(), d_occ.cpu().numpy())
                       and np.array_equal(h_bhits.numpy(), d_bhits.view(torch.int32).cpu().numpy()))
@@ -478,7 +480,7 @@ def main():
                        "rays_per_step_per_gpu": rays_per_step, "bvh_nodes": n_nodes, "bvh_depth": depth,
                        "l2": "BVH+triangles (~1 GB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",
                        "scene_gen_s": t_gen, "bvh_build_upload_s": t_build},
-            "kernel_ms": kernel_ms,
+            "kernel_ms": kernel_ms, "hits_crc32": hits_crc,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
                     "api": "pb2_intersect / pb2_intersect_p with pinned host buffers"},
             "gpu_launches": launches_per_step * args.steps + path_launches,

@@ -324,6 +324,7 @@ int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* 
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream) {
     int rc = check_ready(scene);
     if (rc) return rc;
+    if (n >> 32) return set_error(PB2_ERR_INVALID, "device batches are limited to 2^32 - 1 rays per call");
     launch_closest_hit(scene->view, d_rays, n, d_hits, d_b0, scene->next_counter(), (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;
@@ -332,6 +333,7 @@ int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void*
 int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream) {
     int rc = check_ready(scene);
     if (rc) return rc;
+    if (n >> 32) return set_error(PB2_ERR_INVALID, "device batches are limited to 2^32 - 1 rays per call");
     launch_any_hit(scene->view, d_rays, n, d_out, scene->next_counter(), (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;

@@ -11,38 +11,40 @@ namespace pb2 {
 // k_closest_hit / k_any_hit: bvh.rs:828-879 / :881-932 over a batch.  Rays are 2 x float4 (o,t_max | d,time), hits one
 // uint4 {prim_id, t, b1, b2}.  The walk itself is trace_persistent.cuh.
 // ---------------------------------------------------------------------------------------------------------
-#ifndef PB2_MIN_BLOCKS
-#define PB2_MIN_BLOCKS 8   /* 64 registers: 8 CTAs of 4 warps per SM; 48 registers spill and run slower (profiles/r01_tuning.md) */
-#endif
 
 struct BatchSink {
     const float4* __restrict__ rays;
     uint4* __restrict__ hits;
     float* __restrict__ b0_out;
     uint8_t* __restrict__ occ_out;
-    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
-        const float4 ro = __ldg(rays + 2 * i);
-        const float4 rd = __ldg(rays + 2 * i + 1);
+    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
+        const float4 ro = __ldg(rays + 2ull * i);
+        const float4 rd = __ldg(rays + 2ull * i + 1);
         *o = mk(ro.x, ro.y, ro.z);
         *d = mk(rd.x, rd.y, rd.z);
         *t_max = ro.w;
         return true;
     }
-    PB2_D void closest(uint64_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
+    PB2_D void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
         hits[i] = make_uint4(prim, __float_as_uint(t), __float_as_uint(b1), __float_as_uint(b2));
         if (b0_out) b0_out[i] = b0;
     }
-    PB2_D void occluded(uint64_t i, bool occ) const { occ_out[i] = occ ? 1 : 0; }
+    PB2_D void finish(uint32_t i, bool found, float t_max) const {
+        if (found) return;
+        hits[i] = make_uint4(0xFFFFFFFFu, __float_as_uint(t_max), 0u, 0u);
+        if (b0_out) b0_out[i] = 0.0f;
+    }
+    PB2_D void occluded(uint32_t i, bool occ) const { occ_out[i] = occ ? 1 : 0; }
 };
 
-__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_closest_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_closest_hit(SceneView s, const float4* __restrict__ rays, uint32_t n,
                                                       unsigned long long* __restrict__ counter, uint4* __restrict__ hits,
                                                       float* __restrict__ b0_out, TraceTuning tune) {
     const BatchSink sink{rays, hits, b0_out, nullptr};
     trace_persistent<false>(s, n, counter, sink, tune);
 }
 
-__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, const float4* __restrict__ rays, uint64_t n,
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, const float4* __restrict__ rays, uint32_t n,
                                                   unsigned long long* __restrict__ counter, uint8_t* __restrict__ out,
                                                   TraceTuning tune) {
     const BatchSink sink{rays, nullptr, nullptr, out};
@@ -81,14 +83,14 @@ void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void
                         cudaStream_t st) {
     if (n == 0) return;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
-    k_closest_hit<<<persistent_grid((const void*)k_closest_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, n, d_counter, (uint4*)d_hits,
+    k_closest_hit<<<persistent_grid((const void*)k_closest_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter, (uint4*)d_hits,
                                                                                  (float*)d_b0, trace_tuning());
 }
 
 void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, unsigned long long* d_counter, cudaStream_t st) {
     if (n == 0) return;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
-    k_any_hit<<<persistent_grid((const void*)k_any_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, n, d_counter, (uint8_t*)d_out, trace_tuning());
+    k_any_hit<<<persistent_grid((const void*)k_any_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter, (uint8_t*)d_out, trace_tuning());
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -321,10 +321,14 @@ PB2_HD rgb3 bsdf_sample_f(const Bsdf& b, vec3 wo_w, vec3* wi_w, float u0, float 
     return fv;
 }
 
-// Material::compute_scattering_functions for matte / plastic / glass (pbrt-v3; Appendix B).
+// Material::compute_scattering_functions for matte / plastic / glass (pbrt-v3; Appendix B).  MAT is the material type of
+// `m` known at compile time (the wavefront shades one material type per launch, so the lobe kinds fold to constants and
+// the code of the other materials drops out of that launch's kernel); MAT < 0 reads m.type at run time.
+template <int MAT = -1>
 PB2_HD Bsdf make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
     Bsdf b;
-    b.eta = m.type == 2 ? m.eta : 1.0f;
+    const int type = MAT < 0 ? m.type : MAT;
+    b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = n;
     b.ng = n;
     b.ss = unit(dpdu);                                         // reflection.rs:220-234 (D59: shading = geometric)
@@ -332,12 +336,12 @@ PB2_HD Bsdf make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
     b.n = 0;
     const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);
     const rgb3 kr = mkc(m.kr[0], m.kr[1], m.kr[2]), kt = mkc(m.kt[0], m.kt[1], m.kt[2]);
-    if (m.type == 0 || m.type == 1) {
+    if (type == 0 || type == 1) {
         if (!black(kd)) {
             Lobe& l = b.lobes[b.n++];
             l.kind = kLambert; l.type = kReflection | kDiffuse; l.r = kd; l.t = gray(0.0f); l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f;
         }
-        if (m.type == 1 && !black(ks)) {
+        if (type == 1 && !black(ks)) {
             Lobe& l = b.lobes[b.n++];
             l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = gray(0.0f); l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f;
         }

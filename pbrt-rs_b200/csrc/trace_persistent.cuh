@@ -9,9 +9,13 @@
 //    than `node_quorum` lanes still want a node step, the node step otherwise — so each path runs with most of its
 //    lanes enabled instead of every iteration paying for both.  (The tree is deep and leaves hold ~1.3 triangles: a
 //    per-lane "while-while" loop idles 3 of 4 lanes waiting for the slowest lane to reach its next leaf.)
-//  * The traversal stack (64 entries, bvh.rs:839) lives in local memory with its top entry cached in registers: a pop
-//    consumes the register copy and issues the reload of the next entry, which is not needed before the next pop,
-//    so the local-memory latency stays off the critical path.  Far children are prefetched into L2 when pushed.
+//  * Register diet: throughput follows resident warps (profiles/r01_tuning.md: loading a node's record early into
+//    registers lost 20-35 % because it cost a CTA per SM), so the per-ray state carried between iterations is 15
+//    registers — origin, inverse direction, shear, t_max, current reference, stack depth, ray index and one word of
+//    flags (direction signs, shear axis, slab fast-path, hit-found) — and everything else is rebuilt inside the
+//    step that needs it.  An accepted closest-hit candidate is written to the result at once (the last one written
+//    wins, as primitive.rs:70 keeps the last accepted hit), so no hit record is carried.
+//  * The traversal stack (64 entries, bvh.rs:839) is one uint2 {reference, entry distance} array in local memory.
 // Scheduling has no influence on results: every ray still sees the reference's node and triangle order.
 #pragma once
 #include "traverse.cuh"
@@ -28,14 +32,14 @@ struct TraceTuning {
     int prefetch;
 };
 
-PB2_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-#ifndef PB2_TOPCACHE
-#define PB2_TOPCACHE 1
+#ifndef PB2_MIN_BLOCKS
+#define PB2_MIN_BLOCKS 10   /* 48 registers: 10 CTAs of 4 warps per SM */
 #endif
 #ifndef PB2_FASTSLAB
 #define PB2_FASTSLAB 1
 #endif
+
+PB2_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Slab test for rays whose inverse direction is finite and non-zero on all three axes (every product below is then
 // an ordinary number or +-inf, never 0 * inf = NaN).  Without NaNs the reference's sequence of rejections and
@@ -58,53 +62,73 @@ PB2_D bool slab_entry_fast(const RayCtx& r, float lx, float ly, float lz, float 
 }
 PB2_D bool finite_nonzero(float v) { return v != 0.0f && fabsf(v) < __int_as_float(0x7f800000); }
 
-// Sink = where rays come from and where results go (batch arrays, wavefront queues).
-//   bool load(uint64_t i, vec3* o, vec3* d, float* t_max)   — false: slot i carries no ray
-//   void miss_or_hit(uint64_t i, uint32_t prim, float t, float b0, float b1, float b2)   (closest hit)
-//   void occluded(uint64_t i, bool occ)                                                   (any hit)
+// Flag word of a ray: bits 0-2 direction signs (bvh.rs:832-836), bits 3-4 shear axis kz (triangle.rs:84-92),
+// bit 5 slab fast path allowed, bit 6 a closest-hit candidate has been accepted.
+constexpr uint32_t kFlagPlain = 32u, kFlagFound = 64u;
+
+// The part of RayCtx a step needs, rebuilt from the carried registers (make_ray_ctx computed them once per ray).
+PB2_D RayCtx ctx_of(vec3 o, vec3 inv, vec3 sh, uint32_t flags) {
+    RayCtx r;
+    r.o = o;
+    r.d = mk(0.f, 0.f, 0.f);                 // not used by slab_entry / tri_test
+    r.inv = inv;
+    r.nx = (flags & 1u) != 0u;
+    r.ny = (flags & 2u) != 0u;
+    r.nz = (flags & 4u) != 0u;
+    r.kz = (int)((flags >> 3) & 3u);
+    r.kx = r.kz == 2 ? 0 : r.kz + 1;
+    r.ky = r.kx == 2 ? 0 : r.kx + 1;
+    r.sx = sh.x; r.sy = sh.y; r.sz = sh.z;
+    return r;
+}
+
+// Sink = where rays come from and where results go (batch arrays, wavefront queues).  i < n < 2^32.
+//   bool load(uint32_t i, vec3* o, vec3* d, float* t_max)                                — false: slot i carries no ray
+//   void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2)       — closest hit: a candidate was
+//                                                     accepted (called in test order; the last call is the closest hit)
+//   void finish(uint32_t i, bool found, float t_max)                                     — closest hit: walk over
+//   void occluded(uint32_t i, bool occ)                                                  — any hit: walk over
 template <bool ANY, class Sink>
-__device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n, unsigned long long* __restrict__ counter,
+__device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n, unsigned long long* __restrict__ counter,
                                                  const Sink& sink, const TraceTuning tune) {
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t stack_ref[kStackDepth];
-    float stack_t[kStackDepth];
-    int sp = 0;                              // entries on the stack, the newest one held in (top_ref, top_t)
-    uint32_t top_ref = 0;
-    float top_t = 0.0f;
+    uint2 stack[kStackDepth];                // {reference, entry distance bits}
+    int sp = 0;
     uint32_t cur = kDone;
-    uint64_t ray_idx = 0;
-    RayCtx r = make_ray_ctx(mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 1.f));
+    uint32_t ray_idx = 0;
+    uint32_t flags = 0;
+    vec3 o = mk(0.f, 0.f, 0.f), inv = mk(1.f, 1.f, 1.f), sh = mk(0.f, 0.f, 1.f);
     float t_max = 0.0f;
-    uint32_t h_prim = 0xFFFFFFFFu;
-    float h_b0 = 0.f, h_b1 = 0.f, h_b2 = 0.f;
     bool exhausted = false;                  // warp-uniform: the ray counter ran past n
-    bool plain = true;                       // this lane's ray qualifies for slab_entry_fast
 
     for (;;) {
         // ---- refill idle lanes ----
         if (!exhausted) {
             const unsigned idle = __ballot_sync(kFullMask, cur == kDone);
             if (idle) {
+                const unsigned lane = threadIdx.x & 31u;
                 const int leader = __ffs(idle) - 1;
                 unsigned long long base = 0;
                 if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(idle));
                 base = __shfl_sync(kFullMask, base, leader);
                 exhausted = base + (unsigned)__popc(idle) >= n;
                 if (cur == kDone) {
-                    ray_idx = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                    if (ray_idx < n) {
-                        vec3 o, d;
+                    const unsigned long long mine = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                    if (mine < n) {
+                        ray_idx = (uint32_t)mine;
+                        vec3 d;
                         if (sink.load(ray_idx, &o, &d, &t_max)) {
-                            r = make_ray_ctx(o, d);
-                            plain = finite_nonzero(r.inv.x) && finite_nonzero(r.inv.y) && finite_nonzero(r.inv.z);
-                            h_prim = 0xFFFFFFFFu; h_b0 = 0.f; h_b1 = 0.f; h_b2 = 0.f;
+                            const RayCtx r = make_ray_ctx(o, d);
+                            inv = r.inv;
+                            sh = mk(r.sx, r.sy, r.sz);
+                            flags = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u) | ((uint32_t)r.kz << 3);
+                            if (finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z)) flags |= kFlagPlain;
                             sp = 0;
                             float te;
                             const bool enter = s.n_tris != 0 &&
                                 slab_entry(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2], &te) && te < t_max;
                             if (enter) cur = s.root_ref;
                             else if (ANY) sink.occluded(ray_idx, false);
-                            else sink.closest(ray_idx, 0xFFFFFFFFu, t_max, 0.f, 0.f, 0.f);
+                            else sink.finish(ray_idx, false, t_max);
                         }
                     }
                 }
@@ -119,11 +143,14 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n,
             if (!exhausted && __popc(work_mask) < tune.refill_below) break;
             const int n_node = __popc(node_mask), n_leaf = __popc(work_mask & ~node_mask);
             bool need_pop = false;
-#if PB2_FASTSLAB
-            const bool all_plain = __ballot_sync(kFullMask, at_node && !plain) == 0u;
-#endif
+            // keep the flag word opaque so the per-step decoding below is not hoisted into loop-carried registers
+            asm volatile("" : "+r"(flags));
             if (n_leaf == 0 || (n_node >= tune.node_quorum && n_leaf < tune.leaf_quorum)) {
+#if PB2_FASTSLAB
+                const bool all_plain = __ballot_sync(kFullMask, at_node && !(flags & kFlagPlain)) == 0u;
+#endif
                 if (at_node) {
+                    const RayCtx r = ctx_of(o, inv, sh, flags);
                     const float4* np = s.pairs + 4ull * cur;
                     const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
                     const uint4 m = __ldg(reinterpret_cast<const uint4*>(np + 3));
@@ -140,19 +167,12 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n,
                         okr = slab_entry(r, b.z, b.w, c.x, c.y, c.z, c.w, &tr) && (tr < t_max);
                     }
                     // bvh.rs:856-866: near child first, by the sign of the direction on the split axis
-                    const bool neg = (m.z == 0u) ? r.nx : ((m.z == 1u) ? r.ny : r.nz);
+                    const bool neg = ((flags >> m.z) & 1u) != 0u;
                     const uint32_t near_ref = neg ? m.y : m.x, far_ref = neg ? m.x : m.y;
                     const bool ok_near = neg ? okr : okl, ok_far = neg ? okl : okr;
                     if (ok_near) {
                         if (ok_far) {
-#if PB2_TOPCACHE
-                            if (sp > 0) { stack_ref[sp - 1] = top_ref; stack_t[sp - 1] = top_t; }
-                            top_ref = far_ref;
-                            top_t = neg ? tl : tr;
-#else
-                            stack_ref[sp] = far_ref;
-                            stack_t[sp] = neg ? tl : tr;
-#endif
+                            stack[sp] = make_uint2(far_ref, __float_as_uint(neg ? tl : tr));
                             ++sp;
                             if (tune.prefetch)
                                 prefetch_l2((far_ref & kLeafFlag) ? (const void*)(s.tris + 3ull * (far_ref & ~kLeafFlag))
@@ -167,6 +187,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n,
                 }
             } else if (cur != kDone && !at_node) {
                 // leaf triangles, in leaf order
+                const RayCtx r = ctx_of(o, inv, sh, flags);
                 uint32_t slot = cur & ~kLeafFlag;
                 bool occluded = false;
                 for (;;) {
@@ -180,8 +201,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n,
                         vec3 du, dv;
                         if (tri_frame(p0, p1, p2, &du, &dv)) {
                             t_max = t;                                  // primitive.rs:70
-                            h_prim = __float_as_uint(a.w);
-                            h_b0 = b0; h_b1 = b1; h_b2 = b2;
+                            flags |= kFlagFound;
+                            sink.accept(ray_idx, __float_as_uint(a.w), t, b0, b1, b2);
                         }
                     }
                     if (__float_as_uint(b.w) != 0u) break;              // last triangle of the leaf
@@ -197,21 +218,13 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint64_t n,
             if (need_pop) {
                 cur = kDone;
                 while (sp > 0) {                                        // geometry.rs:749 re-applied at pop time
-#if PB2_TOPCACHE
-                    const uint32_t e_ref = top_ref;
-                    const float e_t = top_t;
                     --sp;
-                    if (sp > 0) { top_ref = stack_ref[sp - 1]; top_t = stack_t[sp - 1]; }
-#else
-                    --sp;
-                    const uint32_t e_ref = stack_ref[sp];
-                    const float e_t = stack_t[sp];
-#endif
-                    if (e_t < t_max) { cur = e_ref; break; }
+                    const uint2 e = stack[sp];
+                    if (__uint_as_float(e.y) < t_max) { cur = e.x; break; }
                 }
                 if (cur == kDone) {
                     if (ANY) sink.occluded(ray_idx, false);
-                    else sink.closest(ray_idx, h_prim, t_max, h_b0, h_b1, h_b2);
+                    else sink.finish(ray_idx, (flags & kFlagFound) != 0u, t_max);
                 }
             }
         }

@@ -136,7 +136,7 @@ struct ExtendSink {
     PathBuffers b;
     ShadeView sh;
     const uint32_t* queue;
-    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
         const uint32_t slot = queue[i];
         const float4 ro = b.ray_o[slot], rd = b.ray_d[slot];
         *o = mk(ro.x, ro.y, ro.z);
@@ -144,24 +144,28 @@ struct ExtendSink {
         *t_max = ro.w;
         return true;
     }
-    PB2_D void closest(uint64_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
+    PB2_D void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
         (void)t;
-        if (prim == 0xFFFFFFFFu) return;                 // escaped: no infinite lights in scope, the path is finished
-        const uint32_t slot = queue[i];
-        b.hit[slot] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
-        const int type = sh.mats[sh.tri_material[prim]].type;
-        queue_push(&b.counters[C_MAT0 + type], b.q_mat[type], slot);
+        b.hit[queue[i]] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
     }
-    PB2_D void occluded(uint64_t, bool) const {}
+    PB2_D void finish(uint32_t i, bool found, float) const {
+        if (!found) return;                              // escaped: no infinite lights in scope, the path is finished
+        const uint32_t slot = queue[i];
+        const uint32_t prim = b.hit[slot].x;             // written by this thread's last accept()
+        const int type = sh.mats[sh.tri_material[prim]].type;
+        // (selects, not b.q_mat[type]: a run-time index would move the whole parameter struct into local memory)
+        queue_push(&b.counters[C_MAT0 + type], type == 0 ? b.q_mat[0] : (type == 1 ? b.q_mat[1] : b.q_mat[2]), slot);
+    }
+    PB2_D void occluded(uint32_t, bool) const {}
 };
-__global__ void __launch_bounds__(128, 8) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
     const ExtendSink sink{b, sh, b.q_active[cur]};
-    trace_persistent<false>(s, (uint64_t)b.counters[C_ACTIVE_A + cur], &b.counters[C_WORK_EXTEND], sink, tune);
+    trace_persistent<false>(s, (uint32_t)b.counters[C_ACTIVE_A + cur], &b.counters[C_WORK_EXTEND], sink, tune);
 }
 
 struct ShadowSink {
     PathBuffers b;
-    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
         const uint32_t slot = b.q_shadow[i];
         const float4 ro = b.sh_o[slot], rd = b.sh_d[slot];
         *o = mk(ro.x, ro.y, ro.z);
@@ -169,17 +173,18 @@ struct ShadowSink {
         *t_max = ro.w;
         return true;
     }
-    PB2_D void closest(uint64_t, uint32_t, float, float, float, float) const {}
-    PB2_D void occluded(uint64_t i, bool occ) const { b.occluded[b.q_shadow[i]] = occ ? 1 : 0; }
+    PB2_D void accept(uint32_t, uint32_t, float, float, float, float) const {}
+    PB2_D void finish(uint32_t, bool, float) const {}
+    PB2_D void occluded(uint32_t i, bool occ) const { b.occluded[b.q_shadow[i]] = occ ? 1 : 0; }
 };
-__global__ void __launch_bounds__(128, 8) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
     const ShadowSink sink{b};
-    trace_persistent<true>(s, (uint64_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
+    trace_persistent<true>(s, (uint32_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
 }
 
 struct MisSink {
     PathBuffers b;
-    PB2_D bool load(uint64_t i, vec3* o, vec3* d, float* t_max) const {
+    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
         const uint32_t slot = b.q_mis[i];
         const float4 ro = b.mis_o[slot], rd = b.mis_d[slot];
         *o = mk(ro.x, ro.y, ro.z);
@@ -187,12 +192,13 @@ struct MisSink {
         *t_max = kInf;
         return true;
     }
-    PB2_D void closest(uint64_t i, uint32_t prim, float, float, float, float) const { b.mis_prim[b.q_mis[i]] = prim; }
-    PB2_D void occluded(uint64_t, bool) const {}
+    PB2_D void accept(uint32_t i, uint32_t prim, float, float, float, float) const { b.mis_prim[b.q_mis[i]] = prim; }
+    PB2_D void finish(uint32_t i, bool found, float) const { if (!found) b.mis_prim[b.q_mis[i]] = 0xFFFFFFFFu; }
+    PB2_D void occluded(uint32_t, bool) const {}
 };
-__global__ void __launch_bounds__(128, 8) k_mis(SceneView s, PathBuffers b, TraceTuning tune) {
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_mis(SceneView s, PathBuffers b, TraceTuning tune) {
     const MisSink sink{b};
-    trace_persistent<false>(s, (uint64_t)b.counters[C_MIS], &b.counters[C_WORK_MIS], sink, tune);
+    trace_persistent<false>(s, (uint32_t)b.counters[C_MIS], &b.counters[C_WORK_MIS], sink, tune);
 }
 
 // ---- shade -----------------------------------------------------------------------------------------------------------------
@@ -324,9 +330,13 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
 }
 
 // One path vertex of PathIntegrator::li (path.rs:79-209) for every hit of material type `mat`.
-__global__ void __launch_bounds__(kThreads) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int mat, int cur) {
-    const uint64_t n = b.counters[C_MAT0 + mat];
-    const uint32_t* queue = b.q_mat[mat];
+#ifndef PB2_SHADE_BLOCKS
+#define PB2_SHADE_BLOCKS 2
+#endif
+template <int MAT>
+__global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
+    const uint64_t n = b.counters[C_MAT0 + MAT];
+    const uint32_t* queue = b.q_mat[MAT];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t slot = queue[i];
         const uint4 h = b.hit[slot];
@@ -350,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) k_shade(SceneView s, ShadeView sh, P
         }
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
         if (alive) {
-            const Bsdf bsdf = make_bsdf(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
+            const Bsdf bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
             Pcg32 rng;
             rng.state = b.rng[slot];
             rng.inc = (slot_info(map, film, slot).seq << 1) | 1ull;
@@ -573,14 +583,16 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
                  const PathParams& pp, uint64_t n, cudaStream_t st) {
     PathBuffers& b = wf->b;
     const TraceTuning tune = trace_tuning();
-    const unsigned trace_grid = (unsigned)wf->sm_count * 8u;
+    const unsigned trace_grid = (unsigned)wf->sm_count * (unsigned)PB2_MIN_BLOCKS;
     k_raygen<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, cam, b);
     int launches = 1;
     for (int depth = 0; depth <= pp.max_depth; ++depth) {
         const int cur = depth & 1;
         k_iter_begin<<<1, 32, 0, st>>>(b, cur);
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
-        for (int mat = 0; mat < 3; ++mat) k_shade<<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, mat, cur);
+        k_shade<0><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+        k_shade<1><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+        k_shade<2><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
         if (depth < pp.max_depth && sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
             k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);
