@@ -114,6 +114,10 @@ int pb2_device_free(void* p);
 int pb2_memcpy_h2d(void* dst_device, const void* src_host, uint64_t bytes);
 int pb2_memcpy_d2h(void* dst_host, const void* src_device, uint64_t bytes);
 int pb2_device_synchronize(void);
+/* Scheduling knobs of the traversal kernels (lanes refilled below / node-step quorum / leaf-step quorum / L2 prefetch of
+ * deferred children); a negative value keeps the current setting.  Results never depend on them (tuning sweeps only;
+ * no reference counterpart). */
+int pb2_set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int prefetch);
 
 /* ---- scene + BVHAccel (src/accelerators/bvh.rs:216-271 BVHAccel::new) ---------------------------------- */
 /* Copies the mesh.  tri_material (index into mats) / tri_light (index into lights or -1) may be NULL for pure

@@ -122,6 +122,7 @@ def lib():
         "pb2_init": [i32], "pb2_shutdown": [], "pb2_device_count": [vp],
         "pb2_host_alloc": [u64, vp], "pb2_host_free": [vp], "pb2_device_alloc": [u64, vp], "pb2_device_free": [vp],
         "pb2_memcpy_h2d": [vp, vp, u64], "pb2_memcpy_d2h": [vp, vp, u64], "pb2_device_synchronize": [],
+        "pb2_set_trace_tuning": [i32, i32, i32, i32],
         "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
         "pb2_bvh_export": [vp, vp, vp],

@@ -37,6 +37,7 @@ using namespace pb2;
 
 void pb2_scene::free_device() {
     if (d_pairs) cudaFree(d_pairs);
+    if (d_quads) cudaFree(d_quads);
     if (d_tris) cudaFree(d_tris);
     if (d_slot_of_prim) cudaFree(d_slot_of_prim);
     if (d_tri_material) cudaFree(d_tri_material);
@@ -46,6 +47,7 @@ void pb2_scene::free_device() {
     if (d_light_cdf) cudaFree(d_light_cdf);
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
+    d_quads = nullptr;
     d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
     for (int i = 0; i < 2; ++i) {
         if (stage[i].d_in) cudaFree(stage[i].d_in);
@@ -60,6 +62,12 @@ void pb2_scene::free_device() {
 extern "C" {
 
 const char* pb2_last_error(void) { return g_err; }
+
+int pb2_set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int prefetch) {
+    if (refill_below > 33 || node_quorum > 33 || leaf_quorum > 33) return set_error(PB2_ERR_INVALID, "quorums are lane counts (<= 33)");
+    pb2::set_trace_tuning(refill_below, node_quorum, leaf_quorum, prefetch);
+    return PB2_OK;
+}
 
 int pb2_device_count(int* out) {
     if (!out) return set_error(PB2_ERR_INVALID, "null out");
@@ -198,6 +206,10 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
         PB2_CUDA(cudaMalloc(&scene->d_tris, b.tris.size() * sizeof(PackedTri)));
         PB2_CUDA(cudaMalloc(&scene->d_slot_of_prim, n_tris * 4));
         if (!b.pairs.empty()) PB2_CUDA(cudaMemcpy(scene->d_pairs, b.pairs.data(), b.pairs.size() * sizeof(PairNode), cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMalloc(&scene->d_quads, std::max<size_t>(128, b.quads.size() * sizeof(QuadNode))));
+        if (!b.quads.empty()) PB2_CUDA(cudaMemcpy(scene->d_quads, b.quads.data(), b.quads.size() * sizeof(QuadNode), cudaMemcpyHostToDevice));
+        v.quads = (const float4*)scene->d_quads;
+        v.quad_root_ref = b.quad_root_ref;
         PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
         std::vector<uint32_t> slot(n_tris);
         for (uint64_t i = 0; i < n_tris; ++i) slot[b.ordered_prims[i]] = (uint32_t)i;
@@ -213,6 +225,7 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     if (rc != PB2_OK) return rc;
     // the device copies are authoritative from here on; drop the host-side device-layout mirrors
     std::vector<PairNode>().swap(b.pairs);
+    std::vector<QuadNode>().swap(b.quads);
     std::vector<PackedTri>().swap(b.tris);
     scene->built = true;
     return PB2_OK;

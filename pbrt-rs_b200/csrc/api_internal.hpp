@@ -51,6 +51,7 @@ struct pb2_scene {
     std::mutex mu;
     // device copies
     void* d_pairs = nullptr;
+    void* d_quads = nullptr;
     void* d_tris = nullptr;
     void* d_slot_of_prim = nullptr;
     void* d_tri_material = nullptr;

@@ -5,6 +5,8 @@
 // equals what the reference algorithm produces for the same primitive list.
 #include "bvh_build.hpp"
 
+#include <limits>
+
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -376,6 +378,61 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
         p.pad = 0;
     }
     out->root_ref = ref_of(0);
+
+    // ---- fold two levels per record (QuadNode), numbered depth-first like the pairs ----
+    out->quads.clear();
+    if (n_nodes && out->nodes[0].n_prims == 0) {
+        out->quads.reserve(n_pairs / 2 + 16);
+        struct Frame { uint32_t node, quad; int slot; };            // slot: next child slot of `quad` to resolve
+        auto new_quad = [&](uint32_t P) -> uint32_t {
+            const uint32_t q = (uint32_t)out->quads.size();
+            out->quads.emplace_back();
+            QuadNode& Q = out->quads.back();
+            const float inf = std::numeric_limits<float>::infinity();
+            for (int k = 0; k < 4; ++k) {
+                Q.lox[k] = Q.loy[k] = Q.loz[k] = inf;
+                Q.hix[k] = Q.hiy[k] = Q.hiz[k] = -inf;
+                Q.ref[k] = kQuadEmpty;
+            }
+            Q.pad[0] = Q.pad[1] = Q.pad[2] = 0;
+            const LinearNode& ln = out->nodes[P];
+            uint32_t axes = ln.axis;
+            const uint32_t kids[2] = {P + 1, ln.offset};
+            for (int g = 0; g < 2; ++g) {
+                const LinearNode& X = out->nodes[kids[g]];
+                uint32_t members[2];
+                int n_members;
+                if (X.n_prims > 0) { members[0] = kids[g]; n_members = 1; }
+                else { members[0] = kids[g] + 1; members[1] = X.offset; n_members = 2; axes |= (uint32_t)X.axis << (2 + 2 * g); }
+                for (int j = 0; j < n_members; ++j) {
+                    const LinearNode& Y = out->nodes[members[j]];
+                    const int k = 2 * g + j;
+                    Q.lox[k] = Y.bmin[0]; Q.loy[k] = Y.bmin[1]; Q.loz[k] = Y.bmin[2];
+                    Q.hix[k] = Y.bmax[0]; Q.hiy[k] = Y.bmax[1]; Q.hiz[k] = Y.bmax[2];
+                    // interior members are resolved by the caller loop (needs their quad index): park the node index
+                    Q.ref[k] = Y.n_prims > 0 ? (kLeafBit | Y.offset) : members[j];
+                }
+            }
+            Q.axes = axes;
+            return q;
+        };
+        std::vector<Frame> work;
+        work.push_back({0u, new_quad(0u), 0});
+        while (!work.empty()) {
+            Frame& f = work.back();
+            if (f.slot == 4) { work.pop_back(); continue; }
+            const int k = f.slot++;
+            const uint32_t r = out->quads[f.quad].ref[k];
+            if (r == kQuadEmpty || (r & kLeafBit)) continue;
+            const uint32_t fq = f.quad;                              // `f` dangles after push_back
+            const uint32_t child_quad = new_quad(r);
+            out->quads[fq].ref[k] = child_quad;
+            work.push_back({r, child_quad, 0});
+        }
+        out->quad_root_ref = 0;
+    } else {
+        out->quad_root_ref = out->root_ref;                          // empty tree or a single leaf
+    }
     for (int k = 0; k < 3; ++k) { out->root_bounds[k] = out->nodes[0].bmin[k]; out->root_bounds[3 + k] = out->nodes[0].bmax[k]; }
 
     out->tris.resize(n_tris);

@@ -6,6 +6,9 @@
 // subtrees on worker threads, and then repacks into the device layout:
 //   * PairNode (64 B): one record per INTERIOR node holding both children's boxes, so one 64-byte fetch feeds
 //     two slab tests and leaves need no node record at all;
+//   * QuadNode (128 B, one cache line): two levels of the binary tree folded into one record — the boxes of the (up to
+//     four) grandchildren of an interior node as six float4 (SoA), their references and the three split axes that
+//     fix the reference's visiting order; a ray takes half as many dependent fetches to reach a leaf;
 //   * PackedTri (48 B): triangles gathered in BVH leaf order as three float4, w-lanes carry the caller's
 //     primitive id and an end-of-leaf flag.
 #pragma once
@@ -38,6 +41,19 @@ struct alignas(64) PairNode {
 };
 static_assert(sizeof(PairNode) == 64, "PairNode must be 64 bytes");
 
+// Device node of the traversal kernels: interior node P with children A (= P+1) and B (= second child) folded with
+// A's and B's own children.  Slots 0,1 belong to A, slots 2,3 to B: an interior child contributes its two children
+// (first child in the lower slot), a leaf child occupies the lower slot of its group and leaves the other one empty
+// (inverted box, ref = kQuadEmpty).  axes = axis(P) | axis(A) << 2 | axis(B) << 4 (bvh.rs:856-866 decides near/far by
+// the sign of the ray direction on these axes).  ref = quad index, or kLeafBit | first triangle slot.
+struct alignas(128) QuadNode {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    uint32_t ref[4];
+    uint32_t axes, pad[3];
+};
+static_assert(sizeof(QuadNode) == 128, "QuadNode must be 128 bytes");
+constexpr uint32_t kQuadEmpty = 0xFFFFFFFFu;
+
 struct alignas(16) PackedTri {
     float v0[3];
     uint32_t prim_id;     // index into the caller's triangle list
@@ -54,8 +70,10 @@ struct HostBVH {
     int max_depth = 0;                      // nodes on the longest root-to-leaf path
     // device layout
     std::vector<PairNode> pairs;
+    std::vector<QuadNode> quads;
     std::vector<PackedTri> tris;
-    uint32_t root_ref = 0;
+    uint32_t root_ref = 0;                  // into pairs
+    uint32_t quad_root_ref = 0;             // into quads
     float root_bounds[6] = {0, 0, 0, 0, 0, 0};
 };
 

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, co
 
 // Scheduling knobs (results do not depend on them).  Defaults tuned on B200 with the C3 workload; the environment
 // variables exist for the tuning sweeps recorded in profiles/.
-TraceTuning trace_tuning() {
+static TraceTuning& tuning_ref() {
     static TraceTuning t = [] {
         TraceTuning v{16, 12, 33, 0};
         if (const char* e = getenv("PB2_REFILL_BELOW")) v.refill_below = atoi(e);
@@ -63,6 +63,14 @@ TraceTuning trace_tuning() {
         return v;
     }();
     return t;
+}
+TraceTuning trace_tuning() { return tuning_ref(); }
+void set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int prefetch) {
+    TraceTuning& t = tuning_ref();
+    if (refill_below >= 0) t.refill_below = refill_below;
+    if (node_quorum >= 0) t.node_quorum = node_quorum;
+    if (leaf_quorum >= 0) t.leaf_quorum = leaf_quorum;
+    if (prefetch >= 0) t.prefetch = prefetch;
 }
 
 // Grid = every SM filled to the occupancy the kernel reaches (queried once), capped by the amount of work.

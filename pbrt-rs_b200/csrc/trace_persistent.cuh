@@ -33,11 +33,17 @@ struct TraceTuning {
 };
 
 #ifndef PB2_MIN_BLOCKS
-#define PB2_MIN_BLOCKS 10   /* 48 registers: 10 CTAs of 4 warps per SM */
+#define PB2_MIN_BLOCKS 8   /* 64 registers: 8 CTAs of 4 warps per SM (the quad step spills below that; profiles/r01_tuning.md) */
 #endif
 #ifndef PB2_FASTSLAB
 #define PB2_FASTSLAB 1
 #endif
+// PB2_QUAD 1: node steps read QuadNode records (two tree levels per fetch, half the dependent fetches and votes per
+// ray); 0: PairNode records (one level per fetch).  Both visit leaves in the reference's order (see quad_step).
+#ifndef PB2_QUAD
+#define PB2_QUAD 1
+#endif
+constexpr int kQuadStackDepth = 96;         // <= 3 pushes per two levels of a tree at most 64 levels deep (bvh.rs:839)
 
 PB2_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -61,6 +67,19 @@ PB2_D bool slab_entry_fast(const RayCtx& r, float lx, float ly, float lz, float 
     return tn <= tf && tf > 0.0f;
 }
 PB2_D bool finite_nonzero(float v) { return v != 0.0f && fabsf(v) < __int_as_float(0x7f800000); }
+
+// Entry distance of one child box for a ray on the slab fast path, +inf when the box is missed or starts beyond t_max
+// (geometry.rs:709-751 incl. its final clause).
+PB2_D float quad_child_entry(float nx, float ny, float nz, float fx, float fy, float fz, vec3 o, vec3 inv, float t_max) {
+    const float widen = 1.0f + 2.0f * gammaf_(3.0f);
+    const float tn = fmaxf(fmaxf((nx - o.x) * inv.x, (ny - o.y) * inv.y), (nz - o.z) * inv.z);
+    const float tf = fminf(fminf(((fx - o.x) * inv.x) * widen, ((fy - o.y) * inv.y) * widen), ((fz - o.z) * inv.z) * widen);
+    return (tn <= tf && tf > 0.0f && tn < t_max) ? tn : __int_as_float(0x7f800000);
+}
+PB2_D void swap_if(bool c, uint32_t& ra, float& ta, uint32_t& rb, float& tb) {
+    const uint32_t r = c ? rb : ra; rb = c ? ra : rb; ra = r;
+    const float t = c ? tb : ta; tb = c ? ta : tb; ta = t;
+}
 
 // Flag word of a ray: bits 0-2 direction signs (bvh.rs:832-836), bits 3-4 shear axis kz (triangle.rs:84-92),
 // bit 5 slab fast path allowed, bit 6 a closest-hit candidate has been accepted.
@@ -91,7 +110,11 @@ PB2_D RayCtx ctx_of(vec3 o, vec3 inv, vec3 sh, uint32_t flags) {
 template <bool ANY, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n, unsigned long long* __restrict__ counter,
                                                  const Sink& sink, const TraceTuning tune) {
+#if PB2_QUAD
+    uint2 stack[kQuadStackDepth];            // {reference, entry distance bits}
+#else
     uint2 stack[kStackDepth];                // {reference, entry distance bits}
+#endif
     int sp = 0;
     uint32_t cur = kDone;
     uint32_t ray_idx = 0;
@@ -121,14 +144,37 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                             inv = r.inv;
                             sh = mk(r.sx, r.sy, r.sz);
                             flags = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u) | ((uint32_t)r.kz << 3);
-                            if (finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z)) flags |= kFlagPlain;
+                            const float inf = __int_as_float(0x7f800000);
+                            if (finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z) && fabsf(o.x) < inf &&
+                                fabsf(o.y) < inf && fabsf(o.z) < inf)
+                                flags |= kFlagPlain;
                             sp = 0;
-                            float te;
-                            const bool enter = s.n_tris != 0 &&
-                                slab_entry(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2], &te) && te < t_max;
-                            if (enter) cur = s.root_ref;
-                            else if (ANY) sink.occluded(ray_idx, false);
-                            else sink.finish(ray_idx, false, t_max);
+#if PB2_QUAD
+                            if (!(flags & kFlagPlain)) {
+                                // A zero direction component makes 0 * inf = NaN possible in the slab test, and a NaN can
+                                // reject a box whose child it accepts; folding two levels relies on "child hit => parent
+                                // hit", so these (rare) rays take the literal one-level walk right here.
+                                HitRec h;
+                                const bool found = traverse<ANY>(s, o, d, t_max, &h);
+                                if (ANY) sink.occluded(ray_idx, found);
+                                else {
+                                    if (found) sink.accept(ray_idx, h.prim, h.t, h.b0, h.b1, h.b2);
+                                    sink.finish(ray_idx, found, found ? h.t : t_max);
+                                }
+                            } else
+#endif
+                            {
+                                float te;
+                                const bool enter = s.n_tris != 0 &&
+                                    slab_entry(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2], &te) && te < t_max;
+#if PB2_QUAD
+                                if (enter) cur = s.quad_root_ref;
+#else
+                                if (enter) cur = s.root_ref;
+#endif
+                                else if (ANY) sink.occluded(ray_idx, false);
+                                else sink.finish(ray_idx, false, t_max);
+                            }
                         }
                     }
                 }
@@ -146,6 +192,46 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
             // keep the flag word opaque so the per-step decoding below is not hoisted into loop-carried registers
             asm volatile("" : "+r"(flags));
             if (n_leaf == 0 || (n_node >= tune.node_quorum && n_leaf < tune.leaf_quorum)) {
+#if PB2_QUAD
+                if (at_node) {
+                    // One QuadNode = interior node P, its children A, B and their children.  bvh.rs:856-866 visits A's
+                    // subtree before B's unless the ray is negative on axis(P), and inside A (B) the first child before
+                    // the second unless negative on axis(A) (axis(B)); a box is tested when its node is visited.  Here
+                    // the four grandchild boxes are tested at once, ordered the same way, the nearest accepted one is
+                    // visited and the others wait on the stack with their entry distance, which is re-checked against
+                    // the then-current t_max when popped.  A's and B's own boxes need no test: on the fast path a box
+                    // that accepts the ray implies its parent does (rounded subtract / multiply are monotone), and the
+                    // parent's t_max at its visit is never smaller than the child's.
+                    const float4* qp = s.quads + 8ull * cur;
+                    const float4 lox = ldg4(qp), loy = ldg4(qp + 1), loz = ldg4(qp + 2);
+                    const float4 hix = ldg4(qp + 3), hiy = ldg4(qp + 4), hiz = ldg4(qp + 5);
+                    const uint4 ref = __ldg(reinterpret_cast<const uint4*>(qp + 6));
+                    const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(qp + 7));
+                    const bool nx = (flags & 1u) != 0u, ny = (flags & 2u) != 0u, nz = (flags & 4u) != 0u;
+                    float t0 = quad_child_entry(nx ? hix.x : lox.x, ny ? hiy.x : loy.x, nz ? hiz.x : loz.x,
+                                                nx ? lox.x : hix.x, ny ? loy.x : hiy.x, nz ? loz.x : hiz.x, o, inv, t_max);
+                    float t1 = quad_child_entry(nx ? hix.y : lox.y, ny ? hiy.y : loy.y, nz ? hiz.y : loz.y,
+                                                nx ? lox.y : hix.y, ny ? loy.y : hiy.y, nz ? loz.y : hiz.y, o, inv, t_max);
+                    float t2 = quad_child_entry(nx ? hix.z : lox.z, ny ? hiy.z : loy.z, nz ? hiz.z : loz.z,
+                                                nx ? lox.z : hix.z, ny ? loy.z : hiy.z, nz ? loz.z : hiz.z, o, inv, t_max);
+                    float t3 = quad_child_entry(nx ? hix.w : lox.w, ny ? hiy.w : loy.w, nz ? hiz.w : loz.w,
+                                                nx ? lox.w : hix.w, ny ? loy.w : hiy.w, nz ? loz.w : hiz.w, o, inv, t_max);
+                    uint32_t r0 = ref.x, r1 = ref.y, r2 = ref.z, r3 = ref.w;
+                    swap_if(((flags >> ((axes >> 2) & 3u)) & 1u) != 0u, r0, t0, r1, t1);      // inside A
+                    swap_if(((flags >> ((axes >> 4) & 3u)) & 1u) != 0u, r2, t2, r3, t3);      // inside B
+                    const bool swap_groups = ((flags >> (axes & 3u)) & 1u) != 0u;            // A before B, or B before A
+                    swap_if(swap_groups, r0, t0, r2, t2);
+                    swap_if(swap_groups, r1, t1, r3, t3);
+                    const float inf = __int_as_float(0x7f800000);
+                    const bool h0 = t0 < inf, h1 = t1 < inf, h2 = t2 < inf, h3 = t3 < inf;
+                    // later candidates first, so the next one in visiting order is popped first
+                    if (h3 && (h0 || h1 || h2)) { stack[sp] = make_uint2(r3, __float_as_uint(t3)); ++sp; }
+                    if (h2 && (h0 || h1)) { stack[sp] = make_uint2(r2, __float_as_uint(t2)); ++sp; }
+                    if (h1 && h0) { stack[sp] = make_uint2(r1, __float_as_uint(t1)); ++sp; }
+                    if (h0 || h1 || h2 || h3) cur = h0 ? r0 : (h1 ? r1 : (h2 ? r2 : r3));
+                    else need_pop = true;
+                }
+#else
 #if PB2_FASTSLAB
                 const bool all_plain = __ballot_sync(kFullMask, at_node && !(flags & kFlagPlain)) == 0u;
 #endif
@@ -185,6 +271,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                         need_pop = true;
                     }
                 }
+#endif
             } else if (cur != kDone && !at_node) {
                 // leaf triangles, in leaf order
                 const RayCtx r = ctx_of(o, inv, sh, flags);

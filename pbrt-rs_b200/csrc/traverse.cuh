@@ -20,7 +20,9 @@ constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr int kStackDepth = 64;     // bvh.rs:839
 
 struct SceneView {
-    const float4* __restrict__ pairs;   // 4 x float4 per interior node (PairNode)
+    const float4* __restrict__ quads;   // 8 x float4 per record (QuadNode): two tree levels per fetch — the kernels' layout
+    uint32_t quad_root_ref;
+    const float4* __restrict__ pairs;   // 4 x float4 per interior node (PairNode): literal one-level walk (traverse())
     const float4* __restrict__ tris;    // 3 x float4 per triangle (PackedTri), BVH leaf order
     const uint32_t* __restrict__ slot_of_prim;   // caller's triangle id -> leaf-order slot
     uint32_t root_ref;

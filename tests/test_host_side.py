@@ -99,3 +99,17 @@ def test_empty_scene_host(pb2):
     assert b.info() == (0, 0, 0)
     wb = b.world_bound()
     assert (wb[:3] > 1e38).all() and (wb[3:] < -1e38).all()
+
+
+@pytest.mark.parametrize("scene", [["c2"], ["soup"], ["c3", "150"]])
+def test_quad_layout_walk_matches_reference_order(scene):
+    import os
+    """QuadNode collapse (bvh_build.cpp): a CPU walk of the two-levels-per-record layout with the kernel's rules tests the
+    same triangles in the same order as the reference-order binary walk — identical ids, t bits and triangle-test counts
+    on primary and bounce rays (tools/quad_sim.py asserts; the arithmetic is the oracle's)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "quad_sim.py")] + scene, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches 0" in r.stdout
