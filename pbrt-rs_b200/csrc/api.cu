@@ -211,6 +211,9 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
         v.quads = (const float4*)scene->d_quads;
         v.quad_root_ref = b.quad_root_ref;
         PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
+        launch_mark_degenerate(scene->d_tris, b.tris.size(), 0);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaDeviceSynchronize());
         std::vector<uint32_t> slot(n_tris);
         for (uint64_t i = 0; i < n_tris; ++i) slot[b.ordered_prims[i]] = (uint32_t)i;
         PB2_CUDA(cudaMemcpy(scene->d_slot_of_prim, slot.data(), n_tris * 4, cudaMemcpyHostToDevice));

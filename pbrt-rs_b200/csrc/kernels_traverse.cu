@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, co
 // variables exist for the tuning sweeps recorded in profiles/.
 static TraceTuning& tuning_ref() {
     static TraceTuning t = [] {
-        TraceTuning v{16, 12, 33, 0};
+        TraceTuning v{12, 8, 33, 0};   // profiles/r01_tuning.md: sweep on the QuadNode kernel
         if (const char* e = getenv("PB2_REFILL_BELOW")) v.refill_below = atoi(e);
         if (const char* e = getenv("PB2_NODE_QUORUM")) v.node_quorum = atoi(e);
         if (const char* e = getenv("PB2_LEAF_QUORUM")) v.leaf_quorum = atoi(e);
@@ -85,6 +85,23 @@ static unsigned persistent_grid(const void* kernel, uint64_t n) {
     const uint64_t want = (n + 127) / 128;
     const uint64_t full = (uint64_t)sm_count * (uint64_t)per_sm;
     return (unsigned)(want < full ? want : full);
+}
+
+// PackedTri.pad (v2.w) = 1 when Triangle::intersect rejects every hit of the triangle (degenerate dpdu/dpdv AND zero
+// geometric normal, triangle.rs:193-215): computed once per scene with the same tri_frame() the walk used to call per hit.
+__global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tris, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = tris[3ull * i], b = tris[3ull * i + 1];
+    float4 c = tris[3ull * i + 2];
+    vec3 du, dv;
+    const bool ok = tri_frame(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), &du, &dv);
+    c.w = __uint_as_float(ok ? 0u : 1u);
+    tris[3ull * i + 2] = c;
+}
+void launch_mark_degenerate(void* d_tris, uint64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_mark_degenerate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((float4*)d_tris, (uint32_t)n);
 }
 
 void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, unsigned long long* d_counter,

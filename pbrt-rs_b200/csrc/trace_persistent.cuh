@@ -116,6 +116,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
     uint2 stack[kStackDepth];                // {reference, entry distance bits}
 #endif
     int sp = 0;
+    uint2 top = make_uint2(0u, 0u);          // register copy of stack[sp - 1]: a pop never waits for local memory
     uint32_t cur = kDone;
     uint32_t ray_idx = 0;
     uint32_t flags = 0;
@@ -225,9 +226,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     const float inf = __int_as_float(0x7f800000);
                     const bool h0 = t0 < inf, h1 = t1 < inf, h2 = t2 < inf, h3 = t3 < inf;
                     // later candidates first, so the next one in visiting order is popped first
-                    if (h3 && (h0 || h1 || h2)) { stack[sp] = make_uint2(r3, __float_as_uint(t3)); ++sp; }
-                    if (h2 && (h0 || h1)) { stack[sp] = make_uint2(r2, __float_as_uint(t2)); ++sp; }
-                    if (h1 && h0) { stack[sp] = make_uint2(r1, __float_as_uint(t1)); ++sp; }
+                    if (h3 && (h0 || h1 || h2)) { top = make_uint2(r3, __float_as_uint(t3)); stack[sp] = top; ++sp; }
+                    if (h2 && (h0 || h1)) { top = make_uint2(r2, __float_as_uint(t2)); stack[sp] = top; ++sp; }
+                    if (h1 && h0) { top = make_uint2(r1, __float_as_uint(t1)); stack[sp] = top; ++sp; }
                     if (h0 || h1 || h2 || h3) cur = h0 ? r0 : (h1 ? r1 : (h2 ? r2 : r3));
                     else need_pop = true;
                 }
@@ -258,7 +259,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     const bool ok_near = neg ? okr : okl, ok_far = neg ? okl : okr;
                     if (ok_near) {
                         if (ok_far) {
-                            stack[sp] = make_uint2(far_ref, __float_as_uint(neg ? tl : tr));
+                            top = make_uint2(far_ref, __float_as_uint(neg ? tl : tr));
+                            stack[sp] = top;
                             ++sp;
                             if (tune.prefetch)
                                 prefetch_l2((far_ref & kLeafFlag) ? (const void*)(s.tris + 3ull * (far_ref & ~kLeafFlag))
@@ -285,8 +287,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     float t, b0, b1, b2;
                     if (tri_test(r, t_max, p0, p1, p2, &t, &b0, &b1, &b2)) {
                         if (ANY) { occluded = true; break; }
-                        vec3 du, dv;
-                        if (tri_frame(p0, p1, p2, &du, &dv)) {
+                        // c.w: Triangle::intersect bails out on this triangle's degenerate frame (triangle.rs:193-215);
+                        // a property of the triangle alone, evaluated once by k_mark_degenerate with tri_frame()
+                        if (__float_as_uint(c.w) == 0u) {
                             t_max = t;                                  // primitive.rs:70
                             flags |= kFlagFound;
                             sink.accept(ray_idx, __float_as_uint(a.w), t, b0, b1, b2);
@@ -306,7 +309,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                 cur = kDone;
                 while (sp > 0) {                                        // geometry.rs:749 re-applied at pop time
                     --sp;
-                    const uint2 e = stack[sp];
+                    const uint2 e = top;
+                    if (sp > 0) top = stack[sp - 1];                    // needed at the next pop, not now
                     if (__uint_as_float(e.y) < t_max) { cur = e.x; break; }
                 }
                 if (cur == kDone) {

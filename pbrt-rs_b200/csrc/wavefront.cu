@@ -1,5 +1,5 @@
 // wavefront.cu — the wavefront PathIntegrator: ray-gen -> extend (closest hit) -> material-sorted shade ->
-// shadow (any hit) + MIS (closest hit) -> resolve -> next bounce, and the Film accumulation kernels (sm_100a).
+// shadow (any hit) + MIS (closest hit), which fold their answers into L -> next bounce, and the Film accumulation kernels (sm_100a).
 //
 // Replaces SamplerIntegrator::render (src/core/integrator.rs:399-480), PathIntegrator::li (src/integrators/path.rs:65-213),
 // uniform_sample_one_light / estimate_direct (src/core/integrator.rs:92-266), DiffuseAreaLight / PointLight sampling
@@ -124,9 +124,11 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
 __global__ void k_iter_begin(PathBuffers b, int cur) {
     if (threadIdx.x == 0) {
         b.counters[T_EXTEND] += b.counters[C_ACTIVE_A + cur];
+        b.counters[T_SHADOW] += b.counters[C_SHADOW];        // rays of the previous bounce's visibility stage
+        b.counters[T_MIS] += b.counters[C_MIS];
         b.counters[C_ACTIVE_A + (cur ^ 1)] = 0;
         b.counters[C_MAT0] = b.counters[C_MAT1] = b.counters[C_MAT2] = 0;
-        b.counters[C_SHADOW] = b.counters[C_MIS] = b.counters[C_NEE] = 0;
+        b.counters[C_SHADOW] = b.counters[C_MIS] = 0;
         b.counters[C_WORK_EXTEND] = b.counters[C_WORK_SHADOW] = b.counters[C_WORK_MIS] = 0;
     }
 }
@@ -163,6 +165,20 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, Sha
     trace_persistent<false>(s, (uint32_t)b.counters[C_ACTIVE_A + cur], &b.counters[C_WORK_EXTEND], sink, tune);
 }
 
+// l += beta * (estimate_direct / light_pdf) (integrator.rs:178-191,243-261,:133, path.rs:117-120) for the NEE record of `slot`:
+// ld = [unoccluded light sample] + [BSDF sample that reached the light], added in that order.  Runs inside the visibility
+// kernels the moment the last pending query of the record is answered, so there is no separate resolve pass.
+__device__ __forceinline__ void resolve_nee(const PathBuffers& b, uint32_t slot, bool add_t1, float4 t1, bool add_t2, float4 t2) {
+    rgb3 ld = gray(0.0f);
+    if (add_t1) ld = ld + mkc(t1.x, t1.y, t1.z);
+    if (add_t2) ld = ld + mkc(t2.x, t2.y, t2.z);
+    const float pick_pdf = b.sh_d[slot].w;
+    const float4 bn = b.beta_nee[slot];
+    float4 Lf = b.L[slot];
+    const rgb3 L = mkc(Lf.x, Lf.y, Lf.z) + mkc(bn.x, bn.y, bn.z) * (ld / pick_pdf);
+    b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
+}
+
 struct ShadowSink {
     PathBuffers b;
     PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
@@ -175,7 +191,12 @@ struct ShadowSink {
     }
     PB2_D void accept(uint32_t, uint32_t, float, float, float, float) const {}
     PB2_D void finish(uint32_t, bool, float) const {}
-    PB2_D void occluded(uint32_t i, bool occ) const { b.occluded[b.q_shadow[i]] = occ ? 1 : 0; }
+    PB2_D void occluded(uint32_t i, bool occ) const {
+        const uint32_t slot = b.q_shadow[i];
+        const float4 t1 = b.t1[slot];
+        if (__float_as_uint(t1.w) == 1u) resolve_nee(b, slot, !occ, t1, false, t1);      // no MIS ray pending: done
+        else b.occluded[slot] = occ ? 1 : 0;                                              // k_mis finishes the record
+    }
 };
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
     const ShadowSink sink{b};
@@ -193,7 +214,13 @@ struct MisSink {
         return true;
     }
     PB2_D void accept(uint32_t i, uint32_t prim, float, float, float, float) const { b.mis_prim[b.q_mis[i]] = prim; }
-    PB2_D void finish(uint32_t i, bool found, float) const { if (!found) b.mis_prim[b.q_mis[i]] = 0xFFFFFFFFu; }
+    PB2_D void finish(uint32_t i, bool found, float) const {
+        const uint32_t slot = b.q_mis[i];
+        const float4 t1 = b.t1[slot], t2 = b.t2[slot];
+        const bool reached_light = found && b.mis_prim[slot] == __float_as_uint(t2.w);    // D56 FIX: the closest hit is the light
+        const bool lit = (__float_as_uint(t1.w) & 1u) && !b.occluded[slot];               // k_shadow ran before this kernel
+        resolve_nee(b, slot, lit, t1, reached_light, t2);
+    }
     PB2_D void occluded(uint32_t, bool) const {}
 };
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_mis(SceneView s, PathBuffers b, TraceTuning tune) {
@@ -319,13 +346,14 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
     b.sh_o[slot] = make_float4(sh_o.x, sh_o.y, sh_o.z, 1.0f - PB2_SHADOW_EPS);
     b.sh_d[slot] = make_float4(sh_d.x, sh_d.y, sh_d.z, pick_pdf);
     b.t1[slot] = make_float4(t1.r, t1.g, t1.b, __uint_as_float(pending));
-    b.mis_o[slot] = make_float4(mis_o.x, mis_o.y, mis_o.z, 0.0f);
-    b.mis_d[slot] = make_float4(mis_d.x, mis_d.y, mis_d.z, 0.0f);
-    b.t2[slot] = make_float4(t2.r, t2.g, t2.b, __uint_as_float(light.prim));
     b.beta_nee[slot] = make_float4(beta.r, beta.g, beta.b, 0.0f);
-    queue_push(&b.counters[C_NEE], b.q_nee, slot);
     if (pending & 1u) queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
-    if (pending & 2u) queue_push(&b.counters[C_MIS], b.q_mis, slot);
+    if (pending & 2u) {
+        b.mis_o[slot] = make_float4(mis_o.x, mis_o.y, mis_o.z, 0.0f);
+        b.mis_d[slot] = make_float4(mis_d.x, mis_d.y, mis_d.z, 0.0f);
+        b.t2[slot] = make_float4(t2.r, t2.g, t2.b, __uint_as_float(light.prim));
+        queue_push(&b.counters[C_MIS], b.q_mis, slot);
+    }
     (void)s;
 }
 
@@ -405,27 +433,6 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
             }
         }
         b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
-    }
-}
-
-// l += beta * (estimate_direct / light_pdf) once both visibility queries are back (integrator.rs:178-191,243-261,:133).
-__global__ void __launch_bounds__(kThreads) k_resolve(PathBuffers b) {
-    const uint64_t n = b.counters[C_NEE];
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t slot = b.q_nee[i];
-        const float4 t1 = b.t1[slot], t2 = b.t2[slot], bn = b.beta_nee[slot];
-        const unsigned pending = __float_as_uint(t1.w);
-        rgb3 ld = gray(0.0f);
-        if ((pending & 1u) && !b.occluded[slot]) ld = ld + mkc(t1.x, t1.y, t1.z);
-        if ((pending & 2u) && b.mis_prim[slot] == __float_as_uint(t2.w)) ld = ld + mkc(t2.x, t2.y, t2.z);
-        const float pick_pdf = b.sh_d[slot].w;
-        float4 Lf = b.L[slot];
-        const rgb3 L = mkc(Lf.x, Lf.y, Lf.z) + mkc(bn.x, bn.y, bn.z) * (ld / pick_pdf);
-        b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        b.counters[T_SHADOW] += b.counters[C_SHADOW];
-        b.counters[T_MIS] += b.counters[C_MIS];
     }
 }
 
@@ -596,8 +603,7 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         if (depth < pp.max_depth && sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
             k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);
-            k_resolve<<<grid_for(wf, n, 4), kThreads, 0, st>>>(b);
-            launches += 3;
+            launches += 2;
         }
         launches += 5;
     }
@@ -612,9 +618,9 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&wf->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    // one arena: 13 float4/uint4 arrays, rng, occluded, mis_prim, 8 queues, counters
+    // one arena: 13 float4/uint4 arrays, rng, occluded, mis_prim, 7 queues, counters
     const size_t f4 = capacity * 16;
-    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + capacity + 8 * capacity * 4 + C_COUNT * 8 + 4096;
+    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + capacity + 7 * capacity * 4 + C_COUNT * 8 + 4096;
     cudaError_t e = cudaMalloc(&wf->arena, bytes);
     if (e != cudaSuccess) { delete wf; *out = nullptr; return (int)e; }
     char* p = (char*)wf->arena;
@@ -631,7 +637,6 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     for (int i = 0; i < 3; ++i) b.q_mat[i] = (uint32_t*)take(capacity * 4);
     b.q_shadow = (uint32_t*)take(capacity * 4);
     b.q_mis = (uint32_t*)take(capacity * 4);
-    b.q_nee = (uint32_t*)take(capacity * 4);
     b.counters = (unsigned long long*)take(C_COUNT * 8);
     cudaMemset(b.counters, 0, C_COUNT * 8);
     *out = wf;

@@ -50,7 +50,7 @@ struct PathMap {
 };
 
 enum Counter : int {
-    C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6, C_NEE = 7,
+    C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6,
     C_WORK_EXTEND = 8, C_WORK_SHADOW = 9, C_WORK_MIS = 10, C_STRAYS = 11, C_STRAY_OVERFLOW = 12,
     T_CAMERA = 16, T_EXTEND = 17, T_SHADOW = 18, T_MIS = 19, T_LAUNCHES = 20, C_COUNT = 24
 };
@@ -76,7 +76,6 @@ struct PathBuffers {
     uint32_t* q_mat[3];
     uint32_t* q_shadow;
     uint32_t* q_mis;
-    uint32_t* q_nee;
     unsigned long long* counters;
 };
 
