@@ -449,9 +449,17 @@ def main():
                                 "nodes_per_ray": float(cnt[0]) / n, "tris_per_ray": float(cnt[1]) / n,
                                 "mrays_s": n / (kernel_ms[name] * 1e-3) / 1e6}
         dom = max(("closest_primary", "any_shadow", "closest_bounce"), key=lambda k: kernel_ms[k])
+        # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (profiles/traffic.json,
+        # written by tools/ncu_traffic.py from the .ncu-rep; dram__bytes_read.sum + dram__bytes_write.sum)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic, traffic_src = tj["launches"].get(dom), tj.get("source")
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "hbm", "kernel": f"k_closest_hit/k_any_hit [{dom}]", "achieved": per_kernel[dom]["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": per_kernel[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                    "per_kernel": per_kernel}
+                    "unit": "GB/s", "frac": per_kernel[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "per_kernel": per_kernel}
         k = max(1, args.cpu_stride)
         sample = [np.ascontiguousarray(g_rays[::k]), np.ascontiguousarray(g_srays[::k]), np.ascontiguousarray(g_brays[::k])]
         n_sample = sum(len(s) for s in sample)

@@ -136,7 +136,7 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
     if (!out) return set_error(PB2_ERR_INVALID, "null out");
     *out = nullptr;
     if ((n_verts && !verts) || (n_tris && !indices)) return set_error(PB2_ERR_INVALID, "null mesh arrays");
-    if (n_tris >= 0x7FFFFFFFull) return set_error(PB2_ERR_LIMIT, "at most 2^31-1 triangles");
+    if (n_tris >= (1ull << 29)) return set_error(PB2_ERR_LIMIT, "at most 2^29-1 triangles (29-bit references in the device BVH records)");
     for (uint64_t i = 0; i < 3 * n_verts; ++i)
         if (!std::isfinite(verts[i])) return set_error(PB2_ERR_INVALID, "vertex %llu has a non-finite coordinate", (unsigned long long)(i / 3));
     for (uint64_t i = 0; i < 3 * n_tris; ++i)

@@ -394,16 +394,16 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
                 Q.hix[k] = Q.hiy[k] = Q.hiz[k] = -inf;
                 Q.ref[k] = kQuadEmpty;
             }
-            Q.pad[0] = Q.pad[1] = Q.pad[2] = 0;
+            Q.pad[0] = Q.pad[1] = Q.pad[2] = Q.pad[3] = 0;
             const LinearNode& ln = out->nodes[P];
-            uint32_t axes = ln.axis;
+            uint32_t axes[3] = {ln.axis, 0u, 0u};
             const uint32_t kids[2] = {P + 1, ln.offset};
             for (int g = 0; g < 2; ++g) {
                 const LinearNode& X = out->nodes[kids[g]];
                 uint32_t members[2];
                 int n_members;
                 if (X.n_prims > 0) { members[0] = kids[g]; n_members = 1; }
-                else { members[0] = kids[g] + 1; members[1] = X.offset; n_members = 2; axes |= (uint32_t)X.axis << (2 + 2 * g); }
+                else { members[0] = kids[g] + 1; members[1] = X.offset; n_members = 2; axes[1 + g] = X.axis; }
                 for (int j = 0; j < n_members; ++j) {
                     const LinearNode& Y = out->nodes[members[j]];
                     const int k = 2 * g + j;
@@ -413,7 +413,7 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
                     Q.ref[k] = Y.n_prims > 0 ? (kLeafBit | Y.offset) : members[j];
                 }
             }
-            Q.axes = axes;
+            Q.pad[0] = axes[0] | (axes[1] << 2) | (axes[2] << 4);      // applied to the references once they are final
             return q;
         };
         std::vector<Frame> work;
@@ -428,6 +428,11 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
             const uint32_t child_quad = new_quad(r);
             out->quads[fq].ref[k] = child_quad;
             work.push_back({r, child_quad, 0});
+        }
+        for (QuadNode& Q : out->quads) {                              // tag the (now final) references with the axes
+            const uint32_t ax = Q.pad[0];
+            Q.pad[0] = 0;
+            for (int k = 0; k < 3; ++k) Q.ref[k] = (Q.ref[k] & kQuadRefMask) | (((ax >> (2 * k)) & 3u) << kQuadAxisShift);
         }
         out->quad_root_ref = 0;
     } else {

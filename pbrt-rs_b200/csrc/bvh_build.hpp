@@ -44,15 +44,17 @@ static_assert(sizeof(PairNode) == 64, "PairNode must be 64 bytes");
 // Device node of the traversal kernels: interior node P with children A (= P+1) and B (= second child) folded with
 // A's and B's own children.  Slots 0,1 belong to A, slots 2,3 to B: an interior child contributes its two children
 // (first child in the lower slot), a leaf child occupies the lower slot of its group and leaves the other one empty
-// (inverted box, ref = kQuadEmpty).  axes = axis(P) | axis(A) << 2 | axis(B) << 4 (bvh.rs:856-866 decides near/far by
-// the sign of the ray direction on these axes).  ref = quad index, or kLeafBit | first triangle slot.
+// (inverted box, ref = kQuadEmpty).  ref = quad index, or kLeafBit | first triangle slot, in bits 0-28 and 31; bits 29-30
+// of ref[0], ref[1], ref[2] carry axis(P), axis(A), axis(B) (bvh.rs:856-866 decides near/far by the sign of the ray
+// direction on these axes), so a visit reads 112 bytes: three 256-bit loads (boxes) and one 128-bit load (references).
 struct alignas(128) QuadNode {
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     uint32_t ref[4];
-    uint32_t axes, pad[3];
+    uint32_t pad[4];
 };
 static_assert(sizeof(QuadNode) == 128, "QuadNode must be 128 bytes");
 constexpr uint32_t kQuadEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kQuadAxisShift = 29, kQuadRefMask = 0x9FFFFFFFu;      // index space: 2^29 quads / triangle slots
 
 struct alignas(16) PackedTri {
     float v0[3];

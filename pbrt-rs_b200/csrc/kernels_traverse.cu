@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, co
 // variables exist for the tuning sweeps recorded in profiles/.
 static TraceTuning& tuning_ref() {
     static TraceTuning t = [] {
-        TraceTuning v{12, 8, 33, 0};   // profiles/r01_tuning.md: sweep on the QuadNode kernel
+        TraceTuning v{12, 8, 18, 0};   // profiles/r01_tuning.md: sweep on the QuadNode kernel
         if (const char* e = getenv("PB2_REFILL_BELOW")) v.refill_below = atoi(e);
         if (const char* e = getenv("PB2_NODE_QUORUM")) v.node_quorum = atoi(e);
         if (const char* e = getenv("PB2_LEAF_QUORUM")) v.leaf_quorum = atoi(e);
@@ -82,6 +82,8 @@ static unsigned persistent_grid(const void* kernel, uint64_t n) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
     if (per_sm < 1) per_sm = 1;
+    static const int cap = getenv("PB2_GRID_PER_SM") ? atoi(getenv("PB2_GRID_PER_SM")) : 0;      // occupancy experiments
+    if (cap > 0 && cap < per_sm) per_sm = cap;
     const uint64_t want = (n + 127) / 128;
     const uint64_t full = (uint64_t)sm_count * (uint64_t)per_sm;
     return (unsigned)(want < full ? want : full);

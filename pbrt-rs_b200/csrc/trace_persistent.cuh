@@ -204,10 +204,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     // that accepts the ray implies its parent does (rounded subtract / multiply are monotone), and the
                     // parent's t_max at its visit is never smaller than the child's.
                     const float4* qp = s.quads + 8ull * cur;
-                    const float4 lox = ldg4(qp), loy = ldg4(qp + 1), loz = ldg4(qp + 2);
-                    const float4 hix = ldg4(qp + 3), hiy = ldg4(qp + 4), hiz = ldg4(qp + 5);
+                    float4 lox, loy, loz, hix, hiy, hiz;
+                    ldg8(qp, &lox, &loy);
+                    ldg8(qp + 2, &loz, &hix);
+                    ldg8(qp + 4, &hiy, &hiz);
                     const uint4 ref = __ldg(reinterpret_cast<const uint4*>(qp + 6));
-                    const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(qp + 7));
                     const bool nx = (flags & 1u) != 0u, ny = (flags & 2u) != 0u, nz = (flags & 4u) != 0u;
                     float t0 = quad_child_entry(nx ? hix.x : lox.x, ny ? hiy.x : loy.x, nz ? hiz.x : loz.x,
                                                 nx ? lox.x : hix.x, ny ? loy.x : hiy.x, nz ? loz.x : hiz.x, o, inv, t_max);
@@ -217,10 +218,12 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                                                 nx ? lox.z : hix.z, ny ? loy.z : hiy.z, nz ? loz.z : hiz.z, o, inv, t_max);
                     float t3 = quad_child_entry(nx ? hix.w : lox.w, ny ? hiy.w : loy.w, nz ? hiz.w : loz.w,
                                                 nx ? lox.w : hix.w, ny ? loy.w : hiy.w, nz ? loz.w : hiz.w, o, inv, t_max);
-                    uint32_t r0 = ref.x, r1 = ref.y, r2 = ref.z, r3 = ref.w;
-                    swap_if(((flags >> ((axes >> 2) & 3u)) & 1u) != 0u, r0, t0, r1, t1);      // inside A
-                    swap_if(((flags >> ((axes >> 4) & 3u)) & 1u) != 0u, r2, t2, r3, t3);      // inside B
-                    const bool swap_groups = ((flags >> (axes & 3u)) & 1u) != 0u;            // A before B, or B before A
+                    // bits 29-30 of the first three references: axis(P), axis(A), axis(B)
+                    const bool swap_groups = ((flags >> ((ref.x >> 29) & 3u)) & 1u) != 0u;   // A before B, or B before A
+                    const bool swap_a = ((flags >> ((ref.y >> 29) & 3u)) & 1u) != 0u, swap_b = ((flags >> ((ref.z >> 29) & 3u)) & 1u) != 0u;
+                    uint32_t r0 = ref.x & 0x9FFFFFFFu, r1 = ref.y & 0x9FFFFFFFu, r2 = ref.z & 0x9FFFFFFFu, r3 = ref.w;
+                    swap_if(swap_a, r0, t0, r1, t1);                                          // inside A
+                    swap_if(swap_b, r2, t2, r3, t3);                                          // inside B
                     swap_if(swap_groups, r0, t0, r2, t2);
                     swap_if(swap_groups, r1, t1, r3, t3);
                     const float inf = __int_as_float(0x7f800000);

@@ -152,6 +152,13 @@ PB2_D bool tri_frame(vec3 p0, vec3 p1, vec3 p2, vec3* dpdu, vec3* dpdv) {
 }
 
 PB2_D float4 ldg4(const float4* p) { return __ldg(p); }
+// One 256-bit read-only load (sm_100: LDG.E.256) of two consecutive float4 at a 32-byte aligned address: half the L1
+// wavefronts and load instructions of two 128-bit loads.
+PB2_D void ldg8(const float4* p, float4* a, float4* b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+                 : "l"(p));
+}
 
 // One ray through the BVH.  ANY = intersect_p semantics (first accepted triangle ends the walk).
 template <bool ANY>

@@ -85,7 +85,7 @@ static SimOut walk_quad(const pb2::HostBVH& b, Ray ray, uint64_t* steps, uint64_
             ++*steps;
             E e[4];
             for (int k = 0; k < 4; ++k) {
-                e[k].ref = q.ref[k];
+                e[k].ref = q.ref[k] == pb2::kQuadEmpty ? q.ref[k] : (q.ref[k] & pb2::kQuadRefMask);
                 e[k].t = kInfinity;
                 if (q.ref[k] == pb2::kQuadEmpty) continue;
                 ++*boxes;
@@ -93,7 +93,7 @@ static SimOut walk_quad(const pb2::HostBVH& b, Ray ray, uint64_t* steps, uint64_
                 Float te;
                 if (slab_test(bb, ray, inv, neg, &te)) e[k].t = te;      // includes te < t_max
             }
-            const int aP = q.axes & 3, aA = (q.axes >> 2) & 3, aB = (q.axes >> 4) & 3;
+            const int aP = (q.ref[0] >> pb2::kQuadAxisShift) & 3, aA = (q.ref[1] >> pb2::kQuadAxisShift) & 3, aB = (q.ref[2] >> pb2::kQuadAxisShift) & 3;
             if (neg[aA]) std::swap(e[0], e[1]);
             if (neg[aB]) std::swap(e[2], e[3]);
             if (neg[aP]) { std::swap(e[0], e[2]); std::swap(e[1], e[3]); }

@@ -44,9 +44,10 @@ def timed(fn, reps=8):
 refills = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "8,12,16,20,24".split(","))]
 nodeqs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "6,10,12,16,20".split(","))]
 prefs = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "0".split(","))]
-for r, q, p in itertools.product(refills, nodeqs, prefs):
-    pb2.check(L.pb2_set_trace_tuning(r, q, 33, p))
+leafqs = [int(x) for x in (sys.argv[4].split(",") if len(sys.argv) > 4 else "33".split(","))]
+for r, q, p, lq in itertools.product(refills, nodeqs, prefs, leafqs):
+    pb2.check(L.pb2_set_trace_tuning(r, q, lq, p))
     t1 = timed(lambda: accel.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), d_b0.data_ptr(), st))
     t2 = timed(lambda: accel.intersect_p_device(d_s.data_ptr(), n, d_occ.data_ptr(), st))
     t3 = timed(lambda: accel.intersect_device(d_b.data_ptr(), n, d_bh.data_ptr(), None, st))
-    print(f"refill<{r:2d} node_q {q:2d} prefetch {p}: primary {t1:.4f} shadow {t2:.4f} bounce {t3:.4f} sum {t1+t2+t3:.4f} ms", flush=True)
+    print(f"refill<{r:2d} node_q {q:2d} leaf_q {lq:2d} prefetch {p}: primary {t1:.4f} shadow {t2:.4f} bounce {t3:.4f} sum {t1+t2+t3:.4f} ms", flush=True)
