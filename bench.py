@@ -389,6 +389,15 @@ def main():
 
     for _ in range(args.warmup):
         e2e_step()
+    # what the link itself delivers: one plain pinned H2D / D2H copy of a ray-set-sized buffer (explains e2e vs value)
+    cp = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    cp[0].record()
+    d_rays.view(torch.float32).copy_(h_rays, non_blocking=True)
+    cp[1].record()
+    h_rays.copy_(d_rays.view(torch.float32), non_blocking=True)
+    cp[2].record()
+    torch.cuda.synchronize()
+    pcie = {"h2d_gbs": n * 32 / (cp[0].elapsed_time(cp[1]) * 1e-3) / 1e9, "d2h_gbs": n * 32 / (cp[1].elapsed_time(cp[2]) * 1e-3) / 1e9}
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -490,7 +499,8 @@ def main():
                        "scene_gen_s": t_gen, "bvh_build_upload_s": t_build},
             "kernel_ms": kernel_ms, "hits_crc32": hits_crc,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
-                    "api": "pb2_intersect / pb2_intersect_p with pinned host buffers"},
+                    "api": "pb2_intersect / pb2_intersect_p with pinned host buffers", "pcie_measured": pcie,
+                    "link_bound_mrays_s": world * rays_per_step / (3 * n * 32 / (pcie["h2d_gbs"] * 1e9)) / 1e6},
             "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "path": path_c2, "path_multi_gpu": path_c5,

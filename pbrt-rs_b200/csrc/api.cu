@@ -49,13 +49,20 @@ void pb2_scene::free_device() {
     d_counters = nullptr;
     d_quads = nullptr;
     d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
-    for (int i = 0; i < 2; ++i) {
-        if (stage[i].d_in) cudaFree(stage[i].d_in);
-        if (stage[i].d_out) cudaFree(stage[i].d_out);
-        if (stage[i].d_aux) cudaFree(stage[i].d_aux);
-        if (stage[i].stream) cudaStreamDestroy(stage[i].stream);
-        stage[i] = Stage();
+    for (int i = 0; i < kStages; ++i) {
+        Stage& st = pipe.slot[i];
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+        if (st.d_aux) cudaFree(st.d_aux);
+        if (st.in_ready) cudaEventDestroy(st.in_ready);
+        if (st.done) cudaEventDestroy(st.done);
+        if (st.drained) cudaEventDestroy(st.drained);
+        st = Stage();
     }
+    if (pipe.h2d) cudaStreamDestroy(pipe.h2d);
+    if (pipe.compute) cudaStreamDestroy(pipe.compute);
+    if (pipe.d2h) cudaStreamDestroy(pipe.d2h);
+    pipe.h2d = pipe.compute = pipe.d2h = nullptr;
     if (wf) { wavefront_destroy(wf); wf = nullptr; }
 }
 
@@ -265,9 +272,15 @@ int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prim
 
 // ---- batched intersect ------------------------------------------------------------------------------------
 static int ensure_stage(pb2_scene* s, size_t chunk) {
-    for (int i = 0; i < 2; ++i) {
-        Stage& st = s->stage[i];
-        if (!st.stream) PB2_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+    Pipe& p = s->pipe;
+    if (!p.h2d) PB2_CUDA(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+    if (!p.compute) PB2_CUDA(cudaStreamCreateWithFlags(&p.compute, cudaStreamNonBlocking));
+    if (!p.d2h) PB2_CUDA(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < kStages; ++i) {
+        Stage& st = p.slot[i];
+        if (!st.in_ready) PB2_CUDA(cudaEventCreateWithFlags(&st.in_ready, cudaEventDisableTiming));
+        if (!st.done) PB2_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+        if (!st.drained) PB2_CUDA(cudaEventCreateWithFlags(&st.drained, cudaEventDisableTiming));
         if (st.cap < chunk) {
             if (st.d_in) cudaFree(st.d_in);
             if (st.d_out) cudaFree(st.d_out);
@@ -288,9 +301,38 @@ static int check_ready(const pb2_scene* scene) {
     return PB2_OK;
 }
 
-// Host-buffer entry points stream the batch through two device staging buffers so that the H2D copy of chunk k+1,
-// the traversal of chunk k and the D2H copy of chunk k-1 overlap (pinned caller memory: pb2_host_alloc).
-static const size_t kChunk = 1u << 18;
+// Host-buffer entry points stream the batch through the ring (api_internal.hpp: Pipe): the H2D copy of chunk k+1, the
+// traversal of chunk k and the D2H copy of chunk k-1 run on different engines at the same time (pinned caller memory:
+// pb2_host_alloc; pageable memory works but its copies are staged by the driver).  128 K rays per chunk keeps the pipeline
+// fill (one H2D) and drain (one kernel + one D2H) short against the 8+ chunks of a megaray batch.
+static const size_t kChunk = 1u << 17;
+
+extern "C++" {
+template <class Launch>
+static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t out_bytes, void* out, float* b0, Launch&& launch) {
+    int rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
+    if (rc) return rc;
+    Pipe& p = scene->pipe;
+    uint64_t c = 0;
+    for (uint64_t off = 0; off < n; off += kChunk, ++c) {
+        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
+        Stage& st = p.slot[c % kStages];
+        if (c >= (uint64_t)kStages) PB2_CUDA(cudaStreamWaitEvent(p.h2d, st.drained, 0));       // slot's previous chunk fully out
+        PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, p.h2d));
+        PB2_CUDA(cudaEventRecord(st.in_ready, p.h2d));
+        PB2_CUDA(cudaStreamWaitEvent(p.compute, st.in_ready, 0));
+        launch(st, m, p.compute);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaEventRecord(st.done, p.compute));
+        PB2_CUDA(cudaStreamWaitEvent(p.d2h, st.done, 0));
+        PB2_CUDA(cudaMemcpyAsync((char*)out + off * out_bytes, st.d_out, m * out_bytes, cudaMemcpyDeviceToHost, p.d2h));
+        if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, p.d2h));
+        PB2_CUDA(cudaEventRecord(st.drained, p.d2h));
+    }
+    PB2_CUDA(cudaStreamSynchronize(p.d2h));
+    return PB2_OK;
+}
+}  // extern "C++"
 
 int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0) {
     int rc = check_ready(scene);
@@ -298,21 +340,9 @@ int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hi
     if (n && (!rays || !hits)) return set_error(PB2_ERR_INVALID, "null ray/hit buffer");
     std::lock_guard<std::mutex> lock(scene->mu);
     PB2_CUDA(cudaSetDevice(scene->device));
-    rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
-    if (rc) return rc;
-    int k = 0;
-    for (uint64_t off = 0; off < n; off += kChunk, k ^= 1) {
-        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
-        Stage& st = scene->stage[k];
-        PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
-        launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, scene->next_counter(), st.stream);
-        PB2_CUDA(cudaGetLastError());
-        PB2_CUDA(cudaMemcpyAsync(hits + off, st.d_out, m * 16, cudaMemcpyDeviceToHost, st.stream));
-        if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, st.stream));
-    }
-    PB2_CUDA(cudaStreamSynchronize(scene->stage[0].stream));
-    PB2_CUDA(cudaStreamSynchronize(scene->stage[1].stream));
-    return PB2_OK;
+    return run_pipe(scene, rays, n, 16, hits, b0, [&](Stage& st, uint64_t m, cudaStream_t s) {
+        launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, scene->next_counter(), s);
+    });
 }
 
 int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out) {
@@ -321,20 +351,9 @@ int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* 
     if (n && (!rays || !out)) return set_error(PB2_ERR_INVALID, "null ray/output buffer");
     std::lock_guard<std::mutex> lock(scene->mu);
     PB2_CUDA(cudaSetDevice(scene->device));
-    rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
-    if (rc) return rc;
-    int k = 0;
-    for (uint64_t off = 0; off < n; off += kChunk, k ^= 1) {
-        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
-        Stage& st = scene->stage[k];
-        PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, st.stream));
-        launch_any_hit(scene->view, st.d_in, m, st.d_out, scene->next_counter(), st.stream);
-        PB2_CUDA(cudaGetLastError());
-        PB2_CUDA(cudaMemcpyAsync(out + off, st.d_out, m, cudaMemcpyDeviceToHost, st.stream));
-    }
-    PB2_CUDA(cudaStreamSynchronize(scene->stage[0].stream));
-    PB2_CUDA(cudaStreamSynchronize(scene->stage[1].stream));
-    return PB2_OK;
+    return run_pipe(scene, rays, n, 1, out, nullptr, [&](Stage& st, uint64_t m, cudaStream_t s) {
+        launch_any_hit(scene->view, st.d_in, m, st.d_out, scene->next_counter(), s);
+    });
 }
 
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream) {

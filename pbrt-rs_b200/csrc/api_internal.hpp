@@ -25,12 +25,21 @@ int make_camera_view(const pb2_camera* cam, CameraView* out);
         if (pb2_e_ != cudaSuccess) return pb2::cuda_fail(pb2_e_, #call, __FILE__, __LINE__); \
     } while (0)
 
-struct Stage {
-    cudaStream_t stream = nullptr;
+// Host-buffer batches stream through a ring of device slots on three streams — H2D copies, kernels, D2H copies — so the
+// two copy engines and the SMs each run their own in-order queue and all three overlap.
+struct Stage {                          // one ring slot
     void* d_in = nullptr;
     void* d_out = nullptr;
     void* d_aux = nullptr;
+    cudaEvent_t in_ready = nullptr;     // H2D of the chunk in this slot finished
+    cudaEvent_t done = nullptr;         // kernel finished
+    cudaEvent_t drained = nullptr;      // D2H finished: the slot may be overwritten
     size_t cap = 0;
+};
+constexpr int kStages = 4;
+struct Pipe {
+    cudaStream_t h2d = nullptr, compute = nullptr, d2h = nullptr;
+    Stage slot[kStages];
 };
 
 struct Wavefront;
@@ -68,7 +77,7 @@ struct pb2_scene {
     std::vector<float> light_func[2], light_cdf[2];
     float light_func_int[2] = {0.0f, 0.0f};
     pb2::SceneView view;
-    pb2::Stage stage[2];
+    pb2::Pipe pipe;
     pb2::Wavefront* wf = nullptr;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void free_device();
