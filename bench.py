@@ -172,6 +172,44 @@ def bench_path_c2(pb2, scenes, torch, args, dist, world):
             "mean_rgb": [float(v) for v in pb2_mean_rgb(film)]}, (accel, camera, integ, film, sc)
 
 
+def bench_path_c4(pb2, scenes, torch, args, dist, world, spp_timed=16):
+    """BASELINE config 3 (mixed matte / plastic / glass, point + area light, maxdepth 8, 1920x1080 @ 256 spp, power light
+    distribution, material-sorted shading): a step renders sample indices [0, spp_timed) of the 256 spp of every pixel —
+    every sample index costs the same, so Msamples/s is that of the full frame."""
+    sc = scenes.scene_c4()
+    cam = scenes.C4_CAMERA
+    pk = dict(scenes.C4_PATH)
+    accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4)
+    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    integ = pb2.PathIntegrator(accel, camera, **pk)
+    film = pb2.Film(cam["res"])
+    stream = torch.cuda.current_stream().cuda_stream
+    integ.render(film, 0, 4, stream=stream)
+    torch.cuda.synchronize()
+    c0 = integ.counters()
+    steps = 2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        film.clear()
+        a.record()
+        integ.render(film, 0, spp_timed, stream=stream)
+        b.record()
+    torch.cuda.synchronize()
+    c1 = integ.counters()
+    tot = float(sum(a.elapsed_time(b) for a, b in ev))
+    if world > 1:
+        t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = float(t[0])
+    n_samples = cam["res"][0] * cam["res"][1] * spp_timed
+    rays = {k: (c1[k] - c0[k]) / steps for k in ("extend_rays", "shadow_rays", "mis_rays")}
+    return {"workload": f"C4: {len(sc['idx'])}-triangle room, matte / plastic / glass spheres, area + point light, PathIntegrator maxdepth=8, "
+                        f"1920x1080, sample indices [0,{spp_timed}) of 256 spp per step, power light distribution",
+            "unit": "Msamples/s", "value": world * n_samples * steps / (tot * 1e-3) / 1e6, "ms_per_step": tot / steps,
+            "samples_per_step": n_samples, "rays_per_step": rays, "mrays_per_s": sum(rays.values()) / (tot / steps * 1e-3) / 1e6,
+            "mean_rgb": [float(v) for v in pb2_mean_rgb(film)]}
+
+
 def pb2_mean_rgb(film):
     return film.resolve_rgb().mean(axis=(0, 1))
 
@@ -414,6 +452,7 @@ def main():
     # ---- path tracing (second half of the BASELINE metric) ----
     dist_mod = dist if world > 1 else None
     path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
+    path_c4 = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
     path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world) if world > 1 else None
     path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0])
 
@@ -503,7 +542,7 @@ def main():
                     "link_bound_mrays_s": world * rays_per_step / (3 * n * 32 / (pcie["h2d_gbs"] * 1e9)) / 1e6},
             "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "path": path_c2, "path_multi_gpu": path_c5,
+            "path": path_c2, "path_c4": path_c4, "path_multi_gpu": path_c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

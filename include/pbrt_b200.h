@@ -180,6 +180,10 @@ int pb2_film_read_xyzw(pb2_film* film, float* out);
 /* Film::write_image (:153-178): XYZ -> RGB, / weight, clamp >= 0, * scale. */
 int pb2_film_resolve_rgb(pb2_film* film, float scale, float* rgb);
 int pb2_film_device_ptr(pb2_film* film, void** d_xyzw, uint64_t* n_floats);
+/* Film::write_image (film.rs:153-180) through to a file — the reference stops at todo!() after building the RGB array
+ * (imageio.rs:3-5).  ".pfm": float RGB, rows bottom-to-top, little-endian; ".ppm": 8-bit P6 with pbrt's sRGB gamma
+ * (pbrt-v3 imageio.cpp GammaCorrect + 255 v + 0.5 clamp).  Any other extension is PB2_ERR_INVALID. */
+int pb2_film_write_image(pb2_film* film, const char* filename, float scale);
 
 /* ---- Integrator::render / PathIntegrator::li (src/core/integrator.rs:399-480, src/integrators/path.rs) -- */
 /* Wavefront path tracer: renders sample indices [sample_begin, sample_end) of every pixel into `film`

@@ -136,6 +136,7 @@ def lib():
         "pb2_film_create": [vp, vp], "pb2_film_destroy": [vp], "pb2_film_clear": [vp],
         "pb2_film_add_samples": [vp, vp, vp, vp, u64], "pb2_film_read_xyzw": [vp, vp],
         "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_device_ptr": [vp, vp, vp],
+        "pb2_film_write_image": [vp, C.c_char_p, f32],
         "pb2_render_path": [vp, vp, vp, vp, vp], "pb2_path_li": [vp, vp, vp, vp, vp, u64, vp, vp],
         "pb2_render_counters": [vp, vp],
         "pb2_nccl_unique_id": [vp], "pb2_nccl_init": [vp, i32, i32], "pb2_nccl_shutdown": [],
@@ -384,6 +385,10 @@ class Film:
         out = np.empty((self.res[1], self.res[0], 3), dtype=np.float32)
         check(lib().pb2_film_resolve_rgb(self.h, scale, _p(out)))
         return out
+
+    def write_image(self, filename, scale=1.0):
+        """Film::write_image (film.rs:153-180) through to a .pfm / .ppm file."""
+        check(lib().pb2_film_write_image(self.h, os.fsencode(filename), scale))
 
     def device_ptr(self):
         ptr, n = C.c_void_p(), C.c_uint64()

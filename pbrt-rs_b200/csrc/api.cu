@@ -60,9 +60,9 @@ void pb2_scene::free_device() {
         st = Stage();
     }
     if (pipe.h2d) cudaStreamDestroy(pipe.h2d);
-    if (pipe.compute) cudaStreamDestroy(pipe.compute);
+    for (int i = 0; i < 2; ++i) { if (pipe.compute[i]) cudaStreamDestroy(pipe.compute[i]); pipe.compute[i] = nullptr; }
     if (pipe.d2h) cudaStreamDestroy(pipe.d2h);
-    pipe.h2d = pipe.compute = pipe.d2h = nullptr;
+    pipe.h2d = pipe.d2h = nullptr;
     if (wf) { wavefront_destroy(wf); wf = nullptr; }
 }
 
@@ -274,7 +274,8 @@ int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prim
 static int ensure_stage(pb2_scene* s, size_t chunk) {
     Pipe& p = s->pipe;
     if (!p.h2d) PB2_CUDA(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
-    if (!p.compute) PB2_CUDA(cudaStreamCreateWithFlags(&p.compute, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i)
+        if (!p.compute[i]) PB2_CUDA(cudaStreamCreateWithFlags(&p.compute[i], cudaStreamNonBlocking));
     if (!p.d2h) PB2_CUDA(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
     for (int i = 0; i < kStages; ++i) {
         Stage& st = p.slot[i];
@@ -320,10 +321,11 @@ static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t ou
         if (c >= (uint64_t)kStages) PB2_CUDA(cudaStreamWaitEvent(p.h2d, st.drained, 0));       // slot's previous chunk fully out
         PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, p.h2d));
         PB2_CUDA(cudaEventRecord(st.in_ready, p.h2d));
-        PB2_CUDA(cudaStreamWaitEvent(p.compute, st.in_ready, 0));
-        launch(st, m, p.compute);
+        cudaStream_t cs = p.compute[c & 1];
+        PB2_CUDA(cudaStreamWaitEvent(cs, st.in_ready, 0));
+        launch(st, m, cs);
         PB2_CUDA(cudaGetLastError());
-        PB2_CUDA(cudaEventRecord(st.done, p.compute));
+        PB2_CUDA(cudaEventRecord(st.done, cs));
         PB2_CUDA(cudaStreamWaitEvent(p.d2h, st.done, 0));
         PB2_CUDA(cudaMemcpyAsync((char*)out + off * out_bytes, st.d_out, m * out_bytes, cudaMemcpyDeviceToHost, p.d2h));
         if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, p.d2h));

@@ -38,7 +38,8 @@ struct Stage {                          // one ring slot
 };
 constexpr int kStages = 4;
 struct Pipe {
-    cudaStream_t h2d = nullptr, compute = nullptr, d2h = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaStream_t compute[2] = {nullptr, nullptr};   // alternate chunks: the tail of one chunk's kernel overlaps the next one
     Stage slot[kStages];
 };
 

@@ -5,6 +5,10 @@
 #include <cmath>
 
 #include "api_internal.hpp"
+
+#include <cstdio>
+#include <string>
+#include <vector>
 #include "wavefront.cuh"
 
 namespace pb2 {
@@ -295,6 +299,41 @@ int pb2_film_resolve_rgb(pb2_film* f, float scale, float* rgb) {
     if (e == cudaSuccess) e = cudaMemcpy(rgb, d, npix * 12, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return cuda_fail(e, "film resolve", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_film_write_image(pb2_film* f, const char* filename, float scale) {
+    if (!f || !filename) return set_error(PB2_ERR_INVALID, "null argument");
+    const std::string name(filename);
+    const size_t dot = name.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : name.substr(dot);
+    if (ext != ".pfm" && ext != ".ppm") return set_error(PB2_ERR_INVALID, "unsupported image extension '%s' (.pfm or .ppm)", ext.c_str());
+    const int w = f->desc.res_x, h = f->desc.res_y;
+    std::vector<float> rgb((size_t)w * h * 3);
+    int rc = pb2_film_resolve_rgb(f, scale, rgb.data());
+    if (rc != PB2_OK) return rc;
+    FILE* fp = fopen(filename, "wb");
+    if (!fp) return set_error(PB2_ERR_INVALID, "cannot open '%s' for writing", filename);
+    bool ok = true;
+    if (ext == ".pfm") {
+        ok = fprintf(fp, "PF\n%d %d\n-1.0\n", w, h) > 0;
+        for (int y = h - 1; y >= 0 && ok; --y) ok = fwrite(rgb.data() + (size_t)y * w * 3, sizeof(float), (size_t)w * 3, fp) == (size_t)w * 3;
+    } else {
+        ok = fprintf(fp, "P6\n%d %d\n255\n", w, h) > 0;
+        std::vector<unsigned char> row((size_t)w * 3);
+        for (int y = 0; y < h && ok; ++y) {
+            for (int i = 0; i < w * 3; ++i) {
+                const float v = rgb[(size_t)y * w * 3 + i];
+                const float g = v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+                float b = 255.0f * g + 0.5f;
+                b = b < 0.0f ? 0.0f : (b > 255.0f ? 255.0f : b);
+                row[i] = (unsigned char)b;
+            }
+            ok = fwrite(row.data(), 1, row.size(), fp) == row.size();
+        }
+    }
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) return set_error(PB2_ERR_INVALID, "short write to '%s'", filename);
     return PB2_OK;
 }
 

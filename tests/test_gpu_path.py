@@ -185,3 +185,32 @@ def test_render_argument_errors(gpu, OP, scenes):
     with pytest.raises(gpu.Pb2Error) as e:
         gpu.PathIntegrator(bare, cam, spp=4).render(gpu.Film((32, 32)))
     assert "without materials" in str(e.value)
+
+
+def test_write_image_pfm_and_ppm(gpu, OP, scenes, tmp_path):
+    """Film::write_image through to a file: the PFM holds exactly resolve_rgb() (rows bottom-to-top), the PPM its sRGB bytes."""
+    sc = scenes.scene_c2()
+    cam = dict(scenes.C2_CAMERA, res=(48, 32))
+    kw = dict(max_depth=3, rr_threshold=1.0, light_strategy="uniform", spp=2)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    rgb = film.resolve_rgb()
+    pfm, ppm = str(tmp_path / "a.pfm"), str(tmp_path / "a.ppm")
+    film.write_image(pfm)
+    film.write_image(ppm)
+    raw = open(pfm, "rb").read()
+    head = b"PF\n48 32\n-1.0\n"
+    assert raw.startswith(head)
+    data = np.frombuffer(raw[len(head):], dtype="<f4").reshape(32, 48, 3)[::-1]
+    assert np.array_equal(bits(data), bits(rgb))
+    raw = open(ppm, "rb").read()
+    head = b"P6\n48 32\n255\n"
+    assert raw.startswith(head)
+    px = np.frombuffer(raw[len(head):], dtype=np.uint8).reshape(32, 48, 3)
+    v = rgb.astype(np.float32)
+    g = np.where(v <= 0.0031308, 12.92 * v, 1.055 * np.power(np.maximum(v, 0), 1 / 2.4) - 0.055)
+    want = np.clip(255.0 * g + 0.5, 0, 255).astype(np.uint8)
+    assert np.abs(px.astype(int) - want.astype(int)).max() <= 1
+    with pytest.raises(gpu.Pb2Error):
+        film.write_image(str(tmp_path / "a.exr"))
