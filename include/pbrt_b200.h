@@ -127,11 +127,16 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
                      const pb2_light* lights, uint32_t n_lights, pb2_scene** out);
 int pb2_scene_destroy(pb2_scene* scene);
 /* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
- * node layout + 48-byte triangles, upload to the current device.  split_method: 0 = SAH (only one built). */
+ * node layout + 48-byte triangles, upload to the current device.  split_method (bvh.rs:199-204): 0 = SplitMethod::SAH,
+ * built on the host; 1 = SplitMethod::HLBVH (bvh.rs:475-772), built on the GPU (Morton codes, radix sort, one LBVH treelet
+ * per 12-bit Morton prefix, SAH over the treelet roots).  Middle / EqualCounts are not built. */
 int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_method);
 /* Host half only (no device needed): the flattened array can then be inspected with pb2_bvh_info / pb2_bvh_export. */
 int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_method);
 /* bvh.rs:819-826 BVHAccel::world_bound -> {min.xyz, max.xyz} */
+/* Stage times of the last HLBVH build in ms: bounds + Morton codes, sort, treelets, upper SAH (host), flatten + download,
+ * repack to the device layout (host).  All zero after a SAH build. */
+int pb2_bvh_build_stats(const pb2_scene* scene, double ms[6]);
 int pb2_world_bound(const pb2_scene* scene, float out[6]);
 /* Parity hooks: the flattened LinearBVHNode array (bvh.rs:129-135 as 32-byte nodes {bounds[6], offset u32,
  * n_prims u16, axis u8, pad}) and the ordered primitive list. */

@@ -38,6 +38,8 @@ def lib():
         L.orc_slab_widen.restype = C.c_float
         L.orc_bvh_build.restype = C.c_void_p
         L.orc_bvh_build.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
+        L.orc_bvh_build2.restype = C.c_void_p
+        L.orc_bvh_build2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.orc_bvh_free.argtypes = [C.c_void_p]
         for f in ("orc_bvh_num_nodes", "orc_bvh_num_prims"):
             getattr(L, f).restype = C.c_uint64
@@ -133,16 +135,16 @@ def triangle_test(tri9, ray8):
 
 
 class BVHAccel:
-    """Oracle restatement of src/accelerators/bvh.rs BVHAccel (SAH)."""
+    """Oracle restatement of src/accelerators/bvh.rs BVHAccel (split_method 0 = SAH, 1 = HLBVH)."""
 
-    def __init__(self, verts, idx, max_prims_in_node=4, _handle=None):
+    def __init__(self, verts, idx, max_prims_in_node=4, _handle=None, split_method=0):
         self._own = _handle is None
         if _handle is not None:
             self.h = _handle
             return
         self.verts = _f32(verts).reshape(-1, 3)
         self.idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
-        self.h = lib().orc_bvh_build(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), max_prims_in_node)
+        self.h = lib().orc_bvh_build2(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), max_prims_in_node, split_method)
 
     def __del__(self):
         if getattr(self, "h", None) and self._own:

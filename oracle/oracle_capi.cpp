@@ -54,6 +54,12 @@ void* orc_bvh_build(const float* verts, uint64_t nv, const uint32_t* idx, uint64
     b->build(verts, nv, idx, nt, max_prims_in_node);
     return b;
 }
+// split_method: 0 = SplitMethod::SAH, 1 = SplitMethod::HLBVH (bvh.rs:199-204)
+void* orc_bvh_build2(const float* verts, uint64_t nv, const uint32_t* idx, uint64_t nt, int max_prims_in_node, int split_method) {
+    BVHAccel* b = new BVHAccel();
+    b->build(verts, nv, idx, nt, max_prims_in_node, split_method);
+    return b;
+}
 void orc_bvh_free(void* h) { delete (BVHAccel*)h; }
 uint64_t orc_bvh_num_nodes(void* h) { return ((BVHAccel*)h)->nodes.size(); }
 uint64_t orc_bvh_num_prims(void* h) { return ((BVHAccel*)h)->ordered_prims.size(); }

@@ -280,7 +280,7 @@ public:
     }
 
     // bvh.rs:216-271
-    void build(const Float* v, size_t nv, const uint32_t* idx, size_t nt, int max_prims) {
+    void build(const Float* v, size_t nv, const uint32_t* idx, size_t nt, int max_prims, int split_method = 0) {
         verts.resize(nv);
         for (size_t i = 0; i < nv; ++i) verts[i] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
         indices.assign(idx, idx + 3 * nt);
@@ -296,7 +296,13 @@ public:
         build_nodes_.clear();
         build_nodes_.reserve(2 * nt);
         ordered_prims.reserve(nt);
-        int root = recursive_build(info, 0, nt);
+        int root;
+        if (split_method == 1) {                              // SplitMethod::HLBVH (:239-243)
+            ordered_prims.resize(nt);
+            root = hlbvh_build(info);
+        } else {
+            root = recursive_build(info, 0, nt);
+        }
         nodes.resize(build_nodes_.size());
         uint32_t offset = 0;
         max_depth_seen = 0;
@@ -485,6 +491,181 @@ private:
         int c0 = recursive_build(info, start, mid);
         int c1 = recursive_build(info, mid, end);
         BuildNode& n = build_nodes_[index];                   // :53-92 init_interior
+        n.bounds = bunion(build_nodes_[c0].bounds, build_nodes_[c1].bounds);
+        n.children[0] = c0;
+        n.children[1] = c1;
+        n.split_axis = dim;
+        n.n_primitives = 0;
+        return index;
+    }
+
+    // ---- SplitMethod::HLBVH: bvh.rs:137-197 (Morton codes, radix sort), :475-568 hlbvh_build, :570-676 emit_lbvh,
+    // :678-772 build_upper_sah.  The Rust port does not run as written (H1-H6 below); this follows pbrt-v3
+    // (accelerators/bvh.cpp HLBVHBuild / emitLBVH / buildUpperSAH), which the reference declares itself a port of:
+    //   H1 :482-485 the centroid bound discards Bounds3::union's result          -> FIX (accumulate)
+    //   H2 :508     `start` is never advanced after a treelet is emitted          -> FIX (start = end)
+    //   H3 :595     leaves are written into an empty ordered_prims Vec            -> FIX (sized up front)
+    //   H4 :723-731,:755-763  `n_buckets * (x as usize)` casts before multiplying -> FIX ((n_buckets * x) as usize)
+    //   H5 :752     partitions [start, end]                                       -> FIX ([start, end))
+    //   H6 :765     keeps b < split bucket                                        -> FIX (b <= split bucket, pbrt-v3)
+    //   H7 treelets are emitted sequentially in Morton order, so a leaf's first_prim_offset is its position in the sorted
+    //      array (pbrt-v3 hands offsets out with an atomic; any order is a valid run of it)
+    //   H8 pbrt-v3 CHECKs that the upper-level centroid extent is non-zero and that the partition is proper; here a
+    //      zero extent or an improper partition splits the range in the middle instead of aborting
+    struct MortonPrimitive { uint32_t primitive_index, morton_code; };
+    static uint32_t left_shift3(uint32_t x) {                 // :138-152
+        if (x == (1u << 10)) x -= 1;
+        x = (x | (x << 16)) & 0b00000011000000000000000011111111u;
+        x = (x | (x << 8)) & 0b00000011000000001111000000001111u;
+        x = (x | (x << 4)) & 0b00000011000011000011000011000011u;
+        x = (x | (x << 2)) & 0b00001001001001001001001001001001u;
+        return x;
+    }
+    static uint32_t f2u_sat(Float v) {                        // Rust `as u32`: NaN -> 0, saturating
+        if (!(v > 0.0f)) return 0u;
+        if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+        return (uint32_t)v;
+    }
+    static uint32_t encode_morton3(V3 v) {                    // :154-157
+        return (left_shift3(f2u_sat(v.z)) << 2) | (left_shift3(f2u_sat(v.y)) << 1) | left_shift3(f2u_sat(v.x));
+    }
+    static void radix_sort(std::vector<MortonPrimitive>& v) { // :159-196
+        const int bits_per_pass = 6, n_bits = 30, n_passes = n_bits / bits_per_pass;
+        std::vector<MortonPrimitive> temp(v.size());
+        for (int pass = 0; pass < n_passes; ++pass) {
+            const int low_bit = pass * bits_per_pass;
+            std::vector<MortonPrimitive>& in = (pass & 1) ? temp : v;
+            std::vector<MortonPrimitive>& out = (pass & 1) ? v : temp;
+            const int n_buckets = 1 << bits_per_pass;
+            const uint32_t bit_mask = (1u << bits_per_pass) - 1u;
+            size_t bucket_count[64] = {0}, out_index[64];
+            for (const MortonPrimitive& mp : in) bucket_count[(mp.morton_code >> low_bit) & bit_mask]++;
+            out_index[0] = 0;
+            for (int i = 1; i < n_buckets; ++i) out_index[i] = out_index[i - 1] + bucket_count[i - 1];
+            for (const MortonPrimitive& mp : in) out[out_index[(mp.morton_code >> low_bit) & bit_mask]++] = mp;
+        }
+        if (n_passes & 1) std::swap(v, temp);
+    }
+
+    int hlbvh_build(const std::vector<BVHPrimitiveInfo>& info) {
+        Bounds3 bounds;
+        for (const BVHPrimitiveInfo& pi : info) bounds = bunion(bounds, pi.centroid);                            // H1
+        std::vector<MortonPrimitive> morton(info.size());
+        for (size_t i = 0; i < info.size(); ++i) {
+            const int morton_bits = 10, morton_scale = 1 << morton_bits;
+            const V3 centroid_offset = bounds.offset(info[i].centroid);
+            morton[i].primitive_index = info[i].primitive_number;
+            morton[i].morton_code = encode_morton3(centroid_offset * (Float)morton_scale);
+        }
+        radix_sort(morton);
+        std::vector<int> roots;
+        size_t ordered_offset = 0;
+        for (size_t start = 0, end = 1; end <= morton.size(); ++end) {
+            const uint32_t mask = 0b00111111111111000000000000000000u;
+            if (end == morton.size() || (morton[start].morton_code & mask) != (morton[end].morton_code & mask)) {
+                const int first_bit_index = 29 - 12;
+                roots.push_back(emit_lbvh(info, morton.data() + start, end - start, &ordered_offset, first_bit_index));
+                start = end;                                                                                     // H2
+            }
+        }
+        return build_upper_sah(roots, 0, roots.size());
+    }
+
+    int emit_lbvh(const std::vector<BVHPrimitiveInfo>& info, const MortonPrimitive* mp, size_t n_primitives, size_t* ordered_offset,
+                  int bit_index) {
+        if (bit_index == -1 || n_primitives < (size_t)max_prims_in_node) {                                       // :583
+            const int index = (int)build_nodes_.size();
+            build_nodes_.emplace_back();
+            Bounds3 bounds;
+            const size_t first = *ordered_offset;
+            *ordered_offset += n_primitives;                                                                     // H7
+            for (size_t i = 0; i < n_primitives; ++i) {
+                ordered_prims[first + i] = mp[i].primitive_index;                                                // H3
+                bounds = bunion(bounds, info[mp[i].primitive_index].bounds);
+            }
+            BuildNode& n = build_nodes_[index];
+            n.first_prim_offset = (uint32_t)first;
+            n.n_primitives = (uint32_t)n_primitives;
+            n.bounds = bounds;
+            return index;
+        }
+        const uint32_t mask = 1u << bit_index;
+        if ((mp[0].morton_code & mask) == (mp[n_primitives - 1].morton_code & mask))                              // :608-625
+            return emit_lbvh(info, mp, n_primitives, ordered_offset, bit_index - 1);
+        size_t search_start = 0, search_end = n_primitives - 1;
+        while (search_start + 1 != search_end) {                                                                 // :627-638
+            const size_t mid = (search_start + search_end) / 2;
+            if ((mp[search_start].morton_code & mask) == (mp[mid].morton_code & mask)) search_start = mid;
+            else search_end = mid;
+        }
+        const size_t split_offset = search_end;
+        const int index = (int)build_nodes_.size();
+        build_nodes_.emplace_back();
+        const int c0 = emit_lbvh(info, mp, split_offset, ordered_offset, bit_index - 1);
+        const int c1 = emit_lbvh(info, mp + split_offset, n_primitives - split_offset, ordered_offset, bit_index - 1);
+        BuildNode& n = build_nodes_[index];
+        n.bounds = bunion(build_nodes_[c0].bounds, build_nodes_[c1].bounds);
+        n.children[0] = c0;
+        n.children[1] = c1;
+        n.split_axis = bit_index % 3;                                                                            // :671
+        n.n_primitives = 0;
+        return index;
+    }
+
+    int build_upper_sah(std::vector<int>& roots, size_t start, size_t end) {
+        const size_t n_nodes = end - start;
+        if (n_nodes == 1) return roots[start];
+        const int index = (int)build_nodes_.size();
+        build_nodes_.emplace_back();
+        Bounds3 bounds, centroid_bounds;
+        for (size_t i = start; i < end; ++i) bounds = bunion(bounds, build_nodes_[roots[i]].bounds);
+        for (size_t i = start; i < end; ++i) {
+            const Bounds3& b = build_nodes_[roots[i]].bounds;
+            centroid_bounds = bunion(centroid_bounds, (b.mn + b.mx) * 0.5f);                                     // :703
+        }
+        const int dim = centroid_bounds.maximum_extent();
+        size_t mid = (start + end) / 2;
+        if (centroid_bounds.mx[dim] != centroid_bounds.mn[dim]) {                                                // H8
+            constexpr int n_buckets = 12;
+            struct Bucket { int count = 0; Bounds3 bounds; } buckets[n_buckets];
+            auto bucket_of = [&](int root) {
+                const Bounds3& nb = build_nodes_[root].bounds;
+                const Float centroid = (nb.mn[dim] + nb.mx[dim]) * 0.5f;
+                int b = (int)((Float)n_buckets * ((centroid - centroid_bounds.mn[dim]) / (centroid_bounds.mx[dim] - centroid_bounds.mn[dim])));   // H4
+                if (b == n_buckets) b = n_buckets - 1;
+                return b;
+            };
+            for (size_t i = start; i < end; ++i) {
+                const int b = bucket_of(roots[i]);
+                buckets[b].count++;
+                buckets[b].bounds = bunion(buckets[b].bounds, build_nodes_[roots[i]].bounds);
+            }
+            Float cost[n_buckets - 1];
+            for (int i = 0; i < n_buckets - 1; ++i) {
+                Bounds3 b0, b1;
+                int count0 = 0, count1 = 0;
+                for (int j = 0; j <= i; ++j) { b0 = bunion(b0, buckets[j].bounds); count0 += buckets[j].count; }
+                for (int j = i + 1; j < n_buckets; ++j) { b1 = bunion(b1, buckets[j].bounds); count1 += buckets[j].count; }
+                cost[i] = 0.125f + ((Float)count0 * b0.surface_area() + (Float)count1 * b1.surface_area()) / bounds.surface_area();   // :736
+            }
+            Float min_cost = std::numeric_limits<Float>::max();
+            int min_cost_split_bucket = 0;
+            for (int i = 0; i < n_buckets - 1; ++i)
+                if (cost[i] < min_cost) { min_cost = cost[i]; min_cost_split_bucket = i; }
+            size_t lo = start, hi = end;                                                                         // partition_in_place, H5 H6
+            for (;;) {
+                while (lo < hi && bucket_of(roots[lo]) <= min_cost_split_bucket) ++lo;
+                if (lo == hi) break;
+                do { --hi; } while (lo < hi && !(bucket_of(roots[hi]) <= min_cost_split_bucket));
+                if (lo == hi) break;
+                std::swap(roots[lo], roots[hi]);
+                ++lo;
+            }
+            if (lo > start && lo < end) mid = lo;                                                                // H8
+        }
+        const int c0 = build_upper_sah(roots, start, mid);
+        const int c1 = build_upper_sah(roots, mid, end);
+        BuildNode& n = build_nodes_[index];
         n.bounds = bunion(build_nodes_[c0].bounds, build_nodes_[c1].bounds);
         n.children[0] = c0;
         n.children[1] = c1;

@@ -125,7 +125,7 @@ def lib():
         "pb2_set_trace_tuning": [i32, i32, i32, i32],
         "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
-        "pb2_bvh_export": [vp, vp, vp],
+        "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
         "pb2_intersect_device": [vp, vp, u64, vp, vp, vp], "pb2_intersect_p_device": [vp, vp, u64, vp, vp],
         "pb2_camera_generate_rays": [vp, vp, u64, vp], "pb2_camera_primary_rays_device": [vp, vp, vp],
@@ -255,6 +255,12 @@ class BVHAccel:
         out = np.empty(6, dtype=np.float32)
         check(lib().pb2_world_bound(self.h, _p(out)))
         return out
+
+    def build_stats(self):
+        """HLBVH stage times in ms: bounds + Morton, sort, treelets, upper SAH (host), flatten + download, repack (host)."""
+        ms = (C.c_double * 6)()
+        check(lib().pb2_bvh_build_stats(self.h, ms))
+        return list(ms)
 
     def info(self):
         n_nodes, n_prims, depth = C.c_uint64(), C.c_uint64(), C.c_int()

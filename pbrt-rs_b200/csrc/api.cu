@@ -176,12 +176,21 @@ int pb2_scene_destroy(pb2_scene* scene) {
 }
 
 static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_method) {
-    if (split_method != 0) return set_error(PB2_ERR_INVALID, "only SplitMethod::SAH (0) is built");
+    if (split_method != 0 && split_method != 1)
+        return set_error(PB2_ERR_INVALID, "split_method %d: SplitMethod::SAH (0, host build) and ::HLBVH (1, GPU build) are built", split_method);
     if (max_prims_in_node < 1) return set_error(PB2_ERR_INVALID, "max_prims_in_node must be >= 1");
     scene->built = false;
     scene->built_host = false;
     const uint64_t n_tris = scene->indices.size() / 3;
-    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
+    for (double& v : scene->build_ms) v = 0.0;
+    if (split_method == 1) {
+        char msg[256] = "";
+        if (build_hlbvh_gpu(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, &scene->bvh, msg,
+                            (int)sizeof msg, scene->build_ms) != 0)
+            return set_error(PB2_ERR_CUDA, "%s", msg);
+    } else {
+        build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
+    }
     if (scene->bvh.max_depth > kStackDepth)
         return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
     scene->built_host = true;
@@ -238,6 +247,12 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     std::vector<QuadNode>().swap(b.quads);
     std::vector<PackedTri>().swap(b.tris);
     scene->built = true;
+    return PB2_OK;
+}
+
+int pb2_bvh_build_stats(const pb2_scene* scene, double ms[6]) {
+    if (!scene || !ms) return set_error(PB2_ERR_INVALID, "null argument");
+    for (int k = 0; k < 6; ++k) ms[k] = scene->build_ms[k];
     return PB2_OK;
 }
 

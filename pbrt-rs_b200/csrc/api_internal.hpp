@@ -55,6 +55,7 @@ struct pb2_scene {
     std::vector<pb2_material> materials;
     std::vector<pb2_light> lights;
     pb2::HostBVH bvh;
+    double build_ms[6] = {0, 0, 0, 0, 0, 0};   // HLBVH stage times (bvh_build.hpp: build_hlbvh_gpu)
     bool built_host = false;   // LinearNode array + ordered prims valid
     bool built = false;        // device copies valid
     int device = 0;

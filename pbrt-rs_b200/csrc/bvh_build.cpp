@@ -351,8 +351,11 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
     }
     Builder b(refs, max_prims, threads);
     b.run(out);
+    repack_device_layout(verts, indices, n_tris, out);
+}
 
-    // ---- repack into the device layout ----
+// LinearNode array + ordered_prims -> PairNode / QuadNode / PackedTri (shared by the SAH and HLBVH builders).
+void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out) {
     const size_t n_nodes = out->nodes.size();
     std::vector<uint32_t> pair_of(n_nodes, 0);
     uint32_t n_pairs = 0;

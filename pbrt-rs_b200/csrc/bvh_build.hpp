@@ -83,4 +83,13 @@ struct HostBVH {
 void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
                    int max_prims_in_node, int threads, HostBVH* out);
 
+// Fills pairs / quads / tris / root refs / root bounds of `out` from its nodes + ordered_prims.
+void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out);
+
+// SplitMethod::HLBVH (bvh.rs:475-772) on the GPU: Morton codes, radix sort, one LBVH treelet per 12-bit Morton prefix,
+// SAH over the treelet roots, flatten — bvh_hlbvh.cu.  Returns 0, or -1 with a message in *err.  timing_ms (optional, 6
+// doubles): bounds+morton, sort, treelets+emit, upper SAH (host), flatten+download, repack (host).
+int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris, int max_prims_in_node,
+                    HostBVH* out, char* err, int err_len, double* timing_ms);
+
 }  // namespace pb2

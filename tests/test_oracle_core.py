@@ -155,3 +155,30 @@ def test_empty_and_single_triangle(orc):
     rays = np.array([orc.make_ray([0.2, 0.2, -1], [0, 0, 1]), orc.make_ray([2, 2, -1], [0, 0, 1])])
     h = one.intersect(rays)[0]
     assert h["prim_id"].tolist() == [0, 0xFFFFFFFF] and h["t"][0] == 1.0 and np.isinf(h["t"][1])
+
+
+@pytest.mark.parametrize("max_prims", [1, 4, 16])
+def test_hlbvh_oracle_closest_hit_equals_brute_force_and_sah(orc, scenes, max_prims):
+    """SplitMethod::HLBVH restatement (bvh.rs:475-772, pbrt-v3 semantics): every triangle lands in exactly one leaf, the walk
+    over the HLBVH tree finds the brute-force hit, and ids / t bits equal the SAH tree's (different topology, same answer)."""
+    v, i = scenes.random_soup(4000, seed=21 + max_prims)
+    hl = orc.BVHAccel(v, i, max_prims, split_method=1)
+    sah = orc.BVHAccel(v, i, max_prims)
+    assert sorted(hl.ordered_prims().tolist()) == list(range(len(i)))
+    nodes = hl.nodes()
+    leaves = nodes[nodes["n_prims"] > 0]
+    assert int(leaves["n_prims"].sum()) == len(i)
+    assert (leaves["n_prims"] < max(max_prims, 2)).all() or max_prims == 1      # emit_lbvh: n < max_prims_in_node makes a leaf
+    rng = np.random.default_rng(5)
+    rays = np.zeros((20000, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-12, 12, (20000, 3))
+    d = rng.normal(size=(20000, 3))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3] = np.inf
+    h, _ = hl.intersect(rays)[:2] if False else (hl.intersect(rays)[0], None)
+    hs = sah.intersect(rays)[0]
+    hb = hl.brute_force(rays)
+    assert (h["prim_id"] != 0xFFFFFFFF).sum() > 500
+    assert np.array_equal(h["prim_id"], hb["prim_id"]) and np.array_equal(h["t"].view(np.uint32), hb["t"].view(np.uint32))
+    assert np.array_equal(h["t"].view(np.uint32), hs["t"].view(np.uint32))
+    assert np.array_equal(hl.intersect_p(rays)[0], (h["prim_id"] != 0xFFFFFFFF).astype(np.uint8))
