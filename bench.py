@@ -456,6 +456,36 @@ def main():
     path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world) if world > 1 else None
     path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0])
 
+    # ---- BVH build: SplitMethod::HLBVH built on the GPU next to the host SAH build, and what the C3
+    # ray sets cost on that tree (same rays, same hits: tests/ compare ids and t bits)
+    bvh_build = None
+    if rank == 0:
+        t0 = time.time()
+        accel_h = pb2.BVHAccel(verts, idx, max_prims_in_node=4, split_method=1)
+        t_hl = time.time() - t0
+        stages = accel_h.build_stats()
+
+        def hl_step():
+            accel_h.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), d_b0.data_ptr(), stream)
+            accel_h.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), stream)
+            accel_h.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
+        prim_before = d_hits.view(torch.int32)[::4].clone()
+        hl_step()
+        flush.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        hl_step()
+        ev[1].record()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(prim_before, d_hits.view(torch.int32)[::4]))
+        hn, _, hdepth = accel_h.info()
+        bvh_build = {"sah_host_build_upload_s": t_build, "hlbvh_gpu_build_upload_s": t_hl,
+                     "hlbvh_stage_ms": dict(zip(["bounds_morton", "sort", "treelets", "upper_sah_host", "flatten_download", "repack_host"],
+                                                [round(x, 3) for x in stages])),
+                     "hlbvh_nodes": hn, "hlbvh_depth": hdepth, "hlbvh_c3_pass_mrays_s": 3 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e6,
+                     "hlbvh_primary_hit_ids_equal_sah": same}
+        del accel_h
+
     # ---- max over ranks ----
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -542,7 +572,7 @@ def main():
                     "link_bound_mrays_s": world * rays_per_step / (3 * n * 32 / (pcie["h2d_gbs"] * 1e9)) / 1e6},
             "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "path": path_c2, "path_c4": path_c4, "path_multi_gpu": path_c5,
+            "path": path_c2, "path_c4": path_c4, "path_multi_gpu": path_c5, "bvh_build": bvh_build,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

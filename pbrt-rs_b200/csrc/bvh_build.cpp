@@ -354,111 +354,113 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
     repack_device_layout(verts, indices, n_tris, out);
 }
 
-// LinearNode array + ordered_prims -> PairNode / QuadNode / PackedTri (shared by the SAH and HLBVH builders).
+// Runs fn(begin, end) over [0, n) on the host's hardware threads.
+template <class F>
+static void parallel_ranges(size_t n, F&& fn) {
+    const size_t T = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), n / 65536 + 1));
+    if (T == 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t step = (n + T - 1) / T;
+    for (size_t t = 0; t < T; ++t) {
+        const size_t lo = t * step, hi = std::min(n, lo + step);
+        if (lo < hi) pool.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// LinearNode array + ordered_prims -> PairNode / QuadNode / PackedTri (shared by the SAH and HLBVH builders).  The node
+// array is in depth-first order, so the numbering of the device records follows from two prefix counts over it (interior
+// nodes -> pair index; interior nodes at even depth -> quad index, depth-first like the pairs) and every record can then
+// be filled independently of the others.
 void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out) {
     const size_t n_nodes = out->nodes.size();
-    std::vector<uint32_t> pair_of(n_nodes, 0);
-    uint32_t n_pairs = 0;
-    for (size_t i = 0; i < n_nodes; ++i)
-        if (out->nodes[i].n_prims == 0) pair_of[i] = n_pairs++;
+    const std::vector<LinearNode>& nodes = out->nodes;
+    std::vector<uint32_t> pair_of(n_nodes, 0), quad_of(n_nodes, 0);
+    std::vector<uint8_t> odd(n_nodes, 0);                               // depth parity (parents precede their children)
+    uint32_t n_pairs = 0, n_quads = 0;
+    for (size_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].n_prims != 0) continue;
+        pair_of[i] = n_pairs++;
+        if (!odd[i]) quad_of[i] = n_quads++;
+        odd[i + 1] = odd[nodes[i].offset] = (uint8_t)(odd[i] ^ 1);
+    }
     out->pairs.resize(n_pairs);
+    out->quads.resize(n_quads);
     auto ref_of = [&](uint32_t node) -> uint32_t {
-        const LinearNode& ln = out->nodes[node];
+        const LinearNode& ln = nodes[node];
         return ln.n_prims > 0 ? (kLeafBit | ln.offset) : pair_of[node];
     };
-    for (size_t i = 0; i < n_nodes; ++i) {
-        const LinearNode& ln = out->nodes[i];
-        if (ln.n_prims != 0) continue;
-        const LinearNode& L = out->nodes[i + 1];
-        const LinearNode& R = out->nodes[ln.offset];
-        PairNode& p = out->pairs[pair_of[i]];
-        p.a[0] = L.bmin[0]; p.a[1] = L.bmin[1]; p.a[2] = L.bmin[2]; p.a[3] = L.bmax[0];
-        p.b[0] = L.bmax[1]; p.b[1] = L.bmax[2]; p.b[2] = R.bmin[0]; p.b[3] = R.bmin[1];
-        p.c[0] = R.bmin[2]; p.c[1] = R.bmax[0]; p.c[2] = R.bmax[1]; p.c[3] = R.bmax[2];
-        p.left = ref_of((uint32_t)i + 1);
-        p.right = ref_of(ln.offset);
-        p.axis = ln.axis;
-        p.pad = 0;
-    }
-    out->root_ref = ref_of(0);
-
-    // ---- fold two levels per record (QuadNode), numbered depth-first like the pairs ----
-    out->quads.clear();
-    if (n_nodes && out->nodes[0].n_prims == 0) {
-        out->quads.reserve(n_pairs / 2 + 16);
-        struct Frame { uint32_t node, quad; int slot; };            // slot: next child slot of `quad` to resolve
-        auto new_quad = [&](uint32_t P) -> uint32_t {
-            const uint32_t q = (uint32_t)out->quads.size();
-            out->quads.emplace_back();
-            QuadNode& Q = out->quads.back();
-            const float inf = std::numeric_limits<float>::infinity();
+    parallel_ranges(n_nodes, [&](size_t lo, size_t hi) {
+        const float inf = std::numeric_limits<float>::infinity();
+        for (size_t i = lo; i < hi; ++i) {
+            const LinearNode& ln = nodes[i];
+            if (ln.n_prims != 0) continue;
+            const LinearNode& L = nodes[i + 1];
+            const LinearNode& R = nodes[ln.offset];
+            PairNode& p = out->pairs[pair_of[i]];
+            p.a[0] = L.bmin[0]; p.a[1] = L.bmin[1]; p.a[2] = L.bmin[2]; p.a[3] = L.bmax[0];
+            p.b[0] = L.bmax[1]; p.b[1] = L.bmax[2]; p.b[2] = R.bmin[0]; p.b[3] = R.bmin[1];
+            p.c[0] = R.bmin[2]; p.c[1] = R.bmax[0]; p.c[2] = R.bmax[1]; p.c[3] = R.bmax[2];
+            p.left = ref_of((uint32_t)i + 1);
+            p.right = ref_of(ln.offset);
+            p.axis = ln.axis;
+            p.pad = 0;
+            if (odd[i]) continue;
+            // two levels folded into one record (see QuadNode in bvh_build.hpp)
+            QuadNode& Q = out->quads[quad_of[i]];
             for (int k = 0; k < 4; ++k) {
                 Q.lox[k] = Q.loy[k] = Q.loz[k] = inf;
                 Q.hix[k] = Q.hiy[k] = Q.hiz[k] = -inf;
                 Q.ref[k] = kQuadEmpty;
+                Q.pad[k] = 0;
             }
-            Q.pad[0] = Q.pad[1] = Q.pad[2] = Q.pad[3] = 0;
-            const LinearNode& ln = out->nodes[P];
             uint32_t axes[3] = {ln.axis, 0u, 0u};
-            const uint32_t kids[2] = {P + 1, ln.offset};
+            const uint32_t kids[2] = {(uint32_t)i + 1, ln.offset};
             for (int g = 0; g < 2; ++g) {
-                const LinearNode& X = out->nodes[kids[g]];
+                const LinearNode& X = nodes[kids[g]];
                 uint32_t members[2];
                 int n_members;
                 if (X.n_prims > 0) { members[0] = kids[g]; n_members = 1; }
                 else { members[0] = kids[g] + 1; members[1] = X.offset; n_members = 2; axes[1 + g] = X.axis; }
                 for (int j = 0; j < n_members; ++j) {
-                    const LinearNode& Y = out->nodes[members[j]];
+                    const LinearNode& Y = nodes[members[j]];
                     const int k = 2 * g + j;
                     Q.lox[k] = Y.bmin[0]; Q.loy[k] = Y.bmin[1]; Q.loz[k] = Y.bmin[2];
                     Q.hix[k] = Y.bmax[0]; Q.hiy[k] = Y.bmax[1]; Q.hiz[k] = Y.bmax[2];
-                    // interior members are resolved by the caller loop (needs their quad index): park the node index
-                    Q.ref[k] = Y.n_prims > 0 ? (kLeafBit | Y.offset) : members[j];
+                    Q.ref[k] = Y.n_prims > 0 ? (kLeafBit | Y.offset) : quad_of[members[j]];
                 }
             }
-            Q.pad[0] = axes[0] | (axes[1] << 2) | (axes[2] << 4);      // applied to the references once they are final
-            return q;
-        };
-        std::vector<Frame> work;
-        work.push_back({0u, new_quad(0u), 0});
-        while (!work.empty()) {
-            Frame& f = work.back();
-            if (f.slot == 4) { work.pop_back(); continue; }
-            const int k = f.slot++;
-            const uint32_t r = out->quads[f.quad].ref[k];
-            if (r == kQuadEmpty || (r & kLeafBit)) continue;
-            const uint32_t fq = f.quad;                              // `f` dangles after push_back
-            const uint32_t child_quad = new_quad(r);
-            out->quads[fq].ref[k] = child_quad;
-            work.push_back({r, child_quad, 0});
+            for (int k = 0; k < 3; ++k) Q.ref[k] = (Q.ref[k] & kQuadRefMask) | (axes[k] << kQuadAxisShift);
         }
-        for (QuadNode& Q : out->quads) {                              // tag the (now final) references with the axes
-            const uint32_t ax = Q.pad[0];
-            Q.pad[0] = 0;
-            for (int k = 0; k < 3; ++k) Q.ref[k] = (Q.ref[k] & kQuadRefMask) | (((ax >> (2 * k)) & 3u) << kQuadAxisShift);
-        }
-        out->quad_root_ref = 0;
+    });
+    if (n_nodes) {
+        out->root_ref = ref_of(0);
+        out->quad_root_ref = nodes[0].n_prims == 0 ? 0u : out->root_ref;      // a single leaf has no record of either kind
+        for (int k = 0; k < 3; ++k) { out->root_bounds[k] = nodes[0].bmin[k]; out->root_bounds[3 + k] = nodes[0].bmax[k]; }
     } else {
-        out->quad_root_ref = out->root_ref;                          // empty tree or a single leaf
+        out->root_ref = out->quad_root_ref = 0;
     }
-    for (int k = 0; k < 3; ++k) { out->root_bounds[k] = out->nodes[0].bmin[k]; out->root_bounds[3 + k] = out->nodes[0].bmax[k]; }
 
     out->tris.resize(n_tris);
-    for (size_t i = 0; i < n_tris; ++i) {
-        const uint32_t t = out->ordered_prims[i];
-        PackedTri& pt = out->tris[i];
-        const float* p0 = verts + 3ull * indices[3ull * t];
-        const float* p1 = verts + 3ull * indices[3ull * t + 1];
-        const float* p2 = verts + 3ull * indices[3ull * t + 2];
-        for (int k = 0; k < 3; ++k) { pt.v0[k] = p0[k]; pt.v1[k] = p1[k]; pt.v2[k] = p2[k]; }
-        pt.prim_id = t;
-        pt.last = 0;
-        pt.pad = 0;
-    }
-    for (size_t i = 0; i < n_nodes; ++i) {
-        const LinearNode& ln = out->nodes[i];
-        if (ln.n_prims > 0) out->tris[(size_t)ln.offset + ln.n_prims - 1].last = 1;
-    }
+    parallel_ranges(n_tris, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const uint32_t t = out->ordered_prims[i];
+            PackedTri& pt = out->tris[i];
+            const float* p0 = verts + 3ull * indices[3ull * t];
+            const float* p1 = verts + 3ull * indices[3ull * t + 1];
+            const float* p2 = verts + 3ull * indices[3ull * t + 2];
+            for (int k = 0; k < 3; ++k) { pt.v0[k] = p0[k]; pt.v1[k] = p1[k]; pt.v2[k] = p2[k]; }
+            pt.prim_id = t;
+            pt.last = 0;
+            pt.pad = 0;
+        }
+    });
+    parallel_ranges(n_nodes, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const LinearNode& ln = nodes[i];
+            if (ln.n_prims > 0) out->tris[(size_t)ln.offset + ln.n_prims - 1].last = 1;
+        }
+    });
 }
 
 }  // namespace pb2
