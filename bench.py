@@ -480,7 +480,7 @@ def main():
         same = bool(torch.equal(prim_before, d_hits.view(torch.int32)[::4]))
         hn, _, hdepth = accel_h.info()
         bvh_build = {"sah_host_build_upload_s": t_build, "hlbvh_gpu_build_upload_s": t_hl,
-                     "hlbvh_stage_ms": dict(zip(["bounds_morton", "sort", "treelets", "upper_sah_host", "flatten_download", "repack_host"],
+                     "hlbvh_stage_ms": dict(zip(["upload_bounds_morton", "sort", "treelets", "upper_sah_host", "flatten", "device_repack"],
                                                 [round(x, 3) for x in stages])),
                      "hlbvh_nodes": hn, "hlbvh_depth": hdepth, "hlbvh_c3_pass_mrays_s": 3 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e6,
                      "hlbvh_primary_hit_ids_equal_sah": same}

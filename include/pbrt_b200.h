@@ -134,8 +134,8 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
 /* Host half only (no device needed): the flattened array can then be inspected with pb2_bvh_info / pb2_bvh_export. */
 int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_method);
 /* bvh.rs:819-826 BVHAccel::world_bound -> {min.xyz, max.xyz} */
-/* Stage times of the last HLBVH build in ms: bounds + Morton codes, sort, treelets, upper SAH (host), flatten + download,
- * repack to the device layout (host).  All zero after a SAH build. */
+/* Stage times of the last HLBVH build in ms: upload + bounds + Morton codes, sort, treelets, upper SAH (host, <= 4096
+ * treelet roots), flatten, repack into the traversal layout (device).  All zero after a SAH build. */
 int pb2_bvh_build_stats(const pb2_scene* scene, double ms[6]);
 int pb2_world_bound(const pb2_scene* scene, float out[6]);
 /* Parity hooks: the flattened LinearBVHNode array (bvh.rs:129-135 as 32-byte nodes {bounds[6], offset u32,

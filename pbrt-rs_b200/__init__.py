@@ -257,7 +257,7 @@ class BVHAccel:
         return out
 
     def build_stats(self):
-        """HLBVH stage times in ms: bounds + Morton, sort, treelets, upper SAH (host), flatten + download, repack (host)."""
+        """HLBVH stage times in ms: upload + bounds + Morton, sort, treelets, upper SAH (host), flatten, device-layout repack."""
         ms = (C.c_double * 6)()
         check(lib().pb2_bvh_build_stats(self.h, ms))
         return list(ms)

@@ -38,6 +38,9 @@ using namespace pb2;
 void pb2_scene::free_device() {
     if (d_pairs) cudaFree(d_pairs);
     if (d_quads) cudaFree(d_quads);
+    if (d_lin_nodes) cudaFree(d_lin_nodes);
+    if (d_lin_prims) cudaFree(d_lin_prims);
+    d_lin_nodes = d_lin_prims = nullptr;
     if (d_tris) cudaFree(d_tris);
     if (d_slot_of_prim) cudaFree(d_slot_of_prim);
     if (d_tri_material) cudaFree(d_tri_material);
@@ -175,24 +178,29 @@ int pb2_scene_destroy(pb2_scene* scene) {
     return PB2_OK;
 }
 
-static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_method) {
+static int check_build_args(int max_prims_in_node, int split_method) {
     if (split_method != 0 && split_method != 1)
         return set_error(PB2_ERR_INVALID, "split_method %d: SplitMethod::SAH (0, host build) and ::HLBVH (1, GPU build) are built", split_method);
     if (max_prims_in_node < 1) return set_error(PB2_ERR_INVALID, "max_prims_in_node must be >= 1");
+    return PB2_OK;
+}
+
+static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_method) {
+    int rc = check_build_args(max_prims_in_node, split_method);
+    if (rc) return rc;
+    if (split_method == 1) return set_error(PB2_ERR_INVALID, "SplitMethod::HLBVH is built on the device: use pb2_scene_build_bvh");
     scene->built = false;
     scene->built_host = false;
     const uint64_t n_tris = scene->indices.size() / 3;
     for (double& v : scene->build_ms) v = 0.0;
-    if (split_method == 1) {
-        char msg[256] = "";
-        if (build_hlbvh_gpu(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, &scene->bvh, msg,
-                            (int)sizeof msg, scene->build_ms) != 0)
-            return set_error(PB2_ERR_CUDA, "%s", msg);
-    } else {
-        build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
-    }
+    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
     if (scene->bvh.max_depth > kStackDepth)
         return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
+    scene->n_nodes = scene->bvh.nodes.size();
+    scene->n_prims = scene->bvh.ordered_prims.size();
+    scene->tree_depth = scene->bvh.max_depth;
+    if (scene->n_nodes)
+        for (int k = 0; k < 3; ++k) { scene->root_bounds[k] = scene->bvh.nodes[0].bmin[k]; scene->root_bounds[3 + k] = scene->bvh.nodes[0].bmax[k]; }
     scene->built_host = true;
     return PB2_OK;
 }
@@ -203,49 +211,96 @@ int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_
     return build_host_locked(scene, max_prims_in_node, split_method);
 }
 
+// SplitMethod::HLBVH: everything up to and including the traversal layout is produced on the device (bvh_hlbvh.cu).
+static int build_device_locked(pb2_scene* scene, int max_prims_in_node, SceneView* v) {
+    scene->built = false;
+    scene->built_host = false;
+    for (double& x : scene->build_ms) x = 0.0;
+    scene->bvh = HostBVH();
+    const uint64_t n_tris = scene->indices.size() / 3;
+    DeviceBVH dv;
+    char msg[256] = "";
+    const int brc = build_hlbvh_gpu(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, &dv, msg,
+                                    (int)sizeof msg, scene->build_ms);
+    scene->d_pairs = dv.d_pairs;
+    scene->d_quads = dv.d_quads;
+    scene->d_tris = dv.d_tris;
+    scene->d_slot_of_prim = dv.d_slot_of_prim;
+    scene->d_lin_nodes = dv.d_nodes;
+    scene->d_lin_prims = dv.d_ordered_prims;                           // (free_device() releases whatever was allocated)
+    if (brc != 0) return set_error(PB2_ERR_CUDA, "%s", msg);
+    if (dv.max_depth > kStackDepth)
+        return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", dv.max_depth);
+    scene->n_nodes = dv.n_nodes;
+    scene->n_prims = dv.n_tris;
+    scene->tree_depth = dv.max_depth;
+    for (int k = 0; k < 6; ++k) scene->root_bounds[k] = dv.root_bounds[k];
+    if (n_tris) {
+        launch_mark_degenerate(scene->d_tris, n_tris, 0);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaDeviceSynchronize());
+        v->quads = (const float4*)scene->d_quads;
+        v->quad_root_ref = dv.quad_root_ref;
+        v->pairs = (const float4*)scene->d_pairs;
+        v->tris = (const float4*)scene->d_tris;
+        v->slot_of_prim = (const uint32_t*)scene->d_slot_of_prim;
+        v->root_ref = dv.root_ref;
+        for (int k = 0; k < 3; ++k) { v->root_lo[k] = dv.root_bounds[k]; v->root_hi[k] = dv.root_bounds[3 + k]; }
+    }
+    scene->built_host = true;
+    return PB2_OK;
+}
+
 int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_method) {
     if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
     std::lock_guard<std::mutex> lock(scene->mu);
+    int rc = check_build_args(max_prims_in_node, split_method);
+    if (rc) return rc;
     scene->free_device();
-    int rc = build_host_locked(scene, max_prims_in_node, split_method);
-    if (rc != PB2_OK) return rc;
     const uint64_t n_tris = scene->indices.size() / 3;
-    HostBVH& b = scene->bvh;
     PB2_CUDA(cudaGetDevice(&scene->device));
     SceneView v;
     memset(&v, 0, sizeof v);
     v.n_tris = (uint32_t)n_tris;
     PB2_CUDA(cudaMalloc(&scene->d_counters, pb2_scene::kCounters * sizeof(unsigned long long)));
     PB2_CUDA(cudaMemset(scene->d_counters, 0, pb2_scene::kCounters * sizeof(unsigned long long)));
-    if (n_tris) {
-        PB2_CUDA(cudaMalloc(&scene->d_pairs, std::max<size_t>(64, b.pairs.size() * sizeof(PairNode))));
-        PB2_CUDA(cudaMalloc(&scene->d_tris, b.tris.size() * sizeof(PackedTri)));
-        PB2_CUDA(cudaMalloc(&scene->d_slot_of_prim, n_tris * 4));
-        if (!b.pairs.empty()) PB2_CUDA(cudaMemcpy(scene->d_pairs, b.pairs.data(), b.pairs.size() * sizeof(PairNode), cudaMemcpyHostToDevice));
-        PB2_CUDA(cudaMalloc(&scene->d_quads, std::max<size_t>(128, b.quads.size() * sizeof(QuadNode))));
-        if (!b.quads.empty()) PB2_CUDA(cudaMemcpy(scene->d_quads, b.quads.data(), b.quads.size() * sizeof(QuadNode), cudaMemcpyHostToDevice));
-        v.quads = (const float4*)scene->d_quads;
-        v.quad_root_ref = b.quad_root_ref;
-        PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
-        launch_mark_degenerate(scene->d_tris, b.tris.size(), 0);
-        PB2_CUDA(cudaGetLastError());
-        PB2_CUDA(cudaDeviceSynchronize());
-        std::vector<uint32_t> slot(n_tris);
-        for (uint64_t i = 0; i < n_tris; ++i) slot[b.ordered_prims[i]] = (uint32_t)i;
-        PB2_CUDA(cudaMemcpy(scene->d_slot_of_prim, slot.data(), n_tris * 4, cudaMemcpyHostToDevice));
-        v.pairs = (const float4*)scene->d_pairs;
-        v.tris = (const float4*)scene->d_tris;
-        v.slot_of_prim = (const uint32_t*)scene->d_slot_of_prim;
-        v.root_ref = b.root_ref;
-        for (int k = 0; k < 3; ++k) { v.root_lo[k] = b.root_bounds[k]; v.root_hi[k] = b.root_bounds[3 + k]; }
+    if (split_method == 1) {
+        rc = build_device_locked(scene, max_prims_in_node, &v);
+        if (rc != PB2_OK) return rc;
+    } else {
+        rc = build_host_locked(scene, max_prims_in_node, split_method);
+        if (rc != PB2_OK) return rc;
+        HostBVH& b = scene->bvh;
+        if (n_tris) {
+            PB2_CUDA(cudaMalloc(&scene->d_pairs, std::max<size_t>(64, b.pairs.size() * sizeof(PairNode))));
+            PB2_CUDA(cudaMalloc(&scene->d_tris, b.tris.size() * sizeof(PackedTri)));
+            PB2_CUDA(cudaMalloc(&scene->d_slot_of_prim, n_tris * 4));
+            if (!b.pairs.empty()) PB2_CUDA(cudaMemcpy(scene->d_pairs, b.pairs.data(), b.pairs.size() * sizeof(PairNode), cudaMemcpyHostToDevice));
+            PB2_CUDA(cudaMalloc(&scene->d_quads, std::max<size_t>(128, b.quads.size() * sizeof(QuadNode))));
+            if (!b.quads.empty()) PB2_CUDA(cudaMemcpy(scene->d_quads, b.quads.data(), b.quads.size() * sizeof(QuadNode), cudaMemcpyHostToDevice));
+            v.quads = (const float4*)scene->d_quads;
+            v.quad_root_ref = b.quad_root_ref;
+            PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
+            launch_mark_degenerate(scene->d_tris, b.tris.size(), 0);
+            PB2_CUDA(cudaGetLastError());
+            PB2_CUDA(cudaDeviceSynchronize());
+            std::vector<uint32_t> slot(n_tris);
+            for (uint64_t i = 0; i < n_tris; ++i) slot[b.ordered_prims[i]] = (uint32_t)i;
+            PB2_CUDA(cudaMemcpy(scene->d_slot_of_prim, slot.data(), n_tris * 4, cudaMemcpyHostToDevice));
+            v.pairs = (const float4*)scene->d_pairs;
+            v.tris = (const float4*)scene->d_tris;
+            v.slot_of_prim = (const uint32_t*)scene->d_slot_of_prim;
+            v.root_ref = b.root_ref;
+            for (int k = 0; k < 3; ++k) { v.root_lo[k] = b.root_bounds[k]; v.root_hi[k] = b.root_bounds[3 + k]; }
+        }
+        // the device copies are authoritative from here on; drop the host-side device-layout mirrors
+        std::vector<PairNode>().swap(b.pairs);
+        std::vector<QuadNode>().swap(b.quads);
+        std::vector<PackedTri>().swap(b.tris);
     }
     scene->view = v;
     rc = upload_shading_tables(scene);
     if (rc != PB2_OK) return rc;
-    // the device copies are authoritative from here on; drop the host-side device-layout mirrors
-    std::vector<PairNode>().swap(b.pairs);
-    std::vector<QuadNode>().swap(b.quads);
-    std::vector<PackedTri>().swap(b.tris);
     scene->built = true;
     return PB2_OK;
 }
@@ -259,27 +314,32 @@ int pb2_bvh_build_stats(const pb2_scene* scene, double ms[6]) {
 int pb2_world_bound(const pb2_scene* scene, float out[6]) {
     if (!scene || !out) return set_error(PB2_ERR_INVALID, "null argument");
     if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
-    if (scene->bvh.nodes.empty()) {          // Bounds3f::default(): bvh.rs:825
+    if (scene->n_nodes == 0) {               // Bounds3f::default(): bvh.rs:825
         out[0] = out[1] = out[2] = 3.402823466e+38f;
         out[3] = out[4] = out[5] = -3.402823466e+38f;
         return PB2_OK;
     }
-    for (int k = 0; k < 3; ++k) { out[k] = scene->bvh.nodes[0].bmin[k]; out[3 + k] = scene->bvh.nodes[0].bmax[k]; }
+    for (int k = 0; k < 6; ++k) out[k] = scene->root_bounds[k];
     return PB2_OK;
 }
 
 int pb2_bvh_info(const pb2_scene* scene, uint64_t* n_nodes, uint64_t* n_prims, int* max_depth) {
     if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
     if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
-    if (n_nodes) *n_nodes = scene->bvh.nodes.size();
-    if (n_prims) *n_prims = scene->bvh.ordered_prims.size();
-    if (max_depth) *max_depth = scene->bvh.max_depth;
+    if (n_nodes) *n_nodes = scene->n_nodes;
+    if (n_prims) *n_prims = scene->n_prims;
+    if (max_depth) *max_depth = scene->tree_depth;
     return PB2_OK;
 }
 
 int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prims) {
     if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
     if (!scene->built_host) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (scene->d_lin_nodes) {                // device-built tree: the reference-layout arrays live on the device
+        if (nodes32) PB2_CUDA(cudaMemcpy(nodes32, scene->d_lin_nodes, scene->n_nodes * sizeof(LinearNode), cudaMemcpyDeviceToHost));
+        if (ordered_prims) PB2_CUDA(cudaMemcpy(ordered_prims, scene->d_lin_prims, scene->n_prims * 4, cudaMemcpyDeviceToHost));
+        return PB2_OK;
+    }
     if (nodes32) memcpy(nodes32, scene->bvh.nodes.data(), scene->bvh.nodes.size() * sizeof(LinearNode));
     if (ordered_prims) memcpy(ordered_prims, scene->bvh.ordered_prims.data(), scene->bvh.ordered_prims.size() * 4);
     return PB2_OK;

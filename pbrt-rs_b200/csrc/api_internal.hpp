@@ -61,6 +61,12 @@ struct pb2_scene {
     int device = 0;
     std::mutex mu;
     // device copies
+    // device-built trees (HLBVH): the flattened reference-layout nodes / primitive order stay on the device until exported
+    void* d_lin_nodes = nullptr;
+    void* d_lin_prims = nullptr;
+    uint64_t n_nodes = 0, n_prims = 0;
+    int tree_depth = 0;
+    float root_bounds[6] = {0, 0, 0, 0, 0, 0};
     void* d_pairs = nullptr;
     void* d_quads = nullptr;
     void* d_tris = nullptr;

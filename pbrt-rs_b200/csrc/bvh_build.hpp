@@ -86,10 +86,27 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
 // Fills pairs / quads / tris / root refs / root bounds of `out` from its nodes + ordered_prims.
 void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out);
 
+// What a device-side build hands over: the traversal layout already in device memory (ownership passes to the caller,
+// cudaFree each pointer) plus the flattened reference-layout nodes and primitive order, kept on the device and only
+// copied to the host when someone asks for them (pb2_bvh_export).
+struct DeviceBVH {
+    void* d_pairs = nullptr;          // PairNode[n_pairs]
+    void* d_quads = nullptr;          // QuadNode[n_quads]
+    void* d_tris = nullptr;           // PackedTri[n_tris]
+    void* d_slot_of_prim = nullptr;   // uint32[n_tris]
+    void* d_nodes = nullptr;          // LinearNode[n_nodes], depth-first (pad = depth parity)
+    void* d_ordered_prims = nullptr;  // uint32[n_tris]
+    uint64_t n_pairs = 0, n_quads = 0, n_nodes = 0, n_tris = 0;
+    uint32_t root_ref = 0, quad_root_ref = 0;
+    float root_bounds[6] = {0, 0, 0, 0, 0, 0};
+    int max_depth = 0;
+};
+
 // SplitMethod::HLBVH (bvh.rs:475-772) on the GPU: Morton codes, radix sort, one LBVH treelet per 12-bit Morton prefix,
-// SAH over the treelet roots, flatten — bvh_hlbvh.cu.  Returns 0, or -1 with a message in *err.  timing_ms (optional, 6
-// doubles): bounds+morton, sort, treelets+emit, upper SAH (host), flatten+download, repack (host).
+// SAH over the treelet roots, flatten, repack into the traversal layout — bvh_hlbvh.cu.  Nothing but the <= 4096 treelet
+// roots visits the host.  Returns 0, or -1 with a message in *err.  timing_ms (optional, 6 doubles): upload + bounds +
+// Morton, sort, treelets, upper SAH (host), flatten, device-layout repack.
 int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris, int max_prims_in_node,
-                    HostBVH* out, char* err, int err_len, double* timing_ms);
+                    DeviceBVH* out, char* err, int err_len, double* timing_ms);
 
 }  // namespace pb2

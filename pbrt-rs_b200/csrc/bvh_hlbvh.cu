@@ -20,6 +20,7 @@
 //
 // Every float operation is a separately rounded IEEE op in the reference's order (-fmad=false).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(64) k_emit_treelets(const uint32_t* __restrict
         if (it.patch >= 0) nodes[it.patch].offset = me;                 // second child of `patch`
         if (it.level > deepest) deepest = it.level;
         LinearNode& nd = nodes[me];
-        nd.pad = 0;
+        nd.pad = (uint8_t)((it.level - 1) & 1);                         // depth parity inside the treelet
         if (it.bit < 0 || it.n < (uint32_t)max_prims) {
             if (it.n > 65535u) err = 1;                                 // LinearBVHNode::n_primitives is 16 bits (pbrt-v3 CHECKs)
             nd.offset = it.s;                                           // H7: position in the sorted order
@@ -183,14 +184,16 @@ __global__ void __launch_bounds__(64) k_emit_treelets(const uint32_t* __restrict
 
 // Treelet t's block -> final[base[t] ...]; interior second-child indices become global.
 __global__ void __launch_bounds__(256) k_place_treelets(const uint32_t* __restrict__ starts, const uint4* __restrict__ meta,
-                                                       const uint32_t* __restrict__ base, const LinearNode* __restrict__ local,
-                                                       LinearNode* __restrict__ final_nodes) {
+                                                       const uint32_t* __restrict__ base, const uint8_t* __restrict__ root_parity,
+                                                       const LinearNode* __restrict__ local, LinearNode* __restrict__ final_nodes) {
     const uint32_t t = blockIdx.x;
     const LinearNode* src = local + 2ull * starts[t];
     const uint32_t count = meta[t].x, b = base[t];
+    const uint8_t par = root_parity[t];
     for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
         LinearNode nd = src[k];
         if (nd.n_prims == 0) nd.offset += b;
+        nd.pad ^= par;                                                  // depth parity in the whole tree
         final_nodes[b + k] = nd;
     }
 }
@@ -199,6 +202,91 @@ __global__ void __launch_bounds__(256) k_gather_roots(const uint32_t* __restrict
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_treelets) roots[t] = local[2ull * starts[t]];
 }
+// ---- device-layout repack: the host's repack_device_layout (bvh_build.cpp) as kernels over the flattened array --------------
+__global__ void __launch_bounds__(256) k_record_flags(const LinearNode* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ is_pair,
+                                                      uint32_t* __restrict__ is_quad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool interior = nodes[i].n_prims == 0;
+    is_pair[i] = interior ? 1u : 0u;
+    is_quad[i] = (interior && nodes[i].pad == 0) ? 1u : 0u;             // interior node at even depth
+}
+__device__ __forceinline__ uint32_t node_ref(const LinearNode& ln, uint32_t index_of) {
+    return ln.n_prims > 0 ? (kLeafBit | ln.offset) : index_of;
+}
+__global__ void __launch_bounds__(256) k_fill_records(const LinearNode* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ pair_of,
+                                                      const uint32_t* __restrict__ quad_of, PairNode* __restrict__ pairs,
+                                                      QuadNode* __restrict__ quads) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const LinearNode ln = nodes[i];
+    if (ln.n_prims != 0) return;
+    const LinearNode L = nodes[i + 1], R = nodes[ln.offset];
+    PairNode p;
+    p.a[0] = L.bmin[0]; p.a[1] = L.bmin[1]; p.a[2] = L.bmin[2]; p.a[3] = L.bmax[0];
+    p.b[0] = L.bmax[1]; p.b[1] = L.bmax[2]; p.b[2] = R.bmin[0]; p.b[3] = R.bmin[1];
+    p.c[0] = R.bmin[2]; p.c[1] = R.bmax[0]; p.c[2] = R.bmax[1]; p.c[3] = R.bmax[2];
+    p.left = node_ref(L, pair_of[i + 1]);
+    p.right = node_ref(R, pair_of[ln.offset]);
+    p.axis = ln.axis;
+    p.pad = 0;
+    pairs[pair_of[i]] = p;
+    if (ln.pad != 0) return;
+    QuadNode Q;
+    const float inf = __int_as_float(0x7f800000);
+    for (int k = 0; k < 4; ++k) {
+        Q.lox[k] = Q.loy[k] = Q.loz[k] = inf;
+        Q.hix[k] = Q.hiy[k] = Q.hiz[k] = -inf;
+        Q.ref[k] = kQuadEmpty;
+        Q.pad[k] = 0;
+    }
+    uint32_t axes[3] = {ln.axis, 0u, 0u};
+    const uint32_t kids[2] = {i + 1, ln.offset};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const LinearNode X = g == 0 ? L : R;
+        if (X.n_prims > 0) {
+            const int k = 2 * g;
+            Q.lox[k] = X.bmin[0]; Q.loy[k] = X.bmin[1]; Q.loz[k] = X.bmin[2];
+            Q.hix[k] = X.bmax[0]; Q.hiy[k] = X.bmax[1]; Q.hiz[k] = X.bmax[2];
+            Q.ref[k] = kLeafBit | X.offset;
+        } else {
+            axes[1 + g] = X.axis;
+            const uint32_t members[2] = {kids[g] + 1, X.offset};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const LinearNode Y = nodes[members[j]];
+                const int k = 2 * g + j;
+                Q.lox[k] = Y.bmin[0]; Q.loy[k] = Y.bmin[1]; Q.loz[k] = Y.bmin[2];
+                Q.hix[k] = Y.bmax[0]; Q.hiy[k] = Y.bmax[1]; Q.hiz[k] = Y.bmax[2];
+                Q.ref[k] = node_ref(Y, quad_of[members[j]]);
+            }
+        }
+    }
+    for (int k = 0; k < 3; ++k) Q.ref[k] = (Q.ref[k] & kQuadRefMask) | (axes[k] << kQuadAxisShift);
+    quads[quad_of[i]] = Q;
+}
+__global__ void __launch_bounds__(256) k_fill_tris(const float* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ prim,
+                                                   uint32_t n, PackedTri* __restrict__ tris, uint32_t* __restrict__ slot_of_prim) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = prim[i];
+    PackedTri pt;
+    const uint32_t i0 = idx[3ull * t], i1 = idx[3ull * t + 1], i2 = idx[3ull * t + 2];
+    for (int k = 0; k < 3; ++k) { pt.v0[k] = verts[3ull * i0 + k]; pt.v1[k] = verts[3ull * i1 + k]; pt.v2[k] = verts[3ull * i2 + k]; }
+    pt.prim_id = t;
+    pt.last = 0;
+    pt.pad = 0;
+    tris[i] = pt;
+    slot_of_prim[t] = i;
+}
+__global__ void __launch_bounds__(256) k_mark_last(const LinearNode* __restrict__ nodes, uint32_t n, PackedTri* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const LinearNode ln = nodes[i];
+    if (ln.n_prims > 0) tris[(size_t)ln.offset + ln.n_prims - 1].last = 1;
+}
+
 struct UpperNode {
     uint32_t position;
     LinearNode node;
@@ -301,6 +389,7 @@ struct Flattener {
     const std::vector<uint32_t>& counts;
     const std::vector<uint32_t>& depths;
     std::vector<uint32_t> base;
+    std::vector<uint8_t> root_parity;                                   // depth parity of every treelet root
     std::vector<UpperNode> upper;
     uint32_t next = 0;
     int deepest = 0;
@@ -309,6 +398,7 @@ struct Flattener {
             const int t = ~ref;
             const uint32_t my = next;
             base[t] = my;
+            root_parity[t] = (uint8_t)((level - 1) & 1);
             next += counts[t];
             deepest = std::max(deepest, level - 1 + (int)depths[t]);
             return my;
@@ -322,7 +412,7 @@ struct Flattener {
         u.node.offset = second;
         u.node.n_prims = 0;
         u.node.axis = (uint8_t)ut.nodes[ref].axis;
-        u.node.pad = 0;
+        u.node.pad = (uint8_t)((level - 1) & 1);
         upper.push_back(u);
         return my;
     }
@@ -348,19 +438,11 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
         }                                                                                                   \
     } while (0)
 
-int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris, int max_prims_in_node, HostBVH* out,
+int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris, int max_prims_in_node, DeviceBVH* out,
                     char* err, int err_len, double* timing_ms) {
-    out->nodes.clear();
-    out->ordered_prims.clear();
-    out->pairs.clear();
-    out->quads.clear();
-    out->tris.clear();
-    out->max_depth = 0;
+    *out = DeviceBVH();
     double tm[6] = {0, 0, 0, 0, 0, 0};
-    if (n_tris == 0) {
-        repack_device_layout(verts, indices, 0, out);
-        return 0;
-    }
+    if (n_tris == 0) return 0;
     const int max_prims = std::min(max_prims_in_node, 255);             // bvh.rs:222
     const uint32_t n = (uint32_t)n_tris;
     const unsigned grid = (n + 255) / 256;
@@ -418,9 +500,7 @@ int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indice
                                                    max_prims, d_local.as<LinearNode>(), d_meta.as<uint4>());
     HL_CUDA(cudaGetLastError());
     std::vector<uint4> meta(n_treelets);
-    std::vector<uint32_t> starts(n_treelets);
     HL_CUDA(cudaMemcpy(meta.data(), d_meta.p, n_treelets * sizeof(uint4), cudaMemcpyDeviceToHost));
-    HL_CUDA(cudaMemcpy(starts.data(), d_starts.p, n_treelets * 4, cudaMemcpyDeviceToHost));
     DevBuf d_roots;
     HL_CUDA(d_roots.alloc(n_treelets * sizeof(LinearNode)));
     k_gather_roots<<<(n_treelets + 255) / 256, 256>>>(d_starts.as<uint32_t>(), n_treelets, d_local.as<LinearNode>(), d_roots.as<LinearNode>());
@@ -443,33 +523,75 @@ int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indice
     std::vector<int> order(n_treelets);
     for (uint32_t t = 0; t < n_treelets; ++t) order[t] = (int)t;
     const int root_ref = ut.build(order, 0, n_treelets);
-    Flattener fl{ut, counts, depths, std::vector<uint32_t>(n_treelets, 0), {}, 0, 0};
+    Flattener fl{ut, counts, depths, std::vector<uint32_t>(n_treelets, 0), std::vector<uint8_t>(n_treelets, 0), {}, 0, 0};
     fl.visit(root_ref, 1);
     const uint32_t total = fl.next;
     tm[3] = now_ms() - t0;
 
     t0 = now_ms();
-    DevBuf d_final, d_base, d_upper;
+    DevBuf d_final, d_base, d_par, d_upper;
     HL_CUDA(d_final.alloc((size_t)total * sizeof(LinearNode)));
     HL_CUDA(d_base.alloc(n_treelets * 4));
+    HL_CUDA(d_par.alloc(n_treelets));
     HL_CUDA(cudaMemcpy(d_base.p, fl.base.data(), n_treelets * 4, cudaMemcpyHostToDevice));
-    k_place_treelets<<<n_treelets, 256>>>(d_starts.as<uint32_t>(), d_meta.as<uint4>(), d_base.as<uint32_t>(), d_local.as<LinearNode>(),
-                                         d_final.as<LinearNode>());
+    HL_CUDA(cudaMemcpy(d_par.p, fl.root_parity.data(), n_treelets, cudaMemcpyHostToDevice));
+    k_place_treelets<<<n_treelets, 256>>>(d_starts.as<uint32_t>(), d_meta.as<uint4>(), d_base.as<uint32_t>(), d_par.as<uint8_t>(),
+                                         d_local.as<LinearNode>(), d_final.as<LinearNode>());
     if (!fl.upper.empty()) {
         HL_CUDA(d_upper.alloc(fl.upper.size() * sizeof(UpperNode)));
         HL_CUDA(cudaMemcpy(d_upper.p, fl.upper.data(), fl.upper.size() * sizeof(UpperNode), cudaMemcpyHostToDevice));
         k_place_upper<<<((unsigned)fl.upper.size() + 255) / 256, 256>>>(d_upper.as<UpperNode>(), (uint32_t)fl.upper.size(), d_final.as<LinearNode>());
     }
     HL_CUDA(cudaGetLastError());
-    out->nodes.resize(total);
-    out->ordered_prims.resize(n_tris);
-    HL_CUDA(cudaMemcpy(out->nodes.data(), d_final.p, (size_t)total * sizeof(LinearNode), cudaMemcpyDeviceToHost));
-    HL_CUDA(cudaMemcpy(out->ordered_prims.data(), prim, n_tris * 4, cudaMemcpyDeviceToHost));
-    out->max_depth = fl.deepest;
+    HL_CUDA(cudaDeviceSynchronize());
+    // the big scratch buffers are not needed any more
+    cudaFree(d_local.p); d_local.p = nullptr;
+    cudaFree(d_lo.p); d_lo.p = nullptr;
+    cudaFree(d_hi.p); d_hi.p = nullptr;
     tm[4] = now_ms() - t0;
 
+    // ---- traversal layout, on the device ----
     t0 = now_ms();
-    repack_device_layout(verts, indices, n_tris, out);
+    const unsigned ngrid = (total + 255) / 256;
+    DevBuf d_is_pair, d_is_quad, d_pair_of, d_quad_of, d_scan_tmp;
+    HL_CUDA(d_is_pair.alloc((size_t)total * 4));
+    HL_CUDA(d_is_quad.alloc((size_t)total * 4));
+    HL_CUDA(d_pair_of.alloc((size_t)total * 4));
+    HL_CUDA(d_quad_of.alloc((size_t)total * 4));
+    k_record_flags<<<ngrid, 256>>>(d_final.as<LinearNode>(), total, d_is_pair.as<uint32_t>(), d_is_quad.as<uint32_t>());
+    size_t tmp_scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_is_pair.as<uint32_t>(), d_pair_of.as<uint32_t>(), (int)total);
+    HL_CUDA(d_scan_tmp.alloc(tmp_scan));
+    HL_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_scan, d_is_pair.as<uint32_t>(), d_pair_of.as<uint32_t>(), (int)total));
+    HL_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_scan, d_is_quad.as<uint32_t>(), d_quad_of.as<uint32_t>(), (int)total));
+    uint32_t last[4];
+    HL_CUDA(cudaMemcpy(&last[0], d_is_pair.as<uint32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost));
+    HL_CUDA(cudaMemcpy(&last[1], d_pair_of.as<uint32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost));
+    HL_CUDA(cudaMemcpy(&last[2], d_is_quad.as<uint32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost));
+    HL_CUDA(cudaMemcpy(&last[3], d_quad_of.as<uint32_t>() + (total - 1), 4, cudaMemcpyDeviceToHost));
+    out->n_pairs = last[0] + last[1];
+    out->n_quads = last[2] + last[3];
+    out->n_nodes = total;
+    out->n_tris = n_tris;
+    HL_CUDA(cudaMalloc(&out->d_pairs, std::max<size_t>(64, out->n_pairs * sizeof(PairNode))));
+    HL_CUDA(cudaMalloc(&out->d_quads, std::max<size_t>(128, out->n_quads * sizeof(QuadNode))));
+    HL_CUDA(cudaMalloc(&out->d_tris, n_tris * sizeof(PackedTri)));
+    HL_CUDA(cudaMalloc(&out->d_slot_of_prim, n_tris * 4));
+    k_fill_records<<<ngrid, 256>>>(d_final.as<LinearNode>(), total, d_pair_of.as<uint32_t>(), d_quad_of.as<uint32_t>(), (PairNode*)out->d_pairs,
+                                   (QuadNode*)out->d_quads);
+    k_fill_tris<<<grid, 256>>>(d_verts.as<float>(), d_idx.as<uint32_t>(), prim, n, (PackedTri*)out->d_tris, (uint32_t*)out->d_slot_of_prim);
+    k_mark_last<<<ngrid, 256>>>(d_final.as<LinearNode>(), total, (PackedTri*)out->d_tris);
+    HL_CUDA(cudaGetLastError());
+    LinearNode root;
+    HL_CUDA(cudaMemcpy(&root, d_final.p, sizeof root, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) { out->root_bounds[k] = root.bmin[k]; out->root_bounds[3 + k] = root.bmax[k]; }
+    out->root_ref = root.n_prims > 0 ? (kLeafBit | root.offset) : 0u;
+    out->quad_root_ref = out->root_ref;                                 // both numberings start at the root
+    out->max_depth = fl.deepest;
+    HL_CUDA(cudaDeviceSynchronize());
+    // the flattened nodes and the primitive order stay on the device for pb2_bvh_export
+    out->d_nodes = d_final.p; d_final.p = nullptr;
+    out->d_ordered_prims = d_prim2.p; d_prim2.p = nullptr;
     tm[5] = now_ms() - t0;
     if (timing_ms) for (int k = 0; k < 6; ++k) timing_ms[k] = tm[k];
     return 0;
