@@ -40,6 +40,8 @@ extern "C" {
     pub fn pb2_film_destroy(film: *mut pb2_film) -> c_int;
     pub fn pb2_film_read_xyzw(film: *mut pb2_film, out: *mut f32) -> c_int;
     pub fn pb2_film_resolve_rgb(film: *mut pb2_film, scale: f32, rgb: *mut f32) -> c_int;
+    pub fn pb2_film_write_image(film: *mut pb2_film, filename: *const c_char, scale: f32) -> c_int;
+    pub fn pb2_bvh_build_stats(scene: *const pb2_scene, ms: *mut f64) -> c_int;
     pub fn pb2_render_path(scene: *mut pb2_scene, cam: *const pb2_camera, path: *const pb2_path_desc, film: *mut pb2_film,
                            stream: *mut c_void) -> c_int;
 }
@@ -60,12 +62,17 @@ impl B200Accel {
     /// verts / indices: the world-space triangle list that would have been handed to `BVHAccel::new` as
     /// `GeometricPrimitive(Triangle)`s; `max_prims_in_node` and SAH as in src/accelerators/bvh.rs:216-222.
     pub fn new(verts: &[f32], indices: &[u32], max_prims_in_node: usize) -> Self {
+        Self::with_split(verts, indices, max_prims_in_node, 0)
+    }
+    /// `split_method` follows `SplitMethod` (src/accelerators/bvh.rs:199-204): 0 = SAH (built on the host), 1 = HLBVH (built
+    /// on the GPU, bvh.rs:475-772); Middle / EqualCounts are not built.
+    pub fn with_split(verts: &[f32], indices: &[u32], max_prims_in_node: usize, split_method: c_int) -> Self {
         let mut scene = std::ptr::null_mut();
         unsafe {
             check(pb2_init(0));
             check(pb2_scene_create(verts.as_ptr(), (verts.len() / 3) as u64, indices.as_ptr(), (indices.len() / 3) as u64,
                                    std::ptr::null(), std::ptr::null(), 0, std::ptr::null(), 0, &mut scene));
-            check(pb2_scene_build_bvh(scene, max_prims_in_node as c_int, 0));
+            check(pb2_scene_build_bvh(scene, max_prims_in_node as c_int, split_method));
         }
         B200Accel { scene }
     }
