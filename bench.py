@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--grid-n", type=int, default=2237, help="quads per side of the C3 grid (2237 -> 10,008,338 triangles)")
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-stride", type=int, default=4, help="cpu sample = every k-th ray of each ray set")
+    ap.add_argument("--cpu-stride", type=int, default=1, help="cpu sample = every k-th ray of each ray set")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat the sample until this much traversal time")
     return ap.parse_args()
 
 
@@ -214,20 +215,23 @@ def pb2_mean_rgb(film):
     return film.resolve_rgb().mean(axis=(0, 1))
 
 
+PATH_CPU_SPP = 16
+
+
 def bench_path_cpu(orc_mod, scenes, sc, gpu_film_xyzw):
-    """CPU baseline for path tracing: the oracle's SamplerIntegrator::render on a bounded sample (2 of the 64 spp of C2)
+    """CPU baseline for path tracing: the oracle's SamplerIntegrator::render on a bounded sample (16 of the 64 spp of C2)
     with all host threads, and a parity check of that sample range against the GPU."""
     from oracle import oracle_path as OP
     cam = scenes.C2_CAMERA
     pk = dict(scenes.C2_PATH)
     ref = OP.Scene(sc, 4)
     fd = OP.film_desc(cam["res"])
-    pd = OP.path_desc(sample_begin=0, sample_end=2, **pk)
+    pd = OP.path_desc(sample_begin=0, sample_end=PATH_CPU_SPP, **pk)
     xyzw, dt = ref.render(cam, fd, pd, mode=1)
-    n = cam["res"][0] * cam["res"][1] * 2
+    n = cam["res"][0] * cam["res"][1] * PATH_CPU_SPP
     cores, model = host_info()
     return {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": model,
-            "sample": "sample indices [0,2) of the 64 spp of every pixel (524,288 camera samples), render time only"}, xyzw
+            "sample": f"sample indices [0,{PATH_CPU_SPP}) of the 64 spp of every pixel ({n:,} camera samples), render time only"}, xyzw
 
 
 def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
@@ -542,20 +546,24 @@ def main():
         sample = [np.ascontiguousarray(g_rays[::k]), np.ascontiguousarray(g_srays[::k]), np.ascontiguousarray(g_brays[::k])]
         n_sample = sum(len(s) for s in sample)
         ref.intersect(sample[0])
-        cpu_s = ref.intersect(sample[0])[-1] + ref.intersect_p(sample[1])[-1] + ref.intersect(sample[2])[-1]
+        cpu_s, cpu_reps = 0.0, 0
+        while cpu_s < args.cpu_seconds and cpu_reps < 200:          # ~10 s of CPU work on the same rays
+            cpu_s += ref.intersect(sample[0])[-1] + ref.intersect_p(sample[1])[-1] + ref.intersect(sample[2])[-1]
+            cpu_reps += 1
         cores, model = host_info()
-        cpu_baseline = {"value": n_sample / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
-                        "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays), traversal time only"}
+        cpu_baseline = {"value": cpu_reps * n_sample / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
+                        "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays) x {cpu_reps} passes = {cpu_s:.1f} s, "
+                                  "traversal time only"}
         # path tracing: oracle on sample indices [0,2) of C2, and the GPU film of the same range must equal it bit for bit
         accel2, camera2, integ2, film2, sc2 = path_keep
         path_cpu, ref_xyzw = bench_path_cpu(orc, scenes, sc2, None)
         film2.clear()
-        integ2.render(film2, 0, 2)
+        integ2.render(film2, 0, PATH_CPU_SPP)
         g_xyzw = film2.read_xyzw()
         path_c2["cpu_baseline"] = path_cpu
         path_c2["parity"] = {"pixels_checked": int(g_xyzw.shape[0] * g_xyzw.shape[1]),
                              "pixels_differing": int((g_xyzw.view(np.uint32) != ref_xyzw.view(np.uint32)).any(axis=2).sum()),
-                             "checked_against": "oracle SamplerIntegrator::render, per-(pixel,sample) sampler streams, samples [0,2)"}
+                             "checked_against": f"oracle SamplerIntegrator::render, per-(pixel,sample) sampler streams, samples [0,{PATH_CPU_SPP})"}
     if rank == 0:
         line = {
             "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s", "n_gpus": world,
