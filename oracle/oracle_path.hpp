@@ -84,6 +84,7 @@ struct PathDesc {
     int32_t light_strategy;
     int32_t spp;
     int32_t sample_begin, sample_end;
+    int32_t sampler;          // 0 = RandomSampler (samplers/random.rs), 1 = HaltonSampler (samplers/halton.rs)
 };
 
 // ---------------------------------------------------------------- sampling.rs:68-154 Distribution1D (D29 FIX, D57 KEEP, D58)
@@ -472,10 +473,165 @@ public:
     }
 };
 
-struct Sampler {          // RandomSampler (samplers/random.rs:29-56): every dimension straight from PCG32
-    RNG rng;
-    Float get_1d() { return rng.uniform_float(); }
-    void get_2d(Float* a, Float* b) { *a = rng.uniform_float(); *b = rng.uniform_float(); }   // x then y
+// ---------------------------------------------------------------- src/core/lowdiscrepancy.rs + src/samplers/halton.rs
+// HaltonSampler.  The Rust port does not produce Halton points as written; where it is broken this
+// follows pbrt-v3 (core/lowdiscrepancy.h/.cpp, samplers/halton.cpp), the code it is a port of:
+//   S1 lowdiscrepancy.rs:293-305 radical_inverse_specialized never accumulates the reversed digits (`let _reversed_digits`)
+//      and squares inv_base instead of scaling inv_base_n                                        -> FIX
+//   S2 :307-320 scramble_radical_inverse_specialized scales by inv_base instead of inv_base_n   -> FIX
+//   S3 sampler.rs:344-396 GlobalSampler::get_1d/get_2d run on the base struct, which cannot reach the Halton
+//      overrides of get_index_for_sample / sample_dimension (no virtual dispatch through Deref)  -> FIX (dispatch)
+//   S4 halton.rs:122-125 `current_pixel % MAX_RESOLUTION` is negative for negative pixels         -> FIX (pbrt-v3 Mod)
+//   S5 the table of the first 1000 primes (lowdiscrepancy.rs:12-76) is generated by a sieve here, not copied
+struct HaltonTables {
+    static constexpr int kPrimeTableSize = 1000;              // lowdiscrepancy.rs:11
+    static constexpr int kMaxResolution = 128;                // halton.rs:39
+    std::vector<uint32_t> primes, prime_sums;
+    std::vector<uint16_t> perms;                              // RADICAL_INVERSE_PERMUTATIONS (halton.rs:17-22)
+    int base_scales[2], base_exponents[2];
+    uint64_t sample_stride, mult_inverse[2];
+
+    static void extended_gcd(uint64_t a, uint64_t b, int64_t* x, int64_t* y) {       // halton.rs:52-62
+        if (b == 0) { *x = 1; *y = 0; return; }
+        int64_t d = (int64_t)(a / b), xp, yp;
+        extended_gcd(b, a % b, &xp, &yp);
+        *x = yp;
+        *y = xp - d * yp;
+    }
+    static uint64_t multiplicative_inverse(int64_t a, int64_t n) {                   // halton.rs:41-50
+        int64_t x, y;
+        extended_gcd((uint64_t)a, (uint64_t)n, &x, &y);
+        int64_t r = x - (x / n) * n;
+        return (uint64_t)(r < 0 ? r + n : r);
+    }
+    void init(int res_x, int res_y) {                         // HaltonSampler::new, halton.rs:64-103
+        primes.clear();
+        for (uint32_t c = 2; (int)primes.size() < kPrimeTableSize; ++c) {
+            bool is_prime = true;
+            for (uint32_t p : primes) { if (p * p > c) break; if (c % p == 0) { is_prime = false; break; } }
+            if (is_prime) primes.push_back(c);
+        }
+        prime_sums.assign(kPrimeTableSize, 0);
+        for (int i = 1; i < kPrimeTableSize; ++i) prime_sums[i] = prime_sums[i - 1] + primes[i - 1];
+        // compute_radical_inverse_permutations (lowdiscrepancy.rs:333-349) with RNG::default(); shuffle = sampling.rs:280-287
+        perms.resize(prime_sums.back() + primes.back());
+        RNG rng;
+        size_t off = 0;
+        for (int i = 0; i < kPrimeTableSize; ++i) {
+            const uint32_t n = primes[i];
+            for (uint32_t j = 0; j < n; ++j) perms[off + j] = (uint16_t)j;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t other = j + uniform_u32_bounded(rng, n - j);
+                std::swap(perms[off + j], perms[off + other]);
+            }
+            off += n;
+        }
+        const int res[2] = {res_x, res_y};
+        for (int i = 0; i < 2; ++i) {
+            const int base = i == 0 ? 2 : 3;
+            int scale = 1, exp = 0;
+            while (scale < std::min(kMaxResolution, res[i])) { scale *= base; ++exp; }
+            base_scales[i] = scale;
+            base_exponents[i] = exp;
+        }
+        sample_stride = (uint64_t)base_scales[0] * (uint64_t)base_scales[1];
+        mult_inverse[0] = multiplicative_inverse(base_scales[1], base_scales[0]);
+        mult_inverse[1] = multiplicative_inverse(base_scales[0], base_scales[1]);
+    }
+    static uint32_t uniform_u32_bounded(RNG& rng, uint32_t b) {                      // rng.rs:36-44
+        const uint32_t threshold = (~b + 1u) % b;
+        for (;;) {
+            const uint32_t r = rng.uniform_u32();
+            if (r >= threshold) return r % b;
+        }
+    }
+    static uint32_t reverse_bits32(uint32_t n) {                                     // lowdiscrepancy.rs:371-379
+        n = (n << 16) | (n >> 16);
+        n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
+        n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
+        n = ((n & 0x33333333u) << 2) | ((n & 0xccccccccu) >> 2);
+        n = ((n & 0x55555555u) << 1) | ((n & 0xaaaaaaaau) >> 1);
+        return n;
+    }
+    static uint64_t reverse_bits64(uint64_t n) {                                     // :364-369
+        return ((uint64_t)reverse_bits32((uint32_t)n) << 32) | (uint64_t)reverse_bits32((uint32_t)(n >> 32));
+    }
+    static uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, int n_digits) {      // :381-390
+        uint64_t index = 0;
+        for (int i = 0; i < n_digits; ++i) {
+            const uint64_t digit = inverse % base;
+            inverse /= base;
+            index = index * base + digit;
+        }
+        return index;
+    }
+    Float radical_inverse(int base_index, uint64_t a) const {                       // :322-331, S1
+        if (base_index == 0) return (Float)reverse_bits64(a) * 5.4210108624275222e-20f;
+        const uint64_t base = primes[base_index];
+        const Float inv_base = 1.0f / (Float)base;
+        uint64_t reversed = 0;
+        Float inv_base_n = 1.0f;
+        while (a != 0) {
+            const uint64_t next = a / base, digit = a - next * base;
+            reversed = reversed * base + digit;
+            inv_base_n *= inv_base;
+            a = next;
+        }
+        return fmin_((Float)reversed * inv_base_n, kOneMinusEpsilon);
+    }
+    Float scrambled_radical_inverse(int base_index, uint64_t a) const {             // :307-320,:351-362, S2
+        const uint64_t base = primes[base_index];
+        const uint16_t* perm = perms.data() + prime_sums[base_index];                // halton.rs:105-113
+        const Float inv_base = 1.0f / (Float)base;
+        uint64_t reversed = 0;
+        Float inv_base_n = 1.0f;
+        while (a != 0) {
+            const uint64_t next = a / base, digit = a - next * base;
+            reversed = reversed * base + perm[digit];
+            inv_base_n *= inv_base;
+            a = next;
+        }
+        return fmin_(inv_base_n * ((Float)reversed + inv_base * (Float)perm[0] / (1.0f - inv_base)), kOneMinusEpsilon);
+    }
+    // HaltonSampler::get_index_for_sample (halton.rs:117-141)
+    int64_t index_for_sample(int px, int py, uint64_t sample_num) const {
+        int64_t offset = 0;
+        if (sample_stride > 1) {
+            const int pm[2] = {((px % kMaxResolution) + kMaxResolution) % kMaxResolution, ((py % kMaxResolution) + kMaxResolution) % kMaxResolution};   // S4
+            for (int i = 0; i < 2; ++i) {
+                const uint64_t dim_offset = inverse_radical_inverse(i == 0 ? 2 : 3, (uint64_t)pm[i], base_exponents[i]);
+                offset += (int64_t)(dim_offset * (sample_stride / (uint64_t)base_scales[i]) * mult_inverse[i]);
+            }
+            offset %= (int64_t)sample_stride;
+        }
+        return offset + (int64_t)(sample_num * sample_stride);
+    }
+    // HaltonSampler::sample_dimension (halton.rs:143-155), sample_at_pixel_center = false
+    Float sample_dimension(int64_t index, int dim) const {
+        if (dim == 0) return radical_inverse(0, (uint64_t)index >> base_exponents[0]);
+        if (dim == 1) return radical_inverse(1, (uint64_t)index / (uint64_t)base_scales[1]);
+        return scrambled_radical_inverse(dim, (uint64_t)index);
+    }
+};
+
+struct Sampler {          // kind 0: RandomSampler (samplers/random.rs:29-56), every dimension straight from PCG32;
+    RNG rng;              // kind 1: HaltonSampler through GlobalSampler::get_1d/get_2d (sampler.rs:371-389; no sample arrays)
+    int kind = 0;
+    const HaltonTables* halton = nullptr;
+    int64_t index = 0;
+    int dimension = 0;
+    void start_sample(int px, int py, uint64_t sample_num) {   // start_pixel / set_sample_number (sampler.rs:347-350,405-409)
+        if (kind == 1) { index = halton->index_for_sample(px, py, sample_num); dimension = 0; }
+    }
+    Float get_1d() {
+        if (kind == 1) return halton->sample_dimension(index, dimension++);
+        return rng.uniform_float();
+    }
+    void get_2d(Float* a, Float* b) {                          // x then y
+        if (kind == 1) { *a = halton->sample_dimension(index, dimension); *b = halton->sample_dimension(index, dimension + 1); dimension += 2; return; }
+        *a = rng.uniform_float();
+        *b = rng.uniform_float();
+    }
 };
 
 // integrator.rs:136-266 (handle_media = false, specular = false)
@@ -685,6 +841,8 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
     const int W = film.sb_x1 - film.sb_x0, H = film.sb_y1 - film.sb_y0;
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
     const size_t npix = (size_t)fd.res_x * fd.res_y;
+    HaltonTables halton;
+    if (pd.sampler == 1) halton.init(W, H);                   // sample_bounds extent (halton.rs:69)
     std::vector<RGB> acc(npix, rgb(0));
     std::vector<Float> wsum(npix, 0.0f);
     std::vector<std::vector<Stray>> strays(threads);
@@ -696,6 +854,8 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
             if (t >= tiles_x * tiles_y) break;
             int tx = t % tiles_x, ty = t / tiles_x;
             Sampler tile_sampler;
+            tile_sampler.kind = pd.sampler;
+            tile_sampler.halton = &halton;
             tile_sampler.rng.set_sequence((uint64_t)(ty * tiles_x + tx));                       // integrator.rs:414-415
             int x0 = film.sb_x0 + tx * 16, x1 = std::min(x0 + 16, film.sb_x1);
             int y0 = film.sb_y0 + ty * 16, y1 = std::min(y0 + 16, film.sb_y1);
@@ -704,9 +864,12 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                 for (int x = x0; x < x1; ++x)
                     for (int s = pd.sample_begin; s < pd.sample_end; ++s) {
                         Sampler own;
+                        own.kind = pd.sampler;
+                        own.halton = &halton;
                         uint64_t order = ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)) * (uint64_t)pd.spp + (uint64_t)s;
                         if (mode == 1) own.rng.set_sequence(order);
                         Sampler& smp = mode == 1 ? own : tile_sampler;
+                        smp.start_sample(x, y, (uint64_t)s);
                         Float u0, u1, ut, l0, l1;
                         smp.get_2d(&u0, &u1);                                                   // sampler.rs:27-33
                         ut = smp.get_1d();

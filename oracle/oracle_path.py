@@ -32,9 +32,10 @@ class FilmDesc(C.Structure):
 
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32)]
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32)]
 
 
+_SAMPLER = {"random": 0, "halton": 1}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2}
 _STRAT = {"uniform": 0, "power": 1}
 _FILTER = {"box": 0, "gaussian": 1}
@@ -86,7 +87,7 @@ def film_desc(res, filt="box", radius=(0.5, 0.5), alpha=2.0):
     return f
 
 
-def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None):
+def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None, sampler="random"):
     p = PathDesc()
     p.max_depth = max_depth
     p.rr_threshold = rr_threshold
@@ -94,7 +95,18 @@ def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sa
     p.spp = spp
     p.sample_begin = sample_begin
     p.sample_end = spp if sample_end is None else sample_end
+    p.sampler = _SAMPLER[sampler]
     return p
+
+
+def halton_probe(res, pixel, sample_num, n_dims=8, n_perm=32):
+    """(sample index, first n_dims sample_dimension values, first n_perm entries of the permutation table)."""
+    index = C.c_int64()
+    dims = np.zeros(n_dims, np.float32)
+    perm = np.zeros(n_perm, np.uint16)
+    O.lib().orc_halton_probe(int(res[0]), int(res[1]), int(pixel[0]), int(pixel[1]), C.c_uint64(int(sample_num)), int(n_dims), C.byref(index),
+                             _p(dims), int(n_perm), _p(perm))
+    return index.value, dims, perm
 
 
 def _p(a):

@@ -22,8 +22,11 @@ for r in csv.reader(io.StringIO(out)):
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
-want = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'smsp__inst_executed.sum',
-        'smsp__thread_inst_executed.sum']
+want = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes_read.sum.per_second', 'dram__bytes_write.sum.per_second',
+        'lts__t_bytes.sum', 'lts__t_bytes.sum.per_second', 'lts__t_sectors.sum', 'l1tex__t_bytes.sum', 'smsp__inst_executed.sum',
+        'smsp__thread_inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__inst_executed.avg.per_cycle_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'gpu__time_duration.sum']
 stall = [c for c in h if 'pcsamp_warps_issue_stalled' in c and 'not_issued' not in c]
 for k in want + stall:
     if k in h:
