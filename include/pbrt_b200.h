@@ -87,6 +87,10 @@ typedef struct pb2_film_desc {
 } pb2_film_desc;
 
 enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1 };
+/* PB2_SAMPLER_RANDOM: RandomSampler (src/samplers/random.rs), one PCG32 stream per (pixel, sample).
+ * PB2_SAMPLER_HALTON: HaltonSampler (src/samplers/halton.rs, src/core/lowdiscrepancy.rs:293-390) — every dimension is a pure
+ * function of (pixel, sample index, dimension), so the per-sample values equal the reference's tile-ordered render. */
+enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1 };
 /* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
 typedef struct pb2_path_desc {
     int32_t max_depth;
@@ -95,6 +99,7 @@ typedef struct pb2_path_desc {
     int32_t spp;                /* samples per pixel of the whole frame */
     int32_t sample_begin;       /* this call renders sample indices [sample_begin, sample_end) of every pixel */
     int32_t sample_end;
+    int32_t sampler;            /* PB2_SAMPLER_* */
 } pb2_path_desc;
 
 typedef struct pb2_scene pb2_scene;

@@ -53,7 +53,10 @@ class FilmDesc(C.Structure):
 
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32)]
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32)]
+
+
+_SAMPLER = {"random": 0, "halton": 1}
 
 
 def matte(kd):
@@ -406,9 +409,10 @@ class Film:
 
 
 class PathIntegrator:
-    """Mirror of src/integrators/path.rs PathIntegrator + SamplerIntegrator::render (RandomSampler streams per sample)."""
+    """Mirror of src/integrators/path.rs PathIntegrator + SamplerIntegrator::render; sampler = "random" (RandomSampler streams
+    per (pixel, sample)) or "halton" (HaltonSampler, src/samplers/halton.rs)."""
 
-    def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1):
+    def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sampler="random"):
         self.accel, self.camera = accel, camera
         self.desc = PathDesc()
         self.desc.max_depth = max_depth
@@ -416,6 +420,7 @@ class PathIntegrator:
         self.desc.light_strategy = _STRATEGY[light_strategy]
         self.desc.spp = spp
         self.desc.sample_begin, self.desc.sample_end = 0, spp
+        self.desc.sampler = _SAMPLER[sampler]
 
     def render(self, film, sample_begin=0, sample_end=None, stream=None):
         """Integrator::render: accumulates sample indices [sample_begin, sample_end) of every pixel into `film`."""

@@ -67,6 +67,10 @@ void pb2_scene::free_device() {
     if (pipe.d2h) cudaStreamDestroy(pipe.d2h);
     pipe.h2d = pipe.d2h = nullptr;
     if (wf) { wavefront_destroy(wf); wf = nullptr; }
+    if (d_halton_perms) cudaFree(d_halton_perms);
+    if (d_halton_primes) cudaFree(d_halton_primes);
+    if (d_halton_sums) cudaFree(d_halton_sums);
+    d_halton_perms = d_halton_primes = d_halton_sums = nullptr;
 }
 
 extern "C" {

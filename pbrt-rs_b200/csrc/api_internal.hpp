@@ -87,6 +87,10 @@ struct pb2_scene {
     pb2::SceneView view;
     pb2::Pipe pipe;
     pb2::Wavefront* wf = nullptr;
+    // HaltonSampler tables on the device (built on first use; the scales depend on the sample-bounds extent)
+    void* d_halton_perms = nullptr;
+    void* d_halton_primes = nullptr;
+    void* d_halton_sums = nullptr;
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void free_device();
 };

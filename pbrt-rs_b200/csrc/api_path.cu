@@ -157,8 +157,78 @@ static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_pa
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
     if (path->light_strategy != PB2_LIGHTS_UNIFORM && path->light_strategy != PB2_LIGHTS_POWER)
         return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
+    if (path->sampler != PB2_SAMPLER_RANDOM && path->sampler != PB2_SAMPLER_HALTON)
+        return set_error(PB2_ERR_INVALID, "unknown sampler %d", path->sampler);
+    if (path->sampler == PB2_SAMPLER_HALTON && 5 + 8 * (path->max_depth + 1) > 1000)      // lowdiscrepancy.rs:11 PRIME_TABLE_SIZE
+        return set_error(PB2_ERR_LIMIT, "HaltonSampler has 1000 dimensions; max_depth %d needs %d", path->max_depth, 5 + 8 * (path->max_depth + 1));
     if (fd && (cam->res_x != fd->res_x || cam->res_y != fd->res_y)) return set_error(PB2_ERR_INVALID, "camera and film resolutions differ");
     return make_camera_view(cam, cv);
+}
+
+// ---- HaltonSampler set-up (samplers/halton.rs:64-103, lowdiscrepancy.rs:333-349; host, once per scene) ------------------------
+static void halton_gcd(uint64_t a, uint64_t b, int64_t* x, int64_t* y) {                     // halton.rs:52-62
+    if (b == 0) { *x = 1; *y = 0; return; }
+    int64_t xp, yp;
+    halton_gcd(b, a % b, &xp, &yp);
+    *x = yp;
+    *y = xp - (int64_t)(a / b) * yp;
+}
+static uint64_t halton_mult_inverse(int64_t a, int64_t n) {                                  // halton.rs:41-50
+    int64_t x, y;
+    halton_gcd((uint64_t)a, (uint64_t)n, &x, &y);
+    const int64_t r = x - (x / n) * n;
+    return (uint64_t)(r < 0 ? r + n : r);
+}
+static int sampler_view(pb2_scene* scene, int sampler, int sb_w, int sb_h, SamplerView* out) {
+    memset(out, 0, sizeof *out);
+    if (sampler != PB2_SAMPLER_HALTON) return PB2_OK;
+    if (!scene->d_halton_perms) {
+        constexpr int kPrimes = 1000;                                                        // lowdiscrepancy.rs:11
+        std::vector<uint32_t> primes, sums(kPrimes, 0);
+        for (uint32_t c = 2; (int)primes.size() < kPrimes; ++c) {
+            bool is_prime = true;
+            for (uint32_t p : primes) { if (p * p > c) break; if (c % p == 0) { is_prime = false; break; } }
+            if (is_prime) primes.push_back(c);
+        }
+        for (int i = 1; i < kPrimes; ++i) sums[i] = sums[i - 1] + primes[i - 1];
+        std::vector<uint16_t> perms(sums.back() + primes.back());
+        Pcg32 rng;                                                                           // RNG::default(), rng.rs:14-19
+        rng.state = 0x853c49e6748fea9bULL;
+        rng.inc = 0xda3e39cb94b95bdbULL;
+        size_t off = 0;
+        for (int i = 0; i < kPrimes; ++i) {
+            const uint32_t n = primes[i];
+            for (uint32_t j = 0; j < n; ++j) perms[off + j] = (uint16_t)j;
+            for (uint32_t j = 0; j < n; ++j) {                                               // shuffle, sampling.rs:280-287
+                const uint32_t b = n - j, threshold = (~b + 1u) % b;                         // uniform_u32_u32, rng.rs:36-44
+                uint32_t r;
+                do { r = rng.next_u32(); } while (r < threshold);
+                std::swap(perms[off + j], perms[off + j + r % b]);
+            }
+            off += n;
+        }
+        PB2_CUDA(cudaMalloc(&scene->d_halton_perms, perms.size() * 2));
+        PB2_CUDA(cudaMalloc(&scene->d_halton_primes, kPrimes * 4));
+        PB2_CUDA(cudaMalloc(&scene->d_halton_sums, kPrimes * 4));
+        PB2_CUDA(cudaMemcpy(scene->d_halton_perms, perms.data(), perms.size() * 2, cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMemcpy(scene->d_halton_primes, primes.data(), kPrimes * 4, cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMemcpy(scene->d_halton_sums, sums.data(), kPrimes * 4, cudaMemcpyHostToDevice));
+    }
+    out->perms = (const uint16_t*)scene->d_halton_perms;
+    out->primes = (const uint32_t*)scene->d_halton_primes;
+    out->prime_sums = (const uint32_t*)scene->d_halton_sums;
+    const int res[2] = {sb_w, sb_h};
+    for (int i = 0; i < 2; ++i) {
+        const int base = i == 0 ? 2 : 3;
+        int scale = 1, exp = 0;
+        while (scale < std::min(128, res[i])) { scale *= base; ++exp; }                      // MAX_RESOLUTION, halton.rs:39,72-79
+        out->base_scales[i] = scale;
+        out->base_exponents[i] = exp;
+    }
+    out->sample_stride = (unsigned long long)out->base_scales[0] * (unsigned long long)out->base_scales[1];
+    out->mult_inverse[0] = halton_mult_inverse(out->base_scales[1], out->base_scales[0]);
+    out->mult_inverse[1] = halton_mult_inverse(out->base_scales[0], out->base_scales[1]);
+    return PB2_OK;
 }
 
 static int ensure_wavefront(pb2_scene* scene, uint64_t min_capacity) {
@@ -355,7 +425,10 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     rc = ensure_wavefront(scene, (uint64_t)fv.sb_w * fv.sb_h);
     if (rc) return rc;
     const PathParams pp{path->max_depth, path->rr_threshold};
-    wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, path->spp, path->sample_begin,
+    SamplerView smp;
+    rc = sampler_view(scene, path->sampler, fv.sb_w, fv.sb_h, &smp);
+    if (rc) return rc;
+    wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, path->sample_begin,
                      path->sample_end, (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;
@@ -378,6 +451,9 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     int32_t* d_xy = nullptr;
     uint32_t* d_s = nullptr;
     float *d_L = nullptr, *d_pf = nullptr;
+    SamplerView smp;
+    rc = sampler_view(scene, path->sampler, fv.sb_w, fv.sb_h, &smp);
+    if (rc) return rc;
     cudaError_t e = cudaMalloc(&d_xy, n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_s, n * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d_L, n * 12);
@@ -386,7 +462,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     if (e == cudaSuccess) e = cudaMemcpy(d_s, sample_index, n * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         const PathParams pp{path->max_depth, path->rr_threshold};
-        wavefront_li(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, path->spp, d_xy, d_s, n, d_L, d_pf, 0);
+        wavefront_li(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, d_xy, d_s, n, d_L, d_pf, 0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(L_rgb, d_L, n * 12, cudaMemcpyDeviceToHost);

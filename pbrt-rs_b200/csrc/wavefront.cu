@@ -41,6 +41,7 @@ __device__ __forceinline__ void queue_push(unsigned long long* counter, uint32_t
 // ---- slot <-> (pixel, sample) -----------------------------------------------------------------------------------
 struct SlotInfo {
     int x, y;                 // pixel in image coordinates (may lie outside the image for wide filters)
+    uint32_t sample;          // sample index of the pixel
     unsigned long long seq;   // sampler stream: ((y - sb_y0) * sb_w + (x - sb_x0)) * spp + sample
 };
 __device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& f, uint64_t slot) {
@@ -56,9 +57,83 @@ __device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& 
         s.x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w);
         s.y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
     }
+    s.sample = sample;
     s.seq = ((unsigned long long)(s.y - f.sb_y0) * (unsigned long long)f.sb_w + (unsigned long long)(s.x - f.sb_x0)) * (unsigned long long)m.spp + sample;
     return s;
 }
+
+// ---- samplers --------------------------------------------------------------------------------------------------------------
+// HaltonSampler (samplers/halton.rs, core/lowdiscrepancy.rs:293-390; pbrt-v3 semantics where the port is broken).
+__device__ __forceinline__ unsigned long long inverse_radical_inverse(unsigned base, unsigned long long inverse, int n_digits) {
+    unsigned long long index = 0;
+    for (int i = 0; i < n_digits; ++i) {
+        const unsigned long long digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
+}
+__device__ __forceinline__ long long halton_index(const SamplerView& h, int px, int py, unsigned long long sample_num) {    // halton.rs:117-141
+    long long offset = 0;
+    if (h.sample_stride > 1ull) {
+        const int pm0 = ((px % 128) + 128) % 128, pm1 = ((py % 128) + 128) % 128;
+        offset += (long long)(inverse_radical_inverse(2u, (unsigned long long)pm0, h.base_exponents[0]) *
+                              (h.sample_stride / (unsigned long long)h.base_scales[0]) * h.mult_inverse[0]);
+        offset += (long long)(inverse_radical_inverse(3u, (unsigned long long)pm1, h.base_exponents[1]) *
+                              (h.sample_stride / (unsigned long long)h.base_scales[1]) * h.mult_inverse[1]);
+        offset %= (long long)h.sample_stride;
+    }
+    return offset + (long long)(sample_num * h.sample_stride);
+}
+__device__ __forceinline__ float halton_dimension(const SamplerView& h, unsigned long long index, unsigned dim) {            // halton.rs:143-155
+    if (dim == 0u) return __ull2float_rn(__brevll(index >> h.base_exponents[0])) * 5.4210108624275222e-20f;
+    unsigned long long a = dim == 1u ? index / (unsigned long long)h.base_scales[1] : index;
+    const unsigned base = h.primes[dim];
+    const float inv_base = 1.0f / (float)base;
+    unsigned long long reversed = 0;
+    float inv_base_n = 1.0f;
+    if (dim == 1u) {                                                                       // radical_inverse, lowdiscrepancy.rs:293-305
+        while (a != 0ull) {
+            const unsigned long long next = a / base, digit = a - next * base;
+            reversed = reversed * base + digit;
+            inv_base_n = inv_base_n * inv_base;
+            a = next;
+        }
+        return fminf(__ull2float_rn(reversed) * inv_base_n, PB2_ONE_MINUS_EPS);
+    }
+    const uint16_t* perm = h.perms + h.prime_sums[dim];                                    // scramble_radical_inverse, :307-320
+    while (a != 0ull) {
+        const unsigned long long next = a / base, digit = a - next * base;
+        reversed = reversed * base + perm[digit];
+        inv_base_n = inv_base_n * inv_base;
+        a = next;
+    }
+    return fminf(inv_base_n * (__ull2float_rn(reversed) + inv_base * (float)perm[0] / (1.0f - inv_base)), PB2_ONE_MINUS_EPS);
+}
+// One path's sampler: the PCG32 stream of RandomSampler, or (index, dimension) of the Halton sequence.
+struct PathSampler {
+    Pcg32 rng;
+    unsigned long long index;
+    unsigned dim;
+    const SamplerView* h;
+    __device__ __forceinline__ bool halton() const { return h->perms != nullptr; }
+    __device__ __forceinline__ void start(const SamplerView& view, const SlotInfo& si) {   // start of a pixel sample
+        h = &view;
+        dim = 0u;
+        if (halton()) index = (unsigned long long)halton_index(view, si.x, si.y, si.sample);
+        else rng.set_sequence(si.seq);
+    }
+    __device__ __forceinline__ void resume(const SamplerView& view, const SlotInfo& si, unsigned long long saved) {
+        h = &view;
+        if (halton()) { index = (unsigned long long)halton_index(view, si.x, si.y, si.sample); dim = (unsigned)saved; }
+        else { rng.state = saved; rng.inc = (si.seq << 1) | 1ull; }
+    }
+    __device__ __forceinline__ unsigned long long save() const { return halton() ? (unsigned long long)dim : rng.state; }
+    __device__ __forceinline__ float next() {
+        if (halton()) return halton_dimension(*h, index, dim++);
+        return rng.next_float();
+    }
+};
 
 // ---- Camera::generate_ray (perspective.rs:90-112 + geometry.rs:865-881) ----------------------------------------------
 __device__ __forceinline__ vec3 cam_point(const mat4& m, vec3 p) {
@@ -97,12 +172,11 @@ __device__ void gen_camera_ray(const CameraView& cam, float fx, float fy, vec3* 
 __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, FilmView film, CameraView cam, PathBuffers b) {
     for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
         const SlotInfo si = slot_info(map, film, slot);
-        Pcg32 rng;
-        rng.set_sequence(si.seq);
-        const float u0 = rng.next_float(), u1 = rng.next_float();     // p_film offset (x then y)
-        (void)rng.next_float();                                       // time
-        (void)rng.next_float();                                       // p_lens
-        (void)rng.next_float();
+        PathSampler smp;
+        smp.start(map.smp, si);
+        const float u0 = smp.next(), u1 = smp.next();                 // p_film offset (x then y)
+        if (smp.halton()) smp.dim += 3u;                              // time, p_lens: drawn, never used (pinhole)
+        else { (void)smp.next(); (void)smp.next(); (void)smp.next(); }
         vec3 o, d;
         float t_max;
         gen_camera_ray(cam, (float)si.x + u0, (float)si.y + u1, &o, &d, &t_max);
@@ -110,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
         b.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
         b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
         b.L[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-        b.rng[slot] = rng.state;
+        b.rng[slot] = smp.save();
         b.q_active[0][slot] = (uint32_t)slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -389,19 +463,18 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
         if (alive) {
             const Bsdf bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
-            Pcg32 rng;
-            rng.state = b.rng[slot];
-            rng.inc = (slot_info(map, film, slot).seq << 1) | 1ull;
+            PathSampler rng;
+            rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot]);
             if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
                 float pick_pdf;
-                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next_float(), &pick_pdf);
+                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next(), &pick_pdf);
                 if (pick_pdf != 0.0f) {
-                    const float ul0 = rng.next_float(), ul1 = rng.next_float();
-                    const float us0 = rng.next_float(), us1 = rng.next_float();
+                    const float ul0 = rng.next(), ul1 = rng.next();
+                    const float us0 = rng.next(), us1 = rng.next();
                     direct_lighting(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
                 }
             }
-            const float u0 = rng.next_float(), u1 = rng.next_float();                     // path.rs:123-134
+            const float u0 = rng.next(), u1 = rng.next();                                 // path.rs:123-134
             vec3 wi = mk(0.f, 0.f, 0.f);
             float pdf = 0.0f;
             unsigned sampled = 0u;
@@ -418,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
                 const rgb3 rr_beta = beta * eta_scale;                                   // path.rs:200-207, D27 KEEP
                 if (max_channel(rr_beta) < pp.rr_threshold && bounces > 3u) {
                     const float q = fminf(1.0f - max_channel(rr_beta), 0.05f);
-                    if (rng.next_float() < q) alive = false;
+                    if (rng.next() < q) alive = false;
                     else beta = beta / (1.0f - q);
                 }
                 if (alive) {
@@ -426,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
                     b.ray_o[slot] = make_float4(o.x, o.y, o.z, kInf);
                     b.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, 0.0f);
                     b.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
-                    b.rng[slot] = rng.state;
+                    b.rng[slot] = rng.save();
                     Lf.w = __uint_as_float(bounces | ((spec ? 1u : 0u) << 16));
                     queue_push(&b.counters[C_ACTIVE_A + (cur ^ 1)], b.q_active[cur ^ 1], slot);
                 }
@@ -484,10 +557,10 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map,
             const float4 Lf = b.L[slot];
             const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
             const SlotInfo si = slot_info(map, f, slot);
-            Pcg32 rng;
-            rng.set_sequence(si.seq);
-            const float pfx = (float)x + rng.next_float();
-            const float pfy = (float)y + rng.next_float();
+            PathSampler rng;
+            rng.start(map.smp, si);
+            const float pfx = (float)x + rng.next();
+            const float pfy = (float)y + rng.next();
             film_footprint(f, pfx, pfy, [&](int px, int py, float fw) {
                 const rgb3 c = L * 1.0f * fw;                            // l * sample_weight * filter_weight
                 if (px == x && py == y) { acc.x += c.r; acc.y += c.g; acc.z += c.b; acc.w += fw; }
@@ -503,10 +576,10 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_atomic(uint64_t n,
         const float4 Lf = b.L[slot];
         const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
         const SlotInfo si = slot_info(map, f, slot);
-        Pcg32 rng;
-        rng.set_sequence(si.seq);
-        const float pfx = (float)si.x + rng.next_float();
-        const float pfy = (float)si.y + rng.next_float();
+        PathSampler rng;
+        rng.start(map.smp, si);
+        const float pfx = (float)si.x + rng.next();
+        const float pfy = (float)si.y + rng.next();
         film_footprint(f, pfx, pfy, [&](int px, int py, float fw) { film_atomic_add(f, px, py, L * 1.0f * fw, fw); });
     }
 }
@@ -572,10 +645,10 @@ __global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, fl
         const float4 Lf = b.L[slot];
         L_out[3 * slot] = Lf.x; L_out[3 * slot + 1] = Lf.y; L_out[3 * slot + 2] = Lf.z;
         const SlotInfo si = slot_info(map, f, slot);
-        Pcg32 rng;
-        rng.set_sequence(si.seq);
-        pf_out[2 * slot] = (float)si.x + rng.next_float();
-        pf_out[2 * slot + 1] = (float)si.y + rng.next_float();
+        PathSampler rng;
+        rng.start(map.smp, si);
+        pf_out[2 * slot] = (float)si.x + rng.next();
+        pf_out[2 * slot + 1] = (float)si.y + rng.next();
     }
 }
 
@@ -650,13 +723,13 @@ void wavefront_destroy(Wavefront* wf) {
 }
 
 int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
-                     const PathParams& pp, int spp, int sample_begin, int sample_end, cudaStream_t st) {
+                     const PathParams& pp, const SamplerView& smp, int spp, int sample_begin, int sample_end, cudaStream_t st) {
     const uint64_t n_pix = (uint64_t)film.sb_w * (uint64_t)film.sb_h;
     if (n_pix == 0 || sample_end <= sample_begin) return 0;
     const int per_batch = (int)std::max<uint64_t>(1, wf->capacity / n_pix);
     for (int s0 = sample_begin; s0 < sample_end; s0 += per_batch) {
         const int ns = std::min(per_batch, sample_end - s0);
-        PathMap map{(uint32_t)n_pix, spp, s0, nullptr, nullptr};
+        PathMap map{(uint32_t)n_pix, spp, s0, nullptr, nullptr, smp};
         const uint64_t n = n_pix * (uint64_t)ns;
         trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
         if (film.exact) k_film_accumulate_exact<<<grid_for(wf, n_pix), kThreads, 0, st>>>(map, film, wf->b, ns);
@@ -668,10 +741,10 @@ int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
 }
 
 int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
-                 const PathParams& pp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L, float* d_pfilm,
-                 cudaStream_t st) {
+                 const PathParams& pp, const SamplerView& smp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L,
+                 float* d_pfilm, cudaStream_t st) {
     if (n == 0) return 0;
-    PathMap map{(uint32_t)std::max<uint64_t>(1, n), spp, 0, d_xy, d_s};
+    PathMap map{(uint32_t)std::max<uint64_t>(1, n), spp, 0, d_xy, d_s, smp};
     trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
     k_copy_li<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, wf->b, d_L, d_pfilm);
     return 0;

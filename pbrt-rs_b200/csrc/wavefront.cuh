@@ -40,6 +40,16 @@ struct FilmView {
     uint32_t stray_capacity;
 };
 
+// HaltonSampler state shared by all paths (samplers/halton.rs:24-37 + the permutation table of lowdiscrepancy.rs:333-349);
+// perms == nullptr selects the RandomSampler streams.
+struct SamplerView {
+    const uint16_t* perms;        // RADICAL_INVERSE_PERMUTATIONS
+    const uint32_t* primes;       // first 1000 primes
+    const uint32_t* prime_sums;   // offset of every base's permutation
+    int base_scales[2], base_exponents[2];
+    unsigned long long sample_stride, mult_inverse[2];
+};
+
 // slot -> (pixel, sample index)
 struct PathMap {
     uint32_t n_pix;               // sample-bounds pixels per sample index
@@ -47,6 +57,7 @@ struct PathMap {
     int sample0;
     const int32_t* explicit_xy;   // pb2_path_li: explicit pixel coordinates, else null
     const uint32_t* explicit_s;
+    SamplerView smp;
 };
 
 enum Counter : int {
@@ -94,10 +105,10 @@ struct Wavefront {
 
 int wavefront_create(uint64_t capacity, Wavefront** out);
 int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
-                     const PathParams& pp, int spp, int sample_begin, int sample_end, cudaStream_t st);
+                     const PathParams& pp, const SamplerView& smp, int spp, int sample_begin, int sample_end, cudaStream_t st);
 int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
-                 const PathParams& pp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L, float* d_pfilm,
-                 cudaStream_t st);
+                 const PathParams& pp, const SamplerView& smp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L,
+                 float* d_pfilm, cudaStream_t st);
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
 void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st);

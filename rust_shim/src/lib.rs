@@ -20,7 +20,7 @@ pub struct pb2_camera { pub pos: [f32; 3], pub look: [f32; 3], pub up: [f32; 3],
 pub struct pb2_film_desc { pub res_x: i32, pub res_y: i32, pub filter: i32, pub radius_x: f32, pub radius_y: f32, pub gaussian_alpha: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_path_desc { pub max_depth: i32, pub rr_threshold: f32, pub light_strategy: i32, pub spp: i32,
-                           pub sample_begin: i32, pub sample_end: i32 }
+                           pub sample_begin: i32, pub sample_end: i32, pub sampler: i32 /* 0 RandomSampler, 1 HaltonSampler */ }
 pub enum pb2_scene {}
 pub enum pb2_film {}
 pub const PB2_MISS: u32 = 0xFFFF_FFFF;

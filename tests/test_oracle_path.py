@@ -71,3 +71,23 @@ def test_sincos_contract_accuracy(OP):
     s = np.array([OP.sincos(float(x)) for x in xs])
     assert np.abs(s[:, 0] - np.sin(xs.astype(np.float64))).max() < 2.5e-7
     assert np.abs(s[:, 1] - np.cos(xs.astype(np.float64))).max() < 2.5e-7
+
+
+def test_halton_known_answers(OP):
+    """HaltonSampler restatement (samplers/halton.rs, lowdiscrepancy.rs): radical inverses of small indices, the pixel
+    property of dimensions 0 / 1, and the permutation table being permutations."""
+    # base 2 / base 3 radical inverses through dimension 0 / 1 of a 1x1 image (scales 1, stride 1 => index = sample number)
+    idx, dims, perm = OP.halton_probe((1, 1), (0, 0), 0, n_dims=2, n_perm=2 + 3 + 5 + 7)
+    assert idx == 0 and dims[0] == 0.0 and dims[1] == 0.0
+    for s, (a, b) in {1: (0.5, 1 / 3), 2: (0.25, 2 / 3), 3: (0.75, 1 / 9), 4: (0.125, 4 / 9), 5: (0.625, 7 / 9)}.items():
+        idx, dims, _ = OP.halton_probe((1, 1), (0, 0), s, n_dims=2)
+        assert idx == s
+        assert dims[0] == np.float32(a) and abs(dims[1] - b) < 1e-7
+    assert sorted(perm[0:2]) == [0, 1] and sorted(perm[2:5]) == [0, 1, 2] and sorted(perm[5:10]) == list(range(5)) and sorted(perm[10:17]) == list(range(7))
+    # the sample index of pixel (x, y) puts dimensions 0 / 1 of EVERY sample of that pixel inside the pixel's cell of the
+    # 128 x 243 grid the sampler tiles the image with (halton.rs:117-141)
+    for px, py in [(0, 0), (3, 5), (127, 200), (500, 17), (511, 511)]:
+        for s in (0, 1, 7):
+            idx, dims, _ = OP.halton_probe((512, 512), (px, py), s, n_dims=8)
+            assert idx % (128 * 243) == OP.halton_probe((512, 512), (px, py), 0)[0] and idx // (128 * 243) == s
+            assert ((dims >= 0) & (dims < 1)).all()
