@@ -247,60 +247,77 @@ PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, 
     return ft / abs_cos_t(*wi);
 }
 
-struct Bsdf {
+// NL = the most lobes the material can have (1 for matte and glass, 2 for plastic): with NL = 1 every lobe index is the
+// constant 0, the lobe kind set by make_bsdf<MAT> is a compile-time constant and the lobe array lives in registers.
+template <int NL>
+struct BsdfT {
     float eta;
     vec3 ns, ng, ss, ts;
     int n;
-    Lobe lobes[2];
+    Lobe lobes[NL];
 };
+using Bsdf = BsdfT<2>;
 
-PB2_HD int bsdf_count(const Bsdf& b, unsigned flags) {
+template <int NL>
+PB2_HD int bsdf_count(const BsdfT<NL>& b, unsigned flags) {
     int c = 0;
-    for (int i = 0; i < b.n; ++i) c += lobe_matches(b.lobes[i], flags) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) c += (i < b.n && lobe_matches(b.lobes[i], flags)) ? 1 : 0;
     return c;
 }
-PB2_HD vec3 to_local(const Bsdf& b, vec3 v) { return mk(dot3(v, b.ss), dot3(v, b.ts), dot3(v, b.ns)); }
-PB2_HD vec3 to_world(const Bsdf& b, vec3 v) {                  // D34 FIX
+template <int NL>
+PB2_HD vec3 to_local(const BsdfT<NL>& b, vec3 v) { return mk(dot3(v, b.ss), dot3(v, b.ts), dot3(v, b.ns)); }
+template <int NL>
+PB2_HD vec3 to_world(const BsdfT<NL>& b, vec3 v) {                  // D34 FIX
     return mk((b.ss.x * v.x + b.ts.x * v.y) + b.ns.x * v.z, (b.ss.y * v.x + b.ts.y * v.y) + b.ns.y * v.z,
               (b.ss.z * v.x + b.ts.z * v.y) + b.ns.z * v.z);
 }
-PB2_HD rgb3 bsdf_sum_f(const Bsdf& b, vec3 wo, vec3 wi, bool refl, unsigned flags) {
+template <int NL>
+PB2_HD rgb3 bsdf_sum_f(const BsdfT<NL>& b, vec3 wo, vec3 wi, bool refl, unsigned flags) {
     rgb3 sum = gray(0.0f);
-    for (int i = 0; i < b.n; ++i) {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        if (i >= b.n) break;
         const Lobe& l = b.lobes[i];
         if (lobe_matches(l, flags) && ((refl && (l.type & kReflection)) || (!refl && (l.type & kTransmission)))) sum = sum + lobe_f(l, wo, wi);
     }
     return sum;
 }
-PB2_HD rgb3 bsdf_f(const Bsdf& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+template <int NL>
+PB2_HD rgb3 bsdf_f(const BsdfT<NL>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
     const vec3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0f) return gray(0.0f);
     const bool refl = dot3(wi_w, b.ng) * dot3(wo_w, b.ng) > 0.0f;
     return bsdf_sum_f(b, wo, wi, refl, flags);
 }
-PB2_HD float bsdf_pdf(const Bsdf& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+template <int NL>
+PB2_HD float bsdf_pdf(const BsdfT<NL>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
     if (b.n == 0) return 0.0f;
     const vec3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
     if (wo.z == 0.0f) return 0.0f;
     float p = 0.0f;
     int matching = 0;
-    for (int i = 0; i < b.n; ++i)
-        if (lobe_matches(b.lobes[i], flags)) { ++matching; p += lobe_pdf(b.lobes[i], wo, wi); }
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+        if (i < b.n && lobe_matches(b.lobes[i], flags)) { ++matching; p += lobe_pdf(b.lobes[i], wo, wi); }
     return matching > 0 ? p / (float)matching : 0.0f;
 }
 // BSDF::sample_f (:286-381).  *pdf must be pre-set by the caller (it is left untouched on the early exits, as in the reference).
-PB2_HD rgb3 bsdf_sample_f(const Bsdf& b, vec3 wo_w, vec3* wi_w, float u0, float u1, float* pdf, unsigned flags, unsigned* sampled) {
+template <int NL>
+PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, float u1, float* pdf, unsigned flags, unsigned* sampled) {
     const int matching = bsdf_count(b, flags);
     if (matching == 0) { *pdf = 0.0f; *sampled = 0u; return gray(0.0f); }
     int comp = (int)floorf(u0 * (float)matching);
     if (comp > matching - 1) comp = matching - 1;
     int count = comp, chosen = 0;
-    for (int i = 0; i < b.n; ++i)
-        if (lobe_matches(b.lobes[i], flags)) {
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+        if (i < b.n && lobe_matches(b.lobes[i], flags)) {
             if (count == 0) { chosen = i; break; }
             --count;
         }
-    const Lobe& bx = b.lobes[chosen];
+    // (a select, not lobes[chosen]: a run-time index would push the lobe array into local memory)
+    const Lobe bx = (NL > 1 && chosen == 1) ? b.lobes[NL - 1] : b.lobes[0];
     const float u0r = fminf(PB2_ONE_MINUS_EPS, u0 * (float)matching - (float)comp);
     vec3 wi = mk(0.0f, 0.0f, 0.0f);
     const vec3 wo = to_local(b, wo_w);
@@ -310,9 +327,11 @@ PB2_HD rgb3 bsdf_sample_f(const Bsdf& b, vec3 wo_w, vec3* wi_w, float u0, float 
     rgb3 fv = lobe_sample_f(bx, wo, &wi, u0r, u1, pdf, sampled);
     if (*pdf == 0.0f) { *sampled = 0u; return gray(0.0f); }
     *wi_w = to_world(b, wi);
-    if (!(bx.type & kSpecular) && matching > 1)
-        for (int i = 0; i < b.n; ++i)
-            if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    if (!(bx.type & kSpecular) && matching > 1) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+            if (i < b.n && i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    }
     if (matching > 1) *pdf = *pdf / (float)matching;
     if (!(bx.type & kSpecular)) {
         const bool refl = dot3(*wi_w, b.ng) * dot3(wo_w, b.ng) > 0.0f;
@@ -325,8 +344,8 @@ PB2_HD rgb3 bsdf_sample_f(const Bsdf& b, vec3 wo_w, vec3* wi_w, float u0, float 
 // `m` known at compile time (the wavefront shades one material type per launch, so the lobe kinds fold to constants and
 // the code of the other materials drops out of that launch's kernel); MAT < 0 reads m.type at run time.
 template <int MAT = -1>
-PB2_HD Bsdf make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
-    Bsdf b;
+PB2_HD BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
+    BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> b;
     const int type = MAT < 0 ? m.type : MAT;
     b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = n;

@@ -324,8 +324,9 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, uint32_t pr
 __device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
 
 // estimate_direct (integrator.rs:136-266) up to the two visibility queries: fills the NEE record of `slot`.
+template <class BsdfType>
 __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeView& sh, const PathBuffers& b, uint32_t slot, const Vertex& v, vec3 wo,
-                                                const Bsdf& bsdf, const DLight& light, float pick_pdf, float ul0, float ul1, float us0,
+                                                const BsdfType& bsdf, const DLight& light, float pick_pdf, float ul0, float ul1, float us0,
                                                 float us1, rgb3 beta) {
     const unsigned flags = kAllLobes & ~kSpecular;                       // D23 FIX
     const rgb3 l_emit = mkc(light.l[0], light.l[1], light.l[2]);
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
         }
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
         if (alive) {
-            const Bsdf bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
+            const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
             PathSampler rng;
             rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot]);
             if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
