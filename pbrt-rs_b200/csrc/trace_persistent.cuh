@@ -35,41 +35,22 @@ struct TraceTuning {
 #ifndef PB2_MIN_BLOCKS
 #define PB2_MIN_BLOCKS 8   /* 64 registers: 8 CTAs of 4 warps per SM (the quad step spills below that; profiles/r01_tuning.md) */
 #endif
-#ifndef PB2_FASTSLAB
-#define PB2_FASTSLAB 1
-#endif
-// PB2_QUAD 1: node steps read QuadNode records (two tree levels per fetch, half the dependent fetches and votes per
-// ray); 0: PairNode records (one level per fetch).  Both visit leaves in the reference's order (see quad_step).
-#ifndef PB2_QUAD
-#define PB2_QUAD 1
-#endif
+// Node steps read QuadNode records: two tree levels per fetch, half the dependent fetches and votes per ray of the
+// one-level PairNode walk this kernel used first (profiles/r01_tuning.md); leaves are still visited in the reference's order.
 constexpr int kQuadStackDepth = 96;         // <= 3 pushes per two levels of a tree at most 64 levels deep (bvh.rs:839)
 
 PB2_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Slab test for rays whose inverse direction is finite and non-zero on all three axes (every product below is then
-// an ordinary number or +-inf, never 0 * inf = NaN).  Without NaNs the reference's sequence of rejections and
-// conditional updates (geometry.rs:709-751) reduces to entry = max of the three near values, exit = min of the three
-// widened far values, accept iff entry <= exit and exit > 0: the two early rejections are exactly the six cross-axis
-// comparisons, and the three same-axis comparisons hold automatically whenever exit > 0 (far >= near before widening,
-// and widening a positive value never decreases it).  entry equals the reference's final t_min.
-PB2_D bool slab_entry_fast(const RayCtx& r, float lx, float ly, float lz, float hx, float hy, float hz, float* t_entry) {
-    const float widen = 1.0f + 2.0f * gammaf_(3.0f);
-    const float txn = ((r.nx ? hx : lx) - r.o.x) * r.inv.x;
-    const float txf = (((r.nx ? lx : hx) - r.o.x) * r.inv.x) * widen;
-    const float tyn = ((r.ny ? hy : ly) - r.o.y) * r.inv.y;
-    const float tyf = (((r.ny ? ly : hy) - r.o.y) * r.inv.y) * widen;
-    const float tzn = ((r.nz ? hz : lz) - r.o.z) * r.inv.z;
-    const float tzf = (((r.nz ? lz : hz) - r.o.z) * r.inv.z) * widen;
-    const float tn = fmaxf(fmaxf(txn, tyn), tzn);
-    const float tf = fminf(fminf(txf, tyf), tzf);
-    *t_entry = tn;
-    return tn <= tf && tf > 0.0f;
-}
 PB2_D bool finite_nonzero(float v) { return v != 0.0f && fabsf(v) < __int_as_float(0x7f800000); }
 
-// Entry distance of one child box for a ray on the slab fast path, +inf when the box is missed or starts beyond t_max
-// (geometry.rs:709-751 incl. its final clause).
+// Slab test for rays whose inverse direction is finite and non-zero on all three axes (every product below is then an
+// ordinary number or +-inf, never 0 * inf = NaN).  Without NaNs the reference's sequence of rejections and conditional
+// updates (geometry.rs:709-751) reduces to entry = max of the three near values, exit = min of the three widened far
+// values, accept iff entry <= exit, exit > 0 and entry < t_max: the two early rejections are exactly the six cross-axis
+// comparisons, and the three same-axis comparisons hold automatically whenever exit > 0 (far >= near before widening, and
+// widening a positive value never decreases it); entry equals the reference's final t_min.  Arguments: the near and far
+// planes of the box for this ray's direction signs.  Returns the entry distance, +inf when the box is missed or starts
+// beyond t_max.
 PB2_D float quad_child_entry(float nx, float ny, float nz, float fx, float fy, float fz, vec3 o, vec3 inv, float t_max) {
     const float widen = 1.0f + 2.0f * gammaf_(3.0f);
     const float tn = fmaxf(fmaxf((nx - o.x) * inv.x, (ny - o.y) * inv.y), (nz - o.z) * inv.z);
@@ -110,11 +91,7 @@ PB2_D RayCtx ctx_of(vec3 o, vec3 inv, vec3 sh, uint32_t flags) {
 template <bool ANY, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n, unsigned long long* __restrict__ counter,
                                                  const Sink& sink, const TraceTuning tune) {
-#if PB2_QUAD
     uint2 stack[kQuadStackDepth];            // {reference, entry distance bits}
-#else
-    uint2 stack[kStackDepth];                // {reference, entry distance bits}
-#endif
     int sp = 0;
     uint2 top = make_uint2(0u, 0u);          // register copy of stack[sp - 1]: a pop never waits for local memory
     uint32_t cur = kDone;
@@ -150,7 +127,6 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                                 fabsf(o.y) < inf && fabsf(o.z) < inf)
                                 flags |= kFlagPlain;
                             sp = 0;
-#if PB2_QUAD
                             if (!(flags & kFlagPlain)) {
                                 // A zero direction component makes 0 * inf = NaN possible in the slab test, and a NaN can
                                 // reject a box whose child it accepts; folding two levels relies on "child hit => parent
@@ -163,16 +139,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                                     sink.finish(ray_idx, found, found ? h.t : t_max);
                                 }
                             } else
-#endif
                             {
                                 float te;
                                 const bool enter = s.n_tris != 0 &&
                                     slab_entry(r, s.root_lo[0], s.root_lo[1], s.root_lo[2], s.root_hi[0], s.root_hi[1], s.root_hi[2], &te) && te < t_max;
-#if PB2_QUAD
                                 if (enter) cur = s.quad_root_ref;
-#else
-                                if (enter) cur = s.root_ref;
-#endif
                                 else if (ANY) sink.occluded(ray_idx, false);
                                 else sink.finish(ray_idx, false, t_max);
                             }
@@ -193,7 +164,6 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
             // keep the flag word opaque so the per-step decoding below is not hoisted into loop-carried registers
             asm volatile("" : "+r"(flags));
             if (n_leaf == 0 || (n_node >= tune.node_quorum && n_leaf < tune.leaf_quorum)) {
-#if PB2_QUAD
                 if (at_node) {
                     // One QuadNode = interior node P, its children A, B and their children.  bvh.rs:856-866 visits A's
                     // subtree before B's unless the ray is negative on axis(P), and inside A (B) the first child before
@@ -235,48 +205,6 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     if (h0 || h1 || h2 || h3) cur = h0 ? r0 : (h1 ? r1 : (h2 ? r2 : r3));
                     else need_pop = true;
                 }
-#else
-#if PB2_FASTSLAB
-                const bool all_plain = __ballot_sync(kFullMask, at_node && !(flags & kFlagPlain)) == 0u;
-#endif
-                if (at_node) {
-                    const RayCtx r = ctx_of(o, inv, sh, flags);
-                    const float4* np = s.pairs + 4ull * cur;
-                    const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
-                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(np + 3));
-                    float tl, tr;
-                    bool okl, okr;
-#if PB2_FASTSLAB
-                    if (all_plain) {
-                        okl = slab_entry_fast(r, a.x, a.y, a.z, a.w, b.x, b.y, &tl) && (tl < t_max);
-                        okr = slab_entry_fast(r, b.z, b.w, c.x, c.y, c.z, c.w, &tr) && (tr < t_max);
-                    } else
-#endif
-                    {
-                        okl = slab_entry(r, a.x, a.y, a.z, a.w, b.x, b.y, &tl) && (tl < t_max);
-                        okr = slab_entry(r, b.z, b.w, c.x, c.y, c.z, c.w, &tr) && (tr < t_max);
-                    }
-                    // bvh.rs:856-866: near child first, by the sign of the direction on the split axis
-                    const bool neg = ((flags >> m.z) & 1u) != 0u;
-                    const uint32_t near_ref = neg ? m.y : m.x, far_ref = neg ? m.x : m.y;
-                    const bool ok_near = neg ? okr : okl, ok_far = neg ? okl : okr;
-                    if (ok_near) {
-                        if (ok_far) {
-                            top = make_uint2(far_ref, __float_as_uint(neg ? tl : tr));
-                            stack[sp] = top;
-                            ++sp;
-                            if (tune.prefetch)
-                                prefetch_l2((far_ref & kLeafFlag) ? (const void*)(s.tris + 3ull * (far_ref & ~kLeafFlag))
-                                                                  : (const void*)(s.pairs + 4ull * far_ref));
-                        }
-                        cur = near_ref;
-                    } else if (ok_far) {
-                        cur = far_ref;
-                    } else {
-                        need_pop = true;
-                    }
-                }
-#endif
             } else if (cur != kDone && !at_node) {
                 // leaf triangles, in leaf order
                 const RayCtx r = ctx_of(o, inv, sh, flags);

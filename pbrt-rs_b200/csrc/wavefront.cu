@@ -85,29 +85,32 @@ __device__ __forceinline__ long long halton_index(const SamplerView& h, int px, 
     }
     return offset + (long long)(sample_num * h.sample_stride);
 }
+// Digit loop of radical_inverse_specialized / scramble_radical_inverse_specialized (lowdiscrepancy.rs:293-320): integer
+// digits are exact, so a 32-bit index (every practical frame: index < stride * spp) takes 32-bit divisions.
+template <class UInt, bool SCRAMBLED>
+__device__ __forceinline__ void halton_digits(UInt a, UInt base, const uint16_t* perm, float inv_base, unsigned long long* reversed, float* inv_base_n) {
+    while (a != 0) {
+        const UInt next = a / base, digit = a - next * base;
+        *reversed = *reversed * base + (SCRAMBLED ? (unsigned long long)perm[digit] : (unsigned long long)digit);
+        *inv_base_n = *inv_base_n * inv_base;
+        a = next;
+    }
+}
 __device__ __forceinline__ float halton_dimension(const SamplerView& h, unsigned long long index, unsigned dim) {            // halton.rs:143-155
     if (dim == 0u) return __ull2float_rn(__brevll(index >> h.base_exponents[0])) * 5.4210108624275222e-20f;
-    unsigned long long a = dim == 1u ? index / (unsigned long long)h.base_scales[1] : index;
+    const unsigned long long a = dim == 1u ? index / (unsigned long long)h.base_scales[1] : index;
     const unsigned base = h.primes[dim];
     const float inv_base = 1.0f / (float)base;
     unsigned long long reversed = 0;
     float inv_base_n = 1.0f;
-    if (dim == 1u) {                                                                       // radical_inverse, lowdiscrepancy.rs:293-305
-        while (a != 0ull) {
-            const unsigned long long next = a / base, digit = a - next * base;
-            reversed = reversed * base + digit;
-            inv_base_n = inv_base_n * inv_base;
-            a = next;
-        }
+    if (dim == 1u) {                                                                       // radical_inverse
+        if (a >> 32) halton_digits<unsigned long long, false>(a, base, nullptr, inv_base, &reversed, &inv_base_n);
+        else halton_digits<unsigned, false>((unsigned)a, base, nullptr, inv_base, &reversed, &inv_base_n);
         return fminf(__ull2float_rn(reversed) * inv_base_n, PB2_ONE_MINUS_EPS);
     }
-    const uint16_t* perm = h.perms + h.prime_sums[dim];                                    // scramble_radical_inverse, :307-320
-    while (a != 0ull) {
-        const unsigned long long next = a / base, digit = a - next * base;
-        reversed = reversed * base + perm[digit];
-        inv_base_n = inv_base_n * inv_base;
-        a = next;
-    }
+    const uint16_t* perm = h.perms + h.prime_sums[dim];                                    // scramble_radical_inverse
+    if (a >> 32) halton_digits<unsigned long long, true>(a, base, perm, inv_base, &reversed, &inv_base_n);
+    else halton_digits<unsigned, true>((unsigned)a, base, perm, inv_base, &reversed, &inv_base_n);
     return fminf(inv_base_n * (__ull2float_rn(reversed) + inv_base * (float)perm[0] / (1.0f - inv_base)), PB2_ONE_MINUS_EPS);
 }
 // One path's sampler: the PCG32 stream of RandomSampler, or (index, dimension) of the Halton sequence.
