@@ -200,6 +200,8 @@ static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_
     build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
     if (scene->bvh.max_depth > kStackDepth)
         return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
+    if (scene->bvh.leaf_overflow)
+        return set_error(PB2_ERR_LIMIT, "a leaf holds more than 65535 primitives with coincident centroids (16-bit n_primitives of the 32-byte node)");
     scene->n_nodes = scene->bvh.nodes.size();
     scene->n_prims = scene->bvh.ordered_prims.size();
     scene->tree_depth = scene->bvh.max_depth;

@@ -124,6 +124,7 @@ public:
         if (s.leaf) {
             out[me].offset = (uint32_t)start;      // leaves are emitted in order, so first_prim_offset == start
             out[me].n_prims = (uint16_t)(end - start);
+            if (end - start > 65535) leaf_overflow_.store(true);      // n_primitives is 16 bits in the 32-byte node
             out[me].axis = 0;
             out[me].pad = 0;
             return;
@@ -198,9 +199,11 @@ public:
         emit(root, out->nodes);
         out->ordered_prims.resize(n);
         for (size_t i = 0; i < n; ++i) out->ordered_prims[i] = refs_[i].id;
+        out->leaf_overflow = leaf_overflow_.load();
     }
 
 private:
+    std::atomic<bool> leaf_overflow_{false};
     std::vector<PrimRef>& refs_;
     int max_prims_;
     int threads_;

@@ -70,6 +70,7 @@ struct HostBVH {
     std::vector<LinearNode> nodes;          // reference layout (parity export)
     std::vector<uint32_t> ordered_prims;    // leaf order -> caller triangle id
     int max_depth = 0;                      // nodes on the longest root-to-leaf path
+    bool leaf_overflow = false;             // a leaf holds more primitives than LinearNode::n_prims (16 bits) can count
     // device layout
     std::vector<PairNode> pairs;
     std::vector<QuadNode> quads;

@@ -274,3 +274,26 @@ def test_split_method_errors(gpu, scenes):
     v, i = scenes.random_soup(100, seed=1)
     with pytest.raises(gpu.Pb2Error):
         gpu.BVHAccel(v, i, 4, split_method=2)       # Middle / EqualCounts are not built
+
+
+@pytest.mark.gpu
+def test_hlbvh_leaf_limit_is_an_error(gpu, scenes):
+    """LinearBVHNode::n_primitives is 16 bits (bvh.rs:129-135; pbrt-v3 CHECKs it): 70,000 triangles with one centroid cannot be
+    split by Morton bits (or by SAH: coincident centroids make a leaf, bvh.rs:320-334) and must be refused, not truncated;
+    60,000 fit, and the walk over that one fat leaf keeps the reference's tie rule."""
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    n = 70000
+    v = np.tile(tri, (n, 1))
+    i = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    scene = gpu.Scene(v, i)
+    for split in (1, 0):
+        with pytest.raises(gpu.Pb2Error):
+            gpu.BVHAccel(scene, max_prims_in_node=4, split_method=split)
+    n = 60000
+    accel = gpu.BVHAccel(gpu.Scene(v[:3 * n], i[:n]), max_prims_in_node=255, split_method=0)
+    rays = np.zeros((4, 8), np.float32)
+    rays[:, 0:3] = (0.25, 0.25, -1.0)
+    rays[:, 6] = 1.0
+    rays[:, 3] = np.inf
+    hits = accel.intersect(rays)
+    assert (hits["prim_id"] == n - 1).all() and (hits["t"] == 1.0).all()       # equal t: the last triangle tested wins

@@ -113,3 +113,16 @@ def test_quad_layout_walk_matches_reference_order(scene):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "quad_sim.py")] + scene, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches 0" in r.stdout
+
+
+def test_oversized_leaf_is_refused_not_truncated(pb2):
+    """70,000 triangles with one centroid end up in one SAH leaf (bvh.rs:320-334); the 32-byte node counts primitives in 16
+    bits, so the build must fail with PB2_ERR_LIMIT instead of dropping triangles."""
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    v = np.tile(tri, (70000, 1))
+    i = np.arange(3 * 70000, dtype=np.uint32).reshape(-1, 3)
+    with pytest.raises(pb2.Pb2Error) as e:
+        pb2.BVHAccel(v, i, 255, host_only=True)
+    assert e.value.code == -5
+    ok = pb2.BVHAccel(v[:3 * 60000], i[:60000], 255, host_only=True)
+    assert ok.info()[:2] == (1, 60000)
