@@ -58,14 +58,20 @@ typedef struct pb2_material {
     float eta;          /* glass index of refraction */
 } pb2_material;
 
-/* src/lights/point.rs PointLight; src/lights/diffuse.rs DiffuseAreaLight (one per emissive triangle). */
-enum { PB2_LIGHT_POINT = 0, PB2_LIGHT_AREA = 1 };
+/* src/lights/point.rs PointLight; src/lights/diffuse.rs DiffuseAreaLight (one per emissive triangle);
+ * src/lights/spot.rs SpotLight; src/lights/distant.rs DistantLight. */
+enum { PB2_LIGHT_POINT = 0, PB2_LIGHT_AREA = 1, PB2_LIGHT_SPOT = 2, PB2_LIGHT_DISTANT = 3 };
 typedef struct pb2_light {
     int32_t type;
-    float p[3];         /* point: position */
-    float i[3];         /* point: intensity I; area: emitted radiance L_emit */
+    float p[3];         /* point, spot: position (light_to_world * origin, point.rs:30, spot.rs:37) */
+    float i[3];         /* point, spot: intensity I; area: emitted radiance L_emit; distant: radiance L */
     uint32_t prim_id;   /* area: the emissive triangle */
     int32_t two_sided;  /* area */
+    float axis[3];      /* spot: third row of world_to_light's 3x3 block, the vector SpotLight::falloff projects onto
+                         * (spot.rs:51-53) = normalize(to - from) for pbrt's from/to spot light;
+                         * distant: the direction w TOWARDS the light (distant.rs:31; normalised by the library) */
+    float total_width;  /* spot: cone half-angle in degrees (spot.rs:38) */
+    float falloff_start;/* spot: half-angle where the falloff starts, degrees (spot.rs:39) */
 } pb2_light;
 
 /* src/cameras/perspective.rs:34-82 PerspectiveCamera (pinhole: lens_radius = 0) + Transform::look_at. */
@@ -90,7 +96,11 @@ enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1 };
 /* PB2_SAMPLER_RANDOM: RandomSampler (src/samplers/random.rs), one PCG32 stream per (pixel, sample).
  * PB2_SAMPLER_HALTON: HaltonSampler (src/samplers/halton.rs, src/core/lowdiscrepancy.rs:293-390) — every dimension is a pure
  * function of (pixel, sample index, dimension), so the per-sample values equal the reference's tile-ordered render. */
-enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1 };
+/* PB2_SAMPLER_STRATIFIED / PB2_SAMPLER_ZEROTWO: StratifiedSampler (src/samplers/stratified.rs), ZeroTwoSequenceSampler
+ * (src/samplers/zerotwosequence.rs) — PixelSamplers (src/core/sampler.rs:257-322): the first n_sampled_dimensions 1D and 2D
+ * dimensions of every pixel come from per-pixel tables of spp values generated on the device by Sampler::start_pixel from
+ * the stream RNG::new(n_pixels*spp + pixel); later dimensions fall back to the per-(pixel, sample) PCG32 stream. */
+enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1, PB2_SAMPLER_STRATIFIED = 2, PB2_SAMPLER_ZEROTWO = 3 };
 /* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
 typedef struct pb2_path_desc {
     int32_t max_depth;
@@ -100,6 +110,9 @@ typedef struct pb2_path_desc {
     int32_t sample_begin;       /* this call renders sample indices [sample_begin, sample_end) of every pixel */
     int32_t sample_end;
     int32_t sampler;            /* PB2_SAMPLER_* */
+    int32_t n_sampled_dimensions; /* stratified, (0,2): PixelSampler::new (sampler.rs:268); pbrt's default is 4 */
+    int32_t x_samples, y_samples; /* stratified: StratifiedSampler::new (stratified.rs:23-39); spp must equal x_samples * y_samples */
+    int32_t jitter;             /* stratified: jitter_samples */
 } pb2_path_desc;
 
 typedef struct pb2_scene pb2_scene;

@@ -57,13 +57,16 @@ struct MaterialDesc {
     Float kr[3], kt[3];
     Float eta;
 };
-enum { LIGHT_POINT = 0, LIGHT_AREA = 1 };
+enum { LIGHT_POINT = 0, LIGHT_AREA = 1, LIGHT_SPOT = 2, LIGHT_DISTANT = 3 };
 struct LightDesc {
     int32_t type;
     Float p[3];
     Float i[3];
     uint32_t prim_id;
     int32_t two_sided;
+    Float axis[3];          // spot: row 2 of world_to_light (spot.rs:52-53); distant: w (distant.rs:31)
+    Float total_width;      // spot, degrees (spot.rs:38)
+    Float falloff_start;    // spot, degrees (spot.rs:39)
 };
 struct CameraDesc {
     Float pos[3], look[3], up[3];
@@ -84,7 +87,11 @@ struct PathDesc {
     int32_t light_strategy;
     int32_t spp;
     int32_t sample_begin, sample_end;
-    int32_t sampler;          // 0 = RandomSampler (samplers/random.rs), 1 = HaltonSampler (samplers/halton.rs)
+    int32_t sampler;          // 0 = RandomSampler (samplers/random.rs), 1 = HaltonSampler (samplers/halton.rs),
+                              // 2 = StratifiedSampler (samplers/stratified.rs), 3 = ZeroTwoSequenceSampler (samplers/zerotwosequence.rs)
+    int32_t n_sampled_dimensions;   // PixelSampler::new (sampler.rs:268-284): tabulated 1D and 2D dimensions (kinds 2, 3)
+    int32_t x_samples, y_samples;   // StratifiedSampler::new (stratified.rs:23-39); spp == x_samples * y_samples
+    int32_t jitter;
 };
 
 // ---------------------------------------------------------------- sampling.rs:68-154 Distribution1D (D29 FIX, D57 KEEP, D58)
@@ -378,8 +385,18 @@ struct LightRt {
     LightDesc d;
     V3 p0, p1, p2;      // area: the emissive triangle
     Float area;
+    Float cos_total_width, cos_falloff_start;     // spot.rs:38-39
+    V3 w_light;                                   // distant.rs:31
+    Float world_radius;                           // distant.rs:73-77 pre_process
     RGB l() const { return {d.i[0], d.i[1], d.i[2]}; }
-    bool is_delta() const { return d.type == LIGHT_POINT; }                                  // light.rs:28-31, D24 FIX
+    bool is_delta() const { return d.type != LIGHT_AREA; }                                   // light.rs:28-31, D24 FIX
+    Float falloff(V3 w) const {                                                              // spot.rs:51-63
+        const Float cos_theta = (d.axis[0] * w.x + d.axis[1] * w.y) + d.axis[2] * w.z;       // (world_to_light * w).z, transform.rs:374-386
+        if (cos_theta < cos_total_width) return 0.0f;
+        if (cos_theta >= cos_falloff_start) return 1.0f;
+        const Float delta = (cos_theta - cos_total_width) / (cos_falloff_start - cos_total_width);
+        return (delta * delta) * (delta * delta);
+    }
 };
 
 struct MaterialRt {
@@ -410,6 +427,20 @@ public:
         for (uint32_t i = 0; i < n_lights; ++i) {
             lights[i].d = lts[i];
             lights[i].area = 0;
+            lights[i].cos_total_width = lights[i].cos_falloff_start = lights[i].world_radius = 0;
+            lights[i].w_light = V3{0, 0, 0};
+            if (lts[i].type == LIGHT_SPOT) {                                                   // spot.rs:38-39, pbrt.rs:133-135
+                lights[i].cos_total_width = std::cos(kPi / 180.0f * lts[i].total_width);
+                lights[i].cos_falloff_start = std::cos(kPi / 180.0f * lts[i].falloff_start);
+            }
+            if (lts[i].type == LIGHT_DISTANT) {
+                lights[i].w_light = normalize(V3{lts[i].axis[0], lts[i].axis[1], lts[i].axis[2]});   // distant.rs:31
+                // Light::pre_process (distant.rs:73-77) + Bounds3::bounding_sphere (geometry.rs:473-480)
+                const Bounds3 wb = bvh.world_bound();
+                const V3 c = (wb.mn + wb.mx) / 2.0f;
+                const bool inside = c.x >= wb.mn.x && c.x <= wb.mx.x && c.y >= wb.mn.y && c.y <= wb.mx.y && c.z >= wb.mn.z && c.z <= wb.mx.z;
+                lights[i].world_radius = inside ? length(c - wb.mx) : 0.0f;
+            }
             if (lts[i].type == LIGHT_AREA) {
                 bvh.tri(lts[i].prim_id, &lights[i].p0, &lights[i].p1, &lights[i].p2);
                 lights[i].area = length(cross(lights[i].p1 - lights[i].p0, lights[i].p2 - lights[i].p0)) * 0.5f;   // triangle.rs:323-328
@@ -423,8 +454,11 @@ public:
         if (strategy == LIGHTS_POWER && lights.size() != 1)
             for (size_t i = 0; i < lights.size(); ++i) {
                 const LightRt& l = lights[i];
-                RGB power = l.is_delta() ? l.l() * (4.0f * kPi)                                              // point.rs:68-70
-                                         : l.l() * ((l.d.two_sided ? 2.0f : 1.0f) * l.area * kPi);            // diffuse.rs:83-85
+                RGB power;
+                if (l.d.type == LIGHT_POINT) power = l.l() * (4.0f * kPi);                                      // point.rs:68-70
+                else if (l.d.type == LIGHT_SPOT) power = l.l() * (2.0f * kPi * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width)));   // spot.rs:87-89
+                else if (l.d.type == LIGHT_DISTANT) power = l.l() * (kPi * l.world_radius * l.world_radius);    // distant.rs:69-71
+                else power = l.l() * ((l.d.two_sided ? 2.0f : 1.0f) * l.area * kPi);                            // diffuse.rs:83-85
                 f[i] = y_value(power);
             }
         light_distrib.init(f);
@@ -614,21 +648,110 @@ struct HaltonTables {
     }
 };
 
+// PixelSampler (sampler.rs:257-322): n_sampled_dimensions tabulated 1D and 2D dimensions of spp values each, filled by
+// start_pixel of StratifiedSampler (samplers/stratified.rs:44-105) or ZeroTwoSequenceSampler (samplers/zerotwosequence.rs:31-63);
+// no sample arrays are requested on this path (PathIntegrator never calls request_*_array).  Where the port cannot run,
+// this follows pbrt-v3 (samplers/stratified.cpp, samplers/zerotwosequence.cpp, core/lowdiscrepancy.h):
+//   P1 lowdiscrepancy.rs:452-459 van_der_corput shuffles `samples[i * n_pixel_samples..]`: out of range for i >= 1  -> FIX (i * n_samples_per_pixel_sample)
+//   P2 stratified.rs:44-105 start_pixel never resets current_pixel_sample_index (no PixelSampler::start_pixel call)  -> FIX (reset)
+//   P3 sampler.rs:443-445 impl_pixel_sampler!::set_sample_number calls itself                                        -> FIX (PixelSampler's)
+//   P4 the second Sobol' generator matrix (lowdiscrepancy.rs:480-486) is generated (c[j] = c[j-1] ^ (c[j-1] >> 1)), not copied
+struct PixelTables {
+    int n_dims = 0, spp = 0;
+    std::vector<Float> t1, t2;                                   // t1[dim * spp + s]; t2[(dim * spp + s) * 2 + {0,1}]
+    void resize(int dims, int samples) { n_dims = dims; spp = samples; t1.assign((size_t)dims * samples, 0.0f); t2.assign((size_t)dims * samples * 2, 0.0f); }
+    static void shuffle1(Float* a, int count, int n_dimensions, RNG& rng) {                    // sampling.rs:280-287
+        for (int i = 0; i < count; ++i) {
+            const int other = i + (int)HaltonTables::uniform_u32_bounded(rng, (uint32_t)(count - i));
+            for (int j = 0; j < n_dimensions; ++j) std::swap(a[n_dimensions * i + j], a[n_dimensions * other + j]);
+        }
+    }
+    // StratifiedSampler::start_pixel (stratified.rs:44-76)
+    void start_pixel_stratified(RNG& rng, int xs, int ys, bool jitter) {
+        const int n = xs * ys;
+        for (int d = 0; d < n_dims; ++d) {
+            Float* a = t1.data() + (size_t)d * spp;
+            const Float inv_n = 1.0f / (Float)n;                                               // sampling.rs:11-17
+            for (int i = 0; i < n; ++i) {
+                const Float delta = jitter ? rng.uniform_float() : 0.5f;
+                a[i] = fmin_(kOneMinusEpsilon, ((Float)i + delta) * inv_n);
+            }
+            shuffle1(a, n, 1, rng);
+        }
+        for (int d = 0; d < n_dims; ++d) {
+            Float* a = t2.data() + (size_t)d * spp * 2;
+            const Float dx = 1.0f / (Float)xs, dy = 1.0f / (Float)ys;                          // sampling.rs:19-41
+            int i = 0;
+            for (int y = 0; y < ys; ++y)
+                for (int x = 0; x < xs; ++x) {
+                    Float jx = 0.5f, jy = 0.5f;
+                    if (jitter) { jx = rng.uniform_float(); jy = rng.uniform_float(); }
+                    a[2 * i] = fmin_(kOneMinusEpsilon, ((Float)x + jx) * dx);
+                    a[2 * i + 1] = fmin_(kOneMinusEpsilon, ((Float)y + jy) * dy);
+                    ++i;
+                }
+            shuffle1(a, n, 2, rng);                                                            // whole Point2f elements swap
+        }
+    }
+    // ZeroTwoSequenceSampler::start_pixel (zerotwosequence.rs:31-48) for n_samples_per_pixel_sample = 1
+    void start_pixel_zerotwo(RNG& rng) {
+        for (int d = 0; d < n_dims; ++d) {                                                     // van_der_corput, lowdiscrepancy.rs:436-460
+            Float* a = t1.data() + (size_t)d * spp;
+            uint32_t v = rng.uniform_u32();
+            for (int i = 0; i < spp; ++i) {                                                    // gray_code_sample :416-422, C[j] = 1 << (31 - j)
+                a[i] = fmin_(kOneMinusEpsilon, (Float)v * 2.3283064365386963e-10f);
+                v ^= 0x80000000u >> __builtin_ctz((uint32_t)(i + 1));
+            }
+            for (int i = 0; i < spp; ++i) shuffle1(a + i, 1, 1, rng);                          // P1 FIX
+            shuffle1(a, spp, 1, rng);
+        }
+        uint32_t c1[32];                                                                       // P4
+        c1[0] = 0x80000000u;
+        for (int j = 1; j < 32; ++j) c1[j] = c1[j - 1] ^ (c1[j - 1] >> 1);
+        for (int d = 0; d < n_dims; ++d) {                                                     // sobol_2d, lowdiscrepancy.rs:462-505
+            Float* a = t2.data() + (size_t)d * spp * 2;
+            uint32_t v0 = rng.uniform_u32(), v1 = rng.uniform_u32();
+            for (int i = 0; i < spp; ++i) {                                                    // gray_code_sample_2d :425-434
+                a[2 * i] = fmin_(kOneMinusEpsilon, (Float)v0 * 2.3283064365386963e-10f);
+                a[2 * i + 1] = fmin_(kOneMinusEpsilon, (Float)v1 * 2.3283064365386963e-10f);
+                const int tz = __builtin_ctz((uint32_t)(i + 1));
+                v0 ^= 0x80000000u >> tz;
+                v1 ^= c1[tz];
+            }
+            for (int i = 0; i < spp; ++i) shuffle1(a + 2 * i, 1, 2, rng);
+            shuffle1(a, spp, 2, rng);
+        }
+    }
+    void start_pixel(int kind, RNG& rng, const PathDesc& pd) {
+        if (kind == 2) start_pixel_stratified(rng, pd.x_samples, pd.y_samples, pd.jitter != 0);
+        else if (kind == 3) start_pixel_zerotwo(rng);
+    }
+};
+
 struct Sampler {          // kind 0: RandomSampler (samplers/random.rs:29-56), every dimension straight from PCG32;
     RNG rng;              // kind 1: HaltonSampler through GlobalSampler::get_1d/get_2d (sampler.rs:371-389; no sample arrays)
-    int kind = 0;
+    int kind = 0;         // kind 2 / 3: PixelSampler::get_1d/get_2d (sampler.rs:289-307): tables first, then `rng`
     const HaltonTables* halton = nullptr;
+    const PixelTables* tabs = nullptr;
     int64_t index = 0;
     int dimension = 0;
-    void start_sample(int px, int py, uint64_t sample_num) {   // start_pixel / set_sample_number (sampler.rs:347-350,405-409)
+    int cur1 = 0, cur2 = 0, sample_index = 0;                  // current_1d_dimension, current_2d_dimension, current_pixel_sample_index
+    void start_sample(int px, int py, uint64_t sample_num) {   // start_pixel / set_sample_number (sampler.rs:347-350,405-409,316-321)
         if (kind == 1) { index = halton->index_for_sample(px, py, sample_num); dimension = 0; }
+        if (kind >= 2) { cur1 = cur2 = 0; sample_index = (int)sample_num; }
     }
     Float get_1d() {
         if (kind == 1) return halton->sample_dimension(index, dimension++);
+        if (kind >= 2 && cur1 < tabs->n_dims) return tabs->t1[(size_t)(cur1++) * tabs->spp + sample_index];
         return rng.uniform_float();
     }
     void get_2d(Float* a, Float* b) {                          // x then y
         if (kind == 1) { *a = halton->sample_dimension(index, dimension); *b = halton->sample_dimension(index, dimension + 1); dimension += 2; return; }
+        if (kind >= 2 && cur2 < tabs->n_dims) {
+            const size_t o = ((size_t)(cur2++) * tabs->spp + sample_index) * 2;
+            *a = tabs->t2[o]; *b = tabs->t2[o + 1];
+            return;
+        }
         *a = rng.uniform_float();
         *b = rng.uniform_float();
     }
@@ -644,11 +767,18 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
     RGB li = rgb(0);
     Ray shadow{};
     // ---- Light::sample_li ----
-    if (light.is_delta()) {                                                                    // point.rs:47-66
+    if (light.is_delta()) {                                                                    // point.rs:47-66, spot.rs:71-85, distant.rs:50-67
         V3 pl{light.d.p[0], light.d.p[1], light.d.p[2]};
-        wi = normalize(pl - it.p);
         light_pdf = 1.0f;
-        li = light.l() / length_squared(pl - it.p);
+        if (light.d.type == LIGHT_DISTANT) {
+            wi = light.w_light;
+            pl = it.p + light.w_light * (2.0f * light.world_radius);                           // p_outside
+            li = light.l();
+        } else {
+            wi = normalize(pl - it.p);
+            if (light.d.type == LIGHT_SPOT) li = light.l() * light.falloff(-wi) / length_squared(pl - it.p);
+            else li = light.l() / length_squared(pl - it.p);
+        }
         // VisibilityTester: spawn_ray_to(&BaseInteraction) with a bare point (interaction.rs:146-153)
         V3 origin = offset_ray_origin(it.p, it.error, it.n, pl - it.p);
         V3 target = offset_ray_origin(pl, V3{0, 0, 0}, V3{0, 0, 0}, origin - pl);
@@ -860,12 +990,22 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
             int x0 = film.sb_x0 + tx * 16, x1 = std::min(x0 + 16, film.sb_x1);
             int y0 = film.sb_y0 + ty * 16, y1 = std::min(y0 + 16, film.sb_y1);
             // mode 0 accumulates into a tile-local buffer first (FilmTile), merged below
+            PixelTables tabs;
+            if (pd.sampler >= 2) tabs.resize(pd.n_sampled_dimensions, pd.spp);
+            tile_sampler.tabs = &tabs;
             for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x)
+                for (int x = x0; x < x1; ++x) {
+                    if (pd.sampler >= 2) {                                                      // Sampler::start_pixel (integrator.rs:433)
+                        // mode 1: the tables of a pixel come from their own stream, RNG::new(W*H*spp + pixel index)
+                        RNG table_rng;
+                        table_rng.set_sequence((uint64_t)W * H * (uint64_t)pd.spp + ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)));
+                        tabs.start_pixel(pd.sampler, mode == 1 ? table_rng : tile_sampler.rng, pd);
+                    }
                     for (int s = pd.sample_begin; s < pd.sample_end; ++s) {
                         Sampler own;
                         own.kind = pd.sampler;
                         own.halton = &halton;
+                        own.tabs = &tabs;
                         uint64_t order = ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)) * (uint64_t)pd.spp + (uint64_t)s;
                         if (mode == 1) own.rng.set_sequence(order);
                         Sampler& smp = mode == 1 ? own : tile_sampler;
@@ -888,6 +1028,7 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                             wsum[o] += fw;
                         });
                     }
+                }
         }
     };
     std::vector<std::thread> pool;

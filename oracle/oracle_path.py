@@ -17,7 +17,7 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("p", C.c_float * 3), ("i", C.c_float * 3), ("prim_id", C.c_uint32),
-                ("two_sided", C.c_int32)]
+                ("two_sided", C.c_int32), ("axis", C.c_float * 3), ("total_width", C.c_float), ("falloff_start", C.c_float)]
 
 
 class CameraDesc(C.Structure):
@@ -32,10 +32,11 @@ class FilmDesc(C.Structure):
 
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32)]
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32),
+                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
 
 
-_SAMPLER = {"random": 0, "halton": 1}
+_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2}
 _STRAT = {"uniform": 0, "power": 1}
 _FILTER = {"box": 0, "gaussian": 1}
@@ -60,6 +61,17 @@ def light(d):
         l.type = 0
         l.p[:] = d["p"]
         l.i[:] = d["I"]
+    elif d["type"] == "spot":          # axis = row 2 of world_to_light = normalize(to - from) for pbrt's from/to spot light
+        l.type = 2
+        l.p[:] = d["p"]
+        l.i[:] = d["I"]
+        l.axis[:] = d["axis"]
+        l.total_width = d["total_width"]
+        l.falloff_start = d["falloff_start"]
+    elif d["type"] == "distant":
+        l.type = 3
+        l.i[:] = d["L"]
+        l.axis[:] = d["w"]
     else:
         l.type = 1
         l.i[:] = d["L"]
@@ -87,7 +99,8 @@ def film_desc(res, filt="box", radius=(0.5, 0.5), alpha=2.0):
     return f
 
 
-def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None, sampler="random"):
+def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None, sampler="random",
+              n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True):
     p = PathDesc()
     p.max_depth = max_depth
     p.rr_threshold = rr_threshold
@@ -96,7 +109,21 @@ def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sa
     p.sample_begin = sample_begin
     p.sample_end = spp if sample_end is None else sample_end
     p.sampler = _SAMPLER[sampler]
+    p.n_sampled_dimensions = n_sampled_dimensions
+    p.x_samples, p.y_samples, p.jitter = x_samples, y_samples, int(jitter)
+    if sampler == "stratified":
+        assert x_samples * y_samples == spp, "StratifiedSampler: spp = x_samples * y_samples (stratified.rs:31-32)"
+    if sampler == "zerotwo":
+        assert spp & (spp - 1) == 0, "ZeroTwoSequenceSampler rounds spp up to a power of two (zerotwosequence.rs:21); pass the rounded value"
     return p
+
+
+def pixel_tables(path, table_sequence):
+    """PixelSampler tables of one pixel: (t1 [n_dims, spp], t2 [n_dims, spp, 2])."""
+    t1 = np.zeros((path.n_sampled_dimensions, path.spp), np.float32)
+    t2 = np.zeros((path.n_sampled_dimensions, path.spp, 2), np.float32)
+    O.lib().orc_pixel_tables(C.byref(path), C.c_uint64(int(table_sequence)), _p(t1), _p(t2))
+    return t1, t2
 
 
 def halton_probe(res, pixel, sample_num, n_dims=8, n_perm=32):

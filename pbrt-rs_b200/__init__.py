@@ -20,7 +20,7 @@ NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_pri
                        ("pad", np.uint8)])
 
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS = 0, 1, 2
-LIGHT_POINT, LIGHT_AREA = 0, 1
+LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
 
@@ -38,7 +38,7 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("p", C.c_float * 3), ("i", C.c_float * 3), ("prim_id", C.c_uint32),
-                ("two_sided", C.c_int32)]
+                ("two_sided", C.c_int32), ("axis", C.c_float * 3), ("total_width", C.c_float), ("falloff_start", C.c_float)]
 
 
 class CameraDesc(C.Structure):
@@ -53,10 +53,11 @@ class FilmDesc(C.Structure):
 
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32)]
+                ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32),
+                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
 
 
-_SAMPLER = {"random": 0, "halton": 1}
+_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
 
 
 def matte(kd):
@@ -90,6 +91,29 @@ def point_light(p, intensity):
     l.type = LIGHT_POINT
     l.p[:] = p
     l.i[:] = intensity
+    return l
+
+
+def spot_light(p, axis, intensity, total_width, falloff_start):
+    """src/lights/spot.rs SpotLight::new: `axis` is the third row of world_to_light (normalize(to - from) for pbrt's from/to
+    spot light), `total_width` / `falloff_start` the cone half-angles in degrees."""
+    l = Light()
+    l.type = LIGHT_SPOT
+    l.p[:] = p
+    l.i[:] = intensity
+    l.axis[:] = axis
+    l.total_width = total_width
+    l.falloff_start = falloff_start
+    return l
+
+
+def distant_light(w, radiance):
+    """src/lights/distant.rs DistantLight::new: `w` points towards the light; the scene's bounding sphere (pre_process) is
+    taken from the BVH's world bound when the scene is built."""
+    l = Light()
+    l.type = LIGHT_DISTANT
+    l.i[:] = radiance
+    l.axis[:] = w
     return l
 
 
@@ -345,6 +369,10 @@ def material_from_dict(d):
 def light_from_dict(d):
     if d["type"] == "point":
         return point_light(d["p"], d["I"])
+    if d["type"] == "spot":
+        return spot_light(d["p"], d["axis"], d["I"], d["total_width"], d["falloff_start"])
+    if d["type"] == "distant":
+        return distant_light(d["w"], d["L"])
     return area_light(d["prim"], d["L"], d.get("two_sided", False))
 
 
@@ -410,9 +438,16 @@ class Film:
 
 class PathIntegrator:
     """Mirror of src/integrators/path.rs PathIntegrator + SamplerIntegrator::render; sampler = "random" (RandomSampler streams
-    per (pixel, sample)) or "halton" (HaltonSampler, src/samplers/halton.rs)."""
+    per (pixel, sample)), "halton" (HaltonSampler, src/samplers/halton.rs), "stratified" (StratifiedSampler::new(x_samples,
+    y_samples, jitter, n_sampled_dimensions), src/samplers/stratified.rs) or "zerotwo" (ZeroTwoSequenceSampler::new(spp,
+    n_sampled_dimensions), src/samplers/zerotwosequence.rs: spp is rounded up to a power of two as the constructor does)."""
 
-    def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sampler="random"):
+    def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sampler="random",
+                 n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True):
+        if sampler == "zerotwo":
+            spp = 1 << max(0, int(spp) - 1).bit_length()             # round_up_pow2_i64, zerotwosequence.rs:21
+        if sampler == "stratified" and x_samples and y_samples:
+            spp = x_samples * y_samples                              # stratified.rs:31-32
         self.accel, self.camera = accel, camera
         self.desc = PathDesc()
         self.desc.max_depth = max_depth
@@ -421,6 +456,9 @@ class PathIntegrator:
         self.desc.spp = spp
         self.desc.sample_begin, self.desc.sample_end = 0, spp
         self.desc.sampler = _SAMPLER[sampler]
+        self.desc.n_sampled_dimensions = n_sampled_dimensions
+        self.desc.x_samples, self.desc.y_samples, self.desc.jitter = x_samples, y_samples, int(jitter)
+        self.spp = spp
 
     def render(self, film, sample_begin=0, sample_end=None, stream=None):
         """Integrator::render: accumulates sample indices [sample_begin, sample_end) of every pixel into `film`."""

@@ -71,6 +71,9 @@ void pb2_scene::free_device() {
     if (d_halton_primes) cudaFree(d_halton_primes);
     if (d_halton_sums) cudaFree(d_halton_sums);
     d_halton_perms = d_halton_primes = d_halton_sums = nullptr;
+    if (d_tab1) cudaFree(d_tab1);
+    if (d_tab2) cudaFree(d_tab2);
+    d_tab1 = d_tab2 = nullptr;
 }
 
 extern "C" {
@@ -163,7 +166,12 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
     for (uint32_t i = 0; i < n_lights; ++i) {
         if (lights[i].type == PB2_LIGHT_AREA && lights[i].prim_id >= n_tris)
             return set_error(PB2_ERR_INVALID, "area light %u references triangle %u >= %llu", i, lights[i].prim_id, (unsigned long long)n_tris);
-        if (lights[i].type != PB2_LIGHT_AREA && lights[i].type != PB2_LIGHT_POINT) return set_error(PB2_ERR_INVALID, "light %u has unknown type %d", i, lights[i].type);
+        if (lights[i].type < PB2_LIGHT_POINT || lights[i].type > PB2_LIGHT_DISTANT) return set_error(PB2_ERR_INVALID, "light %u has unknown type %d", i, lights[i].type);
+        if (lights[i].type == PB2_LIGHT_DISTANT || lights[i].type == PB2_LIGHT_SPOT) {
+            const float* a = lights[i].axis;
+            if (!(std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2])) || (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f))
+                return set_error(PB2_ERR_INVALID, "light %u needs a finite non-zero axis", i);
+        }
     }
     pb2_scene* s = new pb2_scene();
     s->verts.assign(verts, verts + 3 * n_verts);

@@ -91,6 +91,10 @@ struct pb2_scene {
     void* d_halton_perms = nullptr;
     void* d_halton_primes = nullptr;
     void* d_halton_sums = nullptr;
+    // PixelSampler tables (stratified / (0,2)) and the parameters they were generated for
+    void* d_tab1 = nullptr;
+    void* d_tab2 = nullptr;
+    long long tab_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void free_device();
 };

@@ -103,6 +103,21 @@ int upload_shading_tables(pb2_scene* scene) {
             d.area = len(cross3(p1 - p0, p2 - p0)) * 0.5f;               // triangle.rs:323-328
             tri_light[l.prim_id] = (int32_t)i;
             pw = mkc(l.i[0], l.i[1], l.i[2]) * ((l.two_sided ? 2.0f : 1.0f) * d.area * PB2_PI);      // diffuse.rs:83-85
+        } else if (l.type == PB2_LIGHT_SPOT) {                           // spot.rs:30-49
+            for (int k = 0; k < 3; ++k) d.axis[k] = l.axis[k];
+            d.cos_total_width = std::cos(PB2_PI / 180.0f * l.total_width);       // radians(), pbrt.rs:133-135
+            d.cos_falloff_start = std::cos(PB2_PI / 180.0f * l.falloff_start);
+            pw = mkc(l.i[0], l.i[1], l.i[2]) * (2.0f * PB2_PI * (1.0f - 0.5f * (d.cos_falloff_start + d.cos_total_width)));      // spot.rs:87-89
+        } else if (l.type == PB2_LIGHT_DISTANT) {                        // distant.rs:29-45
+            const vec3 w = unit(mk(l.axis[0], l.axis[1], l.axis[2]));
+            d.axis[0] = w.x; d.axis[1] = w.y; d.axis[2] = w.z;
+            // Light::pre_process (distant.rs:73-77) + Bounds3::bounding_sphere (geometry.rs:473-480) of the scene's world bound
+            const float* rb = scene->root_bounds;
+            const vec3 lo = mk(rb[0], rb[1], rb[2]), hi = mk(rb[3], rb[4], rb[5]);
+            const vec3 c = (lo + hi) / 2.0f;
+            const bool inside = c.x >= lo.x && c.x <= hi.x && c.y >= lo.y && c.y <= hi.y && c.z >= lo.z && c.z <= hi.z;
+            d.world_radius = inside ? len(c - hi) : 0.0f;
+            pw = mkc(l.i[0], l.i[1], l.i[2]) * (PB2_PI * d.world_radius * d.world_radius);       // distant.rs:69-71
         } else {
             pw = mkc(l.i[0], l.i[1], l.i[2]) * (4.0f * PB2_PI);          // point.rs:68-70
         }
@@ -157,8 +172,16 @@ static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_pa
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
     if (path->light_strategy != PB2_LIGHTS_UNIFORM && path->light_strategy != PB2_LIGHTS_POWER)
         return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
-    if (path->sampler != PB2_SAMPLER_RANDOM && path->sampler != PB2_SAMPLER_HALTON)
+    if (path->sampler < PB2_SAMPLER_RANDOM || path->sampler > PB2_SAMPLER_ZEROTWO)
         return set_error(PB2_ERR_INVALID, "unknown sampler %d", path->sampler);
+    if (path->sampler >= PB2_SAMPLER_STRATIFIED) {
+        if (path->n_sampled_dimensions < 0 || path->n_sampled_dimensions > 127)
+            return set_error(PB2_ERR_INVALID, "n_sampled_dimensions %d outside [0, 127]", path->n_sampled_dimensions);
+        if (path->sampler == PB2_SAMPLER_STRATIFIED && (path->x_samples <= 0 || path->y_samples <= 0 || (long long)path->x_samples * path->y_samples != path->spp))
+            return set_error(PB2_ERR_INVALID, "StratifiedSampler: spp %d != x_samples %d * y_samples %d (stratified.rs:31-32)", path->spp, path->x_samples, path->y_samples);
+        if (path->sampler == PB2_SAMPLER_ZEROTWO && (path->spp & (path->spp - 1)) != 0)
+            return set_error(PB2_ERR_INVALID, "ZeroTwoSequenceSampler: spp %d is not a power of two (zerotwosequence.rs:21 rounds up; pass the rounded count)", path->spp);
+    }
     if (path->sampler == PB2_SAMPLER_HALTON && 5 + 8 * (path->max_depth + 1) > 1000)      // lowdiscrepancy.rs:11 PRIME_TABLE_SIZE
         return set_error(PB2_ERR_LIMIT, "HaltonSampler has 1000 dimensions; max_depth %d needs %d", path->max_depth, 5 + 8 * (path->max_depth + 1));
     if (fd && (cam->res_x != fd->res_x || cam->res_y != fd->res_y)) return set_error(PB2_ERR_INVALID, "camera and film resolutions differ");
@@ -179,8 +202,46 @@ static uint64_t halton_mult_inverse(int64_t a, int64_t n) {                     
     const int64_t r = x - (x / n) * n;
     return (uint64_t)(r < 0 ? r + n : r);
 }
-static int sampler_view(pb2_scene* scene, int sampler, int sb_w, int sb_h, SamplerView* out) {
+// PixelSampler tables (stratified / (0,2)): generated on the device once per (sampler parameters, sample-bounds extent) and
+// kept with the scene; a frame rendered in several pb2_render_path calls (sample ranges) reuses them.
+static int pixel_sampler_tables(pb2_scene* scene, const pb2_path_desc* path, int sb_w, int sb_h, cudaStream_t st, SamplerView* out) {
+    const uint64_t n_pix = (uint64_t)sb_w * (uint64_t)sb_h;
+    const uint64_t entries = n_pix * (uint64_t)path->spp * (uint64_t)path->n_sampled_dimensions;
+    if (entries >= (1ull << 32))
+        return set_error(PB2_ERR_LIMIT, "PixelSampler tables: %llu pixels x %d spp x %d dimensions exceed 2^32 entries (12 bytes each); render in tiles of fewer pixels",
+                         (unsigned long long)n_pix, path->spp, path->n_sampled_dimensions);
+    const long long key[8] = {path->sampler, path->spp, path->n_sampled_dimensions, path->sampler == PB2_SAMPLER_STRATIFIED ? path->x_samples : 0,
+                              path->sampler == PB2_SAMPLER_STRATIFIED ? path->y_samples : 0,
+                              path->sampler == PB2_SAMPLER_STRATIFIED ? (path->jitter != 0) : 0, sb_w, sb_h};
+    if (!scene->d_tab1 || memcmp(key, scene->tab_key, sizeof key) != 0) {
+        if (scene->d_tab1) { cudaFree(scene->d_tab1); scene->d_tab1 = nullptr; }
+        if (scene->d_tab2) { cudaFree(scene->d_tab2); scene->d_tab2 = nullptr; }
+        cudaError_t e = cudaMalloc(&scene->d_tab1, std::max<uint64_t>(entries, 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&scene->d_tab2, std::max<uint64_t>(entries, 1) * 8);
+        if (e != cudaSuccess) {
+            cudaFree(scene->d_tab1); scene->d_tab1 = nullptr; scene->d_tab2 = nullptr;
+            (void)cudaGetLastError();
+            return set_error(PB2_ERR_LIMIT, "PixelSampler tables need %.1f GB of device memory: %s", (double)entries * 12e-9, cudaGetErrorString(e));
+        }
+        // table stream of pixel p: RNG::new(n_pix * spp + p), disjoint from the per-(pixel, sample) streams [0, n_pix * spp)
+        pixel_tables_generate(path->sampler, (uint32_t)n_pix, path->spp, path->n_sampled_dimensions, path->x_samples, path->y_samples, path->jitter != 0,
+                              n_pix * (uint64_t)path->spp, (float*)scene->d_tab1, (float2*)scene->d_tab2, st);
+        PB2_CUDA(cudaGetLastError());
+        memcpy(scene->tab_key, key, sizeof key);
+    }
+    out->n_dims = path->n_sampled_dimensions;
+    out->spp_tab = path->spp;
+    out->tab_n_pix = (uint32_t)n_pix;
+    out->t1 = (const float*)scene->d_tab1;
+    out->t2 = (const float2*)scene->d_tab2;
+    return PB2_OK;
+}
+
+static int sampler_view(pb2_scene* scene, const pb2_path_desc* path, int sb_w, int sb_h, cudaStream_t st, SamplerView* out) {
     memset(out, 0, sizeof *out);
+    const int sampler = path->sampler;
+    out->kind = sampler;
+    if (sampler >= PB2_SAMPLER_STRATIFIED) return pixel_sampler_tables(scene, path, sb_w, sb_h, st, out);
     if (sampler != PB2_SAMPLER_HALTON) return PB2_OK;
     if (!scene->d_halton_perms) {
         constexpr int kPrimes = 1000;                                                        // lowdiscrepancy.rs:11
@@ -426,7 +487,7 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     if (rc) return rc;
     const PathParams pp{path->max_depth, path->rr_threshold};
     SamplerView smp;
-    rc = sampler_view(scene, path->sampler, fv.sb_w, fv.sb_h, &smp);
+    rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
     if (rc) return rc;
     wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, path->sample_begin,
                      path->sample_end, (cudaStream_t)stream);
@@ -452,7 +513,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     uint32_t* d_s = nullptr;
     float *d_L = nullptr, *d_pf = nullptr;
     SamplerView smp;
-    rc = sampler_view(scene, path->sampler, fv.sb_w, fv.sb_h, &smp);
+    rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, 0, &smp);
     if (rc) return rc;
     cudaError_t e = cudaMalloc(&d_xy, n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_s, n * 4);

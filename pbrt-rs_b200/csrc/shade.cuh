@@ -181,6 +181,9 @@ struct DLight {
     int two_sided;
     float area;
     float p0[3], p1[3], p2[3];
+    float axis[3];          // spot: row 2 of world_to_light (spot.rs:52-53); distant: w_light (distant.rs:31)
+    float cos_total_width, cos_falloff_start;   // spot.rs:38-39
+    float world_radius;     // distant.rs:73-77
 };
 
 enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u };

@@ -43,6 +43,7 @@ struct SlotInfo {
     int x, y;                 // pixel in image coordinates (may lie outside the image for wide filters)
     uint32_t sample;          // sample index of the pixel
     unsigned long long seq;   // sampler stream: ((y - sb_y0) * sb_w + (x - sb_x0)) * spp + sample
+    uint32_t pix;             // (y - sb_y0) * sb_w + (x - sb_x0)
 };
 __device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& f, uint64_t slot) {
     SlotInfo s;
@@ -58,7 +59,9 @@ __device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& 
         s.y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
     }
     s.sample = sample;
-    s.seq = ((unsigned long long)(s.y - f.sb_y0) * (unsigned long long)f.sb_w + (unsigned long long)(s.x - f.sb_x0)) * (unsigned long long)m.spp + sample;
+    const unsigned long long pix = (unsigned long long)(s.y - f.sb_y0) * (unsigned long long)f.sb_w + (unsigned long long)(s.x - f.sb_x0);
+    s.pix = (uint32_t)pix;
+    s.seq = pix * (unsigned long long)m.spp + sample;
     return s;
 }
 
@@ -113,30 +116,147 @@ __device__ __forceinline__ float halton_dimension(const SamplerView& h, unsigned
     else halton_digits<unsigned, true>((unsigned)a, base, perm, inv_base, &reversed, &inv_base_n);
     return fminf(inv_base_n * (__ull2float_rn(reversed) + inv_base * (float)perm[0] / (1.0f - inv_base)), PB2_ONE_MINUS_EPS);
 }
-// One path's sampler: the PCG32 stream of RandomSampler, or (index, dimension) of the Halton sequence.
+// One path's sampler.  RandomSampler: the PCG32 stream; HaltonSampler: (index, dimension) of the sequence; PixelSamplers
+// (stratified, (0,2)): PixelSampler::get_1d / get_2d (sampler.rs:289-307) — the next tabulated dimension of this pixel's
+// sample while one is left, then the PCG32 stream.  TABLES = false compiles the table branch out (k_shade is at its register limit).
 struct PathSampler {
     Pcg32 rng;
     unsigned long long index;
     unsigned dim;
+    unsigned cur1, cur2;          // current_1d_dimension, current_2d_dimension
+    unsigned tab_base;            // sample * tab_n_pix + pixel
     const SamplerView* h;
-    __device__ __forceinline__ bool halton() const { return h->perms != nullptr; }
+    __device__ __forceinline__ bool halton() const { return h->kind == 1; }
+    __device__ __forceinline__ bool tables() const { return h->kind >= 2; }
     __device__ __forceinline__ void start(const SamplerView& view, const SlotInfo& si) {   // start of a pixel sample
         h = &view;
         dim = 0u;
+        cur1 = cur2 = 0u;
+        tab_base = si.sample * view.tab_n_pix + si.pix;
         if (halton()) index = (unsigned long long)halton_index(view, si.x, si.y, si.sample);
         else rng.set_sequence(si.seq);
     }
-    __device__ __forceinline__ void resume(const SamplerView& view, const SlotInfo& si, unsigned long long saved) {
+    // `extra` = the PixelSampler dimension counters kept in bits 17-30 of the path's state word
+    __device__ __forceinline__ void resume(const SamplerView& view, const SlotInfo& si, unsigned long long saved, unsigned extra) {
         h = &view;
+        cur1 = extra & 0x7Fu;
+        cur2 = (extra >> 7) & 0x7Fu;
+        tab_base = si.sample * view.tab_n_pix + si.pix;
         if (halton()) { index = (unsigned long long)halton_index(view, si.x, si.y, si.sample); dim = (unsigned)saved; }
         else { rng.state = saved; rng.inc = (si.seq << 1) | 1ull; }
     }
     __device__ __forceinline__ unsigned long long save() const { return halton() ? (unsigned long long)dim : rng.state; }
-    __device__ __forceinline__ float next() {
+    __device__ __forceinline__ unsigned extra() const { return cur1 | (cur2 << 7); }
+    template <bool TABLES = true>
+    __device__ __forceinline__ float next1() {                                             // Sampler::get_1d
+        if (TABLES && tables() && cur1 < (unsigned)h->n_dims) {
+            const float v = __ldg(h->t1 + (size_t)(cur1 * (unsigned)h->spp_tab) * h->tab_n_pix + tab_base);
+            ++cur1;
+            return v;
+        }
         if (halton()) return halton_dimension(*h, index, dim++);
         return rng.next_float();
     }
+    template <bool TABLES = true>
+    __device__ __forceinline__ void next2(float* a, float* b) {                            // Sampler::get_2d, x then y
+        if (TABLES && tables() && cur2 < (unsigned)h->n_dims) {
+            const float2 v = __ldg(h->t2 + (size_t)(cur2 * (unsigned)h->spp_tab) * h->tab_n_pix + tab_base);
+            ++cur2;
+            *a = v.x; *b = v.y;
+            return;
+        }
+        if (halton()) { *a = halton_dimension(*h, index, dim); *b = halton_dimension(*h, index, dim + 1u); dim += 2u; return; }
+        *a = rng.next_float();
+        *b = rng.next_float();
+    }
 };
+
+// ---- PixelSampler tables: Sampler::start_pixel for every pixel of the sample bounds ---------------------------------------
+// One thread per pixel walks its own RNG stream exactly as StratifiedSampler::start_pixel (stratified.rs:44-76) /
+// ZeroTwoSequenceSampler::start_pixel (zerotwosequence.rs:31-48) do (1D dimensions first, then 2D; generate, then shuffle),
+// on columns of the tables (stride tab_n_pix).  pbrt-v3 semantics where the port cannot run: DESIGN.md §9 (P1-P4).
+struct TableGen {
+    int kind, spp, n_dims, xs, ys, jitter;
+    uint32_t n_pix;
+    unsigned long long seq0;
+    float* t1;
+    float2* t2;
+};
+__device__ __forceinline__ uint32_t pcg_bounded(Pcg32& rng, uint32_t b) {                  // rng.rs:36-44 uniform_u32_u32
+    const uint32_t threshold = (~b + 1u) % b;
+    for (;;) {
+        const uint32_t r = rng.next_u32();
+        if (r >= threshold) return r % b;
+    }
+}
+template <class T>
+__device__ __forceinline__ void shuffle_column(T* col, uint32_t stride, int count, Pcg32& rng) {      // sampling.rs:280-287
+    for (int i = 0; i < count; ++i) {
+        const int other = i + (int)pcg_bounded(rng, (uint32_t)(count - i));
+        const T a = col[(size_t)i * stride], b = col[(size_t)other * stride];
+        col[(size_t)i * stride] = b;
+        col[(size_t)other * stride] = a;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_pixel_tables(TableGen g) {
+    const float kScale = 2.3283064365386963e-10f;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < g.n_pix; pix += gridDim.x * blockDim.x) {
+        Pcg32 rng;
+        rng.set_sequence(g.seq0 + pix);
+        const uint32_t stride = g.n_pix;
+        if (g.kind == 2) {
+            const int n = g.xs * g.ys;
+            const float inv_n = 1.0f / (float)n;
+            for (int d = 0; d < g.n_dims; ++d) {                                           // stratified_sample_1d, sampling.rs:11-17
+                float* col = g.t1 + (size_t)d * g.spp * stride + pix;
+                for (int i = 0; i < n; ++i) {
+                    const float delta = g.jitter ? rng.next_float() : 0.5f;
+                    col[(size_t)i * stride] = fminf(PB2_ONE_MINUS_EPS, ((float)i + delta) * inv_n);
+                }
+                shuffle_column(col, stride, n, rng);
+            }
+            const float dx = 1.0f / (float)g.xs, dy = 1.0f / (float)g.ys;
+            for (int d = 0; d < g.n_dims; ++d) {                                           // stratified_sample_2d, sampling.rs:19-41
+                float2* col = g.t2 + (size_t)d * g.spp * stride + pix;
+                int i = 0;
+                for (int y = 0; y < g.ys; ++y)
+                    for (int x = 0; x < g.xs; ++x) {
+                        float jx = 0.5f, jy = 0.5f;
+                        if (g.jitter) { jx = rng.next_float(); jy = rng.next_float(); }
+                        col[(size_t)i * stride] = make_float2(fminf(PB2_ONE_MINUS_EPS, ((float)x + jx) * dx), fminf(PB2_ONE_MINUS_EPS, ((float)y + jy) * dy));
+                        ++i;
+                    }
+                shuffle_column(col, stride, n, rng);
+            }
+        } else {
+            for (int d = 0; d < g.n_dims; ++d) {                                           // van_der_corput, lowdiscrepancy.rs:436-460
+                float* col = g.t1 + (size_t)d * g.spp * stride + pix;
+                uint32_t v = rng.next_u32();
+                for (int i = 0; i < g.spp; ++i) {                                          // gray_code_sample :416-422
+                    col[(size_t)i * stride] = fminf(PB2_ONE_MINUS_EPS, __uint2float_rn(v) * kScale);
+                    v ^= 0x80000000u >> (__ffs(i + 1) - 1);
+                }
+                for (int i = 0; i < g.spp; ++i) (void)rng.next_u32();                      // P1: shuffle of 1 element = uniform_u32_u32(1), one draw
+                shuffle_column(col, stride, g.spp, rng);
+            }
+            for (int d = 0; d < g.n_dims; ++d) {                                           // sobol_2d, lowdiscrepancy.rs:462-505
+                float2* col = g.t2 + (size_t)d * g.spp * stride + pix;
+                uint32_t v0 = rng.next_u32(), v1 = rng.next_u32();
+                for (int i = 0; i < g.spp; ++i) {                                          // gray_code_sample_2d :425-434
+                    col[(size_t)i * stride] = make_float2(fminf(PB2_ONE_MINUS_EPS, __uint2float_rn(v0) * kScale), fminf(PB2_ONE_MINUS_EPS, __uint2float_rn(v1) * kScale));
+                    const int tz = __ffs(i + 1) - 1;
+                    v0 ^= 0x80000000u >> tz;
+                    // column tz of the second Sobol' matrix: c[0] = 1 << 31, c[j] = c[j-1] ^ (c[j-1] >> 1) (P4)
+                    uint32_t c = 0x80000000u;
+                    for (int j = 0; j < tz; ++j) c ^= c >> 1;
+                    v1 ^= c;
+                }
+                for (int i = 0; i < g.spp; ++i) (void)rng.next_u32();
+                shuffle_column(col, stride, g.spp, rng);
+            }
+        }
+    }
+}
 
 // ---- Camera::generate_ray (perspective.rs:90-112 + geometry.rs:865-881) ----------------------------------------------
 __device__ __forceinline__ vec3 cam_point(const mat4& m, vec3 p) {
@@ -177,16 +297,17 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
         const SlotInfo si = slot_info(map, film, slot);
         PathSampler smp;
         smp.start(map.smp, si);
-        const float u0 = smp.next(), u1 = smp.next();                 // p_film offset (x then y)
+        float u0, u1, l0, l1;
+        smp.next2(&u0, &u1);                                          // p_film offset (x then y)
         if (smp.halton()) smp.dim += 3u;                              // time, p_lens: drawn, never used (pinhole)
-        else { (void)smp.next(); (void)smp.next(); (void)smp.next(); }
+        else { (void)smp.next1(); smp.next2(&l0, &l1); }
         vec3 o, d;
         float t_max;
         gen_camera_ray(cam, (float)si.x + u0, (float)si.y + u1, &o, &d, &t_max);
         b.ray_o[slot] = make_float4(o.x, o.y, o.z, t_max);
         b.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
         b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-        b.L[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+        b.L[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp.extra() << 17));
         b.rng[slot] = smp.save();
         b.q_active[0][slot] = (uint32_t)slot;
     }
@@ -333,17 +454,33 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
                                                 float us1, rgb3 beta) {
     const unsigned flags = kAllLobes & ~kSpecular;                       // D23 FIX
     const rgb3 l_emit = mkc(light.l[0], light.l[1], light.l[2]);
-    const bool delta = light.type == 0;                                  // light.rs:28-31, D24 FIX
+    const bool delta = light.type != 1;                                  // light.rs:28-31, D24 FIX: point, spot, distant
     vec3 wi = mk(0.f, 0.f, 0.f);
     float light_pdf = 0.0f, scattering_pdf = 0.0f;
     rgb3 li = gray(0.0f);
     vec3 sh_o = mk(0.f, 0.f, 0.f), sh_d = mk(0.f, 0.f, 0.f);
     const vec3 lp0 = ld3(light.p0), lp1 = ld3(light.p1), lp2 = ld3(light.p2);
-    if (delta) {                                                         // point.rs:47-66
-        const vec3 pl = ld3(light.p);
-        wi = unit(pl - v.p);
+    if (delta) {                                                         // point.rs:47-66, spot.rs:71-85, distant.rs:50-67
+        vec3 pl = ld3(light.p);
         light_pdf = 1.0f;
-        li = l_emit / len2(pl - v.p);
+        if (light.type == 3) {                                           // DistantLight: the tester's far end is p_outside
+            wi = ld3(light.axis);
+            pl = v.p + wi * (2.0f * light.world_radius);
+            li = l_emit;
+        } else {
+            wi = unit(pl - v.p);
+            if (light.type == 2) {                                       // SpotLight::falloff(-wi), spot.rs:51-63
+                const vec3 w = -wi;
+                const float cos_theta = (light.axis[0] * w.x + light.axis[1] * w.y) + light.axis[2] * w.z;
+                float fall = 1.0f;
+                if (cos_theta < light.cos_total_width) fall = 0.0f;
+                else if (!(cos_theta >= light.cos_falloff_start)) {
+                    const float dl = (cos_theta - light.cos_total_width) / (light.cos_falloff_start - light.cos_total_width);
+                    fall = (dl * dl) * (dl * dl);
+                }
+                li = l_emit * fall / len2(pl - v.p);
+            } else li = l_emit / len2(pl - v.p);
+        }
         sh_o = offset_ray_origin(v.p, v.err, v.n, pl - v.p);             // interaction.rs:146-153
         const vec3 target = offset_ray_origin(pl, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), sh_o - pl);
         sh_d = target - sh_o;
@@ -439,7 +576,7 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
 #ifndef PB2_SHADE_BLOCKS
 #define PB2_SHADE_BLOCKS 2
 #endif
-template <int MAT>
+template <int MAT, bool TABLES>
 __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
     const uint64_t n = b.counters[C_MAT0 + MAT];
     const uint32_t* queue = b.q_mat[MAT];
@@ -468,17 +605,19 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
         if (alive) {
             const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
             PathSampler rng;
-            rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot]);
+            rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot], TABLES ? (state >> 17) & 0x3FFFu : 0u);
             if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
                 float pick_pdf;
-                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next(), &pick_pdf);
+                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next1<TABLES>(), &pick_pdf);
                 if (pick_pdf != 0.0f) {
-                    const float ul0 = rng.next(), ul1 = rng.next();
-                    const float us0 = rng.next(), us1 = rng.next();
+                    float ul0, ul1, us0, us1;
+                    rng.next2<TABLES>(&ul0, &ul1);
+                    rng.next2<TABLES>(&us0, &us1);
                     direct_lighting(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
                 }
             }
-            const float u0 = rng.next(), u1 = rng.next();                                 // path.rs:123-134
+            float u0, u1;
+            rng.next2<TABLES>(&u0, &u1);                                                  // path.rs:123-134
             vec3 wi = mk(0.f, 0.f, 0.f);
             float pdf = 0.0f;
             unsigned sampled = 0u;
@@ -495,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
                 const rgb3 rr_beta = beta * eta_scale;                                   // path.rs:200-207, D27 KEEP
                 if (max_channel(rr_beta) < pp.rr_threshold && bounces > 3u) {
                     const float q = fminf(1.0f - max_channel(rr_beta), 0.05f);
-                    if (rng.next() < q) alive = false;
+                    if (rng.next1<TABLES>() < q) alive = false;
                     else beta = beta / (1.0f - q);
                 }
                 if (alive) {
@@ -504,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
                     b.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, 0.0f);
                     b.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
                     b.rng[slot] = rng.save();
-                    Lf.w = __uint_as_float(bounces | ((spec ? 1u : 0u) << 16));
+                    Lf.w = __uint_as_float(bounces | ((spec ? 1u : 0u) << 16) | (TABLES ? rng.extra() << 17 : 0u));
                     queue_push(&b.counters[C_ACTIVE_A + (cur ^ 1)], b.q_active[cur ^ 1], slot);
                 }
             }
@@ -563,8 +702,10 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map,
             const SlotInfo si = slot_info(map, f, slot);
             PathSampler rng;
             rng.start(map.smp, si);
-            const float pfx = (float)x + rng.next();
-            const float pfy = (float)y + rng.next();
+            float u0, u1;
+            rng.next2(&u0, &u1);
+            const float pfx = (float)x + u0;
+            const float pfy = (float)y + u1;
             film_footprint(f, pfx, pfy, [&](int px, int py, float fw) {
                 const rgb3 c = L * 1.0f * fw;                            // l * sample_weight * filter_weight
                 if (px == x && py == y) { acc.x += c.r; acc.y += c.g; acc.z += c.b; acc.w += fw; }
@@ -582,8 +723,10 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_atomic(uint64_t n,
         const SlotInfo si = slot_info(map, f, slot);
         PathSampler rng;
         rng.start(map.smp, si);
-        const float pfx = (float)si.x + rng.next();
-        const float pfy = (float)si.y + rng.next();
+        float u0, u1;
+        rng.next2(&u0, &u1);
+        const float pfx = (float)si.x + u0;
+        const float pfy = (float)si.y + u1;
         film_footprint(f, pfx, pfy, [&](int px, int py, float fw) { film_atomic_add(f, px, py, L * 1.0f * fw, fw); });
     }
 }
@@ -651,8 +794,10 @@ __global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, fl
         const SlotInfo si = slot_info(map, f, slot);
         PathSampler rng;
         rng.start(map.smp, si);
-        pf_out[2 * slot] = (float)si.x + rng.next();
-        pf_out[2 * slot + 1] = (float)si.y + rng.next();
+        float u0, u1;
+        rng.next2(&u0, &u1);
+        pf_out[2 * slot] = (float)si.x + u0;
+        pf_out[2 * slot + 1] = (float)si.y + u1;
     }
 }
 
@@ -674,9 +819,15 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         const int cur = depth & 1;
         k_iter_begin<<<1, 32, 0, st>>>(b, cur);
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
-        k_shade<0><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-        k_shade<1><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-        k_shade<2><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+        if (map.smp.kind >= 2) {
+            k_shade<0, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+            k_shade<1, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+            k_shade<2, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+        } else {
+            k_shade<0, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+            k_shade<1, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+            k_shade<2, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+        }
         if (depth < pp.max_depth && sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
             k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);
@@ -752,6 +903,13 @@ int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
     trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
     k_copy_li<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, wf->b, d_L, d_pfilm);
     return 0;
+}
+
+void pixel_tables_generate(int kind, uint32_t n_pix, int spp, int n_dims, int x_samples, int y_samples, int jitter, uint64_t seq0,
+                           float* d_t1, float2* d_t2, cudaStream_t st) {
+    const TableGen g{kind, spp, n_dims, x_samples, y_samples, jitter, n_pix, seq0, d_t1, d_t2};
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, ((uint64_t)n_pix + kThreads - 1) / kThreads);
+    k_pixel_tables<<<grid, kThreads, 0, st>>>(g);
 }
 
 // Ordered application of the strays (exact mode), then merge of the call's sums into the film.

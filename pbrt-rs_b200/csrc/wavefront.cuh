@@ -43,6 +43,14 @@ struct FilmView {
 // HaltonSampler state shared by all paths (samplers/halton.rs:24-37 + the permutation table of lowdiscrepancy.rs:333-349);
 // perms == nullptr selects the RandomSampler streams.
 struct SamplerView {
+    int kind;                     // PB2_SAMPLER_*: 0 random, 1 Halton, 2 stratified, 3 (0,2)-sequence
+    // PixelSampler tables (sampler.rs:257-322) of kinds 2 / 3, written by k_pixel_tables: value of tabulated dimension d,
+    // sample s, pixel p at [(d * spp + s) * tab_n_pix + p] (a warp = neighbouring pixels of one sample: coalesced)
+    int n_dims;
+    int spp_tab;                  // samples per pixel of the tables
+    uint32_t tab_n_pix;
+    const float* t1;
+    const float2* t2;
     const uint16_t* perms;        // RADICAL_INVERSE_PERMUTATIONS
     const uint32_t* primes;       // first 1000 primes
     const uint32_t* prime_sums;   // offset of every base's permutation
@@ -109,6 +117,10 @@ int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
 int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
                  const PathParams& pp, const SamplerView& smp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L,
                  float* d_pfilm, cudaStream_t st);
+// Sampler::start_pixel of StratifiedSampler / ZeroTwoSequenceSampler for every pixel (one thread per pixel, stream
+// RNG::new(seq0 + pixel)).
+void pixel_tables_generate(int kind, uint32_t n_pix, int spp, int n_dims, int x_samples, int y_samples, int jitter, uint64_t seq0,
+                           float* d_t1, float2* d_t2, cudaStream_t st);
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
 void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st);

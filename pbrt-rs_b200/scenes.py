@@ -214,6 +214,19 @@ def scene_c4(n_theta=158, n_phi=316):
     return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=materials, lights=lights)
 
 
+def scene_all_lights(n_theta=24, n_phi=48):
+    """C4's room with every light the backend knows: the ceiling area light, a point light, a spot light aimed at the matte
+    sphere (src/lights/spot.rs; axis = normalize(to - from), 30 degree cone, falloff from 20 degrees) and a distant light
+    shining in through the open front (src/lights/distant.rs)."""
+    sc = scene_c4(n_theta=n_theta, n_phi=n_phi)
+    frm, to = np.array((450.0, 500.0, 60.0), np.float32), np.array((140.0, 90.0, 280.0), np.float32)
+    d = to - frm
+    axis = d / np.float32(np.sqrt(np.float32(np.dot(d, d))))
+    sc["lights"] = sc["lights"] + [dict(type="spot", p=tuple(frm), axis=tuple(float(a) for a in axis), I=(9e5, 8e5, 6e5), total_width=30.0, falloff_start=20.0),
+                                   dict(type="distant", w=(0.2, 0.3, -1.0), L=(1.5, 1.5, 2.0))]
+    return sc
+
+
 C4_CAMERA = dict(pos=(278.0, 273.0, -800.0), look=(278.0, 273.0, 0.0), up=(0.0, 1.0, 0.0), fov=39.3, res=(1920, 1080))
 C4_PATH = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", spp=256)
 C5_CAMERA = dict(C4_CAMERA, res=(3840, 2160))

@@ -13,14 +13,17 @@ pub struct pb2_hit { pub prim_id: u32, pub t: f32, pub b1: f32, pub b2: f32 }
 pub struct pb2_material { pub ty: i32, pub kd: [f32; 3], pub ks: [f32; 3], pub roughness: f32, pub remap_roughness: i32,
                           pub kr: [f32; 3], pub kt: [f32; 3], pub eta: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct pb2_light { pub ty: i32, pub p: [f32; 3], pub i: [f32; 3], pub prim_id: u32, pub two_sided: i32 }
+pub struct pb2_light { pub ty: i32 /* 0 point, 1 area, 2 spot, 3 distant */, pub p: [f32; 3], pub i: [f32; 3], pub prim_id: u32, pub two_sided: i32,
+                       pub axis: [f32; 3] /* spot: row 2 of world_to_light; distant: w */, pub total_width: f32, pub falloff_start: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_camera { pub pos: [f32; 3], pub look: [f32; 3], pub up: [f32; 3], pub fov: f32, pub res_x: i32, pub res_y: i32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_film_desc { pub res_x: i32, pub res_y: i32, pub filter: i32, pub radius_x: f32, pub radius_y: f32, pub gaussian_alpha: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_path_desc { pub max_depth: i32, pub rr_threshold: f32, pub light_strategy: i32, pub spp: i32,
-                           pub sample_begin: i32, pub sample_end: i32, pub sampler: i32 /* 0 RandomSampler, 1 HaltonSampler */ }
+                           pub sample_begin: i32, pub sample_end: i32,
+                           pub sampler: i32 /* 0 RandomSampler, 1 HaltonSampler, 2 StratifiedSampler, 3 ZeroTwoSequenceSampler */,
+                           pub n_sampled_dimensions: i32, pub x_samples: i32, pub y_samples: i32, pub jitter: i32 }
 pub enum pb2_scene {}
 pub enum pb2_film {}
 pub const PB2_MISS: u32 = 0xFFFF_FFFF;

@@ -254,3 +254,75 @@ def test_halton_film_equals_reference_tile_order(gpu, OP, scenes):
     assert np.array_equal(bits(got), bits(want1))
     assert (bits(got) != bits(want0)).any(axis=2).mean() < 0.01
     np.testing.assert_allclose(got, want0, rtol=2e-6, atol=1e-7)
+
+
+def test_spot_and_distant_lights_bit_exact(gpu, OP, scenes):
+    """SpotLight / DistantLight (src/lights/spot.rs, src/lights/distant.rs) beside the area and point lights, power light
+    distribution: per-sample radiance equals the oracle's bits; each new light alone lights the scene."""
+    sc = scenes.scene_all_lights(n_theta=40, n_phi=80)
+    cam = dict(scenes.C4_CAMERA, res=(480, 270))
+    kw = dict(max_depth=6, rr_threshold=1.0, light_strategy="power", spp=16)
+    rng = np.random.default_rng(21)
+    n = 30000
+    xy = np.stack([rng.integers(0, 480, n), rng.integers(60, 270, n)], axis=1)
+    s = rng.integers(0, 16, size=n)
+    for lights in (sc["lights"], sc["lights"][-2:-1], sc["lights"][-1:]):
+        accel, camera, integ, ref = setup_scene(gpu, OP, dict(sc, lights=lights), cam, **kw)
+        L, pf = integ.li(xy, s)
+        rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), xy, s)
+        assert np.array_equal(bits(pf), bits(rpf))
+        mism = (bits(L) != bits(rL)).any(axis=1)
+        assert mism.sum() == 0, f"{len(lights)} lights: {mism.sum()} of {n} samples differ; first {L[mism][:2]} vs {rL[mism][:2]}"
+        assert (L.sum(axis=1) > 0).mean() > 0.05
+    with pytest.raises(gpu.Pb2Error):
+        gpu.scene_from_dict(dict(sc, lights=[dict(type="distant", w=(0, 0, 0), L=(1, 1, 1))]))
+
+
+@pytest.mark.parametrize("sampler,skw", [("stratified", dict(x_samples=4, y_samples=4)), ("stratified", dict(x_samples=8, y_samples=2, jitter=False)),
+                                         ("zerotwo", {}), ("zerotwo", dict(n_sampled_dimensions=9))])
+def test_pixel_samplers_bit_exact(gpu, OP, scenes, sampler, skw):
+    """StratifiedSampler / ZeroTwoSequenceSampler (PixelSampler, src/core/sampler.rs:257-322): the per-pixel tables are
+    generated on the device (k_pixel_tables) from the stream RNG::new(n_pixels*spp + pixel); per-sample radiance, film positions
+    and the box-filtered film equal the oracle's bits (mixed materials: the number of dimensions a path draws is data dependent,
+    so paths leave the tables at different vertices)."""
+    sc = scenes.scene_c4(n_theta=24, n_phi=48)
+    cam = dict(scenes.C4_CAMERA, res=(160, 90))
+    kw = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", spp=16)
+    accel, camera, _, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    integ = gpu.PathIntegrator(accel, camera, sampler=sampler, **kw, **skw)
+    rng = np.random.default_rng(5)
+    n = 20000
+    xy = np.stack([rng.integers(0, 160, n), rng.integers(0, 90, n)], axis=1)
+    s = rng.integers(0, 16, size=n)
+    L, pf = integ.li(xy, s)
+    pd = OP.path_desc(sampler=sampler, **kw, **skw)
+    rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), pd, xy, s)
+    assert np.array_equal(bits(pf), bits(rpf))
+    mism = (bits(L) != bits(rL)).any(axis=1)
+    assert mism.sum() == 0, f"{mism.sum()} of {n} samples differ"
+    film = gpu.Film(cam["res"])
+    integ.render(film, 0, 6)
+    integ.render(film, 6, 16)
+    got = film.read_xyzw()
+    fd = OP.film_desc(cam["res"])
+    want, _ = ref.render(cam, fd, OP.path_desc(sampler=sampler, sample_begin=0, sample_end=6, **kw, **skw), mode=1)
+    want, _ = ref.render(cam, fd, OP.path_desc(sampler=sampler, sample_begin=6, sample_end=16, **kw, **skw), mode=1, out=want)
+    assert np.array_equal(bits(got), bits(want)), f"{(bits(got) != bits(want)).any(axis=2).sum()} pixels differ"
+
+
+def test_pixel_sampler_argument_errors(gpu, scenes):
+    sc = scenes.scene_c2()
+    accel = gpu.BVHAccel(gpu.scene_from_dict(sc))
+    cam = gpu.PerspectiveCamera((278, 273, -800), (278, 273, 0), (0, 1, 0), 39.3, (32, 32))
+    film = gpu.Film((32, 32))
+    bad = gpu.PathIntegrator(accel, cam, spp=16, sampler="stratified", x_samples=4, y_samples=4)
+    bad.desc.spp = 15                                                     # x_samples * y_samples != spp
+    with pytest.raises(gpu.Pb2Error):
+        bad.render(film)
+    z = gpu.PathIntegrator(accel, cam, spp=12, sampler="zerotwo")
+    assert z.desc.spp == 16                                               # rounded up like ZeroTwoSequenceSampler::new
+    z.desc.spp = 12
+    with pytest.raises(gpu.Pb2Error):
+        z.render(film)
+    with pytest.raises(gpu.Pb2Error):
+        gpu.PathIntegrator(accel, cam, spp=16, sampler="zerotwo", n_sampled_dimensions=200).render(film)

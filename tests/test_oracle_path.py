@@ -91,3 +91,80 @@ def test_halton_known_answers(OP):
             idx, dims, _ = OP.halton_probe((512, 512), (px, py), s, n_dims=8)
             assert idx % (128 * 243) == OP.halton_probe((512, 512), (px, py), 0)[0] and idx // (128 * 243) == s
             assert ((dims >= 0) & (dims < 1)).all()
+
+
+def test_spot_and_distant_lights(OP, scenes):
+    """SpotLight (src/lights/spot.rs) and DistantLight (src/lights/distant.rs) on a single matte floor quad, against the closed
+    forms: directly below a spot of intensity I at height h the radiance is kd/pi * I / h^2, zero outside the cone; under a
+    distant light of radiance L from direction w it is kd/pi * L * cos(theta) everywhere."""
+    quad = np.array([(-50, 0, -50), (-50, 0, 50), (50, 0, 50), (50, 0, -50)], np.float32)
+    base = dict(verts=quad, idx=np.array([[0, 1, 2], [0, 2, 3]], np.uint32), tri_material=np.zeros(2, np.uint32),
+                materials=[dict(type="matte", kd=(0.5, 0.5, 0.5))])
+    cam = dict(pos=(0, 40.0, 0), look=(0, 0, 0), up=(0, 0, 1), fov=90.0, res=(33, 33))
+    fd = OP.film_desc(cam["res"])
+    pd = OP.path_desc(max_depth=1, spp=4)
+    spot = dict(type="spot", p=(0, 10.0, 0), axis=(0, -1.0, 0), I=(200.0, 200.0, 200.0), total_width=30.0, falloff_start=20.0)
+    img = OP.resolve_rgb(OP.Scene(dict(base, lights=[spot])).render(cam, fd, pd)[0])
+    # centre pixel (2.4 units wide on the floor): below the light, inside falloff_start; cos^3 falloff over the pixel ~ -1.5 %
+    assert 0.975 < img[16, 16, 0] / (0.5 / np.pi * 200.0 / 100.0) < 1.0
+    assert img[0, 0].max() == 0.0 and img[16, 0].max() == 0.0                   # 40 units out: far outside the 30 degree cone
+    r = np.hypot(*np.meshgrid(np.arange(33) - 16.0, np.arange(33) - 16.0))     # lit disc radius = 10 tan(30 deg) = 5.77 of 80/33 per pixel
+    lit = img[..., 0] > 0
+    assert lit[r < 1.5].all() and not lit[r > 3.5].any()
+    w = np.array((0.0, 0.6, 0.8))
+    distant = dict(type="distant", w=tuple(w), L=(3.0, 2.0, 1.0))
+    img = OP.resolve_rgb(OP.Scene(dict(base, lights=[distant])).render(cam, fd, pd)[0])
+    assert np.allclose(img, 0.5 / np.pi * np.array((3.0, 2.0, 1.0)) * 0.6, rtol=1e-5)
+    # power heuristic of the light distribution: spot 2 pi I (1 - (cos 20 + cos 30) / 2), distant pi r^2 L (both through luminance)
+    both = OP.Scene(dict(base, lights=[spot, distant]))
+    a = OP.resolve_rgb(both.render(cam, fd, OP.path_desc(max_depth=1, spp=256, light_strategy="power"))[0])
+    b = OP.resolve_rgb(both.render(cam, fd, OP.path_desc(max_depth=1, spp=256, light_strategy="uniform"))[0])
+    assert abs(a.mean() - b.mean()) / b.mean() < 0.03
+
+
+def test_pixel_sampler_tables(OP):
+    """StratifiedSampler / ZeroTwoSequenceSampler start_pixel (samplers/stratified.rs:44-76, samplers/zerotwosequence.rs:31-48):
+    every 1D table holds one value per stratum, every stratified 2D table one point per (x, y) cell, every (0,2) 2D table is a
+    (0,2)-net: one point in each elementary interval of area 1/spp."""
+    pd = OP.path_desc(spp=64, sampler="stratified", n_sampled_dimensions=3, x_samples=16, y_samples=4)
+    t1, t2 = OP.pixel_tables(pd, 7)
+    for d in range(3):
+        assert sorted(np.floor(t1[d] * 64).astype(int)) == list(range(64))
+        cells = np.floor(t2[d, :, 0] * 16).astype(int) * 4 + np.floor(t2[d, :, 1] * 4).astype(int)
+        assert sorted(cells) == list(range(64))
+        assert list(np.floor(t1[d] * 64).astype(int)) != list(range(64))          # shuffled
+    nj, _ = OP.pixel_tables(OP.path_desc(spp=64, sampler="stratified", n_sampled_dimensions=1, x_samples=8, y_samples=8, jitter=False), 7)
+    assert sorted(nj[0]) == [np.float32((i + 0.5) / 64) for i in range(64)]
+    pd = OP.path_desc(spp=64, sampler="zerotwo", n_sampled_dimensions=3)
+    t1, t2 = OP.pixel_tables(pd, 7)
+    for d in range(3):
+        assert sorted(np.floor(t1[d] * 64).astype(int)) == list(range(64))        # scrambled van der Corput: stratified at every power of two
+        for k in range(7):                                                        # 2^k x 2^(6-k) boxes
+            a, b = 1 << k, 1 << (6 - k)
+            cells = np.floor(t2[d, :, 0] * a).astype(int) * b + np.floor(t2[d, :, 1] * b).astype(int)
+            assert sorted(cells) == list(range(64)), (d, k)
+    u1, u2 = OP.pixel_tables(pd, 8)
+    assert not np.array_equal(t1, u1) and not np.array_equal(t2, u2)              # another pixel, another scramble
+
+
+@pytest.mark.parametrize("sampler,kw", [("stratified", dict(x_samples=8, y_samples=8)), ("zerotwo", {})])
+def test_pixel_samplers_render_and_converge(OP, scenes, sampler, kw):
+    """Cornell box with the PixelSamplers: same mean as the RandomSampler render (unbiased), lower pixel variance at equal spp
+    on the directly lit floor, and the reference's tile-sequential order (mode 0) agrees statistically with per-pixel streams."""
+    sc = OP.Scene(scenes.scene_c2())
+    cam = dict(scenes.C2_CAMERA, res=(48, 48))
+    fd = OP.film_desc((48, 48))
+    base = dict(max_depth=5, spp=64)
+    rnd = OP.resolve_rgb(sc.render(cam, fd, OP.path_desc(**base))[0])
+    a = OP.resolve_rgb(sc.render(cam, fd, OP.path_desc(sampler=sampler, **base, **kw), mode=1)[0])
+    b = OP.resolve_rgb(sc.render(cam, fd, OP.path_desc(sampler=sampler, **base, **kw), mode=0)[0])
+    assert abs(a.mean() - rnd.mean()) / rnd.mean() < 0.02
+    assert abs(a.mean() - b.mean()) / b.mean() < 0.02
+    ref = OP.resolve_rgb(sc.render(cam, fd, OP.path_desc(max_depth=5, spp=1024))[0])
+    err = lambda img: float(np.mean((img - ref) ** 2))
+    assert err(a) < err(rnd)
+    # sample ranges add up exactly with per-pixel tables too
+    half, _ = sc.render(cam, fd, OP.path_desc(sampler=sampler, sample_begin=0, sample_end=40, **base, **kw))
+    whole, _ = sc.render(cam, fd, OP.path_desc(sampler=sampler, sample_begin=40, sample_end=64, **base, **kw), out=half)
+    full, _ = sc.render(cam, fd, OP.path_desc(sampler=sampler, **base, **kw))
+    assert np.allclose(whole, full, rtol=1e-5, atol=1e-6)
