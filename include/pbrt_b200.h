@@ -147,7 +147,8 @@ int pb2_scene_destroy(pb2_scene* scene);
 /* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
  * node layout + 48-byte triangles, upload to the current device.  split_method (bvh.rs:199-204): 0 = SplitMethod::SAH,
  * built on the host; 1 = SplitMethod::HLBVH (bvh.rs:475-772), built on the GPU (Morton codes, radix sort, one LBVH treelet
- * per 12-bit Morton prefix, SAH over the treelet roots).  Middle / EqualCounts are not built. */
+ * per 12-bit Morton prefix, SAH over the treelet roots); 2 = SplitMethod::Middle, 3 = SplitMethod::EqualCounts
+ * (bvh.rs:331-360), built on the host by the same recursive_build. */
 int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_method);
 /* Host half only (no device needed): the flattened array can then be inspected with pb2_bvh_info / pb2_bvh_export. */
 int pb2_scene_build_bvh_host(pb2_scene* scene, int max_prims_in_node, int split_method);

@@ -297,6 +297,7 @@ public:
         build_nodes_.reserve(2 * nt);
         ordered_prims.reserve(nt);
         int root;
+        split_method_ = split_method;
         if (split_method == 1) {                              // SplitMethod::HLBVH (:239-243)
             ordered_prims.resize(nt);
             root = hlbvh_build(info);
@@ -427,7 +428,10 @@ private:
         return index;
     }
 
-    // bvh.rs:273-473, SplitMethod::SAH only, with D12-D17 fixed (pbrt-v3 semantics)
+    // bvh.rs:273-473: SplitMethod::SAH (0), ::Middle (2), ::EqualCounts (3), with D12-D17 fixed (pbrt-v3 semantics).
+    // Middle as written (:331-349) partitions [start, end] and, when the partition is improper, sorts about a SHADOWED `mid`
+    // while recursing on the improper one (unbounded recursion); pbrt-v3 falls through to EqualCounts, followed here (D60 FIX).
+    int split_method_ = 0;
     int recursive_build(std::vector<BVHPrimitiveInfo>& info, size_t start, size_t end) {
         int index = (int)build_nodes_.size();
         build_nodes_.emplace_back();
@@ -440,8 +444,24 @@ private:
         int dim = centroid_bounds.maximum_extent();
         size_t mid = (start + end) / 2;
         if (centroid_bounds.mx[dim] == centroid_bounds.mn[dim]) return make_leaf(index, info, start, end, bounds);
-        if (n_primitives <= 2) {
-            // :361-371 (D17): nth_element on [start,end) by centroid[dim]
+        bool equal_counts = split_method_ == 3;
+        if (split_method_ == 2) {                                                                         // :331-349 SplitMethod::Middle
+            const Float p_mid = (centroid_bounds.mn[dim] + centroid_bounds.mx[dim]) / 2.0f;
+            size_t lo = start, hi = end;                                                                  // partition_in_place, as below
+            for (;;) {
+                while (lo < hi && info[lo].centroid[dim] < p_mid) ++lo;
+                if (lo == hi) break;
+                do { --hi; } while (lo < hi && !(info[hi].centroid[dim] < p_mid));
+                if (lo == hi) break;
+                std::swap(info[lo], info[hi]);
+                ++lo;
+            }
+            mid = lo;
+            if (mid == start || mid == end) equal_counts = true;
+        }
+        if (split_method_ == 2 && !equal_counts) {
+        } else if (equal_counts || n_primitives <= 2) {
+            // :350-371 (D17): nth_element on [start,end) by centroid[dim]
             mid = (start + end) / 2;
             std::nth_element(info.begin() + start, info.begin() + mid, info.begin() + end,
                              [dim](const BVHPrimitiveInfo& a, const BVHPrimitiveInfo& b) { return a.centroid[dim] < b.centroid[dim]; });

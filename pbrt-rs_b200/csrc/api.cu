@@ -191,8 +191,8 @@ int pb2_scene_destroy(pb2_scene* scene) {
 }
 
 static int check_build_args(int max_prims_in_node, int split_method) {
-    if (split_method != 0 && split_method != 1)
-        return set_error(PB2_ERR_INVALID, "split_method %d: SplitMethod::SAH (0, host build) and ::HLBVH (1, GPU build) are built", split_method);
+    if (split_method < 0 || split_method > 3)
+        return set_error(PB2_ERR_INVALID, "split_method %d: SplitMethod::SAH (0), ::HLBVH (1, GPU build), ::Middle (2), ::EqualCounts (3) (bvh.rs:199-204)", split_method);
     if (max_prims_in_node < 1) return set_error(PB2_ERR_INVALID, "max_prims_in_node must be >= 1");
     return PB2_OK;
 }
@@ -205,7 +205,7 @@ static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_
     scene->built_host = false;
     const uint64_t n_tris = scene->indices.size() / 3;
     for (double& v : scene->build_ms) v = 0.0;
-    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh);
+    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh, split_method);
     if (scene->bvh.max_depth > kStackDepth)
         return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
     if (scene->bvh.leaf_overflow)

@@ -60,7 +60,8 @@ struct Split {
 
 class Builder {
 public:
-    Builder(std::vector<PrimRef>& refs, int max_prims, int threads) : refs_(refs), max_prims_(max_prims), threads_(threads) {}
+    Builder(std::vector<PrimRef>& refs, int max_prims, int threads, int split_method)
+        : refs_(refs), max_prims_(max_prims), threads_(threads), split_method_(split_method) {}
 
     // Decide what happens to [start, end): leaf, or partition about `mid` along `dim`.
     Split split_range(size_t start, size_t end, bool parallel) {
@@ -72,6 +73,28 @@ public:
         s.dim = cb.widest();
         const int dim = s.dim;
         if (cb.hi[dim] == cb.lo[dim]) { s.leaf = true; return s; }
+        if (split_method_ == 2) {
+            // SplitMethod::Middle (bvh.rs:331-349): partition about the centroid-bound midpoint; an improper partition
+            // falls through to EqualCounts as in pbrt-v3 (the port recurses on the improper split)
+            const float p_mid = (cb.lo[dim] + cb.hi[dim]) / 2.0f;
+            size_t lo = start, hi = end;
+            for (;;) {
+                while (lo < hi && refs_[lo].c[dim] < p_mid) ++lo;
+                if (lo == hi) break;
+                do { --hi; } while (lo < hi && !(refs_[hi].c[dim] < p_mid));
+                if (lo == hi) break;
+                std::swap(refs_[lo], refs_[hi]);
+                ++lo;
+            }
+            if (lo != start && lo != end) { s.mid = lo; return s; }
+        }
+        if (split_method_ == 2 || split_method_ == 3) {
+            // SplitMethod::EqualCounts (bvh.rs:350-360): nth_element about the middle by centroid[dim]
+            s.mid = (start + end) / 2;
+            std::nth_element(refs_.begin() + start, refs_.begin() + s.mid, refs_.begin() + end,
+                             [dim](const PrimRef& a, const PrimRef& b) { return a.c[dim] < b.c[dim]; });
+            return s;
+        }
         if (n <= 2) {
             // bvh.rs:361-371: nth_element about the middle by centroid[dim]
             if (refs_[start + 1].c[dim] < refs_[start].c[dim]) std::swap(refs_[start], refs_[start + 1]);
@@ -207,6 +230,7 @@ private:
     std::vector<PrimRef>& refs_;
     int max_prims_;
     int threads_;
+    int split_method_;          // bvh.rs:199-204: 0 SAH, 2 Middle, 3 EqualCounts (HLBVH is built on the device)
     std::vector<TopNode> top_;
     std::vector<Task> tasks_;
 
@@ -310,7 +334,7 @@ private:
 }  // namespace
 
 void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
-                   int max_prims_in_node, int threads, HostBVH* out) {
+                   int max_prims_in_node, int threads, HostBVH* out, int split_method) {
     (void)n_verts;
     *out = HostBVH();
     if (n_tris == 0) return;
@@ -352,7 +376,7 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
         work();
         for (auto& t : pool) t.join();
     }
-    Builder b(refs, max_prims, threads);
+    Builder b(refs, max_prims, threads, split_method);
     b.run(out);
     repack_device_layout(verts, indices, n_tris, out);
 }

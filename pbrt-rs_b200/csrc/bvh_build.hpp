@@ -80,9 +80,10 @@ struct HostBVH {
     float root_bounds[6] = {0, 0, 0, 0, 0, 0};
 };
 
-// verts: 3 floats per vertex; indices: 3 per triangle.  threads <= 0 -> hardware concurrency.
+// verts: 3 floats per vertex; indices: 3 per triangle.  threads <= 0 -> hardware concurrency.  split_method
+// (bvh.rs:199-204): 0 = SplitMethod::SAH, 2 = ::Middle, 3 = ::EqualCounts (the top-down recursive_build, bvh.rs:273-473).
 void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
-                   int max_prims_in_node, int threads, HostBVH* out);
+                   int max_prims_in_node, int threads, HostBVH* out, int split_method = 0);
 
 // Fills pairs / quads / tris / root refs / root bounds of `out` from its nodes + ordered_prims.
 void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out);

@@ -68,7 +68,7 @@ impl B200Accel {
         Self::with_split(verts, indices, max_prims_in_node, 0)
     }
     /// `split_method` follows `SplitMethod` (src/accelerators/bvh.rs:199-204): 0 = SAH (built on the host), 1 = HLBVH (built
-    /// on the GPU, bvh.rs:475-772); Middle / EqualCounts are not built.
+    /// on the GPU, bvh.rs:475-772), 2 = Middle, 3 = EqualCounts (host, bvh.rs:331-360).
     pub fn with_split(verts: &[f32], indices: &[u32], max_prims_in_node: usize, split_method: c_int) -> Self {
         let mut scene = std::ptr::null_mut();
         unsafe {

@@ -273,7 +273,28 @@ def test_hlbvh_gpu_build_equals_oracle(gpu, orc, scenes, scene, max_prims):
 def test_split_method_errors(gpu, scenes):
     v, i = scenes.random_soup(100, seed=1)
     with pytest.raises(gpu.Pb2Error):
-        gpu.BVHAccel(v, i, 4, split_method=2)       # Middle / EqualCounts are not built
+        gpu.BVHAccel(v, i, 4, split_method=4)       # bvh.rs:199-204 has four split methods
+    with pytest.raises(gpu.Pb2Error):
+        gpu.BVHAccel(v, i, 4, split_method=-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", [2, 3])
+def test_middle_and_equal_counts_trees_traverse_bit_exact(gpu, orc, scenes, split):
+    """SplitMethod::Middle / ::EqualCounts trees (bvh.rs:331-360) through the same QuadNode kernels: hits equal the oracle's
+    walk of the same tree bit for bit, and the primitive a ray hits is the one the SAH tree finds (same geometry)."""
+    v, i = scenes.scene_c1()
+    accel = gpu.BVHAccel(v, i, 4, split_method=split)
+    ref = orc.BVHAccel(v, i, 4, split_method=split)
+    cam = scenes.C1_CAMERA
+    rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], (256, 256))
+    rays = np.concatenate([rays, random_rays(60000, seed=4, finite_tmax=True)])
+    hits, b0 = accel.intersect(rays, want_b0=True)
+    rh, rb0, _ = ref.intersect(rays, want_b0=True)
+    assert_hits_equal(hits, rh, b0, rb0)
+    assert np.array_equal(accel.intersect_p(rays), ref.intersect_p(rays)[0])
+    sah = gpu.BVHAccel(v, i, 4).intersect(rays)
+    assert np.array_equal(bits(sah["t"]), bits(hits["t"]))
 
 
 @pytest.mark.gpu

@@ -76,6 +76,36 @@ def test_host_sah_build_equals_oracle(pb2, orc, scenes, case):
     assert np.array_equal(mine.world_bound(), ref.world_bound())
 
 
+@pytest.mark.parametrize("split", [2, 3])
+@pytest.mark.parametrize("case", ["soup", "grid", "coincident", "ties"])
+def test_host_middle_and_equal_counts_builds_equal_oracle(pb2, orc, scenes, case, split):
+    """SplitMethod::Middle (2) / ::EqualCounts (3) (bvh.rs:331-360): node array and primitive order equal the oracle's, on a
+    soup, on a grid large enough for the parallel top of the builder, with coincident centroids, and with many equal centroid
+    coordinates (Middle's partition is improper there and falls through to EqualCounts)."""
+    if case == "soup":
+        v, i = scenes.random_soup(20000, seed=3)
+    elif case == "grid":
+        v, i = scenes.displaced_grid(n=300)
+    elif case == "coincident":
+        v0, i0 = scenes.random_soup(50, seed=5)
+        v = np.concatenate([v0, np.tile(v0[:3], (40, 1))]).astype(np.float32)
+        i = np.concatenate([i0, (len(v0) + np.arange(120)).reshape(40, 3)]).astype(np.uint32)
+    else:
+        rng = np.random.default_rng(2)
+        c = np.stack([rng.integers(0, 3, 4000), rng.integers(0, 2, 4000), np.zeros(4000)], axis=1).astype(np.float32)[:, None, :]
+        v = (c + np.array([[-0.25, -0.25, 0], [0.25, -0.25, 0], [0, 0.5, 0]], np.float32)[None]).reshape(-1, 3).astype(np.float32)
+        i = np.arange(12000, dtype=np.uint32).reshape(-1, 3)
+    mine = pb2.BVHAccel(v, i, max_prims_in_node=4, split_method=split, host_only=True)
+    ref = orc.BVHAccel(v, i, 4, split_method=split)
+    nodes, prims = mine.export()
+    assert len(nodes) == ref.num_nodes
+    assert np.array_equal(prims, ref.ordered_prims())
+    assert _same_nodes(nodes, ref.nodes())
+    assert mine.info()[2] == ref.max_depth
+    sah = orc.BVHAccel(v, i, 4)
+    assert sorted(prims) == list(range(len(i))) and ref.num_nodes >= sah.num_nodes       # leaves of one primitive unless centroids coincide
+
+
 def test_host_build_parallel_path_equals_oracle(pb2, orc, scenes):
     # large enough that the builder splits the top of the tree across worker threads (grain = n / (8 * threads))
     v, i = scenes.displaced_grid(n=300)
