@@ -394,8 +394,21 @@ static int check_ready(const pb2_scene* scene) {
 // Host-buffer entry points stream the batch through the ring (api_internal.hpp: Pipe): the H2D copy of chunk k+1, the
 // traversal of chunk k and the D2H copy of chunk k-1 run on different engines at the same time (pinned caller memory:
 // pb2_host_alloc; pageable memory works but its copies are staged by the driver).  128 K rays per chunk keeps the pipeline
-// fill (one H2D) and drain (one kernel + one D2H) short against the 8+ chunks of a megaray batch.
-static const size_t kChunk = 1u << 17;
+// fill (one H2D) and drain (one kernel + one D2H) short against the 8+ chunks of a megaray batch.  The H2D engine is the
+// bottleneck (32 B in per ray against 16 B out and ~0.4 ns of traversal), so a call ends one kernel + one D2H after the last
+// H2D copy.  Chunks can halve towards the end of the batch (down to kTailChunk rays) to shorten that drain; measured on B200
+// (profiles/r01_tuning.md, session 3) every extra chunk costs more than the drain it saves, so the default tail equals the
+// chunk.  Reading the rays straight from pinned host memory inside the kernel (zero-copy, one launch per call) was built and
+// measured too: its reads alone run at 42 GB/s, no faster than this ring's H2D copies, and per-ray result writes over PCIe
+// (one small TLP each) made the call 1.5x slower — the link, not the pipeline, bounds these entry points.
+static size_t env_size(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long long x = atoll(v);
+    return x > 0 ? (size_t)x : dflt;
+}
+static const size_t kChunk = env_size("PB2_PIPE_CHUNK", 1u << 17);          // tuning overrides for sweeps (tools/e2e_sweep.py)
+static const size_t kTailChunk = std::min(kChunk, env_size("PB2_PIPE_TAIL", 1u << 17));
 
 extern "C++" {
 template <class Launch>
@@ -403,9 +416,10 @@ static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t ou
     int rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
     if (rc) return rc;
     Pipe& p = scene->pipe;
-    uint64_t c = 0;
-    for (uint64_t off = 0; off < n; off += kChunk, ++c) {
-        const uint64_t m = std::min<uint64_t>(kChunk, n - off);
+    uint64_t c = 0, m = 0;
+    for (uint64_t off = 0; off < n; off += m, ++c) {
+        const uint64_t left = n - off;
+        m = std::min<uint64_t>(left, std::min<uint64_t>(kChunk, std::max<uint64_t>(kTailChunk, (left + 1) / 2)));
         Stage& st = p.slot[c % kStages];
         if (c >= (uint64_t)kStages) PB2_CUDA(cudaStreamWaitEvent(p.h2d, st.drained, 0));       // slot's previous chunk fully out
         PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, p.h2d));
