@@ -83,13 +83,19 @@ typedef struct pb2_camera {
     int32_t res_x, res_y;
 } pb2_camera;
 
-enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1 };
-/* src/core/film.rs:31-75 Film::new + src/filters/{boxf,gaussian}.rs */
+enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1, PB2_FILTER_TRIANGLE = 2, PB2_FILTER_MITCHELL = 3, PB2_FILTER_SINC = 4 };
+/* src/core/film.rs:31-75 Film::new + src/filters/{boxf,gaussian,triangle,mitchell,sinc}.rs */
 typedef struct pb2_film_desc {
-    int32_t res_x, res_y;
-    int32_t filter;     /* PB2_FILTER_* */
+    int32_t res_x, res_y;       /* full_resolution */
+    int32_t filter;             /* PB2_FILTER_* */
     float radius_x, radius_y;
-    float gaussian_alpha;
+    float gaussian_alpha;       /* GaussianFilter::new(radius, alpha) */
+    float mitchell_b, mitchell_c;   /* MitchellFilter::new(radius, b, c) */
+    float sinc_tau;             /* LanczosSincFilter::new(radius, tau) */
+    float crop_window[4];       /* {min.x, min.y, max.x, max.y} as fractions of the full resolution (film.rs:33,41-50);
+                                 * all zero means the whole image {0, 0, 1, 1}.  The film stores, and pb2_film_read_xyzw /
+                                 * pb2_film_resolve_rgb / pb2_film_write_image return, only cropped_pixel_bounds. */
+    float max_sample_luminance; /* FilmTile::add_sample clamp (film.rs:259-261); <= 0 means infinity */
 } pb2_film_desc;
 
 enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1 };
@@ -204,6 +210,8 @@ int pb2_film_read_xyzw(pb2_film* film, float* out);
 /* Film::write_image (:153-178): XYZ -> RGB, / weight, clamp >= 0, * scale. */
 int pb2_film_resolve_rgb(pb2_film* film, float scale, float* rgb);
 int pb2_film_device_ptr(pb2_film* film, void** d_xyzw, uint64_t* n_floats);
+/* Film::cropped_pixel_bounds (film.rs:41-50) and Film::get_sample_bounds (:76-81): {x0, y0, x1, y1} each (x1, y1 exclusive). */
+int pb2_film_bounds(const pb2_film* film, int32_t pixel_bounds[4], int32_t sample_bounds[4]);
 /* Film::write_image (film.rs:153-180) through to a file — the reference stops at todo!() after building the RGB array
  * (imageio.rs:3-5).  ".pfm": float RGB, rows bottom-to-top, little-endian; ".ppm": 8-bit P6 with pbrt's sRGB gamma
  * (pbrt-v3 imageio.cpp GammaCorrect + 255 v + 0.5 clamp).  Any other extension is PB2_ERR_INVALID. */

@@ -73,12 +73,16 @@ struct CameraDesc {
     Float fov;
     int32_t res_x, res_y;
 };
-enum { FILTER_BOX = 0, FILTER_GAUSSIAN = 1 };
+enum { FILTER_BOX = 0, FILTER_GAUSSIAN = 1, FILTER_TRIANGLE = 2, FILTER_MITCHELL = 3, FILTER_SINC = 4 };
 struct FilmDesc {
-    int32_t res_x, res_y;
+    int32_t res_x, res_y;        // full_resolution (film.rs:19)
     int32_t filter;
     Float radius_x, radius_y;
     Float gaussian_alpha;
+    Float mitchell_b, mitchell_c;
+    Float sinc_tau;
+    Float crop_window[4];        // {min.x, min.y, max.x, max.y} (film.rs:33,41-50); all zero = {0, 0, 1, 1}
+    Float max_sample_luminance;  // film.rs:27; <= 0 = infinity
 };
 enum { LIGHTS_UNIFORM = 0, LIGHTS_POWER = 1 };
 struct PathDesc {
@@ -910,24 +914,65 @@ inline RGB path_li(const Scene& scene, Ray ray, Sampler& s, int max_depth, Float
 struct Film {
     FilmDesc d;
     Float table[16 * 16];
+    int px0, py0, px1, py1;                  // cropped_pixel_bounds (film.rs:41-50)
     int sb_x0, sb_y0, sb_x1, sb_y1;          // sample bounds (D42 FIX)
+    Float max_lum;
     void init(const FilmDesc& desc) {
         d = desc;
+        const Float* cw = d.crop_window;
+        const bool full = cw[0] == 0.0f && cw[1] == 0.0f && cw[2] == 0.0f && cw[3] == 0.0f;
+        const Float c0x = full ? 0.0f : cw[0], c0y = full ? 0.0f : cw[1], c1x = full ? 1.0f : cw[2], c1y = full ? 1.0f : cw[3];
+        px0 = (int)std::ceil((Float)d.res_x * c0x);                                            // film.rs:41-50
+        py0 = (int)std::ceil((Float)d.res_y * c0y);
+        px1 = (int)std::ceil((Float)d.res_x * c1x);
+        py1 = (int)std::ceil((Float)d.res_y * c1y);
+        max_lum = d.max_sample_luminance > 0.0f ? d.max_sample_luminance : std::numeric_limits<Float>::infinity();
         for (int y = 0; y < 16; ++y)
             for (int x = 0; x < 16; ++x) {
                 Float px = ((Float)x + 0.5f) * d.radius_x / 16.0f, py = ((Float)y + 0.5f) * d.radius_y / 16.0f;   // film.rs:53-63
                 table[y * 16 + x] = evaluate(px, py);
             }
-        sb_x0 = (int)std::floor(0.0f + 0.5f - d.radius_x);
-        sb_y0 = (int)std::floor(0.0f + 0.5f - d.radius_y);
-        sb_x1 = (int)std::ceil((Float)d.res_x - 0.5f + d.radius_x);
-        sb_y1 = (int)std::ceil((Float)d.res_y - 0.5f + d.radius_y);
+        // Film::get_sample_bounds (film.rs:76-81; D42 FIX: pbrt-v3 floor(min + 0.5 - r), ceil(max - 0.5 + r))
+        sb_x0 = (int)std::floor((Float)px0 + 0.5f - d.radius_x);
+        sb_y0 = (int)std::floor((Float)py0 + 0.5f - d.radius_y);
+        sb_x1 = (int)std::ceil((Float)px1 - 0.5f + d.radius_x);
+        sb_y1 = (int)std::ceil((Float)py1 - 0.5f + d.radius_y);
     }
+    int width() const { return px1 - px0; }
+    int height() const { return py1 - py0; }
+    size_t index(int x, int y) const { return (size_t)(y - py0) * (size_t)width() + (size_t)(x - px0); }
     Float gaussian(Float v, Float expv) const { return fmax_(std::exp(-d.gaussian_alpha * v * v) - expv, 0.0f); }   // gaussian.rs:29-31
+    Float mitchell_1d(Float x) const {                                                         // mitchell.rs:24-38
+        const Float B = d.mitchell_b, C = d.mitchell_c;
+        x = std::fabs(2.0f * x);
+        if (x > 1.0f)
+            return ((-B - 6.0f * C) * x * x * x + (6.0f * B + 30.0f * C) * x * x + (-12.0f * B - 48.0f * C) * x + (8.0f * B + 24.0f * C)) * (1.0f / 6.0f);
+        return ((12.0f - 9.0f * B - 6.0f * C) * x * x * x + (-18.0f + 12.0f * B + 6.0f * C) * x * x + (6.0f - 2.0f * B)) * (1.0f / 6.0f);
+    }
+    static Float sinc(Float x) {                                                               // sinc.rs:22-29
+        x = std::fabs(x);
+        if (x < 1e-5f) return 1.0f;
+        return std::sin(kPi * x) / (kPi * x);
+    }
+    Float windowed_sinc(Float x, Float radius) const {                                         // sinc.rs:30-38
+        x = std::fabs(x);
+        if (x > radius) return 0.0f;
+        const Float lanczos = sinc(x / d.sinc_tau);
+        return sinc(x) * lanczos;
+    }
     Float evaluate(Float x, Float y) const {
         if (d.filter == FILTER_BOX) return 1.0f;                                               // boxf.rs:26-28
+        if (d.filter == FILTER_TRIANGLE) return fmax_(d.radius_x - std::fabs(x), 0.0f) * fmax_(d.radius_y - std::fabs(y), 0.0f);   // triangle.rs:20-22
+        if (d.filter == FILTER_MITCHELL) return mitchell_1d(x * (1.0f / d.radius_x)) * mitchell_1d(y * (1.0f / d.radius_y));     // mitchell.rs:42-45
+        if (d.filter == FILTER_SINC) return windowed_sinc(x, d.radius_x) * windowed_sinc(y, d.radius_y);                         // sinc.rs:42-44
         Float ex = std::exp(-d.gaussian_alpha * d.radius_x * d.radius_x), ey = std::exp(-d.gaussian_alpha * d.radius_y * d.radius_y);
         return gaussian(x, ex) * gaussian(y, ey);
+    }
+    // FilmTile::add_sample (film.rs:259-261): luminance clamp
+    RGB clamp_luminance(RGB l) const {
+        const Float y = y_value(l);
+        if (y > max_lum) l = l * (max_lum / y);
+        return l;
     }
     // film.rs:252-295 FilmTile::add_sample footprint + weights (D43, D44 FIX); calls fn(px, py, filter_weight)
     template <class F>
@@ -935,8 +980,8 @@ struct Film {
         Float dx = pfx - 0.5f, dy = pfy - 0.5f;
         int x0 = (int)std::ceil(dx - d.radius_x), y0 = (int)std::ceil(dy - d.radius_y);
         int x1 = (int)std::floor(dx + d.radius_x) + 1, y1 = (int)std::floor(dy + d.radius_y) + 1;
-        x0 = std::max(x0, 0); y0 = std::max(y0, 0);
-        x1 = std::min(x1, d.res_x); y1 = std::min(y1, d.res_y);
+        x0 = std::max(x0, px0); y0 = std::max(y0, py0);
+        x1 = std::min(x1, px1); y1 = std::min(y1, py1);
         for (int y = y0; y < y1; ++y) {
             Float fy = std::fabs(((Float)y - dy) * (1.0f / d.radius_y) * 16.0f);
             int iy = std::min(15, (int)std::floor(fy));
@@ -970,7 +1015,7 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
     film.init(fd);
     const int W = film.sb_x1 - film.sb_x0, H = film.sb_y1 - film.sb_y0;
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
-    const size_t npix = (size_t)fd.res_x * fd.res_y;
+    const size_t npix = (size_t)film.width() * film.height();  // cropped_pixel_bounds.area() (film.rs:51)
     HaltonTables halton;
     if (pd.sampler == 1) halton.init(W, H);                   // sample_bounds extent (halton.rs:69)
     std::vector<RGB> acc(npix, rgb(0));
@@ -1019,11 +1064,12 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                         Ray ray = cam.generate_ray(pfx, pfy);
                         RGB L = path_li(scene, ray, smp, pd.max_depth, pd.rr_threshold);
                         if (has_nans(L) || y_value(L) < -1e-5f || std::isinf(y_value(L))) L = rgb(0);   // D22 FIX
+                        L = film.clamp_luminance(L);
                         film.footprint(pfx, pfy, [&](int px, int py, Float fw) {
                             RGB c = L * 1.0f * fw;                                              // l * sample_weight * filter_weight
                             if (mode == 1 && !(px == x && py == y)) { strays[tid].push_back(Stray{order, px, py, c, fw}); return; }
                             if (mode == 0 && (px < x0 || px >= x1 || py < y0 || py >= y1)) { strays[tid].push_back(Stray{order, px, py, c, fw}); return; }
-                            size_t o = (size_t)py * fd.res_x + px;
+                            size_t o = film.index(px, py);
                             acc[o] = acc[o] + c;
                             wsum[o] += fw;
                         });
@@ -1043,7 +1089,7 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
         return a.x < b.x;
     });
     for (const Stray& s : all) {
-        size_t o = (size_t)s.y * fd.res_x + s.x;
+        size_t o = film.index(s.x, s.y);
         acc[o] = acc[o] + s.c;
         wsum[o] += s.w;
     }

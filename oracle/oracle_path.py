@@ -27,7 +27,8 @@ class CameraDesc(C.Structure):
 
 class FilmDesc(C.Structure):
     _fields_ = [("res_x", C.c_int32), ("res_y", C.c_int32), ("filter", C.c_int32), ("radius_x", C.c_float),
-                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float)]
+                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float), ("mitchell_b", C.c_float), ("mitchell_c", C.c_float),
+                ("sinc_tau", C.c_float), ("crop_window", C.c_float * 4), ("max_sample_luminance", C.c_float)]
 
 
 class PathDesc(C.Structure):
@@ -39,7 +40,7 @@ class PathDesc(C.Structure):
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2}
 _STRAT = {"uniform": 0, "power": 1}
-_FILTER = {"box": 0, "gaussian": 1}
+_FILTER = {"box": 0, "gaussian": 1, "triangle": 2, "mitchell": 3, "sinc": 4}
 
 
 def material(d):
@@ -90,13 +91,30 @@ def camera_desc(cam):
     return c
 
 
-def film_desc(res, filt="box", radius=(0.5, 0.5), alpha=2.0):
+def film_desc(res, filt="box", radius=(0.5, 0.5), alpha=2.0, b=1.0 / 3.0, c=1.0 / 3.0, tau=3.0, crop=None, max_sample_luminance=0.0):
+    """crop = (x0, y0, x1, y1) fractions of the full resolution (Film::new's crop_window, film.rs:33); None = full image."""
     f = FilmDesc()
     f.res_x, f.res_y = res
     f.filter = _FILTER[filt]
     f.radius_x, f.radius_y = radius
     f.gaussian_alpha = alpha
+    f.mitchell_b, f.mitchell_c, f.sinc_tau = b, c, tau
+    if crop is not None:
+        f.crop_window[:] = crop
+    f.max_sample_luminance = max_sample_luminance
     return f
+
+
+def film_bounds(film):
+    """(cropped_pixel_bounds (x0, y0, x1, y1), sample bounds (x0, y0, x1, y1))."""
+    out = np.zeros(8, np.int32)
+    O.lib().orc_film_bounds(C.byref(film), _p(out))
+    return tuple(int(v) for v in out[:4]), tuple(int(v) for v in out[4:])
+
+
+def film_shape(film):
+    (x0, y0, x1, y1), _ = film_bounds(film)
+    return (y1 - y0, x1 - x0)
 
 
 def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None, sampler="random",
@@ -164,7 +182,7 @@ class Scene:
         """Returns (xyzw [H,W,4] accumulators, seconds)."""
         cd, fd = camera_desc(cam), film
         if out is None:
-            out = np.zeros((fd.res_y, fd.res_x, 4), dtype=np.float32)
+            out = np.zeros(film_shape(fd) + (4,), dtype=np.float32)
         dt = O.lib().orc_render(self.h, C.byref(cd), C.byref(fd), C.byref(path), mode, threads, _p(out))
         return out, dt
 
@@ -191,7 +209,7 @@ def film_add_samples(film, p_film, L_rgb, weight):
     p_film = np.ascontiguousarray(p_film, dtype=np.float32)
     L_rgb = np.ascontiguousarray(L_rgb, dtype=np.float32)
     weight = np.ascontiguousarray(weight, dtype=np.float32)
-    out = np.zeros((film.res_y, film.res_x, 4), dtype=np.float32)
+    out = np.zeros(film_shape(film) + (4,), dtype=np.float32)
     O.lib().orc_film_add_samples(C.byref(film), _p(p_film), _p(L_rgb), _p(weight), len(weight), _p(out))
     return out
 

@@ -21,7 +21,7 @@ NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_pri
 
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS = 0, 1, 2
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
-FILTER_BOX, FILTER_GAUSSIAN = 0, 1
+FILTER_BOX, FILTER_GAUSSIAN, FILTER_TRIANGLE, FILTER_MITCHELL, FILTER_SINC = 0, 1, 2, 3, 4
 LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
 
 
@@ -48,7 +48,8 @@ class CameraDesc(C.Structure):
 
 class FilmDesc(C.Structure):
     _fields_ = [("res_x", C.c_int32), ("res_y", C.c_int32), ("filter", C.c_int32), ("radius_x", C.c_float),
-                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float)]
+                ("radius_y", C.c_float), ("gaussian_alpha", C.c_float), ("mitchell_b", C.c_float), ("mitchell_c", C.c_float),
+                ("sinc_tau", C.c_float), ("crop_window", C.c_float * 4), ("max_sample_luminance", C.c_float)]
 
 
 class PathDesc(C.Structure):
@@ -159,7 +160,7 @@ def lib():
         "pb2_camera_matrices": [vp, vp, vp],
         "pb2_spawn_shadow_rays_device": [vp, vp, vp, u64, vp, vp, vp],
         "pb2_spawn_bounce_rays_device": [vp, vp, vp, u64, vp, vp],
-        "pb2_rng_uniform_floats": [u64, u32, u32, vp],
+        "pb2_rng_uniform_floats": [u64, u32, u32, vp], "pb2_film_bounds": [vp, vp, vp],
         "pb2_film_create": [vp, vp], "pb2_film_destroy": [vp], "pb2_film_clear": [vp],
         "pb2_film_add_samples": [vp, vp, vp, vp, u64], "pb2_film_read_xyzw": [vp, vp],
         "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_device_ptr": [vp, vp, vp],
@@ -355,7 +356,7 @@ class PerspectiveCamera:
 
 _MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS}
 _STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER}
-_FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN}
+_FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN, "triangle": FILTER_TRIANGLE, "mitchell": FILTER_MITCHELL, "sinc": FILTER_SINC}
 
 
 def material_from_dict(d):
@@ -383,17 +384,32 @@ def scene_from_dict(sc):
 
 
 class Film:
-    """Mirror of src/core/film.rs Film (+ FilmTile::add_sample), accumulators resident on the device."""
+    """Mirror of src/core/film.rs Film (+ FilmTile::add_sample), accumulators resident on the device.  filter: "box",
+    "gaussian" (alpha), "triangle", "mitchell" (b, c), "sinc" (tau) — src/filters/*.rs; crop = (x0, y0, x1, y1) fractions of the
+    full resolution (Film::new's crop_window); max_sample_luminance as in Film::new (None = infinity).  `res` is the size of
+    the stored image (cropped_pixel_bounds), `full_res` the full resolution."""
 
-    def __init__(self, res, filter="box", radius=(0.5, 0.5), alpha=2.0):
+    def __init__(self, res, filter="box", radius=(0.5, 0.5), alpha=2.0, b=1.0 / 3.0, c=1.0 / 3.0, tau=3.0, crop=None, max_sample_luminance=None):
         self.desc = FilmDesc()
         self.desc.res_x, self.desc.res_y = res
         self.desc.filter = _FILTER[filter]
         self.desc.radius_x, self.desc.radius_y = radius
         self.desc.gaussian_alpha = alpha
-        self.res = tuple(res)
+        self.desc.mitchell_b, self.desc.mitchell_c, self.desc.sinc_tau = b, c, tau
+        if crop is not None:
+            self.desc.crop_window[:] = crop
+        self.desc.max_sample_luminance = 0.0 if max_sample_luminance is None else max_sample_luminance
+        self.full_res = tuple(res)
         self.h = C.c_void_p()
         check(lib().pb2_film_create(C.byref(self.desc), C.byref(self.h)))
+        self.pixel_bounds, self.sample_bounds = self.bounds()
+        self.res = (self.pixel_bounds[2] - self.pixel_bounds[0], self.pixel_bounds[3] - self.pixel_bounds[1])
+
+    def bounds(self):
+        """(cropped_pixel_bounds, sample bounds), each (x0, y0, x1, y1) with exclusive maxima."""
+        pb, sb = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        check(lib().pb2_film_bounds(self.h, pb, sb))
+        return tuple(pb), tuple(sb)
 
     def destroy(self):
         if self.h:

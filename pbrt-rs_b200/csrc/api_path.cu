@@ -25,15 +25,18 @@ struct pb2_film {
     float4* d_stray_vals = nullptr;
     uint32_t stray_capacity = 0;
     unsigned long long* d_counters = nullptr;      // C_COUNT slots, used when the film is filled without a wavefront
+    int px0, py0, px1, py1;                        // cropped_pixel_bounds (film.rs:41-50)
     int sb_x0, sb_y0, sb_x1, sb_y1;
     int device = 0;
+    size_t n_pixels() const { return (size_t)(px1 - px0) * (size_t)(py1 - py0); }
 };
 
 namespace pb2 {
 
 static FilmView film_view(const pb2_film* f) {
     FilmView v;
-    v.res_x = f->desc.res_x; v.res_y = f->desc.res_y;
+    v.px0 = f->px0; v.py0 = f->py0; v.px1 = f->px1; v.py1 = f->py1;
+    v.max_lum = f->desc.max_sample_luminance > 0.0f ? f->desc.max_sample_luminance : __builtin_huge_valf();
     v.sb_x0 = f->sb_x0; v.sb_y0 = f->sb_y0; v.sb_w = f->sb_x1 - f->sb_x0; v.sb_h = f->sb_y1 - f->sb_y0;
     v.radius_x = f->desc.radius_x; v.radius_y = f->desc.radius_y;
     v.exact = (f->desc.filter == PB2_FILTER_BOX && f->desc.radius_x == 0.5f && f->desc.radius_y == 0.5f) ? 1 : 0;
@@ -344,25 +347,58 @@ int pb2_film_create(const pb2_film_desc* desc, pb2_film** out) {
     *out = nullptr;
     if (desc->res_x <= 0 || desc->res_y <= 0 || !(desc->radius_x > 0.0f) || !(desc->radius_y > 0.0f))
         return set_error(PB2_ERR_INVALID, "bad film description");
-    if (desc->filter != PB2_FILTER_BOX && desc->filter != PB2_FILTER_GAUSSIAN) return set_error(PB2_ERR_INVALID, "unknown filter %d", desc->filter);
+    if (desc->filter < PB2_FILTER_BOX || desc->filter > PB2_FILTER_SINC) return set_error(PB2_ERR_INVALID, "unknown filter %d", desc->filter);
+    if (desc->filter == PB2_FILTER_SINC && !(desc->sinc_tau > 0.0f)) return set_error(PB2_ERR_INVALID, "LanczosSincFilter needs tau > 0");
+    const float* cw = desc->crop_window;
+    const bool full = cw[0] == 0.0f && cw[1] == 0.0f && cw[2] == 0.0f && cw[3] == 0.0f;
+    const float c0x = full ? 0.0f : cw[0], c0y = full ? 0.0f : cw[1], c1x = full ? 1.0f : cw[2], c1y = full ? 1.0f : cw[3];
+    if (!(c0x >= 0.0f && c0y >= 0.0f && c1x <= 1.0f && c1y <= 1.0f && c0x < c1x && c0y < c1y))
+        return set_error(PB2_ERR_INVALID, "crop window {%g, %g, %g, %g} is not inside [0, 1]^2 with min < max", c0x, c0y, c1x, c1y);
     pb2_film* f = new pb2_film();
     f->desc = *desc;
-    // Film::new filter table (film.rs:53-63) with BoxFilter / GaussianFilter::evaluate (boxf.rs:26-28, gaussian.rs:17-39)
-    const float a = desc->gaussian_alpha;
-    const float ex = std::exp(-a * desc->radius_x * desc->radius_x), ey = std::exp(-a * desc->radius_y * desc->radius_y);
+    // cropped_pixel_bounds (film.rs:41-50)
+    f->px0 = (int)std::ceil((float)desc->res_x * c0x);
+    f->py0 = (int)std::ceil((float)desc->res_y * c0y);
+    f->px1 = (int)std::ceil((float)desc->res_x * c1x);
+    f->py1 = (int)std::ceil((float)desc->res_y * c1y);
+    if (f->px1 <= f->px0 || f->py1 <= f->py0) { delete f; return set_error(PB2_ERR_INVALID, "crop window holds no pixel"); }
+    // Film::new filter table (film.rs:53-63) with Filter::evaluate (boxf.rs:26-28, gaussian.rs:17-39, triangle.rs:20-22,
+    // mitchell.rs:24-45, sinc.rs:22-44); exp / sin are evaluated once here by the host's libm
+    const float a = desc->gaussian_alpha, rx = desc->radius_x, ry = desc->radius_y;
+    const float ex = std::exp(-a * rx * rx), ey = std::exp(-a * ry * ry);
+    const float B = desc->mitchell_b, Cc = desc->mitchell_c, tau = desc->sinc_tau;
+    auto mitchell_1d = [&](float x) {
+        x = std::fabs(2.0f * x);
+        if (x > 1.0f) return ((-B - 6.0f * Cc) * x * x * x + (6.0f * B + 30.0f * Cc) * x * x + (-12.0f * B - 48.0f * Cc) * x + (8.0f * B + 24.0f * Cc)) * (1.0f / 6.0f);
+        return ((12.0f - 9.0f * B - 6.0f * Cc) * x * x * x + (-18.0f + 12.0f * B + 6.0f * Cc) * x * x + (6.0f - 2.0f * B)) * (1.0f / 6.0f);
+    };
+    auto sinc = [](float x) {
+        x = std::fabs(x);
+        if (x < 1e-5f) return 1.0f;
+        return std::sin(PB2_PI * x) / (PB2_PI * x);
+    };
+    auto windowed_sinc = [&](float x, float radius) {
+        x = std::fabs(x);
+        if (x > radius) return 0.0f;
+        const float lanczos = sinc(x / tau);
+        return sinc(x) * lanczos;
+    };
     for (int y = 0; y < 16; ++y)
         for (int x = 0; x < 16; ++x) {
-            const float px = ((float)x + 0.5f) * desc->radius_x / 16.0f, py = ((float)y + 0.5f) * desc->radius_y / 16.0f;
+            const float px = ((float)x + 0.5f) * rx / 16.0f, py = ((float)y + 0.5f) * ry / 16.0f;
             float w = 1.0f;
             if (desc->filter == PB2_FILTER_GAUSSIAN) w = std::fmax(std::exp(-a * px * px) - ex, 0.0f) * std::fmax(std::exp(-a * py * py) - ey, 0.0f);
+            else if (desc->filter == PB2_FILTER_TRIANGLE) w = std::fmax(rx - std::fabs(px), 0.0f) * std::fmax(ry - std::fabs(py), 0.0f);
+            else if (desc->filter == PB2_FILTER_MITCHELL) w = mitchell_1d(px * (1.0f / rx)) * mitchell_1d(py * (1.0f / ry));
+            else if (desc->filter == PB2_FILTER_SINC) w = windowed_sinc(px, rx) * windowed_sinc(py, ry);
             f->table[y * 16 + x] = w;
         }
     // Film::get_sample_bounds (film.rs:76-81, D42 FIX)
-    f->sb_x0 = (int)std::floor(0.0f + 0.5f - desc->radius_x);
-    f->sb_y0 = (int)std::floor(0.0f + 0.5f - desc->radius_y);
-    f->sb_x1 = (int)std::ceil((float)desc->res_x - 0.5f + desc->radius_x);
-    f->sb_y1 = (int)std::ceil((float)desc->res_y - 0.5f + desc->radius_y);
-    const size_t npix = (size_t)desc->res_x * desc->res_y;
+    f->sb_x0 = (int)std::floor((float)f->px0 + 0.5f - desc->radius_x);
+    f->sb_y0 = (int)std::floor((float)f->py0 + 0.5f - desc->radius_y);
+    f->sb_x1 = (int)std::ceil((float)f->px1 - 0.5f + desc->radius_x);
+    f->sb_y1 = (int)std::ceil((float)f->py1 - 0.5f + desc->radius_y);
+    const size_t npix = f->n_pixels();
     f->stray_capacity = 1u << 20;
     const size_t stray_bytes = (size_t)f->stray_capacity * (2 * 8 + 2 * 4) + film_sort_scratch_bytes(f->stray_capacity) + 1024;
     cudaError_t e = cudaGetDevice(&f->device);
@@ -390,7 +426,7 @@ int pb2_film_destroy(pb2_film* f) {
 
 int pb2_film_clear(pb2_film* f) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
-    const size_t npix = (size_t)f->desc.res_x * f->desc.res_y;
+    const size_t npix = f->n_pixels();
     PB2_CUDA(cudaMemset(f->d_xyzw, 0, npix * 16));
     PB2_CUDA(cudaMemset(f->d_acc, 0, npix * 16));
     return PB2_OK;
@@ -416,13 +452,13 @@ int pb2_film_add_samples(pb2_film* f, const float* p_film, const float* L_rgb, c
 
 int pb2_film_read_xyzw(pb2_film* f, float* out) {
     if (!f || !out) return set_error(PB2_ERR_INVALID, "null argument");
-    PB2_CUDA(cudaMemcpy(out, f->d_xyzw, (size_t)f->desc.res_x * f->desc.res_y * 16, cudaMemcpyDeviceToHost));
+    PB2_CUDA(cudaMemcpy(out, f->d_xyzw, f->n_pixels() * 16, cudaMemcpyDeviceToHost));
     return PB2_OK;
 }
 
 int pb2_film_resolve_rgb(pb2_film* f, float scale, float* rgb) {
     if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
-    const size_t npix = (size_t)f->desc.res_x * f->desc.res_y;
+    const size_t npix = f->n_pixels();
     float* d = nullptr;
     PB2_CUDA(cudaMalloc(&d, npix * 12));
     film_resolve(film_view(f), scale, d, 0);
@@ -439,7 +475,7 @@ int pb2_film_write_image(pb2_film* f, const char* filename, float scale) {
     const size_t dot = name.rfind('.');
     const std::string ext = dot == std::string::npos ? "" : name.substr(dot);
     if (ext != ".pfm" && ext != ".ppm") return set_error(PB2_ERR_INVALID, "unsupported image extension '%s' (.pfm or .ppm)", ext.c_str());
-    const int w = f->desc.res_x, h = f->desc.res_y;
+    const int w = f->px1 - f->px0, h = f->py1 - f->py0;      // cropped_pixel_bounds, as Film::write_image hands to write_image
     std::vector<float> rgb((size_t)w * h * 3);
     int rc = pb2_film_resolve_rgb(f, scale, rgb.data());
     if (rc != PB2_OK) return rc;
@@ -471,7 +507,14 @@ int pb2_film_write_image(pb2_film* f, const char* filename, float scale) {
 int pb2_film_device_ptr(pb2_film* f, void** d_xyzw, uint64_t* n_floats) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     if (d_xyzw) *d_xyzw = f->d_xyzw;
-    if (n_floats) *n_floats = (uint64_t)f->desc.res_x * f->desc.res_y * 4;
+    if (n_floats) *n_floats = (uint64_t)f->n_pixels() * 4;
+    return PB2_OK;
+}
+
+int pb2_film_bounds(const pb2_film* f, int32_t pixel_bounds[4], int32_t sample_bounds[4]) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    if (pixel_bounds) { pixel_bounds[0] = f->px0; pixel_bounds[1] = f->py0; pixel_bounds[2] = f->px1; pixel_bounds[3] = f->py1; }
+    if (sample_bounds) { sample_bounds[0] = f->sb_x0; sample_bounds[1] = f->sb_y0; sample_bounds[2] = f->sb_x1; sample_bounds[3] = f->sb_y1; }
     return PB2_OK;
 }
 
@@ -508,7 +551,8 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     // box filter, r = 0.5 sample bounds: streams are indexed by image pixel
     FilmView fv;
     memset(&fv, 0, sizeof fv);
-    fv.res_x = cam->res_x; fv.res_y = cam->res_y; fv.sb_w = cam->res_x; fv.sb_h = cam->res_y; fv.radius_x = fv.radius_y = 0.5f;
+    fv.px1 = cam->res_x; fv.py1 = cam->res_y; fv.sb_w = cam->res_x; fv.sb_h = cam->res_y; fv.radius_x = fv.radius_y = 0.5f;
+    fv.max_lum = __builtin_huge_valf();
     int32_t* d_xy = nullptr;
     uint32_t* d_s = nullptr;
     float *d_L = nullptr, *d_pf = nullptr;
@@ -579,7 +623,7 @@ int pb2_nccl_shutdown(void) {
 int pb2_film_reduce(pb2_film* f, int root, void* stream) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     if (!g_comm) return set_error(PB2_ERR_STATE, "pb2_nccl_init has not been called");
-    const size_t count = (size_t)f->desc.res_x * f->desc.res_y * 4;
+    const size_t count = f->n_pixels() * 4;
     ncclResult_t r = g_nccl.Reduce(f->d_xyzw, f->d_xyzw, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
     if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString(r));
     return PB2_OK;

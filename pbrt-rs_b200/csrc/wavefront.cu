@@ -659,8 +659,8 @@ __device__ __forceinline__ void film_footprint(const FilmView& f, float pfx, flo
     const float dx = pfx - 0.5f, dy = pfy - 0.5f;
     int x0 = (int)ceilf(dx - f.radius_x), y0 = (int)ceilf(dy - f.radius_y);
     int x1 = (int)floorf(dx + f.radius_x) + 1, y1 = (int)floorf(dy + f.radius_y) + 1;
-    x0 = max(x0, 0); y0 = max(y0, 0);
-    x1 = min(x1, f.res_x); y1 = min(y1, f.res_y);
+    x0 = max(x0, f.px0); y0 = max(y0, f.py0);
+    x1 = min(x1, f.px1); y1 = min(y1, f.py1);
     const float inv_rx = 1.0f / f.radius_x, inv_ry = 1.0f / f.radius_y;
     for (int y = y0; y < y1; ++y) {
         const int iy = min(15, (int)floorf(fabsf(((float)y - dy) * inv_ry * 16.0f)));
@@ -674,14 +674,19 @@ __device__ __forceinline__ rgb3 guard_radiance(rgb3 L) {                  // int
     if (any_nan(L) || luminance(L) < -1e-5f || isinf(luminance(L))) return gray(0.0f);
     return L;
 }
+__device__ __forceinline__ rgb3 clamp_luminance(const FilmView& f, rgb3 L) {   // FilmTile::add_sample, film.rs:259-261
+    const float y = luminance(L);
+    if (y > f.max_lum) L = L * (f.max_lum / y);
+    return L;
+}
 __device__ __forceinline__ void film_atomic_add(const FilmView& f, int px, int py, rgb3 c, float w) {
-    float* a = reinterpret_cast<float*>(f.acc + ((size_t)py * f.res_x + px));
+    float* a = reinterpret_cast<float*>(f.acc + f.index(px, py));
     atomicAdd(a, c.r); atomicAdd(a + 1, c.g); atomicAdd(a + 2, c.b); atomicAdd(a + 3, w);
 }
 __device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long* counters, unsigned long long order, int px, int py, rgb3 c, float w) {
     const unsigned long long pos = atomicAdd(&counters[C_STRAYS], 1ull);
     if (pos < f.stray_capacity) {
-        f.stray_keys[pos] = ((unsigned long long)((size_t)py * f.res_x + px) << 40) | (order & 0xFFFFFFFFFFull);
+        f.stray_keys[pos] = ((unsigned long long)f.index(px, py) << 40) | (order & 0xFFFFFFFFFFull);
         f.stray_vals[pos] = make_float4(c.r, c.g, c.b, w);
     } else {
         atomicAdd(&counters[C_STRAY_OVERFLOW], 1ull);                     // still accumulated, but in arrival order
@@ -693,12 +698,12 @@ __device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long
 __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map, FilmView f, PathBuffers b, int n_samples) {
     for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < map.n_pix; pix += gridDim.x * blockDim.x) {
         const int x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w), y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
-        const bool inside = x >= 0 && y >= 0 && x < f.res_x && y < f.res_y;
-        float4 acc = inside ? f.acc[(size_t)y * f.res_x + x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool inside = x >= f.px0 && y >= f.py0 && x < f.px1 && y < f.py1;
+        float4 acc = inside ? f.acc[f.index(x, y)] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < n_samples; ++s) {
             const uint64_t slot = (uint64_t)s * map.n_pix + pix;
             const float4 Lf = b.L[slot];
-            const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
+            const rgb3 L = clamp_luminance(f, guard_radiance(mkc(Lf.x, Lf.y, Lf.z)));
             const SlotInfo si = slot_info(map, f, slot);
             PathSampler rng;
             rng.start(map.smp, si);
@@ -712,14 +717,14 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map,
                 else film_stray(f, b.counters, si.seq, px, py, c, fw);
             });
         }
-        if (inside) f.acc[(size_t)y * f.res_x + x] = acc;
+        if (inside) f.acc[f.index(x, y)] = acc;
     }
 }
 // General mode: one thread per path, atomics into the call's accumulators.
 __global__ void __launch_bounds__(kThreads) k_film_accumulate_atomic(uint64_t n, PathMap map, FilmView f, PathBuffers b) {
     for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
         const float4 Lf = b.L[slot];
-        const rgb3 L = guard_radiance(mkc(Lf.x, Lf.y, Lf.z));
+        const rgb3 L = clamp_luminance(f, guard_radiance(mkc(Lf.x, Lf.y, Lf.z)));
         const SlotInfo si = slot_info(map, f, slot);
         PathSampler rng;
         rng.start(map.smp, si);
@@ -754,7 +759,7 @@ __global__ void __launch_bounds__(kThreads) k_fill_index(uint32_t* idx, unsigned
 }
 // Film::merge_film_tile (film.rs:111-123): XYZ of the call's RGB sums is added to the film; the call accumulators reset.
 __global__ void __launch_bounds__(kThreads) k_film_merge(FilmView f, unsigned long long* counters) {
-    const size_t n = (size_t)f.res_x * f.res_y;
+    const size_t n = f.n_pixels();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 a = f.acc[i];
         float x, y, z;
@@ -769,14 +774,14 @@ __global__ void __launch_bounds__(kThreads) k_film_merge(FilmView f, unsigned lo
 // FilmTile::add_sample for explicit samples (pb2_film_add_samples): atomics, any filter.
 __global__ void __launch_bounds__(kThreads) k_film_add_samples(FilmView f, const float2* pf, const float* L, const float* w, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const rgb3 c = mkc(L[3 * i], L[3 * i + 1], L[3 * i + 2]);
+        const rgb3 c = clamp_luminance(f, mkc(L[3 * i], L[3 * i + 1], L[3 * i + 2]));
         const float sw = w[i];
         film_footprint(f, pf[i].x, pf[i].y, [&](int px, int py, float fw) { film_atomic_add(f, px, py, c * sw * fw, fw); });
     }
 }
 // Film::write_image (film.rs:153-178)
 __global__ void __launch_bounds__(kThreads) k_film_resolve(FilmView f, float scale, float* rgb) {
-    const size_t n = (size_t)f.res_x * f.res_y;
+    const size_t n = f.n_pixels();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 p = f.xyzw[i];
         rgb3 c = from_xyz(p.x, p.y, p.z);

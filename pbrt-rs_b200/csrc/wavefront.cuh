@@ -28,8 +28,9 @@ struct ShadeView {
 
 // Film geometry: image, sample bounds (film.rs:76-81 with D42), filter radius and its 16x16 table (film.rs:53-63).
 struct FilmView {
-    int res_x, res_y;
+    int px0, py0, px1, py1;       // cropped_pixel_bounds (film.rs:41-50): the pixels the film stores, row-major
     int sb_x0, sb_y0, sb_w, sb_h;
+    float max_lum;                // max_sample_luminance (film.rs:259-261), +inf when unset
     float radius_x, radius_y;
     int exact;                    // box filter, r = 0.5: ordered accumulation (bit-reproducible)
     const float* table;           // 256 floats
@@ -38,6 +39,9 @@ struct FilmView {
     unsigned long long* stray_keys;
     float4* stray_vals;
     uint32_t stray_capacity;
+    __host__ __device__ int width() const { return px1 - px0; }
+    __host__ __device__ size_t n_pixels() const { return (size_t)(px1 - px0) * (size_t)(py1 - py0); }
+    __host__ __device__ size_t index(int x, int y) const { return (size_t)(y - py0) * (size_t)(px1 - px0) + (size_t)(x - px0); }
 };
 
 // HaltonSampler state shared by all paths (samplers/halton.rs:24-37 + the permutation table of lowdiscrepancy.rs:333-349);

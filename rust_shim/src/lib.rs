@@ -18,7 +18,9 @@ pub struct pb2_light { pub ty: i32 /* 0 point, 1 area, 2 spot, 3 distant */, pub
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_camera { pub pos: [f32; 3], pub look: [f32; 3], pub up: [f32; 3], pub fov: f32, pub res_x: i32, pub res_y: i32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct pb2_film_desc { pub res_x: i32, pub res_y: i32, pub filter: i32, pub radius_x: f32, pub radius_y: f32, pub gaussian_alpha: f32 }
+pub struct pb2_film_desc { pub res_x: i32, pub res_y: i32, pub filter: i32 /* 0 box, 1 gaussian, 2 triangle, 3 mitchell, 4 sinc */,
+                           pub radius_x: f32, pub radius_y: f32, pub gaussian_alpha: f32, pub mitchell_b: f32, pub mitchell_c: f32, pub sinc_tau: f32,
+                           pub crop_window: [f32; 4] /* all zero = whole image */, pub max_sample_luminance: f32 /* <= 0 = infinity */ }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_path_desc { pub max_depth: i32, pub rr_threshold: f32, pub light_strategy: i32, pub spp: i32,
                            pub sample_begin: i32, pub sample_end: i32,

@@ -326,3 +326,49 @@ def test_pixel_sampler_argument_errors(gpu, scenes):
         z.render(film)
     with pytest.raises(gpu.Pb2Error):
         gpu.PathIntegrator(accel, cam, spp=16, sampler="zerotwo", n_sampled_dimensions=200).render(film)
+
+
+@pytest.mark.parametrize("filt,fkw", [("box", {}), ("triangle", dict(radius=(1.5, 1.0))), ("mitchell", dict(radius=(2.0, 2.0), b=1 / 3, c=1 / 3)),
+                                     ("sinc", dict(radius=(3.0, 3.0), tau=3.0))])
+def test_film_crop_clamp_and_filters_match_oracle(gpu, OP, scenes, filt, fkw):
+    """Film::new's crop window, max_sample_luminance and the Triangle / Mitchell / LanczosSinc filters (film.rs:31-75,259-261,
+    src/filters/*.rs): bounds equal the oracle's, the cropped render's accumulators equal the oracle's (bit for bit with the box
+    filter, rtol 1e-5 with wide filters: float atomics), and pb2_film_add_samples clamps like FilmTile::add_sample."""
+    cam = dict(scenes.C2_CAMERA, res=(96, 64))
+    kw = dict(max_depth=4, rr_threshold=1.0, light_strategy="uniform", spp=8)
+    accel, camera, integ, ref = setup_scene(gpu, OP, scenes.scene_c2(), cam, **kw)
+    crop = (0.26, 0.1, 0.83, 0.77)
+    film = gpu.Film(cam["res"], filter=filt, crop=crop, max_sample_luminance=1.5, **fkw)
+    fd = OP.film_desc(cam["res"], filt, fkw.get("radius", (0.5, 0.5)), b=fkw.get("b", 1 / 3), c=fkw.get("c", 1 / 3), tau=fkw.get("tau", 3.0),
+                      crop=crop, max_sample_luminance=1.5)
+    assert (film.pixel_bounds, film.sample_bounds) == OP.film_bounds(fd)
+    assert film.res == (film.pixel_bounds[2] - film.pixel_bounds[0], film.pixel_bounds[3] - film.pixel_bounds[1]) and film.full_res == (96, 64)
+    integ.render(film, 0, 5)
+    integ.render(film, 5, 8)
+    got = film.read_xyzw()
+    want, _ = ref.render(cam, fd, OP.path_desc(sample_begin=0, sample_end=5, **kw), mode=1)
+    want, _ = ref.render(cam, fd, OP.path_desc(sample_begin=5, sample_end=8, **kw), mode=1, out=want)
+    assert got.shape == want.shape == (film.res[1], film.res[0], 4)
+    if filt == "box":
+        assert np.array_equal(bits(got), bits(want))
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
+    unclamped = gpu.Film(cam["res"], filter=filt, crop=crop, **fkw)
+    integ.render(unclamped)
+    assert unclamped.resolve_rgb().max() > film.resolve_rgb().max()                 # the light is visible: its samples were clamped
+    # explicit samples
+    rng = np.random.default_rng(8)
+    n = 5000
+    pf = rng.uniform(20, 85, size=(n, 2)).astype(np.float32)
+    L = rng.uniform(0, 4, size=(n, 3)).astype(np.float32)
+    w = rng.uniform(0.5, 1.0, size=n).astype(np.float32)
+    film.clear()
+    film.add_samples(pf, L, w)
+    np.testing.assert_allclose(film.read_xyzw(), OP.film_add_samples(fd, pf, L, w), rtol=2e-5, atol=1e-5)
+
+
+def test_film_argument_errors(gpu):
+    for bad in (dict(crop=(0.5, 0.5, 0.4, 0.9)), dict(crop=(-0.1, 0.0, 1.0, 1.0)), dict(crop=(0.0, 0.0, 1.0, 1.2)), dict(filter="sinc", tau=0.0),
+                dict(radius=(0.0, 1.0)), dict(crop=(0.501, 0.0, 0.502, 1.0))):
+        with pytest.raises(gpu.Pb2Error):
+            gpu.Film((16, 16), **bad)

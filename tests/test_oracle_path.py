@@ -168,3 +168,40 @@ def test_pixel_samplers_render_and_converge(OP, scenes, sampler, kw):
     whole, _ = sc.render(cam, fd, OP.path_desc(sampler=sampler, sample_begin=40, sample_end=64, **base, **kw), out=half)
     full, _ = sc.render(cam, fd, OP.path_desc(sampler=sampler, **base, **kw))
     assert np.allclose(whole, full, rtol=1e-5, atol=1e-6)
+
+
+def test_film_crop_window_clamp_and_filters(OP, scenes):
+    """Film::new (film.rs:31-75): cropped_pixel_bounds = ceil(res * crop), sample bounds around it; a cropped render equals the
+    same pixels of the full render for the box filter (a pixel only sees its own samples); max_sample_luminance rescales a
+    sample to that luminance (film.rs:259-261); Triangle / Mitchell / LanczosSinc tables (src/filters/*.rs) against closed forms."""
+    fd = OP.film_desc((40, 30), crop=(0.25, 0.2, 0.8, 0.9))
+    pb, sb = OP.film_bounds(fd)
+    assert pb == (10, 6, 32, 27) and sb == (10, 6, 32, 27)
+    pb, sb = OP.film_bounds(OP.film_desc((40, 30), "gaussian", (2.0, 2.0), crop=(0.25, 0.2, 0.8, 0.9)))
+    assert pb == (10, 6, 32, 27) and sb == (8, 4, 34, 29)
+    assert OP.film_bounds(OP.film_desc((40, 30)))[0] == (0, 0, 40, 30)
+    sc = OP.Scene(scenes.scene_c2())
+    cam = dict(scenes.C2_CAMERA, res=(40, 30))
+    pd = OP.path_desc(max_depth=3, spp=4)
+    full, _ = sc.render(cam, OP.film_desc((40, 30)), pd)
+    crop, _ = sc.render(cam, fd, pd)
+    assert crop.shape == (21, 22, 4)
+    # per-(pixel, sample) streams are indexed inside the sample bounds, so the crop draws different numbers: same estimator
+    assert abs(OP.resolve_rgb(crop).mean() - OP.resolve_rgb(full[6:27, 10:32]).mean()) / OP.resolve_rgb(crop).mean() < 0.15
+    # luminance clamp on explicit samples
+    L = np.array([[10.0, 10.0, 10.0], [0.1, 0.2, 0.3]], np.float32)
+    pf = np.array([[1.5, 1.5], [2.5, 1.5]], np.float32)
+    got = OP.film_add_samples(OP.film_desc((4, 4), max_sample_luminance=2.0), pf, L, np.ones(2, np.float32))
+    rgb = OP.resolve_rgb(got)
+    assert np.allclose(rgb[1, 1], 2.0, rtol=1e-5) and np.allclose(rgb[1, 2], L[1], rtol=1e-5)
+    # filter tables
+    t = OP.film_table(OP.film_desc((4, 4), "triangle", (2.0, 1.0))).reshape(16, 16)
+    x = (np.arange(16) + 0.5) * 2.0 / 16
+    y = (np.arange(16) + 0.5) * 1.0 / 16
+    assert np.allclose(t, np.outer(1.0 - y, 2.0 - x), rtol=1e-6)
+    t = OP.film_table(OP.film_desc((4, 4), "mitchell", (2.0, 2.0), b=1 / 3, c=1 / 3)).reshape(16, 16)
+    assert t[0, 0] == t.max() and t.min() < 0 and np.allclose(t, t.T)                 # Mitchell has negative lobes
+    t = OP.film_table(OP.film_desc((4, 4), "sinc", (4.0, 4.0), tau=3.0)).reshape(16, 16)
+    xs = (np.arange(16) + 0.5) * 4.0 / 16
+    w = np.sinc(xs) * np.sinc(xs / 3.0)
+    assert np.allclose(t, np.outer(w, w), atol=2e-6)
