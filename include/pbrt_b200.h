@@ -149,6 +149,10 @@ int pb2_set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int
 int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
                      const uint32_t* tri_material, const pb2_material* mats, uint32_t n_mats,
                      const pb2_light* lights, uint32_t n_lights, pb2_scene** out);
+/* TriangleMesh's optional per-vertex shading normals `n`, tangents `s` and parametric coordinates `uv`
+ * (src/shapes/triangle.rs:17-26; 3 / 3 / 2 floats per vertex, world space, NULL = absent), as Triangle::intersect (:251-311),
+ * Triangle::get_uvs (:60-72) and Triangle::sample (:338-341) use them.  Call before pb2_scene_build_bvh. */
+int pb2_scene_set_shading_geometry(pb2_scene* scene, const float* normals, const float* tangents, const float* uvs);
 int pb2_scene_destroy(pb2_scene* scene);
 /* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
  * node layout + 48-byte triangles, upload to the current device.  split_method (bvh.rs:199-204): 0 = SplitMethod::SAH,

@@ -201,11 +201,14 @@ inline TriHit triangle_intersect_test(V3 p0, V3 p1, V3 p2, const Ray& ray) {
 }
 
 // triangle.rs:182-215: Triangle::intersect rejects an accepted candidate when dpdu x dpdv == 0 and
-// the geometric normal is degenerate too (default UVs (0,0),(1,0),(1,1): determinant == 1).
-inline bool triangle_frame(V3 p0, V3 p1, V3 p2, V3* dpdu, V3* dpdv) {
+// the geometric normal is degenerate too.  uv = {u0, v0, u1, v1, u2, v2} of the mesh (Triangle::get_uvs, :60-72), or null for
+// the default UVs (0,0),(1,0),(1,1) (determinant == 1).
+inline bool triangle_frame(V3 p0, V3 p1, V3 p2, V3* dpdu, V3* dpdv, const Float* uv = nullptr) {
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
-    const Float duv02[2] = {0.0f - 1.0f, 0.0f - 1.0f};
-    const Float duv12[2] = {1.0f - 1.0f, 0.0f - 1.0f};
+    const Float duv[6] = {0.0f, 0.0f, 1.0f, 0.0f, 1.0f, 1.0f};
+    if (!uv) uv = duv;
+    const Float duv02[2] = {uv[0] - uv[4], uv[1] - uv[5]};
+    const Float duv12[2] = {uv[2] - uv[4], uv[3] - uv[5]};
     Float determinant = duv02[0] * duv12[1] - duv02[1] * duv12[0];
     bool degenerate_uv = std::fabs(determinant) < 1e-8f;      // D11 FIX
     V3 du{0, 0, 0}, dv{0, 0, 0};
@@ -264,9 +267,16 @@ public:
     std::vector<uint32_t> indices;          // 3 per triangle, mesh order
     std::vector<uint32_t> ordered_prims;    // BVH leaf order -> mesh triangle id
     std::vector<LinearBVHNode> nodes;
+    std::vector<Float> uvs;                 // TriangleMesh::uv (triangle.rs:21): 2 per vertex, empty = default UVs
     int max_prims_in_node = 4;
     int max_depth_seen = 0;
 
+    // Triangle::get_uvs (triangle.rs:60-72): the mesh's, or null for the defaults
+    const Float* tri_uv(uint32_t prim, Float out[6]) const {
+        if (uvs.empty()) return nullptr;
+        for (int k = 0; k < 3; ++k) { out[2 * k] = uvs[2 * indices[3 * prim + k]]; out[2 * k + 1] = uvs[2 * indices[3 * prim + k] + 1]; }
+        return out;
+    }
     void tri(uint32_t prim, V3* p0, V3* p1, V3* p2) const {
         *p0 = verts[indices[3 * prim]];
         *p1 = verts[indices[3 * prim + 1]];
@@ -338,7 +348,8 @@ public:
                         TriHit h = triangle_intersect_test(p0, p1, p2, ray);
                         if (!h.hit) continue;
                         V3 du, dv;
-                        if (!triangle_frame(p0, p1, p2, &du, &dv)) continue;
+                        Float uvb[6];
+                        if (!triangle_frame(p0, p1, p2, &du, &dv, tri_uv(prim, uvb))) continue;
                         ray.t_max = h.t;                      // primitive.rs:70
                         out->prim_id = prim; out->t = h.t; out->b1 = h.b1; out->b2 = h.b2;
                         if (b0_out) *b0_out = h.b0;
@@ -408,7 +419,8 @@ public:
             TriHit h = triangle_intersect_test(p0, p1, p2, ray);
             if (!h.hit) continue;
             V3 du, dv;
-            if (!triangle_frame(p0, p1, p2, &du, &dv)) continue;
+            Float uvb[6];
+            if (!triangle_frame(p0, p1, p2, &du, &dv, tri_uv(prim, uvb))) continue;
             ray.t_max = h.t;
             out->prim_id = prim; out->t = h.t; out->b1 = h.b1; out->b2 = h.b2;
             hit = true;

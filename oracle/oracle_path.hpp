@@ -382,12 +382,16 @@ inline Float power_heuristic(Float f_pdf, Float g_pdf) {                        
 // ---------------------------------------------------------------- interaction.rs SurfaceInteraction (subset)
 struct SurfaceInteraction {
     V3 p, error, n, wo, dpdu;
+    V3 sn, sdpdu;         // shading.n, shading.dpdu (interaction.rs:305-316; D59: the geometric values without mesh normals / tangents)
     uint32_t prim;
 };
 
 struct LightRt {
     LightDesc d;
     V3 p0, p1, p2;      // area: the emissive triangle
+    bool has_n = false, has_uv = false;
+    V3 n0, n1, n2;      // its vertex normals (TriangleMesh::n), when the mesh has them
+    Float uv[6];        // its UVs (TriangleMesh::uv)
     Float area;
     Float cos_total_width, cos_falloff_start;     // spot.rs:38-39
     V3 w_light;                                   // distant.rs:31
@@ -416,6 +420,23 @@ public:
     std::vector<LightRt> lights;
     std::vector<int32_t> tri_light;
     Distribution1D light_distrib;
+    std::vector<V3> vn, vs;                  // TriangleMesh::n / ::s (triangle.rs:19-20), one per vertex, empty = absent
+
+    // TriangleMesh's optional per-vertex normals, tangents and UVs (world space, as given); call after init()
+    void set_shading_geometry(const Float* normals, const Float* tangents, const Float* uv) {
+        const size_t nv = bvh.verts.size();
+        vn.clear(); vs.clear(); bvh.uvs.clear();
+        if (normals) { vn.resize(nv); for (size_t i = 0; i < nv; ++i) vn[i] = {normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]}; }
+        if (tangents) { vs.resize(nv); for (size_t i = 0; i < nv; ++i) vs[i] = {tangents[3 * i], tangents[3 * i + 1], tangents[3 * i + 2]}; }
+        if (uv) bvh.uvs.assign(uv, uv + 2 * nv);
+        for (LightRt& l : lights) {
+            if (l.d.type != LIGHT_AREA) continue;
+            const uint32_t* ix = &bvh.indices[3 * (size_t)l.d.prim_id];
+            l.has_n = !vn.empty();
+            if (l.has_n) { l.n0 = vn[ix[0]]; l.n1 = vn[ix[1]]; l.n2 = vn[ix[2]]; }
+            l.has_uv = bvh.tri_uv(l.d.prim_id, l.uv) != nullptr;
+        }
+    }
 
     void init(const Float* verts, uint64_t nv, const uint32_t* idx, uint64_t nt, const uint32_t* tri_mat, const MaterialDesc* mats,
               uint32_t n_mats, const LightDesc* lts, uint32_t n_lights, int max_prims) {
@@ -479,9 +500,32 @@ public:
         si->p = it.p; si->error = it.error; si->n = it.n;
         si->wo = -ray.d;
         V3 du, dv;
-        triangle_frame(p0, p1, p2, &du, &dv);
+        Float uvb[6];
+        triangle_frame(p0, p1, p2, &du, &dv, bvh.tri_uv(h.prim_id, uvb));
         si->dpdu = du;
+        si->sn = si->n;                                                                         // D59 FIX
+        si->sdpdu = du;
         si->prim = h.prim_id;
+        if (!vn.empty() || !vs.empty()) {                                                       // triangle.rs:251-311
+            const uint32_t* ix = &bvh.indices[3 * (size_t)h.prim_id];
+            V3 ns = si->n;
+            if (!vn.empty()) {
+                ns = (vn[ix[0]] * b0 + vn[ix[1]] * h.b1) + vn[ix[2]] * h.b2;
+                ns = length_squared(ns) > 0.0f ? normalize(ns) : si->n;
+            }
+            V3 ss = normalize(si->dpdu);
+            if (!vs.empty()) {
+                const V3 st = (vs[ix[0]] * b0 + vs[ix[1]] * h.b1) + vs[ix[2]] * h.b2;
+                if (length_squared(st) > 0.0f) ss = normalize(st);
+            }
+            V3 ts = cross(ss, ns);
+            if (length_squared(ts) > 0.0f) { ts = normalize(ts); ss = cross(ts, ns); }
+            else coordinate_system(ns, &ss, &ts);
+            // set_shading_geometry(ss, ts, .., orientation_is_authoritative = true) (interaction.rs:297-316)
+            si->sn = normalize(cross(ss, ts));
+            si->n = faceforward(si->n, si->sn);                                                 // D6 FIX
+            si->sdpdu = ss;
+        }
         return true;
     }
     RGB le(const SurfaceInteraction& si, V3 w) const {                                          // interaction.rs:387-395 + diffuse.rs:150-156
@@ -495,8 +539,8 @@ public:
         const MaterialRt& m = materials[tri_material[si.prim]];
         BSDF b;
         b.eta = m.d.type == MAT_GLASS ? m.d.eta : 1.0f;
-        b.ns = si.n; b.ng = si.n;                                                               // reflection.rs:220-234
-        b.ss = normalize(si.dpdu);
+        b.ns = si.sn; b.ng = si.n;                                                              // reflection.rs:220-234
+        b.ss = normalize(si.sdpdu);
         b.ts = cross(b.ns, b.ss);
         RGB kd{m.d.kd[0], m.d.kd[1], m.d.kd[2]}, ks{m.d.ks[0], m.d.ks[1], m.d.ks[2]};
         RGB kr{m.d.kr[0], m.d.kr[1], m.d.kr[2]}, kt{m.d.kt[0], m.d.kt[1], m.d.kt[2]};
@@ -792,6 +836,7 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
         Float b0 = 1.0f - su0, b1 = ul1 * su0;                                                 // sampling.rs:275-278
         V3 ps = (light.p0 * b0 + light.p1 * b1) + light.p2 * ((1.0f - b0) - b1);
         V3 ns = normalize(cross(light.p1 - light.p0, light.p2 - light.p0));
+        if (light.has_n) ns = faceforward(ns, (light.n0 * b0 + light.n1 * b1) + light.n2 * ((1.0f - b0) - b1));   // triangle.rs:338-341, D6 FIX
         V3 pe = ((vabs(light.p0 * b0) + vabs(light.p1 * b1)) + vabs(light.p2 * ((1.0f - b0) - b1))) * gamma(6.0f);
         Float pdf = 1.0f / light.area;
         V3 w = ps - it.p;
@@ -836,7 +881,7 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
                 Ray r = spawn_ray(base, wi);
                 TriHit th = triangle_intersect_test(light.p0, light.p1, light.p2, r);
                 V3 du, dv;
-                if (!th.hit || !triangle_frame(light.p0, light.p1, light.p2, &du, &dv)) return ld;
+                if (!th.hit || !triangle_frame(light.p0, light.p1, light.p2, &du, &dv, light.has_uv ? light.uv : nullptr)) return ld;
                 Interaction li_it = triangle_interaction(light.p0, light.p1, light.p2, th.b0, th.b1, th.b2);
                 Float lp = length_squared(it.p - li_it.p) / (std::fabs(dot(li_it.n, -wi)) * light.area);
                 if (std::isinf(lp)) lp = 0.0f;

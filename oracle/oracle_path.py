@@ -169,6 +169,10 @@ class Scene:
         self.h = L.orc_scene_create(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), _p(tm),
                                     C.cast(mats, C.c_void_p), len(sc["materials"]), C.cast(lts, C.c_void_p),
                                     len(sc["lights"]), max_prims_in_node)
+        # TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26)
+        self._sg = [None if sc.get(k) is None else np.ascontiguousarray(sc[k], dtype=np.float32) for k in ("normals", "tangents", "uvs")]
+        if any(a is not None for a in self._sg):
+            L.orc_scene_set_shading_geometry(C.c_void_p(self.h), *[None if a is None else _p(a) for a in self._sg])
 
     def __del__(self):
         if getattr(self, "h", None):

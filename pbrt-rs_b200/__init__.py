@@ -152,6 +152,7 @@ def lib():
         "pb2_memcpy_h2d": [vp, vp, u64], "pb2_memcpy_d2h": [vp, vp, u64], "pb2_device_synchronize": [],
         "pb2_set_trace_tuning": [i32, i32, i32, i32],
         "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
+        "pb2_scene_set_shading_geometry": [vp, vp, vp, vp],
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
         "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
@@ -238,9 +239,10 @@ class DeviceBuffer:
 
 
 class Scene:
-    """Triangle list + materials + lights handed to BVHAccel::new (pb2_scene_create)."""
+    """Triangle list + materials + lights handed to BVHAccel::new (pb2_scene_create); normals / tangents / uvs are
+    TriangleMesh's optional per-vertex arrays (src/shapes/triangle.rs:17-26)."""
 
-    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None):
+    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None, normals=None, tangents=None, uvs=None):
         verts = _f32(verts).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         self.n_tris = len(idx)
@@ -252,6 +254,9 @@ class Scene:
                                      C.cast(mats, C.c_void_p) if mats else None, len(materials) if materials else 0,
                                      C.cast(lts, C.c_void_p) if lts else None, len(lights) if lights else 0,
                                      C.byref(self.h)))
+        if normals is not None or tangents is not None or uvs is not None:
+            sg = [None if a is None else _f32(a).reshape(len(verts), k) for a, k in ((normals, 3), (tangents, 3), (uvs, 2))]
+            check(lib().pb2_scene_set_shading_geometry(self.h, *[_p(a) for a in sg]))
 
     def destroy(self):
         if self.h:
@@ -380,7 +385,7 @@ def light_from_dict(d):
 def scene_from_dict(sc):
     """Scene from the plain-dict description the generators in scenes.py return."""
     return Scene(sc["verts"], sc["idx"], sc["tri_material"], [material_from_dict(m) for m in sc["materials"]],
-                 [light_from_dict(l) for l in sc["lights"]])
+                 [light_from_dict(l) for l in sc["lights"]], normals=sc.get("normals"), tangents=sc.get("tangents"), uvs=sc.get("uvs"))
 
 
 class Film:

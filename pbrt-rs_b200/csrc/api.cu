@@ -50,6 +50,11 @@ void pb2_scene::free_device() {
     if (d_light_cdf) cudaFree(d_light_cdf);
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
+    if (d_indices) cudaFree(d_indices);
+    if (d_normals) cudaFree(d_normals);
+    if (d_tangents) cudaFree(d_tangents);
+    if (d_uvs) cudaFree(d_uvs);
+    d_indices = d_normals = d_tangents = d_uvs = nullptr;
     d_quads = nullptr;
     d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
     for (int i = 0; i < kStages; ++i) {
@@ -183,6 +188,22 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
     return PB2_OK;
 }
 
+int pb2_scene_set_shading_geometry(pb2_scene* scene, const float* normals, const float* tangents, const float* uvs) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    if (scene->built) return set_error(PB2_ERR_STATE, "set the mesh attributes before pb2_scene_build_bvh");
+    const size_t nv = scene->verts.size() / 3;
+    const struct { const float* p; size_t k; const char* name; } in[3] = {{normals, 3, "normal"}, {tangents, 3, "tangent"}, {uvs, 2, "uv"}};
+    for (const auto& a : in)
+        if (a.p)
+            for (size_t i = 0; i < a.k * nv; ++i)
+                if (!std::isfinite(a.p[i])) return set_error(PB2_ERR_INVALID, "%s of vertex %zu is not finite", a.name, i / a.k);
+    scene->normals.assign(normals ? normals : nullptr, normals ? normals + 3 * nv : nullptr);
+    scene->tangents.assign(tangents ? tangents : nullptr, tangents ? tangents + 3 * nv : nullptr);
+    scene->uvs.assign(uvs ? uvs : nullptr, uvs ? uvs + 2 * nv : nullptr);
+    return PB2_OK;
+}
+
 int pb2_scene_destroy(pb2_scene* scene) {
     if (!scene) return PB2_OK;
     scene->free_device();
@@ -250,7 +271,7 @@ static int build_device_locked(pb2_scene* scene, int max_prims_in_node, SceneVie
     scene->tree_depth = dv.max_depth;
     for (int k = 0; k < 6; ++k) scene->root_bounds[k] = dv.root_bounds[k];
     if (n_tris) {
-        launch_mark_degenerate(scene->d_tris, n_tris, 0);
+        launch_mark_degenerate(scene->d_tris, n_tris, scene->d_indices, scene->d_uvs, 0);
         PB2_CUDA(cudaGetLastError());
         PB2_CUDA(cudaDeviceSynchronize());
         v->quads = (const float4*)scene->d_quads;
@@ -278,6 +299,17 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     v.n_tris = (uint32_t)n_tris;
     PB2_CUDA(cudaMalloc(&scene->d_counters, pb2_scene::kCounters * sizeof(unsigned long long)));
     PB2_CUDA(cudaMemset(scene->d_counters, 0, pb2_scene::kCounters * sizeof(unsigned long long)));
+    // mesh attributes first: the per-triangle "degenerate frame" flag follows the mesh's UVs
+    if (n_tris && (!scene->normals.empty() || !scene->tangents.empty() || !scene->uvs.empty())) {
+        auto up = [](void** d, const void* h, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(d, bytes);
+            return e == cudaSuccess ? cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) : e;
+        };
+        PB2_CUDA(up(&scene->d_indices, scene->indices.data(), scene->indices.size() * 4));
+        if (!scene->normals.empty()) PB2_CUDA(up(&scene->d_normals, scene->normals.data(), scene->normals.size() * 4));
+        if (!scene->tangents.empty()) PB2_CUDA(up(&scene->d_tangents, scene->tangents.data(), scene->tangents.size() * 4));
+        if (!scene->uvs.empty()) PB2_CUDA(up(&scene->d_uvs, scene->uvs.data(), scene->uvs.size() * 4));
+    }
     if (split_method == 1) {
         rc = build_device_locked(scene, max_prims_in_node, &v);
         if (rc != PB2_OK) return rc;
@@ -295,7 +327,7 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
             v.quads = (const float4*)scene->d_quads;
             v.quad_root_ref = b.quad_root_ref;
             PB2_CUDA(cudaMemcpy(scene->d_tris, b.tris.data(), b.tris.size() * sizeof(PackedTri), cudaMemcpyHostToDevice));
-            launch_mark_degenerate(scene->d_tris, b.tris.size(), 0);
+            launch_mark_degenerate(scene->d_tris, b.tris.size(), scene->d_indices, scene->d_uvs, 0);
             PB2_CUDA(cudaGetLastError());
             PB2_CUDA(cudaDeviceSynchronize());
             std::vector<uint32_t> slot(n_tris);

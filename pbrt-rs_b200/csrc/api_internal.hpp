@@ -54,6 +54,12 @@ struct pb2_scene {
     std::vector<uint32_t> tri_material;
     std::vector<pb2_material> materials;
     std::vector<pb2_light> lights;
+    // TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26), pb2_scene_set_shading_geometry
+    std::vector<float> normals, tangents, uvs;
+    void* d_indices = nullptr;
+    void* d_normals = nullptr;
+    void* d_tangents = nullptr;
+    void* d_uvs = nullptr;
     pb2::HostBVH bvh;
     double build_ms[6] = {0, 0, 0, 0, 0, 0};   // HLBVH stage times (bvh_build.hpp: build_hlbvh_gpu)
     bool built_host = false;   // LinearNode array + ordered prims valid

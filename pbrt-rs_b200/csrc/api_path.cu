@@ -104,6 +104,12 @@ int upload_shading_tables(pb2_scene* scene) {
             d.p1[0] = p1.x; d.p1[1] = p1.y; d.p1[2] = p1.z;
             d.p2[0] = p2.x; d.p2[1] = p2.y; d.p2[2] = p2.z;
             d.area = len(cross3(p1 - p0, p2 - p0)) * 0.5f;               // triangle.rs:323-328
+            d.has_n = scene->normals.empty() ? 0 : 1;
+            d.has_uv = scene->uvs.empty() ? 0 : 1;
+            for (int c = 0; c < 3; ++c) {
+                if (d.has_n) { d.n0[c] = scene->normals[3 * ix[0] + c]; d.n1[c] = scene->normals[3 * ix[1] + c]; d.n2[c] = scene->normals[3 * ix[2] + c]; }
+                if (d.has_uv && c < 2) { d.uv[c] = scene->uvs[2 * ix[0] + c]; d.uv[2 + c] = scene->uvs[2 * ix[1] + c]; d.uv[4 + c] = scene->uvs[2 * ix[2] + c]; }
+            }
             tri_light[l.prim_id] = (int32_t)i;
             pw = mkc(l.i[0], l.i[1], l.i[2]) * ((l.two_sided ? 2.0f : 1.0f) * d.area * PB2_PI);      // diffuse.rs:83-85
         } else if (l.type == PB2_LIGHT_SPOT) {                           // spot.rs:30-49
@@ -163,6 +169,10 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
     v.light_func = base + off;
     v.light_cdf = base + off + n;
     v.light_func_int = s->light_func_int[strategy == PB2_LIGHTS_POWER ? 1 : 0];
+    v.indices = (const uint32_t*)s->d_indices;
+    v.normals = (const float*)s->d_normals;
+    v.tangents = (const float*)s->d_tangents;
+    v.uvs = (const float2*)s->d_uvs;
     return v;
 }
 

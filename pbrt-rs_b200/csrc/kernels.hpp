@@ -24,7 +24,7 @@ void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, 
 void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
                          void* d_out, cudaStream_t st);
 void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st);
-void launch_mark_degenerate(void* d_tris, uint64_t n, cudaStream_t st);
+void launch_mark_degenerate(void* d_tris, uint64_t n, const void* d_indices, const void* d_uvs, cudaStream_t st);
 void set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int prefetch);
 void launch_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* d_out, cudaStream_t st);
 

@@ -91,19 +91,26 @@ static unsigned persistent_grid(const void* kernel, uint64_t n) {
 
 // PackedTri.pad (v2.w) = 1 when Triangle::intersect rejects every hit of the triangle (degenerate dpdu/dpdv AND zero
 // geometric normal, triangle.rs:193-215): computed once per scene with the same tri_frame() the walk used to call per hit.
-__global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tris, uint32_t n) {
+// With mesh UVs (TriangleMesh::uv) the frame, and so the flag, follows them (indices: 3 vertex ids per caller triangle).
+__global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tris, uint32_t n, const uint32_t* __restrict__ indices,
+                                                         const float2* __restrict__ uvs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 a = tris[3ull * i], b = tris[3ull * i + 1];
     float4 c = tris[3ull * i + 2];
     vec3 du, dv;
-    const bool ok = tri_frame(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), &du, &dv);
+    bool ok;
+    if (uvs) {
+        const uint32_t prim = __float_as_uint(a.w);
+        ok = tri_frame_uv(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), uvs[indices[3ull * prim]], uvs[indices[3ull * prim + 1]],
+                          uvs[indices[3ull * prim + 2]], &du, &dv);
+    } else ok = tri_frame(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), &du, &dv);
     c.w = __uint_as_float(ok ? 0u : 1u);
     tris[3ull * i + 2] = c;
 }
-void launch_mark_degenerate(void* d_tris, uint64_t n, cudaStream_t st) {
+void launch_mark_degenerate(void* d_tris, uint64_t n, const void* d_indices, const void* d_uvs, cudaStream_t st) {
     if (n == 0) return;
-    k_mark_degenerate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((float4*)d_tris, (uint32_t)n);
+    k_mark_degenerate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((float4*)d_tris, (uint32_t)n, (const uint32_t*)d_indices, (const float2*)d_uvs);
 }
 
 void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, unsigned long long* d_counter,

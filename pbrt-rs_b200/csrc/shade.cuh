@@ -184,6 +184,9 @@ struct DLight {
     float axis[3];          // spot: row 2 of world_to_light (spot.rs:52-53); distant: w_light (distant.rs:31)
     float cos_total_width, cos_falloff_start;   // spot.rs:38-39
     float world_radius;     // distant.rs:73-77
+    int has_n, has_uv;      // area: the mesh carries vertex normals / UVs
+    float n0[3], n1[3], n2[3];   // vertex normals of the emissive triangle (Triangle::sample, triangle.rs:338-341)
+    float uv[6];            // its UVs (Shape::pdf2 -> Triangle::intersect frame check)
 };
 
 enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u };
@@ -346,14 +349,15 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, f
 // Material::compute_scattering_functions for matte / plastic / glass (pbrt-v3; Appendix B).  MAT is the material type of
 // `m` known at compile time (the wavefront shades one material type per launch, so the lobe kinds fold to constants and
 // the code of the other materials drops out of that launch's kernel); MAT < 0 reads m.type at run time.
+// ng = si.n, ns = si.shading.n, sdpdu = si.shading.dpdu (the geometric values without mesh normals / tangents, D59).
 template <int MAT = -1>
-PB2_HD BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 n, vec3 dpdu) {
+PB2_HD BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
     BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> b;
     const int type = MAT < 0 ? m.type : MAT;
     b.eta = type == 2 ? m.eta : 1.0f;
-    b.ns = n;
-    b.ng = n;
-    b.ss = unit(dpdu);                                         // reflection.rs:220-234 (D59: shading = geometric)
+    b.ns = ns;
+    b.ng = ng;
+    b.ss = unit(sdpdu);                                        // reflection.rs:220-234
     b.ts = cross3(b.ns, b.ss);
     b.n = 0;
     const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);

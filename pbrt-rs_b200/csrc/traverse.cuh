@@ -132,8 +132,28 @@ PB2_D bool tri_test(const RayCtx& r, float ray_t_max, vec3 p0, vec3 p1, vec3 p2,
     return true;
 }
 
-// triangle.rs:193-215 with default UVs (0,0),(1,0),(1,1): dpdu, dpdv; false when Triangle::intersect bails out on a
-// degenerate frame (closest-hit only — intersect_p never runs this).
+// triangle.rs:193-215: dpdu, dpdv from the triangle's UVs (Triangle::get_uvs, :60-72; uv0/uv1/uv2, default (0,0),(1,0),(1,1));
+// false when Triangle::intersect bails out on a degenerate frame (closest-hit only — intersect_p never runs this).
+PB2_D bool tri_frame_uv(vec3 p0, vec3 p1, vec3 p2, float2 uv0, float2 uv1, float2 uv2, vec3* dpdu, vec3* dpdv) {
+    const vec3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float duv02x = uv0.x - uv2.x, duv02y = uv0.y - uv2.y, duv12x = uv1.x - uv2.x, duv12y = uv1.y - uv2.y;
+    const float determinant = duv02x * duv12y - duv02y * duv12x;
+    const bool degenerate_uv = fabsf(determinant) < 1e-8f;               // D11 FIX
+    vec3 du = mk(0.f, 0.f, 0.f), dv = mk(0.f, 0.f, 0.f);
+    if (!degenerate_uv) {
+        const float inv_det = 1.0f / determinant;
+        du = (dp02 * duv12y - dp12 * duv02y) * inv_det;
+        dv = (dp02 * -duv12x + dp12 * duv02x) * inv_det;
+    }
+    if (degenerate_uv || len2(cross3(du, dv)) == 0.0f) {
+        const vec3 ng = cross3(p2 - p0, p1 - p0);
+        if (len2(ng) == 0.0f) return false;
+        coord_system(unit(ng), &du, &dv);
+    }
+    *dpdu = du;
+    *dpdv = dv;
+    return true;
+}
 PB2_D bool tri_frame(vec3 p0, vec3 p1, vec3 p2, vec3* dpdu, vec3* dpdv) {
     const vec3 dp02 = p0 - p2, dp12 = p1 - p2;
     const float duv02x = 0.0f - 1.0f, duv02y = 0.0f - 1.0f, duv12x = 1.0f - 1.0f, duv12y = 0.0f - 1.0f;
@@ -185,8 +205,7 @@ PB2_D bool traverse(const SceneView& s, vec3 o, vec3 d, float ray_t_max, HitRec*
                 float t, b0, b1, b2;
                 if (tri_test(r, t_max, p0, p1, p2, &t, &b0, &b1, &b2)) {
                     if (ANY) return true;
-                    vec3 du, dv;
-                    if (tri_frame(p0, p1, p2, &du, &dv)) {
+                    if (__float_as_uint(c.w) == 0u) {          // frame not degenerate (k_mark_degenerate, triangle.rs:193-215)
                         t_max = t;                              // primitive.rs:70
                         hit->prim = __float_as_uint(a.w);
                         hit->slot = slot;

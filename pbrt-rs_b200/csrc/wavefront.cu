@@ -427,10 +427,15 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_mis(SceneView s, PathBu
 }
 
 // ---- shade -----------------------------------------------------------------------------------------------------------------
-struct Vertex {           // SurfaceInteraction subset rebuilt from the hit record (triangle.rs:193-250, D59)
+__device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+
+struct Vertex {           // SurfaceInteraction subset rebuilt from the hit record (triangle.rs:193-311, D59)
     vec3 p, err, n, dpdu;
+    vec3 sn, sdpdu;       // shading.n, shading.dpdu: n and dpdu unless the mesh has vertex normals / tangents
 };
-__device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, uint32_t prim, float b0, float b1, float b2) {
+// SG = the mesh carries per-vertex normals, tangents or UVs (compiled out otherwise: k_shade is at its register limit).
+template <bool SG>
+__device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const ShadeView& sh, uint32_t prim, float b0, float b1, float b2) {
     const uint32_t slot = __ldg(s.slot_of_prim + prim);
     const float4 a = ldg4(s.tris + 3ull * slot), b = ldg4(s.tris + 3ull * slot + 1), c = ldg4(s.tris + 3ull * slot + 2);
     const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
@@ -442,13 +447,40 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, uint32_t pr
     v.p = (p0 * b0 + p1 * b1) + p2 * b2;
     v.n = unit(cross3(p0 - p2, p1 - p2));
     vec3 dv;
-    tri_frame(p0, p1, p2, &v.dpdu, &dv);
+    if (!SG) {
+        tri_frame(p0, p1, p2, &v.dpdu, &dv);
+        v.sn = v.n;
+        v.sdpdu = v.dpdu;
+        return v;
+    }
+    const uint32_t i0 = __ldg(sh.indices + 3ull * prim), i1 = __ldg(sh.indices + 3ull * prim + 1), i2 = __ldg(sh.indices + 3ull * prim + 2);
+    if (sh.uvs) tri_frame_uv(p0, p1, p2, __ldg(sh.uvs + i0), __ldg(sh.uvs + i1), __ldg(sh.uvs + i2), &v.dpdu, &dv);   // Triangle::get_uvs
+    else tri_frame(p0, p1, p2, &v.dpdu, &dv);
+    v.sn = v.n;
+    v.sdpdu = v.dpdu;
+    if (sh.normals || sh.tangents) {                                     // triangle.rs:251-311
+        vec3 ns = v.n;
+        if (sh.normals) {
+            ns = (ld3(sh.normals + 3ull * i0) * b0 + ld3(sh.normals + 3ull * i1) * b1) + ld3(sh.normals + 3ull * i2) * b2;
+            ns = len2(ns) > 0.0f ? unit(ns) : v.n;
+        }
+        vec3 ss = unit(v.dpdu);
+        if (sh.tangents) {
+            const vec3 st = (ld3(sh.tangents + 3ull * i0) * b0 + ld3(sh.tangents + 3ull * i1) * b1) + ld3(sh.tangents + 3ull * i2) * b2;
+            if (len2(st) > 0.0f) ss = unit(st);
+        }
+        vec3 ts = cross3(ss, ns);
+        if (len2(ts) > 0.0f) { ts = unit(ts); ss = cross3(ts, ns); }
+        else coord_system(ns, &ss, &ts);
+        // SurfaceInteraction::set_shading_geometry(ss, ts, .., true) (interaction.rs:297-316)
+        v.sn = unit(cross3(ss, ts));
+        v.n = face_toward(v.n, v.sn);                                    // D6 FIX
+        v.sdpdu = ss;
+    }
     return v;
 }
-__device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
-
 // estimate_direct (integrator.rs:136-266) up to the two visibility queries: fills the NEE record of `slot`.
-template <class BsdfType>
+template <bool SG, class BsdfType>
 __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeView& sh, const PathBuffers& b, uint32_t slot, const Vertex& v, vec3 wo,
                                                 const BsdfType& bsdf, const DLight& light, float pick_pdf, float ul0, float ul1, float us0,
                                                 float us1, rgb3 beta) {
@@ -489,7 +521,8 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
         const float b0 = 1.0f - su0, b1 = ul1 * su0;                     // sampling.rs:275-278
         const float b2 = (1.0f - b0) - b1;
         const vec3 ps = (lp0 * b0 + lp1 * b1) + lp2 * b2;
-        const vec3 ns = unit(cross3(lp1 - lp0, lp2 - lp0));
+        vec3 ns = unit(cross3(lp1 - lp0, lp2 - lp0));
+        if (light.has_n) ns = face_toward(ns, (ld3(light.n0) * b0 + ld3(light.n1) * b1) + ld3(light.n2) * b2);     // triangle.rs:338-341, D6 FIX
         const vec3 pe = ((abs3(lp0 * b0) + abs3(lp1 * b1)) + abs3(lp2 * b2)) * gammaf_(6.0f);
         float pdf = 1.0f / light.area;
         vec3 w = ps - v.p;
@@ -529,12 +562,16 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
             float weight = 1.0f;
             bool go = true;
             const vec3 ro = offset_ray_origin(v.p, v.err, v.n, wi);      // it.spawn_ray(wi)
+            float lb0 = 0.0f, lb1 = 0.0f, lb2 = 0.0f;
             if (!sampled_specular) {
                 // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): the light's own triangle
                 const RayCtx rc = make_ray_ctx(ro, wi);
-                float t, lb0, lb1, lb2;
+                float t;
                 vec3 du, dv;
-                if (!tri_test(rc, kInf, lp0, lp1, lp2, &t, &lb0, &lb1, &lb2) || !tri_frame(lp0, lp1, lp2, &du, &dv)) go = false;
+                const bool frame_ok = light.has_uv ? tri_frame_uv(lp0, lp1, lp2, make_float2(light.uv[0], light.uv[1]), make_float2(light.uv[2], light.uv[3]),
+                                                                   make_float2(light.uv[4], light.uv[5]), &du, &dv)
+                                                   : tri_frame(lp0, lp1, lp2, &du, &dv);
+                if (!tri_test(rc, kInf, lp0, lp1, lp2, &t, &lb0, &lb1, &lb2) || !frame_ok) go = false;
                 else {
                     const vec3 p_l = (lp0 * lb0 + lp1 * lb1) + lp2 * lb2;
                     const vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
@@ -545,8 +582,11 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
                 }
             }
             if (go) {
-                // li = light_isect.le(-wi) if the closest hit is this light's triangle (D56 FIX); its normal is known here
-                const vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                // li = light_isect.le(-wi) if the closest hit is this light's triangle (D56 FIX); its normal is known here:
+                // the geometric one, or — on a mesh with vertex normals / tangents — the one Triangle::intersect leaves in the
+                // interaction at these barycentrics (flipped towards the shading normal, set_shading_geometry)
+                vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                if (SG && !sampled_specular) n_l = rebuild_vertex<true>(s, sh, light.prim, lb0, lb1, lb2).n;
                 const rgb3 lmis = (light.two_sided || dot3(n_l, -wi) > 0.0f) ? l_emit : gray(0.0f);
                 if (!black(lmis)) {
                     pending |= 2u;
@@ -576,7 +616,7 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
 #ifndef PB2_SHADE_BLOCKS
 #define PB2_SHADE_BLOCKS 2
 #endif
-template <int MAT, bool TABLES>
+template <int MAT, bool TABLES, bool SG>
 __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
     const uint64_t n = b.counters[C_MAT0 + MAT];
     const uint32_t* queue = b.q_mat[MAT];
@@ -591,7 +631,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
         const unsigned state = __float_as_uint(Lf.w);
         unsigned bounces = state & 0xFFFFu;
         const bool specular_bounce = (state >> 16) & 1u;
-        const Vertex v = rebuild_vertex(s, h.x, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w));
+        const Vertex v = rebuild_vertex<SG>(s, sh, h.x, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w));
         const vec3 wo = -mk(rd.x, rd.y, rd.z);
         if (bounces == 0u || specular_bounce) {                          // path.rs:80-82 + interaction.rs:387-395
             const int li = sh.tri_light[h.x];
@@ -603,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
         }
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
         if (alive) {
-            const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.dpdu);
+            const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.sn, v.sdpdu);
             PathSampler rng;
             rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot], TABLES ? (state >> 17) & 0x3FFFu : 0u);
             if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
@@ -613,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
                     float ul0, ul1, us0, us1;
                     rng.next2<TABLES>(&ul0, &ul1);
                     rng.next2<TABLES>(&us0, &us1);
-                    direct_lighting(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
+                    direct_lighting<SG>(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
                 }
             }
             float u0, u1;
@@ -812,6 +852,23 @@ unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
     return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
 }
 
+// k_shade<material, PixelSampler tables, mesh shading geometry> for the three material queues of one bounce.
+template <bool TABLES, bool SG>
+void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
+                    const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
+    k_shade<0, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    k_shade<1, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    k_shade<2, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+}
+void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
+                  const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
+    const bool tables = map.smp.kind >= 2, sg = sh.indices != nullptr;
+    if (tables && sg) launch_shade_t<true, true>(wf, sv, sh, b, map, film, pp, cur, n, st);
+    else if (tables) launch_shade_t<true, false>(wf, sv, sh, b, map, film, pp, cur, n, st);
+    else if (sg) launch_shade_t<false, true>(wf, sv, sh, b, map, film, pp, cur, n, st);
+    else launch_shade_t<false, false>(wf, sv, sh, b, map, film, pp, cur, n, st);
+}
+
 // All bounces of one batch of `n` path slots.
 void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film, const PathMap& map,
                  const PathParams& pp, uint64_t n, cudaStream_t st) {
@@ -824,15 +881,7 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         const int cur = depth & 1;
         k_iter_begin<<<1, 32, 0, st>>>(b, cur);
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
-        if (map.smp.kind >= 2) {
-            k_shade<0, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-            k_shade<1, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-            k_shade<2, true><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-        } else {
-            k_shade<0, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-            k_shade<1, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-            k_shade<2, false><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-        }
+        launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
         if (depth < pp.max_depth && sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
             k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);

@@ -24,6 +24,11 @@ struct ShadeView {
     const float* light_func;      // Distribution1D func[n_lights]
     const float* light_cdf;       // cdf[n_lights + 1]
     float light_func_int;
+    // TriangleMesh's optional attributes (triangle.rs:17-26), all null for a plain mesh
+    const uint32_t* indices;      // 3 vertex ids per caller triangle
+    const float* normals;         // 3 per vertex
+    const float* tangents;        // 3 per vertex
+    const float2* uvs;            // per vertex
 };
 
 // Film geometry: image, sample bounds (film.rs:76-81 with D42), filter radius and its 16x16 table (film.rs:53-63).

@@ -214,6 +214,37 @@ def scene_c4(n_theta=158, n_phi=316):
     return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=materials, lights=lights)
 
 
+def scene_c4_smooth(n_theta=24, n_phi=48, uvs=True, tangents=False, emissive_normals=True):
+    """C4's room as a TriangleMesh WITH per-vertex attributes (src/shapes/triangle.rs:17-26): the three spheres get their analytic
+    normals (smooth shading; the glass one too), the room's flat faces their face normals — the ceiling light's tilted and, on one
+    vertex, flipped, so Triangle::sample's face_forward matters —, UVs from the vertex positions and, optionally, tangents."""
+    sc = scene_c4(n_theta=n_theta, n_phi=n_phi)
+    v, idx = sc["verts"].astype(np.float64), sc["idx"]
+    nrm = np.zeros_like(v)
+    fn = np.cross(v[idx[:, 1]] - v[idx[:, 0]], v[idx[:, 2]] - v[idx[:, 0]])
+    for k in range(3):
+        np.add.at(nrm, idx[:, k], fn)
+    centers = [((140.0, 90.0, 280.0), 3), ((278.0, 130.0, 220.0), 4), ((416.0, 90.0, 280.0), 5)]
+    for c, mat in centers:
+        used = np.unique(idx[sc["tri_material"] == mat])
+        nrm[used] = v[used] - np.array(c)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    if emissive_normals:
+        for l in sc["lights"]:
+            if l["type"] == "area":
+                nrm[idx[l["prim"]]] += np.array((0.3, 0.0, 0.2))
+        first = idx[[l["prim"] for l in sc["lights"] if l["type"] == "area"][0]][0]
+        nrm[first] = -nrm[first]
+    sc["normals"] = nrm.astype(np.float32)
+    if uvs:
+        sc["uvs"] = np.stack([v[:, 0] / 556.0 + 0.37 * v[:, 1] / 556.0, v[:, 2] / 559.2 - 0.21 * v[:, 1] / 556.0], axis=1).astype(np.float32)
+    if tangents:
+        t = np.cross(nrm, np.array((0.0, 1.0, 0.0)))
+        t[np.linalg.norm(t, axis=1) < 1e-6] = (1.0, 0.0, 0.0)
+        sc["tangents"] = t.astype(np.float32)
+    return sc
+
+
 def scene_all_lights(n_theta=24, n_phi=48):
     """C4's room with every light the backend knows: the ceiling area light, a point light, a spot light aimed at the matte
     sphere (src/lights/spot.rs; axis = normalize(to - from), 30 degree cone, falloff from 20 degrees) and a distant light

@@ -36,6 +36,7 @@ extern "C" {
     pub fn pb2_scene_create(verts: *const f32, n_verts: u64, indices: *const u32, n_tris: u64, tri_material: *const u32,
                             mats: *const pb2_material, n_mats: u32, lights: *const pb2_light, n_lights: u32,
                             out: *mut *mut pb2_scene) -> c_int;
+    pub fn pb2_scene_set_shading_geometry(scene: *mut pb2_scene, normals: *const f32, tangents: *const f32, uvs: *const f32) -> c_int;
     pub fn pb2_scene_destroy(scene: *mut pb2_scene) -> c_int;
     pub fn pb2_scene_build_bvh(scene: *mut pb2_scene, max_prims_in_node: c_int, split_method: c_int) -> c_int;
     pub fn pb2_world_bound(scene: *const pb2_scene, out: *mut f32) -> c_int;

@@ -372,3 +372,60 @@ def test_film_argument_errors(gpu):
                 dict(radius=(0.0, 1.0)), dict(crop=(0.501, 0.0, 0.502, 1.0))):
         with pytest.raises(gpu.Pb2Error):
             gpu.Film((16, 16), **bad)
+
+
+@pytest.mark.parametrize("variant", ["normals+uvs", "normals+uvs+tangents", "uvs", "normals"])
+def test_mesh_shading_geometry_bit_exact(gpu, OP, scenes, variant):
+    """TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26): shading frame from interpolated normals
+    (:251-311), dpdu from the mesh UVs (:60-72,193-215), the geometric normal flipped towards the shading normal
+    (set_shading_geometry, interaction.rs:297-316) — which decides emission sides, glass entering/leaving and
+    Triangle::sample's light normal (:338-341).  Per-sample radiance and the film equal the oracle's bits."""
+    sc = scenes.scene_c4_smooth(n_theta=24, n_phi=48, uvs="uvs" in variant, tangents="tangents" in variant)
+    if "normals" not in variant:
+        sc.pop("normals")
+    cam = dict(scenes.C4_CAMERA, res=(240, 135))
+    kw = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", spp=16)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    rng = np.random.default_rng(31)
+    n = 30000
+    xy = np.stack([rng.integers(0, 240, n), rng.integers(0, 135, n)], axis=1)
+    s = rng.integers(0, 16, size=n)
+    L, pf = integ.li(xy, s)
+    rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), xy, s)
+    assert np.array_equal(bits(pf), bits(rpf))
+    mism = (bits(L) != bits(rL)).any(axis=1)
+    assert mism.sum() == 0, f"{mism.sum()} of {n} samples differ; first {L[mism][:2]} vs {rL[mism][:2]}"
+    assert (L.sum(axis=1) > 0).mean() > 0.3
+    plain, _ = gpu.PathIntegrator(gpu.BVHAccel(gpu.scene_from_dict(scenes.scene_c4(24, 48)), 4), camera, **kw).li(xy, s)
+    assert (bits(plain) != bits(L)).any()                  # the attributes do change the shading
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), mode=1)
+    assert np.array_equal(bits(film.read_xyzw()), bits(want))
+    # closest hit over a mesh with UVs still equals the oracle's walk (the degenerate-frame flag follows the UVs)
+    rays = random_rays_in_room(20000, seed=3)
+    hits = accel.intersect(rays)
+    rh = ref.bvh().intersect(rays)[0]
+    assert np.array_equal(hits["prim_id"], rh["prim_id"]) and np.array_equal(bits(hits["t"]), bits(rh["t"]))
+
+
+def random_rays_in_room(n, seed):
+    rng = np.random.default_rng(seed)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform((50, 50, 50), (500, 500, 500), (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3] = np.inf
+    return rays
+
+
+def test_shading_geometry_argument_errors(gpu, scenes):
+    sc = scenes.scene_c2()
+    bad = np.zeros((len(sc["verts"]), 3), np.float32)
+    bad[3, 1] = np.nan
+    with pytest.raises(gpu.Pb2Error):
+        gpu.Scene(sc["verts"], sc["idx"], normals=bad)
+    scene = gpu.Scene(sc["verts"], sc["idx"])
+    gpu.BVHAccel(scene)
+    with pytest.raises(gpu.Pb2Error):                        # after the build
+        gpu.check(gpu.lib().pb2_scene_set_shading_geometry(scene.h, None, None, None))

@@ -205,3 +205,42 @@ def test_film_crop_window_clamp_and_filters(OP, scenes):
     xs = (np.arange(16) + 0.5) * 4.0 / 16
     w = np.sinc(xs) * np.sinc(xs / 3.0)
     assert np.allclose(t, np.outer(w, w), atol=2e-6)
+
+
+def test_mesh_shading_normals_uvs_tangents(OP, scenes):
+    """TriangleMesh's optional n / s / uv (triangle.rs:17-26, 60-72, 251-311): analytic vertex normals make a coarsely tessellated
+    matte sphere shade smoothly (neighbouring pixels differ less than on the faceted mesh), UVs / tangents only rotate the
+    tangent frame of isotropic BSDFs (same image statistically), and nothing turns into NaN."""
+    v, i = scenes.uv_sphere(radius=1.0, n_theta=10, n_phi=20)
+    base = dict(verts=v, idx=i, tri_material=np.zeros(len(i), np.uint32), materials=[dict(type="matte", kd=(0.8, 0.8, 0.8))],
+                lights=[dict(type="distant", w=(0.3, 0.5, -1.0), L=(3.0, 3.0, 3.0))])
+    cam = dict(pos=(0, 0, -4.0), look=(0, 0, 0), up=(0, 1, 0), fov=30.0, res=(64, 64))
+    fd = OP.film_desc(cam["res"])
+    pd = OP.path_desc(max_depth=1, spp=16)
+    flat = OP.resolve_rgb(OP.Scene(base).render(cam, fd, pd)[0])[..., 0]
+    smooth = OP.resolve_rgb(OP.Scene(dict(base, normals=v.copy())).render(cam, fd, pd)[0])[..., 0]
+    assert not np.isnan(smooth).any() and abs(smooth.mean() - flat.mean()) / flat.mean() < 0.05
+    # analytic: Lambert under a distant light, radiance = kd/pi * L * max(0, n.w) with n = the unit position on the sphere
+    w = np.array((0.3, 0.5, -1.0)) / np.linalg.norm((0.3, 0.5, -1.0))
+    ys, xs = np.mgrid[20:44, 20:44]                       # central pixels, well inside the silhouette
+    tanh = np.tan(np.radians(15.0))
+    d = np.stack([(xs + 0.5 - 32) / 32 * tanh, -(ys + 0.5 - 32) / 32 * tanh, np.ones_like(xs, dtype=float)], axis=-1)   # raster y points down
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.array((0, 0, -4.0))
+    b = (d @ o)
+    t = -b - np.sqrt(b * b - (o @ o - 1.0))
+    n = o + d * t[..., None]
+    want = 0.8 / np.pi * 3.0 * np.maximum(0.0, n @ w)
+    err_smooth = np.abs(smooth[20:44, 20:44] - want).mean()
+    err_flat = np.abs(flat[20:44, 20:44] - want).mean()
+    assert err_smooth < 0.2 * err_flat and err_smooth < 0.004, (err_smooth, err_flat)
+    # UVs / tangents: the frame changes, the estimator does not
+    sc4 = scenes.scene_c4(n_theta=12, n_phi=24)
+    cam4 = dict(scenes.C4_CAMERA, res=(48, 27))
+    fd4, pd4 = OP.film_desc(cam4["res"]), OP.path_desc(max_depth=4, spp=64, light_strategy="power")
+    a = OP.resolve_rgb(OP.Scene(sc4).render(cam4, fd4, pd4)[0])
+    full = scenes.scene_c4_smooth(n_theta=12, n_phi=24, tangents=True)
+    bimg = OP.resolve_rgb(OP.Scene(dict(sc4, uvs=full["uvs"])).render(cam4, fd4, pd4)[0])
+    assert not np.array_equal(a, bimg) and abs(a.mean() - bimg.mean()) / a.mean() < 0.03
+    cimg = OP.resolve_rgb(OP.Scene(full).render(cam4, fd4, pd4)[0])
+    assert not np.isnan(cimg).any() and cimg.mean() > 0.01
