@@ -74,13 +74,15 @@ typedef struct pb2_light {
     float falloff_start;/* spot: half-angle where the falloff starts, degrees (spot.rs:39) */
 } pb2_light;
 
-/* src/cameras/perspective.rs:34-82 PerspectiveCamera (pinhole: lens_radius = 0) + Transform::look_at. */
+/* src/cameras/perspective.rs:34-82 PerspectiveCamera + Transform::look_at. */
 typedef struct pb2_camera {
     float pos[3];
     float look[3];
     float up[3];
     float fov;          /* degrees, applies to the shorter image axis */
-    int32_t res_x, res_y;
+    int32_t res_x, res_y;   /* the film's full resolution */
+    float lens_radius;  /* thin lens (perspective.rs:101-107); 0 = pinhole */
+    float focal_distance;
 } pb2_camera;
 
 enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1, PB2_FILTER_TRIANGLE = 2, PB2_FILTER_MITCHELL = 3, PB2_FILTER_SINC = 4 };
@@ -182,8 +184,9 @@ int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void*
 int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream);
 
 /* ---- Camera::generate_ray (src/cameras/perspective.rs:90-112), batched -------------------------------- */
-/* One ray per film point p_film[i] = {x, y} in raster space. */
-int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, uint64_t n, pb2_ray* rays);
+/* One ray per CameraSample: p_film[i] = {x, y} in raster space and, for a thin lens, p_lens[i] = {u, v} in [0,1)^2
+ * (NULL: the lens centre). */
+int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, const float* p_lens, uint64_t n, pb2_ray* rays);
 /* One ray through every pixel centre (x+0.5, y+0.5), row-major; device output. */
 int pb2_camera_primary_rays_device(const pb2_camera* cam, void* d_rays, void* stream);
 /* Host-side matrices for parity checks: raster_to_camera, camera_to_world (row-major 4x4 each). */

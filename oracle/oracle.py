@@ -60,6 +60,7 @@ def lib():
         L.orc_camera_matrices.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_camera_primary_rays.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_camera_rays_lens.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         _bind_path(L)
         _LIB = L
     return _LIB
@@ -220,10 +221,15 @@ def camera_primary_rays(pos, look, up, fov, res):
     return rays
 
 
-def camera_rays(pos, look, up, fov, res, pfilm):
+def camera_rays(pos, look, up, fov, res, pfilm, plens=None, lens_radius=0.0, focal_distance=1e6):
     pfilm = _f32(pfilm).reshape(-1, 2)
     rays = np.empty((len(pfilm), 8), dtype=np.float32)
-    lib().orc_camera_rays(_p(_cam9(pos, look, up)), fov, res[0], res[1], _p(pfilm), len(pfilm), _p(rays))
+    if plens is None:
+        lib().orc_camera_rays(_p(_cam9(pos, look, up)), fov, res[0], res[1], _p(pfilm), len(pfilm), _p(rays))
+    else:
+        plens = _f32(plens).reshape(-1, 2)
+        lib().orc_camera_rays_lens(_p(_cam9(pos, look, up)), fov, res[0], res[1], lens_radius, focal_distance, _p(pfilm), _p(plens),
+                                   len(pfilm), _p(rays))
     return rays
 
 

@@ -238,6 +238,18 @@ void orc_camera_rays(const float* cam9, float fov, int rx, int ry, const float* 
         std::memcpy(rays8 + 8 * i, &r, 32);
     }
 }
+// Thin lens (perspective.rs:101-107): film points + lens samples.
+void orc_camera_rays_lens(const float* cam9, float fov, int rx, int ry, float lens_radius, float focal_distance, const float* pfilm2,
+                          const float* plens2, uint64_t n, float* rays8) {
+    Camera c;
+    c.init({cam9[0], cam9[1], cam9[2]}, {cam9[3], cam9[4], cam9[5]}, {cam9[6], cam9[7], cam9[8]}, fov, rx, ry);
+    c.lens_radius = lens_radius;
+    c.focal_distance = focal_distance;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r = c.generate_ray(pfilm2[2 * i], pfilm2[2 * i + 1], plens2[2 * i], plens2[2 * i + 1]);
+        std::memcpy(rays8 + 8 * i, &r, 32);
+    }
+}
 
 }  // extern "C"
 

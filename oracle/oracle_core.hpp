@@ -940,10 +940,11 @@ inline V3 t_vector(const M4& m, V3 v) {                                         
             (m.m[2][0] * v.x + m.m[2][1] * v.y) + m.m[2][2] * v.z};
 }
 
-struct Camera {                    // cameras/perspective.rs:34-82 (pinhole: lens_radius = 0)
+struct Camera {                    // cameras/perspective.rs:34-82
     M4 raster_to_camera;
     M4 camera_to_world;
     int res_x, res_y;
+    Float lens_radius = 0.0f, focal_distance = 1e6f;        // perspective.rs:26-27 (pbrt's defaults)
     void init(V3 pos, V3 look, V3 up, Float fov, int rx, int ry) {
         res_x = rx; res_y = ry;
         // pbrt-v3 api.cpp default screen window: the shorter axis spans [-1,1]
@@ -961,12 +962,22 @@ struct Camera {                    // cameras/perspective.rs:34-82 (pinhole: len
         raster_to_camera = r2c.m;
         camera_to_world = t_look_at(pos, look, up).m_inv;
     }
-    // perspective.rs:90-112 + geometry.rs:865-881
-    Ray generate_ray(Float fx, Float fy) const {
+    // perspective.rs:90-112 + geometry.rs:865-881; (lx, ly) = CameraSample::p_lens, used by the thin lens only
+    Ray generate_ray(Float fx, Float fy, Float lx = 0.0f, Float ly = 0.0f) const {
         V3 p_camera = t_point(raster_to_camera, V3{fx, fy, 0.0f});
         V3 d_cam = normalize(p_camera);
+        V3 o_cam{0, 0, 0};
+        if (lens_radius > 0.0f) {                                                   // :101-107
+            Float px, py;
+            concentric_sample_disk(lx, ly, &px, &py);
+            px = px * lens_radius; py = py * lens_radius;
+            const Float ft = focal_distance / d_cam.z;
+            const V3 p_focus = o_cam + d_cam * ft;                                  // Ray::point, geometry.rs:790-792
+            o_cam = V3{px, py, 0.0f};
+            d_cam = normalize(p_focus - o_cam);
+        }
         V3 o_error;
-        V3 o = t_point_err(camera_to_world, V3{0, 0, 0}, &o_error);
+        V3 o = t_point_err(camera_to_world, o_cam, &o_error);
         V3 d = t_vector(camera_to_world, d_cam);
         Float ls = length_squared(d);
         Float t_max = kInfinity;

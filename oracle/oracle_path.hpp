@@ -72,6 +72,7 @@ struct CameraDesc {
     Float pos[3], look[3], up[3];
     Float fov;
     int32_t res_x, res_y;
+    Float lens_radius, focal_distance;       // perspective.rs:26-27; lens_radius <= 0: pinhole
 };
 enum { FILTER_BOX = 0, FILTER_GAUSSIAN = 1, FILTER_TRIANGLE = 2, FILTER_MITCHELL = 3, FILTER_SINC = 4 };
 struct FilmDesc {
@@ -1056,6 +1057,8 @@ struct Stray {
 inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& fd, const PathDesc& pd, int mode, int threads, Float* out_xyzw) {
     Camera cam;
     cam.init({cd.pos[0], cd.pos[1], cd.pos[2]}, {cd.look[0], cd.look[1], cd.look[2]}, {cd.up[0], cd.up[1], cd.up[2]}, cd.fov, cd.res_x, cd.res_y);
+    cam.lens_radius = cd.lens_radius;
+    cam.focal_distance = cd.focal_distance;
     Film film;
     film.init(fd);
     const int W = film.sb_x1 - film.sb_x0, H = film.sb_y1 - film.sb_y0;
@@ -1104,9 +1107,9 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                         smp.get_2d(&u0, &u1);                                                   // sampler.rs:27-33
                         ut = smp.get_1d();
                         smp.get_2d(&l0, &l1);
-                        (void)ut; (void)l0; (void)l1;
+                        (void)ut;
                         Float pfx = (Float)x + u0, pfy = (Float)y + u1;
-                        Ray ray = cam.generate_ray(pfx, pfy);
+                        Ray ray = cam.generate_ray(pfx, pfy, l0, l1);
                         RGB L = path_li(scene, ray, smp, pd.max_depth, pd.rr_threshold);
                         if (has_nans(L) || y_value(L) < -1e-5f || std::isinf(y_value(L))) L = rgb(0);   // D22 FIX
                         L = film.clamp_luminance(L);

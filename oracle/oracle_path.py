@@ -22,7 +22,7 @@ class Light(C.Structure):
 
 class CameraDesc(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
-                ("res_x", C.c_int32), ("res_y", C.c_int32)]
+                ("res_x", C.c_int32), ("res_y", C.c_int32), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
 
 
 class FilmDesc(C.Structure):
@@ -88,6 +88,8 @@ def camera_desc(cam):
     c.up[:] = cam["up"]
     c.fov = cam["fov"]
     c.res_x, c.res_y = cam["res"]
+    c.lens_radius = cam.get("lens_radius", 0.0)
+    c.focal_distance = cam.get("focal_distance", 1e6)
     return c
 
 

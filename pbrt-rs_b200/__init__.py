@@ -43,7 +43,7 @@ class Light(C.Structure):
 
 class CameraDesc(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
-                ("res_x", C.c_int32), ("res_y", C.c_int32)]
+                ("res_x", C.c_int32), ("res_y", C.c_int32), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
 
 
 class FilmDesc(C.Structure):
@@ -157,7 +157,7 @@ def lib():
         "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
         "pb2_intersect_device": [vp, vp, u64, vp, vp, vp], "pb2_intersect_p_device": [vp, vp, u64, vp, vp],
-        "pb2_camera_generate_rays": [vp, vp, u64, vp], "pb2_camera_primary_rays_device": [vp, vp, vp],
+        "pb2_camera_generate_rays": [vp, vp, vp, u64, vp], "pb2_camera_primary_rays_device": [vp, vp, vp],
         "pb2_camera_matrices": [vp, vp, vp],
         "pb2_spawn_shadow_rays_device": [vp, vp, vp, u64, vp, vp, vp],
         "pb2_spawn_bounce_rays_device": [vp, vp, vp, u64, vp, vp],
@@ -196,13 +196,14 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def camera_desc(pos, look, up, fov, res):
+def camera_desc(pos, look, up, fov, res, lens_radius=0.0, focal_distance=1e6):
     c = CameraDesc()
     c.pos[:] = pos
     c.look[:] = look
     c.up[:] = up
     c.fov = fov
     c.res_x, c.res_y = res
+    c.lens_radius, c.focal_distance = lens_radius, focal_distance
     return c
 
 
@@ -337,10 +338,10 @@ class BVHAccel:
 
 
 class PerspectiveCamera:
-    """Mirror of src/cameras/perspective.rs (pinhole)."""
+    """Mirror of src/cameras/perspective.rs: pinhole, or thin lens when lens_radius > 0 (perspective.rs:101-107)."""
 
-    def __init__(self, pos, look, up, fov, res):
-        self.desc = camera_desc(pos, look, up, fov, res)
+    def __init__(self, pos, look, up, fov, res, lens_radius=0.0, focal_distance=1e6):
+        self.desc = camera_desc(pos, look, up, fov, res, lens_radius, focal_distance)
         self.res = tuple(res)
 
     def matrices(self):
@@ -349,10 +350,12 @@ class PerspectiveCamera:
         check(lib().pb2_camera_matrices(C.byref(self.desc), _p(r2c), _p(c2w)))
         return r2c, c2w
 
-    def generate_rays(self, p_film):
+    def generate_rays(self, p_film, p_lens=None):
+        """Camera::generate_ray per CameraSample (p_film [n,2] raster points, p_lens [n,2] lens samples for a thin lens)."""
         p_film = _f32(p_film).reshape(-1, 2)
+        p_lens = None if p_lens is None else _f32(p_lens).reshape(-1, 2)
         rays = np.empty((len(p_film), 8), dtype=np.float32)
-        check(lib().pb2_camera_generate_rays(C.byref(self.desc), _p(p_film), len(p_film), _p(rays)))
+        check(lib().pb2_camera_generate_rays(C.byref(self.desc), _p(p_film), _p(p_lens), len(p_film), _p(rays)))
         return rays
 
     def primary_rays_device(self, d_rays, stream=None):

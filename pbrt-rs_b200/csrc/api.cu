@@ -27,7 +27,11 @@ void camera_setup(const float pos[3], const float look[3], const float up[3], fl
 int make_camera_view(const pb2_camera* cam, CameraView* out) {
     if (!cam || cam->res_x <= 0 || cam->res_y <= 0 || !(cam->fov > 0.0f && cam->fov < 180.0f))
         return set_error(PB2_ERR_INVALID, "invalid camera description");
+    if (!(cam->lens_radius >= 0.0f) || (cam->lens_radius > 0.0f && !(cam->focal_distance > 0.0f)))
+        return set_error(PB2_ERR_INVALID, "thin lens needs lens_radius >= 0 and focal_distance > 0");
     camera_setup(cam->pos, cam->look, cam->up, cam->fov, cam->res_x, cam->res_y, out);
+    out->lens_radius = cam->lens_radius;
+    out->focal_distance = cam->focal_distance;
     return PB2_OK;
 }
 
@@ -521,20 +525,23 @@ int pb2_camera_matrices(const pb2_camera* cam, float r2c[16], float c2w[16]) {
     return PB2_OK;
 }
 
-int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, uint64_t n, pb2_ray* rays) {
+int pb2_camera_generate_rays(const pb2_camera* cam, const float* p_film, const float* p_lens, uint64_t n, pb2_ray* rays) {
     CameraView v;
     int rc = make_camera_view(cam, &v);
     if (rc) return rc;
     if (n == 0) return PB2_OK;
     if (!p_film || !rays) return set_error(PB2_ERR_INVALID, "null buffer");
-    void *d_p = nullptr, *d_r = nullptr;
+    void *d_p = nullptr, *d_l = nullptr, *d_r = nullptr;
     PB2_CUDA(cudaMalloc(&d_p, n * 8));
     cudaError_t e = cudaMalloc(&d_r, n * 32);
-    if (e != cudaSuccess) { cudaFree(d_p); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    if (e == cudaSuccess && p_lens) e = cudaMalloc(&d_l, n * 8);
+    if (e != cudaSuccess) { cudaFree(d_p); cudaFree(d_r); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     e = cudaMemcpy(d_p, p_film, n * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) { launch_camera_rays(v, d_p, n, d_r, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess && p_lens) e = cudaMemcpy(d_l, p_lens, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch_camera_rays(v, d_p, d_l, n, d_r, 0); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpy(rays, d_r, n * 32, cudaMemcpyDeviceToHost);
     cudaFree(d_p);
+    cudaFree(d_l);
     cudaFree(d_r);
     if (e != cudaSuccess) return cuda_fail(e, "camera ray generation", __FILE__, __LINE__);
     return PB2_OK;
@@ -545,7 +552,7 @@ int pb2_camera_primary_rays_device(const pb2_camera* cam, void* d_rays, void* st
     int rc = make_camera_view(cam, &v);
     if (rc) return rc;
     if (!d_rays) return set_error(PB2_ERR_INVALID, "null buffer");
-    launch_camera_rays(v, nullptr, (uint64_t)v.res_x * (uint64_t)v.res_y, d_rays, (cudaStream_t)stream);
+    launch_camera_rays(v, nullptr, nullptr, (uint64_t)v.res_x * (uint64_t)v.res_y, d_rays, (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
     return PB2_OK;
 }

@@ -15,12 +15,13 @@ struct CameraView {
     mat4 raster_to_camera;
     mat4 camera_to_world;
     int res_x, res_y;
+    float lens_radius, focal_distance;    // thin lens (perspective.rs:101-107); lens_radius <= 0: pinhole
 };
 
 void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, unsigned long long* d_counter,
                         cudaStream_t st);
 void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, unsigned long long* d_counter, cudaStream_t st);
-void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, void* d_rays, cudaStream_t st);
+void launch_camera_rays(const CameraView& cam, const void* d_pfilm, const void* d_plens, uint64_t n, void* d_rays, cudaStream_t st);
 void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
                          void* d_out, cudaStream_t st);
 void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st);

@@ -1,6 +1,7 @@
 // kernels_traverse.cu — batched Primitive::intersect / intersect_p kernels and the ray builders of the
 // ray-casting workloads (sm_100a; compile with -fmad=false).
 #include "kernels.hpp"
+#include "shade.cuh"
 #include "trace_persistent.cuh"
 
 #include <cstdlib>
@@ -156,11 +157,21 @@ PB2_D vec3 xf_vector(const mat4& m, vec3 v) {                                 //
               (m.m[2][0] * v.x + m.m[2][1] * v.y) + m.m[2][2] * v.z);
 }
 
-__device__ void camera_ray(const CameraView& cam, float fx, float fy, vec3* o_out, vec3* d_out, float* t_max_out) {
+__device__ void camera_ray(const CameraView& cam, float fx, float fy, float lx, float ly, vec3* o_out, vec3* d_out, float* t_max_out) {
     const vec3 p_camera = xf_point(cam.raster_to_camera, mk(fx, fy, 0.0f));
-    const vec3 d_cam = unit(p_camera);
+    vec3 d_cam = unit(p_camera);
+    vec3 o_cam = mk(0.0f, 0.0f, 0.0f);
+    if (cam.lens_radius > 0.0f) {                                             // perspective.rs:101-107
+        float px, py;
+        concentric_disk(lx, ly, &px, &py);
+        px = px * cam.lens_radius; py = py * cam.lens_radius;
+        const float ft = cam.focal_distance / d_cam.z;
+        const vec3 p_focus = o_cam + d_cam * ft;
+        o_cam = mk(px, py, 0.0f);
+        d_cam = unit(p_focus - o_cam);
+    }
     vec3 o_err;
-    vec3 o = xf_point_err(cam.camera_to_world, mk(0.0f, 0.0f, 0.0f), &o_err);
+    vec3 o = xf_point_err(cam.camera_to_world, o_cam, &o_err);
     const vec3 d = xf_vector(cam.camera_to_world, d_cam);
     const float ls = len2(d);
     float t_max = __int_as_float(0x7f800000);
@@ -174,8 +185,8 @@ __device__ void camera_ray(const CameraView& cam, float fx, float fy, vec3* o_ou
     *t_max_out = t_max;
 }
 
-__global__ void __launch_bounds__(256) k_camera_rays(CameraView cam, const float2* __restrict__ p_film, uint64_t n,
-                                                      float4* __restrict__ rays) {
+__global__ void __launch_bounds__(256) k_camera_rays(CameraView cam, const float2* __restrict__ p_film, const float2* __restrict__ p_lens,
+                                                      uint64_t n, float4* __restrict__ rays) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float fx, fy;
@@ -188,14 +199,15 @@ __global__ void __launch_bounds__(256) k_camera_rays(CameraView cam, const float
     }
     vec3 o, d;
     float t_max;
-    camera_ray(cam, fx, fy, &o, &d, &t_max);
+    const float2 pl = p_lens ? p_lens[i] : make_float2(0.5f, 0.5f);           // lens centre when no lens samples are given
+    camera_ray(cam, fx, fy, pl.x, pl.y, &o, &d, &t_max);
     rays[2 * i] = make_float4(o.x, o.y, o.z, t_max);
     rays[2 * i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
 }
 
-void launch_camera_rays(const CameraView& cam, const void* d_pfilm, uint64_t n, void* d_rays, cudaStream_t st) {
+void launch_camera_rays(const CameraView& cam, const void* d_pfilm, const void* d_plens, uint64_t n, void* d_rays, cudaStream_t st) {
     if (n == 0) return;
-    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, (const float2*)d_pfilm, n, (float4*)d_rays);
+    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, (const float2*)d_pfilm, (const float2*)d_plens, n, (float4*)d_rays);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -245,20 +257,7 @@ __global__ void __launch_bounds__(256) k_spawn_shadow(SceneView s, const float4*
     out[2 * i + 1] = d4;
 }
 
-// sampling.rs:258-273 concentric_sample_disk, :289-294 cosine_sample_hemisphere (D30 FIX: z = sqrt(max(0, 1-x^2-y^2)))
-PB2_D vec3 cosine_hemisphere(float u0, float u1) {
-    const float ox = 2.0f * u0 - 1.0f, oy = 2.0f * u1 - 1.0f;
-    float dx = 0.0f, dy = 0.0f;
-    if (!(ox == 0.0f && oy == 0.0f)) {
-        float r, theta;
-        if (fabsf(ox) > fabsf(oy)) { r = ox; theta = (PB2_PI / 4.0f) * (oy / ox); }
-        else { r = oy; theta = (PB2_PI / 2.0f) - (PB2_PI / 4.0f) * (ox / oy); }
-        dx = r * det_cos(theta);
-        dy = r * det_sin(theta);
-    }
-    const float z = sqrtf(fmaxf(0.0f, (1.0f - dx * dx) - dy * dy));
-    return mk(dx, dy, z);
-}
+// (cosine_hemisphere: shade.cuh — sampling.rs:258-273, :289-294)
 
 // interaction.rs:132-135 spawn_ray(d): o = offset_ray_origin(p, err, n, d), t_max = inf.  Direction: cosine-weighted
 // about the geometric normal flipped towards the incoming side, frame from coordinate_system(n); PCG32 stream = ray index.

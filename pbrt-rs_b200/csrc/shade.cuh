@@ -85,7 +85,7 @@ PB2_HD float fresnel_dielectric(float ci, float eta_i, float eta_t) {
 }
 
 // ---- sampling.rs --------------------------------------------------------------------------------------------------
-PB2_HD vec3 cosine_hemisphere(float u0, float u1) {          // :258-273 concentric disk, :289-294 (D30 FIX)
+PB2_HD void concentric_disk(float u0, float u1, float* x, float* y) {      // concentric_sample_disk, :258-273
     const float ox = u0 * 2.0f - 1.0f, oy = u1 * 2.0f - 1.0f;
     float dx = 0.0f, dy = 0.0f;
     if (!(ox == 0.0f && oy == 0.0f)) {
@@ -97,6 +97,12 @@ PB2_HD vec3 cosine_hemisphere(float u0, float u1) {          // :258-273 concent
         dx = c * r;
         dy = s * r;
     }
+    *x = dx;
+    *y = dy;
+}
+PB2_HD vec3 cosine_hemisphere(float u0, float u1) {          // :289-294 (D30 FIX)
+    float dx, dy;
+    concentric_disk(u0, u1, &dx, &dy);
     return mk(dx, dy, sqrtf(fmaxf(0.0f, (1.0f - dx * dx) - dy * dy)));
 }
 PB2_HD float power_heuristic(float f_pdf, float g_pdf) {

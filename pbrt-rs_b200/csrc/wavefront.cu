@@ -267,14 +267,24 @@ __device__ __forceinline__ vec3 cam_point(const mat4& m, vec3 p) {
     if (wp == 1.0f) return mk(xp, yp, zp);
     return mk(xp, yp, zp) / wp;
 }
-__device__ void gen_camera_ray(const CameraView& cam, float fx, float fy, vec3* o_out, vec3* d_out, float* t_max_out) {
-    const vec3 d_cam = unit(cam_point(cam.raster_to_camera, mk(fx, fy, 0.0f)));
+__device__ void gen_camera_ray(const CameraView& cam, float fx, float fy, float lx, float ly, vec3* o_out, vec3* d_out, float* t_max_out) {
+    vec3 d_cam = unit(cam_point(cam.raster_to_camera, mk(fx, fy, 0.0f)));
+    vec3 oc = mk(0.0f, 0.0f, 0.0f);
+    if (cam.lens_radius > 0.0f) {                                      // thin lens, perspective.rs:101-107
+        float px, py;
+        concentric_disk(lx, ly, &px, &py);
+        px = px * cam.lens_radius; py = py * cam.lens_radius;
+        const float ft = cam.focal_distance / d_cam.z;
+        const vec3 p_focus = oc + d_cam * ft;
+        oc = mk(px, py, 0.0f);
+        d_cam = unit(p_focus - oc);
+    }
     const mat4& m = cam.camera_to_world;
-    // origin (0,0,0) through camera_to_world with its error bound (geometry.rs:898-936)
-    vec3 o = cam_point(m, mk(0.0f, 0.0f, 0.0f));
-    const float xs = ((fabsf(m.m[0][0] * 0.0f) + fabsf(m.m[0][1] * 0.0f)) + fabsf(m.m[0][2] * 0.0f)) + fabsf(m.m[0][3]);
-    const float ys = ((fabsf(m.m[1][0] * 0.0f) + fabsf(m.m[1][1] * 0.0f)) + fabsf(m.m[1][2] * 0.0f)) + fabsf(m.m[1][3]);
-    const float zs = ((fabsf(m.m[2][0] * 0.0f) + fabsf(m.m[2][1] * 0.0f)) + fabsf(m.m[2][2] * 0.0f)) + fabsf(m.m[2][3]);
+    // origin through camera_to_world with its error bound (geometry.rs:898-936)
+    vec3 o = cam_point(m, oc);
+    const float xs = ((fabsf(m.m[0][0] * oc.x) + fabsf(m.m[0][1] * oc.y)) + fabsf(m.m[0][2] * oc.z)) + fabsf(m.m[0][3]);
+    const float ys = ((fabsf(m.m[1][0] * oc.x) + fabsf(m.m[1][1] * oc.y)) + fabsf(m.m[1][2] * oc.z)) + fabsf(m.m[1][3]);
+    const float zs = ((fabsf(m.m[2][0] * oc.x) + fabsf(m.m[2][1] * oc.y)) + fabsf(m.m[2][2] * oc.z)) + fabsf(m.m[2][3]);
     const vec3 o_err = mk(xs, ys, zs) * gammaf_(3.0f);
     const vec3 d = mk((m.m[0][0] * d_cam.x + m.m[0][1] * d_cam.y) + m.m[0][2] * d_cam.z,
                       (m.m[1][0] * d_cam.x + m.m[1][1] * d_cam.y) + m.m[1][2] * d_cam.z,
@@ -297,13 +307,13 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
         const SlotInfo si = slot_info(map, film, slot);
         PathSampler smp;
         smp.start(map.smp, si);
-        float u0, u1, l0, l1;
+        float u0, u1, l0 = 0.0f, l1 = 0.0f;
         smp.next2(&u0, &u1);                                          // p_film offset (x then y)
-        if (smp.halton()) smp.dim += 3u;                              // time, p_lens: drawn, never used (pinhole)
+        if (smp.halton() && !(cam.lens_radius > 0.0f)) smp.dim += 3u; // time, p_lens: drawn, never used by a pinhole
         else { (void)smp.next1(); smp.next2(&l0, &l1); }
         vec3 o, d;
         float t_max;
-        gen_camera_ray(cam, (float)si.x + u0, (float)si.y + u1, &o, &d, &t_max);
+        gen_camera_ray(cam, (float)si.x + u0, (float)si.y + u1, l0, l1, &o, &d, &t_max);
         b.ray_o[slot] = make_float4(o.x, o.y, o.z, t_max);
         b.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
         b.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);

@@ -16,7 +16,8 @@ pub struct pb2_material { pub ty: i32, pub kd: [f32; 3], pub ks: [f32; 3], pub r
 pub struct pb2_light { pub ty: i32 /* 0 point, 1 area, 2 spot, 3 distant */, pub p: [f32; 3], pub i: [f32; 3], pub prim_id: u32, pub two_sided: i32,
                        pub axis: [f32; 3] /* spot: row 2 of world_to_light; distant: w */, pub total_width: f32, pub falloff_start: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct pb2_camera { pub pos: [f32; 3], pub look: [f32; 3], pub up: [f32; 3], pub fov: f32, pub res_x: i32, pub res_y: i32 }
+pub struct pb2_camera { pub pos: [f32; 3], pub look: [f32; 3], pub up: [f32; 3], pub fov: f32, pub res_x: i32, pub res_y: i32,
+                        pub lens_radius: f32 /* 0 = pinhole */, pub focal_distance: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_film_desc { pub res_x: i32, pub res_y: i32, pub filter: i32 /* 0 box, 1 gaussian, 2 triangle, 3 mitchell, 4 sinc */,
                            pub radius_x: f32, pub radius_y: f32, pub gaussian_alpha: f32, pub mitchell_b: f32, pub mitchell_c: f32, pub sinc_tau: f32,

@@ -24,7 +24,7 @@ def OP(orc):
 
 def setup_scene(gpu, OP, sc, cam, **path_kw):
     accel = gpu.BVHAccel(gpu.scene_from_dict(sc), max_prims_in_node=4)
-    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"], cam.get("lens_radius", 0.0), cam.get("focal_distance", 1e6))
     integ = gpu.PathIntegrator(accel, camera, **path_kw)
     ref = OP.Scene(sc, 4)
     return accel, camera, integ, ref
@@ -429,3 +429,35 @@ def test_shading_geometry_argument_errors(gpu, scenes):
     gpu.BVHAccel(scene)
     with pytest.raises(gpu.Pb2Error):                        # after the build
         gpu.check(gpu.lib().pb2_scene_set_shading_geometry(scene.h, None, None, None))
+
+
+@pytest.mark.parametrize("sampler", ["random", "halton", "zerotwo"])
+def test_thin_lens_camera_bit_exact(gpu, OP, orc, scenes, sampler):
+    """PerspectiveCamera with lens_radius > 0 (perspective.rs:101-107): the lens sample of every camera sample (CameraSample::p_lens,
+    drawn after p_film and time) moves the ray origin onto the lens and re-aims it at the plane of focus.  Rays for explicit
+    (p_film, p_lens) pairs, per-sample radiance and the film equal the oracle's bits; out-of-focus geometry blurs."""
+    cam = dict(scenes.C2_CAMERA, res=(96, 96), lens_radius=25.0, focal_distance=1080.0)
+    kw = dict(max_depth=4, rr_threshold=1.0, light_strategy="uniform", spp=16)
+    accel, camera, _, ref = setup_scene(gpu, OP, scenes.scene_c2(), cam, **kw)
+    rng = np.random.default_rng(2)
+    pf = rng.uniform(0, 96, size=(5000, 2)).astype(np.float32)
+    pl = rng.uniform(0, 1, size=(5000, 2)).astype(np.float32)
+    rays = camera.generate_rays(pf, pl)
+    want = orc.camera_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"], pf, pl, cam["lens_radius"], cam["focal_distance"])
+    assert np.array_equal(bits(rays), bits(want))
+    pin = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"]).generate_rays(pf)
+    assert np.abs(rays[:, 0:3] - pin[:, 0:3]).max() > 10.0                  # origins spread over the lens
+    integ = gpu.PathIntegrator(accel, camera, sampler=sampler, **kw)
+    xy = np.stack([rng.integers(0, 96, 20000), rng.integers(0, 96, 20000)], axis=1)
+    s = rng.integers(0, 16, size=20000)
+    L, pfilm = integ.li(xy, s)
+    rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), OP.path_desc(sampler=sampler, **kw), xy, s)
+    assert np.array_equal(bits(pfilm), bits(rpf))
+    mism = (bits(L) != bits(rL)).any(axis=1)
+    assert mism.sum() == 0, f"{mism.sum()} samples differ"
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(sampler=sampler, **kw), mode=1)
+    assert np.array_equal(bits(film.read_xyzw()), bits(want))
+    with pytest.raises(gpu.Pb2Error):
+        gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"], lens_radius=1.0, focal_distance=0.0).generate_rays(pf)
