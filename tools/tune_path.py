@@ -23,8 +23,9 @@ def setup(sc, cam, pk):
     return accel, camera, pb2.PathIntegrator(accel, camera, **pk), pb2.Film(cam["res"])
 
 
-c2 = setup(scenes.scene_c2(), scenes.C2_CAMERA, dict(scenes.C2_PATH, spp=16))
-c4 = setup(scenes.scene_c4(), scenes.C4_CAMERA, dict(scenes.C4_PATH, spp=4))
+SPP2, SPP4 = int(os.environ.get("TUNE_C2_SPP", "16")), int(os.environ.get("TUNE_C4_SPP", "4"))
+c2 = setup(scenes.scene_c2(), scenes.C2_CAMERA, dict(scenes.C2_PATH, spp=SPP2))
+c4 = setup(scenes.scene_c4(), scenes.C4_CAMERA, dict(scenes.C4_PATH, spp=SPP4))
 
 
 def timed(w, reps=4):
