@@ -334,6 +334,7 @@ __global__ void k_iter_begin(PathBuffers b, int cur) {
         b.counters[T_EXTEND] += b.counters[C_ACTIVE_A + cur];
         b.counters[T_SHADOW] += b.counters[C_SHADOW];        // rays of the previous bounce's visibility stage
         b.counters[T_MIS] += b.counters[C_MIS];
+        b.counters[C_MIS_PREV] = b.counters[C_MIS];         // the MIS rays of the previous bounce ride in this bounce's k_extend
         b.counters[C_ACTIVE_A + (cur ^ 1)] = 0;
         b.counters[C_MAT0] = b.counters[C_MAT1] = b.counters[C_MAT2] = 0;
         b.counters[C_SHADOW] = b.counters[C_MIS] = 0;
@@ -342,37 +343,6 @@ __global__ void k_iter_begin(PathBuffers b, int cur) {
 }
 
 // ---- extend: closest hit over the active queue; hits are binned by material type (material-sorted shading) ---------------
-struct ExtendSink {
-    PathBuffers b;
-    ShadeView sh;
-    const uint32_t* queue;
-    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
-        const uint32_t slot = queue[i];
-        const float4 ro = b.ray_o[slot], rd = b.ray_d[slot];
-        *o = mk(ro.x, ro.y, ro.z);
-        *d = mk(rd.x, rd.y, rd.z);
-        *t_max = ro.w;
-        return true;
-    }
-    PB2_D void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
-        (void)t;
-        b.hit[queue[i]] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
-    }
-    PB2_D void finish(uint32_t i, bool found, float) const {
-        if (!found) return;                              // escaped: no infinite lights in scope, the path is finished
-        const uint32_t slot = queue[i];
-        const uint32_t prim = b.hit[slot].x;             // written by this thread's last accept()
-        const int type = sh.mats[sh.tri_material[prim]].type;
-        // (selects, not b.q_mat[type]: a run-time index would move the whole parameter struct into local memory)
-        queue_push(&b.counters[C_MAT0 + type], type == 0 ? b.q_mat[0] : (type == 1 ? b.q_mat[1] : b.q_mat[2]), slot);
-    }
-    PB2_D void occluded(uint32_t, bool) const {}
-};
-__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
-    const ExtendSink sink{b, sh, b.q_active[cur]};
-    trace_persistent<false>(s, (uint32_t)b.counters[C_ACTIVE_A + cur], &b.counters[C_WORK_EXTEND], sink, tune);
-}
-
 // l += beta * (estimate_direct / light_pdf) (integrator.rs:178-191,243-261,:133, path.rs:117-120) for the NEE record of `slot`:
 // ld = [unoccluded light sample] + [BSDF sample that reached the light], added in that order.  Runs inside the visibility
 // kernels the moment the last pending query of the record is answered, so there is no separate resolve pass.
@@ -385,6 +355,53 @@ __device__ __forceinline__ void resolve_nee(const PathBuffers& b, uint32_t slot,
     float4 Lf = b.L[slot];
     const rgb3 L = mkc(Lf.x, Lf.y, Lf.z) + mkc(bn.x, bn.y, bn.z) * (ld / pick_pdf);
     b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
+}
+
+// Work items [0, n_extend) are this bounce's path rays; [n_extend, n_extend + n_mis) are the MIS rays the previous bounce's
+// estimate_direct left behind (BSDF-sampled rays towards the chosen light, integrator.rs:243-261): both are closest-hit
+// walks, so they share the launch (a launch of their own cost 3-4 % of a frame for 0.1 % of the rays).  The shadow rays of
+// that bounce were answered by k_shadow earlier in the stream, so an MIS ray finishing here completes its NEE record.
+struct ExtendSink {
+    PathBuffers b;
+    ShadeView sh;
+    const uint32_t* queue;
+    uint32_t n_extend;
+    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
+        const bool mis = i >= n_extend;
+        const uint32_t slot = mis ? b.q_mis[i - n_extend] : queue[i];
+        const float4 ro = mis ? b.mis_o[slot] : b.ray_o[slot], rd = mis ? b.mis_d[slot] : b.ray_d[slot];
+        *o = mk(ro.x, ro.y, ro.z);
+        *d = mk(rd.x, rd.y, rd.z);
+        *t_max = mis ? kInf : ro.w;
+        return true;
+    }
+    PB2_D void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2) const {
+        (void)t;
+        if (i >= n_extend) b.mis_prim[b.q_mis[i - n_extend]] = prim;
+        else b.hit[queue[i]] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
+    }
+    PB2_D void finish(uint32_t i, bool found, float) const {
+        if (i >= n_extend) {
+            const uint32_t slot = b.q_mis[i - n_extend];
+            const float4 t1 = b.t1[slot], t2 = b.t2[slot];
+            const bool reached_light = found && b.mis_prim[slot] == __float_as_uint(t2.w);    // D56 FIX: the closest hit is the light
+            const bool lit = (__float_as_uint(t1.w) & 1u) && !b.occluded[slot];               // k_shadow ran before this kernel
+            resolve_nee(b, slot, lit, t1, reached_light, t2);
+            return;
+        }
+        if (!found) return;                              // escaped: no infinite lights in scope, the path is finished
+        const uint32_t slot = queue[i];
+        const uint32_t prim = b.hit[slot].x;             // written by this thread's last accept()
+        const int type = sh.mats[sh.tri_material[prim]].type;
+        // (selects, not b.q_mat[type]: a run-time index would move the whole parameter struct into local memory)
+        queue_push(&b.counters[C_MAT0 + type], type == 0 ? b.q_mat[0] : (type == 1 ? b.q_mat[1] : b.q_mat[2]), slot);
+    }
+    PB2_D void occluded(uint32_t, bool) const {}
+};
+__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
+    const uint32_t n_extend = (uint32_t)b.counters[C_ACTIVE_A + cur], n_mis = (uint32_t)b.counters[C_MIS_PREV];
+    const ExtendSink sink{b, sh, b.q_active[cur], n_extend};
+    trace_persistent<false>(s, n_extend + n_mis, &b.counters[C_WORK_EXTEND], sink, tune);
 }
 
 struct ShadowSink {
@@ -409,31 +426,6 @@ struct ShadowSink {
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
     const ShadowSink sink{b};
     trace_persistent<true>(s, (uint32_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
-}
-
-struct MisSink {
-    PathBuffers b;
-    PB2_D bool load(uint32_t i, vec3* o, vec3* d, float* t_max) const {
-        const uint32_t slot = b.q_mis[i];
-        const float4 ro = b.mis_o[slot], rd = b.mis_d[slot];
-        *o = mk(ro.x, ro.y, ro.z);
-        *d = mk(rd.x, rd.y, rd.z);
-        *t_max = kInf;
-        return true;
-    }
-    PB2_D void accept(uint32_t i, uint32_t prim, float, float, float, float) const { b.mis_prim[b.q_mis[i]] = prim; }
-    PB2_D void finish(uint32_t i, bool found, float) const {
-        const uint32_t slot = b.q_mis[i];
-        const float4 t1 = b.t1[slot], t2 = b.t2[slot];
-        const bool reached_light = found && b.mis_prim[slot] == __float_as_uint(t2.w);    // D56 FIX: the closest hit is the light
-        const bool lit = (__float_as_uint(t1.w) & 1u) && !b.occluded[slot];               // k_shadow ran before this kernel
-        resolve_nee(b, slot, lit, t1, reached_light, t2);
-    }
-    PB2_D void occluded(uint32_t, bool) const {}
-};
-__global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_mis(SceneView s, PathBuffers b, TraceTuning tune) {
-    const MisSink sink{b};
-    trace_persistent<false>(s, (uint32_t)b.counters[C_MIS], &b.counters[C_WORK_MIS], sink, tune);
 }
 
 // ---- shade -----------------------------------------------------------------------------------------------------------------
@@ -893,9 +885,8 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
         launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
         if (depth < pp.max_depth && sh.n_lights > 0) {
-            k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);
-            k_mis<<<trace_grid, 128, 0, st>>>(sv, b, tune);
-            launches += 2;
+            k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
+            launches += 1;
         }
         launches += 5;
     }

@@ -78,7 +78,7 @@ struct PathMap {
 };
 
 enum Counter : int {
-    C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6,
+    C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6, C_MIS_PREV = 7,
     C_WORK_EXTEND = 8, C_WORK_SHADOW = 9, C_WORK_MIS = 10, C_STRAYS = 11, C_STRAY_OVERFLOW = 12,
     T_CAMERA = 16, T_EXTEND = 17, T_SHADOW = 18, T_MIS = 19, T_LAUNCHES = 20, C_COUNT = 24
 };
