@@ -318,3 +318,54 @@ def test_hlbvh_leaf_limit_is_an_error(gpu, scenes):
     rays[:, 3] = np.inf
     hits = accel.intersect(rays)
     assert (hits["prim_id"] == n - 1).all() and (hits["t"] == 1.0).all()       # equal t: the last triangle tested wins
+
+
+@pytest.mark.gpu
+def test_entry_points_are_thread_safe(gpu, orc, scenes):
+    """The reference's Primitive / Integrator objects are Sync + Send and called from rayon workers (parallel.rs:4-17); the C ABI
+    serialises per scene handle.  Eight host threads hammer pb2_intersect / pb2_intersect_p on one shared scene and on scenes of
+    their own, and two render into separate films of one scene: every result equals the single-threaded one bit for bit."""
+    import threading
+    v, i = scenes.scene_c1()
+    shared = gpu.BVHAccel(v, i, 4)
+    cam = scenes.C1_CAMERA
+    rays = np.concatenate([orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], (192, 192)), random_rays(30000, seed=23, finite_tmax=True)])
+    want_h, want_o = shared.intersect(rays), shared.intersect_p(rays)
+    errors = []
+
+    def work(k):
+        try:
+            own_v, own_i = scenes.random_soup(2000 + 100 * k, seed=k)
+            own = gpu.BVHAccel(own_v, own_i, 4)
+            own_want = own.intersect(rays[:5000])
+            for rep in range(6):
+                sl = slice(k * 1000, k * 1000 + 20000 + rep)
+                h = shared.intersect(rays[sl])
+                o = shared.intersect_p(rays[sl])
+                if not (np.array_equal(h.view(np.uint32), want_h[sl].view(np.uint32)) and np.array_equal(o, want_o[sl])):
+                    errors.append(f"thread {k} rep {rep}: shared scene results differ")
+                if not np.array_equal(own.intersect(rays[:5000]).view(np.uint32), own_want.view(np.uint32)):
+                    errors.append(f"thread {k} rep {rep}: own scene results differ")
+        except Exception as e:          # noqa: BLE001
+            errors.append(f"thread {k}: {e!r}")
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    # two threads rendering with one scene into two films
+    sc = scenes.scene_c2()
+    accel = gpu.BVHAccel(gpu.scene_from_dict(sc), 4)
+    camera = gpu.PerspectiveCamera(*[scenes.C2_CAMERA[k] for k in ("pos", "look", "up", "fov")], (64, 64))
+    films = [gpu.Film((64, 64)) for _ in range(3)]
+    integ = [gpu.PathIntegrator(accel, camera, max_depth=4, spp=8) for _ in range(3)]
+    integ[2].render(films[2])
+    ts = [threading.Thread(target=lambda j=j: integ[j].render(films[j])) for j in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for j in range(2):
+        assert np.array_equal(films[j].read_xyzw().view(np.uint32), films[2].read_xyzw().view(np.uint32))
