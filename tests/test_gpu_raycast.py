@@ -369,3 +369,43 @@ def test_entry_points_are_thread_safe(gpu, orc, scenes):
         t.join()
     for j in range(2):
         assert np.array_equal(films[j].read_xyzw().view(np.uint32), films[2].read_xyzw().view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_hostile_rays_match_the_oracle(gpu, orc, scenes):
+    """Rays no renderer should produce but a caller might: NaN / inf origins and directions, the zero direction, t_max of 0,
+    negative, NaN and subnormal size, coordinates near FLT_MAX, origins exactly on vertices / edges / box planes.  No crash, no
+    hang, and every result (id, t bits, any-hit flag) equals the oracle's — the comparisons of the reference are followed
+    literally, NaN outcomes included."""
+    v, i = scenes.merge(scenes.uv_sphere(n_theta=24, n_phi=48), scenes.ground_grid())
+    accel = gpu.BVHAccel(v, i, 4)
+    ref = orc.BVHAccel(v, i, 4)
+    rng = np.random.default_rng(99)
+    base = random_rays(4000, seed=5, extent=3.0)
+    special = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, 3.0e38, -3.0e38, 1e-30]
+    rays = []
+    for k in range(4000):
+        r = base[k].copy()
+        for _ in range(rng.integers(1, 4)):
+            r[rng.choice([0, 1, 2, 3, 4, 5, 6])] = special[rng.integers(len(special))]
+        rays.append(r)
+    rays = np.array(rays, np.float32)
+    zero_dir = base[:200].copy(); zero_dir[:, 4:7] = 0.0
+    neg_t = base[:200].copy(); neg_t[:, 3] = -1.0
+    on_vertex = base[:600].copy(); on_vertex[:, 0:3] = v[rng.integers(0, len(v), 600)]
+    on_plane = base[:400].copy(); on_plane[:, 1] = -1.0; on_plane[:, 5] = 0.0          # in the ground plane, parallel to it
+    allr = np.concatenate([rays, zero_dir, neg_t, on_vertex, on_plane]).astype(np.float32)
+    hits, b0 = accel.intersect(allr, want_b0=True)
+    rh, rb0, _ = ref.intersect(allr, want_b0=True)
+    found = rh["prim_id"] != 0xFFFFFFFF
+    assert np.array_equal(hits["prim_id"], rh["prim_id"])
+
+    def same_bits_or_both_nan(a, b):          # a NaN is a NaN on both sides (a ray with a NaN component "hits" under the
+        return ((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))).all()      # reference's comparisons); its payload bits are not specified
+
+    assert same_bits_or_both_nan(hits["t"], rh["t"])          # a miss reports the ray's own t_max
+    assert same_bits_or_both_nan(hits["b1"][found], rh["b1"][found]) and same_bits_or_both_nan(hits["b2"][found], rh["b2"][found])
+    assert same_bits_or_both_nan(b0[found], rb0[found])
+    finite = found & np.isfinite(rh["t"])
+    assert np.array_equal(bits(hits["t"])[finite], bits(rh["t"])[finite]) and finite.sum() > 300
+    assert np.array_equal(accel.intersect_p(allr), ref.intersect_p(allr)[0])
