@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Minimal render driver: build a scene, render it with the wavefront PathIntegrator, write the image.
     python tools/render.py --scene c2 --spp 64 --sampler halton --out cornell.ppm
-Scenes: c2 (Cornell box), c4 (room with matte / plastic / glass spheres).  Output: .ppm (8-bit sRGB) or .pfm (float)."""
+Scenes: c2 (Cornell box), c4 (room with matte / plastic / glass spheres), c4smooth (the same mesh with analytic vertex normals and
+UVs), lights (c4smooth + spot and distant lights).  Output: .ppm (8-bit sRGB) or .pfm (float)."""
 import argparse
 import os
 import sys
@@ -13,10 +14,14 @@ import __graft_entry__ as ge  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scene", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--scene", default="c2", choices=["c2", "c4", "c4smooth", "lights"])
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--res", type=int, nargs=2, default=None)
-    ap.add_argument("--sampler", default="random", choices=["random", "halton"])
+    ap.add_argument("--sampler", default="random", choices=["random", "halton", "stratified", "zerotwo"])
+    ap.add_argument("--filter", default="box", choices=["box", "gaussian", "triangle", "mitchell", "sinc"])
+    ap.add_argument("--radius", type=float, default=None)
+    ap.add_argument("--lens", type=float, nargs=2, default=None, metavar=("RADIUS", "FOCAL_DISTANCE"))
+    ap.add_argument("--crop", type=float, nargs=4, default=None, metavar=("X0", "Y0", "X1", "Y1"))
     ap.add_argument("--split", default="sah", choices=["sah", "hlbvh"])
     ap.add_argument("--out", default="out.ppm")
     args = ap.parse_args()
@@ -24,17 +29,29 @@ def main():
     pb2.init(0)
     if args.scene == "c2":
         sc, cam, pk = scenes.scene_c2(), dict(scenes.C2_CAMERA), dict(scenes.C2_PATH)
-    else:
+    elif args.scene == "c4":
         sc, cam, pk = scenes.scene_c4(), dict(scenes.C4_CAMERA), dict(scenes.C4_PATH)
+    else:
+        sc, cam, pk = scenes.scene_c4_smooth(n_theta=64, n_phi=128, emissive_normals=False), dict(scenes.C4_CAMERA), dict(scenes.C4_PATH)
+        if args.scene == "lights":
+            extra = scenes.scene_all_lights(8, 16)["lights"][-2:]
+            sc["lights"] = [l for l in sc["lights"] if l["type"] == "area"] + extra
     if args.res:
         cam["res"] = tuple(args.res)
     pk["spp"] = args.spp
     t0 = time.time()
     accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4, split_method=1 if args.split == "hlbvh" else 0)
     t1 = time.time()
-    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
-    integ = pb2.PathIntegrator(accel, camera, sampler=args.sampler, **pk)
-    film = pb2.Film(cam["res"])
+    lens = dict(lens_radius=args.lens[0], focal_distance=args.lens[1]) if args.lens else {}
+    camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"], **lens)
+    skw = {}
+    if args.sampler == "stratified":
+        side = max(1, int(round(args.spp ** 0.5)))
+        skw = dict(x_samples=side, y_samples=side)
+    integ = pb2.PathIntegrator(accel, camera, sampler=args.sampler, **pk, **skw)
+    args.spp = integ.spp
+    fkw = dict(radius=(args.radius, args.radius)) if args.radius else ({} if args.filter == "box" else dict(radius=(2.0, 2.0)))
+    film = pb2.Film(cam["res"], filter=args.filter, crop=args.crop, **fkw)
     integ.render(film)
     film.write_image(args.out)
     t2 = time.time()
