@@ -115,71 +115,140 @@ __global__ void __launch_bounds__(256) k_treelet_flags(const uint32_t* __restric
     flags[i] = (i == 0u || ((codes[i] ^ codes[i - 1]) & kTreeletMask) != 0u) ? 1 : 0;
 }
 
-// emit_lbvh (bvh.rs:570-676) for treelet t over sorted range [s0, s1): nodes land in local[2 * s0 ...] in depth-first
-// order.  meta[t] = {node count, deepest level, error flag}.
-__global__ void __launch_bounds__(64) k_emit_treelets(const uint32_t* __restrict__ starts, uint32_t n_treelets, uint32_t n_prims,
-                                                     const uint32_t* __restrict__ codes, const uint32_t* __restrict__ prim,
-                                                     const float4* __restrict__ lo, const float4* __restrict__ hi, int max_prims,
-                                                     LinearNode* __restrict__ local, uint4* __restrict__ meta) {
+// emit_lbvh (bvh.rs:570-676) for all treelets at once.  pbrt's recursion is a deterministic function of the sorted Morton
+// codes, so it is evaluated here level by level instead of depth first (one thread per treelet walking its whole subtree
+// left 97 % of the machine idle: ncu, 2.7 % occupancy):
+//   k_lbvh_split    one thread per node of the current level: skip the bits the range agrees on (:608-625), make a leaf
+//                   (:583) or find the split by binary search (:627-638) and append its two children to the next level;
+//   k_lbvh_up       one thread per leaf: box of the leaf, then up the tree — the second child to arrive at a node (atomic
+//                   arrival counter) combines sizes and boxes and carries on;
+//   k_lbvh_place    one thread per node: its position in the treelet's depth-first order is its depth plus the sizes of the
+//                   first-child subtrees it hangs to the right of (walk up to the root), which is where emit_lbvh's
+//                   recursion would have written it; writes the LinearNode there (in local[2 * s0 ...], as before).
+// meta[t] = {node count, deepest level, error flag}.
+struct TNode {
+    uint32_t s, n;          // sorted range
+    uint32_t parent;        // index into the TNode array, 0xFFFFFFFF for a treelet root (roots are nodes [0, n_treelets))
+    uint32_t child;         // first child (second = child + 1); 0 for a leaf
+    uint32_t size;          // nodes in the subtree
+    int8_t bit;             // split bit (after skipping), -1..17
+    uint8_t second;         // this node is its parent's second child
+    uint8_t level;          // 0 = treelet root
+    uint8_t leaf;
+    float bmin[3], bmax[3];
+};
+
+__global__ void __launch_bounds__(256) k_lbvh_roots(const uint32_t* __restrict__ starts, uint32_t n_treelets, uint32_t n_prims, TNode* __restrict__ nodes) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_treelets) return;
-    const uint32_t s0 = starts[t], s1 = (t + 1 < n_treelets) ? starts[t + 1] : n_prims;
-    LinearNode* nodes = local + 2ull * s0;
-    struct Item { uint32_t s, n; int bit, patch, level; };
-    Item stack[40];                                                     // <= 2 pending items per Morton bit level
-    int sp = 0;
-    stack[sp++] = {s0, s1 - s0, kFirstBit, -1, 1};
-    uint32_t count = 0, err = 0;
-    int deepest = 0;
-    while (sp > 0) {
-        Item it = stack[--sp];
-        // bits on which the whole range agrees make no node (:608-625); a short range or no bits left makes a leaf (:583)
-        while (it.bit >= 0 && it.n >= (uint32_t)max_prims && ((codes[it.s] ^ codes[it.s + it.n - 1]) & (1u << it.bit)) == 0u) --it.bit;
-        const uint32_t me = count++;
-        if (it.patch >= 0) nodes[it.patch].offset = me;                 // second child of `patch`
-        if (it.level > deepest) deepest = it.level;
-        LinearNode& nd = nodes[me];
-        nd.pad = (uint8_t)((it.level - 1) & 1);                         // depth parity inside the treelet
-        if (it.bit < 0 || it.n < (uint32_t)max_prims) {
-            if (it.n > 65535u) err = 1;                                 // LinearBVHNode::n_primitives is 16 bits (pbrt-v3 CHECKs)
-            nd.offset = it.s;                                           // H7: position in the sorted order
-            nd.n_prims = (uint16_t)it.n;
-            nd.axis = 0;
-        } else {
-            const uint32_t mask = 1u << it.bit;
-            uint32_t a = 0, b = it.n - 1;                               // :627-638
-            while (a + 1 != b) {
-                const uint32_t mid = (a + b) / 2;
-                if (((codes[it.s + a] ^ codes[it.s + mid]) & mask) == 0u) a = mid; else b = mid;
-            }
-            nd.n_prims = 0;
-            nd.axis = (uint8_t)(it.bit % 3);                            // :671
-            nd.offset = 0;
-            stack[sp++] = {it.s + b, it.n - b, it.bit - 1, (int)me, it.level + 1};      // second child, visited after the first
-            stack[sp++] = {it.s, b, it.bit - 1, -1, it.level + 1};
+    TNode nd;
+    nd.s = starts[t];
+    nd.n = ((t + 1 < n_treelets) ? starts[t + 1] : n_prims) - nd.s;
+    nd.parent = 0xFFFFFFFFu; nd.child = 0u; nd.size = 0u;
+    nd.bit = (int8_t)kFirstBit; nd.second = 0; nd.level = 0; nd.leaf = 0;
+    for (int d = 0; d < 3; ++d) { nd.bmin[d] = 0.f; nd.bmax[d] = 0.f; }
+    nodes[t] = nd;
+}
+
+// counters: [0] nodes appended so far (next level grows from `next_begin`), [1] error flag
+__global__ void __launch_bounds__(256) k_lbvh_split(TNode* __restrict__ nodes, uint32_t level_begin, uint32_t level_count, uint32_t next_begin,
+                                                    const uint32_t* __restrict__ codes, int max_prims, uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ arrivals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= level_count) return;
+    const uint32_t q = level_begin + i;
+    TNode nd = nodes[q];
+    int bit = nd.bit;
+    // bits on which the whole range agrees make no node (:608-625); a short range or no bits left makes a leaf (:583)
+    while (bit >= 0 && nd.n >= (uint32_t)max_prims && ((codes[nd.s] ^ codes[nd.s + nd.n - 1]) & (1u << bit)) == 0u) --bit;
+    nd.bit = (int8_t)bit;
+    arrivals[q] = 0u;
+    if (bit < 0 || nd.n < (uint32_t)max_prims) {
+        if (nd.n > 65535u) atomicOr(&counters[1], 1u);                  // LinearBVHNode::n_primitives is 16 bits (pbrt-v3 CHECKs)
+        nd.leaf = 1;
+        nd.child = 0u;
+        nodes[q] = nd;
+        return;
+    }
+    const uint32_t mask = 1u << bit;
+    uint32_t a = 0, b = nd.n - 1;                                       // :627-638
+    while (a + 1 != b) {
+        const uint32_t mid = (a + b) / 2;
+        if (((codes[nd.s + a] ^ codes[nd.s + mid]) & mask) == 0u) a = mid; else b = mid;
+    }
+    const uint32_t c = next_begin + atomicAdd(&counters[0], 2u);
+    nd.leaf = 0;
+    nd.child = c;
+    nodes[q] = nd;
+    TNode ch;
+    ch.parent = q; ch.child = 0u; ch.size = 0u; ch.bit = (int8_t)(bit - 1); ch.level = (uint8_t)(nd.level + 1); ch.leaf = 0;
+    for (int d = 0; d < 3; ++d) { ch.bmin[d] = 0.f; ch.bmax[d] = 0.f; }
+    ch.s = nd.s; ch.n = b; ch.second = 0;
+    nodes[c] = ch;
+    ch.s = nd.s + b; ch.n = nd.n - b; ch.second = 1;
+    nodes[c + 1] = ch;
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_up(TNode* __restrict__ nodes, uint32_t n_nodes, const uint32_t* __restrict__ prim,
+                                                 const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t* __restrict__ arrivals) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_nodes || !nodes[q].leaf) return;
+    float l[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, h[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    {
+        const uint32_t s = nodes[q].s, n = nodes[q].n;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t p = prim[s + j];
+            const float4 pl = lo[p], ph = hi[p];
+            l[0] = fminf(l[0], pl.x); l[1] = fminf(l[1], pl.y); l[2] = fminf(l[2], pl.z);
+            h[0] = fmaxf(h[0], ph.x); h[1] = fmaxf(h[1], ph.y); h[2] = fmaxf(h[2], ph.z);
         }
     }
-    // boxes, children before parents (children have larger indices)
-    for (uint32_t k = count; k-- > 0;) {
-        LinearNode& nd = nodes[k];
-        float l[3], h[3];
-        if (nd.n_prims > 0) {
-            l[0] = l[1] = l[2] = 3.402823466e+38f;
-            h[0] = h[1] = h[2] = -3.402823466e+38f;
-            for (uint32_t j = 0; j < nd.n_prims; ++j) {
-                const uint32_t p = prim[nd.offset + j];
-                const float4 pl = lo[p], ph = hi[p];
-                l[0] = fminf(l[0], pl.x); l[1] = fminf(l[1], pl.y); l[2] = fminf(l[2], pl.z);
-                h[0] = fmaxf(h[0], ph.x); h[1] = fmaxf(h[1], ph.y); h[2] = fmaxf(h[2], ph.z);
-            }
-        } else {
-            const LinearNode& c0 = nodes[k + 1];
-            const LinearNode& c1 = nodes[nd.offset];
-            for (int d = 0; d < 3; ++d) { l[d] = fminf(c0.bmin[d], c1.bmin[d]); h[d] = fmaxf(c0.bmax[d], c1.bmax[d]); }
-        }
+    uint32_t size = 1u;
+    for (;;) {
+        TNode& nd = nodes[q];
         for (int d = 0; d < 3; ++d) { nd.bmin[d] = l[d]; nd.bmax[d] = h[d]; }
+        nd.size = size;
+        const uint32_t parent = nd.parent;
+        if (parent == 0xFFFFFFFFu) return;
+        __threadfence();
+        if (atomicAdd(&arrivals[parent], 1u) == 0u) return;             // the sibling's thread finishes the parent
+        __threadfence();
+        const uint32_t sib = nd.second ? q - 1u : q + 1u;
+        const volatile TNode& sb = nodes[sib];
+        for (int d = 0; d < 3; ++d) { l[d] = fminf(l[d], sb.bmin[d]); h[d] = fmaxf(h[d], sb.bmax[d]); }
+        size = size + sb.size + 1u;
+        q = parent;
     }
-    meta[t] = make_uint4(count, (uint32_t)deepest, err, 0u);
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_place(const TNode* __restrict__ nodes, uint32_t n_nodes, LinearNode* __restrict__ local,
+                                                    uint4* __restrict__ meta) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_nodes) return;
+    const TNode nd = nodes[q];
+    // depth-first position inside the treelet: one step per level, plus every first-child subtree passed on the right
+    uint32_t dfs = nd.level, up = q;
+    for (uint32_t k = nd.level; k > 0; --k) {
+        const TNode& cur = nodes[up];
+        if (cur.second) dfs += nodes[up - 1u].size;
+        up = cur.parent;
+    }
+    const uint32_t t = up;                                              // treelet roots are nodes [0, n_treelets)
+    LinearNode out;
+    for (int d = 0; d < 3; ++d) { out.bmin[d] = nd.bmin[d]; out.bmax[d] = nd.bmax[d]; }
+    out.pad = (uint8_t)(nd.level & 1u);                                 // depth parity inside the treelet
+    if (nd.leaf) {
+        out.offset = nd.s;                                              // H7: position in the sorted order
+        out.n_prims = (uint16_t)nd.n;
+        out.axis = 0;
+    } else {
+        out.offset = dfs + 1u + nodes[nd.child].size;                   // second child, local index
+        out.n_prims = 0;
+        out.axis = (uint8_t)(nd.bit % 3);                               // :671
+    }
+    local[2ull * nodes[t].s + dfs] = out;
+    atomicMax(&meta[t].y, (uint32_t)nd.level + 1u);
+    if (q == t) meta[t].x = nd.size;
 }
 
 // Treelet t's block -> final[base[t] ...]; interior second-child indices become global.
@@ -496,9 +565,34 @@ int build_hlbvh_gpu(const float* verts, uint64_t n_verts, const uint32_t* indice
     if (n_treelets == 0 || n_treelets > 4096) { snprintf(err, err_len, "HLBVH: %u treelets (expected 1..4096)", n_treelets); return -1; }
     HL_CUDA(d_local.alloc(2ull * n_tris * sizeof(LinearNode)));
     HL_CUDA(d_meta.alloc(n_treelets * sizeof(uint4)));
-    k_emit_treelets<<<(n_treelets + 63) / 64, 64>>>(d_starts.as<uint32_t>(), n_treelets, n, codes, prim, d_lo.as<float4>(), d_hi.as<float4>(),
-                                                   max_prims, d_local.as<LinearNode>(), d_meta.as<uint4>());
-    HL_CUDA(cudaGetLastError());
+    HL_CUDA(cudaMemset(d_meta.p, 0, n_treelets * sizeof(uint4)));
+    {
+        // level-synchronous emit_lbvh: at most 2 * n - 1 nodes per treelet; a level holds the children appended by the one before
+        DevBuf d_tn, d_arr, d_cnt;
+        const uint64_t cap = 2ull * n_tris + n_treelets;
+        HL_CUDA(d_tn.alloc(cap * sizeof(TNode)));
+        HL_CUDA(d_arr.alloc(cap * sizeof(uint32_t)));
+        HL_CUDA(d_cnt.alloc(2 * sizeof(uint32_t)));
+        HL_CUDA(cudaMemset(d_cnt.p, 0, 2 * sizeof(uint32_t)));
+        k_lbvh_roots<<<(n_treelets + 255) / 256, 256>>>(d_starts.as<uint32_t>(), n_treelets, n, d_tn.as<TNode>());
+        uint32_t level_begin = 0, level_count = n_treelets, total = n_treelets;
+        while (level_count > 0) {
+            k_lbvh_split<<<(level_count + 255) / 256, 256>>>(d_tn.as<TNode>(), level_begin, level_count, n_treelets, codes, max_prims,
+                                                           d_cnt.as<uint32_t>(), d_arr.as<uint32_t>());
+            uint32_t appended = 0;
+            HL_CUDA(cudaMemcpy(&appended, d_cnt.p, 4, cudaMemcpyDeviceToHost));          // nodes appended after the roots so far
+            level_begin += level_count;
+            level_count = n_treelets + appended - total;
+            total = n_treelets + appended;
+        }
+        uint32_t flag = 0;
+        HL_CUDA(cudaMemcpy(&flag, (const char*)d_cnt.p + 4, 4, cudaMemcpyDeviceToHost));
+        if (flag) { snprintf(err, err_len, "HLBVH: a leaf holds more than 65535 primitives with identical Morton codes"); return -1; }
+        k_lbvh_up<<<(total + 255) / 256, 256>>>(d_tn.as<TNode>(), total, prim, d_lo.as<float4>(), d_hi.as<float4>(), d_arr.as<uint32_t>());
+        k_lbvh_place<<<(total + 255) / 256, 256>>>(d_tn.as<TNode>(), total, d_local.as<LinearNode>(), d_meta.as<uint4>());
+        HL_CUDA(cudaGetLastError());
+        HL_CUDA(cudaDeviceSynchronize());
+    }
     std::vector<uint4> meta(n_treelets);
     HL_CUDA(cudaMemcpy(meta.data(), d_meta.p, n_treelets * sizeof(uint4), cudaMemcpyDeviceToHost));
     DevBuf d_roots;
