@@ -44,18 +44,23 @@ typedef struct pb2_hit {
     float b2;
 } pb2_hit;
 
-/* pbrt-v3 matte / plastic / glass (the reference's src/materials/{matte,plastic,glass}.rs are empty files;
- * SURVEY.md Appendix B).  */
-enum { PB2_MAT_MATTE = 0, PB2_MAT_PLASTIC = 1, PB2_MAT_GLASS = 2 };
+/* pbrt-v3 matte / plastic / glass / mirror / metal over the reference's BxDF blocks (the reference's src/materials/*.rs are
+ * empty files): LambertianReflection or OrenNayar (reflection.rs:821-855, 917-971), MicrofacetReflection +
+ * TrowbridgeReitz + FresnelDielectric / FresnelConductor (:977-1056, :571-604, :42-69), FresnelSpecular (:733-819),
+ * SpecularReflection + FresnelNoOp (:606-659). */
+enum { PB2_MAT_MATTE = 0, PB2_MAT_PLASTIC = 1, PB2_MAT_GLASS = 2, PB2_MAT_MIRROR = 3, PB2_MAT_METAL = 4 };
 typedef struct pb2_material {
     int32_t type;
     float kd[3];        /* matte, plastic: diffuse reflectance */
     float ks[3];        /* plastic: glossy reflectance */
-    float roughness;    /* plastic */
+    float roughness;    /* plastic, metal */
     int32_t remap_roughness;
-    float kr[3];        /* glass */
+    float kr[3];        /* glass, mirror */
     float kt[3];        /* glass */
     float eta;          /* glass index of refraction */
+    float sigma;        /* matte: Oren-Nayar roughness in degrees, clamped to [0, 90]; 0 = Lambertian */
+    float metal_eta[3]; /* metal: conductor index of refraction ... */
+    float metal_k[3];   /* ... and absorption coefficient, per RGB channel */
 } pb2_material;
 
 /* src/lights/point.rs PointLight; src/lights/diffuse.rs DiffuseAreaLight (one per emissive triangle);

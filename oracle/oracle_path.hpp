@@ -48,7 +48,7 @@ inline void xyz_to_rgb(const Float xyz[3], Float out[3]) {                      
 inline Float clampf(Float v, Float lo, Float hi) { return v < lo ? lo : (v > hi ? hi : v); }   // pbrt.rs:112-120
 
 // ---------------------------------------------------------------- scene description (same POD layout as the C ABI)
-enum { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_GLASS = 2 };
+enum { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_GLASS = 2, MAT_MIRROR = 3, MAT_METAL = 4 };
 struct MaterialDesc {
     int32_t type;
     Float kd[3], ks[3];
@@ -56,6 +56,8 @@ struct MaterialDesc {
     int32_t remap_roughness;
     Float kr[3], kt[3];
     Float eta;
+    Float sigma;                     // matte: Oren-Nayar roughness in degrees (reflection.rs:917-937); 0 = Lambertian
+    Float metal_eta[3], metal_k[3];  // metal: conductor index of refraction and absorption (reflection.rs:42-69)
 };
 enum { LIGHT_POINT = 0, LIGHT_AREA = 1, LIGHT_SPOT = 2, LIGHT_DISTANT = 3 };
 struct LightDesc {
@@ -237,18 +239,63 @@ struct TrowbridgeReitz {
     }
 };
 
+// fr_conductor (reflection.rs:42-69), one channel; eta_i = 1
+inline Float fr_conductor1(Float cos_theta_i, Float eta_i, Float eta_t, Float k) {
+    cos_theta_i = clampf(cos_theta_i, -1.0f, 1.0f);
+    const Float eta = eta_t / eta_i, eta_k = k / eta_i;
+    const Float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.0f - cos2;
+    const Float eta2 = eta * eta, eta_k2 = eta_k * eta_k;
+    const Float t0 = (eta2 - eta_k2) - sin2;
+    const Float a2_plus_b2 = std::sqrt(t0 * t0 + (eta2 * eta_k2) * 4.0f);
+    const Float t1 = a2_plus_b2 + cos2;
+    const Float a = std::sqrt((a2_plus_b2 + t0) * 0.5f);
+    const Float t2 = a * (2.0f * cos_theta_i);
+    const Float rs = (t1 - t2) / (t1 + t2);
+    const Float t3 = a2_plus_b2 * cos2 + sin2 * sin2;
+    const Float t4 = t2 * sin2;
+    const Float rp = (rs * (t3 - t4)) / (t3 + t4);
+    return (rp + rs) * 0.5f;
+}
+
 // ---------------------------------------------------------------- BxDFs as tagged PODs
-enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR };
+// The Rust OrenNayar (reflection.rs:917-971) does not convert sigma to radians (`signma` is unused), takes sin_phi_o from
+// sin_theta(wo) and builds d_cos from sin_theta instead of sin_phi; pbrt-v3 semantics here (D61 FIX).
+enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR, LOBE_OREN_NAYAR, LOBE_SPECULAR_REFLECTION, LOBE_MICROFACET_CONDUCTOR };
 struct Lobe {
     LobeKind kind;
     uint8_t type;       // BxDFType bits
-    RGB r, t;           // reflectance / transmittance
+    RGB r, t;           // reflectance / transmittance (conductor: t = eta)
     Float alpha;        // microfacet
-    Float eta_a, eta_b; // fresnel specular / dielectric
+    Float eta_a, eta_b; // fresnel specular / dielectric; Oren-Nayar: A, B
+    RGB k{0, 0, 0};     // conductor absorption
     bool matches(uint8_t flags) const { return (type & flags) == type; }                    // :455-457, D33 FIX
     RGB f(V3 wo, V3 wi) const {
         switch (kind) {
             case LOBE_LAMBERT: return r * (1.0f / kPi);                                     // :840-842 (r * INV_PI)
+            case LOBE_OREN_NAYAR: {                                                          // :943-971 (pbrt-v3)
+                const Float sin_theta_i = sin_theta(wi), sin_theta_o = sin_theta(wo);
+                Float max_cos = 0.0f;
+                if (sin_theta_i > 1e-4f && sin_theta_o > 1e-4f) {
+                    const Float sin_phi_i = sin_phi(wi), cos_phi_i = cos_phi(wi), sin_phi_o = sin_phi(wo), cos_phi_o = cos_phi(wo);
+                    const Float d_cos = cos_phi_i * cos_phi_o + sin_phi_i * sin_phi_o;
+                    max_cos = fmax_(0.0f, d_cos);
+                }
+                Float sin_alpha, tan_beta;
+                if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_theta_o; tan_beta = sin_theta_i / abs_cos_theta(wi); }
+                else { sin_alpha = sin_theta_i; tan_beta = sin_theta_o / abs_cos_theta(wo); }
+                return r * (1.0f / kPi) * (eta_a + ((eta_b * max_cos) * sin_alpha) * tan_beta);
+            }
+            case LOBE_MICROFACET_CONDUCTOR: {                                                // :998-1017 with FresnelConductor (:583-587)
+                Float co = abs_cos_theta(wo), ci = abs_cos_theta(wi);
+                V3 wh = wi + wo;
+                if (ci == 0.0f || co == 0.0f) return rgb(0);
+                if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return rgb(0);
+                wh = normalize(wh);
+                TrowbridgeReitz tr{alpha, alpha};
+                const Float c = std::fabs(dot(wi, faceforward(wh, V3{0, 0, 1})));
+                const RGB fr{fr_conductor1(c, 1.0f, t.r, k.r), fr_conductor1(c, 1.0f, t.g, k.g), fr_conductor1(c, 1.0f, t.b, k.b)};
+                return r * tr.d(wh) * tr.g(wo, wi) * fr / (4.0f * ci * co);
+            }
             case LOBE_MICROFACET: {                                                          // :998-1017
                 Float co = abs_cos_theta(wo), ci = abs_cos_theta(wi);
                 V3 wh = wi + wo;
@@ -264,7 +311,9 @@ struct Lobe {
     }
     Float pdf(V3 wo, V3 wi) const {
         switch (kind) {
-            case LOBE_LAMBERT: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * (1.0f / kPi) : 0.0f;   // :501-507
+            case LOBE_LAMBERT:
+            case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * (1.0f / kPi) : 0.0f;   // :501-507
+            case LOBE_MICROFACET_CONDUCTOR:
             case LOBE_MICROFACET: {                                                          // :1042-1048
                 if (!same_hemisphere(wo, wi)) return 0.0f;
                 V3 wh = normalize(wo + wi);
@@ -276,12 +325,19 @@ struct Lobe {
     }
     RGB sample_f(V3 wo, V3* wi, Float u0, Float u1, Float* pdf_out, uint8_t* sampled_type) const {
         switch (kind) {
-            case LOBE_LAMBERT: {                                                             // :459-472 BxDF default
+            case LOBE_SPECULAR_REFLECTION: {                                                 // :640-651, FresnelNoOp (:606-611)
+                *wi = V3{-wo.x, -wo.y, wo.z};
+                *pdf_out = 1.0f;
+                return r * rgb(1.0f) / abs_cos_theta(*wi);
+            }
+            case LOBE_LAMBERT:
+            case LOBE_OREN_NAYAR: {                                                          // :459-472 BxDF default
                 *wi = cosine_sample_hemisphere(u0, u1);
                 if (wo.z < 0.0f) wi->z *= -1.0f;
                 *pdf_out = pdf(wo, *wi);
                 return f(wo, *wi);
             }
+            case LOBE_MICROFACET_CONDUCTOR:
             case LOBE_MICROFACET: {                                                          // :1019-1040, D36 FIX
                 if (wo.z == 0.0f) return rgb(0);
                 TrowbridgeReitz tr{alpha, alpha};
@@ -410,7 +466,8 @@ struct LightRt {
 
 struct MaterialRt {
     MaterialDesc d;
-    Float alpha;        // plastic: roughness (remapped) — host-side, microfacet.rs:160-168
+    Float alpha;        // plastic, metal: roughness (remapped) — host-side, microfacet.rs:160-168
+    Float on_a, on_b;   // matte with sigma: OrenNayar::new's A and B (reflection.rs:925-937, sigma in radians: D61 FIX)
 };
 
 class Scene {
@@ -447,6 +504,11 @@ public:
         for (uint32_t i = 0; i < n_mats; ++i) {
             materials[i].d = mats[i];
             materials[i].alpha = mats[i].remap_roughness ? roughness_to_alpha(mats[i].roughness) : mats[i].roughness;
+            {
+                const Float sig = kPi / 180.0f * clampf(mats[i].sigma, 0.0f, 90.0f), sigma2 = sig * sig;     // MatteMaterial clamps to [0, 90]
+                materials[i].on_a = 1.0f - (sigma2 / (2.0f * (sigma2 + 0.33f)));
+                materials[i].on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
+            }
         }
         tri_light.assign(nt, -1);
         lights.resize(n_lights);
@@ -545,7 +607,15 @@ public:
         b.ts = cross(b.ns, b.ss);
         RGB kd{m.d.kd[0], m.d.kd[1], m.d.kd[2]}, ks{m.d.ks[0], m.d.ks[1], m.d.ks[2]};
         RGB kr{m.d.kr[0], m.d.kr[1], m.d.kr[2]}, kt{m.d.kt[0], m.d.kt[1], m.d.kt[2]};
-        if (m.d.type == MAT_MATTE || m.d.type == MAT_PLASTIC) {
+        if (m.d.type == MAT_MIRROR) {                                                           // pbrt-v3 MirrorMaterial
+            if (!is_black(kr)) b.lobes[b.n++] = Lobe{LOBE_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, kr, rgb(0), 0, 1, 1};
+        } else if (m.d.type == MAT_METAL) {                                                     // pbrt-v3 MetalMaterial (isotropic)
+            Lobe l{LOBE_MICROFACET_CONDUCTOR, BSDF_REFLECTION | BSDF_GLOSSY, rgb(1.0f), RGB{m.d.metal_eta[0], m.d.metal_eta[1], m.d.metal_eta[2]}, m.alpha, 1, 1};
+            l.k = RGB{m.d.metal_k[0], m.d.metal_k[1], m.d.metal_k[2]};
+            b.lobes[b.n++] = l;
+        } else if (m.d.type == MAT_MATTE && m.d.sigma != 0.0f) {                                // pbrt-v3 MatteMaterial, sigma != 0
+            if (!is_black(kd)) b.lobes[b.n++] = Lobe{LOBE_OREN_NAYAR, BSDF_REFLECTION | BSDF_DIFFUSE, kd, rgb(0), 0, m.on_a, m.on_b};
+        } else if (m.d.type == MAT_MATTE || m.d.type == MAT_PLASTIC) {
             if (!is_black(kd)) b.lobes[b.n++] = Lobe{LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, kd, rgb(0), 0, 1, 1};
             if (m.d.type == MAT_PLASTIC && !is_black(ks))
                 b.lobes[b.n++] = Lobe{LOBE_MICROFACET, BSDF_REFLECTION | BSDF_GLOSSY, ks, rgb(0), m.alpha, 1.5f, 1.0f};

@@ -12,7 +12,8 @@ from . import oracle as O
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("roughness", C.c_float),
-                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float)]
+                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
+                ("sigma", C.c_float), ("metal_eta", C.c_float * 3), ("metal_k", C.c_float * 3)]
 
 
 class Light(C.Structure):
@@ -38,7 +39,7 @@ class PathDesc(C.Structure):
 
 
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
-_MAT = {"matte": 0, "plastic": 1, "glass": 2}
+_MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4}
 _STRAT = {"uniform": 0, "power": 1}
 _FILTER = {"box": 0, "gaussian": 1, "triangle": 2, "mitchell": 3, "sinc": 4}
 
@@ -53,6 +54,11 @@ def material(d):
     m.kr[:] = d.get("kr", (0, 0, 0))
     m.kt[:] = d.get("kt", (0, 0, 0))
     m.eta = d.get("eta", 1.5)
+    m.sigma = d.get("sigma", 0.0)
+    m.metal_eta[:] = d.get("metal_eta", (0.2, 0.92, 1.1))       # copper-ish defaults (pbrt's metal.cpp tabulates Cu)
+    m.metal_k[:] = d.get("metal_k", (3.9, 2.45, 2.14))
+    if d["type"] == "metal":
+        m.roughness = d.get("roughness", 0.01)
     return m
 
 

@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("prim_id", np.uint32), ("t", np.float32), ("b1", np.float
 NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_prims", np.uint16), ("axis", np.uint8),
                        ("pad", np.uint8)])
 
-MAT_MATTE, MAT_PLASTIC, MAT_GLASS = 0, 1, 2
+MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_MIRROR, MAT_METAL = 0, 1, 2, 3, 4
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN, FILTER_TRIANGLE, FILTER_MITCHELL, FILTER_SINC = 0, 1, 2, 3, 4
 LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
@@ -33,7 +33,8 @@ class Pb2Error(RuntimeError):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("roughness", C.c_float),
-                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float)]
+                ("remap_roughness", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
+                ("sigma", C.c_float), ("metal_eta", C.c_float * 3), ("metal_k", C.c_float * 3)]
 
 
 class Light(C.Structure):
@@ -61,10 +62,31 @@ class PathDesc(C.Structure):
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
 
 
-def matte(kd):
+def matte(kd, sigma=0.0):
+    """pbrt-v3 MatteMaterial: LambertianReflection, or OrenNayar (reflection.rs:917-971) when sigma (degrees) != 0."""
     m = Material()
     m.type = MAT_MATTE
     m.kd[:] = kd
+    m.sigma = sigma
+    return m
+
+
+def mirror(kr=(0.9, 0.9, 0.9)):
+    """pbrt-v3 MirrorMaterial: SpecularReflection(Kr, FresnelNoOp) (reflection.rs:606-659)."""
+    m = Material()
+    m.type = MAT_MIRROR
+    m.kr[:] = kr
+    return m
+
+
+def metal(eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), roughness=0.01, remap=True):
+    """pbrt-v3 MetalMaterial (isotropic): MicrofacetReflection(1, TrowbridgeReitz, FresnelConductor(1, eta, k))."""
+    m = Material()
+    m.type = MAT_METAL
+    m.metal_eta[:] = eta
+    m.metal_k[:] = k
+    m.roughness = roughness
+    m.remap_roughness = int(remap)
     return m
 
 
@@ -362,14 +384,18 @@ class PerspectiveCamera:
         check(lib().pb2_camera_primary_rays_device(C.byref(self.desc), d_rays, stream))
 
 
-_MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS}
+_MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS, "mirror": MAT_MIRROR, "metal": MAT_METAL}
 _STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER}
 _FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN, "triangle": FILTER_TRIANGLE, "mitchell": FILTER_MITCHELL, "sinc": FILTER_SINC}
 
 
 def material_from_dict(d):
     if d["type"] == "matte":
-        return matte(d["kd"])
+        return matte(d["kd"], d.get("sigma", 0.0))
+    if d["type"] == "mirror":
+        return mirror(d.get("kr", (0.9, 0.9, 0.9)))
+    if d["type"] == "metal":
+        return metal(d.get("metal_eta", (0.2, 0.92, 1.1)), d.get("metal_k", (3.9, 2.45, 2.14)), d.get("roughness", 0.01), d.get("remap", True))
     if d["type"] == "plastic":
         return plastic(d["kd"], d["ks"], d.get("roughness", 0.1), d.get("remap", True))
     return glass(d.get("kr", (1, 1, 1)), d.get("kt", (1, 1, 1)), d.get("eta", 1.5))

@@ -74,12 +74,21 @@ int upload_shading_tables(pb2_scene* scene) {
     std::vector<DMaterial> mats(scene->materials.size());
     for (size_t i = 0; i < mats.size(); ++i) {
         const pb2_material& m = scene->materials[i];
-        if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_GLASS) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
+        if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_METAL) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
         DMaterial& d = mats[i];
         d.type = m.type;
-        for (int k = 0; k < 3; ++k) { d.kd[k] = m.kd[k]; d.ks[k] = m.ks[k]; d.kr[k] = m.kr[k]; d.kt[k] = m.kt[k]; }
+        for (int k = 0; k < 3; ++k) { d.kd[k] = m.kd[k]; d.ks[k] = m.ks[k]; d.kr[k] = m.kr[k]; d.kt[k] = m.kt[k]; d.metal_eta[k] = m.metal_eta[k]; d.metal_k[k] = m.metal_k[k]; }
         d.alpha = m.remap_roughness ? roughness_to_alpha(m.roughness) : m.roughness;
         d.eta = m.eta;
+        {
+            // OrenNayar::new (reflection.rs:925-937; sigma in radians: D61 FIX); MatteMaterial clamps sigma to [0, 90] degrees
+            const float sd = m.sigma < 0.0f ? 0.0f : (m.sigma > 90.0f ? 90.0f : m.sigma);
+            const float sig = PB2_PI / 180.0f * sd, sigma2 = sig * sig;
+            d.on_a = 1.0f - (sigma2 / (2.0f * (sigma2 + 0.33f)));
+            d.on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
+        }
+        // shading class (shade.cuh: make_bsdf<CLS>)
+        d.cls = (m.type == PB2_MAT_MATTE && m.sigma == 0.0f) ? 0 : ((m.type == PB2_MAT_GLASS || m.type == PB2_MAT_MIRROR) ? 2 : 1);
     }
     const size_t n_lights = scene->lights.size();
     std::vector<DLight> lights(std::max<size_t>(1, n_lights));

@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cfloat>
 #include <cstring>
 #include <thread>
@@ -376,9 +379,14 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
         work();
         for (auto& t : pool) t.join();
     }
+    const bool timing = getenv("PB2_BUILD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     Builder b(refs, max_prims, threads, split_method);
     b.run(out);
+    const double t1 = now();
     repack_device_layout(verts, indices, n_tris, out);
+    if (timing) fprintf(stderr, "[pb2] host build: tree %.3f s, device-layout repack %.3f s (%d threads)\n", t1 - t0, now() - t1, threads);
 }
 
 // Runs fn(begin, end) over [0, n) on the host's hardware threads.

@@ -174,9 +174,13 @@ PB2_HD vec3 tr_sample_wh(float a, vec3 wo, float u0, float u1) {
 // ---- materials as device PODs -------------------------------------------------------------------------------------
 struct DMaterial {
     int type;               // PB2_MAT_*
+    int cls;                // shading class = material queue / k_shade instantiation: 0 Lambertian matte, 1 general
+                            // (plastic, metal, Oren-Nayar matte), 2 specular (glass, mirror)
     float kd[3], ks[3], kr[3], kt[3];
-    float alpha;            // plastic: Trowbridge-Reitz alpha (roughness_to_alpha applied on the host when remapping)
+    float alpha;            // plastic, metal: Trowbridge-Reitz alpha (roughness_to_alpha applied on the host when remapping)
     float eta;              // glass
+    float on_a, on_b;       // matte with sigma: OrenNayar::new's A and B (reflection.rs:925-937)
+    float metal_eta[3], metal_k[3];
 };
 
 struct DLight {
@@ -195,31 +199,67 @@ struct DLight {
     float uv[6];            // its UVs (Shape::pdf2 -> Triangle::intersect frame check)
 };
 
-enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u };
+enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u };
 struct Lobe {
     unsigned kind, type;
-    rgb3 r, t;
-    float alpha, eta_a, eta_b;
+    rgb3 r, t;              // conductor: t = eta
+    float alpha, eta_a, eta_b;   // Oren-Nayar: eta_a, eta_b = A, B
+    rgb3 k;                 // conductor absorption
 };
+
+// fr_conductor (reflection.rs:42-69), one channel
+PB2_HD float fresnel_conductor1(float ci, float eta_i, float eta_t, float k) {
+    ci = clamp01s(ci, -1.0f, 1.0f);
+    const float eta = eta_t / eta_i, eta_k = k / eta_i;
+    const float cos2 = ci * ci, sin2 = 1.0f - cos2;
+    const float eta2 = eta * eta, eta_k2 = eta_k * eta_k;
+    const float t0 = (eta2 - eta_k2) - sin2;
+    const float a2_plus_b2 = sqrtf(t0 * t0 + (eta2 * eta_k2) * 4.0f);
+    const float t1 = a2_plus_b2 + cos2;
+    const float a = sqrtf((a2_plus_b2 + t0) * 0.5f);
+    const float t2 = a * (2.0f * ci);
+    const float rs = (t1 - t2) / (t1 + t2);
+    const float t3 = a2_plus_b2 * cos2 + sin2 * sin2;
+    const float t4 = t2 * sin2;
+    const float rp = (rs * (t3 - t4)) / (t3 + t4);
+    return (rp + rs) * 0.5f;
+}
 
 PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags) == l.type; }       // D33 FIX
 
 PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
     if (l.kind == kLambert) return l.r * (1.0f / PB2_PI);
-    if (l.kind == kMicrofacet) {
+    if (l.kind == kOrenNayar) {                                  // reflection.rs:943-971 (pbrt-v3 semantics, D61)
+        const float sti = sin_t(wi), sto = sin_t(wo);
+        float max_cos = 0.0f;
+        if (sti > 1e-4f && sto > 1e-4f) {
+            const float d_cos = cos_p(wi) * cos_p(wo) + sin_p(wi) * sin_p(wo);
+            max_cos = fmaxf(0.0f, d_cos);
+        }
+        float sin_alpha, tan_beta;
+        if (abs_cos_t(wi) > abs_cos_t(wo)) { sin_alpha = sto; tan_beta = sti / abs_cos_t(wi); }
+        else { sin_alpha = sti; tan_beta = sto / abs_cos_t(wo); }
+        return l.r * (1.0f / PB2_PI) * (l.eta_a + ((l.eta_b * max_cos) * sin_alpha) * tan_beta);
+    }
+    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
         const float co = abs_cos_t(wo), ci = abs_cos_t(wi);
         vec3 wh = wi + wo;
         if (ci == 0.0f || co == 0.0f) return gray(0.0f);
         if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return gray(0.0f);
         wh = unit(wh);
-        const float fr = fresnel_dielectric(dot3(wi, face_toward(wh, mk(0.0f, 0.0f, 1.0f))), l.eta_a, l.eta_b);   // D6 FIX
-        return l.r * tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi) * gray(fr) / (4.0f * ci * co);
+        const float c = dot3(wi, face_toward(wh, mk(0.0f, 0.0f, 1.0f)));                                            // D6 FIX
+        rgb3 fr;
+        if (l.kind == kMicrofacetConductor) {                    // FresnelConductor::evaluate(|cos|), reflection.rs:583-587
+            const float ac = fabsf(c);
+            fr = mkc(fresnel_conductor1(ac, 1.0f, l.t.r, l.k.r), fresnel_conductor1(ac, 1.0f, l.t.g, l.k.g), fresnel_conductor1(ac, 1.0f, l.t.b, l.k.b));
+        } else fr = gray(fresnel_dielectric(c, l.eta_a, l.eta_b));
+        return l.r * tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi) * fr / (4.0f * ci * co);
     }
     return gray(0.0f);
 }
 PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
-    if (l.kind == kLambert) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
-    if (l.kind == kMicrofacet) {
+    if (l.kind == kLambert || l.kind == kOrenNayar) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
+    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
         if (!same_side(wo, wi)) return 0.0f;
         const vec3 wh = unit(wo + wi);
         return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
@@ -227,13 +267,18 @@ PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
     return 0.0f;
 }
 PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, float* pdf, unsigned* sampled) {
-    if (l.kind == kLambert) {
+    if (l.kind == kSpecularReflection) {                         // reflection.rs:640-651 with FresnelNoOp (:606-611)
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *pdf = 1.0f;
+        return l.r * gray(1.0f) / abs_cos_t(*wi);
+    }
+    if (l.kind == kLambert || l.kind == kOrenNayar) {
         *wi = cosine_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi->z = wi->z * -1.0f;
         *pdf = lobe_pdf(l, wo, *wi);
         return lobe_f(l, wo, *wi);
     }
-    if (l.kind == kMicrofacet) {
+    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
         if (wo.z == 0.0f) return gray(0.0f);
         const vec3 wh = tr_sample_wh(l.alpha, wo, u0, u1);
         if (dot3(wo, wh) < 0.0f) return gray(0.0f);
@@ -352,14 +397,15 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, f
     return fv;
 }
 
-// Material::compute_scattering_functions for matte / plastic / glass (pbrt-v3; Appendix B).  MAT is the material type of
-// `m` known at compile time (the wavefront shades one material type per launch, so the lobe kinds fold to constants and
-// the code of the other materials drops out of that launch's kernel); MAT < 0 reads m.type at run time.
-// ng = si.n, ns = si.shading.n, sdpdu = si.shading.dpdu (the geometric values without mesh normals / tangents, D59).
-template <int MAT = -1>
-PB2_HD BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
-    BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> b;
-    const int type = MAT < 0 ? m.type : MAT;
+// Material::compute_scattering_functions (pbrt-v3 materials over the reference's BxDF blocks): matte
+// (Lambertian, or Oren-Nayar when sigma != 0), plastic, glass, mirror, metal.  CLS is the shading class of `m` (DMaterial::cls)
+// known at compile time — the wavefront shades one class per launch: 0 = Lambertian matte (one lobe whose kind is a
+// compile-time constant: the kernel that carries C2 / C4), 1 = general (plastic, metal, Oren-Nayar matte; up to two lobes),
+// 2 = specular (glass, mirror; one lobe); CLS < 0 reads everything at run time.
+template <int CLS = -1>
+PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
+    BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> b;
+    const int type = CLS == 0 ? 0 : m.type;
     b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = ns;
     b.ng = ng;
@@ -368,18 +414,30 @@ PB2_HD BsdfT<(MAT == 0 || MAT == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 
     b.n = 0;
     const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);
     const rgb3 kr = mkc(m.kr[0], m.kr[1], m.kr[2]), kt = mkc(m.kt[0], m.kt[1], m.kt[2]);
+    const rgb3 zero = gray(0.0f);
     if (type == 0 || type == 1) {
         if (!black(kd)) {
             Lobe& l = b.lobes[b.n++];
-            l.kind = kLambert; l.type = kReflection | kDiffuse; l.r = kd; l.t = gray(0.0f); l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f;
+            const bool oren_nayar = CLS != 0 && type == 0;     // class 0 is Lambertian by construction
+            l.kind = oren_nayar ? kOrenNayar : kLambert; l.type = kReflection | kDiffuse; l.r = kd; l.t = zero; l.alpha = 0.0f;
+            l.eta_a = oren_nayar ? m.on_a : 1.0f; l.eta_b = oren_nayar ? m.on_b : 1.0f; l.k = zero;
         }
         if (type == 1 && !black(ks)) {
             Lobe& l = b.lobes[b.n++];
-            l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = gray(0.0f); l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f;
+            l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = zero; l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f; l.k = zero;
+        }
+    } else if (type == 4) {                                    // MetalMaterial: MicrofacetReflection(1, TrowbridgeReitz, FresnelConductor(1, eta, k))
+        Lobe& l = b.lobes[b.n++];
+        l.kind = kMicrofacetConductor; l.type = kReflection | kGlossy; l.r = gray(1.0f); l.t = mkc(m.metal_eta[0], m.metal_eta[1], m.metal_eta[2]);
+        l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = 1.0f; l.k = mkc(m.metal_k[0], m.metal_k[1], m.metal_k[2]);
+    } else if (type == 3) {                                    // MirrorMaterial: SpecularReflection(Kr, FresnelNoOp)
+        if (!black(kr)) {
+            Lobe& l = b.lobes[b.n++];
+            l.kind = kSpecularReflection; l.type = kReflection | kSpecular; l.r = kr; l.t = zero; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f; l.k = zero;
         }
     } else if (!(black(kr) && black(kt))) {
         Lobe& l = b.lobes[b.n++];
-        l.kind = kFresnelSpecular; l.type = kReflection | kTransmission | kSpecular; l.r = kr; l.t = kt; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = m.eta;
+        l.kind = kFresnelSpecular; l.type = kReflection | kTransmission | kSpecular; l.r = kr; l.t = kt; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = m.eta; l.k = zero;
     }
     return b;
 }

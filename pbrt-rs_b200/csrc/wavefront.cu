@@ -351,7 +351,7 @@ struct ExtendSink {
         if (!found) return;                              // escaped: no infinite lights in scope, the path is finished
         const uint32_t slot = queue[i];
         const uint32_t prim = b.hit[slot].x;             // written by this thread's last accept()
-        const int type = sh.mats[sh.tri_material[prim]].type;
+        const int type = sh.mats[sh.tri_material[prim]].cls;      // shading class: the queue of the k_shade instantiation that handles it
         // (selects, not b.q_mat[type]: a run-time index would move the whole parameter struct into local memory)
         queue_push(&b.counters[C_MAT0 + type], type == 0 ? b.q_mat[0] : (type == 1 ? b.q_mat[1] : b.q_mat[2]), slot);
     }

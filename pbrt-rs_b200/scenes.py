@@ -245,6 +245,26 @@ def scene_c4_smooth(n_theta=24, n_phi=48, uvs=True, tangents=False, emissive_nor
     return sc
 
 
+def scene_materials(n_theta=32, n_phi=64):
+    """C4's room with every material the backend knows: Oren-Nayar matte (sigma = 35), metal (copper-like conductor), mirror on
+    the three big spheres, glass and plastic on two small ones in front, Lambertian walls."""
+    sc = scene_c4(n_theta=n_theta, n_phi=n_phi)
+    meshes = [(sc["verts"], sc["idx"])]
+    tm = list(sc["tri_material"])
+    for (cx, cz), mat in (((200.0, 120.0), 6), ((350.0, 120.0), 7)):
+        v, i = uv_sphere(radius=45.0, center=(cx, 45.0, cz), n_theta=max(8, n_theta // 2), n_phi=max(16, n_phi // 2))
+        meshes.append((v, i))
+        tm.extend([mat] * len(i))
+    verts, idx = merge(*meshes)
+    mats = list(sc["materials"])
+    mats[3] = dict(type="matte", kd=(0.6, 0.6, 0.7), sigma=35.0)
+    mats[4] = dict(type="metal", metal_eta=(0.2, 0.92, 1.1), metal_k=(3.9, 2.45, 2.14), roughness=0.05, remap=True)
+    mats[5] = dict(type="mirror", kr=(0.9, 0.9, 0.9))
+    mats += [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5),
+             dict(type="plastic", kd=(0.25, 0.35, 0.25), ks=(0.3, 0.3, 0.3), roughness=0.1, remap=True)]
+    return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=mats, lights=sc["lights"])
+
+
 def scene_all_lights(n_theta=24, n_phi=48):
     """C4's room with every light the backend knows: the ceiling area light, a point light, a spot light aimed at the matte
     sphere (src/lights/spot.rs; axis = normalize(to - from), 30 degree cone, falloff from 20 degrees) and a distant light

@@ -11,7 +11,8 @@ pub struct pb2_ray { pub o: [f32; 3], pub t_max: f32, pub d: [f32; 3], pub time:
 pub struct pb2_hit { pub prim_id: u32, pub t: f32, pub b1: f32, pub b2: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_material { pub ty: i32, pub kd: [f32; 3], pub ks: [f32; 3], pub roughness: f32, pub remap_roughness: i32,
-                          pub kr: [f32; 3], pub kt: [f32; 3], pub eta: f32 }
+                          pub kr: [f32; 3], pub kt: [f32; 3], pub eta: f32,
+                          pub sigma: f32 /* matte: Oren-Nayar, degrees */, pub metal_eta: [f32; 3], pub metal_k: [f32; 3] }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_light { pub ty: i32 /* 0 point, 1 area, 2 spot, 3 distant */, pub p: [f32; 3], pub i: [f32; 3], pub prim_id: u32, pub two_sided: i32,
                        pub axis: [f32; 3] /* spot: row 2 of world_to_light; distant: w */, pub total_width: f32, pub falloff_start: f32 }

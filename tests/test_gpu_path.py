@@ -461,3 +461,33 @@ def test_thin_lens_camera_bit_exact(gpu, OP, orc, scenes, sampler):
     assert np.array_equal(bits(film.read_xyzw()), bits(want))
     with pytest.raises(gpu.Pb2Error):
         gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"], lens_radius=1.0, focal_distance=0.0).generate_rays(pf)
+
+
+def test_all_materials_bit_exact(gpu, OP, scenes):
+    """Matte (Lambertian and Oren-Nayar), plastic, glass, mirror and metal in one scene — three shading classes, so three material
+    queues and k_shade instantiations, two of which pick the lobe kind at run time: per-sample radiance and the film equal the
+    oracle's bits; the mirror and the metal sphere do reflect (their pixels differ from a matte version of the scene)."""
+    sc = scenes.scene_materials(32, 64)
+    cam = dict(scenes.C4_CAMERA, res=(320, 180))
+    kw = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", spp=16)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    rng = np.random.default_rng(41)
+    n = 40000
+    xy = np.stack([rng.integers(0, 320, n), rng.integers(30, 180, n)], axis=1)
+    s = rng.integers(0, 16, size=n)
+    L, pf = integ.li(xy, s)
+    rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), xy, s)
+    assert np.array_equal(bits(pf), bits(rpf))
+    mism = (bits(L) != bits(rL)).any(axis=1)
+    assert mism.sum() == 0, f"{mism.sum()} of {n} samples differ; first {L[mism][:2]} vs {rL[mism][:2]}"
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), mode=1)
+    assert np.array_equal(bits(film.read_xyzw()), bits(want))
+    dull = dict(sc, materials=[dict(type="matte", kd=(0.5, 0.5, 0.5))] * len(sc["materials"]))
+    L2, _ = gpu.PathIntegrator(gpu.BVHAccel(gpu.scene_from_dict(dull), 4), camera, **kw).li(xy, s)
+    assert (bits(L2) != bits(L)).any(axis=1).mean() > 0.2
+    bad = gpu.Material()
+    bad.type = 9
+    with pytest.raises(gpu.Pb2Error):                       # unknown material type is refused at build time
+        gpu.BVHAccel(gpu.Scene(sc["verts"], sc["idx"], sc["tri_material"], [bad] * len(sc["materials"]), []), 4)

@@ -244,3 +244,47 @@ def test_mesh_shading_normals_uvs_tangents(OP, scenes):
     assert not np.array_equal(a, bimg) and abs(a.mean() - bimg.mean()) / a.mean() < 0.03
     cimg = OP.resolve_rgb(OP.Scene(full).render(cam4, fd4, pd4)[0])
     assert not np.isnan(cimg).any() and cimg.mean() > 0.01
+
+
+def test_mirror_metal_and_oren_nayar(OP, scenes):
+    """pbrt-v3 mirror / metal / matte-with-sigma over the reference's BxDF blocks (SpecularReflection + FresnelNoOp, MicrofacetReflection +
+    FresnelConductor, OrenNayar): a mirror shows the light at Kr x L_e; a smooth conductor at normal incidence at
+    F0 = ((eta-1)^2 + k^2) / ((eta+1)^2 + k^2) x L_e; Oren-Nayar with sigma = 0 renders exactly like the Lambertian, with sigma > 0 it
+    flattens a sphere lit from the camera (limb brighter relative to the centre)."""
+    # a reflector quad at z = 0 facing -z, an emitter quad at z = -10 facing +z, the camera just in front of the emitter looking at the reflector
+    refl = np.array([(-4, -4, 0), (4, -4, 0), (4, 4, 0), (-4, 4, 0)], np.float32)
+    emit = np.array([(-3, -3, -10), (-3, 3, -10), (3, 3, -10), (3, -3, -10)], np.float32)
+    verts = np.concatenate([refl, emit])
+    idx = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.uint32)
+    lights = [dict(type="area", prim=2, L=(2.0, 3.0, 4.0), two_sided=True), dict(type="area", prim=3, L=(2.0, 3.0, 4.0), two_sided=True)]
+    cam = dict(pos=(0.3, 0.2, -9.0), look=(0.0, 0.0, 0.0), up=(0, 1, 0), fov=10.0, res=(8, 8))
+    fd = OP.film_desc(cam["res"])
+
+    def centre(mat, **pk):
+        sc = OP.Scene(dict(verts=verts, idx=idx, tri_material=np.array([1, 1, 0, 0], np.uint32), materials=[dict(type="matte", kd=(0, 0, 0)), mat], lights=lights))
+        img = OP.resolve_rgb(sc.render(cam, fd, OP.path_desc(max_depth=2, spp=pk.get("spp", 4)))[0])
+        return img[3:5, 3:5].mean(axis=(0, 1))
+
+    got = centre(dict(type="mirror", kr=(0.9, 0.8, 0.7)))
+    assert np.allclose(got, np.array((2.0, 3.0, 4.0)) * (0.9, 0.8, 0.7), rtol=1e-5)
+    eta, k = np.array((0.2, 0.92, 1.1)), np.array((3.9, 2.45, 2.14))
+    f0 = ((eta - 1) ** 2 + k ** 2) / ((eta + 1) ** 2 + k ** 2)
+    got = centre(dict(type="metal", metal_eta=tuple(eta), metal_k=tuple(k), roughness=0.002, remap=False), spp=4096)
+    assert np.allclose(got, np.array((2.0, 3.0, 4.0)) * f0, rtol=0.05), (got, np.array((2.0, 3.0, 4.0)) * f0)
+    # Oren-Nayar
+    v, i = scenes.uv_sphere(radius=1.0, n_theta=48, n_phi=96)
+    base = dict(verts=v, idx=i, tri_material=np.zeros(len(i), np.uint32), lights=[dict(type="distant", w=(0.0, 0.0, -1.0), L=(3.0, 3.0, 3.0))],
+                normals=v.copy())
+    cam = dict(pos=(0, 0, -6.0), look=(0, 0, 0), up=(0, 1, 0), fov=22.0, res=(64, 64))
+    fd = OP.film_desc(cam["res"])
+    pd = OP.path_desc(max_depth=1, spp=8)
+    lam = OP.resolve_rgb(OP.Scene(dict(base, materials=[dict(type="matte", kd=(0.8, 0.8, 0.8))])).render(cam, fd, pd)[0])[..., 0]
+    on = OP.resolve_rgb(OP.Scene(dict(base, materials=[dict(type="matte", kd=(0.8, 0.8, 0.8), sigma=40.0)])).render(cam, fd, pd)[0])[..., 0]
+    assert np.array_equal(lam, OP.resolve_rgb(OP.Scene(dict(base, materials=[dict(type="matte", kd=(0.8, 0.8, 0.8), sigma=0.0)])).render(cam, fd, pd)[0])[..., 0])
+    centre_ratio = on[30:34, 30:34].mean() / lam[30:34, 30:34].mean()
+    limb_ratio = on[32, 8:12].mean() / lam[32, 8:12].mean()
+    assert centre_ratio < 0.95 and limb_ratio > 1.15 * centre_ratio, (centre_ratio, limb_ratio)
+    # everything together: finite, plausible
+    img = OP.resolve_rgb(OP.Scene(scenes.scene_materials(12, 24)).render(dict(scenes.C4_CAMERA, res=(48, 27)), OP.film_desc((48, 27)),
+                                                                       OP.path_desc(max_depth=6, spp=16, light_strategy="power"))[0])
+    assert not np.isnan(img).any() and 0.01 < img.mean() < 2.0
