@@ -227,9 +227,17 @@ PB2_HD float fresnel_conductor1(float ci, float eta_i, float eta_t, float k) {
 
 PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags) == l.type; }       // D33 FIX
 
+// Lobe kinds a shading class can hold (make_bsdf<CLS>): the branches of the other kinds drop out of that class's kernel.
+template <int CLS>
+PB2_HD constexpr bool may_be(unsigned kind) {
+    return CLS < 0 || (CLS == 0 && kind == kLambert) ||
+           (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor)) ||
+           (CLS == 2 && (kind == kFresnelSpecular || kind == kSpecularReflection));
+}
+template <int CLS>
 PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
-    if (l.kind == kLambert) return l.r * (1.0f / PB2_PI);
-    if (l.kind == kOrenNayar) {                                  // reflection.rs:943-971 (pbrt-v3 semantics, D61)
+    if (may_be<CLS>(kLambert) && l.kind == kLambert) return l.r * (1.0f / PB2_PI);
+    if (may_be<CLS>(kOrenNayar) && l.kind == kOrenNayar) {                                  // reflection.rs:943-971 (pbrt-v3 semantics, D61)
         const float sti = sin_t(wi), sto = sin_t(wo);
         float max_cos = 0.0f;
         if (sti > 1e-4f && sto > 1e-4f) {
@@ -241,7 +249,7 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
         else { sin_alpha = sti; tan_beta = sto / abs_cos_t(wo); }
         return l.r * (1.0f / PB2_PI) * (l.eta_a + ((l.eta_b * max_cos) * sin_alpha) * tan_beta);
     }
-    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
         const float co = abs_cos_t(wo), ci = abs_cos_t(wi);
         vec3 wh = wi + wo;
         if (ci == 0.0f || co == 0.0f) return gray(0.0f);
@@ -257,36 +265,39 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
     }
     return gray(0.0f);
 }
+template <int CLS>
 PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
-    if (l.kind == kLambert || l.kind == kOrenNayar) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
-    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
+    if (may_be<CLS>(kLambert) && (l.kind == kLambert || l.kind == kOrenNayar)) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
         if (!same_side(wo, wi)) return 0.0f;
         const vec3 wh = unit(wo + wi);
         return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
     }
     return 0.0f;
 }
+template <int CLS>
 PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, float* pdf, unsigned* sampled) {
-    if (l.kind == kSpecularReflection) {                         // reflection.rs:640-651 with FresnelNoOp (:606-611)
+    if (may_be<CLS>(kSpecularReflection) && l.kind == kSpecularReflection) {   // reflection.rs:640-651 with FresnelNoOp (:606-611)
         *wi = mk(-wo.x, -wo.y, wo.z);
         *pdf = 1.0f;
         return l.r * gray(1.0f) / abs_cos_t(*wi);
     }
-    if (l.kind == kLambert || l.kind == kOrenNayar) {
+    if (may_be<CLS>(kLambert) && (l.kind == kLambert || l.kind == kOrenNayar)) {
         *wi = cosine_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi->z = wi->z * -1.0f;
-        *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        *pdf = lobe_pdf<CLS>(l, wo, *wi);
+        return lobe_f<CLS>(l, wo, *wi);
     }
-    if (l.kind == kMicrofacet || l.kind == kMicrofacetConductor) {
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
         if (wo.z == 0.0f) return gray(0.0f);
         const vec3 wh = tr_sample_wh(l.alpha, wo, u0, u1);
         if (dot3(wo, wh) < 0.0f) return gray(0.0f);
         *wi = mirror(wo, wh);                                   // D36 FIX
         if (!same_side(wo, *wi)) return gray(0.0f);
         *pdf = tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
-        return lobe_f(l, wo, *wi);
+        return lobe_f<CLS>(l, wo, *wi);
     }
+    if (!may_be<CLS>(kFresnelSpecular)) return gray(0.0f);
     const float fr = fresnel_dielectric(cos_t(wo), l.eta_a, l.eta_b);
     if (u0 < fr) {
         *wi = mk(-wo.x, -wo.y, wo.z);
@@ -306,49 +317,49 @@ PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, 
 
 // NL = the most lobes the material can have (1 for matte and glass, 2 for plastic): with NL = 1 every lobe index is the
 // constant 0, the lobe kind set by make_bsdf<MAT> is a compile-time constant and the lobe array lives in registers.
-template <int NL>
+template <int NL, int CLS = -1>
 struct BsdfT {
     float eta;
     vec3 ns, ng, ss, ts;
     int n;
     Lobe lobes[NL];
 };
-using Bsdf = BsdfT<2>;
+using Bsdf = BsdfT<2, -1>;
 
-template <int NL>
-PB2_HD int bsdf_count(const BsdfT<NL>& b, unsigned flags) {
+template <int NL, int CLS>
+PB2_HD int bsdf_count(const BsdfT<NL, CLS>& b, unsigned flags) {
     int c = 0;
 #pragma unroll
     for (int i = 0; i < NL; ++i) c += (i < b.n && lobe_matches(b.lobes[i], flags)) ? 1 : 0;
     return c;
 }
-template <int NL>
-PB2_HD vec3 to_local(const BsdfT<NL>& b, vec3 v) { return mk(dot3(v, b.ss), dot3(v, b.ts), dot3(v, b.ns)); }
-template <int NL>
-PB2_HD vec3 to_world(const BsdfT<NL>& b, vec3 v) {                  // D34 FIX
+template <int NL, int CLS>
+PB2_HD vec3 to_local(const BsdfT<NL, CLS>& b, vec3 v) { return mk(dot3(v, b.ss), dot3(v, b.ts), dot3(v, b.ns)); }
+template <int NL, int CLS>
+PB2_HD vec3 to_world(const BsdfT<NL, CLS>& b, vec3 v) {                  // D34 FIX
     return mk((b.ss.x * v.x + b.ts.x * v.y) + b.ns.x * v.z, (b.ss.y * v.x + b.ts.y * v.y) + b.ns.y * v.z,
               (b.ss.z * v.x + b.ts.z * v.y) + b.ns.z * v.z);
 }
-template <int NL>
-PB2_HD rgb3 bsdf_sum_f(const BsdfT<NL>& b, vec3 wo, vec3 wi, bool refl, unsigned flags) {
+template <int NL, int CLS>
+PB2_HD rgb3 bsdf_sum_f(const BsdfT<NL, CLS>& b, vec3 wo, vec3 wi, bool refl, unsigned flags) {
     rgb3 sum = gray(0.0f);
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
         if (i >= b.n) break;
         const Lobe& l = b.lobes[i];
-        if (lobe_matches(l, flags) && ((refl && (l.type & kReflection)) || (!refl && (l.type & kTransmission)))) sum = sum + lobe_f(l, wo, wi);
+        if (lobe_matches(l, flags) && ((refl && (l.type & kReflection)) || (!refl && (l.type & kTransmission)))) sum = sum + lobe_f<CLS>(l, wo, wi);
     }
     return sum;
 }
-template <int NL>
-PB2_HD rgb3 bsdf_f(const BsdfT<NL>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+template <int NL, int CLS>
+PB2_HD rgb3 bsdf_f(const BsdfT<NL, CLS>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
     const vec3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0f) return gray(0.0f);
     const bool refl = dot3(wi_w, b.ng) * dot3(wo_w, b.ng) > 0.0f;
     return bsdf_sum_f(b, wo, wi, refl, flags);
 }
-template <int NL>
-PB2_HD float bsdf_pdf(const BsdfT<NL>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
+template <int NL, int CLS>
+PB2_HD float bsdf_pdf(const BsdfT<NL, CLS>& b, vec3 wo_w, vec3 wi_w, unsigned flags) {
     if (b.n == 0) return 0.0f;
     const vec3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
     if (wo.z == 0.0f) return 0.0f;
@@ -356,12 +367,12 @@ PB2_HD float bsdf_pdf(const BsdfT<NL>& b, vec3 wo_w, vec3 wi_w, unsigned flags) 
     int matching = 0;
 #pragma unroll
     for (int i = 0; i < NL; ++i)
-        if (i < b.n && lobe_matches(b.lobes[i], flags)) { ++matching; p += lobe_pdf(b.lobes[i], wo, wi); }
+        if (i < b.n && lobe_matches(b.lobes[i], flags)) { ++matching; p += lobe_pdf<CLS>(b.lobes[i], wo, wi); }
     return matching > 0 ? p / (float)matching : 0.0f;
 }
 // BSDF::sample_f (:286-381).  *pdf must be pre-set by the caller (it is left untouched on the early exits, as in the reference).
-template <int NL>
-PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, float u1, float* pdf, unsigned flags, unsigned* sampled) {
+template <int NL, int CLS>
+PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL, CLS>& b, vec3 wo_w, vec3* wi_w, float u0, float u1, float* pdf, unsigned flags, unsigned* sampled) {
     const int matching = bsdf_count(b, flags);
     if (matching == 0) { *pdf = 0.0f; *sampled = 0u; return gray(0.0f); }
     int comp = (int)floorf(u0 * (float)matching);
@@ -381,13 +392,13 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, f
     if (wo.z == 0.0f) return gray(0.0f);
     *pdf = 0.0f;
     *sampled = bx.type;
-    rgb3 fv = lobe_sample_f(bx, wo, &wi, u0r, u1, pdf, sampled);
+    rgb3 fv = lobe_sample_f<CLS>(bx, wo, &wi, u0r, u1, pdf, sampled);
     if (*pdf == 0.0f) { *sampled = 0u; return gray(0.0f); }
     *wi_w = to_world(b, wi);
     if (!(bx.type & kSpecular) && matching > 1) {
 #pragma unroll
         for (int i = 0; i < NL; ++i)
-            if (i < b.n && i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+            if (i < b.n && i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf<CLS>(b.lobes[i], wo, wi);
     }
     if (matching > 1) *pdf = *pdf / (float)matching;
     if (!(bx.type & kSpecular)) {
@@ -403,8 +414,8 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL>& b, vec3 wo_w, vec3* wi_w, float u0, f
 // compile-time constant: the kernel that carries C2 / C4), 1 = general (plastic, metal, Oren-Nayar matte; up to two lobes),
 // 2 = specular (glass, mirror; one lobe); CLS < 0 reads everything at run time.
 template <int CLS = -1>
-PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
-    BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> b;
+PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
+    BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> b;
     const int type = CLS == 0 ? 0 : m.type;
     b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = ns;
@@ -415,9 +426,12 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 
     const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);
     const rgb3 kr = mkc(m.kr[0], m.kr[1], m.kr[2]), kt = mkc(m.kt[0], m.kt[1], m.kt[2]);
     const rgb3 zero = gray(0.0f);
+    // (the first lobe of every material is written to lobes[0] by constant index: a `lobes[b.n++]` whose index the compiler
+    // cannot fold moves the whole lobe array to local memory)
     if (type == 0 || type == 1) {
         if (!black(kd)) {
-            Lobe& l = b.lobes[b.n++];
+            Lobe& l = b.lobes[0];
+            b.n = 1;
             const bool oren_nayar = CLS != 0 && type == 0;     // class 0 is Lambertian by construction
             l.kind = oren_nayar ? kOrenNayar : kLambert; l.type = kReflection | kDiffuse; l.r = kd; l.t = zero; l.alpha = 0.0f;
             l.eta_a = oren_nayar ? m.on_a : 1.0f; l.eta_b = oren_nayar ? m.on_b : 1.0f; l.k = zero;
@@ -427,17 +441,21 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2> make_bsdf(const DMaterial& m, vec3 
             l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = zero; l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f; l.k = zero;
         }
     } else if (type == 4) {                                    // MetalMaterial: MicrofacetReflection(1, TrowbridgeReitz, FresnelConductor(1, eta, k))
-        Lobe& l = b.lobes[b.n++];
+        Lobe& l = b.lobes[0];
+        b.n = 1;
         l.kind = kMicrofacetConductor; l.type = kReflection | kGlossy; l.r = gray(1.0f); l.t = mkc(m.metal_eta[0], m.metal_eta[1], m.metal_eta[2]);
         l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = 1.0f; l.k = mkc(m.metal_k[0], m.metal_k[1], m.metal_k[2]);
-    } else if (type == 3) {                                    // MirrorMaterial: SpecularReflection(Kr, FresnelNoOp)
-        if (!black(kr)) {
-            Lobe& l = b.lobes[b.n++];
-            l.kind = kSpecularReflection; l.type = kReflection | kSpecular; l.r = kr; l.t = zero; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f; l.k = zero;
+    } else {
+        // type 3 = MirrorMaterial: SpecularReflection(Kr, FresnelNoOp); type 2 = GlassMaterial: FresnelSpecular(Kr, Kt, 1, eta).
+        // One write site with selects, so the lobe stays in registers whichever of the two it is.
+        const bool mir = type == 3;
+        if (mir ? !black(kr) : !(black(kr) && black(kt))) {
+            Lobe& l = b.lobes[0];
+            b.n = 1;
+            l.kind = mir ? kSpecularReflection : kFresnelSpecular;
+            l.type = mir ? (kReflection | kSpecular) : (kReflection | kTransmission | kSpecular);
+            l.r = kr; l.t = mir ? zero : kt; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = mir ? 1.0f : m.eta; l.k = zero;
         }
-    } else if (!(black(kr) && black(kt))) {
-        Lobe& l = b.lobes[b.n++];
-        l.kind = kFresnelSpecular; l.type = kReflection | kTransmission | kSpecular; l.r = kr; l.t = kt; l.alpha = 0.0f; l.eta_a = 1.0f; l.eta_b = m.eta; l.k = zero;
     }
     return b;
 }
