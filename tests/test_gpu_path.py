@@ -491,3 +491,34 @@ def test_all_materials_bit_exact(gpu, OP, scenes):
     bad.type = 9
     with pytest.raises(gpu.Pb2Error):                       # unknown material type is refused at build time
         gpu.BVHAccel(gpu.Scene(sc["verts"], sc["idx"], sc["tri_material"], [bad] * len(sc["materials"]), []), 4)
+
+
+def test_no_device_memory_leak_over_scene_and_film_lifecycles(gpu, scenes):
+    """Handles own their device memory: building, rendering with every sampler (tables, Halton permutations, wavefront arena, ring
+    stages) and destroying scenes / films 12 times leaves the free device memory where it was."""
+    import torch
+    sc = scenes.scene_c4_smooth(16, 32)
+    cam = scenes.C4_CAMERA
+    rays = np.zeros((1000, 8), np.float32)
+    rays[:, 0:3] = (278, 273, -800); rays[:, 6] = 1.0; rays[:, 3] = np.inf
+
+    def cycle():
+        scene = gpu.scene_from_dict(sc)
+        accel = gpu.BVHAccel(scene, 4, split_method=1)
+        accel.intersect(rays); accel.intersect_p(rays)
+        camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], (64, 36))
+        for sampler, kw in (("random", {}), ("halton", {}), ("stratified", dict(x_samples=2, y_samples=2)), ("zerotwo", {})):
+            film = gpu.Film((64, 36), filter="gaussian", radius=(2.0, 2.0))
+            gpu.PathIntegrator(accel, camera, max_depth=3, spp=4, sampler=sampler, **kw).render(film)
+            film.read_xyzw()
+            film.destroy()
+        scene.destroy()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(12):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, f"{(free0 - free1) >> 20} MiB of device memory not returned"
