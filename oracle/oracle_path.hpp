@@ -260,7 +260,10 @@ inline Float fr_conductor1(Float cos_theta_i, Float eta_i, Float eta_t, Float k)
 // ---------------------------------------------------------------- BxDFs as tagged PODs
 // The Rust OrenNayar (reflection.rs:917-971) does not convert sigma to radians (`signma` is unused), takes sin_phi_o from
 // sin_theta(wo) and builds d_cos from sin_theta instead of sin_phi; pbrt-v3 semantics here (D61 FIX).
-enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR, LOBE_OREN_NAYAR, LOBE_SPECULAR_REFLECTION, LOBE_MICROFACET_CONDUCTOR };
+// MicrofacetTransmission::pdf (reflection.rs:1170-1187) divides by sqrt_denom and then MULTIPLIES by it (`/ sqrt_denom * sqrt_denom`);
+// pbrt-v3's dwh_dwi = |eta^2 (wi . wh) / sqrt_denom^2| is followed (D62 FIX).
+enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR, LOBE_OREN_NAYAR, LOBE_SPECULAR_REFLECTION, LOBE_MICROFACET_CONDUCTOR,
+                          LOBE_MICROFACET_TRANSMISSION };
 struct Lobe {
     LobeKind kind;
     uint8_t type;       // BxDFType bits
@@ -284,6 +287,22 @@ struct Lobe {
                 if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_theta_o; tan_beta = sin_theta_i / abs_cos_theta(wi); }
                 else { sin_alpha = sin_theta_i; tan_beta = sin_theta_o / abs_cos_theta(wo); }
                 return r * (1.0f / kPi) * (eta_a + ((eta_b * max_cos) * sin_alpha) * tan_beta);
+            }
+            case LOBE_MICROFACET_TRANSMISSION: {                                             // :1093-1136 (TransportMode::Radiance)
+                if (same_hemisphere(wo, wi)) return rgb(0);
+                const Float cos_theta_o = cos_theta(wo), cos_theta_i = cos_theta(wi);
+                if (cos_theta_i == 0.0f || cos_theta_o == 0.0f) return rgb(0);
+                const Float eta = cos_theta(wo) > 0.0f ? eta_b / eta_a : eta_a / eta_b;
+                V3 wh = normalize(wo + wi * eta);
+                if (wh.z < 0.0f) wh = -wh;
+                if (dot(wo, wh) * dot(wi, wh) > 0.0f) return rgb(0);
+                TrowbridgeReitz tr{alpha, alpha};
+                const Float fr = fr_dielectric(dot(wo, wh), eta_a, eta_b);
+                const Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+                const Float factor = 1.0f / eta;
+                const Float num = ((((((tr.d(wh) * tr.g(wo, wi)) * eta) * eta) * std::fabs(dot(wi, wh))) * std::fabs(dot(wo, wh))) * factor) * factor;
+                const Float den = ((cos_theta_i * cos_theta_o) * sqrt_denom) * sqrt_denom;
+                return (rgb(1.0f) + rgb(fr) * -1.0f) * t * std::fabs(num / den);
             }
             case LOBE_MICROFACET_CONDUCTOR: {                                                // :998-1017 with FresnelConductor (:583-587)
                 Float co = abs_cos_theta(wo), ci = abs_cos_theta(wi);
@@ -313,6 +332,16 @@ struct Lobe {
         switch (kind) {
             case LOBE_LAMBERT:
             case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * (1.0f / kPi) : 0.0f;   // :501-507
+            case LOBE_MICROFACET_TRANSMISSION: {                                             // :1170-1187, D62 FIX
+                if (same_hemisphere(wo, wi)) return 0.0f;
+                const Float eta = cos_theta(wo) > 0.0f ? eta_b / eta_a : eta_a / eta_b;
+                const V3 wh = normalize(wo + wi * eta);
+                if (dot(wo, wh) * dot(wi, wh) > 0.0f) return 0.0f;
+                const Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+                const Float dwh_dwi = std::fabs(((eta * eta) * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+                TrowbridgeReitz tr{alpha, alpha};
+                return tr.pdf(wo, wh) * dwh_dwi;
+            }
             case LOBE_MICROFACET_CONDUCTOR:
             case LOBE_MICROFACET: {                                                          // :1042-1048
                 if (!same_hemisphere(wo, wi)) return 0.0f;
@@ -334,6 +363,16 @@ struct Lobe {
             case LOBE_OREN_NAYAR: {                                                          // :459-472 BxDF default
                 *wi = cosine_sample_hemisphere(u0, u1);
                 if (wo.z < 0.0f) wi->z *= -1.0f;
+                *pdf_out = pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case LOBE_MICROFACET_TRANSMISSION: {                                             // :1138-1168
+                if (wo.z == 0.0f) return rgb(0);
+                TrowbridgeReitz tr{alpha, alpha};
+                const V3 wh = tr.sample_wh(wo, u0, u1);
+                if (dot(wo, wh) < 0.0f) return rgb(0);
+                const Float eta = cos_theta(wo) > 0.0f ? eta_a / eta_b : eta_b / eta_a;
+                if (!refract(wo, wh, eta, wi)) return rgb(0);
                 *pdf_out = pdf(wo, *wi);
                 return f(wo, *wi);
             }
@@ -619,6 +658,9 @@ public:
             if (!is_black(kd)) b.lobes[b.n++] = Lobe{LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, kd, rgb(0), 0, 1, 1};
             if (m.d.type == MAT_PLASTIC && !is_black(ks))
                 b.lobes[b.n++] = Lobe{LOBE_MICROFACET, BSDF_REFLECTION | BSDF_GLOSSY, ks, rgb(0), m.alpha, 1.5f, 1.0f};
+        } else if (m.d.type == MAT_GLASS && m.d.roughness != 0.0f) {                            // pbrt-v3 GlassMaterial, rough: two microfacet lobes
+            if (!is_black(kr)) b.lobes[b.n++] = Lobe{LOBE_MICROFACET, BSDF_REFLECTION | BSDF_GLOSSY, kr, rgb(0), m.alpha, 1.0f, m.d.eta};
+            if (!is_black(kt)) b.lobes[b.n++] = Lobe{LOBE_MICROFACET_TRANSMISSION, BSDF_TRANSMISSION | BSDF_GLOSSY, rgb(0), kt, m.alpha, 1.0f, m.d.eta};
         } else if (!(is_black(kr) && is_black(kt))) {
             b.lobes[b.n++] = Lobe{LOBE_FRESNEL_SPECULAR, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, kr, kt, 0, 1.0f, m.d.eta};
         }

@@ -49,7 +49,7 @@ def material(d):
     m.type = _MAT[d["type"]]
     m.kd[:] = d.get("kd", (0, 0, 0))
     m.ks[:] = d.get("ks", (0, 0, 0))
-    m.roughness = d.get("roughness", 0.1)
+    m.roughness = d.get("roughness", 0.0 if d["type"] == "glass" else 0.1)      # glass: 0 = smooth (FresnelSpecular), > 0 = rough
     m.remap_roughness = int(d.get("remap", True))
     m.kr[:] = d.get("kr", (0, 0, 0))
     m.kt[:] = d.get("kt", (0, 0, 0))

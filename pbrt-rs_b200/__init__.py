@@ -100,12 +100,15 @@ def plastic(kd, ks, roughness=0.1, remap=True):
     return m
 
 
-def glass(kr=(1, 1, 1), kt=(1, 1, 1), eta=1.5):
+def glass(kr=(1, 1, 1), kt=(1, 1, 1), eta=1.5, roughness=0.0, remap=True):
+    """pbrt-v3 GlassMaterial: FresnelSpecular when smooth, MicrofacetReflection + MicrofacetTransmission when roughness > 0."""
     m = Material()
     m.type = MAT_GLASS
     m.kr[:] = kr
     m.kt[:] = kt
     m.eta = eta
+    m.roughness = roughness
+    m.remap_roughness = int(remap)
     return m
 
 
@@ -398,7 +401,7 @@ def material_from_dict(d):
         return metal(d.get("metal_eta", (0.2, 0.92, 1.1)), d.get("metal_k", (3.9, 2.45, 2.14)), d.get("roughness", 0.01), d.get("remap", True))
     if d["type"] == "plastic":
         return plastic(d["kd"], d["ks"], d.get("roughness", 0.1), d.get("remap", True))
-    return glass(d.get("kr", (1, 1, 1)), d.get("kt", (1, 1, 1)), d.get("eta", 1.5))
+    return glass(d.get("kr", (1, 1, 1)), d.get("kt", (1, 1, 1)), d.get("eta", 1.5), d.get("roughness", 0.0), d.get("remap", True))
 
 
 def light_from_dict(d):

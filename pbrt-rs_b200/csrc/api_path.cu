@@ -88,7 +88,7 @@ int upload_shading_tables(pb2_scene* scene) {
             d.on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
         }
         // shading class (shade.cuh: make_bsdf<CLS>)
-        d.cls = (m.type == PB2_MAT_MATTE && m.sigma == 0.0f) ? 0 : ((m.type == PB2_MAT_GLASS || m.type == PB2_MAT_MIRROR) ? 2 : 1);
+        d.cls = (m.type == PB2_MAT_MATTE && m.sigma == 0.0f) ? 0 : (((m.type == PB2_MAT_GLASS && m.roughness == 0.0f) || m.type == PB2_MAT_MIRROR) ? 2 : 1);
     }
     const size_t n_lights = scene->lights.size();
     std::vector<DLight> lights(std::max<size_t>(1, n_lights));

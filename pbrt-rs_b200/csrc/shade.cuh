@@ -199,7 +199,8 @@ struct DLight {
     float uv[6];            // its UVs (Shape::pdf2 -> Triangle::intersect frame check)
 };
 
-enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u };
+enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u,
+                           kMicrofacetTransmission = 6u };
 struct Lobe {
     unsigned kind, type;
     rgb3 r, t;              // conductor: t = eta
@@ -231,7 +232,7 @@ PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags
 template <int CLS>
 PB2_HD constexpr bool may_be(unsigned kind) {
     return CLS < 0 || (CLS == 0 && kind == kLambert) ||
-           (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor)) ||
+           (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor || kind == kMicrofacetTransmission)) ||
            (CLS == 2 && (kind == kFresnelSpecular || kind == kSpecularReflection));
 }
 template <int CLS>
@@ -263,6 +264,21 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
         } else fr = gray(fresnel_dielectric(c, l.eta_a, l.eta_b));
         return l.r * tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi) * fr / (4.0f * ci * co);
     }
+    if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1093-1136, TransportMode::Radiance
+        if (same_side(wo, wi)) return gray(0.0f);
+        const float cto = cos_t(wo), cti = cos_t(wi);
+        if (cti == 0.0f || cto == 0.0f) return gray(0.0f);
+        const float eta = cto > 0.0f ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+        vec3 wh = unit(wo + wi * eta);
+        if (wh.z < 0.0f) wh = -wh;
+        if (dot3(wo, wh) * dot3(wi, wh) > 0.0f) return gray(0.0f);
+        const float fr = fresnel_dielectric(dot3(wo, wh), l.eta_a, l.eta_b);
+        const float sqrt_denom = dot3(wo, wh) + eta * dot3(wi, wh);
+        const float factor = 1.0f / eta;
+        const float num = ((((((tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi)) * eta) * eta) * fabsf(dot3(wi, wh))) * fabsf(dot3(wo, wh))) * factor) * factor;
+        const float den = ((cti * cto) * sqrt_denom) * sqrt_denom;
+        return (gray(1.0f) + gray(fr) * -1.0f) * l.t * fabsf(num / den);
+    }
     return gray(0.0f);
 }
 template <int CLS>
@@ -272,6 +288,15 @@ PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
         if (!same_side(wo, wi)) return 0.0f;
         const vec3 wh = unit(wo + wi);
         return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+    }
+    if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1170-1187, D62 FIX
+        if (same_side(wo, wi)) return 0.0f;
+        const float eta = cos_t(wo) > 0.0f ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+        const vec3 wh = unit(wo + wi * eta);
+        if (dot3(wo, wh) * dot3(wi, wh) > 0.0f) return 0.0f;
+        const float sqrt_denom = dot3(wo, wh) + eta * dot3(wi, wh);
+        const float dwh_dwi = fabsf(((eta * eta) * dot3(wi, wh)) / (sqrt_denom * sqrt_denom));
+        return tr_pdf(l.alpha, wo, wh) * dwh_dwi;
     }
     return 0.0f;
 }
@@ -295,6 +320,15 @@ PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, 
         *wi = mirror(wo, wh);                                   // D36 FIX
         if (!same_side(wo, *wi)) return gray(0.0f);
         *pdf = tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+        return lobe_f<CLS>(l, wo, *wi);
+    }
+    if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1138-1168
+        if (wo.z == 0.0f) return gray(0.0f);
+        const vec3 wh = tr_sample_wh(l.alpha, wo, u0, u1);
+        if (dot3(wo, wh) < 0.0f) return gray(0.0f);
+        const float eta = cos_t(wo) > 0.0f ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
+        if (!refract_dir(wo, wh, eta, wi)) return gray(0.0f);
+        *pdf = lobe_pdf<CLS>(l, wo, *wi);
         return lobe_f<CLS>(l, wo, *wi);
     }
     if (!may_be<CLS>(kFresnelSpecular)) return gray(0.0f);
@@ -439,6 +473,17 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, 
         if (type == 1 && !black(ks)) {
             Lobe& l = b.lobes[b.n++];
             l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = ks; l.t = zero; l.alpha = m.alpha; l.eta_a = 1.5f; l.eta_b = 1.0f; l.k = zero;
+        }
+    } else if (type == 2 && (CLS == 1 || (CLS < 0 && m.cls == 1))) {
+        // GlassMaterial with roughness: MicrofacetReflection(Kr, TrowbridgeReitz, FresnelDielectric(1, eta)) + MicrofacetTransmission(Kt, ..., 1, eta)
+        if (!black(kr)) {
+            Lobe& l = b.lobes[0];
+            b.n = 1;
+            l.kind = kMicrofacet; l.type = kReflection | kGlossy; l.r = kr; l.t = zero; l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = m.eta; l.k = zero;
+        }
+        if (!black(kt)) {
+            Lobe& l = b.lobes[b.n++];
+            l.kind = kMicrofacetTransmission; l.type = kTransmission | kGlossy; l.r = zero; l.t = kt; l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = m.eta; l.k = zero;
         }
     } else if (type == 4) {                                    // MetalMaterial: MicrofacetReflection(1, TrowbridgeReitz, FresnelConductor(1, eta, k))
         Lobe& l = b.lobes[0];

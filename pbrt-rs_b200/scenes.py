@@ -260,8 +260,13 @@ def scene_materials(n_theta=32, n_phi=64):
     mats[3] = dict(type="matte", kd=(0.6, 0.6, 0.7), sigma=35.0)
     mats[4] = dict(type="metal", metal_eta=(0.2, 0.92, 1.1), metal_k=(3.9, 2.45, 2.14), roughness=0.05, remap=True)
     mats[5] = dict(type="mirror", kr=(0.9, 0.9, 0.9))
-    mats += [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5),
+    mats += [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5, roughness=0.2, remap=True),      # frosted
              dict(type="plastic", kd=(0.25, 0.35, 0.25), ks=(0.3, 0.3, 0.3), roughness=0.1, remap=True)]
+    mats[0] = dict(mats[0])
+    mats.append(dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5))                                 # smooth
+    tm = np.array(tm, dtype=np.uint32)
+    tm[tm == 7] = np.where(np.arange((tm == 7).sum()) % 2 == 0, 7, 8)          # half of the plastic ball's triangles are smooth glass
+    tm = list(tm)
     return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=mats, lights=sc["lights"])
 
 
