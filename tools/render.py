@@ -14,7 +14,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scene", default="c2", choices=["c2", "c4", "c4smooth", "lights"])
+    ap.add_argument("--scene", default="c2", choices=["c2", "c4", "c4smooth", "lights", "materials"])
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--res", type=int, nargs=2, default=None)
     ap.add_argument("--sampler", default="random", choices=["random", "halton", "stratified", "zerotwo"])
@@ -31,6 +31,20 @@ def main():
         sc, cam, pk = scenes.scene_c2(), dict(scenes.C2_CAMERA), dict(scenes.C2_PATH)
     elif args.scene == "c4":
         sc, cam, pk = scenes.scene_c4(), dict(scenes.C4_CAMERA), dict(scenes.C4_PATH)
+    elif args.scene == "materials":
+        sc, cam, pk = scenes.scene_materials(96, 192), dict(scenes.C4_CAMERA), dict(scenes.C4_PATH)
+        import numpy as np
+        v = sc["verts"].astype(np.float64)                  # smooth shading: analytic normals for the five balls
+        nrm = np.zeros_like(v)
+        for c, mats in (((140.0, 90.0, 280.0), (3,)), ((278.0, 130.0, 220.0), (4,)), ((416.0, 90.0, 280.0), (5,)), ((200.0, 45.0, 120.0), (6,)),
+                        ((350.0, 45.0, 120.0), (7, 8))):
+            used = np.unique(sc["idx"][np.isin(sc["tri_material"], mats)])
+            nrm[used] = v[used] - np.array(c)
+        flat = np.linalg.norm(nrm, axis=1) == 0
+        fn = np.cross(v[sc["idx"][:, 1]] - v[sc["idx"][:, 0]], v[sc["idx"][:, 2]] - v[sc["idx"][:, 0]])
+        for k in range(3):
+            np.add.at(nrm, sc["idx"][:, k], fn * flat[sc["idx"][:, k]][:, None])
+        sc["normals"] = (nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)).astype(np.float32)
     else:
         sc, cam, pk = scenes.scene_c4_smooth(n_theta=64, n_phi=128, emissive_normals=False), dict(scenes.C4_CAMERA), dict(scenes.C4_PATH)
         if args.scene == "lights":
