@@ -192,10 +192,14 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     const bool swap_groups = ((flags >> ((ref.x >> 29) & 3u)) & 1u) != 0u;   // A before B, or B before A
                     const bool swap_a = ((flags >> ((ref.y >> 29) & 3u)) & 1u) != 0u, swap_b = ((flags >> ((ref.z >> 29) & 3u)) & 1u) != 0u;
                     uint32_t r0 = ref.x & 0x9FFFFFFFu, r1 = ref.y & 0x9FFFFFFFu, r2 = ref.z & 0x9FFFFFFFu, r3 = ref.w;
-                    swap_if(swap_a, r0, t0, r1, t1);                                          // inside A
-                    swap_if(swap_b, r2, t2, r3, t3);                                          // inside B
-                    swap_if(swap_groups, r0, t0, r2, t2);
-                    swap_if(swap_groups, r1, t1, r3, t3);
+                    if (!ANY) {
+                        swap_if(swap_a, r0, t0, r1, t1);                                      // inside A
+                        swap_if(swap_b, r2, t2, r3, t3);                                      // inside B
+                        swap_if(swap_groups, r0, t0, r2, t2);
+                        swap_if(swap_groups, r1, t1, r3, t3);
+                    }
+                    // (intersect_p's answer does not depend on the visiting order: t_max never shrinks, so the set of leaves whose
+                    // boxes the ray passes — and with it "some triangle in them is hit" — is the same in any order)
                     const float inf = __int_as_float(0x7f800000);
                     const bool h0 = t0 < inf, h1 = t1 < inf, h2 = t2 < inf, h3 = t3 < inf;
                     // later candidates first, so the next one in visiting order is popped first
@@ -242,7 +246,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     --sp;
                     const uint2 e = top;
                     if (sp > 0) top = stack[sp - 1];                    // needed at the next pop, not now
-                    if (__uint_as_float(e.y) < t_max) { cur = e.x; break; }
+                    if (ANY || __uint_as_float(e.y) < t_max) { cur = e.x; break; }   // (any hit: t_max is the ray's own, checked at push time)
                 }
                 if (cur == kDone) {
                     if (ANY) sink.occluded(ray_idx, false);
