@@ -47,23 +47,25 @@ struct SlotInfo {
     unsigned long long seq;   // sampler stream: ((y - sb_y0) * sb_w + (x - sb_x0)) * spp + sample
     uint32_t pix;             // (y - sb_y0) * sb_w + (x - sb_x0)
 };
-__device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& f, uint64_t slot) {
+// (32-bit arithmetic: a wavefront holds at most 2^28 slots, and a 64-bit modulo costs ~100 instructions in every kernel
+// that resumes a sampler)
+__device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& f, uint64_t slot64) {
+    const uint32_t slot = (uint32_t)slot64;
     SlotInfo s;
-    uint32_t sample;
     if (m.explicit_xy) {
-        s.x = m.explicit_xy[2 * slot];
-        s.y = m.explicit_xy[2 * slot + 1];
-        sample = m.explicit_s[slot];
+        s.x = m.explicit_xy[2ull * slot];
+        s.y = m.explicit_xy[2ull * slot + 1];
+        s.sample = m.explicit_s[slot];
+        s.pix = (uint32_t)(s.y - f.sb_y0) * (uint32_t)f.sb_w + (uint32_t)(s.x - f.sb_x0);
     } else {
-        const uint32_t pix = (uint32_t)(slot % m.n_pix);
-        sample = (uint32_t)m.sample0 + (uint32_t)(slot / m.n_pix);
-        s.x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w);
-        s.y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
+        const uint32_t s_local = slot / m.n_pix;
+        s.pix = slot - s_local * m.n_pix;
+        s.sample = (uint32_t)m.sample0 + s_local;
+        const uint32_t row = s.pix / (uint32_t)f.sb_w;
+        s.x = f.sb_x0 + (int)(s.pix - row * (uint32_t)f.sb_w);
+        s.y = f.sb_y0 + (int)row;
     }
-    s.sample = sample;
-    const unsigned long long pix = (unsigned long long)(s.y - f.sb_y0) * (unsigned long long)f.sb_w + (unsigned long long)(s.x - f.sb_x0);
-    s.pix = (uint32_t)pix;
-    s.seq = pix * (unsigned long long)m.spp + sample;
+    s.seq = (unsigned long long)s.pix * (unsigned long long)m.spp + s.sample;
     return s;
 }
 
