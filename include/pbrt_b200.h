@@ -47,12 +47,12 @@ typedef struct pb2_hit {
 /* pbrt-v3 matte / plastic / glass / mirror / metal over the reference's BxDF blocks (the reference's src/materials/*.rs are
  * empty files): LambertianReflection or OrenNayar (reflection.rs:821-855, 917-971), MicrofacetReflection +
  * TrowbridgeReitz + FresnelDielectric / FresnelConductor (:977-1056, :571-604, :42-69), FresnelSpecular (:733-819),
- * SpecularReflection + FresnelNoOp (:606-659), MicrofacetTransmission (:1058-1192). */
-enum { PB2_MAT_MATTE = 0, PB2_MAT_PLASTIC = 1, PB2_MAT_GLASS = 2, PB2_MAT_MIRROR = 3, PB2_MAT_METAL = 4 };
+ * SpecularReflection + FresnelNoOp (:606-659), MicrofacetTransmission (:1058-1192), FresnelBlend (:1194-1280; substrate: kd, ks, roughness). */
+enum { PB2_MAT_MATTE = 0, PB2_MAT_PLASTIC = 1, PB2_MAT_GLASS = 2, PB2_MAT_MIRROR = 3, PB2_MAT_METAL = 4, PB2_MAT_SUBSTRATE = 5 };
 typedef struct pb2_material {
     int32_t type;
-    float kd[3];        /* matte, plastic: diffuse reflectance */
-    float ks[3];        /* plastic: glossy reflectance */
+    float kd[3];        /* matte, plastic, substrate: diffuse reflectance */
+    float ks[3];        /* plastic, substrate: glossy reflectance */
     float roughness;    /* plastic, metal; glass: 0 = smooth (FresnelSpecular), > 0 = rough (MicrofacetReflection + MicrofacetTransmission) */
     int32_t remap_roughness;
     float kr[3];        /* glass, mirror */

@@ -48,7 +48,7 @@ inline void xyz_to_rgb(const Float xyz[3], Float out[3]) {                      
 inline Float clampf(Float v, Float lo, Float hi) { return v < lo ? lo : (v > hi ? hi : v); }   // pbrt.rs:112-120
 
 // ---------------------------------------------------------------- scene description (same POD layout as the C ABI)
-enum { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_GLASS = 2, MAT_MIRROR = 3, MAT_METAL = 4 };
+enum { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_GLASS = 2, MAT_MIRROR = 3, MAT_METAL = 4, MAT_SUBSTRATE = 5 };
 struct MaterialDesc {
     int32_t type;
     Float kd[3], ks[3];
@@ -263,7 +263,7 @@ inline Float fr_conductor1(Float cos_theta_i, Float eta_i, Float eta_t, Float k)
 // MicrofacetTransmission::pdf (reflection.rs:1170-1187) divides by sqrt_denom and then MULTIPLIES by it (`/ sqrt_denom * sqrt_denom`);
 // pbrt-v3's dwh_dwi = |eta^2 (wi . wh) / sqrt_denom^2| is followed (D62 FIX).
 enum LobeKind : uint8_t { LOBE_LAMBERT, LOBE_MICROFACET, LOBE_FRESNEL_SPECULAR, LOBE_OREN_NAYAR, LOBE_SPECULAR_REFLECTION, LOBE_MICROFACET_CONDUCTOR,
-                          LOBE_MICROFACET_TRANSMISSION };
+                          LOBE_MICROFACET_TRANSMISSION, LOBE_FRESNEL_BLEND };
 struct Lobe {
     LobeKind kind;
     uint8_t type;       // BxDFType bits
@@ -287,6 +287,18 @@ struct Lobe {
                 if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_theta_o; tan_beta = sin_theta_i / abs_cos_theta(wi); }
                 else { sin_alpha = sin_theta_i; tan_beta = sin_theta_o / abs_cos_theta(wo); }
                 return r * (1.0f / kPi) * (eta_a + ((eta_b * max_cos) * sin_alpha) * tan_beta);
+            }
+            case LOBE_FRESNEL_BLEND: {                                                       // :1224-1240 (r = Rd, t = Rs)
+                auto pow5 = [](Float v) { return (v * v) * (v * v) * v; };
+                const RGB diffuse = rgb(28.0f / (23.0f * kPi)) * r * (rgb(1.0f) + t * -1.0f) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
+                                    (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo)));
+                V3 wh = wi + wo;
+                if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return rgb(0);
+                wh = normalize(wh);
+                TrowbridgeReitz tr{alpha, alpha};
+                const RGB schlick = t + (rgb(1.0f) + t * -1.0f) * pow5(1.0f - dot(wi, wh));    // schlick_fresnel :1212-1215
+                const RGB specular = schlick * (tr.d(wh) / ((4.0f * std::fabs(dot(wi, wh))) * fmax_(abs_cos_theta(wi), abs_cos_theta(wo))));
+                return diffuse + specular;
             }
             case LOBE_MICROFACET_TRANSMISSION: {                                             // :1093-1136 (TransportMode::Radiance)
                 if (same_hemisphere(wo, wi)) return rgb(0);
@@ -332,6 +344,13 @@ struct Lobe {
         switch (kind) {
             case LOBE_LAMBERT:
             case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * (1.0f / kPi) : 0.0f;   // :501-507
+            case LOBE_FRESNEL_BLEND: {                                                       // :1267-1275
+                if (!same_hemisphere(wo, wi)) return 0.0f;
+                const V3 wh = normalize(wo + wi);
+                TrowbridgeReitz tr{alpha, alpha};
+                const Float pdf_wh = tr.pdf(wo, wh);
+                return 0.5f * (abs_cos_theta(wi) * (1.0f / kPi) + pdf_wh / (4.0f * dot(wo, wh)));
+            }
             case LOBE_MICROFACET_TRANSMISSION: {                                             // :1170-1187, D62 FIX
                 if (same_hemisphere(wo, wi)) return 0.0f;
                 const Float eta = cos_theta(wo) > 0.0f ? eta_b / eta_a : eta_a / eta_b;
@@ -363,6 +382,19 @@ struct Lobe {
             case LOBE_OREN_NAYAR: {                                                          // :459-472 BxDF default
                 *wi = cosine_sample_hemisphere(u0, u1);
                 if (wo.z < 0.0f) wi->z *= -1.0f;
+                *pdf_out = pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case LOBE_FRESNEL_BLEND: {                                                       // :1242-1265
+                if (u0 < 0.5f) {
+                    *wi = cosine_sample_hemisphere(fmin_(kOneMinusEpsilon, 2.0f * u0), u1);
+                    if (wo.z < 0.0f) wi->z *= -1.0f;
+                } else {
+                    TrowbridgeReitz tr{alpha, alpha};
+                    const V3 wh = tr.sample_wh(wo, fmin_(kOneMinusEpsilon, 2.0f * (u0 - 0.5f)), u1);
+                    *wi = reflect(wo, wh);
+                    if (!same_hemisphere(wo, *wi)) return rgb(0);
+                }
                 *pdf_out = pdf(wo, *wi);
                 return f(wo, *wi);
             }
@@ -648,6 +680,8 @@ public:
         RGB kr{m.d.kr[0], m.d.kr[1], m.d.kr[2]}, kt{m.d.kt[0], m.d.kt[1], m.d.kt[2]};
         if (m.d.type == MAT_MIRROR) {                                                           // pbrt-v3 MirrorMaterial
             if (!is_black(kr)) b.lobes[b.n++] = Lobe{LOBE_SPECULAR_REFLECTION, BSDF_REFLECTION | BSDF_SPECULAR, kr, rgb(0), 0, 1, 1};
+        } else if (m.d.type == MAT_SUBSTRATE) {                                                 // pbrt-v3 SubstrateMaterial (isotropic)
+            if (!is_black(kd) || !is_black(ks)) b.lobes[b.n++] = Lobe{LOBE_FRESNEL_BLEND, BSDF_REFLECTION | BSDF_GLOSSY, kd, ks, m.alpha, 1, 1};
         } else if (m.d.type == MAT_METAL) {                                                     // pbrt-v3 MetalMaterial (isotropic)
             Lobe l{LOBE_MICROFACET_CONDUCTOR, BSDF_REFLECTION | BSDF_GLOSSY, rgb(1.0f), RGB{m.d.metal_eta[0], m.d.metal_eta[1], m.d.metal_eta[2]}, m.alpha, 1, 1};
             l.k = RGB{m.d.metal_k[0], m.d.metal_k[1], m.d.metal_k[2]};

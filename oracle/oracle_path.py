@@ -39,7 +39,7 @@ class PathDesc(C.Structure):
 
 
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
-_MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4}
+_MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4, "substrate": 5}
 _STRAT = {"uniform": 0, "power": 1}
 _FILTER = {"box": 0, "gaussian": 1, "triangle": 2, "mitchell": 3, "sinc": 4}
 

@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("prim_id", np.uint32), ("t", np.float32), ("b1", np.float
 NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_prims", np.uint16), ("axis", np.uint8),
                        ("pad", np.uint8)])
 
-MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_MIRROR, MAT_METAL = 0, 1, 2, 3, 4
+MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_MIRROR, MAT_METAL, MAT_SUBSTRATE = 0, 1, 2, 3, 4, 5
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN, FILTER_TRIANGLE, FILTER_MITCHELL, FILTER_SINC = 0, 1, 2, 3, 4
 LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
@@ -68,6 +68,13 @@ def matte(kd, sigma=0.0):
     m.type = MAT_MATTE
     m.kd[:] = kd
     m.sigma = sigma
+    return m
+
+
+def substrate(kd, ks, roughness=0.1, remap=True):
+    """pbrt-v3 SubstrateMaterial (isotropic): FresnelBlend(Kd, Ks, TrowbridgeReitz) (reflection.rs:1194-1280)."""
+    m = plastic(kd, ks, roughness, remap)
+    m.type = MAT_SUBSTRATE
     return m
 
 
@@ -387,7 +394,7 @@ class PerspectiveCamera:
         check(lib().pb2_camera_primary_rays_device(C.byref(self.desc), d_rays, stream))
 
 
-_MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS, "mirror": MAT_MIRROR, "metal": MAT_METAL}
+_MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS, "mirror": MAT_MIRROR, "metal": MAT_METAL, "substrate": MAT_SUBSTRATE}
 _STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER}
 _FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN, "triangle": FILTER_TRIANGLE, "mitchell": FILTER_MITCHELL, "sinc": FILTER_SINC}
 
@@ -399,6 +406,8 @@ def material_from_dict(d):
         return mirror(d.get("kr", (0.9, 0.9, 0.9)))
     if d["type"] == "metal":
         return metal(d.get("metal_eta", (0.2, 0.92, 1.1)), d.get("metal_k", (3.9, 2.45, 2.14)), d.get("roughness", 0.01), d.get("remap", True))
+    if d["type"] == "substrate":
+        return substrate(d["kd"], d["ks"], d.get("roughness", 0.1), d.get("remap", True))
     if d["type"] == "plastic":
         return plastic(d["kd"], d["ks"], d.get("roughness", 0.1), d.get("remap", True))
     return glass(d.get("kr", (1, 1, 1)), d.get("kt", (1, 1, 1)), d.get("eta", 1.5), d.get("roughness", 0.0), d.get("remap", True))

@@ -74,7 +74,7 @@ int upload_shading_tables(pb2_scene* scene) {
     std::vector<DMaterial> mats(scene->materials.size());
     for (size_t i = 0; i < mats.size(); ++i) {
         const pb2_material& m = scene->materials[i];
-        if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_METAL) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
+        if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_SUBSTRATE) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
         DMaterial& d = mats[i];
         d.type = m.type;
         for (int k = 0; k < 3; ++k) { d.kd[k] = m.kd[k]; d.ks[k] = m.ks[k]; d.kr[k] = m.kr[k]; d.kt[k] = m.kt[k]; d.metal_eta[k] = m.metal_eta[k]; d.metal_k[k] = m.metal_k[k]; }

@@ -200,7 +200,7 @@ struct DLight {
 };
 
 enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u,
-                           kMicrofacetTransmission = 6u };
+                           kMicrofacetTransmission = 6u, kFresnelBlend = 7u };
 struct Lobe {
     unsigned kind, type;
     rgb3 r, t;              // conductor: t = eta
@@ -232,7 +232,7 @@ PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags
 template <int CLS>
 PB2_HD constexpr bool may_be(unsigned kind) {
     return CLS < 0 || (CLS == 0 && kind == kLambert) ||
-           (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor || kind == kMicrofacetTransmission)) ||
+           (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor || kind == kMicrofacetTransmission || kind == kFresnelBlend)) ||
            (CLS == 2 && (kind == kFresnelSpecular || kind == kSpecularReflection));
 }
 template <int CLS>
@@ -264,6 +264,18 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
         } else fr = gray(fresnel_dielectric(c, l.eta_a, l.eta_b));
         return l.r * tr_d(l.alpha, wh) * tr_g(l.alpha, wo, wi) * fr / (4.0f * ci * co);
     }
+    if (may_be<CLS>(kFresnelBlend) && l.kind == kFresnelBlend) {                          // reflection.rs:1224-1240 (r = Rd, t = Rs)
+        const float ai = 1.0f - 0.5f * abs_cos_t(wi), ao = 1.0f - 0.5f * abs_cos_t(wo);
+        const rgb3 diffuse = gray(28.0f / (23.0f * PB2_PI)) * l.r * (gray(1.0f) + l.t * -1.0f) * (1.0f - (ai * ai) * (ai * ai) * ai) *
+                             (1.0f - (ao * ao) * (ao * ao) * ao);
+        vec3 wh = wi + wo;
+        if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return gray(0.0f);
+        wh = unit(wh);
+        const float c = 1.0f - dot3(wi, wh);
+        const rgb3 schlick = l.t + (gray(1.0f) + l.t * -1.0f) * ((c * c) * (c * c) * c);  // schlick_fresnel :1212-1215
+        const rgb3 specular = schlick * (tr_d(l.alpha, wh) / ((4.0f * fabsf(dot3(wi, wh))) * fmaxf(abs_cos_t(wi), abs_cos_t(wo))));
+        return diffuse + specular;
+    }
     if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1093-1136, TransportMode::Radiance
         if (same_side(wo, wi)) return gray(0.0f);
         const float cto = cos_t(wo), cti = cos_t(wi);
@@ -288,6 +300,12 @@ PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
         if (!same_side(wo, wi)) return 0.0f;
         const vec3 wh = unit(wo + wi);
         return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+    }
+    if (may_be<CLS>(kFresnelBlend) && l.kind == kFresnelBlend) {                          // reflection.rs:1267-1275
+        if (!same_side(wo, wi)) return 0.0f;
+        const vec3 wh = unit(wo + wi);
+        const float pdf_wh = tr_pdf(l.alpha, wo, wh);
+        return 0.5f * (abs_cos_t(wi) * (1.0f / PB2_PI) + pdf_wh / (4.0f * dot3(wo, wh)));
     }
     if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1170-1187, D62 FIX
         if (same_side(wo, wi)) return 0.0f;
@@ -320,6 +338,18 @@ PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, 
         *wi = mirror(wo, wh);                                   // D36 FIX
         if (!same_side(wo, *wi)) return gray(0.0f);
         *pdf = tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
+        return lobe_f<CLS>(l, wo, *wi);
+    }
+    if (may_be<CLS>(kFresnelBlend) && l.kind == kFresnelBlend) {                          // reflection.rs:1242-1265
+        if (u0 < 0.5f) {
+            *wi = cosine_hemisphere(fminf(PB2_ONE_MINUS_EPS, 2.0f * u0), u1);
+            if (wo.z < 0.0f) wi->z = wi->z * -1.0f;
+        } else {
+            const vec3 wh = tr_sample_wh(l.alpha, wo, fminf(PB2_ONE_MINUS_EPS, 2.0f * (u0 - 0.5f)), u1);
+            *wi = mirror(wo, wh);
+            if (!same_side(wo, *wi)) return gray(0.0f);
+        }
+        *pdf = lobe_pdf<CLS>(l, wo, *wi);
         return lobe_f<CLS>(l, wo, *wi);
     }
     if (may_be<CLS>(kMicrofacetTransmission) && l.kind == kMicrofacetTransmission) {      // reflection.rs:1138-1168
@@ -484,6 +514,12 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, 
         if (!black(kt)) {
             Lobe& l = b.lobes[b.n++];
             l.kind = kMicrofacetTransmission; l.type = kTransmission | kGlossy; l.r = zero; l.t = kt; l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = m.eta; l.k = zero;
+        }
+    } else if (type == 5) {                                    // SubstrateMaterial: FresnelBlend(Kd, Ks, TrowbridgeReitz)
+        if (!black(kd) || !black(ks)) {
+            Lobe& l = b.lobes[0];
+            b.n = 1;
+            l.kind = kFresnelBlend; l.type = kReflection | kGlossy; l.r = kd; l.t = ks; l.alpha = m.alpha; l.eta_a = 1.0f; l.eta_b = 1.0f; l.k = zero;
         }
     } else if (type == 4) {                                    // MetalMaterial: MicrofacetReflection(1, TrowbridgeReitz, FresnelConductor(1, eta, k))
         Lobe& l = b.lobes[0];

@@ -262,7 +262,7 @@ def scene_materials(n_theta=32, n_phi=64):
     mats[5] = dict(type="mirror", kr=(0.9, 0.9, 0.9))
     mats += [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5, roughness=0.2, remap=True),      # frosted
              dict(type="plastic", kd=(0.25, 0.35, 0.25), ks=(0.3, 0.3, 0.3), roughness=0.1, remap=True)]
-    mats[0] = dict(mats[0])
+    mats[2] = dict(type="substrate", kd=(0.14, 0.45, 0.091), ks=(0.04, 0.04, 0.04), roughness=0.05, remap=True)   # the green wall, lacquered
     mats.append(dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5))                                 # smooth
     tm = np.array(tm, dtype=np.uint32)
     tm[tm == 7] = np.where(np.arange((tm == 7).sum()) % 2 == 0, 7, 8)          # half of the plastic ball's triangles are smooth glass

@@ -10,7 +10,7 @@ pub struct pb2_ray { pub o: [f32; 3], pub t_max: f32, pub d: [f32; 3], pub time:
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct pb2_hit { pub prim_id: u32, pub t: f32, pub b1: f32, pub b2: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct pb2_material { pub ty: i32, pub kd: [f32; 3], pub ks: [f32; 3], pub roughness: f32, pub remap_roughness: i32,
+pub struct pb2_material { pub ty: i32 /* 0 matte, 1 plastic, 2 glass, 3 mirror, 4 metal, 5 substrate */, pub kd: [f32; 3], pub ks: [f32; 3], pub roughness: f32, pub remap_roughness: i32,
                           pub kr: [f32; 3], pub kt: [f32; 3], pub eta: f32,
                           pub sigma: f32 /* matte: Oren-Nayar, degrees */, pub metal_eta: [f32; 3], pub metal_k: [f32; 3] }
 #[repr(C)] #[derive(Clone, Copy, Default)]
