@@ -609,7 +609,8 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
             const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.sn, v.sdpdu);
             PathSampler rng;
             rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot], TABLES ? (state >> 17) & 0x3FFFu : 0u);
-            if (bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
+            // (class 2 holds specular lobes only — FresnelSpecular, SpecularReflection — so estimate_direct is never reached there)
+            if (MAT != 2 && bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
                 float pick_pdf;
                 const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next1<TABLES>(), &pick_pdf);
                 if (pick_pdf != 0.0f) {
