@@ -69,14 +69,25 @@ __global__ void __launch_bounds__(256) k_tri_bounds(const float* __restrict__ ve
         lo[i] = make_float4(l[0], l[1], l[2], 0.f);
         hi[i] = make_float4(h[0], h[1], h[2], 0.f);
     }
-    // centroid bounds: warp reduce, one atomic per warp and component
+    // centroid bounds: warp reduce, then one atomic per CTA and component (one per warp serialised ~240 K same-address atomics
+    // in L2 for 1.3 M triangles: 160 us at 4 % issue utilisation in ncu)
+    __shared__ uint32_t s_mn[3][8], s_mx[3][8];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int k = 0; k < 3; ++k) {
         uint32_t mn = live ? f_enc(c[k]) : 0xFFFFFFFFu, mx = live ? f_enc(c[k]) : 0u;
         for (int o = 16; o > 0; o >>= 1) {
             mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
             mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         }
-        if ((threadIdx.x & 31u) == 0u) { atomicMin(&cb[k], mn); atomicMax(&cb[3 + k], mx); }
+        if (lane == 0u) { s_mn[k][warp] = mn; s_mx[k][warp] = mx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3u) {
+        const int k = (int)threadIdx.x;
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        for (int w = 0; w < 8; ++w) { mn = min(mn, s_mn[k][w]); mx = max(mx, s_mx[k][w]); }
+        atomicMin(&cb[k], mn);
+        atomicMax(&cb[3 + k], mx);
     }
 }
 
