@@ -44,7 +44,7 @@ typedef struct pb2_hit {
     float b2;
 } pb2_hit;
 
-/* pbrt-v3 matte / plastic / glass / mirror / metal over the reference's BxDF blocks (the reference's src/materials/*.rs are
+/* pbrt-v3 matte / plastic / glass / mirror / metal over the reference's BxDF blocks (the reference's src/materials/ files are
  * empty files): LambertianReflection or OrenNayar (reflection.rs:821-855, 917-971), MicrofacetReflection +
  * TrowbridgeReitz + FresnelDielectric / FresnelConductor (:977-1056, :571-604, :42-69), FresnelSpecular (:733-819),
  * SpecularReflection + FresnelNoOp (:606-659), MicrofacetTransmission (:1058-1192), FresnelBlend (:1194-1280; substrate: kd, ks, roughness). */
@@ -105,7 +105,12 @@ typedef struct pb2_film_desc {
     float max_sample_luminance; /* FilmTile::add_sample clamp (film.rs:259-261); <= 0 means infinity */
 } pb2_film_desc;
 
-enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1 };
+/* create_light_sample_distribution (src/core/lightdistrib.rs:222-232): "uniform", "power", "spatial".  PB2_LIGHTS_SPATIAL is
+ * SpatialLightDistribution (lightdistrib.rs:71-220): one Distribution1D per voxel of a grid over the world bound (64 voxels
+ * along its longest axis), each from 128 Halton points x every light's sample_li.  The reference fills voxels lazily into a
+ * hash table; this backend fills the whole grid on the device the first time a render asks for it (k_spatial_contrib,
+ * k_spatial_distrib) — the same distributions, so the same paths.  A scene with one light uses "uniform" (:223). */
+enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1, PB2_LIGHTS_SPATIAL = 2 };
 /* PB2_SAMPLER_RANDOM: RandomSampler (src/samplers/random.rs), one PCG32 stream per (pixel, sample).
  * PB2_SAMPLER_HALTON: HaltonSampler (src/samplers/halton.rs, src/core/lowdiscrepancy.rs:293-390) — every dimension is a pure
  * function of (pixel, sample index, dimension), so the per-sample values equal the reference's tile-ordered render. */
@@ -236,6 +241,10 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
 /* Per-sample radiance of PathIntegrator::li for explicit (pixel, sample) pairs — parity hook.  host arrays. */
 int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, const uint32_t* pixel_xy,
                 const uint32_t* sample_index, uint64_t n, float* L_rgb, float* p_film);
+/* SpatialLightDistribution probe (lightdistrib.rs:83-158): builds the voxel grid if needed and returns its extents; when
+ * non-null, func receives every voxel's Distribution1D func ([voxel][n_lights], voxel = (z * ny + y) * nx + x), cdf its cdf
+ * ([voxel][n_lights + 1]) and func_int its integral ([voxel]).  Host arrays. */
+int pb2_spatial_light_distribution(pb2_scene* scene, int32_t n_voxels[3], float* func, float* cdf, float* func_int);
 /* Counters of the last pb2_render_path call: {camera_samples, extend_rays, shadow_rays, mis_rays, kernel_launches}. */
 int pb2_render_counters(pb2_scene* scene, uint64_t out[8]);
 

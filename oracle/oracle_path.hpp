@@ -12,7 +12,10 @@
 
 #include <atomic>
 #include <chrono>
+#include <memory>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 namespace orc {
 
@@ -87,7 +90,7 @@ struct FilmDesc {
     Float crop_window[4];        // {min.x, min.y, max.x, max.y} (film.rs:33,41-50); all zero = {0, 0, 1, 1}
     Float max_sample_luminance;  // film.rs:27; <= 0 = infinity
 };
-enum { LIGHTS_UNIFORM = 0, LIGHTS_POWER = 1 };
+enum { LIGHTS_UNIFORM = 0, LIGHTS_POWER = 1, LIGHTS_SPATIAL = 2 };
 struct PathDesc {
     int32_t max_depth;
     Float rr_threshold;
@@ -130,6 +133,28 @@ struct Distribution1D {
         return (size_t)off;
     }
 };
+
+// lowdiscrepancy.rs:322-331 radical_inverse for the first five bases (2, 3, 5, 7, 11), as SpatialLightDistribution uses it
+// (lightdistrib.rs:128-142); the digit loop follows pbrt-v3 where the port's is broken (S1 below).
+inline Float radical_inverse_small(int base_index, uint64_t a) {
+    static const uint64_t kBases[5] = {2, 3, 5, 7, 11};
+    if (base_index == 0) {
+        uint64_t r = 0;
+        for (int i = 0; i < 64; ++i) r |= ((a >> i) & 1ull) << (63 - i);       // reverse_bits64, :364-369
+        return (Float)r * 5.4210108624275222e-20f;
+    }
+    const uint64_t base = kBases[base_index];
+    const Float inv_base = 1.0f / (Float)base;
+    uint64_t reversed = 0;
+    Float inv_base_n = 1.0f;
+    while (a != 0) {
+        const uint64_t next = a / base, digit = a - next * base;
+        reversed = reversed * base + digit;
+        inv_base_n *= inv_base;
+        a = next;
+    }
+    return fmin_((Float)reversed * inv_base_n, kOneMinusEpsilon);
+}
 
 // ---------------------------------------------------------------- reflection.rs
 enum : uint8_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
@@ -535,6 +560,37 @@ struct LightRt {
     }
 };
 
+// Light::sample_li without its VisibilityTester (point.rs:47-66, spot.rs:71-85, distant.rs:50-67, diffuse.rs:60-81 +
+// shape.rs:38-53 + triangle.rs:330-348): incident radiance and pdf at a bare point `p` — what SpatialLightDistribution
+// integrates per voxel (lightdistrib.rs:143-157).  Same operations, in the same order, as the head of estimate_direct.
+inline RGB light_sample_li(const LightRt& light, V3 p, Float ul0, Float ul1, Float* pdf_out) {
+    if (light.is_delta()) {
+        *pdf_out = 1.0f;
+        if (light.d.type == LIGHT_DISTANT) return light.l();
+        const V3 pl{light.d.p[0], light.d.p[1], light.d.p[2]};
+        const V3 wi = normalize(pl - p);
+        if (light.d.type == LIGHT_SPOT) return light.l() * light.falloff(-wi) / length_squared(pl - p);
+        return light.l() / length_squared(pl - p);
+    }
+    Float su0 = std::sqrt(ul0);
+    Float b0 = 1.0f - su0, b1 = ul1 * su0;
+    V3 ps = (light.p0 * b0 + light.p1 * b1) + light.p2 * ((1.0f - b0) - b1);
+    V3 ns = normalize(cross(light.p1 - light.p0, light.p2 - light.p0));
+    if (light.has_n) ns = faceforward(ns, (light.n0 * b0 + light.n1 * b1) + light.n2 * ((1.0f - b0) - b1));
+    Float pdf = 1.0f / light.area;
+    V3 w = ps - p;
+    if (length_squared(w) == 0.0f) pdf = 0.0f;
+    else {
+        w = normalize(w);
+        pdf *= length_squared(p - ps) / std::fabs(dot(ns, -w));
+        if (std::isinf(pdf)) pdf = 0.0f;
+    }
+    *pdf_out = pdf;
+    if (pdf == 0.0f || length_squared(ps - p) == 0.0f) { *pdf_out = 0.0f; return rgb(0); }
+    const V3 wi = normalize(ps - p);
+    return (light.d.two_sided || dot(ns, -wi) > 0.0f) ? light.l() : rgb(0);                   // D55 FIX
+}
+
 struct MaterialRt {
     MaterialDesc d;
     Float alpha;        // plastic, metal: roughness (remapped) — host-side, microfacet.rs:160-168
@@ -609,6 +665,9 @@ public:
     }
     // lightdistrib.rs:222-232 + integrator.rs:268-277
     void set_light_strategy(int strategy) {
+        light_strategy = strategy;
+        spatial_on = strategy == LIGHTS_SPATIAL && lights.size() != 1;                          // :223: one light -> uniform
+        if (spatial_on) init_spatial(64);
         std::vector<Float> f(lights.size(), 1.0f);
         if (strategy == LIGHTS_POWER && lights.size() != 1)
             for (size_t i = 0; i < lights.size(); ++i) {
@@ -621,6 +680,78 @@ public:
                 f[i] = y_value(power);
             }
         light_distrib.init(f);
+    }
+
+    // ---- SpatialLightDistribution (lightdistrib.rs:71-220), selected by "spatial" when the scene has more than one light --------
+    //   D63 FIX  :115-119 `pi as Float + 1.0 / n_voxel` -> (pi + 1) / n_voxel (pbrt-v3: the voxel's far corner)
+    // The reference fills a lock-free hash table lazily (:166-219); which entry a voxel lands in cannot change a result, so the
+    // restatement keeps a mutex-protected map from the packed voxel position to its distribution.
+    int light_strategy = LIGHTS_UNIFORM;
+    bool spatial_on = false;
+    int n_voxel[3] = {1, 1, 1};
+    mutable std::mutex spatial_mu;
+    mutable std::unordered_map<uint64_t, std::unique_ptr<Distribution1D>> spatial_map;
+    static int float_as_usize(Float r) { return std::isnan(r) || r <= 0.0f ? 0 : (r >= 1.0e9f ? 1000000000 : (int)r); }   // Rust `as usize`: saturating
+    void init_spatial(int max_voxels) {                                                        // :83-105
+        const Bounds3 b = bvh.world_bound();
+        const V3 diag = b.mx - b.mn;
+        const Float b_max = diag[max_dimension(diag)];
+        for (int i = 0; i < 3; ++i) n_voxel[i] = std::max(1, float_as_usize(std::round(diag[i] / b_max * (Float)max_voxels)));
+        spatial_map.clear();
+    }
+    static V3 bounds_lerp(const Bounds3& b, V3 t) {                                            // geometry.rs:454-458 + pbrt.rs:224-226
+        return {(1.0f - t.x) * b.mn.x + t.x * b.mx.x, (1.0f - t.y) * b.mn.y + t.y * b.mx.y, (1.0f - t.z) * b.mn.z + t.z * b.mx.z};
+    }
+    void spatial_contrib(const int pi[3], std::vector<Float>* contrib) const {                 // :107-158
+        const Bounds3 wb = bvh.world_bound();
+        const V3 p0{(Float)pi[0] / (Float)n_voxel[0], (Float)pi[1] / (Float)n_voxel[1], (Float)pi[2] / (Float)n_voxel[2]};
+        const V3 p1{(Float)(pi[0] + 1) / (Float)n_voxel[0], (Float)(pi[1] + 1) / (Float)n_voxel[1], (Float)(pi[2] + 1) / (Float)n_voxel[2]};   // D63 FIX
+        const V3 c0 = bounds_lerp(wb, p0), c1 = bounds_lerp(wb, p1);
+        const Bounds3 vb{vmin(c0, c1), vmax(c0, c1)};                                          // geometry.rs:549-559
+        const int n_samples = 128;
+        contrib->assign(lights.size(), 0.0f);
+        for (int i = 0; i < n_samples; ++i) {
+            const V3 po = bounds_lerp(vb, V3{radical_inverse_small(0, i), radical_inverse_small(1, i), radical_inverse_small(2, i)});
+            const Float u0 = radical_inverse_small(3, i), u1 = radical_inverse_small(4, i);
+            for (size_t j = 0; j < lights.size(); ++j) {
+                Float pdf = 0.0f;
+                const RGB li = light_sample_li(lights[j], po, u0, u1, &pdf);
+                if (pdf > 0.0f) (*contrib)[j] += y_value(li) / pdf;
+            }
+        }
+        Float sum_contrib = 0.0f;
+        for (Float c : *contrib) sum_contrib += c;
+        const Float avg_contrib = sum_contrib / (Float)((size_t)n_samples * contrib->size());
+        const Float min_contrib = avg_contrib > 0.0f ? 0.001f * avg_contrib : 1.0f;
+        for (Float& c : *contrib) c = fmax_(min_contrib, c);
+    }
+    void voxel_of(V3 p, int pi[3]) const {                                                     // :165-175 + geometry.rs:460-467
+        const Bounds3 wb = bvh.world_bound();
+        V3 o = p - wb.mn;
+        if (wb.mx.x > wb.mn.x) o.x /= wb.mx.x - wb.mn.x;
+        if (wb.mx.y > wb.mn.y) o.y /= wb.mx.y - wb.mn.y;
+        if (wb.mx.z > wb.mn.z) o.z /= wb.mx.z - wb.mn.z;
+        for (int i = 0; i < 3; ++i) {
+            const Float f = o[i] * (Float)n_voxel[i];
+            const int v = std::isnan(f) ? 0 : (f >= 2147483648.0f ? 2147483647 : (f <= -2147483648.0f ? -2147483647 - 1 : (int)f));   // Rust `as i32`
+            pi[i] = std::min(std::max(v, 0), n_voxel[i] - 1);
+        }
+    }
+    // LightDistribution::lookup (lightdistrib.rs:22-24, :41-43, :63-65, :160-219)
+    const Distribution1D& lookup(V3 p) const {
+        if (!spatial_on) return light_distrib;
+        int pi[3];
+        voxel_of(p, pi);
+        const uint64_t packed = ((uint64_t)pi[0] << 40) | ((uint64_t)pi[1] << 20) | (uint64_t)pi[2];
+        std::lock_guard<std::mutex> lock(spatial_mu);
+        std::unique_ptr<Distribution1D>& e = spatial_map[packed];
+        if (!e) {
+            std::vector<Float> contrib;
+            spatial_contrib(pi, &contrib);
+            e.reset(new Distribution1D());
+            e->init(contrib);
+        }
+        return *e;
     }
 
     // Scene::intersect -> SurfaceInteraction (triangle.rs:182-250; D59: shading = geometric)
@@ -1052,7 +1183,7 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
 inline RGB uniform_sample_one_light(const Scene& scene, const SurfaceInteraction& it, const BSDF& bsdf, Sampler& s) {
     if (scene.lights.empty()) return rgb(0);
     Float light_pdf;
-    size_t num = scene.light_distrib.sample_discrete(s.get_1d(), &light_pdf);
+    size_t num = scene.lookup(it.p).sample_discrete(s.get_1d(), &light_pdf);                  // path.rs:100-104
     if (light_pdf == 0.0f) return rgb(0);
     Float ul0, ul1, us0, us1;
     s.get_2d(&ul0, &ul1);

@@ -40,7 +40,7 @@ class PathDesc(C.Structure):
 
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4, "substrate": 5}
-_STRAT = {"uniform": 0, "power": 1}
+_STRAT = {"uniform": 0, "power": 1, "spatial": 2}
 _FILTER = {"box": 0, "gaussian": 1, "triangle": 2, "mitchell": 3, "sinc": 4}
 
 
@@ -197,6 +197,26 @@ class Scene:
             out = np.zeros(film_shape(fd) + (4,), dtype=np.float32)
         dt = O.lib().orc_render(self.h, C.byref(cd), C.byref(fd), C.byref(path), mode, threads, _p(out))
         return out, dt
+
+    # SpatialLightDistribution probes (lightdistrib.rs:71-220)
+    def spatial_grid(self):
+        """Voxels per axis of the "spatial" light distribution (selects that strategy on the scene)."""
+        nv = np.zeros(3, np.int32)
+        O.lib().orc_spatial_grid(C.c_void_p(self.h), _p(nv))
+        return tuple(int(v) for v in nv)
+
+    def spatial_voxel(self, pi, n_lights):
+        """(func [n_lights], cdf [n_lights + 1], func_int) of voxel pi = (x, y, z); call spatial_grid() first."""
+        func = np.zeros(n_lights, np.float32)
+        cdf = np.zeros(n_lights + 1, np.float32)
+        fi = C.c_float()
+        O.lib().orc_spatial_voxel(C.c_void_p(self.h), _p(np.asarray(pi, np.int32)), _p(func), _p(cdf), C.byref(fi))
+        return func, cdf, np.float32(fi.value)
+
+    def spatial_voxel_of(self, p):
+        pi = np.zeros(3, np.int32)
+        O.lib().orc_spatial_voxel_of(C.c_void_p(self.h), _p(np.asarray(p, np.float32)), _p(pi))
+        return tuple(int(v) for v in pi)
 
     def path_li(self, cam, film, path, pixel_xy, sample_index):
         pixel_xy = np.ascontiguousarray(pixel_xy, dtype=np.int32).reshape(-1, 2)

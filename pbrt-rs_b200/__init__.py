@@ -22,7 +22,7 @@ NODE_DTYPE = np.dtype([("bounds", np.float32, 6), ("offset", np.uint32), ("n_pri
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_MIRROR, MAT_METAL, MAT_SUBSTRATE = 0, 1, 2, 3, 4, 5
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN, FILTER_TRIANGLE, FILTER_MITCHELL, FILTER_SINC = 0, 1, 2, 3, 4
-LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 
 
 class Pb2Error(RuntimeError):
@@ -199,7 +199,7 @@ def lib():
         "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_device_ptr": [vp, vp, vp],
         "pb2_film_write_image": [vp, C.c_char_p, f32],
         "pb2_render_path": [vp, vp, vp, vp, vp], "pb2_path_li": [vp, vp, vp, vp, vp, u64, vp, vp],
-        "pb2_render_counters": [vp, vp],
+        "pb2_render_counters": [vp, vp], "pb2_spatial_light_distribution": [vp, vp, vp, vp, vp],
         "pb2_nccl_unique_id": [vp], "pb2_nccl_init": [vp, i32, i32], "pb2_nccl_shutdown": [],
         "pb2_film_reduce": [vp, i32, vp],
     }
@@ -279,6 +279,7 @@ class Scene:
         verts = _f32(verts).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         self.n_tris = len(idx)
+        self.n_lights = len(lights) if lights else 0
         tm = None if tri_material is None else np.ascontiguousarray(tri_material, dtype=np.uint32)
         mats = (Material * len(materials))(*materials) if materials else None
         lts = (Light * len(lights))(*lights) if lights else None
@@ -321,6 +322,21 @@ class BVHAccel:
         out = np.empty(6, dtype=np.float32)
         check(lib().pb2_world_bound(self.h, _p(out)))
         return out
+
+    def spatial_light_distribution(self, tables=True):
+        """SpatialLightDistribution (src/core/lightdistrib.rs:71-220) of the scene: (n_voxels (x, y, z), func [z, y, x, n_lights],
+        cdf [z, y, x, n_lights + 1], func_int [z, y, x]); tables=False returns only the grid extents."""
+        nv = np.zeros(3, dtype=np.int32)
+        check(lib().pb2_spatial_light_distribution(self.h, _p(nv), None, None, None))
+        if not tables:
+            return tuple(int(v) for v in nv)
+        n = self.scene.n_lights
+        shape = (int(nv[2]), int(nv[1]), int(nv[0]))
+        func = np.empty(shape + (n,), dtype=np.float32)
+        cdf = np.empty(shape + (n + 1,), dtype=np.float32)
+        func_int = np.empty(shape, dtype=np.float32)
+        check(lib().pb2_spatial_light_distribution(self.h, _p(nv), _p(func), _p(cdf), _p(func_int)))
+        return tuple(int(v) for v in nv), func, cdf, func_int
 
     def build_stats(self):
         """HLBVH stage times in ms: upload + bounds + Morton, sort, treelets, upper SAH (host), flatten, device-layout repack."""
@@ -395,7 +411,7 @@ class PerspectiveCamera:
 
 
 _MAT = {"matte": MAT_MATTE, "plastic": MAT_PLASTIC, "glass": MAT_GLASS, "mirror": MAT_MIRROR, "metal": MAT_METAL, "substrate": MAT_SUBSTRATE}
-_STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER}
+_STRATEGY = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER, "spatial": LIGHTS_SPATIAL}
 _FILTER = {"box": FILTER_BOX, "gaussian": FILTER_GAUSSIAN, "triangle": FILTER_TRIANGLE, "mitchell": FILTER_MITCHELL, "sinc": FILTER_SINC}
 
 

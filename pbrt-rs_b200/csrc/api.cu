@@ -52,6 +52,8 @@ void pb2_scene::free_device() {
     if (d_materials) cudaFree(d_materials);
     if (d_lights) cudaFree(d_lights);
     if (d_light_cdf) cudaFree(d_light_cdf);
+    if (d_spatial) cudaFree(d_spatial);
+    d_spatial = nullptr;
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
     if (d_indices) cudaFree(d_indices);

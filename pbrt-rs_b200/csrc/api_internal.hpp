@@ -90,6 +90,10 @@ struct pb2_scene {
     // Distribution1D of the light-selection strategies: [0] uniform, [1] power (lightdistrib.rs:26-69)
     std::vector<float> light_func[2], light_cdf[2];
     float light_func_int[2] = {0.0f, 0.0f};
+    // SpatialLightDistribution tables (lightdistrib.rs:71-220), filled on the device the first time "spatial" is asked for:
+    // [func n_vox * n | cdf n_vox * (n + 1) | func_int n_vox] floats in one allocation
+    void* d_spatial = nullptr;
+    int spatial_nv[3] = {0, 0, 0};
     pb2::SceneView view;
     pb2::Pipe pipe;
     pb2::Wavefront* wf = nullptr;

@@ -165,6 +165,44 @@ int upload_shading_tables(pb2_scene* scene) {
     return PB2_OK;
 }
 
+// SpatialLightDistribution::new + every voxel's compute_distribution (lightdistrib.rs:83-158); scene->mu is held.
+static constexpr uint64_t kSpatialMaxBytes = 16ull << 30;
+static SpatialView spatial_view(const pb2_scene* s) {
+    SpatialView g;
+    const size_t n = s->lights.size();
+    const size_t n_vox = (size_t)s->spatial_nv[0] * s->spatial_nv[1] * s->spatial_nv[2];
+    const float* base = (const float*)s->d_spatial;
+    g.func = base;
+    g.cdf = base + n_vox * n;
+    g.func_int = base + n_vox * n + n_vox * (n + 1);
+    for (int i = 0; i < 3; ++i) { g.nv[i] = s->spatial_nv[i]; g.lo[i] = s->root_bounds[i]; g.hi[i] = s->root_bounds[3 + i]; }
+    return g;
+}
+static int ensure_spatial(pb2_scene* scene, cudaStream_t st) {
+    if (scene->d_spatial) return PB2_OK;
+    const size_t n = scene->lights.size();
+    if (n == 0) return set_error(PB2_ERR_STATE, "the scene has no lights");
+    int nv[3];
+    spatial_grid_extents(scene->root_bounds, 64, nv);
+    const uint64_t n_vox = (uint64_t)nv[0] * nv[1] * nv[2];
+    const uint64_t bytes = (n_vox * n + n_vox * (n + 1) + n_vox) * sizeof(float);
+    if (bytes > kSpatialMaxBytes)
+        return set_error(PB2_ERR_INVALID, "spatial light distribution: %llu voxels x %zu lights need %.1f GB of tables (limit %.0f GB); use \"power\"",
+                         (unsigned long long)n_vox, n, bytes / 1e9, kSpatialMaxBytes / 1e9);
+    PB2_CUDA(cudaMalloc(&scene->d_spatial, bytes));
+    for (int i = 0; i < 3; ++i) scene->spatial_nv[i] = nv[i];
+    const SpatialView g = spatial_view(scene);
+    spatial_distribution_build(g, (const DLight*)scene->d_lights, (int)n, (float*)g.func, (float*)g.cdf, (float*)g.func_int, st);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(scene->d_spatial);
+        scene->d_spatial = nullptr;
+        return cuda_fail(e, "spatial_distribution_build", __FILE__, __LINE__);
+    }
+    return PB2_OK;
+}
+
 static ShadeView shade_view(const pb2_scene* s, int strategy) {
     ShadeView v;
     const size_t n = s->lights.size();
@@ -178,6 +216,8 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
     v.light_func = base + off;
     v.light_cdf = base + off + n;
     v.light_func_int = s->light_func_int[strategy == PB2_LIGHTS_POWER ? 1 : 0];
+    memset(&v.spatial, 0, sizeof v.spatial);
+    if (strategy == PB2_LIGHTS_SPATIAL && n > 1 && s->d_spatial) v.spatial = spatial_view(s);      // lightdistrib.rs:223: one light -> uniform
     v.indices = (const uint32_t*)s->d_indices;
     v.normals = (const float*)s->d_normals;
     v.tangents = (const float*)s->d_tangents;
@@ -192,7 +232,7 @@ static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_pa
     if (path->max_depth < 0 || path->max_depth > 65535) return set_error(PB2_ERR_INVALID, "max_depth out of range");
     if (path->spp <= 0 || path->sample_begin < 0 || path->sample_end > path->spp || path->sample_begin > path->sample_end)
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
-    if (path->light_strategy != PB2_LIGHTS_UNIFORM && path->light_strategy != PB2_LIGHTS_POWER)
+    if (path->light_strategy < PB2_LIGHTS_UNIFORM || path->light_strategy > PB2_LIGHTS_SPATIAL)
         return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
     if (path->sampler < PB2_SAMPLER_RANDOM || path->sampler > PB2_SAMPLER_ZEROTWO)
         return set_error(PB2_ERR_INVALID, "unknown sampler %d", path->sampler);
@@ -561,6 +601,10 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     SamplerView smp;
     rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
     if (rc) return rc;
+    if (path->light_strategy == PB2_LIGHTS_SPATIAL && scene->lights.size() > 1) {      // PathIntegrator::pre_process (path.rs:58-63)
+        rc = ensure_spatial(scene, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, path->sample_begin,
                      path->sample_end, (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
@@ -588,6 +632,10 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     SamplerView smp;
     rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, 0, &smp);
     if (rc) return rc;
+    if (path->light_strategy == PB2_LIGHTS_SPATIAL && scene->lights.size() > 1) {
+        rc = ensure_spatial(scene, 0);
+        if (rc) return rc;
+    }
     cudaError_t e = cudaMalloc(&d_xy, n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_s, n * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d_L, n * 12);
@@ -603,6 +651,22 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     if (e == cudaSuccess) e = cudaMemcpy(p_film, d_pf, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_xy); cudaFree(d_s); cudaFree(d_L); cudaFree(d_pf);
     if (e != cudaSuccess) return cuda_fail(e, "pb2_path_li", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+int pb2_spatial_light_distribution(pb2_scene* scene, int32_t n_voxels[3], float* func, float* cdf, float* func_int) {
+    if (!scene || !n_voxels) return set_error(PB2_ERR_INVALID, "null argument");
+    if (!scene->built) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
+    if (scene->tri_material.empty()) return set_error(PB2_ERR_STATE, "the scene was created without materials");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    int rc = ensure_spatial(scene, 0);
+    if (rc) return rc;
+    const SpatialView g = spatial_view(scene);
+    const size_t n = scene->lights.size(), n_vox = (size_t)g.nv[0] * g.nv[1] * g.nv[2];
+    for (int i = 0; i < 3; ++i) n_voxels[i] = g.nv[i];
+    if (func) PB2_CUDA(cudaMemcpy(func, g.func, n_vox * n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (cdf) PB2_CUDA(cudaMemcpy(cdf, g.cdf, n_vox * (n + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    if (func_int) PB2_CUDA(cudaMemcpy(func_int, g.func_int, n_vox * sizeof(float), cudaMemcpyDeviceToHost));
     return PB2_OK;
 }
 

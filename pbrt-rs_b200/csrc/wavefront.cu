@@ -612,7 +612,16 @@ __global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView 
             // (class 2 holds specular lobes only — FresnelSpecular, SpecularReflection — so estimate_direct is never reached there)
             if (MAT != 2 && bsdf_count(bsdf, kAllLobes & ~kSpecular) > 0 && sh.n_lights > 0) {      // path.rs:105-121, integrator.rs:99-134
                 float pick_pdf;
-                const int li = sample_discrete(sh.light_cdf, sh.light_func, sh.n_lights, sh.light_func_int, rng.next1<TABLES>(), &pick_pdf);
+                // light_distribution.lookup(&isect.p) (path.rs:100-104)
+                const float *l_cdf = sh.light_cdf, *l_func = sh.light_func;
+                float l_int = sh.light_func_int;
+                if (sh.spatial.func) {
+                    const size_t vox = spatial_voxel(sh.spatial, v.p);
+                    l_cdf = sh.spatial.cdf + vox * (size_t)(sh.n_lights + 1);
+                    l_func = sh.spatial.func + vox * (size_t)sh.n_lights;
+                    l_int = __ldg(sh.spatial.func_int + vox);
+                }
+                const int li = sample_discrete(l_cdf, l_func, sh.n_lights, l_int, rng.next1<TABLES>(), &pick_pdf);
                 if (pick_pdf != 0.0f) {
                     float ul0, ul1, us0, us1;
                     rng.next2<TABLES>(&ul0, &ul1);

@@ -14,6 +14,27 @@
 
 namespace pb2 {
 
+// SpatialLightDistribution (lightdistrib.rs:77-81) as filled by light_distrib.cu; func == nullptr: not selected.
+struct SpatialView {
+    const float* func;            // [voxel][n_lights], voxel = (z * nv[1] + y) * nv[0] + x
+    const float* cdf;             // [voxel][n_lights + 1]
+    const float* func_int;        // [voxel]
+    int nv[3];                    // n_voxel
+    float lo[3], hi[3];           // scene.world_bound()
+};
+// SpatialLightDistribution::lookup (lightdistrib.rs:165-175): Bounds3::offset (geometry.rs:460-467), `as i32` (saturating,
+// NaN -> 0: cvt.rzi.s32.f32 does the same), clamp to the grid.
+__device__ __forceinline__ size_t spatial_voxel(const SpatialView& g, vec3 p) {
+    float ox = p.x - g.lo[0], oy = p.y - g.lo[1], oz = p.z - g.lo[2];
+    if (g.hi[0] > g.lo[0]) ox = ox / (g.hi[0] - g.lo[0]);
+    if (g.hi[1] > g.lo[1]) oy = oy / (g.hi[1] - g.lo[1]);
+    if (g.hi[2] > g.lo[2]) oz = oz / (g.hi[2] - g.lo[2]);
+    const int ix = min(max(__float2int_rz(ox * (float)g.nv[0]), 0), g.nv[0] - 1);
+    const int iy = min(max(__float2int_rz(oy * (float)g.nv[1]), 0), g.nv[1] - 1);
+    const int iz = min(max(__float2int_rz(oz * (float)g.nv[2]), 0), g.nv[2] - 1);
+    return ((size_t)iz * (size_t)g.nv[1] + (size_t)iy) * (size_t)g.nv[0] + (size_t)ix;
+}
+
 // Device-side scene tables for shading (indexed by the caller's primitive id).
 struct ShadeView {
     const uint32_t* tri_material;
@@ -24,6 +45,7 @@ struct ShadeView {
     const float* light_func;      // Distribution1D func[n_lights]
     const float* light_cdf;       // cdf[n_lights + 1]
     float light_func_int;
+    SpatialView spatial;          // "spatial" strategy with more than one light: the vertex's voxel replaces the three above
     // TriangleMesh's optional attributes (triangle.rs:17-26), all null for a plain mesh
     const uint32_t* indices;      // 3 vertex ids per caller triangle
     const float* normals;         // 3 per vertex
@@ -130,6 +152,10 @@ int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
 // RNG::new(seq0 + pixel)).
 void pixel_tables_generate(int kind, uint32_t n_pix, int spp, int n_dims, int x_samples, int y_samples, int jitter, uint64_t seq0,
                            float* d_t1, float2* d_t2, cudaStream_t st);
+// SpatialLightDistribution (light_distrib.cu)
+void spatial_grid_extents(const float wb[6], int max_voxels, int nv[3]);
+void spatial_distribution_build(const SpatialView& grid, const DLight* d_lights, int n_lights, float* d_func, float* d_cdf, float* d_func_int,
+                                cudaStream_t st);
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
 void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st);

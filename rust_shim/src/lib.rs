@@ -109,3 +109,6 @@ impl Drop for B200Accel { fn drop(&mut self) { unsafe { pb2_scene_destroy(self.s
 //
 // impl pbrt::core::integrator::Integrator for B200PathIntegrator (src/core/integrator.rs:29-42):
 //   fn render(&mut self, scene: &Scene)           -> one pb2_render_path call, then pb2_film_read_xyzw -> Film::set_image
+//   light_sample_strategy (path.rs:43, lightdistrib.rs:222-232): "uniform" -> 0, "power" -> 1, "spatial" -> 2 in
+//                                                    pb2_path_desc.light_strategy; any other name panics in the reference and
+//                                                    is PB2_ERR_INVALID here

@@ -522,3 +522,61 @@ def test_no_device_memory_leak_over_scene_and_film_lifecycles(gpu, scenes):
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 << 20, f"{(free0 - free1) >> 20} MiB of device memory not returned"
+
+
+def test_spatial_light_distribution_bit_exact(gpu, OP, scenes):
+    """SpatialLightDistribution (lightdistrib.rs:71-220), PathIntegrator's "spatial" strategy.  The device fills every voxel
+    (k_spatial_contrib / k_spatial_distrib); the oracle computes voxels on demand like the reference's hash table.  Grid
+    extents, the func / cdf / func_int of sampled voxels (area, point, spot and distant lights), per-sample radiance and the
+    box-filtered film equal the oracle's bits."""
+    sc = scenes.scene_all_lights(n_theta=16, n_phi=32)
+    cam = dict(scenes.C4_CAMERA, res=(160, 90))
+    kw = dict(max_depth=6, rr_threshold=1.0, light_strategy="spatial", spp=8)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    n_lights = len(sc["lights"])
+    nv, func, cdf, func_int = accel.spatial_light_distribution()
+    assert nv == ref.spatial_grid() and max(nv) == 64
+    rng = np.random.default_rng(3)
+    picks = [(0, 0, 0), (nv[0] - 1, nv[1] - 1, nv[2] - 1)] + [tuple(int(rng.integers(0, n)) for n in nv) for _ in range(300)]
+    for pi in picks:
+        rf, rc, ri = ref.spatial_voxel(pi, n_lights)
+        z, y, x = pi[2], pi[1], pi[0]
+        assert np.array_equal(bits(func[z, y, x]), bits(rf)), (pi, func[z, y, x], rf)
+        assert np.array_equal(bits(cdf[z, y, x]), bits(rc)), (pi, cdf[z, y, x], rc)
+        assert bits(func_int[z, y, x]) == bits(ri)
+    assert np.isfinite(func).all() and (func > 0).all() and np.all(cdf[..., -1] == 1.0)
+    n = 20000
+    xy = np.stack([rng.integers(0, 160, n), rng.integers(0, 90, n)], axis=1)
+    s = rng.integers(0, 8, size=n)
+    L, pf = integ.li(xy, s)
+    pd = OP.path_desc(**kw)
+    rL, rpf = ref.path_li(cam, OP.film_desc(cam["res"]), pd, xy, s)
+    assert np.array_equal(bits(pf), bits(rpf))
+    mism = (bits(L) != bits(rL)).any(axis=1)
+    assert mism.sum() == 0, f"{mism.sum()} of {n} samples differ"
+    # the strategy changes which light a vertex picks: the radiance differs from "power" sample by sample, not on average
+    Lp, _ = gpu.PathIntegrator(accel, camera, **dict(kw, light_strategy="power")).li(xy, s)
+    assert (bits(L) != bits(Lp)).any(axis=1).mean() > 0.2
+    assert abs(L.mean() - Lp.mean()) / Lp.mean() < 0.1
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), pd, mode=1)
+    got = film.read_xyzw()
+    assert np.array_equal(bits(got), bits(want)), f"{(bits(got) != bits(want)).any(axis=2).sum()} pixels differ"
+
+
+def test_spatial_light_distribution_one_light_and_limits(gpu, OP, scenes):
+    """create_light_sample_distribution (lightdistrib.rs:222-232): one light -> the uniform distribution whatever the name; an
+    unknown strategy is an error, not a panic."""
+    cam = dict(scenes.C2_CAMERA, res=(64, 64))
+    sc = scenes.scene_c2()
+    sc["lights"] = sc["lights"][:1]
+    kw = dict(max_depth=4, rr_threshold=1.0, spp=4)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, light_strategy="spatial", **kw)
+    fa, fb = gpu.Film(cam["res"]), gpu.Film(cam["res"])
+    integ.render(fa)
+    gpu.PathIntegrator(accel, camera, light_strategy="uniform", **kw).render(fb)
+    assert np.array_equal(bits(fa.read_xyzw()), bits(fb.read_xyzw()))
+    integ.desc.light_strategy = 7
+    with pytest.raises(gpu.Pb2Error):
+        integ.render(fa)

@@ -315,3 +315,68 @@ def test_rough_glass(OP, scenes):
     assert abs(smooth[10:22, 10:22].mean() - 1.0) < 0.02
     nearly = render(dict(type="glass", kr=(1, 1, 1), kt=(1, 1, 1), eta=1.5, roughness=0.002, remap=False))
     assert abs(nearly[10:22, 10:22].mean() - smooth[10:22, 10:22].mean()) < 0.06
+
+
+def test_spatial_light_distribution(OP):
+    """SpatialLightDistribution (lightdistrib.rs:71-220).  Grid: 64 voxels along the longest axis of the world bound, the others
+    in proportion (:83-95).  One voxel's distribution, recomputed here in f32 numpy for two point lights over the 128 Halton
+    points (bases 2, 3, 5: known values 1/2, 1/3, 1/5 at index 1), equals the oracle's bits; the 0.1 % floor (:163-170) holds;
+    a voxel next to one light prefers it; the rendered mean agrees with the "uniform" strategy (the estimator stays unbiased)."""
+    f32 = np.float32
+    quad = np.array([(-50, 0, -50), (-50, 0, 50), (50, 0, 50), (50, 0, -50), (-50, 25, -50)], np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3], [0, 1, 4]], np.uint32)
+    la = dict(type="point", p=(-40.0, 5.0, -40.0), I=(100.0, 100.0, 100.0))
+    lb = dict(type="point", p=(40.0, 5.0, 40.0), I=(300.0, 200.0, 100.0))
+    sc = dict(verts=quad, idx=idx, tri_material=np.zeros(3, np.uint32), materials=[dict(type="matte", kd=(0.5, 0.5, 0.5))], lights=[la, lb])
+    s = OP.Scene(sc)
+    assert s.spatial_grid() == (64, 16, 64)                                   # extents 100 x 25 x 100
+    assert s.spatial_voxel_of((-50.0, 0.0, -50.0)) == (0, 0, 0) and s.spatial_voxel_of((50.0, 25.0, 50.0)) == (63, 15, 63)
+    assert s.spatial_voxel_of((1e9, -1e9, float("nan"))) == (63, 0, 0)        # `as i32` saturates, NaN -> 0, then clamp
+
+    def radical_inverse(base, i):
+        inv, inv_n, rev = f32(1.0) / f32(base), f32(1.0), 0
+        while i:
+            i, d = divmod(i, base)
+            rev = rev * base + d
+            inv_n = f32(inv_n * inv)
+        return min(f32(f32(rev) * inv_n), f32(1.0) - f32(2.0 ** -23))
+    assert [float(radical_inverse(b, 1)) for b in (2, 3, 5)] == [0.5, float(f32(1) / f32(3)), float(f32(1) / f32(5))]
+    pi = (5, 3, 60)
+    lo, hi = np.array((-50, 0, -50), f32), np.array((50, 25, 50), f32)
+    nv = np.array((64, 16, 64), f32)
+    lerp = lambda t, a, b: (f32(1) - t) * a + t * b
+    v0, v1 = lerp(np.array(pi, f32) / nv, lo, hi), lerp((np.array(pi, f32) + f32(1)) / nv, lo, hi)
+    contrib = np.zeros(2, f32)
+    for i in range(128):
+        t = np.array([radical_inverse(b, i) for b in (2, 3, 5)], f32)
+        po = lerp(t, np.minimum(v0, v1), np.maximum(v0, v1))
+        for j, l in enumerate((la, lb)):
+            d = np.array(l["p"], f32) - po
+            d2 = f32(f32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+            li = np.array(l["I"], f32) / d2
+            contrib[j] = contrib[j] + f32(f32(f32(0.212671) * li[0] + f32(0.715160) * li[1]) + f32(0.072169) * li[2])
+    func, cdf, func_int = s.spatial_voxel(pi, 2)
+    assert np.array_equal(func.view(np.uint32), contrib.view(np.uint32))
+    assert cdf[0] == 0.0 and cdf[2] == 1.0 and np.isclose(cdf[1], contrib[0] / contrib.sum(), rtol=1e-6)
+    assert np.isclose(func_int, contrib.sum() / 2, rtol=1e-6)
+    near_a, _, _ = s.spatial_voxel(s.spatial_voxel_of(la["p"]), 2)
+    near_b, _, _ = s.spatial_voxel(s.spatial_voxel_of(lb["p"]), 2)
+    assert near_a[0] > 20 * near_a[1] and near_b[1] > 20 * near_b[0]
+    # the floor: a spot light that cannot see the voxel still keeps 0.1 % of the voxel's average contribution
+    spot = dict(type="spot", p=(0, 10.0, 0), axis=(0, -1.0, 0), I=(200.0, 200.0, 200.0), total_width=10.0, falloff_start=5.0)
+    s2 = OP.Scene(dict(sc, lights=[la, spot]))
+    s2.spatial_grid()
+    f2, c2, _ = s2.spatial_voxel((60, 10, 60), 2)
+    assert f2[1] > 0 and np.isclose(f2[1], 0.001 * f2[0] / (128 * 2), rtol=1e-5)      # min_contrib = 0.001 * sum / (n_samples * n_lights)
+    # one light: "spatial" falls back to the uniform distribution (:223); several: same expectation as "uniform"
+    cam = dict(pos=(0, 40.0, 0), look=(0, 0, 0), up=(0, 0, 1), fov=90.0, res=(32, 32))
+    fd = OP.film_desc(cam["res"])
+    one = OP.Scene(dict(sc, lights=[la]))
+    a = one.render(cam, fd, OP.path_desc(max_depth=2, spp=4, light_strategy="spatial"))[0]
+    b = one.render(cam, fd, OP.path_desc(max_depth=2, spp=4, light_strategy="uniform"))[0]
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    a = OP.resolve_rgb(s.render(cam, fd, OP.path_desc(max_depth=2, spp=256, light_strategy="spatial"))[0])
+    b = OP.resolve_rgb(s.render(cam, fd, OP.path_desc(max_depth=2, spp=256, light_strategy="uniform"))[0])
+    assert abs(a.mean() - b.mean()) / b.mean() < 0.02
+    # importance sampling the nearer light lowers the variance under it
+    assert a[2:8, 2:8].std() < b[2:8, 2:8].std()
