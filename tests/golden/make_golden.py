@@ -1,0 +1,93 @@
+"""Generates the committed golden fixtures of tests/golden/ from the CPU oracle (TEST INFRASTRUCTURE).
+
+The reference (lazytiger/pbrt-rs) cannot be compiled or run (no Rust toolchain) and its tests hold no vector
+for this path, so these fixtures are outputs of oracle/ — the restatement of the reference's algorithm — frozen at the commit
+that introduced them.  They pin BOTH sides from then on: `-m "not gpu"` tests check the oracle still reproduces them, `-m gpu`
+tests check the CUDA path against the same bytes, so the two cannot drift together unnoticed.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+
+Inputs (meshes, rays, (pixel, sample) pairs) are stored in the fixtures, so no generator has to reproduce them bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def golden_scene(scenes):
+    """Cornell box with a glass tall block and a point light beside the quad area light: matte + specular shading classes,
+    three lights (two emissive triangles + one delta light) for the "power" / "spatial" strategies.  No libm on this path
+    (no roughness remap, no spot cone, box filter)."""
+    sc = scenes.cornell_box()
+    sc["materials"] = sc["materials"] + [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5)]
+    tm = sc["tri_material"].copy()
+    tm[-10:] = 3                                     # the tall block's ten triangles
+    sc["tri_material"] = tm
+    sc["lights"] = sc["lights"] + [dict(type="point", p=(100.0, 400.0, 100.0), I=(4.0e5, 5.0e5, 6.0e5))]
+    return sc
+
+
+GOLDEN_CAMERA = dict(pos=(278.0, 273.0, -800.0), look=(278.0, 273.0, 0.0), up=(0.0, 1.0, 0.0), fov=39.3, res=(48, 48))
+GOLDEN_PATH = dict(max_depth=6, rr_threshold=1.0, spp=4)
+
+
+def main():
+    ge.build()
+    orc, scenes = ge.load_oracle(), ge.load_scenes()
+    from oracle import oracle_path as OP
+    # ---- ray casting: BVHAccel::intersect / intersect_p, SAH build ------------------------------------------------------------
+    verts, idx = scenes.merge(scenes.uv_sphere(n_theta=20, n_phi=40), scenes.ground_grid())
+    cam = dict(scenes.C1_CAMERA, res=(64, 64))
+    rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    rng = np.random.default_rng(2026)
+    extra = np.zeros((4096, 8), np.float32)
+    extra[:, 0:3] = rng.uniform(-6, 6, (4096, 3))
+    extra[:, 3] = np.where(rng.random(4096) < 0.5, np.inf, rng.uniform(0.5, 8.0, 4096)).astype(np.float32)
+    extra[:, 4:7] = rng.normal(size=(4096, 3))
+    extra[::97, 4] = 0.0                              # axis-parallel rays: the literal one-level walk
+    rays = np.concatenate([np.asarray(rays, np.float32).reshape(-1, 8), extra])
+    bvh = orc.BVHAccel(verts, idx, 4)
+    hits, b0 = bvh.intersect(rays, want_b0=True)[:2]
+    occ = bvh.intersect_p(rays)[0]
+    nodes = bvh.nodes()
+    np.savez_compressed(os.path.join(HERE, "raycast.npz"), verts=np.asarray(verts, np.float32), idx=np.asarray(idx, np.uint32), rays=rays,
+                        prim_id=hits["prim_id"], t=hits["t"].view(np.uint32), b1=hits["b1"].view(np.uint32), b2=hits["b2"].view(np.uint32),
+                        b0=np.asarray(b0, np.float32).view(np.uint32), occluded=np.asarray(occ, np.uint8),
+                        nodes=np.frombuffer(np.ascontiguousarray(nodes).tobytes(), np.uint8), ordered_prims=bvh.ordered_prims(),
+                        world_bound=np.asarray(bvh.world_bound(), np.float32))
+    # ---- path tracing: PathIntegrator::li per (pixel, sample), film, SpatialLightDistribution ----------------------------------
+    sc = golden_scene(scenes)
+    ref = OP.Scene(sc, 4)
+    fd = OP.film_desc(GOLDEN_CAMERA["res"])
+    n = 2048
+    xy = np.stack([rng.integers(0, 48, n), rng.integers(0, 48, n)], axis=1).astype(np.int32)
+    s = rng.integers(0, 4, n).astype(np.uint32)
+    out = dict(xy=xy, sample=s)
+    for strat in ("uniform", "power", "spatial"):
+        L, pf = ref.path_li(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy=strat, **GOLDEN_PATH), xy, s)
+        out["L_" + strat] = L.view(np.uint32)
+        out["p_film"] = pf.view(np.uint32)
+    for sampler, skw in (("halton", {}), ("stratified", dict(x_samples=2, y_samples=2)), ("zerotwo", {})):
+        L, _ = ref.path_li(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", sampler=sampler, **GOLDEN_PATH, **skw), xy, s)
+        out["L_" + sampler] = L.view(np.uint32)
+    film, _ = ref.render(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="spatial", **GOLDEN_PATH), mode=1)
+    out["film_spatial"] = film.view(np.uint32)
+    nv = ref.spatial_grid()
+    out["spatial_grid"] = np.asarray(nv, np.int32)
+    vox = np.stack([rng.integers(0, nv[0], 64), rng.integers(0, nv[1], 64), rng.integers(0, nv[2], 64)], axis=1).astype(np.int32)
+    out["spatial_voxels"] = vox
+    out["spatial_func"] = np.stack([ref.spatial_voxel(v, 3)[0] for v in vox]).view(np.uint32)
+    out["spatial_cdf"] = np.stack([ref.spatial_voxel(v, 3)[1] for v in vox]).view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "path.npz"), **out)
+    for f in ("raycast.npz", "path.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
