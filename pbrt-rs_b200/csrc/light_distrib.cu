@@ -69,14 +69,16 @@ __device__ __forceinline__ vec3 bounds_lerp(vec3 lo, vec3 hi, vec3 t) {
     return mk((1.0f - t.x) * lo.x + t.x * hi.x, (1.0f - t.y) * lo.y + t.y * hi.y, (1.0f - t.z) * lo.z + t.z * hi.z);
 }
 
-// compute_distribution (lightdistrib.rs:107-158), the per-light sums: thread = (voxel, light).
+// compute_distribution (lightdistrib.rs:107-158), the per-light sums: thread = (light, voxel).
 __global__ void __launch_bounds__(128) k_spatial_contrib(SpatialView g, const DLight* __restrict__ lights, int n_lights, SpatialSamples smp,
                                                          float* __restrict__ func) {
     const size_t n_vox = (size_t)g.nv[0] * g.nv[1] * g.nv[2];
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_vox * (size_t)n_lights) return;
-    const size_t vox = idx / (size_t)n_lights;
-    const int j = (int)(idx - vox * (size_t)n_lights);
+    // light-major thread order: a warp integrates one light over 32 neighbouring voxels, so the light-type branches of
+    // sample_li stay uniform (voxel-major ran 12 of 32 lanes with the four light kinds side by side)
+    const int j = (int)(idx / n_vox);
+    const size_t vox = idx - (size_t)j * n_vox;
     const int px = (int)(vox % (size_t)g.nv[0]), py = (int)((vox / (size_t)g.nv[0]) % (size_t)g.nv[1]),
               pz = (int)(vox / ((size_t)g.nv[0] * g.nv[1]));
     const vec3 lo = mk(g.lo[0], g.lo[1], g.lo[2]), hi = mk(g.hi[0], g.hi[1], g.hi[2]);
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(SpatialView g, const DL
         const rgb3 li = light_sample_li(light, po, smp.v[3][i], smp.v[4][i], &pdf);
         if (pdf > 0.0f) contrib = contrib + luminance(li) / pdf;
     }
-    func[idx] = contrib;
+    func[vox * (size_t)n_lights + (size_t)j] = contrib;
 }
 
 // The rest of compute_distribution (:159-172) and Distribution1D::new (sampling.rs:76-98, D29 FIX): thread = voxel.

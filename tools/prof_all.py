@@ -46,6 +46,11 @@ def main():
         integ = pb2.PathIntegrator(accel, camera4, max_depth=8, light_strategy="power", spp=16, sampler=sampler, **kw)
         integ.render(film)
         out.append((sampler, float(film.resolve_rgb().mean()), integ.counters()["extend_rays"]))
+    # SpatialLightDistribution: the voxel tables (k_spatial_contrib, k_spatial_distrib) and a render that looks them up
+    film = pb2.Film(cam4["res"])
+    integ = pb2.PathIntegrator(accel, camera4, max_depth=8, light_strategy="spatial", spp=4)
+    integ.render(film)
+    out.append(("spatial", accel.spatial_light_distribution(tables=False), float(film.resolve_rgb().mean())))
     # plain mesh (the kernels the benchmarks run: k_shade<*, false, false>)
     sc = scenes.scene_c4()
     accel = pb2.BVHAccel(pb2.scene_from_dict(sc), 4)
