@@ -6,8 +6,9 @@ closest hit against the 10,008,338-triangle displaced grid -> shadow rays to the
 cosine-bounce rays (incoherent closest hit) spawned from the hits -> both traced.  3 x 1,048,576 rays per step.
 
   value     = rays traced / device time, inputs resident in HBM (CUDA events on the launching stream)
-  e2e       = the same three batches through the host-buffer C ABI (pb2_intersect / pb2_intersect_p) from pinned host
-              memory, H2D + D2H inside the timed region
+  e2e       = the same three batches through the host-buffer C ABI from pinned host memory, H2D + D2H inside the timed
+              region: enqueued back to back (pb2_intersect_async / pb2_intersect_p_async) and waited for once per step;
+              the synchronous calls (pb2_intersect / pb2_intersect_p, one drain per batch) are timed beside it
   roofline  = algorithmic bytes of the incoherent closest-hit launch (oracle-counted nodes/triangles in reference order,
               SURVEY §8d) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference = the CPU restatement of the reference (oracle/, all host threads) on a bounded sample
@@ -442,11 +443,28 @@ def main():
     torch.cuda.synchronize()
     L = pb2.lib()
 
-    def e2e_step():
+    def e2e_step_sync():
+        # the synchronous entry points: every call returns with its results in the host buffer (one ring drain per batch)
         pb2.check(L.pb2_intersect(accel.h, h_rays.data_ptr(), n, h_hits.data_ptr(), None))
         pb2.check(L.pb2_intersect_p(accel.h, h_srays.data_ptr(), n, h_occ.data_ptr()))
         pb2.check(L.pb2_intersect(accel.h, h_brays.data_ptr(), n, h_bhits.data_ptr(), None))
 
+    def e2e_step():
+        # the three host batches enqueued back to back on the scene's ring, then one wait: all results are in the host
+        # buffers when the step ends, and the drain of one batch runs under the H2D copies of the next
+        pb2.check(L.pb2_intersect_async(accel.h, h_rays.data_ptr(), n, h_hits.data_ptr(), None))
+        pb2.check(L.pb2_intersect_p_async(accel.h, h_srays.data_ptr(), n, h_occ.data_ptr()))
+        pb2.check(L.pb2_intersect_async(accel.h, h_brays.data_ptr(), n, h_bhits.data_ptr(), None))
+        pb2.check(L.pb2_scene_wait(accel.h))
+
+    for _ in range(args.warmup):
+        e2e_step_sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step_sync()
+    torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
     for _ in range(args.warmup):
         e2e_step()
     # what the link itself delivers: one plain pinned H2D / D2H copy of a ray-set-sized buffer (explains e2e vs value)
@@ -510,9 +528,9 @@ def main():
 
     # ---- max over ranks ----
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
     rays_per_step = 3 * n
     value = world * rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
     e2e_value = world * rays_per_step * args.steps / e2e_s / 1e6
@@ -594,7 +612,10 @@ def main():
                        "scene_gen_s": t_gen, "bvh_build_upload_s": t_build},
             "kernel_ms": kernel_ms, "hits_crc32": hits_crc,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
-                    "api": "pb2_intersect / pb2_intersect_p with pinned host buffers", "pcie_measured": pcie,
+                    "api": "pb2_intersect_async x2 + pb2_intersect_p_async + pb2_scene_wait per step, pinned host buffers",
+                    "synchronous_calls_mrays_s": world * rays_per_step * args.steps / e2e_sync_s / 1e6,
+                    "synchronous_api": "pb2_intersect / pb2_intersect_p, each returning with its results on the host",
+                    "pcie_measured": pcie,
                     "link_bound_mrays_s": world * rays_per_step / (3 * n * 32 / (pcie["h2d_gbs"] * 1e9)) / 1e6},
             "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,

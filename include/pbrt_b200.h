@@ -189,6 +189,14 @@ int pb2_bvh_export(const pb2_scene* scene, void* nodes32, uint32_t* ordered_prim
 int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0);
 /* Any hit: out[i] = 1 if Primitive::intersect_p would return true. */
 int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out);
+/* Asynchronous forms ("async variants"): enqueue the batch on the scene's copy / compute ring and return.
+ * The buffers must be pinned (pb2_host_alloc) and stay untouched until pb2_scene_wait(scene) — or any synchronous
+ * pb2_intersect / pb2_intersect_p on the same scene — returns.  Batches enqueued back to back overlap: the drain of one
+ * (its last kernels and device-to-host copies) runs under the host-to-device copies of the next, which is how a caller
+ * with several independent batches (one per tile, per worker thread) keeps the link busy. */
+int pb2_intersect_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0);
+int pb2_intersect_p_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out);
+int pb2_scene_wait(pb2_scene* scene);
 /* Device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`). */
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream);
 int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream);

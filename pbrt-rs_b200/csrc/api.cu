@@ -63,6 +63,9 @@ void pb2_scene::free_device() {
     d_indices = d_normals = d_tangents = d_uvs = nullptr;
     d_quads = nullptr;
     d_pairs = d_tris = d_slot_of_prim = d_tri_material = d_tri_light = d_materials = d_lights = d_light_cdf = nullptr;
+    if (pipe.pending && pipe.d2h) cudaStreamSynchronize(pipe.d2h);      // _async batches still in flight
+    pipe.pending = false;
+    pipe.chunks = 0;
     for (int i = 0; i < kStages; ++i) {
         Stage& st = pipe.slot[i];
         if (st.d_in) cudaFree(st.d_in);
@@ -410,6 +413,7 @@ static int ensure_stage(pb2_scene* s, size_t chunk) {
         if (!st.done) PB2_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         if (!st.drained) PB2_CUDA(cudaEventCreateWithFlags(&st.drained, cudaEventDisableTiming));
         if (st.cap < chunk) {
+            if (p.pending) { PB2_CUDA(cudaStreamSynchronize(p.d2h)); p.pending = false; }     // batches still in flight use the old buffers
             if (st.d_in) cudaFree(st.d_in);
             if (st.d_out) cudaFree(st.d_out);
             if (st.d_aux) cudaFree(st.d_aux);
@@ -447,17 +451,24 @@ static size_t env_size(const char* name, size_t dflt) {
 }
 static const size_t kChunk = env_size("PB2_PIPE_CHUNK", 1u << 17);          // tuning overrides for sweeps (tools/e2e_sweep.py)
 static const size_t kTailChunk = std::min(kChunk, env_size("PB2_PIPE_TAIL", 1u << 17));
+// _async batches pay the ring's fill and drain once per wait, not once per call, so larger chunks win there: C3 sets, three
+// batches per wait, 1058 / 1385 / 1436 / 1293 / 1212 Mrays/s with 64 K / 128 K / 256 K / 512 K / 1 M rays per chunk.
+static const size_t kChunkAsync = getenv("PB2_PIPE_CHUNK") ? kChunk : (size_t)(1u << 18);
 
 extern "C++" {
 template <class Launch>
-static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t out_bytes, void* out, float* b0, Launch&& launch) {
-    int rc = ensure_stage(scene, std::min<uint64_t>(kChunk, std::max<uint64_t>(n, 1)));
+// wait = false (the _async entry points): return once the batch is enqueued; the chunk counter runs on over calls, so the
+// next batch's first H2D copies start while this batch's last kernels and D2H copies are still draining.
+static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t out_bytes, void* out, float* b0, bool wait, Launch&& launch) {
+    const uint64_t chunk = wait ? kChunk : kChunkAsync, tail = wait ? kTailChunk : kChunkAsync;
+    int rc = ensure_stage(scene, std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1)));
     if (rc) return rc;
     Pipe& p = scene->pipe;
-    uint64_t c = 0, m = 0;
-    for (uint64_t off = 0; off < n; off += m, ++c) {
+    uint64_t m = 0;
+    for (uint64_t off = 0; off < n; off += m) {
         const uint64_t left = n - off;
-        m = std::min<uint64_t>(left, std::min<uint64_t>(kChunk, std::max<uint64_t>(kTailChunk, (left + 1) / 2)));
+        m = std::min<uint64_t>(left, std::min<uint64_t>(chunk, std::max<uint64_t>(tail, (left + 1) / 2)));
+        const uint64_t c = p.chunks++;
         Stage& st = p.slot[c % kStages];
         if (c >= (uint64_t)kStages) PB2_CUDA(cudaStreamWaitEvent(p.h2d, st.drained, 0));       // slot's previous chunk fully out
         PB2_CUDA(cudaMemcpyAsync(st.d_in, rays + off, m * 32, cudaMemcpyHostToDevice, p.h2d));
@@ -472,31 +483,47 @@ static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t ou
         if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, p.d2h));
         PB2_CUDA(cudaEventRecord(st.drained, p.d2h));
     }
-    PB2_CUDA(cudaStreamSynchronize(p.d2h));
+    if (!wait) { p.pending = true; return PB2_OK; }
+    PB2_CUDA(cudaStreamSynchronize(p.d2h));               // in-order stream: earlier _async batches are out as well
+    p.pending = false;
     return PB2_OK;
 }
 }  // extern "C++"
 
-int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0) {
+static int intersect_host(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0, bool wait) {
     int rc = check_ready(scene);
     if (rc) return rc;
     if (n && (!rays || !hits)) return set_error(PB2_ERR_INVALID, "null ray/hit buffer");
     std::lock_guard<std::mutex> lock(scene->mu);
     PB2_CUDA(cudaSetDevice(scene->device));
-    return run_pipe(scene, rays, n, 16, hits, b0, [&](Stage& st, uint64_t m, cudaStream_t s) {
+    return run_pipe(scene, rays, n, 16, hits, b0, wait, [&](Stage& st, uint64_t m, cudaStream_t s) {
         launch_closest_hit(scene->view, st.d_in, m, st.d_out, b0 ? st.d_aux : nullptr, scene->next_counter(), s);
     });
 }
-
-int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out) {
+static int intersect_p_host(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out, bool wait) {
     int rc = check_ready(scene);
     if (rc) return rc;
     if (n && (!rays || !out)) return set_error(PB2_ERR_INVALID, "null ray/output buffer");
     std::lock_guard<std::mutex> lock(scene->mu);
     PB2_CUDA(cudaSetDevice(scene->device));
-    return run_pipe(scene, rays, n, 1, out, nullptr, [&](Stage& st, uint64_t m, cudaStream_t s) {
+    return run_pipe(scene, rays, n, 1, out, nullptr, wait, [&](Stage& st, uint64_t m, cudaStream_t s) {
         launch_any_hit(scene->view, st.d_in, m, st.d_out, scene->next_counter(), s);
     });
+}
+
+int pb2_intersect(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0) { return intersect_host(scene, rays, n, hits, b0, true); }
+int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out) { return intersect_p_host(scene, rays, n, out, true); }
+int pb2_intersect_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0) { return intersect_host(scene, rays, n, hits, b0, false); }
+int pb2_intersect_p_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out) { return intersect_p_host(scene, rays, n, out, false); }
+
+int pb2_scene_wait(pb2_scene* scene) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    if (!scene->pipe.pending) return PB2_OK;
+    PB2_CUDA(cudaSetDevice(scene->device));
+    PB2_CUDA(cudaStreamSynchronize(scene->pipe.d2h));
+    scene->pipe.pending = false;
+    return PB2_OK;
 }
 
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream) {

@@ -41,6 +41,8 @@ struct Pipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t compute[2] = {nullptr, nullptr};   // alternate chunks: the tail of one chunk's kernel overlaps the next one
     Stage slot[kStages];
+    uint64_t chunks = 0;                // chunks enqueued so far, over all calls: picks the slot and the compute stream
+    bool pending = false;               // work enqueued by an _async entry point that pb2_scene_wait has not yet waited for
 };
 
 struct Wavefront;

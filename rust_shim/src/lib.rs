@@ -44,6 +44,10 @@ extern "C" {
     pub fn pb2_world_bound(scene: *const pb2_scene, out: *mut f32) -> c_int;
     pub fn pb2_intersect(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, hits: *mut pb2_hit, b0: *mut f32) -> c_int;
     pub fn pb2_intersect_p(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, out: *mut u8) -> c_int;
+    // asynchronous forms: buffers from pb2_host_alloc, untouched until pb2_scene_wait returns
+    pub fn pb2_intersect_async(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, hits: *mut pb2_hit, b0: *mut f32) -> c_int;
+    pub fn pb2_intersect_p_async(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, out: *mut u8) -> c_int;
+    pub fn pb2_scene_wait(scene: *mut pb2_scene) -> c_int;
     pub fn pb2_film_create(desc: *const pb2_film_desc, out: *mut *mut pb2_film) -> c_int;
     pub fn pb2_film_destroy(film: *mut pb2_film) -> c_int;
     pub fn pb2_film_read_xyzw(film: *mut pb2_film, out: *mut f32) -> c_int;

@@ -409,3 +409,52 @@ def test_hostile_rays_match_the_oracle(gpu, orc, scenes):
     finite = found & np.isfinite(rh["t"])
     assert np.array_equal(bits(hits["t"])[finite], bits(rh["t"])[finite]) and finite.sum() > 300
     assert np.array_equal(accel.intersect_p(allr), ref.intersect_p(allr)[0])
+
+
+def test_async_entry_points_match_the_synchronous_ones(gpu, orc, scenes):
+    """pb2_intersect_async / pb2_intersect_p_async + pb2_scene_wait: several batches (a multi-chunk one, a short one, an empty
+    one, one that needs b0) enqueued back to back on the scene's ring land in their own host buffers with the bits the
+    synchronous calls and the oracle give; a synchronous call also drains earlier asynchronous ones."""
+    import ctypes as C
+    v, i = scenes.merge(scenes.uv_sphere(n_theta=40, n_phi=80), scenes.ground_grid())
+    accel = gpu.BVHAccel(v, i, 4)
+    ref = orc.BVHAccel(v, i, 4)
+    L = gpu.lib()
+
+    def pinned(nbytes):
+        p = C.c_void_p()
+        gpu.check(L.pb2_host_alloc(max(nbytes, 16), C.byref(p)))
+        return p
+
+    sizes = [300001, 17, 0, 150000, 40000]
+    batches = []
+    for k, n in enumerate(sizes):
+        rays = random_rays(n, seed=100 + k, extent=6.0, finite_tmax=(k % 2 == 1))
+        p_r, p_h, p_b, p_o = pinned(n * 32), pinned(n * 16), pinned(n * 4), pinned(n)
+        C.memmove(p_r, rays.ctypes.data, rays.nbytes)
+        batches.append((n, rays, p_r, p_h, p_b, p_o))
+    for rnd in range(2):
+        for k, (n, rays, p_r, p_h, p_b, p_o) in enumerate(batches):
+            gpu.check(L.pb2_intersect_async(accel.h, p_r, n, p_h, p_b if k == 3 else None))
+            gpu.check(L.pb2_intersect_p_async(accel.h, p_r, n, p_o))
+        if rnd == 0:
+            gpu.check(L.pb2_scene_wait(accel.h))
+        else:                                     # a synchronous call on the same scene waits for everything before it
+            assert np.array_equal(accel.intersect(batches[1][1])["prim_id"], ref.intersect(batches[1][1])[0]["prim_id"])
+        for k, (n, rays, p_r, p_h, p_b, p_o) in enumerate(batches):
+            if n == 0:
+                continue
+            hits = np.frombuffer((C.c_char * (n * 16)).from_address(p_h.value), dtype=gpu.HIT_DTYPE).copy()
+            occ = np.frombuffer((C.c_char * n).from_address(p_o.value), dtype=np.uint8).copy()
+            want = ref.intersect(rays, want_b0=True)
+            assert_hits_equal(hits, want[0])
+            assert np.array_equal(occ, ref.intersect_p(rays)[0])
+            if k == 3:
+                b0 = np.frombuffer((C.c_char * (n * 4)).from_address(p_b.value), dtype=np.float32).copy()
+                assert np.array_equal(bits(b0), bits(want[1]))
+            C.memset(p_h, 0xFF, n * 16)
+            C.memset(p_o, 0xFF, n)
+    gpu.check(L.pb2_scene_wait(accel.h))          # nothing pending: returns at once
+    for _, _, p_r, p_h, p_b, p_o in batches:
+        for p in (p_r, p_h, p_b, p_o):
+            gpu.check(L.pb2_host_free(p))

@@ -36,7 +36,15 @@ def main():
     h_occ = torch.empty(n, dtype=torch.uint8).pin_memory()
     L = pb2.lib()
 
+    use_async = os.environ.get("E2E_ASYNC") == "1"
+
     def step():
+        if use_async:                       # three batches in flight, one wait (what bench.py's e2e times)
+            pb2.check(L.pb2_intersect_async(accel.h, h[0].data_ptr(), n, h_hits[0].data_ptr(), None))
+            pb2.check(L.pb2_intersect_p_async(accel.h, h[1].data_ptr(), n, h_occ.data_ptr()))
+            pb2.check(L.pb2_intersect_async(accel.h, h[2].data_ptr(), n, h_hits[1].data_ptr(), None))
+            pb2.check(L.pb2_scene_wait(accel.h))
+            return
         pb2.check(L.pb2_intersect(accel.h, h[0].data_ptr(), n, h_hits[0].data_ptr(), None))
         pb2.check(L.pb2_intersect_p(accel.h, h[1].data_ptr(), n, h_occ.data_ptr()))
         pb2.check(L.pb2_intersect(accel.h, h[2].data_ptr(), n, h_hits[1].data_ptr(), None))
@@ -53,7 +61,7 @@ def main():
     dt = (time.perf_counter() - t0) / reps
     import zlib
     crc = "%08x" % zlib.crc32(h_occ.numpy().tobytes(), zlib.crc32(h_hits[1].numpy().tobytes(), zlib.crc32(h_hits[0].numpy().tobytes())))
-    print(f"chunk={os.environ.get('PB2_PIPE_CHUNK', 'default')} tail={os.environ.get('PB2_PIPE_TAIL', 'default')} "
+    print(f"async={int(use_async)} chunk={os.environ.get('PB2_PIPE_CHUNK', 'default')} tail={os.environ.get('PB2_PIPE_TAIL', 'default')} "
           f"e2e mean {3 * n / dt / 1e6:.0f} Mrays/s best {3 * n / best / 1e6:.0f} Mrays/s ({dt * 1e3:.3f} ms/step) crc {crc}", flush=True)
 
 
