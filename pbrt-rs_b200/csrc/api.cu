@@ -454,13 +454,14 @@ static const size_t kTailChunk = std::min(kChunk, env_size("PB2_PIPE_TAIL", 1u <
 // _async batches pay the ring's fill and drain once per wait, not once per call, so larger chunks win there: C3 sets, three
 // batches per wait, 1058 / 1385 / 1436 / 1293 / 1212 Mrays/s with 64 K / 128 K / 256 K / 512 K / 1 M rays per chunk.
 static const size_t kChunkAsync = getenv("PB2_PIPE_CHUNK") ? kChunk : (size_t)(1u << 18);
+static const size_t kTailAsync = std::min(kChunkAsync, env_size("PB2_PIPE_TAIL_ASYNC", kChunkAsync));
 
 extern "C++" {
 template <class Launch>
 // wait = false (the _async entry points): return once the batch is enqueued; the chunk counter runs on over calls, so the
 // next batch's first H2D copies start while this batch's last kernels and D2H copies are still draining.
 static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t out_bytes, void* out, float* b0, bool wait, Launch&& launch) {
-    const uint64_t chunk = wait ? kChunk : kChunkAsync, tail = wait ? kTailChunk : kChunkAsync;
+    const uint64_t chunk = wait ? kChunk : kChunkAsync, tail = wait ? kTailChunk : kTailAsync;
     int rc = ensure_stage(scene, std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1)));
     if (rc) return rc;
     Pipe& p = scene->pipe;
