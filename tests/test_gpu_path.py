@@ -580,3 +580,36 @@ def test_spatial_light_distribution_one_light_and_limits(gpu, OP, scenes):
     integ.desc.light_strategy = 7
     with pytest.raises(gpu.Pb2Error):
         integ.render(fa)
+
+
+def test_c2_full_size_frame_bit_exact(gpu, OP, scenes):
+    """BASELINE config 1 at its full size: Cornell box, maxdepth 5, 512x512 @ 64 spp (16.8 M camera samples, ~68 M path rays).
+    The whole frame's film accumulators — rendered in the batches wavefront_render chooses — equal the oracle's bits, and so
+    does the resolved image."""
+    cam = dict(scenes.C2_CAMERA)
+    kw = dict(scenes.C2_PATH)
+    accel, camera, integ, ref = setup_scene(gpu, OP, scenes.scene_c2(), cam, **kw)
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    got = film.read_xyzw()
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), mode=1)
+    assert np.array_equal(bits(got), bits(want)), f"{(bits(got) != bits(want)).any(axis=2).sum()} of {512 * 512} pixels differ"
+    assert np.array_equal(bits(film.resolve_rgb()), bits(OP.resolve_rgb(want)))
+    c = integ.counters()
+    assert c["camera_samples"] == 512 * 512 * 64 and c["stray_overflow"] == 0
+
+
+def test_c4_full_resolution_frame_bit_exact(gpu, OP, scenes):
+    """BASELINE config 3 at its full resolution and geometry (297,684 triangles, matte / plastic / glass, area + point light,
+    maxdepth 8, power light distribution, 1920x1080): sample indices [0, 2) of the 256 spp of every pixel (4.1 M camera samples)
+    — the film equals the oracle's bits; the remaining sample indices run the same kernels on other sampler streams."""
+    sc = scenes.scene_c4()
+    cam = dict(scenes.C4_CAMERA)
+    kw = dict(scenes.C4_PATH)
+    accel, camera, integ, ref = setup_scene(gpu, OP, sc, cam, **kw)
+    film = gpu.Film(cam["res"])
+    integ.render(film, 0, 2)
+    got = film.read_xyzw()
+    want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(**dict(kw, sample_begin=0, sample_end=2)), mode=1)
+    assert np.array_equal(bits(got), bits(want)), f"{(bits(got) != bits(want)).any(axis=2).sum()} of {1920 * 1080} pixels differ"
+    assert got[..., :3].mean() > 0.01
