@@ -234,6 +234,14 @@ int pb2_film_add_samples(pb2_film* film, const float* p_film, const float* L_rgb
 int pb2_film_read_xyzw(pb2_film* film, float* out);
 /* Film::write_image (:153-178): XYZ -> RGB, / weight, clamp >= 0, * scale. */
 int pb2_film_resolve_rgb(pb2_film* film, float scale, float* rgb);
+/* Film::add_splat (film.rs:137-151) for n splats: p_film[2n] film positions, v_rgb[3n] values; a splat lands on pixel
+ * floor(p) when that lies inside cropped_pixel_bounds, after the max_sample_luminance clamp.  Film::set_image (film.rs:125-135):
+ * rgb[3 * n_pixels] becomes the film (weight 1, splats cleared).  pb2_film_resolve_rgb_splat is Film::write_image's pixel loop
+ * (film.rs:153-178) with its splat_scale argument: rgb = max(xyz_to_rgb(xyz) / weight, 0) + splat_scale * xyz_to_rgb(splat), times
+ * scale; pb2_film_resolve_rgb and pb2_film_write_image use splat_scale = 1. */
+int pb2_film_add_splats(pb2_film* film, const float* p_film, const float* v_rgb, uint64_t n);
+int pb2_film_set_image(pb2_film* film, const float* rgb);
+int pb2_film_resolve_rgb_splat(pb2_film* film, float scale, float splat_scale, float* rgb);
 int pb2_film_device_ptr(pb2_film* film, void** d_xyzw, uint64_t* n_floats);
 /* Film::cropped_pixel_bounds (film.rs:41-50) and Film::get_sample_bounds (:76-81): {x0, y0, x1, y1} each (x1, y1 exclusive). */
 int pb2_film_bounds(const pb2_film* film, int32_t pixel_bounds[4], int32_t sample_bounds[4]);

@@ -82,6 +82,9 @@ def _bind_path(L):
     L.orc_roughness_to_alpha.argtypes = [C.c_float]
     L.orc_sincos.argtypes = [C.c_float, vp, vp]
     L.orc_film_table.argtypes = [vp, vp]
+    L.orc_film_add_splats.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.orc_resolve_rgb_splat.argtypes = [vp, vp, C.c_uint64, C.c_float, C.c_float, vp]
+    L.orc_rgb_to_xyz.argtypes = [vp, C.c_uint64, vp]
     L.orc_spatial_grid.argtypes = [vp, vp]
     L.orc_spatial_voxel.argtypes = [vp, vp, vp, vp, vp]
     L.orc_spatial_voxel_of.argtypes = [vp, vp, vp]

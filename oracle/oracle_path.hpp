@@ -1441,4 +1441,32 @@ inline void resolve_rgb(const Float* xyzw, size_t npix, Float scale, Float* out_
     }
 }
 
+// Film::add_splat (film.rs:137-151) + the splat term of Film::write_image (:167-172).
+//   D64 FIX  :139-141 returns when the pixel IS inside cropped_pixel_bounds (and tests the inclusive box) -> pbrt-v3: skip
+//            pixels outside, upper bound exclusive
+inline void film_add_splats(const Film& film, const Float* p_film, const Float* v_rgb, size_t n, Float* splat_xyz /* 3 per pixel */) {
+    for (size_t i = 0; i < n; ++i) {
+        const Float fx = std::floor(p_film[2 * i]), fy = std::floor(p_film[2 * i + 1]);
+        if (!(fx >= (Float)film.px0 && fx < (Float)film.px1 && fy >= (Float)film.py0 && fy < (Float)film.py1)) continue;
+        const RGB v = film.clamp_luminance(RGB{v_rgb[3 * i], v_rgb[3 * i + 1], v_rgb[3 * i + 2]});
+        Float xyz[3];
+        rgb_to_xyz(v, xyz);
+        Float* dst = splat_xyz + 3 * film.index((int)fx, (int)fy);
+        dst[0] += xyz[0]; dst[1] += xyz[1]; dst[2] += xyz[2];
+    }
+}
+inline void resolve_rgb_splat(const Float* xyzw, const Float* splat_xyz, size_t npix, Float scale, Float splat_scale, Float* out_rgb) {
+    for (size_t i = 0; i < npix; ++i) {
+        Float c[3], sc[3];
+        xyz_to_rgb(xyzw + 4 * i, c);
+        Float w = xyzw[4 * i + 3];
+        if (w != 0.0f) {
+            Float inv = 1.0f / w;
+            c[0] = fmax_(c[0] * inv, 0.0f); c[1] = fmax_(c[1] * inv, 0.0f); c[2] = fmax_(c[2] * inv, 0.0f);
+        }
+        xyz_to_rgb(splat_xyz + 3 * i, sc);
+        for (int k = 0; k < 3; ++k) out_rgb[3 * i + k] = (c[k] + splat_scale * sc[k]) * scale;
+    }
+}
+
 }  // namespace orc

@@ -246,6 +246,32 @@ def film_add_samples(film, p_film, L_rgb, weight):
     return out
 
 
+def film_add_splats(film, p_film, v_rgb, splat_xyz=None):
+    """Film::add_splat for every (p_film[i], v_rgb[i]) in array order -> splat_xyz [H, W, 3] (accumulates into splat_xyz if given)."""
+    p_film = np.ascontiguousarray(p_film, dtype=np.float32)
+    v_rgb = np.ascontiguousarray(v_rgb, dtype=np.float32)
+    if splat_xyz is None:
+        splat_xyz = np.zeros(film_shape(film) + (3,), dtype=np.float32)
+    O.lib().orc_film_add_splats(C.byref(film), _p(p_film), _p(v_rgb), len(v_rgb), _p(splat_xyz))
+    return splat_xyz
+
+
+def resolve_rgb_splat(xyzw, splat_xyz, scale=1.0, splat_scale=1.0):
+    """Film::write_image's pixel loop (film.rs:153-178) including the splat term."""
+    xyzw = np.ascontiguousarray(xyzw, dtype=np.float32)
+    splat_xyz = np.ascontiguousarray(splat_xyz, dtype=np.float32)
+    out = np.empty(xyzw.shape[:-1] + (3,), dtype=np.float32)
+    O.lib().orc_resolve_rgb_splat(_p(xyzw), _p(splat_xyz), xyzw.size // 4, scale, splat_scale, _p(out))
+    return out
+
+
+def rgb_to_xyz(rgb):
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    out = np.empty_like(rgb)
+    O.lib().orc_rgb_to_xyz(_p(rgb), rgb.size // 3, _p(out))
+    return out
+
+
 def roughness_to_alpha(r):
     return np.float32(O.lib().orc_roughness_to_alpha(r))
 

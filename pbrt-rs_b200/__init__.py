@@ -197,7 +197,8 @@ def lib():
         "pb2_rng_uniform_floats": [u64, u32, u32, vp], "pb2_film_bounds": [vp, vp, vp],
         "pb2_film_create": [vp, vp], "pb2_film_destroy": [vp], "pb2_film_clear": [vp],
         "pb2_film_add_samples": [vp, vp, vp, vp, u64], "pb2_film_read_xyzw": [vp, vp],
-        "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_device_ptr": [vp, vp, vp],
+        "pb2_film_resolve_rgb": [vp, f32, vp], "pb2_film_resolve_rgb_splat": [vp, f32, f32, vp],
+        "pb2_film_add_splats": [vp, vp, vp, u64], "pb2_film_set_image": [vp, vp], "pb2_film_device_ptr": [vp, vp, vp],
         "pb2_film_write_image": [vp, C.c_char_p, f32],
         "pb2_render_path": [vp, vp, vp, vp, vp], "pb2_path_li": [vp, vp, vp, vp, vp, u64, vp, vp],
         "pb2_render_counters": [vp, vp], "pb2_spatial_light_distribution": [vp, vp, vp, vp, vp],
@@ -497,10 +498,21 @@ class Film:
         check(lib().pb2_film_read_xyzw(self.h, _p(out)))
         return out
 
-    def resolve_rgb(self, scale=1.0):
+    def resolve_rgb(self, scale=1.0, splat_scale=1.0):
         out = np.empty((self.res[1], self.res[0], 3), dtype=np.float32)
-        check(lib().pb2_film_resolve_rgb(self.h, scale, _p(out)))
+        check(lib().pb2_film_resolve_rgb_splat(self.h, scale, splat_scale, _p(out)))
         return out
+
+    def add_splats(self, p_film, v_rgb):
+        """Film::add_splat (film.rs:137-151) for every (p_film[i], v_rgb[i])."""
+        p_film, v_rgb = _f32(p_film).reshape(-1, 2), _f32(v_rgb).reshape(-1, 3)
+        check(lib().pb2_film_add_splats(self.h, _p(p_film), _p(v_rgb), len(p_film)))
+
+    def set_image(self, rgb):
+        """Film::set_image (film.rs:125-135): rgb [H, W, 3] of the cropped pixel bounds."""
+        rgb = _f32(rgb)
+        assert rgb.size == self.res[0] * self.res[1] * 3
+        check(lib().pb2_film_set_image(self.h, _p(rgb)))
 
     def write_image(self, filename, scale=1.0):
         """Film::write_image (film.rs:153-180) through to a .pfm / .ppm file."""

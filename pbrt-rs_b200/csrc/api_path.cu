@@ -21,6 +21,7 @@ struct pb2_film {
     float* d_table = nullptr;
     float4* d_xyzw = nullptr;
     float4* d_acc = nullptr;
+    float4* d_splat = nullptr;                     // Pixel::splat_xyz, allocated by the first pb2_film_add_splats
     void* d_stray = nullptr;
     float4* d_stray_vals = nullptr;
     uint32_t stray_capacity = 0;
@@ -43,6 +44,7 @@ static FilmView film_view(const pb2_film* f) {
     v.table = f->d_table;
     v.acc = f->d_acc;
     v.xyzw = f->d_xyzw;
+    v.splat = f->d_splat;
     v.stray_keys = (unsigned long long*)f->d_stray;
     v.stray_vals = f->d_stray_vals;
     v.stray_capacity = f->stray_capacity;
@@ -488,6 +490,7 @@ int pb2_film_create(const pb2_film_desc* desc, pb2_film** out) {
 
 int pb2_film_destroy(pb2_film* f) {
     if (!f) return PB2_OK;
+    cudaFree(f->d_splat);
     cudaFree(f->d_table); cudaFree(f->d_xyzw); cudaFree(f->d_acc); cudaFree(f->d_stray); cudaFree(f->d_stray_vals); cudaFree(f->d_counters);
     delete f;
     return PB2_OK;
@@ -498,6 +501,42 @@ int pb2_film_clear(pb2_film* f) {
     const size_t npix = f->n_pixels();
     PB2_CUDA(cudaMemset(f->d_xyzw, 0, npix * 16));
     PB2_CUDA(cudaMemset(f->d_acc, 0, npix * 16));
+    if (f->d_splat) PB2_CUDA(cudaMemset(f->d_splat, 0, npix * 16));
+    return PB2_OK;
+}
+
+// Film::add_splat (film.rs:137-151) for n splats
+int pb2_film_add_splats(pb2_film* f, const float* p_film, const float* v_rgb, uint64_t n) {
+    if (!f) return set_error(PB2_ERR_INVALID, "null film");
+    if (n == 0) return PB2_OK;
+    if (!p_film || !v_rgb) return set_error(PB2_ERR_INVALID, "null splat arrays");
+    if (!f->d_splat) {
+        PB2_CUDA(cudaMalloc(&f->d_splat, f->n_pixels() * 16));
+        PB2_CUDA(cudaMemset(f->d_splat, 0, f->n_pixels() * 16));
+    }
+    float *d_p = nullptr, *d_v = nullptr;
+    cudaError_t e = cudaMalloc(&d_p, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, n * 12);
+    if (e == cudaSuccess) e = cudaMemcpy(d_p, p_film, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_v, v_rgb, n * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { film_add_splats(film_view(f), d_p, d_v, n, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_p); cudaFree(d_v);
+    if (e != cudaSuccess) return cuda_fail(e, "film add_splats", __FILE__, __LINE__);
+    return PB2_OK;
+}
+
+// Film::set_image (film.rs:125-135): every pixel = to_xyz(rgb), weight 1, splat 0
+int pb2_film_set_image(pb2_film* f, const float* rgb) {
+    if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
+    const size_t npix = f->n_pixels();
+    float* d = nullptr;
+    PB2_CUDA(cudaMalloc(&d, npix * 12));
+    cudaError_t e = cudaMemcpy(d, rgb, npix * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { film_set_image(film_view(f), d, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "film set_image", __FILE__, __LINE__);
     return PB2_OK;
 }
 
@@ -525,12 +564,14 @@ int pb2_film_read_xyzw(pb2_film* f, float* out) {
     return PB2_OK;
 }
 
-int pb2_film_resolve_rgb(pb2_film* f, float scale, float* rgb) {
+int pb2_film_resolve_rgb(pb2_film* f, float scale, float* rgb) { return pb2_film_resolve_rgb_splat(f, scale, 1.0f, rgb); }
+
+int pb2_film_resolve_rgb_splat(pb2_film* f, float scale, float splat_scale, float* rgb) {
     if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
     const size_t npix = f->n_pixels();
     float* d = nullptr;
     PB2_CUDA(cudaMalloc(&d, npix * 12));
-    film_resolve(film_view(f), scale, d, 0);
+    film_resolve(film_view(f), scale, splat_scale, d, 0);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(rgb, d, npix * 12, cudaMemcpyDeviceToHost);
     cudaFree(d);

@@ -836,8 +836,8 @@ __global__ void __launch_bounds__(kThreads) k_film_add_samples(FilmView f, const
         film_footprint(f, pf[i].x, pf[i].y, [&](int px, int py, float fw) { film_atomic_add(f, px, py, c * sw * fw, fw); });
     }
 }
-// Film::write_image (film.rs:153-178)
-__global__ void __launch_bounds__(kThreads) k_film_resolve(FilmView f, float scale, float* rgb) {
+// Film::write_image (film.rs:153-178); the splat term (:167-172) only when the film has ever been splatted
+__global__ void __launch_bounds__(kThreads) k_film_resolve(FilmView f, float scale, float splat_scale, float* rgb) {
     const size_t n = f.n_pixels();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 p = f.xyzw[i];
@@ -846,7 +846,36 @@ __global__ void __launch_bounds__(kThreads) k_film_resolve(FilmView f, float sca
             const float inv = 1.0f / p.w;
             c = mkc(fmaxf(c.r * inv, 0.0f), fmaxf(c.g * inv, 0.0f), fmaxf(c.b * inv, 0.0f));
         }
+        if (f.splat) {
+            const float4 sp = f.splat[i];
+            const rgb3 sc = from_xyz(sp.x, sp.y, sp.z);
+            c = mkc(c.r + splat_scale * sc.r, c.g + splat_scale * sc.g, c.b + splat_scale * sc.b);
+        }
         rgb[3 * i] = c.r * scale; rgb[3 * i + 1] = c.g * scale; rgb[3 * i + 2] = c.b * scale;
+    }
+}
+// Film::add_splat (film.rs:137-151; D64 FIX: the port returns when the pixel IS inside the cropped bounds and tests the
+// inclusive box — pbrt-v3: skip pixels outside, upper bound exclusive).  Float atomics: the order of splats on one pixel is
+// not fixed, as in the reference (AtomicFloat from many threads).
+__global__ void __launch_bounds__(kThreads) k_film_add_splats(FilmView f, const float2* pf, const float* v, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float fx = floorf(pf[i].x), fy = floorf(pf[i].y);
+        if (!(fx >= (float)f.px0 && fx < (float)f.px1 && fy >= (float)f.py0 && fy < (float)f.py1)) continue;
+        const rgb3 c = clamp_luminance(f, mkc(v[3 * i], v[3 * i + 1], v[3 * i + 2]));
+        float x, y, z;
+        to_xyz(c, &x, &y, &z);
+        float* dst = reinterpret_cast<float*>(f.splat + f.index((int)fx, (int)fy));
+        atomicAdd(dst, x); atomicAdd(dst + 1, y); atomicAdd(dst + 2, z);
+    }
+}
+// Film::set_image (film.rs:125-135)
+__global__ void __launch_bounds__(kThreads) k_film_set_image(FilmView f, const float* rgb) {
+    const size_t n = f.n_pixels();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float x, y, z;
+        to_xyz(mkc(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), &x, &y, &z);
+        f.xyzw[i] = make_float4(x, y, z, 1.0f);
+        if (f.splat) f.splat[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 __global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, float* L_out, float* pf_out) {
@@ -1021,8 +1050,14 @@ void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d
     k_film_merge<<<148 * 4, kThreads, 0, st>>>(film, nullptr);
 }
 
-void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st) {
-    k_film_resolve<<<148 * 4, kThreads, 0, st>>>(film, scale, d_rgb);
+void film_resolve(const FilmView& film, float scale, float splat_scale, float* d_rgb, cudaStream_t st) {
+    k_film_resolve<<<148 * 4, kThreads, 0, st>>>(film, scale, splat_scale, d_rgb);
+}
+void film_add_splats(const FilmView& film, const float* d_pfilm, const float* d_v, uint64_t n, cudaStream_t st) {
+    if (n) k_film_add_splats<<<148 * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_v, n);
+}
+void film_set_image(const FilmView& film, const float* d_rgb, cudaStream_t st) {
+    k_film_set_image<<<148 * 4, kThreads, 0, st>>>(film, d_rgb);
 }
 
 }  // namespace pb2

@@ -63,6 +63,7 @@ struct FilmView {
     const float* table;           // 256 floats
     float4* acc;                  // per image pixel: RGB sum + filter weight sum of the current render call
     float4* xyzw;                 // per image pixel: X, Y, Z, weight accumulators (the Film itself)
+    float4* splat;                // per image pixel: splat_xyz (film.rs:9-15), null until the first Film::add_splat
     unsigned long long* stray_keys;
     float4* stray_vals;
     uint32_t stray_capacity;
@@ -158,6 +159,8 @@ void spatial_distribution_build(const SpatialView& grid, const DLight* d_lights,
                                 cudaStream_t st);
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
-void film_resolve(const FilmView& film, float scale, float* d_rgb, cudaStream_t st);
+void film_resolve(const FilmView& film, float scale, float splat_scale, float* d_rgb, cudaStream_t st);
+void film_add_splats(const FilmView& film, const float* d_pfilm, const float* d_v, uint64_t n, cudaStream_t st);
+void film_set_image(const FilmView& film, const float* d_rgb, cudaStream_t st);
 
 }  // namespace pb2

@@ -613,3 +613,36 @@ def test_c4_full_resolution_frame_bit_exact(gpu, OP, scenes):
     want, _ = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(**dict(kw, sample_begin=0, sample_end=2)), mode=1)
     assert np.array_equal(bits(got), bits(want)), f"{(bits(got) != bits(want)).any(axis=2).sum()} of {1920 * 1080} pixels differ"
     assert got[..., :3].mean() > 0.01
+
+
+def test_film_splats_and_set_image(gpu, OP):
+    """Film::add_splat / Film::set_image / write_image's splat term on the device against the oracle: one splat per pixel is
+    bit-exact; many splats per pixel accumulate with float atomics (order not fixed, as in the reference's AtomicFloat), compared at
+    rel 1e-5; splats outside the cropped bounds are dropped; clear() zeroes them; set_image replaces the film."""
+    res, crop = (64, 48), (0.25, 0.0, 1.0, 0.75)
+    fd = OP.film_desc(res, crop=crop, max_sample_luminance=3.0)
+    (x0, y0, x1, y1), _ = OP.film_bounds(fd)
+    film = gpu.Film(res, crop=crop, max_sample_luminance=3.0)
+    rng = np.random.default_rng(9)
+    xs, ys = np.meshgrid(np.arange(x0, x1), np.arange(y0, y1))
+    p1 = (np.stack([xs.ravel(), ys.ravel()], axis=1) + rng.random((xs.size, 2))).astype(np.float32) * np.float32(0.999999)
+    p1 = np.maximum(p1, np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32))
+    v1 = rng.uniform(0, 6, (len(p1), 3)).astype(np.float32)
+    film.add_splats(p1, v1)
+    base = rng.uniform(0, 1, (y1 - y0, x1 - x0, 3)).astype(np.float32)
+    xyzw = np.concatenate([OP.rgb_to_xyz(base), np.ones(base.shape[:2] + (1,), np.float32)], axis=2)
+    sp = OP.film_add_splats(fd, p1, v1)
+    film.set_image(base)                                        # clears the splats (film.rs:131-133) ...
+    assert np.array_equal(bits(film.read_xyzw()), bits(xyzw))
+    assert np.array_equal(bits(film.resolve_rgb(2.0, 0.5)), bits(OP.resolve_rgb(xyzw, 2.0)))
+    film.add_splats(p1, v1)                                     # ... so splat again: one per pixel, order-free
+    assert np.array_equal(bits(film.resolve_rgb(2.0, 0.5)), bits(OP.resolve_rgb_splat(xyzw, sp, 2.0, 0.5)))
+    n = 200000
+    p2 = rng.uniform(-4, 70, (n, 2)).astype(np.float32)         # a fifth of them fall outside the cropped bounds
+    v2 = rng.uniform(0, 2, (n, 3)).astype(np.float32)
+    film.add_splats(p2, v2)
+    sp = OP.film_add_splats(fd, p2, v2, sp)
+    got, want = film.resolve_rgb(1.0, 0.25), OP.resolve_rgb_splat(xyzw, sp, 1.0, 0.25)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    film.clear()
+    assert film.resolve_rgb(1.0, 1.0).max() == 0.0

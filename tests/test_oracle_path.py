@@ -380,3 +380,29 @@ def test_spatial_light_distribution(OP):
     assert abs(a.mean() - b.mean()) / b.mean() < 0.02
     # importance sampling the nearer light lowers the variance under it
     assert a[2:8, 2:8].std() < b[2:8, 2:8].std()
+
+
+def test_film_splats_and_write_image_splat_term(OP):
+    """Film::add_splat (film.rs:137-151, D64 FIX) and the splat term of Film::write_image (:167-172): a splat lands on
+    floor(p) inside the cropped bounds only, is clamped to max_sample_luminance, accumulates as XYZ; the written pixel is
+    max(rgb / w, 0) + splat_scale * xyz_to_rgb(splat), times scale."""
+    fd = OP.film_desc((8, 6), crop=(0.25, 0.0, 1.0, 1.0), max_sample_luminance=2.0)
+    assert OP.film_bounds(fd)[0] == (2, 0, 8, 6)
+    p = np.array([(2.0, 0.0), (7.99, 5.99), (1.99, 3.0), (8.0, 2.0), (4.5, -0.01), (4.5, 2.5), (4.2, 2.9)], np.float32)
+    v = np.array([(1, 1, 1), (0.5, 0.25, 0.125), (9, 9, 9), (9, 9, 9), (9, 9, 9), (10, 10, 10), (0.1, 0.2, 0.3)], np.float32)
+    sp = OP.film_add_splats(fd, p, v)
+    assert sp.shape == (6, 6, 3)
+    hit = np.zeros((6, 6), bool)
+    hit[0, 0] = hit[5, 5] = hit[2, 2] = True                 # columns are x - 2
+    assert ((np.abs(sp).sum(axis=2) > 0) == hit).all()       # the three splats outside the cropped bounds are dropped
+    assert np.array_equal(sp[0, 0], OP.rgb_to_xyz(np.array([1, 1, 1], np.float32)))
+    clamped = np.float32(10.0) * (np.float32(2.0) / OP.rgb_to_xyz(np.array([[10, 10, 10]], np.float32))[0, 1])      # y of grey 10 is 10
+    want = OP.rgb_to_xyz(np.array([clamped] * 3, np.float32)) + OP.rgb_to_xyz(np.array([0.1, 0.2, 0.3], np.float32))
+    assert np.allclose(sp[2, 2], want, rtol=1e-6)
+    xyzw = np.zeros((6, 6, 4), np.float32)
+    xyzw[..., :3] = OP.rgb_to_xyz(np.full((6, 6, 3), 0.5, np.float32)) * np.float32(4.0)
+    xyzw[..., 3] = 4.0
+    out = OP.resolve_rgb_splat(xyzw, sp, scale=2.0, splat_scale=0.5)
+    assert np.allclose(out[1, 1], 1.0, rtol=1e-5)                                        # no splat: (0.5 + 0) * 2
+    assert np.allclose(out[0, 0], (0.5 + 0.5 * 1.0) * 2.0, rtol=1e-5)
+    assert np.array_equal(OP.resolve_rgb_splat(xyzw, np.zeros_like(sp), 2.0, 0.5), OP.resolve_rgb(xyzw, 2.0))
