@@ -579,8 +579,11 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
 #ifndef PB2_SHADE_BLOCKS
 #define PB2_SHADE_BLOCKS 2
 #endif
+#ifndef PB2_SHADE_THREADS
+#define PB2_SHADE_THREADS 256
+#endif
 template <int MAT, bool TABLES, bool SG>
-__global__ void __launch_bounds__(kThreads, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
+__global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
     const uint64_t n = b.counters[C_MAT0 + MAT];
     const uint32_t* queue = b.q_mat[MAT];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -902,9 +905,11 @@ unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
 template <bool TABLES, bool SG>
 void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
                     const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
-    k_shade<0, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-    k_shade<1, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
-    k_shade<2, TABLES, SG><<<grid_for(wf, n, 4), kThreads, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + PB2_SHADE_THREADS - 1) / PB2_SHADE_THREADS,
+                                                                             (uint64_t)wf->sm_count * 2 * PB2_SHADE_BLOCKS));
+    k_shade<0, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    k_shade<1, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    k_shade<2, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
 }
 void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
                   const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {

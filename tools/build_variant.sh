@@ -7,7 +7,7 @@ OUT=../build/var_$NAME; mkdir -p $OUT
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-std=c++17 -O3 $ARCH -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-pthread $DEFS"
-for f in api api_path kernels_traverse wavefront bvh_hlbvh; do $NVCC $FLAGS -c csrc/$f.cu -o $OUT/$f.o & done
+for f in api api_path kernels_traverse wavefront light_distrib bvh_hlbvh; do $NVCC $FLAGS -c csrc/$f.cu -o $OUT/$f.o & done
 for f in bvh_build camera_host; do $NVCC $FLAGS -x cu -c csrc/$f.cpp -o $OUT/$f.o & done
 wait
 $NVCC -shared $ARCH -o ../build/libpbrt_b200_$NAME.so $OUT/*.o -ldl
