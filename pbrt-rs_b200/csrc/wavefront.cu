@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "camera.cuh"
 #include "trace_persistent.cuh"
@@ -26,18 +28,107 @@ namespace {
 constexpr float kInf = __builtin_huge_valf();
 constexpr int kThreads = 256;
 
-// Queue append with one atomic per group of lanes that reach this point together (warp-aggregated): every queue has a
-// single tail counter, and one atomicAdd per path on one address serialises in the L2 atomic unit (~0.85 cycles per lane,
-// measured 2.7 ms per 4.2 M-ray extend launch before aggregation).
-__device__ __forceinline__ void queue_push(unsigned long long* counter, uint32_t* queue, uint32_t slot) {
-    // lanes are grouped by target counter: extend bins hits into one queue per material type
-    const unsigned mask = __match_any_sync(__activemask(), (unsigned long long)counter);
-    const int leader = __ffs(mask) - 1;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    queue[base + (unsigned)__popc(mask & ((1u << lane) - 1u))] = slot;
+// ---- order-preserving queues -------------------------------------------------------------------------------------------------
+// The stages talk through queues of path slots.  The visibility / shade kernels do not append to them: each leaves one byte per
+// path (PathBuffers::state) and compact_queues() rebuilds the queues from the bounce's active queue with a stable three-way
+// select, so every queue stays sorted by slot and neighbouring lanes of the next kernel read neighbouring path state.
+// (Appending in completion order of the persistent traversal — one warp-aggregated atomic per group of lanes — scattered a
+// warp's slots over a ~150 K-slot window; with the queues sorted k_shade runs 34-39 % faster, k_shadow 11-22 %, k_extend 3-8 %:
+// profiles/r01_tuning.md, session 4.)
+constexpr unsigned kStateDead = 3u;            // bits 0-1: shading class of the hit, 3 = the ray escaped
+constexpr unsigned kStateContinues = 4u;       // bit 2: the path continues with the ray k_shade wrote
+constexpr int kCompactThreads = 256;           // bits 3, 4: shadow ray / MIS ray of the NEE record pending
+
+struct CompactJob {
+    const uint32_t* in;                        // the bounce's active queue (sorted by slot)
+    const unsigned long long* n_in;
+    const uint8_t* state;
+    uint32_t* out[3];
+    unsigned long long* n_out[3];
+    int by_class;                              // 1: out[k] takes class k (after k_extend); 0: out[k] takes bit 2 + k (after k_shade)
+    uint32_t* counts;                          // [3][gridDim.x]
+};
+__device__ __forceinline__ bool compact_pred(const CompactJob& j, unsigned st, int k) {
+    return j.by_class ? (st & 3u) == (unsigned)k : ((st >> (2 + k)) & 1u) != 0u;
+}
+// CTA b owns the contiguous chunk [b * chunk, (b + 1) * chunk) of the input queue in both passes.
+__device__ __forceinline__ void compact_chunk(unsigned long long n, uint32_t* begin, uint32_t* end) {
+    const unsigned long long chunk = (((n + gridDim.x - 1) / gridDim.x) + kCompactThreads - 1) / kCompactThreads * kCompactThreads;
+    const unsigned long long b0 = (unsigned long long)blockIdx.x * chunk;
+    *begin = (uint32_t)(b0 < n ? b0 : n);
+    *end = (uint32_t)(b0 + chunk < n ? b0 + chunk : n);
+}
+__global__ void __launch_bounds__(kCompactThreads) k_compact_count(CompactJob j) {
+    uint32_t begin, end;
+    compact_chunk(*j.n_in, &begin, &end);
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    for (uint32_t i = begin + threadIdx.x; i < end; i += kCompactThreads) {
+        const unsigned st = j.state[j.in[i]];
+        c0 += compact_pred(j, st, 0); c1 += compact_pred(j, st, 1); c2 += compact_pred(j, st, 2);
+    }
+    __shared__ unsigned sh[3][kCompactThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_down_sync(0xFFFFFFFFu, c0, o); c1 += __shfl_down_sync(0xFFFFFFFFu, c1, o); c2 += __shfl_down_sync(0xFFFFFFFFu, c2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = c0; sh[1][threadIdx.x >> 5] = c1; sh[2][threadIdx.x >> 5] = c2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned t = 0;
+        for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[threadIdx.x][w];
+        j.counts[threadIdx.x * gridDim.x + blockIdx.x] = t;
+    }
+}
+// One CTA: exclusive scan of the per-CTA counts of each output (n_ctas <= 1024), totals into the queue counters.
+__global__ void __launch_bounds__(1024) k_compact_scan(CompactJob j, int n_ctas) {
+    __shared__ unsigned sh[1024];
+    for (int k = 0; k < 3; ++k) {
+        const unsigned v = (int)threadIdx.x < n_ctas ? j.counts[k * n_ctas + threadIdx.x] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned add = (int)threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < n_ctas) j.counts[k * n_ctas + threadIdx.x] = sh[threadIdx.x] - v;
+        if (threadIdx.x == 1023) *j.n_out[k] = sh[1023];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kCompactThreads) k_compact_scatter(CompactJob j) {
+    uint32_t begin, end;
+    compact_chunk(*j.n_in, &begin, &end);
+    __shared__ unsigned warp_tot[3][kCompactThreads / 32];
+    unsigned base[3];
+    for (int k = 0; k < 3; ++k) base[k] = j.counts[k * gridDim.x + blockIdx.x];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t t0 = begin; t0 < end; t0 += kCompactThreads) {          // tiles in queue order: the select is stable
+        const uint32_t i = t0 + threadIdx.x;
+        const bool in_range = i < end;
+        const uint32_t slot = in_range ? j.in[i] : 0u;
+        const unsigned st = in_range ? j.state[slot] : (j.by_class ? kStateDead : 0u);
+        bool f[3];
+        unsigned rank[3];
+        for (int k = 0; k < 3; ++k) {
+            f[k] = compact_pred(j, st, k);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, f[k]);
+            rank[k] = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) warp_tot[k][warp] = __popc(m);
+        }
+        __syncthreads();
+        for (int k = 0; k < 3; ++k) {
+            unsigned before = 0, total = 0;
+            for (int w = 0; w < kCompactThreads / 32; ++w) {
+                const unsigned c = warp_tot[k][w];
+                before += (unsigned)w < warp ? c : 0u;
+                total += c;
+            }
+            if (f[k]) j.out[k][base[k] + before + rank[k]] = slot;
+            base[k] += total;
+        }
+        __syncthreads();
+    }
 }
 
 // ---- slot <-> (pixel, sample) -----------------------------------------------------------------------------------
@@ -350,12 +441,11 @@ struct ExtendSink {
             resolve_nee(b, slot, lit, t1, reached_light, t2);
             return;
         }
-        if (!found) return;                              // escaped: no infinite lights in scope, the path is finished
         const uint32_t slot = queue[i];
+        if (!found) { b.state[slot] = kStateDead; return; }      // escaped: no infinite lights in scope, the path is finished
         const uint32_t prim = b.hit[slot].x;             // written by this thread's last accept()
-        const int type = sh.mats[sh.tri_material[prim]].cls;      // shading class: the queue of the k_shade instantiation that handles it
-        // (selects, not b.q_mat[type]: a run-time index would move the whole parameter struct into local memory)
-        queue_push(&b.counters[C_MAT0 + type], type == 0 ? b.q_mat[0] : (type == 1 ? b.q_mat[1] : b.q_mat[2]), slot);
+        // shading class = the k_shade instantiation that handles the hit; compact_queues() bins the slots by it (material-sorted shading)
+        b.state[slot] = (uint8_t)sh.mats[sh.tri_material[prim]].cls;
     }
     PB2_D void occluded(uint32_t, bool) const {}
 };
@@ -444,7 +534,7 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
 }
 // estimate_direct (integrator.rs:136-266) up to the two visibility queries: fills the NEE record of `slot`.
 template <bool SG, class BsdfType>
-__device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeView& sh, const PathBuffers& b, uint32_t slot, const Vertex& v, vec3 wo,
+__device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const ShadeView& sh, const PathBuffers& b, uint32_t slot, const Vertex& v, vec3 wo,
                                                 const BsdfType& bsdf, const DLight& light, float pick_pdf, float ul0, float ul1, float us0,
                                                 float us1, rgb3 beta) {
     const unsigned flags = kAllLobes & ~kSpecular;                       // D23 FIX
@@ -560,19 +650,18 @@ __device__ __forceinline__ void direct_lighting(const SceneView& s, const ShadeV
             }
         }
     }
-    if (pending == 0u) return;
+    if (pending == 0u) return 0u;
     b.sh_o[slot] = make_float4(sh_o.x, sh_o.y, sh_o.z, 1.0f - PB2_SHADOW_EPS);
     b.sh_d[slot] = make_float4(sh_d.x, sh_d.y, sh_d.z, pick_pdf);
     b.t1[slot] = make_float4(t1.r, t1.g, t1.b, __uint_as_float(pending));
     b.beta_nee[slot] = make_float4(beta.r, beta.g, beta.b, 0.0f);
-    if (pending & 1u) queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
     if (pending & 2u) {
         b.mis_o[slot] = make_float4(mis_o.x, mis_o.y, mis_o.z, 0.0f);
         b.mis_d[slot] = make_float4(mis_d.x, mis_d.y, mis_d.z, 0.0f);
         b.t2[slot] = make_float4(t2.r, t2.g, t2.b, __uint_as_float(light.prim));
-        queue_push(&b.counters[C_MIS], b.q_mis, slot);
     }
     (void)s;
+    return pending;                                  // bit 0: shadow ray, bit 1: MIS ray — queued by compact_queues()
 }
 
 // One path vertex of PathIntegrator::li (path.rs:79-209) for every hit of material type `mat`.
@@ -608,6 +697,7 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
             }
         }
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
+        unsigned queued = (unsigned)MAT;                                 // b.state[slot]: class | continues << 2 | NEE rays << 3
         if (alive) {
             const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.sn, v.sdpdu);
             PathSampler rng;
@@ -629,7 +719,7 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
                     float ul0, ul1, us0, us1;
                     rng.next2<TABLES>(&ul0, &ul1);
                     rng.next2<TABLES>(&us0, &us1);
-                    direct_lighting<SG>(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta);
+                    queued |= direct_lighting<SG>(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta) << 3;
                 }
             }
             float u0, u1;
@@ -660,10 +750,11 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
                     b.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
                     b.rng[slot] = rng.save();
                     Lf.w = __uint_as_float(bounces | ((spec ? 1u : 0u) << 16) | (TABLES ? rng.extra() << 17 : 0u));
-                    queue_push(&b.counters[C_ACTIVE_A + (cur ^ 1)], b.q_active[cur ^ 1], slot);
+                    queued |= kStateContinues;
                 }
             }
         }
+        b.state[slot] = (uint8_t)queued;
         b.L[slot] = make_float4(L.r, L.g, L.b, Lf.w);
     }
 }
@@ -901,6 +992,20 @@ unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
     return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
 }
 
+// Stable three-way select of the active queue `in` by the paths' state bytes (see CompactJob); counts stay on the device.
+void compact_queues(Wavefront* wf, const uint32_t* in, int n_in, bool by_class, uint32_t* o0, int c0, uint32_t* o1, int c1, uint32_t* o2, int c2,
+                    cudaStream_t st) {
+    const PathBuffers& b = wf->b;
+    CompactJob j;
+    j.in = in; j.n_in = b.counters + n_in; j.state = b.state; j.by_class = by_class ? 1 : 0; j.counts = b.compact_counts;
+    j.out[0] = o0; j.out[1] = o1; j.out[2] = o2;
+    j.n_out[0] = b.counters + c0; j.n_out[1] = b.counters + c1; j.n_out[2] = b.counters + c2;
+    const int n_ctas = std::min(1024, wf->sm_count * 4);
+    k_compact_count<<<n_ctas, kCompactThreads, 0, st>>>(j);
+    k_compact_scan<<<1, 1024, 0, st>>>(j, n_ctas);
+    k_compact_scatter<<<n_ctas, kCompactThreads, 0, st>>>(j);
+}
+
 // k_shade<material, PixelSampler tables, mesh shading geometry> for the three material queues of one bounce.
 template <bool TABLES, bool SG>
 void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
@@ -932,12 +1037,18 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         const int cur = depth & 1;
         k_iter_begin<<<1, 32, 0, st>>>(b, cur);
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
+        // hits -> one queue per shading class (material-sorted shading)
+        compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, true, b.q_mat[0], C_MAT0, b.q_mat[1], C_MAT1, b.q_mat[2], C_MAT2, st);
         launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
-        if (depth < pp.max_depth && sh.n_lights > 0) {
+        launches += 8;
+        if (depth == pp.max_depth) break;                                // path.rs:90-92: nothing continues, no NEE record was written
+        compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, false, b.q_active[cur ^ 1], C_ACTIVE_A + (cur ^ 1), b.q_shadow, C_SHADOW,
+                       b.q_mis, C_MIS, st);
+        launches += 3;
+        if (sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
             launches += 1;
         }
-        launches += 5;
     }
     wf->totals[4] += (uint64_t)launches;
 }
@@ -952,7 +1063,7 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     cudaDeviceGetAttribute(&wf->sm_count, cudaDevAttrMultiProcessorCount, dev);
     // one arena: 13 float4/uint4 arrays, rng, occluded, mis_prim, 7 queues, counters
     const size_t f4 = capacity * 16;
-    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + capacity + 7 * capacity * 4 + C_COUNT * 8 + 4096;
+    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + 2 * capacity + 7 * capacity * 4 + C_COUNT * 8 + 3 * 1024 * 4 + 8192;
     cudaError_t e = cudaMalloc(&wf->arena, bytes);
     if (e != cudaSuccess) { delete wf; *out = nullptr; return (int)e; }
     char* p = (char*)wf->arena;
@@ -965,6 +1076,8 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     b.rng = (unsigned long long*)take(capacity * 8);
     b.mis_prim = (uint32_t*)take(capacity * 4);
     b.occluded = (uint8_t*)take(capacity);
+    b.state = (uint8_t*)take(capacity);
+    b.compact_counts = (uint32_t*)take(3 * 1024 * 4);
     for (int i = 0; i < 2; ++i) b.q_active[i] = (uint32_t*)take(capacity * 4);
     for (int i = 0; i < 3; ++i) b.q_mat[i] = (uint32_t*)take(capacity * 4);
     b.q_shadow = (uint32_t*)take(capacity * 4);

@@ -128,6 +128,10 @@ struct PathBuffers {
     uint32_t* q_shadow;
     uint32_t* q_mis;
     unsigned long long* counters;
+    // order-preserving queues: what became of the path in `slot` this bounce — bits 0-1 shading class of its hit (3 = no hit),
+    // bit 2 continues, bit 3 shadow ray pending, bit 4 MIS ray pending — and the per-CTA counts of the compaction passes
+    uint8_t* state;
+    uint32_t* compact_counts;
 };
 
 struct PathParams {
