@@ -94,6 +94,7 @@ struct pb2_scene {
     float light_func_int[2] = {0.0f, 0.0f};
     // SpatialLightDistribution tables (lightdistrib.rs:71-220), filled on the device the first time "spatial" is asked for:
     // [func n_vox * n | cdf n_vox * (n + 1) | func_int n_vox] floats in one allocation
+    unsigned shading_class_mask = 7u;   // bit c: a material of shading class c exists (api_path.cu: upload_shading_tables)
     void* d_spatial = nullptr;
     int spatial_nv[3] = {0, 0, 0};
     pb2::SceneView view;

@@ -74,6 +74,7 @@ int upload_shading_tables(pb2_scene* scene) {
     const size_t n_tris = scene->indices.size() / 3;
     if (scene->tri_material.empty() || n_tris == 0) return PB2_OK;       // ray-casting-only scene
     std::vector<DMaterial> mats(scene->materials.size());
+    unsigned class_mask = 0u;
     for (size_t i = 0; i < mats.size(); ++i) {
         const pb2_material& m = scene->materials[i];
         if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_SUBSTRATE) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
@@ -91,7 +92,9 @@ int upload_shading_tables(pb2_scene* scene) {
         }
         // shading class (shade.cuh: make_bsdf<CLS>)
         d.cls = (m.type == PB2_MAT_MATTE && m.sigma == 0.0f) ? 0 : (((m.type == PB2_MAT_GLASS && m.roughness == 0.0f) || m.type == PB2_MAT_MIRROR) ? 2 : 1);
+        class_mask |= 1u << d.cls;
     }
+    scene->shading_class_mask = class_mask;
     const size_t n_lights = scene->lights.size();
     std::vector<DLight> lights(std::max<size_t>(1, n_lights));
     std::vector<int32_t> tri_light(n_tris, -1);
@@ -213,6 +216,7 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
     v.mats = (const DMaterial*)s->d_materials;
     v.lights = (const DLight*)s->d_lights;
     v.n_lights = (int)n;
+    v.class_mask = s->shading_class_mask;
     const float* base = (const float*)s->d_light_cdf;
     const size_t off = strategy == PB2_LIGHTS_POWER ? (2 * n + 1) : 0;
     v.light_func = base + off;

@@ -96,38 +96,53 @@ __global__ void __launch_bounds__(1024) k_compact_scan(CompactJob j, int n_ctas)
         __syncthreads();
     }
 }
+// Four consecutive queue entries per thread, one barrier per 1024-entry tile (the warp totals are double-buffered).
 __global__ void __launch_bounds__(kCompactThreads) k_compact_scatter(CompactJob j) {
+    constexpr int kItems = 4;
     uint32_t begin, end;
-    compact_chunk(*j.n_in, &begin, &end);
-    __shared__ unsigned warp_tot[3][kCompactThreads / 32];
+    compact_chunk(*j.n_in, &begin, &end);                                 // begin is a multiple of 256: 16-byte aligned loads
+    __shared__ unsigned warp_tot[2][3][kCompactThreads / 32];
     unsigned base[3];
-    for (int k = 0; k < 3; ++k) base[k] = j.counts[k * gridDim.x + blockIdx.x];
+    for (int q = 0; q < 3; ++q) base[q] = j.counts[q * gridDim.x + blockIdx.x];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t t0 = begin; t0 < end; t0 += kCompactThreads) {          // tiles in queue order: the select is stable
-        const uint32_t i = t0 + threadIdx.x;
-        const bool in_range = i < end;
-        const uint32_t slot = in_range ? j.in[i] : 0u;
-        const unsigned st = in_range ? j.state[slot] : (j.by_class ? kStateDead : 0u);
-        bool f[3];
-        unsigned rank[3];
-        for (int k = 0; k < 3; ++k) {
-            f[k] = compact_pred(j, st, k);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, f[k]);
-            rank[k] = __popc(m & ((1u << lane) - 1u));
-            if (lane == 0) warp_tot[k][warp] = __popc(m);
+    int buf = 0;
+    for (uint32_t t0 = begin; t0 < end; t0 += kCompactThreads * kItems, buf ^= 1) {      // tiles in queue order: the select is stable
+        const uint32_t i0 = t0 + threadIdx.x * kItems;
+        uint32_t slot[kItems];
+        if (i0 + kItems <= end) {
+            const uint4 v = *reinterpret_cast<const uint4*>(j.in + i0);
+            slot[0] = v.x; slot[1] = v.y; slot[2] = v.z; slot[3] = v.w;
+        } else {
+            for (int k = 0; k < kItems; ++k) slot[k] = i0 + k < end ? j.in[i0 + k] : 0u;
         }
+        unsigned st[kItems];
+        for (int k = 0; k < kItems; ++k) st[k] = i0 + k < end ? j.state[slot[k]] : (j.by_class ? kStateDead : 0u);
+        unsigned cnt[3], inc[3];
+        for (int q = 0; q < 3; ++q) {
+            cnt[q] = 0;
+            for (int k = 0; k < kItems; ++k) cnt[q] += compact_pred(j, st[k], q) ? 1u : 0u;
+            inc[q] = cnt[q];
+        }
+        for (int o = 1; o < 32; o <<= 1)
+            for (int q = 0; q < 3; ++q) {
+                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, inc[q], o);
+                if (lane >= (unsigned)o) inc[q] += v;
+            }
+        if (lane == 31u)
+            for (int q = 0; q < 3; ++q) warp_tot[buf][q][warp] = inc[q];
         __syncthreads();
-        for (int k = 0; k < 3; ++k) {
+        for (int q = 0; q < 3; ++q) {
             unsigned before = 0, total = 0;
             for (int w = 0; w < kCompactThreads / 32; ++w) {
-                const unsigned c = warp_tot[k][w];
+                const unsigned c = warp_tot[buf][q][w];
                 before += (unsigned)w < warp ? c : 0u;
                 total += c;
             }
-            if (f[k]) j.out[k][base[k] + before + rank[k]] = slot;
-            base[k] += total;
+            unsigned pos = base[q] + before + inc[q] - cnt[q];
+            for (int k = 0; k < kItems; ++k)
+                if (compact_pred(j, st[k], q)) j.out[q][pos++] = slot[k];
+            base[q] += total;
         }
-        __syncthreads();
     }
 }
 
@@ -1012,9 +1027,10 @@ void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, con
                     const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + PB2_SHADE_THREADS - 1) / PB2_SHADE_THREADS,
                                                                              (uint64_t)wf->sm_count * 2 * PB2_SHADE_BLOCKS));
-    k_shade<0, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
-    k_shade<1, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
-    k_shade<2, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    // (a class no material of the scene has leaves its queue empty every bounce: no launch)
+    if (sh.class_mask & 1u) k_shade<0, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    if (sh.class_mask & 2u) k_shade<1, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
+    if (sh.class_mask & 4u) k_shade<2, TABLES, SG><<<grid, PB2_SHADE_THREADS, 0, st>>>(sv, sh, b, map, film, pp, cur);
 }
 void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
                   const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
@@ -1040,7 +1056,7 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         // hits -> one queue per shading class (material-sorted shading)
         compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, true, b.q_mat[0], C_MAT0, b.q_mat[1], C_MAT1, b.q_mat[2], C_MAT2, st);
         launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
-        launches += 8;
+        launches += 5 + __builtin_popcount(sh.class_mask & 7u);
         if (depth == pp.max_depth) break;                                // path.rs:90-92: nothing continues, no NEE record was written
         compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, false, b.q_active[cur ^ 1], C_ACTIVE_A + (cur ^ 1), b.q_shadow, C_SHADOW,
                        b.q_mis, C_MIS, st);

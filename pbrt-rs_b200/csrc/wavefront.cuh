@@ -42,6 +42,7 @@ struct ShadeView {
     const DMaterial* mats;
     const DLight* lights;
     int n_lights;
+    unsigned class_mask;          // bit c: some material of the scene has shading class c (k_shade<c> is launched only then)
     const float* light_func;      // Distribution1D func[n_lights]
     const float* light_cdf;       // cdf[n_lights + 1]
     float light_func_int;
