@@ -110,6 +110,63 @@ def algorithmic_bytes(n_rays, nodes, tris, hit_bytes):
     return n_rays * (32 + hit_bytes) + 32 * int(nodes) + 36 * int(tris)
 
 
+PATH_STATE_BYTES_8D = 160     # SoA path state read + write per path segment (ray 32 + beta 12 + L 12 + pixel 4 + rng 16 + flags 4, each way)
+
+
+def path_roofline(rays_gpu, n_samples, ms, cnt, peak, peak_src, traffic_key):
+    """SURVEY §8d, per path sample: B = sum over its rays of B(r) + 160 x (path segments) + 16 (film).  rays_gpu = the device's
+    own ray counts for the timed frame; nodes / triangles per ray of each kind from the oracle's instrumented render of a
+    bounded sample range of the same frame (reference traversal order).  The achieved figure is whole-frame: every kernel
+    of the wavefront (extend, shade, shadow, compaction, film) runs inside `ms`."""
+    kinds = (("extend", "extend_rays", 16), ("shadow", "shadow_rays", 4), ("mis", "mis_rays", 16))
+    ray_bytes, per_kind = 0.0, {}
+    for k, gk, hb in kinds:
+        r = max(1, cnt["rays"][k])
+        npr, tpr = cnt["nodes"][k] / r, cnt["tris"][k] / r
+        b = rays_gpu[gk] * (32 + hb + 32 * npr + 36 * tpr)
+        ray_bytes += b
+        per_kind[k] = {"rays": rays_gpu[gk], "nodes_per_ray": npr, "tris_per_ray": tpr, "bytes": b}
+    state_bytes = PATH_STATE_BYTES_8D * rays_gpu["extend_rays"]
+    total = ray_bytes + state_bytes + 16.0 * n_samples
+    gbs = total / (ms * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": "whole wavefront frame (k_extend + k_shade + k_shadow + queue compaction + film)", "achieved": gbs, "peak": peak,
+           "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src, "algorithmic_bytes": total,
+           "bytes_per_sample": total / n_samples, "ray_bytes": ray_bytes, "state_bytes_8d": state_bytes, "film_bytes": 16.0 * n_samples,
+           "per_ray_kind": per_kind, "segments_per_sample": rays_gpu["extend_rays"] / n_samples,
+           "state_bytes_actual_per_segment": 250,
+           "note": "the §8d state term counts 160 B per segment; the SoA arrays this build reads and writes per segment (ray, hit, beta, L, rng, "
+                   "NEE record, state byte, queue entries) come to ~250 B, so real HBM traffic for state is ~1.6x the term above",
+           "traffic": None}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = tj.get("path", {}).get(traffic_key)
+        if t:
+            # dram bytes of one ncu-captured batch, scaled to the timed frame by camera samples
+            out["traffic"] = t["dram_bytes"] * (n_samples / t["camera_samples"])
+            out["traffic_source"] = t.get("source")
+            out["dram_frac"] = out["traffic"] / (ms * 1e-3) / 1e9 / peak
+            out["kernel_share"] = t.get("kernel_share")
+    except (OSError, KeyError, ValueError):
+        pass
+    return out
+
+
+def load_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def bench_config(n_tris, res):
+    """The `config` object of both arms (the repo's and --impl reference): same keys, same values."""
+    return {"workload": f"C3: {n_tris}-triangle displaced grid, {res}x{res} primary closest-hit + shadow any-hit + "
+                        "incoherent bounce closest-hit, SAH BVH max_prims_in_node=4", "rays_per_step_per_gpu": 3 * res * res}
+
+
 def host_info():
     model = ""
     try:
@@ -199,17 +256,27 @@ def bench_path_c4(pb2, scenes, torch, args, dist, world, spp_timed=256):
     torch.cuda.synchronize()
     c1 = integ.counters()
     tot = float(sum(a.elapsed_time(b) for a, b in ev))
+    # e2e: the call a user makes — render the frame, then read the film back to the host (wall clock, copy included)
+    film.clear()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    integ.render(film, 0, spp_timed, stream=stream)
+    xyzw = film.read_xyzw()
+    e2e_s = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        t = torch.tensor([tot, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot = float(t[0])
+        tot, e2e_s = float(t[0]), float(t[1])
     n_samples = cam["res"][0] * cam["res"][1] * spp_timed
     rays = {k: (c1[k] - c0[k]) / steps for k in ("extend_rays", "shadow_rays", "mis_rays")}
     return {"workload": f"C4: {len(sc['idx'])}-triangle room, matte / plastic / glass spheres, area + point light, PathIntegrator maxdepth=8, "
                         f"1920x1080, sample indices [0,{spp_timed}) of 256 spp per step, power light distribution",
             "unit": "Msamples/s", "value": world * n_samples * steps / (tot * 1e-3) / 1e6, "ms_per_step": tot / steps,
             "samples_per_step": n_samples, "rays_per_step": rays, "mrays_per_s": sum(rays.values()) / (tot / steps * 1e-3) / 1e6,
-            "mean_rgb": [float(v) for v in pb2_mean_rgb(film)]}
+            "e2e": {"value": world * n_samples / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 192,
+                    "d2h_bytes_per_step": int(xyzw.nbytes), "api": "pb2_render_path + pb2_film_read_xyzw (wall clock, one frame)"},
+            "kernel_launches_per_step": (c1["kernel_launches"] - c0["kernel_launches"]) / steps,
+            "mean_rgb": [float(v) for v in pb2_mean_rgb(film)]}, (accel, camera, integ, film, sc)
 
 
 def pb2_mean_rgb(film):
@@ -235,6 +302,30 @@ def bench_path_cpu(orc_mod, scenes, sc, gpu_film_xyzw):
             "sample": f"sample indices [0,{PATH_CPU_SPP}) of the 64 spp of every pixel ({n:,} camera samples), render time only"}, xyzw
 
 
+def bench_path_c4_cpu(scenes, keep, spp_cpu=2):
+    """C4 on the CPU: the oracle renders sample indices [0, spp_cpu) of every pixel (all host threads) = cpu_baseline; the GPU
+    film of the same range must equal it bit for bit = parity; a counted render of sample index 0 feeds the roofline."""
+    from oracle import oracle_path as OP
+    accel, camera, integ, film, sc = keep
+    cam = scenes.C4_CAMERA
+    pk = dict(scenes.C4_PATH)
+    ref = OP.Scene(sc, 4)
+    fd = OP.film_desc(cam["res"])
+    ref_xyzw, dt = ref.render(cam, fd, OP.path_desc(sample_begin=0, sample_end=spp_cpu, **pk), mode=1)
+    film.clear()
+    integ.render(film, 0, spp_cpu)
+    g_xyzw = film.read_xyzw()
+    n = cam["res"][0] * cam["res"][1] * spp_cpu
+    cores, model = host_info()
+    cpu = {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": model,
+           "sample": f"sample indices [0,{spp_cpu}) of the 256 spp of every pixel ({n:,} camera samples), render time only"}
+    parity = {"pixels_checked": int(g_xyzw.shape[0] * g_xyzw.shape[1]),
+              "pixels_differing": int((g_xyzw.view(np.uint32) != ref_xyzw.view(np.uint32)).any(axis=2).sum()),
+              "checked_against": f"oracle SamplerIntegrator::render, per-(pixel,sample) sampler streams, samples [0,{spp_cpu}), bitwise"}
+    _, _, cnt = ref.render_counted(cam, fd, OP.path_desc(sample_begin=0, sample_end=1, **pk), mode=1)
+    return cpu, parity, cnt
+
+
 def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
     """BASELINE config 4 (C5): the C4 scene (matte / plastic / glass spheres, area + point light, maxdepth 8, power light
     distribution) at 3840x2160 @ 1024 spp, the sample indices of every pixel split across the GPUs (partition_samples), the
@@ -252,7 +343,7 @@ def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
         uid = [pb2.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         pb2.nccl_init(uid[0], rank, world)
-    steps = 2
+    steps = 2 if world > 1 else 1               # N=1: one 14 s frame is the anchor of the strong-scaling curve
     s0, s1 = pb2.partition_samples(spp, rank, world)
 
     def frame(ev=None, end=None):
@@ -267,7 +358,7 @@ def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
         if ev:
             ev[2].record()
 
-    for _ in range(3):
+    for _ in range(3 if world > 1 else 1):
         frame(end=min(s1, s0 + 8))              # warm-up: 8 sample indices per GPU (same kernels, same buffers)
     torch.cuda.synchronize()
     if world > 1:
@@ -302,13 +393,47 @@ def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
     out = {"workload": f"C5: {len(sc['idx'])}-triangle matte/plastic/glass room, maxdepth 8, 3840x2160 @ {spp} spp, sample indices split over "
                        f"{world} GPUs ({s1 - s0} per GPU), one ncclReduce of the float4 film (132.7 MB) to rank 0",
            "unit": "Msamples/s", "scaling": "strong", "value": n_samples * steps / (total_ms * 1e-3) / 1e6, "ms_per_frame": total_ms / steps,
+           "samples_per_frame": n_samples, "frames_timed": steps,
            "render_ms": render_ms / steps, "film_reduce_ms": reduce_ms / steps, "film_reduce_frac_of_frame": reduce_ms / total_ms,
            "film_reduce_note": "film_reduce_ms runs from this rank's last render kernel to the end of ncclReduce, max over ranks: it includes the wait "
                                "for the slowest renderer; film_reduce_alone_ms is the collective with the ranks aligned",
            "film_reduce_alone_ms": reduce_alone_ms,
            "film_reduce_alone_frac_of_frame": None if reduce_alone_ms is None else reduce_alone_ms / (total_ms / steps)}
+    # parity of the split + ncclReduce: sample indices [0, 2N) of the 1024 split over the N ranks and reduced to
+    # rank 0, against the same N ranges rendered one after the other into one film by rank 0 alone.  Weights are sums of
+    # ones (exact in any order); XYZ sums differ only by the association of N float adds.
     if world > 1:
+        p0, p1 = pb2.partition_samples(2 * world, rank, world)
+        film.clear()
+        integ.render(film, p0, p1, stream=stream)
+        film.reduce(0, stream=stream)
+        torch.cuda.synchronize()
+        if rank == 0:
+            got = film.read_xyzw()
+            film.clear()
+            for r in range(world):
+                a, b = pb2.partition_samples(2 * world, r, world)
+                integ.render(film, a, b, stream=stream)
+            torch.cuda.synchronize()
+            want = film.read_xyzw()
+            den = np.maximum(np.abs(want[..., :3]), 1e-6)
+            rel = float((np.abs(got[..., :3] - want[..., :3]) / den).max())
+            out["parity"] = {"pixels_checked": int(want.shape[0] * want.shape[1]), "max_rel_diff": rel,
+                             "weights_equal": bool(np.array_equal(got[..., 3], want[..., 3])),
+                             "bitwise_equal_pixels": int((got.view(np.uint32) == want.view(np.uint32)).all(axis=2).sum()),
+                             "ok": bool(rel <= 1e-6 and np.array_equal(got[..., 3], want[..., 3])),
+                             "checked_against": f"rank 0 rendering the same {world} sample ranges of [0,{2 * world}) alone into one film; tolerance 1e-6 "
+                                                "relative on X, Y, Z (float association of the reduce), weights exact"}
+        dist.barrier()
         pb2.nccl_shutdown()
+    # N=1 anchor of the strong-scaling curve (measured by this bench at --gpus 1 and committed; the driver computes its own ratios)
+    try:
+        n1 = json.load(open(os.path.join(ROOT, "profiles", "c5_n1_anchor.json")))
+        out["n1_anchor"] = n1
+        if world > 1:
+            out["efficiency_vs_n1"] = out["value"] / (world * n1["msamples_s"])
+    except (OSError, KeyError, ValueError):
+        pass
     return out
 
 
@@ -344,8 +469,7 @@ def run_reference(args):
         "impl": "reference", "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C3: {len(idx)}-triangle displaced grid, {args.res}x{args.res} primary closest-hit + shadow any-hit + "
-                               "incoherent bounce closest-hit, SAH BVH max_prims_in_node=4"},
+        "config": bench_config(len(idx), args.res),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
                          "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays per step), traversal time only"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -492,9 +616,9 @@ def main():
     # ---- path tracing (second half of the BASELINE metric) ----
     dist_mod = dist if world > 1 else None
     path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
-    path_c4 = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
-    path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world) if world > 1 else None
-    path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0])
+    path_c4, path_c4_keep = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
+    path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world)
+    path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0] + path_c4["kernel_launches_per_step"] * 2)
 
     # ---- BVH build: SplitMethod::HLBVH built on the GPU next to the host SAH build, and what the C3
     # ray sets cost on that tree (same rays, same hits: tests/ compare ids and t bits)
@@ -536,13 +660,7 @@ def main():
     e2e_value = world * rays_per_step * args.steps / e2e_s / 1e6
 
     # ---- roofline + cpu baseline (rank 0, after the GPU timing so host threads do not perturb it) ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    peak, peak_src = load_peak()
     roofline, cpu_baseline, parity = None, None, None
     if rank == 0 and not args.no_cpu_baseline:
         orc = ge.load_oracle()
@@ -569,14 +687,25 @@ def main():
         dom = max(("closest_primary", "any_shadow", "closest_bounce"), key=lambda k: kernel_ms[k])
         # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (profiles/traffic.json,
         # written by tools/ncu_traffic.py from the .ncu-rep; dram__bytes_read.sum + dram__bytes_write.sum)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, lanes = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic, traffic_src = tj["launches"].get(dom), tj.get("source")
+            lanes = tj.get("lanes_per_inst", {}).get(dom)
+            for name in per_kernel:
+                if tj["launches"].get(name):
+                    per_kernel[name]["dram_bytes"] = tj["launches"][name]
+                    per_kernel[name]["dram_frac"] = tj["launches"][name] / (kernel_ms[name] * 1e-3) / 1e9 / peak
+                    per_kernel[name]["lanes_per_inst"] = tj.get("lanes_per_inst", {}).get(name)
         except (OSError, KeyError, ValueError):
             pass
         roofline = {"bound": "hbm", "kernel": f"k_closest_hit/k_any_hit [{dom}]", "achieved": per_kernel[dom]["gbs"], "peak": peak,
                     "unit": "GB/s", "frac": per_kernel[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    # what the DRAM counters saw (ncu capture of the same launch) against the same peak, and the mean number of
+                    # active lanes per executed warp instruction: `frac` above follows SURVEY §8d's byte definition, which counts
+                    # every node / triangle visit as HBM traffic although the upper tree is served by L1 / L2
+                    "dram_frac": None if traffic is None else traffic / (kernel_ms[dom] * 1e-3) / 1e9 / peak,
+                    "lanes_per_inst": lanes,
                     "peak_source": peak_src, "per_kernel": per_kernel}
         k = max(1, args.cpu_stride)
         sample = [np.ascontiguousarray(g_rays[::k]), np.ascontiguousarray(g_srays[::k]), np.ascontiguousarray(g_brays[::k])]
@@ -600,16 +729,28 @@ def main():
         path_c2["parity"] = {"pixels_checked": int(g_xyzw.shape[0] * g_xyzw.shape[1]),
                              "pixels_differing": int((g_xyzw.view(np.uint32) != ref_xyzw.view(np.uint32)).any(axis=2).sum()),
                              "checked_against": f"oracle SamplerIntegrator::render, per-(pixel,sample) sampler streams, samples [0,{PATH_CPU_SPP})"}
+        from oracle import oracle_path as OP
+        _, _, cnt2 = OP.Scene(sc2, 4).render_counted(scenes.C2_CAMERA, OP.film_desc(scenes.C2_CAMERA["res"]),
+                                                    OP.path_desc(sample_begin=0, sample_end=4, **scenes.C2_PATH), mode=1)
+        path_c2["roofline"] = path_roofline(path_c2["rays_per_frame"], path_c2["samples_per_frame"], path_c2["ms_per_frame"], cnt2, peak, peak_src, "c2")
+        c4_cpu, c4_parity, cnt4 = bench_path_c4_cpu(scenes, path_c4_keep)
+        path_c4["cpu_baseline"], path_c4["parity"] = c4_cpu, c4_parity
+        path_c4["roofline"] = path_roofline(path_c4["rays_per_step"], path_c4["samples_per_step"], path_c4["ms_per_step"], cnt4, peak, peak_src, "c4")
+        if path_c5 is not None:
+            # same scene, same integrator settings, 4x the pixels: per-ray node / triangle counts of the C4 sample apply
+            path_c5["roofline"] = path_roofline({k: path_c4["rays_per_step"][k] * (path_c5["samples_per_frame"] / path_c4["samples_per_step"])
+                                                 for k in path_c4["rays_per_step"]}, path_c5["samples_per_frame"], path_c5["ms_per_frame"], cnt4,
+                                                peak * world, peak_src + f" x {world} GPUs", "c4")
+            path_c5["roofline"]["note_c5"] = "ray counts scaled from the C4 frame of the same run (same scene and integrator, 4x the pixels, 4x the spp)"
+            path_c5["cpu_baseline"] = dict(c4_cpu, note="the C4 sample: same scene and settings; the oracle's rate per camera sample does not depend on resolution")
     if rank == 0:
         line = {
             "metric": "closest-hit + any-hit traversal throughput (C3 pass)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C3: {n_prims}-triangle displaced grid, {args.res}x{args.res} primary closest-hit + shadow any-hit + "
-                                   "incoherent bounce closest-hit, SAH BVH max_prims_in_node=4",
-                       "rays_per_step_per_gpu": rays_per_step, "bvh_nodes": n_nodes, "bvh_depth": depth,
-                       "l2": "BVH+triangles (~1 GB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",
-                       "scene_gen_s": t_gen, "bvh_build_upload_s": t_build},
+            "config": bench_config(n_prims, args.res),
+            "scene": {"bvh_nodes": n_nodes, "bvh_depth": depth, "scene_gen_s": t_gen, "bvh_build_upload_s": t_build,
+                      "l2": "BVH+triangles (~1 GB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps"},
             "kernel_ms": kernel_ms, "hits_crc32": hits_crc,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
                     "api": "pb2_intersect_async x2 + pb2_intersect_p_async + pb2_scene_wait per step, pinned host buffers",

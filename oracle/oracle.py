@@ -76,6 +76,8 @@ def _bind_path(L):
     L.orc_render.restype = C.c_double
     L.orc_render.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
     L.orc_path_li.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp]
+    L.orc_render_counted.restype = C.c_double
+    L.orc_render_counted.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.orc_resolve_rgb.argtypes = [vp, C.c_uint64, C.c_float, vp]
     L.orc_film_add_samples.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
     L.orc_roughness_to_alpha.restype = C.c_float

@@ -532,6 +532,18 @@ inline Float power_heuristic(Float f_pdf, Float g_pdf) {                        
     return (f * f) / (f * f + g * g);
 }
 
+// Instrumentation for the path-tracing roofline (B(sample) = sum of B(r) over the rays of the path + path state per
+// vertex + 16 B film): rays, boxes slab-tested and triangles tested in reference order per ray kind (0 = path / camera rays,
+// 1 = shadow rays of estimate_direct, 2 = its BSDF-sampled MIS rays) and the number of path vertices shaded.  Counting is on
+// only while a thread points tl_path_counters at its own block (orc_render_counted); results never depend on it.
+struct PathCounters {
+    uint64_t camera_samples = 0, vertices = 0;
+    uint64_t rays[3] = {0, 0, 0};
+    TraversalCounters trav[3];
+};
+inline thread_local PathCounters* tl_path_counters = nullptr;
+inline thread_local int tl_ray_kind = 0;
+
 // ---------------------------------------------------------------- interaction.rs SurfaceInteraction (subset)
 struct SurfaceInteraction {
     V3 p, error, n, wo, dpdu;
@@ -758,7 +770,9 @@ public:
     bool intersect(Ray& ray, SurfaceInteraction* si) const {
         Hit h;
         Float b0;
-        if (!bvh.intersect(ray, &h, &b0, nullptr)) return false;
+        PathCounters* pc = tl_path_counters;
+        if (pc) pc->rays[tl_ray_kind]++;
+        if (!bvh.intersect(ray, &h, &b0, pc ? &pc->trav[tl_ray_kind] : nullptr)) return false;
         V3 p0, p1, p2;
         bvh.tri(h.prim_id, &p0, &p1, &p2);
         Interaction it = triangle_interaction(p0, p1, p2, b0, h.b1, h.b2);
@@ -1138,7 +1152,9 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
         scattering_pdf = bsdf.pdf(it.wo, wi, flags);
         RGB f = bsdf.f(it.wo, wi, flags) * std::fabs(dot(wi, bsdf.ns));
         if (!is_black(f)) {
-            if (scene.bvh.intersect_p(shadow, nullptr)) li = rgb(0);                           // light.rs:126-135, D25 FIX
+            PathCounters* pc = tl_path_counters;
+            if (pc) pc->rays[1]++;
+            if (scene.bvh.intersect_p(shadow, pc ? &pc->trav[1] : nullptr)) li = rgb(0);       // light.rs:126-135, D25 FIX
             if (!is_black(li)) {
                 if (light.is_delta()) ld = ld + li * f / light_pdf;
                 else ld = ld + li * f * power_heuristic(light_pdf, scattering_pdf) / light_pdf;
@@ -1170,7 +1186,10 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
             Ray ray = spawn_ray(base, wi);
             SurfaceInteraction light_isect;
             RGB lmis = rgb(0);
-            if (scene.intersect(ray, &light_isect)) {
+            tl_ray_kind = 2;
+            const bool mis_found = scene.intersect(ray, &light_isect);
+            tl_ray_kind = 0;
+            if (mis_found) {
                 if (scene.tri_light[light_isect.prim] == (int32_t)light_index) lmis = scene.le(light_isect, -wi);   // D56 FIX
             }
             if (!is_black(lmis)) ld = ld + lmis * f * rgb(1.0f) * weight / scattering_pdf;
@@ -1191,21 +1210,19 @@ inline RGB uniform_sample_one_light(const Scene& scene, const SurfaceInteraction
     return estimate_direct(scene, it, bsdf, us0, us1, scene.lights[num], (uint32_t)num, ul0, ul1) / light_pdf;
 }
 
-struct PathCounters {
-    uint64_t camera_samples = 0, extend_rays = 0, shadow_rays = 0, mis_rays = 0;
-};
-
 // path.rs:65-213 (BSSRDF branch dead: no subsurface material exists)
 inline RGB path_li(const Scene& scene, Ray ray, Sampler& s, int max_depth, Float rr_threshold) {
     RGB l = rgb(0), beta = rgb(1);
     bool specular_bounce = false;
     int bounces = 0;
     Float eta_scale = 1.0f;
+    if (tl_path_counters) tl_path_counters->camera_samples++;
     for (;;) {
         SurfaceInteraction isect;
         bool found = scene.intersect(ray, &isect);
         if (bounces == 0 || specular_bounce)
             if (found) l = l + beta * scene.le(isect, -ray.d);
+        if (found && tl_path_counters) tl_path_counters->vertices++;
         if (!found || bounces >= max_depth) break;
         BSDF bsdf = scene.make_bsdf(isect);
         if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) l = l + beta * uniform_sample_one_light(scene, isect, bsdf, s);
@@ -1331,7 +1348,8 @@ struct Stray {
 //  mode 0 = the reference's order: one sampler stream per 16x16 tile (seed = tile.y*n_tiles.x + tile.x), consumed
 //           sequentially over pixels, samples and path vertices.
 // out_xyzw: float4 {X, Y, Z, filter_weight_sum} per pixel, ADDED to the buffer.  Returns seconds.
-inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& fd, const PathDesc& pd, int mode, int threads, Float* out_xyzw) {
+inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& fd, const PathDesc& pd, int mode, int threads, Float* out_xyzw,
+                     PathCounters* counters_out = nullptr) {
     Camera cam;
     cam.init({cd.pos[0], cd.pos[1], cd.pos[2]}, {cd.look[0], cd.look[1], cd.look[2]}, {cd.up[0], cd.up[1], cd.up[2]}, cd.fov, cd.res_x, cd.res_y);
     cam.lens_radius = cd.lens_radius;
@@ -1348,10 +1366,13 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
     std::vector<std::vector<Stray>> strays(threads);
     std::atomic<int> next{0};
     auto t0 = std::chrono::steady_clock::now();
+    std::vector<PathCounters> thread_counters(threads);
     auto work = [&](int tid) {
+        tl_path_counters = counters_out ? &thread_counters[tid] : nullptr;
+        tl_ray_kind = 0;
         for (;;) {
             int t = next.fetch_add(1);
-            if (t >= tiles_x * tiles_y) break;
+            if (t >= tiles_x * tiles_y) { tl_path_counters = nullptr; break; }
             int tx = t % tiles_x, ty = t / tiles_x;
             Sampler tile_sampler;
             tile_sampler.kind = pd.sampler;
@@ -1406,6 +1427,16 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
     for (int i = 1; i < threads; ++i) pool.emplace_back(work, i);
     work(0);
     for (auto& t : pool) t.join();
+    if (counters_out)
+        for (const PathCounters& c : thread_counters) {
+            counters_out->camera_samples += c.camera_samples;
+            counters_out->vertices += c.vertices;
+            for (int k = 0; k < 3; ++k) {
+                counters_out->rays[k] += c.rays[k];
+                counters_out->trav[k].nodes_tested += c.trav[k].nodes_tested;
+                counters_out->trav[k].tris_tested += c.trav[k].tris_tested;
+            }
+        }
     std::vector<Stray> all;
     for (auto& v : strays) all.insert(all.end(), v.begin(), v.end());
     std::sort(all.begin(), all.end(), [](const Stray& a, const Stray& b) {

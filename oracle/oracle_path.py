@@ -198,6 +198,20 @@ class Scene:
         dt = O.lib().orc_render(self.h, C.byref(cd), C.byref(fd), C.byref(path), mode, threads, _p(out))
         return out, dt
 
+    def render_counted(self, cam, film, path, mode=1, threads=0):
+        """render() with the traversal instrumentation on: (xyzw, seconds, counters) where counters = {camera_samples, vertices,
+        rays / nodes / tris per ray kind (extend, shadow, mis)} — the inputs of the path roofline."""
+        cd = camera_desc(cam)
+        out = np.zeros(film_shape(film) + (4,), dtype=np.float32)
+        c = np.zeros(11, np.uint64)
+        dt = O.lib().orc_render_counted(self.h, C.byref(cd), C.byref(film), C.byref(path), mode, threads, _p(out), _p(c))
+        kinds = ("extend", "shadow", "mis")
+        cnt = {"camera_samples": int(c[0]), "vertices": int(c[1]),
+               "rays": {k: int(c[2 + i]) for i, k in enumerate(kinds)},
+               "nodes": {k: int(c[5 + i]) for i, k in enumerate(kinds)},
+               "tris": {k: int(c[8 + i]) for i, k in enumerate(kinds)}}
+        return out, dt, cnt
+
     # SpatialLightDistribution probes (lightdistrib.rs:71-220)
     def spatial_grid(self):
         """Voxels per axis of the "spatial" light distribution (selects that strategy on the scene)."""

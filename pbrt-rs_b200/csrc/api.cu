@@ -54,6 +54,7 @@ void pb2_scene::free_device() {
     if (d_light_cdf) cudaFree(d_light_cdf);
     if (d_spatial) cudaFree(d_spatial);
     d_spatial = nullptr;
+    path_chain.destroy();
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
     if (d_indices) cudaFree(d_indices);

@@ -48,6 +48,33 @@ struct Pipe {
 struct Wavefront;
 void wavefront_destroy(Wavefront* wf);
 
+// Orders successive uses of one resource across CUDA streams (a film's accumulators; a scene's wavefront arena, counters and
+// cached sampler tables): every entry point that touches the resource on stream `s` calls enter(s) before its first
+// kernel / copy and leave(s) after its last one, so work enqueued by a later call — on whatever stream, the legacy default
+// stream included — starts after the earlier call's work has finished.  (cudaStreamNonBlocking streams do not synchronise
+// with the legacy stream, which the film's cudaMemset / cudaMemcpy calls use.)  Calls are enqueued under the owner's mutex,
+// so enqueue order is call order.
+struct UseChain {
+    cudaEvent_t ev = nullptr;
+    bool used = false;
+    cudaError_t enter(cudaStream_t s) {
+        if (!ev) {
+            cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        return used ? cudaStreamWaitEvent(s, ev, 0) : cudaSuccess;
+    }
+    cudaError_t leave(cudaStream_t s) {
+        used = true;
+        return cudaEventRecord(ev, s);
+    }
+    void destroy() {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+        used = false;
+    }
+};
+
 }  // namespace pb2
 
 struct pb2_scene {
@@ -100,6 +127,7 @@ struct pb2_scene {
     pb2::SceneView view;
     pb2::Pipe pipe;
     pb2::Wavefront* wf = nullptr;
+    pb2::UseChain path_chain;           // wf + d_tab1 / d_tab2 + d_spatial: shared by every pb2_render_path / pb2_path_li call
     // HaltonSampler tables on the device (built on first use; the scales depend on the sample-bounds extent)
     void* d_halton_perms = nullptr;
     void* d_halton_primes = nullptr;

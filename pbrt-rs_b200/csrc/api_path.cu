@@ -6,6 +6,8 @@
 
 #include "api_internal.hpp"
 
+using pb2::UseChain;
+
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -29,6 +31,7 @@ struct pb2_film {
     int px0, py0, px1, py1;                        // cropped_pixel_bounds (film.rs:41-50)
     int sb_x0, sb_y0, sb_x1, sb_y1;
     int device = 0;
+    UseChain chain;                                // orders every use of the accumulators across streams (api_internal.hpp)
     size_t n_pixels() const { return (size_t)(px1 - px0) * (size_t)(py1 - py0); }
 };
 
@@ -496,6 +499,7 @@ int pb2_film_destroy(pb2_film* f) {
     if (!f) return PB2_OK;
     cudaFree(f->d_splat);
     cudaFree(f->d_table); cudaFree(f->d_xyzw); cudaFree(f->d_acc); cudaFree(f->d_stray); cudaFree(f->d_stray_vals); cudaFree(f->d_counters);
+    f->chain.destroy();
     delete f;
     return PB2_OK;
 }
@@ -503,21 +507,26 @@ int pb2_film_destroy(pb2_film* f) {
 int pb2_film_clear(pb2_film* f) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     const size_t npix = f->n_pixels();
-    PB2_CUDA(cudaMemset(f->d_xyzw, 0, npix * 16));
-    PB2_CUDA(cudaMemset(f->d_acc, 0, npix * 16));
-    if (f->d_splat) PB2_CUDA(cudaMemset(f->d_splat, 0, npix * 16));
+    PB2_CUDA(f->chain.enter(0));
+    PB2_CUDA(cudaMemsetAsync(f->d_xyzw, 0, npix * 16, 0));
+    PB2_CUDA(cudaMemsetAsync(f->d_acc, 0, npix * 16, 0));
+    if (f->d_splat) PB2_CUDA(cudaMemsetAsync(f->d_splat, 0, npix * 16, 0));
+    PB2_CUDA(f->chain.leave(0));
     return PB2_OK;
 }
 
 // Film::add_splat (film.rs:137-151) for n splats
 int pb2_film_add_splats(pb2_film* f, const float* p_film, const float* v_rgb, uint64_t n) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
-    if (n == 0) return PB2_OK;
-    if (!p_film || !v_rgb) return set_error(PB2_ERR_INVALID, "null splat arrays");
+    if (n != 0 && (!p_film || !v_rgb)) return set_error(PB2_ERR_INVALID, "null splat arrays");
     if (!f->d_splat) {
+        // (n == 0 still creates the zeroed splat plane: pb2_film_reduce sums it only on films that have one, and a
+        // collective needs every rank to take part — a rank with nothing to splat calls this with n = 0)
         PB2_CUDA(cudaMalloc(&f->d_splat, f->n_pixels() * 16));
         PB2_CUDA(cudaMemset(f->d_splat, 0, f->n_pixels() * 16));
     }
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(f->chain.enter(0));
     float *d_p = nullptr, *d_v = nullptr;
     cudaError_t e = cudaMalloc(&d_p, n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_v, n * 12);
@@ -535,6 +544,7 @@ int pb2_film_set_image(pb2_film* f, const float* rgb) {
     if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
     const size_t npix = f->n_pixels();
     float* d = nullptr;
+    PB2_CUDA(f->chain.enter(0));
     PB2_CUDA(cudaMalloc(&d, npix * 12));
     cudaError_t e = cudaMemcpy(d, rgb, npix * 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) { film_set_image(film_view(f), d, 0); e = cudaGetLastError(); }
@@ -548,6 +558,7 @@ int pb2_film_add_samples(pb2_film* f, const float* p_film, const float* L_rgb, c
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     if (n == 0) return PB2_OK;
     if (!p_film || !L_rgb || !weight) return set_error(PB2_ERR_INVALID, "null sample arrays");
+    PB2_CUDA(f->chain.enter(0));
     float *d_p = nullptr, *d_L = nullptr, *d_w = nullptr;
     cudaError_t e = cudaMalloc(&d_p, n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_L, n * 12);
@@ -564,6 +575,7 @@ int pb2_film_add_samples(pb2_film* f, const float* p_film, const float* L_rgb, c
 
 int pb2_film_read_xyzw(pb2_film* f, float* out) {
     if (!f || !out) return set_error(PB2_ERR_INVALID, "null argument");
+    PB2_CUDA(f->chain.enter(0));
     PB2_CUDA(cudaMemcpy(out, f->d_xyzw, f->n_pixels() * 16, cudaMemcpyDeviceToHost));
     return PB2_OK;
 }
@@ -574,6 +586,7 @@ int pb2_film_resolve_rgb_splat(pb2_film* f, float scale, float splat_scale, floa
     if (!f || !rgb) return set_error(PB2_ERR_INVALID, "null argument");
     const size_t npix = f->n_pixels();
     float* d = nullptr;
+    PB2_CUDA(f->chain.enter(0));
     PB2_CUDA(cudaMalloc(&d, npix * 12));
     film_resolve(film_view(f), scale, splat_scale, d, 0);
     cudaError_t e = cudaGetLastError();
@@ -642,6 +655,10 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     const FilmView fv = film_view(film);
     rc = ensure_wavefront(scene, (uint64_t)fv.sb_w * fv.sb_h);
     if (rc) return rc;
+    // the wavefront arena, its counters and the cached sampler tables are shared by every render of this scene, and the film
+    // may have been cleared / rendered into on another stream: order this call behind the previous uses of both
+    PB2_CUDA(scene->path_chain.enter((cudaStream_t)stream));
+    PB2_CUDA(film->chain.enter((cudaStream_t)stream));
     const PathParams pp{path->max_depth, path->rr_threshold};
     SamplerView smp;
     rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
@@ -653,6 +670,8 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     wavefront_render(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, path->sample_begin,
                      path->sample_end, (cudaStream_t)stream);
     PB2_CUDA(cudaGetLastError());
+    PB2_CUDA(scene->path_chain.leave((cudaStream_t)stream));
+    PB2_CUDA(film->chain.leave((cudaStream_t)stream));
     return PB2_OK;
 }
 
@@ -663,9 +682,20 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     if (rc) return rc;
     if (n == 0) return PB2_OK;
     if (!pixel_xy || !sample_index || !L_rgb || !p_film) return set_error(PB2_ERR_INVALID, "null argument");
+    // sampler streams, PixelSampler tables and the Halton offsets are indexed by (pixel, sample): anything outside the image or
+    // beyond spp would read past them
+    if (n > (1ull << 28)) return set_error(PB2_ERR_LIMIT, "pb2_path_li: %llu samples exceed the 2^28 path slots of one wavefront", (unsigned long long)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (pixel_xy[2 * i] >= (uint32_t)cam->res_x || pixel_xy[2 * i + 1] >= (uint32_t)cam->res_y)
+            return set_error(PB2_ERR_INVALID, "pb2_path_li: pixel %llu = (%u, %u) lies outside the %d x %d image", (unsigned long long)i,
+                             pixel_xy[2 * i], pixel_xy[2 * i + 1], cam->res_x, cam->res_y);
+        if (sample_index[i] >= (uint32_t)path->spp)
+            return set_error(PB2_ERR_INVALID, "pb2_path_li: sample index %u of entry %llu is not below spp = %d", sample_index[i], (unsigned long long)i, path->spp);
+    }
     std::lock_guard<std::mutex> lock(scene->mu);
     rc = ensure_wavefront(scene, n);
     if (rc) return rc;
+    PB2_CUDA(scene->path_chain.enter(0));
     // box filter, r = 0.5 sample bounds: streams are indexed by image pixel
     FilmView fv;
     memset(&fv, 0, sizeof fv);
@@ -694,6 +724,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     }
     if (e == cudaSuccess) e = cudaMemcpy(L_rgb, d_L, n * 12, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(p_film, d_pf, n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = scene->path_chain.leave(0);
     cudaFree(d_xy); cudaFree(d_s); cudaFree(d_L); cudaFree(d_pf);
     if (e != cudaSuccess) return cuda_fail(e, "pb2_path_li", __FILE__, __LINE__);
     return PB2_OK;
@@ -762,8 +793,13 @@ int pb2_film_reduce(pb2_film* f, int root, void* stream) {
     if (!f) return set_error(PB2_ERR_INVALID, "null film");
     if (!g_comm) return set_error(PB2_ERR_STATE, "pb2_nccl_init has not been called");
     const size_t count = f->n_pixels() * 4;
+    PB2_CUDA(f->chain.enter((cudaStream_t)stream));
     ncclResult_t r = g_nccl.Reduce(f->d_xyzw, f->d_xyzw, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
+    // Pixel::splat_xyz (film.rs:9-15) is part of the film: summed too when this film has a splat plane (every rank's must —
+    // see pb2_film_add_splats with n = 0)
+    if (r == ncclSuccess && f->d_splat) r = g_nccl.Reduce(f->d_splat, f->d_splat, count, ncclFloat32, ncclSum, root, g_comm, (cudaStream_t)stream);
     if (r != ncclSuccess) return set_error(PB2_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString(r));
+    PB2_CUDA(f->chain.leave((cudaStream_t)stream));
     return PB2_OK;
 }
 

@@ -37,112 +37,168 @@ constexpr int kThreads = 256;
 // profiles/r01_tuning.md, session 4.)
 constexpr unsigned kStateDead = 3u;            // bits 0-1: shading class of the hit, 3 = the ray escaped
 constexpr unsigned kStateContinues = 4u;       // bit 2: the path continues with the ray k_shade wrote
-constexpr int kCompactThreads = 256;           // bits 3, 4: shadow ray / MIS ray of the NEE record pending
+                                               // bits 3, 4: shadow ray / MIS ray of the NEE record pending
 
-struct CompactJob {
+// compact_queues(): ONE launch — a stable three-way select with decoupled look-back.  The active queue is cut into tiles of
+// kSelTile entries; a CTA takes the next tile (ticket counter, so a tile's predecessors are always running or done), counts its
+// entries per output, publishes the three counts, obtains its exclusive offsets by looking back over the predecessors'
+// published counts / inclusive prefixes (one 64-bit word per tile and output: {launch epoch : 32 | flag : 2 | value : 30}, so a
+// word is valid only for the launch that wrote it and the array never needs clearing), and scatters.  The input is read once.
+// The CTA of the last tile leaves the totals in the queue counters and does the per-bounce bookkeeping k_iter_begin used to do in
+// a launch of its own.  (Round 1: count -> one-CTA scan -> scatter, three launches that read the queue and the state bytes twice.)
+constexpr int kSelThreads = 256, kSelItems = 8, kSelTile = kSelThreads * kSelItems;
+struct SelectJob {
     const uint32_t* in;                        // the bounce's active queue (sorted by slot)
     const unsigned long long* n_in;
     const uint8_t* state;
     uint32_t* out[3];
     unsigned long long* n_out[3];
     int by_class;                              // 1: out[k] takes class k (after k_extend); 0: out[k] takes bit 2 + k (after k_shade)
-    uint32_t* counts;                          // [3][gridDim.x]
+    unsigned long long* status;                // [3][max_tiles]
+    uint32_t max_tiles;
+    unsigned* ticket;                          // this launch's tile counter (zero on entry)
+    unsigned* ticket_next;                     // the next launch's: zeroed here
+    unsigned epoch;                            // > 0, different for every launch
+    unsigned long long* counters;
 };
-__device__ __forceinline__ bool compact_pred(const CompactJob& j, unsigned st, int k) {
-    return j.by_class ? (st & 3u) == (unsigned)k : ((st >> (2 + k)) & 1u) != 0u;
+__device__ __forceinline__ bool select_pred(int by_class, unsigned st, int k) {
+    return by_class ? (st & 3u) == (unsigned)k : ((st >> (2 + k)) & 1u) != 0u;
 }
-// CTA b owns the contiguous chunk [b * chunk, (b + 1) * chunk) of the input queue in both passes.
-__device__ __forceinline__ void compact_chunk(unsigned long long n, uint32_t* begin, uint32_t* end) {
-    const unsigned long long chunk = (((n + gridDim.x - 1) / gridDim.x) + kCompactThreads - 1) / kCompactThreads * kCompactThreads;
-    const unsigned long long b0 = (unsigned long long)blockIdx.x * chunk;
-    *begin = (uint32_t)(b0 < n ? b0 : n);
-    *end = (uint32_t)(b0 + chunk < n ? b0 + chunk : n);
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-__global__ void __launch_bounds__(kCompactThreads) k_compact_count(CompactJob j) {
-    uint32_t begin, end;
-    compact_chunk(*j.n_in, &begin, &end);
-    unsigned c0 = 0, c1 = 0, c2 = 0;
-    for (uint32_t i = begin + threadIdx.x; i < end; i += kCompactThreads) {
-        const unsigned st = j.state[j.in[i]];
-        c0 += compact_pred(j, st, 0); c1 += compact_pred(j, st, 1); c2 += compact_pred(j, st, 2);
-    }
-    __shared__ unsigned sh[3][kCompactThreads / 32];
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_down_sync(0xFFFFFFFFu, c0, o); c1 += __shfl_down_sync(0xFFFFFFFFu, c1, o); c2 += __shfl_down_sync(0xFFFFFFFFu, c2, o);
-    }
-    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = c0; sh[1][threadIdx.x >> 5] = c1; sh[2][threadIdx.x >> 5] = c2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        unsigned t = 0;
-        for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[threadIdx.x][w];
-        j.counts[threadIdx.x * gridDim.x + blockIdx.x] = t;
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// After the queues of a bounce are rebuilt from the shade stage's state bytes: the ray totals of the frame counters and the
+// work counters of the next two traversal launches (k_shadow of this bounce, k_extend of the next).
+__device__ __forceinline__ void select_finish(const SelectJob& j, unsigned long long t0, unsigned long long t1, unsigned long long t2) {
+    *j.n_out[0] = t0; *j.n_out[1] = t1; *j.n_out[2] = t2;
+    if (!j.by_class) {
+        j.counters[T_EXTEND] += t0;
+        j.counters[T_SHADOW] += t1;
+        j.counters[T_MIS] += t2;
+        j.counters[C_WORK_EXTEND] = 0;
+        j.counters[C_WORK_SHADOW] = 0;
     }
 }
-// One CTA: exclusive scan of the per-CTA counts of each output (n_ctas <= 1024), totals into the queue counters.
-__global__ void __launch_bounds__(1024) k_compact_scan(CompactJob j, int n_ctas) {
-    __shared__ unsigned sh[1024];
-    for (int k = 0; k < 3; ++k) {
-        const unsigned v = (int)threadIdx.x < n_ctas ? j.counts[k * n_ctas + threadIdx.x] : 0u;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const unsigned add = (int)threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
-            __syncthreads();
-            sh[threadIdx.x] += add;
-            __syncthreads();
-        }
-        if ((int)threadIdx.x < n_ctas) j.counts[k * n_ctas + threadIdx.x] = sh[threadIdx.x] - v;
-        if (threadIdx.x == 1023) *j.n_out[k] = sh[1023];
-        __syncthreads();
-    }
-}
-// Four consecutive queue entries per thread, one barrier per 1024-entry tile (the warp totals are double-buffered).
-__global__ void __launch_bounds__(kCompactThreads) k_compact_scatter(CompactJob j) {
-    constexpr int kItems = 4;
-    uint32_t begin, end;
-    compact_chunk(*j.n_in, &begin, &end);                                 // begin is a multiple of 256: 16-byte aligned loads
-    __shared__ unsigned warp_tot[2][3][kCompactThreads / 32];
-    unsigned base[3];
-    for (int q = 0; q < 3; ++q) base[q] = j.counts[q * gridDim.x + blockIdx.x];
+__global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_warp[3][kSelThreads / 32];
+    __shared__ unsigned s_base[3];
+    const unsigned long long n = *j.n_in;
+    const unsigned n_tiles = (unsigned)((n + kSelTile - 1) / kSelTile);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    int buf = 0;
-    for (uint32_t t0 = begin; t0 < end; t0 += kCompactThreads * kItems, buf ^= 1) {      // tiles in queue order: the select is stable
-        const uint32_t i0 = t0 + threadIdx.x * kItems;
-        uint32_t slot[kItems];
-        if (i0 + kItems <= end) {
-            const uint4 v = *reinterpret_cast<const uint4*>(j.in + i0);
-            slot[0] = v.x; slot[1] = v.y; slot[2] = v.z; slot[3] = v.w;
+    const unsigned long long tag = (unsigned long long)j.epoch << 32;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(j.ticket, 1u);
+            if (s_tile == 0u) {
+                *j.ticket_next = 0u;
+                if (n_tiles == 0u) select_finish(j, 0ull, 0ull, 0ull);
+            }
+        }
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= n_tiles) return;
+        // ---- load kSelItems consecutive entries per thread (blocked: the select is stable) ----
+        const unsigned long long i0 = (unsigned long long)tile * kSelTile + (unsigned long long)threadIdx.x * kSelItems;
+        uint32_t slot[kSelItems];
+        if (i0 + kSelItems <= n) {
+            const uint4 a = *reinterpret_cast<const uint4*>(j.in + i0), b = *reinterpret_cast<const uint4*>(j.in + i0 + 4);
+            slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w; slot[4] = b.x; slot[5] = b.y; slot[6] = b.z; slot[7] = b.w;
         } else {
-            for (int k = 0; k < kItems; ++k) slot[k] = i0 + k < end ? j.in[i0 + k] : 0u;
+#pragma unroll
+            for (int k = 0; k < kSelItems; ++k) slot[k] = i0 + k < n ? j.in[i0 + k] : 0u;
         }
-        unsigned st[kItems];
-        for (int k = 0; k < kItems; ++k) st[k] = i0 + k < end ? j.state[slot[k]] : (j.by_class ? kStateDead : 0u);
+        unsigned bits[3] = {0u, 0u, 0u};           // bit k of bits[q]: entry k goes to output q
+#pragma unroll
+        for (int k = 0; k < kSelItems; ++k) {
+            const unsigned st = i0 + k < n ? j.state[slot[k]] : (j.by_class ? kStateDead : 0u);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) bits[q] |= (select_pred(j.by_class, st, q) ? 1u : 0u) << k;
+        }
         unsigned cnt[3], inc[3];
-        for (int q = 0; q < 3; ++q) {
-            cnt[q] = 0;
-            for (int k = 0; k < kItems; ++k) cnt[q] += compact_pred(j, st[k], q) ? 1u : 0u;
-            inc[q] = cnt[q];
-        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) inc[q] = cnt[q] = (unsigned)__popc(bits[q]);
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const unsigned v = __shfl_up_sync(0xFFFFFFFFu, inc[q], o);
                 if (lane >= (unsigned)o) inc[q] += v;
             }
         if (lane == 31u)
-            for (int q = 0; q < 3; ++q) warp_tot[buf][q][warp] = inc[q];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) s_warp[q][warp] = inc[q];
         __syncthreads();
-        for (int q = 0; q < 3; ++q) {
-            unsigned before = 0, total = 0;
-            for (int w = 0; w < kCompactThreads / 32; ++w) {
-                const unsigned c = warp_tot[buf][q][w];
-                before += (unsigned)w < warp ? c : 0u;
-                total += c;
+        // ---- warp 0: tile totals, publish, look back ----
+        if (warp == 0u) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                unsigned total = 0u;
+#pragma unroll
+                for (int w = 0; w < kSelThreads / 32; ++w) total += s_warp[q][w];
+                unsigned long long* st = j.status + (size_t)q * j.max_tiles;
+                if (tile == 0u) {
+                    if (lane == 0u) { st_status(st, tag | (2ull << 30) | total); s_base[q] = 0u; }
+                } else {
+                    if (lane == 0u) st_status(st + tile, tag | (1ull << 30) | total);
+                    unsigned excl = 0u;
+                    int look = (int)tile - 1;
+                    for (;;) {                                       // 32 predecessors per round, nearest first
+                        const int idx = look - (int)lane;
+                        unsigned long long w;
+                        unsigned incl_mask;
+                        for (;;) {                                   // wait for every predecessor up to the nearest inclusive prefix
+                            w = idx >= 0 ? ld_status(st + idx) : (tag | (2ull << 30));
+                            const bool valid = (w >> 32) == (unsigned long long)j.epoch && ((w >> 30) & 3ull) != 0ull;
+                            const unsigned valid_mask = __ballot_sync(0xFFFFFFFFu, valid);
+                            incl_mask = __ballot_sync(0xFFFFFFFFu, valid && ((w >> 30) & 3ull) == 2ull);
+                            const unsigned need = incl_mask ? ((1u << (__ffs(incl_mask) - 1)) - 1u) : 0xFFFFFFFFu;
+                            if ((valid_mask & need) == need) break;
+                        }
+                        // sum the values up to and including the nearest predecessor that holds an inclusive prefix
+                        const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                        unsigned v = (int)lane <= stop ? (unsigned)(w & 0x3FFFFFFFull) : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                        excl += v;
+                        if (incl_mask) break;
+                        look -= 32;
+                    }
+                    if (lane == 0u) { st_status(st + tile, tag | (2ull << 30) | (unsigned long long)(excl + total)); s_base[q] = excl; }
+                }
             }
-            unsigned pos = base[q] + before + inc[q] - cnt[q];
-            for (int k = 0; k < kItems; ++k)
-                if (compact_pred(j, st[k], q)) j.out[q][pos++] = slot[k];
-            base[q] += total;
         }
+        __syncthreads();
+        // ---- scatter ----
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            unsigned before = 0u;
+#pragma unroll
+            for (int w = 0; w < kSelThreads / 32; ++w) before += (unsigned)w < warp ? s_warp[q][w] : 0u;
+            unsigned pos = s_base[q] + before + inc[q] - cnt[q];
+            uint32_t* out = j.out[q];
+#pragma unroll
+            for (int k = 0; k < kSelItems; ++k)
+                if ((bits[q] >> k) & 1u) out[pos++] = slot[k];
+        }
+        if (tile == n_tiles - 1u && threadIdx.x == kSelThreads - 1) {
+            // (the last thread of the last tile: its inclusive position is the total)
+            unsigned long long tot[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                unsigned before = 0u;
+#pragma unroll
+                for (int w = 0; w < kSelThreads / 32; ++w) before += (unsigned)w < warp ? s_warp[q][w] : 0u;
+                tot[q] = (unsigned long long)s_base[q] + before + inc[q];
+            }
+            select_finish(j, tot[0], tot[1], tot[2]);
+        }
+        __syncthreads();                                 // s_tile, s_warp, s_base are reused by the next tile
     }
 }
 
@@ -391,21 +447,10 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         b.counters[C_ACTIVE_A] = n;
         b.counters[C_ACTIVE_B] = 0;
+        b.counters[C_SHADOW] = b.counters[C_MIS] = 0;          // no NEE record precedes the first bounce
+        b.counters[C_WORK_EXTEND] = b.counters[C_WORK_SHADOW] = 0;
         b.counters[T_CAMERA] += n;
-    }
-}
-
-// ---- per-iteration bookkeeping ------------------------------------------------------------------------------------------
-__global__ void k_iter_begin(PathBuffers b, int cur) {
-    if (threadIdx.x == 0) {
-        b.counters[T_EXTEND] += b.counters[C_ACTIVE_A + cur];
-        b.counters[T_SHADOW] += b.counters[C_SHADOW];        // rays of the previous bounce's visibility stage
-        b.counters[T_MIS] += b.counters[C_MIS];
-        b.counters[C_MIS_PREV] = b.counters[C_MIS];         // the MIS rays of the previous bounce ride in this bounce's k_extend
-        b.counters[C_ACTIVE_A + (cur ^ 1)] = 0;
-        b.counters[C_MAT0] = b.counters[C_MAT1] = b.counters[C_MAT2] = 0;
-        b.counters[C_SHADOW] = b.counters[C_MIS] = 0;
-        b.counters[C_WORK_EXTEND] = b.counters[C_WORK_SHADOW] = b.counters[C_WORK_MIS] = 0;
+        b.counters[T_EXTEND] += n;
     }
 }
 
@@ -465,7 +510,7 @@ struct ExtendSink {
     PB2_D void occluded(uint32_t, bool) const {}
 };
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
-    const uint32_t n_extend = (uint32_t)b.counters[C_ACTIVE_A + cur], n_mis = (uint32_t)b.counters[C_MIS_PREV];
+    const uint32_t n_extend = (uint32_t)b.counters[C_ACTIVE_A + cur], n_mis = (uint32_t)b.counters[C_MIS];   // the previous bounce's MIS rays
     const ExtendSink sink{b, sh, b.q_active[cur], n_extend};
     trace_persistent<false>(s, n_extend + n_mis, &b.counters[C_WORK_EXTEND], sink, tune);
 }
@@ -805,10 +850,16 @@ __device__ __forceinline__ void film_atomic_add(const FilmView& f, int px, int p
     float* a = reinterpret_cast<float*>(f.acc + f.index(px, py));
     atomicAdd(a, c.r); atomicAdd(a + 1, c.g); atomicAdd(a + 2, c.b); atomicAdd(a + 3, w);
 }
-__device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long* counters, unsigned long long order, int px, int py, rgb3 c, float w) {
+// A stray = the contribution of a sample of pixel (sx, sy) to another pixel (px, py) (exact mode: box filter, r = 0.5, so the
+// target is one of the eight neighbours).  Strays of one target are applied in the order (source pixel, sample index); the
+// sort key is {target pixel index : 32 | which neighbour the source is, in row-major order : 4 | sample index : 28}, which
+// orders the sources of one target exactly as their sample-bounds pixel indices do.  (A 24-bit pixel field, as this key
+// had first, wrapped on films of more than 2^24 pixels.)
+__device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long* counters, int sx, int sy, uint32_t sample, int px, int py, rgb3 c, float w) {
     const unsigned long long pos = atomicAdd(&counters[C_STRAYS], 1ull);
     if (pos < f.stray_capacity) {
-        f.stray_keys[pos] = ((unsigned long long)f.index(px, py) << 40) | (order & 0xFFFFFFFFFFull);
+        const unsigned nb = (unsigned)((sy - py + 1) * 3 + (sx - px + 1));
+        f.stray_keys[pos] = ((unsigned long long)f.index(px, py) << 32) | ((unsigned long long)nb << 28) | (unsigned long long)(sample & 0x0FFFFFFFu);
         f.stray_vals[pos] = make_float4(c.r, c.g, c.b, w);
     } else {
         atomicAdd(&counters[C_STRAY_OVERFLOW], 1ull);                     // still accumulated, but in arrival order
@@ -836,7 +887,7 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map,
             film_footprint(f, pfx, pfy, [&](int px, int py, float fw) {
                 const rgb3 c = L * 1.0f * fw;                            // l * sample_weight * filter_weight
                 if (px == x && py == y) { acc.x += c.r; acc.y += c.g; acc.z += c.b; acc.w += fw; }
-                else film_stray(f, b.counters, si.seq, px, py, c, fw);
+                else film_stray(f, b.counters, x, y, si.sample, px, py, c, fw);
             });
         }
         if (inside) f.acc[f.index(x, y)] = acc;
@@ -906,11 +957,49 @@ __global__ void __launch_bounds__(kThreads) k_apply_strays(FilmView f, const uns
     unsigned long long n = counters[C_STRAYS];
     if (n > f.stray_capacity) n = f.stray_capacity;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long pixel = keys[j] >> 40;
-        if (j > 0 && (keys[j - 1] >> 40) == pixel) continue;
+        const unsigned long long pixel = keys[j] >> 32;
+        if (j > 0 && (keys[j - 1] >> 32) == pixel) continue;
         float4 acc = f.acc[pixel];
-        for (unsigned long long k = j; k < n && (keys[k] >> 40) == pixel; ++k) {
+        for (unsigned long long k = j; k < n && (keys[k] >> 32) == pixel; ++k) {
             const float4 v = f.stray_vals[index[k]];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        f.acc[pixel] = acc;
+    }
+}
+// Up to kSmallStrays strays (every frame of ordinary size: about 1e-5 of the samples stray): one CTA sorts {key, index} in shared
+// memory (bitonic network) and applies the runs, instead of a device-wide radix sort over the whole buffer.
+constexpr int kSmallStrays = 4096;
+__global__ void __launch_bounds__(1024) k_strays_small(FilmView f, const unsigned long long* counters) {
+    __shared__ unsigned long long key[kSmallStrays];
+    __shared__ uint16_t idx[kSmallStrays];
+    unsigned long long n64 = counters[C_STRAYS];
+    if (n64 > f.stray_capacity) n64 = f.stray_capacity;
+    const int n = (int)n64;
+    if (n == 0) return;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { key[i] = i < n ? f.stray_keys[i] : ~0ull; idx[i] = (uint16_t)i; }
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = key[i], b = key[l];
+                    // (keys of distinct strays can be equal only for one sample reaching one pixel twice, which cannot happen)
+                    if ((a > b) == up) { key[i] = b; key[l] = a; const uint16_t t = idx[i]; idx[i] = idx[l]; idx[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const unsigned long long pixel = key[j] >> 32;
+        if (j > 0 && (key[j - 1] >> 32) == pixel) continue;
+        float4 acc = f.acc[pixel];
+        for (int k = j; k < n && (key[k] >> 32) == pixel; ++k) {
+            const float4 v = f.stray_vals[idx[k]];
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         f.acc[pixel] = acc;
@@ -1001,24 +1090,39 @@ __global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, fl
     }
 }
 
+int device_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
 unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
     const uint64_t want = (n + kThreads - 1) / kThreads;
     const uint64_t cap = (uint64_t)wf->sm_count * per_sm;
     return (unsigned)std::max<uint64_t>(1, std::min(want, cap));
 }
 
-// Stable three-way select of the active queue `in` by the paths' state bytes (see CompactJob); counts stay on the device.
+// Stable three-way select of the active queue `in` by the paths' state bytes (see SelectJob); counts stay on the device.
 void compact_queues(Wavefront* wf, const uint32_t* in, int n_in, bool by_class, uint32_t* o0, int c0, uint32_t* o1, int c1, uint32_t* o2, int c2,
                     cudaStream_t st) {
     const PathBuffers& b = wf->b;
-    CompactJob j;
-    j.in = in; j.n_in = b.counters + n_in; j.state = b.state; j.by_class = by_class ? 1 : 0; j.counts = b.compact_counts;
+    SelectJob j;
+    j.in = in; j.n_in = b.counters + n_in; j.state = b.state; j.by_class = by_class ? 1 : 0;
     j.out[0] = o0; j.out[1] = o1; j.out[2] = o2;
     j.n_out[0] = b.counters + c0; j.n_out[1] = b.counters + c1; j.n_out[2] = b.counters + c2;
-    const int n_ctas = std::min(1024, wf->sm_count * 4);
-    k_compact_count<<<n_ctas, kCompactThreads, 0, st>>>(j);
-    k_compact_scan<<<1, 1024, 0, st>>>(j, n_ctas);
-    k_compact_scatter<<<n_ctas, kCompactThreads, 0, st>>>(j);
+    j.status = b.select_status;
+    j.max_tiles = (uint32_t)(wf->capacity / kSelTile + 1);
+    const unsigned launch = wf->select_launches++;
+    j.ticket = b.select_tickets + (launch & 1u);
+    j.ticket_next = b.select_tickets + ((launch + 1u) & 1u);
+    j.epoch = launch + 1u;                                 // (2^32 launches = years of rendering)
+    j.counters = b.counters;
+    k_select3<<<(unsigned)wf->sm_count * 4u, kSelThreads, 0, st>>>(j);
 }
 
 // k_shade<material, PixelSampler tables, mesh shading geometry> for the three material queues of one bounce.
@@ -1051,16 +1155,15 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
     int launches = 1;
     for (int depth = 0; depth <= pp.max_depth; ++depth) {
         const int cur = depth & 1;
-        k_iter_begin<<<1, 32, 0, st>>>(b, cur);
         k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
         // hits -> one queue per shading class (material-sorted shading)
         compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, true, b.q_mat[0], C_MAT0, b.q_mat[1], C_MAT1, b.q_mat[2], C_MAT2, st);
         launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
-        launches += 5 + __builtin_popcount(sh.class_mask & 7u);
+        launches += 2 + __builtin_popcount(sh.class_mask & 7u);
         if (depth == pp.max_depth) break;                                // path.rs:90-92: nothing continues, no NEE record was written
         compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, false, b.q_active[cur ^ 1], C_ACTIVE_A + (cur ^ 1), b.q_shadow, C_SHADOW,
                        b.q_mis, C_MIS, st);
-        launches += 3;
+        launches += 1;
         if (sh.n_lights > 0) {
             k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
             launches += 1;
@@ -1079,7 +1182,8 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     cudaDeviceGetAttribute(&wf->sm_count, cudaDevAttrMultiProcessorCount, dev);
     // one arena: 13 float4/uint4 arrays, rng, occluded, mis_prim, 7 queues, counters
     const size_t f4 = capacity * 16;
-    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + 2 * capacity + 7 * capacity * 4 + C_COUNT * 8 + 3 * 1024 * 4 + 8192;
+    const size_t status_bytes = 3 * (capacity / kSelTile + 1) * 8;
+    size_t bytes = 13 * f4 + capacity * 8 + capacity * 4 + 2 * capacity + 7 * capacity * 4 + C_COUNT * 8 + status_bytes + 256 + 8192;
     cudaError_t e = cudaMalloc(&wf->arena, bytes);
     if (e != cudaSuccess) { delete wf; *out = nullptr; return (int)e; }
     char* p = (char*)wf->arena;
@@ -1093,7 +1197,10 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     b.mis_prim = (uint32_t*)take(capacity * 4);
     b.occluded = (uint8_t*)take(capacity);
     b.state = (uint8_t*)take(capacity);
-    b.compact_counts = (uint32_t*)take(3 * 1024 * 4);
+    b.select_status = (unsigned long long*)take(status_bytes);
+    b.select_tickets = (unsigned*)take(256);
+    cudaMemset(b.select_status, 0, status_bytes);          // epoch 0 = never written
+    cudaMemset(b.select_tickets, 0, 256);
     for (int i = 0; i < 2; ++i) b.q_active[i] = (uint32_t*)take(capacity * 4);
     for (int i = 0; i < 3; ++i) b.q_mat[i] = (uint32_t*)take(capacity * 4);
     b.q_shadow = (uint32_t*)take(capacity * 4);
@@ -1110,10 +1217,21 @@ void wavefront_destroy(Wavefront* wf) {
     delete wf;
 }
 
-int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film,
+int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film_in,
                      const PathParams& pp, const SamplerView& smp, int spp, int sample_begin, int sample_end, cudaStream_t st) {
-    const uint64_t n_pix = (uint64_t)film.sb_w * (uint64_t)film.sb_h;
+    const uint64_t n_pix = (uint64_t)film_in.sb_w * (uint64_t)film_in.sb_h;
     if (n_pix == 0 || sample_end <= sample_begin) return 0;
+    // Strays (exact mode) are sorted once per call.  About 1e-5 of a call's samples stray (p_film = x + u rounds up to x + 1), so
+    // the sort covers a slice of the stray buffer sized for 1 / 256 of them — at least the 4096 entries one CTA sorts in shared
+    // memory — not the whole 2^20-entry buffer; anything beyond the slice is accumulated in arrival order and counted
+    // (C_STRAY_OVERFLOW), as with the full buffer before.
+    FilmView film = film_in;
+    {
+        const uint64_t samples = n_pix * (uint64_t)(sample_end - sample_begin);
+        uint64_t want = kSmallStrays;
+        while (want < samples / 256) want <<= 1;
+        film.stray_capacity = (uint32_t)std::min<uint64_t>(film_in.stray_capacity, want);
+    }
     const int per_batch = (int)std::max<uint64_t>(1, wf->capacity / n_pix);
     for (int s0 = sample_begin; s0 < sample_end; s0 += per_batch) {
         const int ns = std::min(per_batch, sample_end - s0);
@@ -1154,8 +1272,10 @@ void pixel_tables_generate(int kind, uint32_t n_pix, int spp, int n_dims, int x_
 
 // Ordered application of the strays (exact mode), then merge of the call's sums into the film.
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st) {
-    const unsigned grid = 148 * 4;
-    if (film.exact && counters && film.stray_capacity) {
+    const unsigned grid = (unsigned)device_sm_count() * 4;
+    if (film.exact && counters && film.stray_capacity && film.stray_capacity <= (uint32_t)kSmallStrays) {
+        k_strays_small<<<1, 1024, 0, st>>>(film, counters);
+    } else if (film.exact && counters && film.stray_capacity) {
         // scratch: sorted keys + index pairs live behind the primary arrays (allocated 2x by the film)
         unsigned long long* keys_in = film.stray_keys;
         unsigned long long* keys_out = film.stray_keys + film.stray_capacity;
@@ -1180,18 +1300,18 @@ size_t film_sort_scratch_bytes(uint32_t capacity) {
 
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st) {
     if (n == 0) return;
-    k_film_add_samples<<<148 * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_L, d_w, n);
-    k_film_merge<<<148 * 4, kThreads, 0, st>>>(film, nullptr);
+    k_film_add_samples<<<(unsigned)device_sm_count() * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_L, d_w, n);
+    k_film_merge<<<(unsigned)device_sm_count() * 4, kThreads, 0, st>>>(film, nullptr);
 }
 
 void film_resolve(const FilmView& film, float scale, float splat_scale, float* d_rgb, cudaStream_t st) {
-    k_film_resolve<<<148 * 4, kThreads, 0, st>>>(film, scale, splat_scale, d_rgb);
+    k_film_resolve<<<(unsigned)device_sm_count() * 4, kThreads, 0, st>>>(film, scale, splat_scale, d_rgb);
 }
 void film_add_splats(const FilmView& film, const float* d_pfilm, const float* d_v, uint64_t n, cudaStream_t st) {
-    if (n) k_film_add_splats<<<148 * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_v, n);
+    if (n) k_film_add_splats<<<(unsigned)device_sm_count() * 4, kThreads, 0, st>>>(film, (const float2*)d_pfilm, d_v, n);
 }
 void film_set_image(const FilmView& film, const float* d_rgb, cudaStream_t st) {
-    k_film_set_image<<<148 * 4, kThreads, 0, st>>>(film, d_rgb);
+    k_film_set_image<<<(unsigned)device_sm_count() * 4, kThreads, 0, st>>>(film, d_rgb);
 }
 
 }  // namespace pb2

@@ -130,9 +130,10 @@ struct PathBuffers {
     uint32_t* q_mis;
     unsigned long long* counters;
     // order-preserving queues: what became of the path in `slot` this bounce — bits 0-1 shading class of its hit (3 = no hit),
-    // bit 2 continues, bit 3 shadow ray pending, bit 4 MIS ray pending — and the per-CTA counts of the compaction passes
+    // bit 2 continues, bit 3 shadow ray pending, bit 4 MIS ray pending — and the tile descriptors of the single-pass select that rebuilds the queues
     uint8_t* state;
-    uint32_t* compact_counts;
+    unsigned long long* select_status;     // k_select3: per tile and output, {epoch, flag, count or inclusive prefix}
+    unsigned* select_tickets;              // two tile counters, used by alternate launches
 };
 
 struct PathParams {
@@ -145,6 +146,7 @@ struct Wavefront {
     PathBuffers b{};
     void* arena = nullptr;
     int sm_count = 0;
+    unsigned select_launches = 0;          // k_select3 launches so far: picks the ticket counter and the epoch
     uint64_t totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
