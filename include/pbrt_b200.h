@@ -118,7 +118,13 @@ enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1, PB2_LIGHTS_SPATIAL = 2 };
  * (src/samplers/zerotwosequence.rs) — PixelSamplers (src/core/sampler.rs:257-322): the first n_sampled_dimensions 1D and 2D
  * dimensions of every pixel come from per-pixel tables of spp values generated on the device by Sampler::start_pixel from
  * the stream RNG::new(n_pixels*spp + pixel); later dimensions fall back to the per-(pixel, sample) PCG32 stream. */
-enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1, PB2_SAMPLER_STRATIFIED = 2, PB2_SAMPLER_ZEROTWO = 3 };
+/* PB2_SAMPLER_SOBOL: SobolSampler (src/samplers/sobol.rs, src/core/lowdiscrepancy.rs:507-560, generator matrices of
+ * src/core/sobolmatrices.rs) — a GlobalSampler like Halton: sample index = sobol_interval_to_index(log2 of the sample-bounds
+ * extent rounded up to a power of two, sample number, pixel - sample_bounds.min); dimension d = index bits x the d-th
+ * generator matrix; dimensions 0 / 1 are remapped into the pixel.  spp must be a power of two (sobol.rs:22-28 rounds up).
+ * The reference leaves sample_dimension as todo!() (sobol.rs:56-58) and its sobol_interval_to_index cannot terminate
+ * (lowdiscrepancy.rs:529-534); both follow pbrt-v3 here. */
+enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1, PB2_SAMPLER_STRATIFIED = 2, PB2_SAMPLER_ZEROTWO = 3, PB2_SAMPLER_SOBOL = 4 };
 /* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
 typedef struct pb2_path_desc {
     int32_t max_depth;

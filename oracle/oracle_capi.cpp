@@ -9,6 +9,24 @@
 
 using namespace orc;
 
+// The Sobol' generator matrices (constant data; tools/make_sobol_tables.py) embedded from the package's data directory.
+__asm__(".section .rodata\n"
+        ".balign 16\n"
+        ".global orc_sobol_blob\n"
+        "orc_sobol_blob:\n"
+        ".incbin \"../pbrt-rs_b200/data/sobol_tables.bin\"\n"
+        ".global orc_sobol_blob_end\n"
+        "orc_sobol_blob_end:\n"
+        ".previous\n");
+extern "C" const unsigned char orc_sobol_blob[], orc_sobol_blob_end[];
+namespace orc {
+const SobolTables* sobol_tables_base() {
+    static SobolTables t;
+    static const bool ok = t.load(orc_sobol_blob, (size_t)(orc_sobol_blob_end - orc_sobol_blob));
+    return ok ? &t : nullptr;
+}
+}  // namespace orc
+
 extern "C" {
 
 // ---- scalar helpers ------------------------------------------------------------------------

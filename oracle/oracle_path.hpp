@@ -988,6 +988,77 @@ struct HaltonTables {
     }
 };
 
+// ---------------------------------------------------------------- src/samplers/sobol.rs + lowdiscrepancy.rs:507-560
+// SobolSampler, a GlobalSampler like Halton: sample index = sobol_interval_to_index(log2 resolution, sample
+// number, pixel - sample_bounds.min), dimension d = the index's bits times the d-th 32x52 generator matrix.  The generator
+// matrices are constant data (Joe & Kuo direction numbers): tools/make_sobol_tables.py converts the reference's
+// src/core/sobolmatrices.rs into pbrt-rs_b200/data/sobol_tables.bin, embedded here (oracle_capi.cpp) and in the library.
+// Where the port cannot run this follows pbrt-v3 (samplers/sobol.cpp, core/lowdiscrepancy.h):
+//   Q1 lowdiscrepancy.rs:529-534 the second loop of sobol_interval_to_index never shifts `b` nor advances `c`: it cannot
+//      terminate                                                                                   -> FIX (b >>= 1, c += 1)
+//   Q2 samplers/sobol.rs:56-58 SobolSampler::sample_dimension is todo!()                          -> FIX: pbrt-v3 SampleDimension
+//      (sobol_sample(index, dim, 0); dimensions 0 / 1 remapped to the pixel: s * resolution + sample_bounds.min, minus the
+//      pixel, clamped to [0, 1 - eps])
+//   Q3 the non-float64 branch of sobol_sample (:553-560) is used as written (f32 build)
+struct SobolTables {
+    uint32_t n_dims = 0, size = 0, n_vdc = 0, n_inv = 0;
+    const uint32_t* m32 = nullptr;
+    const uint64_t *vdc = nullptr, *vdc_inv = nullptr;
+    int sb_min[2] = {0, 0};
+    int resolution = 1, log2_resolution = 0;
+    bool load(const unsigned char* blob, size_t bytes) {
+        if (bytes < 32) return false;
+        uint32_t h[8];
+        std::memcpy(h, blob, 32);
+        if (h[0] != 0x31424F53u) return false;
+        n_dims = h[1]; size = h[2]; n_vdc = h[3]; n_inv = h[4];
+        const size_t need = 32 + (size_t)n_dims * size * 4 + ((size_t)n_vdc + n_inv) * size * 8;
+        if (bytes < need) return false;
+        m32 = reinterpret_cast<const uint32_t*>(blob + 32);
+        vdc = reinterpret_cast<const uint64_t*>(blob + 32 + (size_t)n_dims * size * 4);
+        vdc_inv = vdc + (size_t)n_vdc * size;
+        return true;
+    }
+    void init(int sb_x0, int sb_y0, int sb_w, int sb_h) {                               // SobolSampler::new, sobol.rs:20-37
+        sb_min[0] = sb_x0; sb_min[1] = sb_y0;
+        int v = std::max(sb_w, sb_h), r = 1, l = 0;                                      // round_up_pow2_i32 / log_2_int_i32
+        while (r < v) { r <<= 1; ++l; }
+        resolution = r;
+        log2_resolution = l;
+    }
+    uint64_t interval_to_index(uint32_t m, uint64_t frame, int px, int py) const {      // lowdiscrepancy.rs:507-536, Q1
+        if (m == 0) return 0;
+        const uint32_t m2 = m << 1;
+        uint64_t index = frame << m2;
+        uint64_t delta = 0;
+        for (int c = 0; frame != 0; frame >>= 1, ++c)
+            if (frame & 1) delta ^= vdc[(size_t)(m - 1) * size + c];
+        uint64_t b = (uint64_t)((((uint32_t)px) << m) | (uint32_t)py) ^ delta;
+        for (int c = 0; b != 0; b >>= 1, ++c)
+            if (b & 1) index ^= vdc_inv[(size_t)(m - 1) * size + c];
+        return index;
+    }
+    Float sample(int64_t a, int dimension) const {                                      // sobol_sample :538-560, scramble = 0
+        uint32_t v = 0;
+        for (size_t i = (size_t)dimension * size; a != 0; a >>= 1, ++i)
+            if (a & 1) v ^= m32[i];
+        return fmin_(kOneMinusEpsilon, (Float)v * 2.3283064365386963e-10f);
+    }
+    int64_t index_for_sample(int px, int py, uint64_t sample_num) const {               // sobol.rs:48-54
+        return (int64_t)interval_to_index((uint32_t)log2_resolution, sample_num, px - sb_min[0], py - sb_min[1]);
+    }
+    Float sample_dimension(int64_t index, int dim, int px, int py) const {              // Q2: pbrt-v3 SobolSampler::SampleDimension
+        Float s = sample(index, dim);
+        if (dim == 0 || dim == 1) {
+            s = s * (Float)resolution + (Float)sb_min[dim];
+            s = clampf(s - (Float)(dim == 0 ? px : py), 0.0f, kOneMinusEpsilon);
+        }
+        return s;
+    }
+};
+// the embedded table (oracle_capi.cpp); nullptr when the blob is missing or malformed
+const SobolTables* sobol_tables_base();
+
 // PixelSampler (sampler.rs:257-322): n_sampled_dimensions tabulated 1D and 2D dimensions of spp values each, filled by
 // start_pixel of StratifiedSampler (samplers/stratified.rs:44-105) or ZeroTwoSequenceSampler (samplers/zerotwosequence.rs:31-63);
 // no sample arrays are requested on this path (PathIntegrator never calls request_*_array).  Where the port cannot run,
@@ -1073,21 +1144,26 @@ struct Sampler {          // kind 0: RandomSampler (samplers/random.rs:29-56), e
     int kind = 0;         // kind 2 / 3: PixelSampler::get_1d/get_2d (sampler.rs:289-307): tables first, then `rng`
     const HaltonTables* halton = nullptr;
     const PixelTables* tabs = nullptr;
+    const SobolTables* sobol = nullptr;                        // kind 4: SobolSampler, a GlobalSampler like Halton
     int64_t index = 0;
     int dimension = 0;
+    int pix_x = 0, pix_y = 0;                                  // current_pixel (Sobol' remaps dimensions 0 / 1 to it)
     int cur1 = 0, cur2 = 0, sample_index = 0;                  // current_1d_dimension, current_2d_dimension, current_pixel_sample_index
+    bool tabulated() const { return kind == 2 || kind == 3; }
     void start_sample(int px, int py, uint64_t sample_num) {   // start_pixel / set_sample_number (sampler.rs:347-350,405-409,316-321)
         if (kind == 1) { index = halton->index_for_sample(px, py, sample_num); dimension = 0; }
-        if (kind >= 2) { cur1 = cur2 = 0; sample_index = (int)sample_num; }
+        if (kind == 4) { index = sobol->index_for_sample(px, py, sample_num); dimension = 0; pix_x = px; pix_y = py; }
+        if (tabulated()) { cur1 = cur2 = 0; sample_index = (int)sample_num; }
     }
+    Float global_dimension(int dim) const { return kind == 1 ? halton->sample_dimension(index, dim) : sobol->sample_dimension(index, dim, pix_x, pix_y); }
     Float get_1d() {
-        if (kind == 1) return halton->sample_dimension(index, dimension++);
-        if (kind >= 2 && cur1 < tabs->n_dims) return tabs->t1[(size_t)(cur1++) * tabs->spp + sample_index];
+        if (kind == 1 || kind == 4) return global_dimension(dimension++);
+        if (tabulated() && cur1 < tabs->n_dims) return tabs->t1[(size_t)(cur1++) * tabs->spp + sample_index];
         return rng.uniform_float();
     }
     void get_2d(Float* a, Float* b) {                          // x then y
-        if (kind == 1) { *a = halton->sample_dimension(index, dimension); *b = halton->sample_dimension(index, dimension + 1); dimension += 2; return; }
-        if (kind >= 2 && cur2 < tabs->n_dims) {
+        if (kind == 1 || kind == 4) { *a = global_dimension(dimension); *b = global_dimension(dimension + 1); dimension += 2; return; }
+        if (tabulated() && cur2 < tabs->n_dims) {
             const size_t o = ((size_t)(cur2++) * tabs->spp + sample_index) * 2;
             *a = tabs->t2[o]; *b = tabs->t2[o + 1];
             return;
@@ -1361,6 +1437,11 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
     const size_t npix = (size_t)film.width() * film.height();  // cropped_pixel_bounds.area() (film.rs:51)
     HaltonTables halton;
     if (pd.sampler == 1) halton.init(W, H);                   // sample_bounds extent (halton.rs:69)
+    SobolTables sobol;
+    if (pd.sampler == 4) {
+        if (sobol_tables_base()) sobol = *sobol_tables_base();
+        sobol.init(film.sb_x0, film.sb_y0, W, H);
+    }
     std::vector<RGB> acc(npix, rgb(0));
     std::vector<Float> wsum(npix, 0.0f);
     std::vector<std::vector<Stray>> strays(threads);
@@ -1377,16 +1458,17 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
             Sampler tile_sampler;
             tile_sampler.kind = pd.sampler;
             tile_sampler.halton = &halton;
+            tile_sampler.sobol = &sobol;
             tile_sampler.rng.set_sequence((uint64_t)(ty * tiles_x + tx));                       // integrator.rs:414-415
             int x0 = film.sb_x0 + tx * 16, x1 = std::min(x0 + 16, film.sb_x1);
             int y0 = film.sb_y0 + ty * 16, y1 = std::min(y0 + 16, film.sb_y1);
             // mode 0 accumulates into a tile-local buffer first (FilmTile), merged below
             PixelTables tabs;
-            if (pd.sampler >= 2) tabs.resize(pd.n_sampled_dimensions, pd.spp);
+            if (pd.sampler == 2 || pd.sampler == 3) tabs.resize(pd.n_sampled_dimensions, pd.spp);
             tile_sampler.tabs = &tabs;
             for (int y = y0; y < y1; ++y)
                 for (int x = x0; x < x1; ++x) {
-                    if (pd.sampler >= 2) {                                                      // Sampler::start_pixel (integrator.rs:433)
+                    if (pd.sampler == 2 || pd.sampler == 3) {                                   // Sampler::start_pixel (integrator.rs:433)
                         // mode 1: the tables of a pixel come from their own stream, RNG::new(W*H*spp + pixel index)
                         RNG table_rng;
                         table_rng.set_sequence((uint64_t)W * H * (uint64_t)pd.spp + ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)));
@@ -1396,6 +1478,7 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                         Sampler own;
                         own.kind = pd.sampler;
                         own.halton = &halton;
+                        own.sobol = &sobol;
                         own.tabs = &tabs;
                         uint64_t order = ((uint64_t)(y - film.sb_y0) * W + (uint64_t)(x - film.sb_x0)) * (uint64_t)pd.spp + (uint64_t)s;
                         if (mode == 1) own.rng.set_sequence(order);

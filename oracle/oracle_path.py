@@ -38,7 +38,7 @@ class PathDesc(C.Structure):
                 ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
 
 
-_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
+_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3, "sobol": 4}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4, "substrate": 5}
 _STRAT = {"uniform": 0, "power": 1, "spatial": 2}
 _FILTER = {"box": 0, "gaussian": 1, "triangle": 2, "mitchell": 3, "sinc": 4}
@@ -139,6 +139,8 @@ def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sa
     p.x_samples, p.y_samples, p.jitter = x_samples, y_samples, int(jitter)
     if sampler == "stratified":
         assert x_samples * y_samples == spp, "StratifiedSampler: spp = x_samples * y_samples (stratified.rs:31-32)"
+    if sampler == "sobol":
+        assert spp & (spp - 1) == 0, "SobolSampler rounds spp up to a power of two (sobol.rs:22-28); pass the rounded value"
     if sampler == "zerotwo":
         assert spp & (spp - 1) == 0, "ZeroTwoSequenceSampler rounds spp up to a power of two (zerotwosequence.rs:21); pass the rounded value"
     return p
@@ -160,6 +162,17 @@ def halton_probe(res, pixel, sample_num, n_dims=8, n_perm=32):
     O.lib().orc_halton_probe(int(res[0]), int(res[1]), int(pixel[0]), int(pixel[1]), C.c_uint64(int(sample_num)), int(n_dims), C.byref(index),
                              _p(dims), int(n_perm), _p(perm))
     return index.value, dims, perm
+
+
+def sobol_probe(sample_bounds, pixel, sample_num, n_dims=8, raw=False):
+    """SobolSampler probe: (sample index, first n_dims dimensions).  sample_bounds = (x0, y0, w, h).  raw=True: sample_num is
+    taken as the Sobol' index itself and the dimensions are sobol_sample(index, d) without the pixel remap."""
+    index = C.c_int64()
+    dims = np.zeros(n_dims, np.float32)
+    rc = O.lib().orc_sobol_probe(int(sample_bounds[0]), int(sample_bounds[1]), int(sample_bounds[2]), int(sample_bounds[3]), int(pixel[0]),
+                                 int(pixel[1]), C.c_uint64(int(sample_num)), int(n_dims), int(raw), C.byref(index), _p(dims))
+    assert rc == 0, "the Sobol' table is not embedded in liboracle.so"
+    return index.value, dims
 
 
 def _p(a):

@@ -59,7 +59,7 @@ class PathDesc(C.Structure):
                 ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
 
 
-_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3}
+_SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3, "sobol": 4}
 
 
 def matte(kd, sigma=0.0):
@@ -531,12 +531,13 @@ class PathIntegrator:
     """Mirror of src/integrators/path.rs PathIntegrator + SamplerIntegrator::render; sampler = "random" (RandomSampler streams
     per (pixel, sample)), "halton" (HaltonSampler, src/samplers/halton.rs), "stratified" (StratifiedSampler::new(x_samples,
     y_samples, jitter, n_sampled_dimensions), src/samplers/stratified.rs) or "zerotwo" (ZeroTwoSequenceSampler::new(spp,
-    n_sampled_dimensions), src/samplers/zerotwosequence.rs: spp is rounded up to a power of two as the constructor does)."""
+    n_sampled_dimensions), src/samplers/zerotwosequence.rs: spp is rounded up to a power of two as the constructor does) or
+    "sobol" (SobolSampler::new(spp, sample_bounds), src/samplers/sobol.rs; spp rounded up likewise)."""
 
     def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sampler="random",
                  n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True):
-        if sampler == "zerotwo":
-            spp = 1 << max(0, int(spp) - 1).bit_length()             # round_up_pow2_i64, zerotwosequence.rs:21
+        if sampler in ("zerotwo", "sobol"):
+            spp = 1 << max(0, int(spp) - 1).bit_length()             # round_up_pow2_i64, zerotwosequence.rs:21, sobol.rs:22-28
         if sampler == "stratified" and x_samples and y_samples:
             spp = x_samples * y_samples                              # stratified.rs:31-32
         self.accel, self.camera = accel, camera

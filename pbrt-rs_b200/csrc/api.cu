@@ -86,6 +86,8 @@ void pb2_scene::free_device() {
     if (d_halton_primes) cudaFree(d_halton_primes);
     if (d_halton_sums) cudaFree(d_halton_sums);
     d_halton_perms = d_halton_primes = d_halton_sums = nullptr;
+    if (d_sobol) cudaFree(d_sobol);
+    d_sobol = nullptr;
     if (d_tab1) cudaFree(d_tab1);
     if (d_tab2) cudaFree(d_tab2);
     d_tab1 = d_tab2 = nullptr;

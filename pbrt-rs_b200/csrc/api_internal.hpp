@@ -132,6 +132,7 @@ struct pb2_scene {
     void* d_halton_perms = nullptr;
     void* d_halton_primes = nullptr;
     void* d_halton_sums = nullptr;
+    void* d_sobol = nullptr;            // SobolSampler generator matrices: [m32 1024 x 52 u32 | vdc 25 x 52 u64 | vdc_inv 26 x 52 u64]
     // PixelSampler tables (stratified / (0,2)) and the parameters they were generated for
     void* d_tab1 = nullptr;
     void* d_tab2 = nullptr;

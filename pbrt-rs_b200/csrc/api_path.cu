@@ -243,9 +243,15 @@ static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_pa
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
     if (path->light_strategy < PB2_LIGHTS_UNIFORM || path->light_strategy > PB2_LIGHTS_SPATIAL)
         return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
-    if (path->sampler < PB2_SAMPLER_RANDOM || path->sampler > PB2_SAMPLER_ZEROTWO)
+    if (path->sampler < PB2_SAMPLER_RANDOM || path->sampler > PB2_SAMPLER_SOBOL)
         return set_error(PB2_ERR_INVALID, "unknown sampler %d", path->sampler);
-    if (path->sampler >= PB2_SAMPLER_STRATIFIED) {
+    if (path->sampler == PB2_SAMPLER_SOBOL) {
+        if ((path->spp & (path->spp - 1)) != 0)
+            return set_error(PB2_ERR_INVALID, "SobolSampler: spp %d is not a power of two (sobol.rs:22-28 rounds up; pass the rounded count)", path->spp);
+        if (5 + 8 * (path->max_depth + 1) > 1024)                                              // sobolmatrices.rs:1 NUM_SOBOL_DIMENSIONS
+            return set_error(PB2_ERR_LIMIT, "SobolSampler has 1024 dimensions; max_depth %d needs %d", path->max_depth, 5 + 8 * (path->max_depth + 1));
+    }
+    if (path->sampler == PB2_SAMPLER_STRATIFIED || path->sampler == PB2_SAMPLER_ZEROTWO) {
         if (path->n_sampled_dimensions < 0 || path->n_sampled_dimensions > 127)
             return set_error(PB2_ERR_INVALID, "n_sampled_dimensions %d outside [0, 127]", path->n_sampled_dimensions);
         if (path->sampler == PB2_SAMPLER_STRATIFIED && (path->x_samples <= 0 || path->y_samples <= 0 || (long long)path->x_samples * path->y_samples != path->spp))
@@ -308,11 +314,40 @@ static int pixel_sampler_tables(pb2_scene* scene, const pb2_path_desc* path, int
     return PB2_OK;
 }
 
-static int sampler_view(pb2_scene* scene, const pb2_path_desc* path, int sb_w, int sb_h, cudaStream_t st, SamplerView* out) {
+// The Sobol' generator matrices (core/sobolmatrices.rs: constant data, converted by tools/make_sobol_tables.py into
+// data/sobol_tables.bin and linked in by the Makefile: ld -r -b binary).
+extern "C" const unsigned char _binary_data_sobol_tables_bin_start[], _binary_data_sobol_tables_bin_end[];
+static int sobol_view(pb2_scene* scene, int sb_x0, int sb_y0, int sb_w, int sb_h, SamplerView* out) {
+    const unsigned char* blob = _binary_data_sobol_tables_bin_start;
+    const size_t bytes = (size_t)(_binary_data_sobol_tables_bin_end - _binary_data_sobol_tables_bin_start);
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (bytes >= 32) memcpy(h, blob, 32);
+    const size_t n32 = (size_t)h[1] * h[2], nv = (size_t)h[3] * h[2], ni = (size_t)h[4] * h[2];
+    if (h[0] != 0x31424F53u || h[2] != 52u || h[1] < 1024u || bytes < 32 + n32 * 4 + (nv + ni) * 8)
+        return set_error(PB2_ERR_STATE, "the embedded Sobol' table is malformed (rebuild with tools/make_sobol_tables.py)");
+    if (!scene->d_sobol) {
+        PB2_CUDA(cudaMalloc(&scene->d_sobol, bytes - 32));
+        PB2_CUDA(cudaMemcpy(scene->d_sobol, blob + 32, bytes - 32, cudaMemcpyHostToDevice));
+    }
+    out->sobol_m32 = (const uint32_t*)scene->d_sobol;
+    out->sobol_vdc = (const unsigned long long*)((const char*)scene->d_sobol + n32 * 4);
+    out->sobol_vdc_inv = out->sobol_vdc + nv;
+    out->sobol_min[0] = sb_x0;
+    out->sobol_min[1] = sb_y0;
+    int res = 1, lg = 0;                                                                     // round_up_pow2_i32 / log_2_int_i32, sobol.rs:29-30
+    while (res < std::max(sb_w, sb_h)) { res <<= 1; ++lg; }
+    if ((uint32_t)lg > h[3]) return set_error(PB2_ERR_LIMIT, "SobolSampler: sample bounds of %d pixels exceed the 2^%u the van der Corput matrices cover", std::max(sb_w, sb_h), h[3]);
+    out->sobol_resolution = res;
+    out->sobol_log2_resolution = lg;
+    return PB2_OK;
+}
+
+static int sampler_view(pb2_scene* scene, const pb2_path_desc* path, int sb_x0, int sb_y0, int sb_w, int sb_h, cudaStream_t st, SamplerView* out) {
     memset(out, 0, sizeof *out);
     const int sampler = path->sampler;
     out->kind = sampler;
-    if (sampler >= PB2_SAMPLER_STRATIFIED) return pixel_sampler_tables(scene, path, sb_w, sb_h, st, out);
+    if (sampler == PB2_SAMPLER_SOBOL) return sobol_view(scene, sb_x0, sb_y0, sb_w, sb_h, out);
+    if (sampler == PB2_SAMPLER_STRATIFIED || sampler == PB2_SAMPLER_ZEROTWO) return pixel_sampler_tables(scene, path, sb_w, sb_h, st, out);
     if (sampler != PB2_SAMPLER_HALTON) return PB2_OK;
     if (!scene->d_halton_perms) {
         constexpr int kPrimes = 1000;                                                        // lowdiscrepancy.rs:11
@@ -661,7 +696,7 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     PB2_CUDA(film->chain.enter((cudaStream_t)stream));
     const PathParams pp{path->max_depth, path->rr_threshold};
     SamplerView smp;
-    rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
+    rc = sampler_view(scene, path, fv.sb_x0, fv.sb_y0, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
     if (rc) return rc;
     if (path->light_strategy == PB2_LIGHTS_SPATIAL && scene->lights.size() > 1) {      // PathIntegrator::pre_process (path.rs:58-63)
         rc = ensure_spatial(scene, (cudaStream_t)stream);
@@ -705,7 +740,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     uint32_t* d_s = nullptr;
     float *d_L = nullptr, *d_pf = nullptr;
     SamplerView smp;
-    rc = sampler_view(scene, path, fv.sb_w, fv.sb_h, 0, &smp);
+    rc = sampler_view(scene, path, fv.sb_x0, fv.sb_y0, fv.sb_w, fv.sb_h, 0, &smp);
     if (rc) return rc;
     if (path->light_strategy == PB2_LIGHTS_SPATIAL && scene->lights.size() > 1) {
         rc = ensure_spatial(scene, 0);

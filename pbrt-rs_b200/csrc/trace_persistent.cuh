@@ -50,11 +50,14 @@ PB2_D bool finite_nonzero(float v) { return v != 0.0f && fabsf(v) < __int_as_flo
 // comparisons, and the three same-axis comparisons hold automatically whenever exit > 0 (far >= near before widening, and
 // widening a positive value never decreases it); entry equals the reference's final t_min.  Arguments: the near and far
 // planes of the box for this ray's direction signs.  Returns the entry distance, +inf when the box is missed or starts
-// beyond t_max.
+// beyond t_max.  The widening factor is applied once, to the smallest far value: x -> round(x * widen) is non-decreasing
+// (widen > 0, rounding is monotone), so min(round(a*w), round(b*w), round(c*w)) = round(min(a, b, c) * w) bit for bit — two
+// multiplies per box fewer than widening each far plane as geometry.rs:722-738 does.  (Only the sign of a zero can differ, and
+// exit enters two comparisons only.)
 PB2_D float quad_child_entry(float nx, float ny, float nz, float fx, float fy, float fz, vec3 o, vec3 inv, float t_max) {
     const float widen = 1.0f + 2.0f * gammaf_(3.0f);
     const float tn = fmaxf(fmaxf((nx - o.x) * inv.x, (ny - o.y) * inv.y), (nz - o.z) * inv.z);
-    const float tf = fminf(fminf(((fx - o.x) * inv.x) * widen, ((fy - o.y) * inv.y) * widen), ((fz - o.z) * inv.z) * widen);
+    const float tf = fminf(fminf((fx - o.x) * inv.x, (fy - o.y) * inv.y), (fz - o.z) * inv.z) * widen;
     return (tn <= tf && tf > 0.0f && tn < t_max) ? tn : __int_as_float(0x7f800000);
 }
 PB2_D void swap_if(bool c, uint32_t& ra, float& ta, uint32_t& rb, float& tb) {

@@ -46,7 +46,7 @@ constexpr unsigned kStateContinues = 4u;       // bit 2: the path continues with
 // word is valid only for the launch that wrote it and the array never needs clearing), and scatters.  The input is read once.
 // The CTA of the last tile leaves the totals in the queue counters and does the per-bounce bookkeeping k_iter_begin used to do in
 // a launch of its own.  (Round 1: count -> one-CTA scan -> scatter, three launches that read the queue and the state bytes twice.)
-constexpr int kSelThreads = 256, kSelItems = 8, kSelTile = kSelThreads * kSelItems;
+constexpr int kSelThreads = 256, kSelItems = 16, kSelTile = kSelThreads * kSelItems;
 struct SelectJob {
     const uint32_t* in;                        // the bounce's active queue (sorted by slot)
     const unsigned long long* n_in;
@@ -84,6 +84,45 @@ __device__ __forceinline__ void select_finish(const SelectJob& j, unsigned long 
         j.counters[C_WORK_SHADOW] = 0;
     }
 }
+// Exclusive offset of `tile` for one output: the sum of the predecessors' counts, walking back 64 tiles per round (two
+// descriptors per lane in flight) until one that already holds its inclusive prefix.  Run by one warp per output; the
+// tiles in flight started at about the same time, so the walk covers most of them and its depth is what the pass costs.
+__device__ __forceinline__ unsigned select_look_back(const unsigned long long* st, unsigned tile, unsigned epoch, unsigned lane) {
+    const unsigned long long tag = (unsigned long long)epoch << 32;
+    unsigned excl = 0u;
+    int look = (int)tile - 1;
+    for (;;) {
+        const int i0 = look - (int)lane, i1 = look - 32 - (int)lane;            // nearest first: lane 0 of the first word
+        unsigned long long w0, w1;
+        unsigned incl0, incl1;
+        for (;;) {                                   // wait for every predecessor up to the nearest inclusive prefix
+            w0 = i0 >= 0 ? ld_status(st + i0) : (tag | (2ull << 30));
+            w1 = i1 >= 0 ? ld_status(st + i1) : (tag | (2ull << 30));
+            const bool v0 = (w0 >> 32) == (unsigned long long)epoch && ((w0 >> 30) & 3ull) != 0ull;
+            const bool v1 = (w1 >> 32) == (unsigned long long)epoch && ((w1 >> 30) & 3ull) != 0ull;
+            const unsigned vm0 = __ballot_sync(0xFFFFFFFFu, v0), vm1 = __ballot_sync(0xFFFFFFFFu, v1);
+            incl0 = __ballot_sync(0xFFFFFFFFu, v0 && ((w0 >> 30) & 3ull) == 2ull);
+            incl1 = __ballot_sync(0xFFFFFFFFu, v1 && ((w1 >> 30) & 3ull) == 2ull);
+            if (incl0) {
+                const unsigned need = (1u << (__ffs(incl0) - 1)) - 1u;
+                if ((vm0 & need) == need) break;
+            } else if (vm0 == 0xFFFFFFFFu) {
+                const unsigned need = incl1 ? ((1u << (__ffs(incl1) - 1)) - 1u) : 0xFFFFFFFFu;
+                if ((vm1 & need) == need) break;
+            }
+        }
+        // sum the counts up to and including the nearest predecessor that holds an inclusive prefix
+        const int stop0 = incl0 ? __ffs(incl0) - 1 : 31;
+        const int stop1 = incl0 ? -1 : (incl1 ? __ffs(incl1) - 1 : 31);
+        unsigned v = ((int)lane <= stop0 ? (unsigned)(w0 & 0x3FFFFFFFull) : 0u) + ((int)lane <= stop1 ? (unsigned)(w1 & 0x3FFFFFFFull) : 0u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        excl += v;
+        if (incl0 || incl1) break;
+        look -= 64;
+    }
+    return excl;
+}
 __global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
     __shared__ unsigned s_tile;
     __shared__ unsigned s_warp[3][kSelThreads / 32];
@@ -107,8 +146,11 @@ __global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
         const unsigned long long i0 = (unsigned long long)tile * kSelTile + (unsigned long long)threadIdx.x * kSelItems;
         uint32_t slot[kSelItems];
         if (i0 + kSelItems <= n) {
-            const uint4 a = *reinterpret_cast<const uint4*>(j.in + i0), b = *reinterpret_cast<const uint4*>(j.in + i0 + 4);
-            slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w; slot[4] = b.x; slot[5] = b.y; slot[6] = b.z; slot[7] = b.w;
+#pragma unroll
+            for (int k = 0; k < kSelItems; k += 4) {
+                const uint4 a = *reinterpret_cast<const uint4*>(j.in + i0 + k);
+                slot[k] = a.x; slot[k + 1] = a.y; slot[k + 2] = a.z; slot[k + 3] = a.w;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < kSelItems; ++k) slot[k] = i0 + k < n ? j.in[i0 + k] : 0u;
@@ -134,43 +176,19 @@ __global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) s_warp[q][warp] = inc[q];
         __syncthreads();
-        // ---- warp 0: tile totals, publish, look back ----
-        if (warp == 0u) {
+        // ---- warps 0-2: tile total of output `warp`, publish it, look back ----
+        if (warp < 3u) {
+            const int q = (int)warp;
+            unsigned total = 0u;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                unsigned total = 0u;
-#pragma unroll
-                for (int w = 0; w < kSelThreads / 32; ++w) total += s_warp[q][w];
-                unsigned long long* st = j.status + (size_t)q * j.max_tiles;
-                if (tile == 0u) {
-                    if (lane == 0u) { st_status(st, tag | (2ull << 30) | total); s_base[q] = 0u; }
-                } else {
-                    if (lane == 0u) st_status(st + tile, tag | (1ull << 30) | total);
-                    unsigned excl = 0u;
-                    int look = (int)tile - 1;
-                    for (;;) {                                       // 32 predecessors per round, nearest first
-                        const int idx = look - (int)lane;
-                        unsigned long long w;
-                        unsigned incl_mask;
-                        for (;;) {                                   // wait for every predecessor up to the nearest inclusive prefix
-                            w = idx >= 0 ? ld_status(st + idx) : (tag | (2ull << 30));
-                            const bool valid = (w >> 32) == (unsigned long long)j.epoch && ((w >> 30) & 3ull) != 0ull;
-                            const unsigned valid_mask = __ballot_sync(0xFFFFFFFFu, valid);
-                            incl_mask = __ballot_sync(0xFFFFFFFFu, valid && ((w >> 30) & 3ull) == 2ull);
-                            const unsigned need = incl_mask ? ((1u << (__ffs(incl_mask) - 1)) - 1u) : 0xFFFFFFFFu;
-                            if ((valid_mask & need) == need) break;
-                        }
-                        // sum the values up to and including the nearest predecessor that holds an inclusive prefix
-                        const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
-                        unsigned v = (int)lane <= stop ? (unsigned)(w & 0x3FFFFFFFull) : 0u;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                        excl += v;
-                        if (incl_mask) break;
-                        look -= 32;
-                    }
-                    if (lane == 0u) { st_status(st + tile, tag | (2ull << 30) | (unsigned long long)(excl + total)); s_base[q] = excl; }
-                }
+            for (int w = 0; w < kSelThreads / 32; ++w) total += s_warp[q][w];
+            unsigned long long* st = j.status + (size_t)q * j.max_tiles;
+            if (tile == 0u) {
+                if (lane == 0u) { st_status(st, tag | (2ull << 30) | total); s_base[q] = 0u; }
+            } else {
+                if (lane == 0u) st_status(st + tile, tag | (1ull << 30) | total);
+                const unsigned excl = select_look_back(st, tile, j.epoch, lane);
+                if (lane == 0u) { st_status(st + tile, tag | (2ull << 30) | (unsigned long long)(excl + total)); s_base[q] = excl; }
             }
         }
         __syncthreads();
@@ -282,6 +300,41 @@ __device__ __forceinline__ float halton_dimension(const SamplerView& h, unsigned
     else halton_digits<unsigned, true>((unsigned)a, base, perm, inv_base, &reversed, &inv_base_n);
     return fminf(inv_base_n * (__ull2float_rn(reversed) + inv_base * (float)perm[0] / (1.0f - inv_base)), PB2_ONE_MINUS_EPS);
 }
+// SobolSampler (samplers/sobol.rs:48-58, lowdiscrepancy.rs:507-560; pbrt-v3 semantics where the port cannot run: DESIGN.md).
+constexpr unsigned kSobolMatrixSize = 52u;                                 // sobolmatrices.rs:2
+__device__ __forceinline__ unsigned long long sobol_index(const SamplerView& h, int px, int py, unsigned long long frame) {     // sobol_interval_to_index
+    const unsigned m = (unsigned)h.sobol_log2_resolution;
+    if (m == 0u) return 0ull;
+    unsigned long long index = frame << (m << 1), delta = 0ull;
+    const unsigned long long* vdc = h.sobol_vdc + (size_t)(m - 1u) * kSobolMatrixSize;
+    const unsigned long long* inv = h.sobol_vdc_inv + (size_t)(m - 1u) * kSobolMatrixSize;
+    while (frame) {                                                        // XOR over the set bits, in any order
+        delta ^= __ldg(vdc + (__ffsll((long long)frame) - 1));
+        frame &= frame - 1ull;
+    }
+    unsigned long long b = (unsigned long long)((((unsigned)px) << m) | (unsigned)py) ^ delta;
+    while (b) {
+        index ^= __ldg(inv + (__ffsll((long long)b) - 1));
+        b &= b - 1ull;
+    }
+    return index;
+}
+__device__ __forceinline__ float sobol_raw(const SamplerView& h, unsigned long long a, unsigned dim) {       // sobol_sample, scramble = 0
+    const uint32_t* m = h.sobol_m32 + (size_t)dim * kSobolMatrixSize;
+    unsigned v = 0u;
+    while (a) {
+        v ^= __ldg(m + (__ffsll((long long)a) - 1));
+        a &= a - 1ull;
+    }
+    return fminf(PB2_ONE_MINUS_EPS, __uint2float_rn(v) * 2.3283064365386963e-10f);
+}
+// SobolSampler::sample_dimension for dimensions 0 / 1 (pbrt-v3: the film position inside pixel (x, y))
+__device__ __forceinline__ float sobol_pixel_dimension(const SamplerView& h, unsigned long long index, unsigned dim, int pixel) {
+    float s = sobol_raw(h, index, dim);
+    s = s * (float)h.sobol_resolution + (float)h.sobol_min[dim];
+    s = s - (float)pixel;
+    return s < 0.0f ? 0.0f : (s > PB2_ONE_MINUS_EPS ? PB2_ONE_MINUS_EPS : s);
+}
 // One path's sampler.  RandomSampler: the PCG32 stream; HaltonSampler: (index, dimension) of the sequence; PixelSamplers
 // (stratified, (0,2)): PixelSampler::get_1d / get_2d (sampler.rs:289-307) — the next tabulated dimension of this pixel's
 // sample while one is left, then the PCG32 stream.  TABLES = false compiles the table branch out (k_shade is at its register limit).
@@ -292,15 +345,34 @@ struct PathSampler {
     unsigned cur1, cur2;          // current_1d_dimension, current_2d_dimension
     unsigned tab_base;            // sample * tab_n_pix + pixel
     const SamplerView* h;
-    __device__ __forceinline__ bool halton() const { return h->kind == 1; }
-    __device__ __forceinline__ bool tables() const { return h->kind >= 2; }
+    __device__ __forceinline__ bool sobol() const { return h->kind == 4; }
+    __device__ __forceinline__ bool global() const { return h->kind == 1 || h->kind == 4; }          // GlobalSampler (sampler.rs:324-410)
+    __device__ __forceinline__ bool tables() const { return h->kind == 2 || h->kind == 3; }         // PixelSampler (:257-322)
+    __device__ __forceinline__ unsigned long long global_index(const SlotInfo& si) const {         // get_index_for_sample
+        return sobol() ? sobol_index(*h, si.x - h->sobol_min[0], si.y - h->sobol_min[1], si.sample)
+                       : (unsigned long long)halton_index(*h, si.x, si.y, si.sample);
+    }
+    __device__ __forceinline__ float global_dimension(unsigned d) const {                          // sample_dimension, d >= 2 for Sobol'
+        return sobol() ? sobol_raw(*h, index, d) : halton_dimension(*h, index, d);
+    }
     __device__ __forceinline__ void start(const SamplerView& view, const SlotInfo& si) {   // start of a pixel sample
         h = &view;
         dim = 0u;
         cur1 = cur2 = 0u;
         tab_base = si.sample * view.tab_n_pix + si.pix;
-        if (halton()) index = (unsigned long long)halton_index(view, si.x, si.y, si.sample);
+        if (global()) index = global_index(si);
         else rng.set_sequence(si.seq);
+    }
+    // The first draw of every pixel sample: CameraSample::p_film's offset inside the pixel (sampler.rs:27-33).  Sobol' remaps
+    // dimensions 0 / 1 to the pixel, which needs the pixel's coordinates — known here, not carried in the path's sampler state.
+    __device__ __forceinline__ void film_offset(const SlotInfo& si, float* u0, float* u1) {
+        if (sobol()) {
+            *u0 = sobol_pixel_dimension(*h, index, 0u, si.x);
+            *u1 = sobol_pixel_dimension(*h, index, 1u, si.y);
+            dim = 2u;
+            return;
+        }
+        next2(u0, u1);
     }
     // `extra` = the PixelSampler dimension counters kept in bits 17-30 of the path's state word
     __device__ __forceinline__ void resume(const SamplerView& view, const SlotInfo& si, unsigned long long saved, unsigned extra) {
@@ -308,10 +380,10 @@ struct PathSampler {
         cur1 = extra & 0x7Fu;
         cur2 = (extra >> 7) & 0x7Fu;
         tab_base = si.sample * view.tab_n_pix + si.pix;
-        if (halton()) { index = (unsigned long long)halton_index(view, si.x, si.y, si.sample); dim = (unsigned)saved; }
+        if (global()) { index = global_index(si); dim = (unsigned)saved; }
         else { rng.state = saved; rng.inc = (si.seq << 1) | 1ull; }
     }
-    __device__ __forceinline__ unsigned long long save() const { return halton() ? (unsigned long long)dim : rng.state; }
+    __device__ __forceinline__ unsigned long long save() const { return global() ? (unsigned long long)dim : rng.state; }
     __device__ __forceinline__ unsigned extra() const { return cur1 | (cur2 << 7); }
     template <bool TABLES = true>
     __device__ __forceinline__ float next1() {                                             // Sampler::get_1d
@@ -320,7 +392,7 @@ struct PathSampler {
             ++cur1;
             return v;
         }
-        if (halton()) return halton_dimension(*h, index, dim++);
+        if (global()) return global_dimension(dim++);
         return rng.next_float();
     }
     template <bool TABLES = true>
@@ -331,7 +403,7 @@ struct PathSampler {
             *a = v.x; *b = v.y;
             return;
         }
-        if (halton()) { *a = halton_dimension(*h, index, dim); *b = halton_dimension(*h, index, dim + 1u); dim += 2u; return; }
+        if (global()) { *a = global_dimension(dim); *b = global_dimension(dim + 1u); dim += 2u; return; }
         *a = rng.next_float();
         *b = rng.next_float();
     }
@@ -431,8 +503,8 @@ __global__ void __launch_bounds__(kThreads) k_raygen(uint64_t n, PathMap map, Fi
         PathSampler smp;
         smp.start(map.smp, si);
         float u0, u1, l0 = 0.0f, l1 = 0.0f;
-        smp.next2(&u0, &u1);                                          // p_film offset (x then y)
-        if (smp.halton() && !(cam.lens_radius > 0.0f)) smp.dim += 3u; // time, p_lens: drawn, never used by a pinhole
+        smp.film_offset(si, &u0, &u1);                                // p_film offset (x then y)
+        if (smp.global() && !(cam.lens_radius > 0.0f)) smp.dim += 3u; // time, p_lens: drawn, never used by a pinhole
         else { (void)smp.next1(); smp.next2(&l0, &l1); }
         vec3 o, d;
         float t_max;
@@ -881,7 +953,7 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map,
             PathSampler rng;
             rng.start(map.smp, si);
             float u0, u1;
-            rng.next2(&u0, &u1);
+            rng.film_offset(si, &u0, &u1);
             const float pfx = (float)x + u0;
             const float pfy = (float)y + u1;
             film_footprint(f, pfx, pfy, [&](int px, int py, float fw) {
@@ -902,7 +974,7 @@ __global__ void __launch_bounds__(kThreads) k_film_accumulate_atomic(uint64_t n,
         PathSampler rng;
         rng.start(map.smp, si);
         float u0, u1;
-        rng.next2(&u0, &u1);
+        rng.film_offset(si, &u0, &u1);
         const float pfx = (float)si.x + u0;
         const float pfy = (float)si.y + u1;
         film_footprint(f, pfx, pfy, [&](int px, int py, float fw) { film_atomic_add(f, px, py, L * 1.0f * fw, fw); });
@@ -933,7 +1005,7 @@ __global__ void __launch_bounds__(kTileW * kTileH) k_film_accumulate_tiled(PathM
             PathSampler rng;
             rng.start(map.smp, si);
             float u0, u1;
-            rng.next2(&u0, &u1);
+            rng.film_offset(si, &u0, &u1);
             film_footprint(f, (float)si.x + u0, (float)si.y + u1, [&](int px, int py, float fw) {
                 const int cx = px - ox, cy = py - oy;
                 if (cx >= 0 && cy >= 0 && cx < tw && cy < th) {
@@ -1084,7 +1156,7 @@ __global__ void k_copy_li(uint64_t n, PathMap map, FilmView f, PathBuffers b, fl
         PathSampler rng;
         rng.start(map.smp, si);
         float u0, u1;
-        rng.next2(&u0, &u1);
+        rng.film_offset(si, &u0, &u1);
         pf_out[2 * slot] = (float)si.x + u0;
         pf_out[2 * slot + 1] = (float)si.y + u1;
     }
@@ -1138,7 +1210,7 @@ void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, con
 }
 void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
                   const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
-    const bool tables = map.smp.kind >= 2, sg = sh.indices != nullptr;
+    const bool tables = map.smp.kind == 2 || map.smp.kind == 3, sg = sh.indices != nullptr;
     if (tables && sg) launch_shade_t<true, true>(wf, sv, sh, b, map, film, pp, cur, n, st);
     else if (tables) launch_shade_t<true, false>(wf, sv, sh, b, map, film, pp, cur, n, st);
     else if (sg) launch_shade_t<false, true>(wf, sv, sh, b, map, film, pp, cur, n, st);

@@ -76,7 +76,7 @@ struct FilmView {
 // HaltonSampler state shared by all paths (samplers/halton.rs:24-37 + the permutation table of lowdiscrepancy.rs:333-349);
 // perms == nullptr selects the RandomSampler streams.
 struct SamplerView {
-    int kind;                     // PB2_SAMPLER_*: 0 random, 1 Halton, 2 stratified, 3 (0,2)-sequence
+    int kind;                     // PB2_SAMPLER_*: 0 random, 1 Halton, 2 stratified, 3 (0,2)-sequence, 4 Sobol'
     // PixelSampler tables (sampler.rs:257-322) of kinds 2 / 3, written by k_pixel_tables: value of tabulated dimension d,
     // sample s, pixel p at [(d * spp + s) * tab_n_pix + p] (a warp = neighbouring pixels of one sample: coalesced)
     int n_dims;
@@ -89,6 +89,13 @@ struct SamplerView {
     const uint32_t* prime_sums;   // offset of every base's permutation
     int base_scales[2], base_exponents[2];
     unsigned long long sample_stride, mult_inverse[2];
+    // SobolSampler (samplers/sobol.rs:13-37): generator matrices (core/sobolmatrices.rs; 52 entries per dimension / resolution),
+    // sample_bounds.min, resolution = the sample-bounds extent rounded up to a power of two
+    const uint32_t* sobol_m32;
+    const unsigned long long* sobol_vdc;
+    const unsigned long long* sobol_vdc_inv;
+    int sobol_min[2];
+    int sobol_resolution, sobol_log2_resolution;
 };
 
 // slot -> (pixel, sample index)

@@ -6,6 +6,7 @@ that introduced them.  They pin BOTH sides from then on: `-m "not gpu"` tests ch
 tests check the CUDA path against the same bytes, so the two cannot drift together unnoticed.
 
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py --round2 # rewrites tests/golden/path_r02.npz only
 
 Inputs (meshes, rays, (pixel, sample) pairs) are stored in the fixtures, so no generator has to reproduce them bit for bit.
 """
@@ -87,7 +88,28 @@ def main():
     np.savez_compressed(os.path.join(HERE, "path.npz"), **out)
     for f in ("raycast.npz", "path.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+    make_round2(scenes, OP)
+
+
+def make_round2(scenes, OP):
+    """Fixtures of the components added in round 2 (same scene, camera and (pixel, sample) list as path.npz; a file of their
+    own so that the round-1 fixtures stay byte-identical): per-sample radiance and film under the SobolSampler."""
+    g = np.load(os.path.join(HERE, "path.npz"))
+    ref = OP.Scene(golden_scene(scenes), 4)
+    fd = OP.film_desc(GOLDEN_CAMERA["res"])
+    out = {}
+    L, pf = ref.path_li(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", sampler="sobol", **GOLDEN_PATH), g["xy"], g["sample"])
+    out["L_sobol"], out["p_film_sobol"] = L.view(np.uint32), pf.view(np.uint32)
+    film, _ = ref.render(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", sampler="sobol", **GOLDEN_PATH), mode=1)
+    out["film_sobol"] = film.view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "path_r02.npz"), **out)
+    print("path_r02.npz", os.path.getsize(os.path.join(HERE, "path_r02.npz")), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    if "--round2" in sys.argv:                       # only path_r02.npz (the round-1 fixtures are left untouched)
+        ge.build()
+        from oracle import oracle_path as _OP
+        make_round2(ge.load_scenes(), _OP)
+    else:
+        main()

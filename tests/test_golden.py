@@ -20,7 +20,7 @@ def _mk():
 
 @pytest.fixture(scope="module")
 def G():
-    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path")}
+    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path", "path_r02")}
 
 
 @pytest.fixture(scope="module")
@@ -71,6 +71,31 @@ def test_oracle_reproduces_path_fixture(orc, OP, scenes, G):
     for v, f, c in zip(g["spatial_voxels"], g["spatial_func"], g["spatial_cdf"]):
         rf, rc, _ = ref.spatial_voxel(v, 3)
         assert np.array_equal(u32(rf), f) and np.array_equal(u32(rc), c)
+
+
+def test_oracle_reproduces_round2_fixture(orc, OP, scenes, G):
+    g, g2, mk = G["path"], G["path_r02"], _mk()
+    ref = OP.Scene(mk.golden_scene(scenes), 4)
+    fd = OP.film_desc(mk.GOLDEN_CAMERA["res"])
+    L, pf = ref.path_li(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", sampler="sobol", **mk.GOLDEN_PATH), g["xy"], g["sample"])
+    assert np.array_equal(u32(L), g2["L_sobol"]) and np.array_equal(u32(pf), g2["p_film_sobol"])
+    assert (g2["L_sobol"] != g["L_halton"]).any()
+    film, _ = ref.render(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", sampler="sobol", **mk.GOLDEN_PATH), mode=1)
+    assert np.array_equal(u32(film), g2["film_sobol"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_round2_fixture(gpu, scenes, G):
+    g, g2, mk = G["path"], G["path_r02"], _mk()
+    cam = mk.GOLDEN_CAMERA
+    accel = gpu.BVHAccel(gpu.scene_from_dict(mk.golden_scene(scenes)), max_prims_in_node=4)
+    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    integ = gpu.PathIntegrator(accel, camera, light_strategy="power", sampler="sobol", **mk.GOLDEN_PATH)
+    L, pf = integ.li(g["xy"], g["sample"])
+    assert np.array_equal(u32(L), g2["L_sobol"]) and np.array_equal(u32(pf), g2["p_film_sobol"])
+    film = gpu.Film(cam["res"])
+    integ.render(film)
+    assert np.array_equal(u32(film.read_xyzw()), g2["film_sobol"])
 
 
 @pytest.mark.gpu

@@ -93,6 +93,60 @@ def test_halton_known_answers(OP):
             assert ((dims >= 0) & (dims < 1)).all()
 
 
+def test_sobol_known_answers(OP):
+    """SobolSampler restatement (samplers/sobol.rs, lowdiscrepancy.rs:507-560, the generator matrices of sobolmatrices.rs as
+    converted by tools/make_sobol_tables.py).  Pins that do not come from the restatement: dimension 0 of the Sobol' sequence
+    is the base-2 radical inverse, dimension 1 starts 0, 1/2, 3/4, 1/4, 5/8, 1/8, 3/8, 7/8 (Bratley & Fox), the first two
+    dimensions form a (0, 2)-sequence, and sobol_interval_to_index must put dimensions 0 / 1 of EVERY sample of a pixel inside
+    that pixel — which only holds if the van der Corput matrices and their inverses are the right ones."""
+    want1 = [0.0, 0.5, 0.75, 0.25, 0.625, 0.125, 0.375, 0.875]
+    for i in range(8):
+        _, d = OP.sobol_probe((0, 0, 16, 16), (0, 0), i, n_dims=2, raw=True)
+        assert d[0] == np.float32(int(f"{i:03b}"[::-1], 2) / 8.0) and d[1] == np.float32(want1[i])
+    # (0, 2)-sequence: among the first 2^k points every elementary interval 2^-a x 2^-(k-a) holds exactly one
+    k = 6
+    pts = np.array([OP.sobol_probe((0, 0, 16, 16), (0, 0), i, n_dims=2, raw=True)[1] for i in range(1 << k)], np.float64)
+    for a in range(k + 1):
+        cells = (np.floor(pts[:, 0] * (1 << a)).astype(int) << (k - a)) | np.floor(pts[:, 1] * (1 << (k - a))).astype(int)
+        assert sorted(cells) == list(range(1 << k))
+    # higher dimensions are low-discrepancy too: 1024 points of dimensions (7, 200) fill a 16 x 16 grid nearly evenly
+    pts = np.array([OP.sobol_probe((0, 0, 16, 16), (0, 0), i, n_dims=201, raw=True)[1][[7, 200]] for i in range(1024)], np.float64)
+    counts = np.bincount((np.floor(pts[:, 0] * 16).astype(int) * 16 + np.floor(pts[:, 1] * 16).astype(int)), minlength=256)
+    assert counts.min() >= 2 and counts.max() <= 6
+    # pixel property, with sample bounds that neither start at 0 nor are a power of two (resolution rounds up to 256)
+    sb = (-2, -3, 200, 131)
+    for px, py in [(-2, -3), (0, 0), (57, 100), (197, 127), (120, 5)]:
+        for s in (0, 1, 2, 3, 17, 255):
+            idx, dims = OP.sobol_probe(sb, (px, py), s, n_dims=6)
+            assert idx >> 16 == s                                   # index = sample number << 2 log2(resolution), low bits locate the pixel
+            _, raw = OP.sobol_probe(sb, (px, py), idx, n_dims=2, raw=True)
+            pos = raw.astype(np.float64) * 256 + np.array(sb[:2])
+            assert np.floor(pos[0]) == px and np.floor(pos[1]) == py
+            assert 0 <= dims[0] < 1 and 0 <= dims[1] < 1 and np.allclose(dims[:2], pos - (px, py), atol=3e-5)
+            assert ((dims >= 0) & (dims < 1)).all()
+    # different pixels get different indices; consecutive samples of one pixel stay apart in every dimension
+    a = OP.sobol_probe(sb, (10, 10), 0, n_dims=8)[1]
+    b = OP.sobol_probe(sb, (10, 10), 1, n_dims=8)[1]
+    assert (np.abs(a[2:] - b[2:]) > 1e-3).all()
+
+
+def test_sobol_render_converges_like_the_other_samplers(OP, scenes):
+    """A Cornell box rendered with the SobolSampler has the RandomSampler's mean (unbiased) and, at equal spp, a lower error
+    against a 256-spp render — what a low-discrepancy sampler is for."""
+    sc = scenes.scene_c2()
+    cam = dict(scenes.C2_CAMERA, res=(40, 40))
+    fd = OP.film_desc(cam["res"])
+    ref = OP.Scene(sc, 4)
+    kw = dict(max_depth=3, rr_threshold=1.0, light_strategy="uniform")
+    truth = OP.resolve_rgb(ref.render(cam, fd, OP.path_desc(spp=256, **kw))[0]).astype(np.float64)
+    err = {}
+    for sampler in ("random", "sobol"):
+        img = OP.resolve_rgb(ref.render(cam, fd, OP.path_desc(spp=16, sampler=sampler, **kw))[0]).astype(np.float64)
+        err[sampler] = float(((img - truth) ** 2).mean())
+        assert abs(img.mean() / truth.mean() - 1.0) < 0.03
+    assert err["sobol"] < err["random"]
+
+
 def test_spot_and_distant_lights(OP, scenes):
     """SpotLight (src/lights/spot.rs) and DistantLight (src/lights/distant.rs) on a single matte floor quad, against the closed
     forms: directly below a spot of intensity I at height h the radiance is kd/pi * I / h^2, zero outside the cone; under a

@@ -10,5 +10,6 @@ FLAGS="-std=c++17 -O3 $ARCH -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract
 for f in api api_path kernels_traverse wavefront light_distrib bvh_hlbvh; do $NVCC $FLAGS -c csrc/$f.cu -o $OUT/$f.o & done
 for f in bvh_build camera_host; do $NVCC $FLAGS -x cu -c csrc/$f.cpp -o $OUT/$f.o & done
 wait
+ld -r -b binary -z noexecstack -o $OUT/sobol_tables.o data/sobol_tables.bin
 $NVCC -shared $ARCH -o ../build/libpbrt_b200_$NAME.so $OUT/*.o -ldl
 echo built build/libpbrt_b200_$NAME.so
