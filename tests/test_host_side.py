@@ -156,3 +156,33 @@ def test_oversized_leaf_is_refused_not_truncated(pb2):
     assert e.value.code == -5
     ok = pb2.BVHAccel(v[:3 * 60000], i[:60000], 255, host_only=True)
     assert ok.info()[:2] == (1, 60000)
+
+
+def test_rust_shim_matches_header(pb2, tmp_path):
+    """rust_shim/src/lib.rs cannot be compiled here (no rustc); hold it to the header mechanically: its extern block declares
+    exactly the header's functions, and every abi_size!(T, n) equals the C sizeof (gcc on include/pbrt_b200.h) and the size of
+    the ctypes structure the Python binding passes."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(pb2.LIB_PATH))
+    src = open(os.path.join(root, "rust_shim", "src", "lib.rs")).read()
+    block = re.search(r'extern "C" \{(.*?)\n\}', src, flags=re.S).group(1)
+    declared = sorted(set(re.findall(r"pub fn (pb2_[a-z0-9_]+)\s*\(", block)))
+    assert declared == pb2.header_symbols()
+    sizes = dict((t, int(n)) for t, n in re.findall(r"abi_size!\((pb2_[a-z_]+), (\d+)\);", src))
+    assert set(sizes) == {"pb2_ray", "pb2_hit", "pb2_material", "pb2_light", "pb2_camera", "pb2_film_desc", "pb2_path_desc"}
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include "pbrt_b200.h"\nint main(void){' +
+                    "".join(f'printf("{t} %zu\\n", sizeof({t}));' for t in sorted(sizes)) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(prog), "-o", str(exe)])
+    c_sizes = dict((l.split()[0], int(l.split()[1])) for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert c_sizes == sizes
+    py = {"pb2_material": pb2.Material, "pb2_light": pb2.Light, "pb2_camera": pb2.CameraDesc, "pb2_film_desc": pb2.FilmDesc,
+          "pb2_path_desc": pb2.PathDesc}
+    for t, cls in py.items():
+        assert C.sizeof(cls) == sizes[t], t
+    assert sizes["pb2_ray"] == 32 and pb2.HIT_DTYPE.itemsize == sizes["pb2_hit"]      # rays travel as float32[n, 8]
+    # the two trait impls the shim exists for are code, not comments
+    assert re.search(r"^impl Primitive for B200Accel", src, flags=re.M) and re.search(r"^impl Integrator for B200PathIntegrator", src, flags=re.M)
