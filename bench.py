@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--grid-n", type=int, default=2237, help="quads per side of the C3 grid (2237 -> 10,008,338 triangles)")
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-path", action="store_true", help="tuning / profiling runs: C3 traversal only (the default line carries C2, C4 and C5 too)")
     ap.add_argument("--cpu-stride", type=int, default=1, help="cpu sample = every k-th ray of each ray set")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat the sample until this much traversal time")
     return ap.parse_args()
@@ -615,10 +616,13 @@ def main():
 
     # ---- path tracing (second half of the BASELINE metric) ----
     dist_mod = dist if world > 1 else None
-    path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
-    path_c4, path_c4_keep = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
-    path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world)
-    path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0] + path_c4["kernel_launches_per_step"] * 2)
+    path_c2 = path_c4 = path_c5 = None
+    path_launches = 0
+    if not args.no_path:
+        path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
+        path_c4, path_c4_keep = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
+        path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world)
+        path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0] + path_c4["kernel_launches_per_step"] * 2)
 
     # ---- BVH build: SplitMethod::HLBVH built on the GPU next to the host SAH build, and what the C3
     # ray sets cost on that tree (same rays, same hits: tests/ compare ids and t bits)
@@ -719,6 +723,8 @@ def main():
         cpu_baseline = {"value": cpu_reps * n_sample / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu_model": model,
                         "sample": f"every {k}-th ray of each of the 3 ray sets ({n_sample} rays) x {cpu_reps} passes = {cpu_s:.1f} s, "
                                   "traversal time only"}
+    if rank == 0 and not args.no_cpu_baseline and not args.no_path:
+        orc = ge.load_oracle()
         # path tracing: oracle on sample indices [0,2) of C2, and the GPU film of the same range must equal it bit for bit
         accel2, camera2, integ2, film2, sc2 = path_keep
         path_cpu, ref_xyzw = bench_path_cpu(orc, scenes, sc2, None)

@@ -70,6 +70,15 @@ def _bind_path(L):
     vp = C.c_void_p
     L.orc_scene_create.restype = vp
     L.orc_scene_create.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_int]
+    L.orc_scene_create2.restype = vp
+    L.orc_scene_create2.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_int, vp, C.c_uint32]
+    L.orc_sphere_sample2.argtypes = [vp, C.c_uint32, vp, C.c_float, C.c_float, vp]
+    L.orc_sphere_pdf2.restype = C.c_float
+    L.orc_sphere_pdf2.argtypes = [vp, C.c_uint32, vp, vp]
+    L.orc_acos.restype = C.c_float
+    L.orc_acos.argtypes = [C.c_float]
+    L.orc_atan2.restype = C.c_float
+    L.orc_atan2.argtypes = [C.c_float, C.c_float]
     L.orc_scene_free.argtypes = [vp]
     L.orc_scene_bvh.restype = vp
     L.orc_scene_bvh.argtypes = [vp]

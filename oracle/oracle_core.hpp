@@ -227,6 +227,8 @@ inline bool triangle_frame(V3 p0, V3 p1, V3 p2, V3* dpdu, V3* dpdv, const Float*
     return true;
 }
 
+#include "oracle_sphere.hpp"
+
 // ---------------------------------------------------------------- src/accelerators/bvh.rs
 struct LinearBVHNode {            // bvh.rs:129-135 (usize fields narrowed; D19)
     Bounds3 bounds;
@@ -268,6 +270,10 @@ public:
     std::vector<uint32_t> ordered_prims;    // BVH leaf order -> mesh triangle id
     std::vector<LinearBVHNode> nodes;
     std::vector<Float> uvs;                 // TriangleMesh::uv (triangle.rs:21): 2 per vertex, empty = default UVs
+    std::vector<Sphere> spheres;            // analytic spheres (shapes/sphere.rs): primitive ids n_tris() .. n_tris() + spheres.size() - 1; set before build()
+    size_t n_tris() const { return indices.size() / 3; }
+    bool is_sphere(uint32_t prim) const { return prim >= n_tris(); }
+    const Sphere& sphere(uint32_t prim) const { return spheres[prim - n_tris()]; }
     int max_prims_in_node = 4;
     int max_depth_seen = 0;
 
@@ -297,10 +303,12 @@ public:
         max_prims_in_node = std::min(max_prims, 255);        // :222
         nodes.clear();
         ordered_prims.clear();
+        const size_t n_mesh = nt;
+        nt += spheres.size();                                 // the primitive list: the mesh's triangles, then the spheres
         if (nt == 0) return;
         std::vector<BVHPrimitiveInfo> info(nt);
         for (size_t i = 0; i < nt; ++i) {
-            Bounds3 b = tri_bound((uint32_t)i);
+            Bounds3 b = i < n_mesh ? tri_bound((uint32_t)i) : spheres[i - n_mesh].world_bound();
             info[i] = {(uint32_t)i, b, b.mn * 0.5f + b.mx * 0.5f};       // :38
         }
         build_nodes_.clear();
@@ -325,7 +333,8 @@ public:
     Bounds3 world_bound() const { return nodes.empty() ? Bounds3{} : nodes[0].bounds; }   // :819-826
 
     // bvh.rs:828-879 + primitive.rs:65-78 + triangle.rs:182-215
-    bool intersect(Ray& ray, Hit* out, Float* b0_out, TraversalCounters* c) const {
+    // ssi_out: the interaction of the accepted hit when that hit is a sphere (Sphere::intersect builds it at accept time)
+    bool intersect(Ray& ray, Hit* out, Float* b0_out, TraversalCounters* c, SphereSI* ssi_out = nullptr) const {
         out->prim_id = 0xFFFFFFFFu; out->t = ray.t_max; out->b1 = 0; out->b2 = 0;
         if (b0_out) *b0_out = 0;
         if (nodes.empty()) return false;
@@ -342,9 +351,20 @@ public:
                 if (node.n_primitives > 0) {
                     for (uint32_t i = 0; i < node.n_primitives; ++i) {
                         uint32_t prim = ordered_prims[node.primitive_or_second_child_offset + i];
+                        if (c) c->tris_tested++;
+                        if (is_sphere(prim)) {                // GeometricPrimitive(Sphere)::intersect (primitive.rs:65-78, sphere.rs:38-93)
+                            Float t;
+                            SphereSI ssi;
+                            if (!sphere(prim).intersect(ray, &t, &ssi)) continue;
+                            ray.t_max = t;
+                            out->prim_id = prim; out->t = t; out->b1 = ssi.u; out->b2 = ssi.v;
+                            if (b0_out) *b0_out = 0.0f;
+                            if (ssi_out) *ssi_out = ssi;
+                            hit = true;
+                            continue;
+                        }
                         V3 p0, p1, p2;
                         tri(prim, &p0, &p1, &p2);
-                        if (c) c->tris_tested++;
                         TriHit h = triangle_intersect_test(p0, p1, p2, ray);
                         if (!h.hit) continue;
                         V3 du, dv;
@@ -387,9 +407,13 @@ public:
                 if (node.n_primitives > 0) {
                     for (uint32_t i = 0; i < node.n_primitives; ++i) {
                         uint32_t prim = ordered_prims[node.primitive_or_second_child_offset + i];
+                        if (c) c->tris_tested++;
+                        if (is_sphere(prim)) {
+                            if (sphere(prim).intersect_p(ray)) return true;
+                            continue;
+                        }
                         V3 p0, p1, p2;
                         tri(prim, &p0, &p1, &p2);
-                        if (c) c->tris_tested++;
                         if (triangle_intersect_test(p0, p1, p2, ray).hit) return true;
                     }
                     if (to_visit == 0) break;
@@ -414,6 +438,15 @@ public:
         out->prim_id = 0xFFFFFFFFu; out->t = ray.t_max; out->b1 = 0; out->b2 = 0;
         bool hit = false;
         for (uint32_t prim : ordered_prims) {
+            if (is_sphere(prim)) {
+                Float t;
+                SphereSI ssi;
+                if (!sphere(prim).intersect(ray, &t, &ssi)) continue;
+                ray.t_max = t;
+                out->prim_id = prim; out->t = t; out->b1 = ssi.u; out->b2 = ssi.v;
+                hit = true;
+                continue;
+            }
             V3 p0, p1, p2;
             tri(prim, &p0, &p1, &p2);
             TriHit h = triangle_intersect_test(p0, p1, p2, ray);

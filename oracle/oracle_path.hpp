@@ -558,6 +558,7 @@ struct LightRt {
     V3 n0, n1, n2;      // its vertex normals (TriangleMesh::n), when the mesh has them
     Float uv[6];        // its UVs (TriangleMesh::uv)
     Float area;
+    const Sphere* sphere = nullptr;               // area light on an analytic sphere (DiffuseAreaLight over shapes/sphere.rs)
     Float cos_total_width, cos_falloff_start;     // spot.rs:38-39
     V3 w_light;                                   // distant.rs:31
     Float world_radius;                           // distant.rs:73-77 pre_process
@@ -583,6 +584,15 @@ inline RGB light_sample_li(const LightRt& light, V3 p, Float ul0, Float ul1, Flo
         const V3 wi = normalize(pl - p);
         if (light.d.type == LIGHT_SPOT) return light.l() * light.falloff(-wi) / length_squared(pl - p);
         return light.l() / length_squared(pl - p);
+    }
+    if (light.sphere) {                                                                        // diffuse.rs:60-81 + sphere.rs:127-193, bare reference point
+        V3 ps, pe, ns;
+        Float pdf;
+        light.sphere->sample2(p, V3{0, 0, 0}, V3{0, 0, 0}, ul0, ul1, &ps, &pe, &ns, &pdf);
+        *pdf_out = pdf;
+        if (pdf == 0.0f || length_squared(ps - p) == 0.0f) { *pdf_out = 0.0f; return rgb(0); }
+        const V3 wi = normalize(ps - p);
+        return (light.d.two_sided || dot(ns, -wi) > 0.0f) ? light.l() : rgb(0);
     }
     Float su0 = std::sqrt(ul0);
     Float b0 = 1.0f - su0, b1 = ul1 * su0;
@@ -627,7 +637,7 @@ public:
         if (tangents) { vs.resize(nv); for (size_t i = 0; i < nv; ++i) vs[i] = {tangents[3 * i], tangents[3 * i + 1], tangents[3 * i + 2]}; }
         if (uv) bvh.uvs.assign(uv, uv + 2 * nv);
         for (LightRt& l : lights) {
-            if (l.d.type != LIGHT_AREA) continue;
+            if (l.d.type != LIGHT_AREA || l.sphere) continue;
             const uint32_t* ix = &bvh.indices[3 * (size_t)l.d.prim_id];
             l.has_n = !vn.empty();
             if (l.has_n) { l.n0 = vn[ix[0]]; l.n1 = vn[ix[1]]; l.n2 = vn[ix[2]]; }
@@ -635,10 +645,23 @@ public:
         }
     }
 
+    // spheres: analytic Sphere primitives appended to the primitive list (ids nt .. nt + n_spheres - 1); an area light whose prim_id
+    // is such an id is a DiffuseAreaLight over that sphere
     void init(const Float* verts, uint64_t nv, const uint32_t* idx, uint64_t nt, const uint32_t* tri_mat, const MaterialDesc* mats,
-              uint32_t n_mats, const LightDesc* lts, uint32_t n_lights, int max_prims) {
+              uint32_t n_mats, const LightDesc* lts, uint32_t n_lights, int max_prims, const SphereDesc* sph = nullptr, uint32_t n_spheres = 0) {
+        bvh.spheres.resize(n_spheres);
+        for (uint32_t i = 0; i < n_spheres; ++i) {
+            M4 o2w;
+            std::memcpy(o2w.m, sph[i].object_to_world, sizeof(o2w.m));
+            const M4 inv = m4_inverse(o2w);                                                    // Transform::new (transform.rs:198-206)
+            Mat4 w2o;
+            std::memcpy(w2o.m, inv.m, sizeof(w2o.m));
+            bvh.spheres[i].init(sph[i], w2o);
+        }
         bvh.build(verts, nv, idx, nt, max_prims);
         tri_material.assign(tri_mat, tri_mat + nt);
+        for (uint32_t i = 0; i < n_spheres; ++i) tri_material.push_back(sph[i].material);
+        const uint64_t n_prims = nt + n_spheres;
         materials.resize(n_mats);
         for (uint32_t i = 0; i < n_mats; ++i) {
             materials[i].d = mats[i];
@@ -649,7 +672,7 @@ public:
                 materials[i].on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
             }
         }
-        tri_light.assign(nt, -1);
+        tri_light.assign(n_prims, -1);
         lights.resize(n_lights);
         for (uint32_t i = 0; i < n_lights; ++i) {
             lights[i].d = lts[i];
@@ -668,7 +691,12 @@ public:
                 const bool inside = c.x >= wb.mn.x && c.x <= wb.mx.x && c.y >= wb.mn.y && c.y <= wb.mx.y && c.z >= wb.mn.z && c.z <= wb.mx.z;
                 lights[i].world_radius = inside ? length(c - wb.mx) : 0.0f;
             }
-            if (lts[i].type == LIGHT_AREA) {
+            if (lts[i].type == LIGHT_AREA && lts[i].prim_id >= nt) {                            // sphere.rs:100-102
+                lights[i].sphere = &bvh.spheres[lts[i].prim_id - nt];
+                lights[i].p0 = lights[i].p1 = lights[i].p2 = V3{0, 0, 0};
+                lights[i].area = lights[i].sphere->area();
+                tri_light[lts[i].prim_id] = (int32_t)i;
+            } else if (lts[i].type == LIGHT_AREA) {
                 bvh.tri(lts[i].prim_id, &lights[i].p0, &lights[i].p1, &lights[i].p2);
                 lights[i].area = length(cross(lights[i].p1 - lights[i].p0, lights[i].p2 - lights[i].p0)) * 0.5f;   // triangle.rs:323-328
                 tri_light[lts[i].prim_id] = (int32_t)i;
@@ -772,7 +800,14 @@ public:
         Float b0;
         PathCounters* pc = tl_path_counters;
         if (pc) pc->rays[tl_ray_kind]++;
-        if (!bvh.intersect(ray, &h, &b0, pc ? &pc->trav[tl_ray_kind] : nullptr)) return false;
+        SphereSI ssi;
+        if (!bvh.intersect(ray, &h, &b0, pc ? &pc->trav[tl_ray_kind] : nullptr, &ssi)) return false;
+        if (bvh.is_sphere(h.prim_id)) {                                                         // sphere.rs:38-93
+            si->p = ssi.p; si->error = ssi.error; si->n = ssi.n; si->wo = ssi.wo;
+            si->dpdu = ssi.dpdu; si->sn = ssi.sn; si->sdpdu = ssi.sdpdu;
+            si->prim = h.prim_id;
+            return true;
+        }
         V3 p0, p1, p2;
         bvh.tri(h.prim_id, &p0, &p1, &p2);
         Interaction it = triangle_interaction(p0, p1, p2, b0, h.b1, h.b2);
@@ -1199,6 +1234,19 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
         V3 origin = offset_ray_origin(it.p, it.error, it.n, pl - it.p);
         V3 target = offset_ray_origin(pl, V3{0, 0, 0}, V3{0, 0, 0}, origin - pl);
         shadow = Ray{origin, 1.0f - kShadowEpsilon, target - origin, 0.0f};
+    } else if (light.sphere) {                                                                 // diffuse.rs:60-81 + sphere.rs:127-193
+        V3 ps, pe, ns;
+        Float pdf;
+        light.sphere->sample2(it.p, it.error, it.n, ul0, ul1, &ps, &pe, &ns, &pdf);
+        light_pdf = pdf;
+        if (pdf == 0.0f || length_squared(ps - it.p) == 0.0f) { light_pdf = 0.0f; li = rgb(0); }
+        else {
+            wi = normalize(ps - it.p);
+            li = (light.d.two_sided || dot(ns, -wi) > 0.0f) ? light.l() : rgb(0);
+            V3 origin = offset_ray_origin(it.p, it.error, it.n, ps - it.p);
+            V3 target = offset_ray_origin(ps, pe, ns, origin - ps);
+            shadow = Ray{origin, 1.0f - kShadowEpsilon, target - origin, 0.0f};
+        }
     } else {                                                                                   // diffuse.rs:60-81 + shape.rs:38-53 + triangle.rs:330-348
         Float su0 = std::sqrt(ul0);
         Float b0 = 1.0f - su0, b1 = ul1 * su0;                                                 // sampling.rs:275-278
@@ -1246,7 +1294,11 @@ inline RGB estimate_direct(const Scene& scene, const SurfaceInteraction& it, con
         if (!is_black(f) && scattering_pdf > 0.0f) {
             Float weight = 1.0f;
             Interaction base{it.p, it.error, it.n};
-            if (!sampled_specular) {
+            if (!sampled_specular && light.sphere) {                                           // Light::pdf_li -> Sphere::pdf2 (sphere.rs:195-207)
+                light_pdf = light.sphere->pdf2(it.p, it.error, it.n, wi);
+                if (light_pdf == 0.0f) return ld;
+                weight = power_heuristic(scattering_pdf, light_pdf);
+            } else if (!sampled_specular) {
                 // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): intersect the light's own triangle
                 Ray r = spawn_ray(base, wi);
                 TriHit th = triangle_intersect_test(light.p0, light.p1, light.p2, r);

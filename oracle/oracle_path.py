@@ -38,6 +38,29 @@ class PathDesc(C.Structure):
                 ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
 
 
+class Sphere(C.Structure):
+    _fields_ = [("object_to_world", C.c_float * 16), ("radius", C.c_float), ("z_min", C.c_float), ("z_max", C.c_float),
+                ("phi_max", C.c_float), ("reverse_orientation", C.c_int32), ("material", C.c_uint32)]
+
+
+def sphere(d):
+    """dict(o2w=4x4 row-major affine matrix | center=(x, y, z), radius, z_min, z_max, phi_max (degrees), reverse_orientation, material)"""
+    s = Sphere()
+    if "o2w" in d:
+        m = np.asarray(d["o2w"], dtype=np.float32).reshape(4, 4)
+    else:
+        m = np.eye(4, dtype=np.float32)
+        m[:3, 3] = d.get("center", (0, 0, 0))
+    s.object_to_world[:] = [float(v) for v in m.ravel()]
+    s.radius = d["radius"]
+    s.z_min = d.get("z_min", -d["radius"])
+    s.z_max = d.get("z_max", d["radius"])
+    s.phi_max = d.get("phi_max", 360.0)
+    s.reverse_orientation = int(d.get("reverse_orientation", False))
+    s.material = d.get("material", 0)
+    return s
+
+
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3, "sobol": 4}
 _MAT = {"matte": 0, "plastic": 1, "glass": 2, "mirror": 3, "metal": 4, "substrate": 5}
 _STRAT = {"uniform": 0, "power": 1, "spatial": 2}
@@ -187,9 +210,12 @@ class Scene:
         tm = np.ascontiguousarray(sc["tri_material"], dtype=np.uint32)
         mats = (Material * len(sc["materials"]))(*[material(m) for m in sc["materials"]])
         lts = (Light * max(1, len(sc["lights"])))(*[light(l) for l in sc["lights"]])
-        self.h = L.orc_scene_create(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), _p(tm),
-                                    C.cast(mats, C.c_void_p), len(sc["materials"]), C.cast(lts, C.c_void_p),
-                                    len(sc["lights"]), max_prims_in_node)
+        sph = sc.get("spheres") or []
+        sphs = (Sphere * max(1, len(sph)))(*[sphere(d) for d in sph])
+        self.n_spheres = len(sph)
+        self.h = L.orc_scene_create2(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), _p(tm),
+                                     C.cast(mats, C.c_void_p), len(sc["materials"]), C.cast(lts, C.c_void_p),
+                                     len(sc["lights"]), max_prims_in_node, C.cast(sphs, C.c_void_p), len(sph))
         # TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26)
         self._sg = [None if sc.get(k) is None else np.ascontiguousarray(sc[k], dtype=np.float32) for k in ("normals", "tangents", "uvs")]
         if any(a is not None for a in self._sg):

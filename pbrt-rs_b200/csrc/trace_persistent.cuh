@@ -67,7 +67,11 @@ PB2_D void swap_if(bool c, uint32_t& ra, float& ta, uint32_t& rb, float& tb) {
 
 // Flag word of a ray: bits 0-2 direction signs (bvh.rs:832-836), bits 3-4 shear axis kz (triangle.rs:84-92),
 // bit 5 slab fast path allowed, bit 6 a closest-hit candidate has been accepted.
-constexpr uint32_t kFlagPlain = 32u, kFlagFound = 64u;
+// bit 7: the walk is over and its result has not been handed to the sink yet (closest hit: finish(); any hit: occluded(),
+// with bit 6 = "occluded").  The hand-off waits for the warp's next refill, where the ~20 lanes that ended since the last one
+// make their sink calls together; made at the point where a single walk ends it ran with 2.9 of 32 lanes enabled and took
+// 5 % of the warp instructions and 12 % of the stall samples of k_extend (profiles/r02_tuning.md).
+constexpr uint32_t kFlagPlain = 32u, kFlagFound = 64u, kFlagFinish = 128u;
 
 // The part of RayCtx a step needs, rebuilt from the carried registers (make_ray_ctx computed them once per ray).
 PB2_D RayCtx ctx_of(vec3 o, vec3 inv, vec3 sh, uint32_t flags) {
@@ -103,6 +107,16 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
     vec3 o = mk(0.f, 0.f, 0.f), inv = mk(1.f, 1.f, 1.f), sh = mk(0.f, 0.f, 1.f);
     float t_max = 0.0f;
     bool exhausted = false;                  // warp-uniform: the ray counter ran past n
+#ifndef PB2_DEFER_FINISH
+#define PB2_DEFER_FINISH 1      /* 0: hand the result over where the walk ends (the round-1 kernel; tuning builds only) */
+#endif
+    auto hand_off = [&]() {
+        if (flags & kFlagFinish) {
+            flags &= ~kFlagFinish;
+            if (ANY) sink.occluded(ray_idx, (flags & kFlagFound) != 0u);
+            else sink.finish(ray_idx, (flags & kFlagFound) != 0u, t_max);
+        }
+    };
 
     for (;;) {
         // ---- refill idle lanes ----
@@ -116,6 +130,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                 base = __shfl_sync(kFullMask, base, leader);
                 exhausted = base + (unsigned)__popc(idle) >= n;
                 if (cur == kDone) {
+                    hand_off();
                     const unsigned long long mine = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                     if (mine < n) {
                         ray_idx = (uint32_t)mine;
@@ -160,7 +175,10 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
             const bool at_node = !(cur & kLeafFlag);
             const unsigned node_mask = __ballot_sync(kFullMask, at_node);
             const unsigned work_mask = __ballot_sync(kFullMask, cur != kDone);
-            if (work_mask == 0u) { if (exhausted) return; break; }
+            if (work_mask == 0u) {
+                if (exhausted) { hand_off(); return; }
+                break;
+            }
             if (!exhausted && __popc(work_mask) < tune.refill_below) break;
             const int n_node = __popc(node_mask), n_leaf = __popc(work_mask & ~node_mask);
             bool need_pop = false;
@@ -238,7 +256,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                 }
                 if (ANY && occluded) {
                     cur = kDone;
-                    sink.occluded(ray_idx, true);
+                    flags |= kFlagFinish | kFlagFound;
+                    if (!PB2_DEFER_FINISH) hand_off();
                 } else {
                     need_pop = true;
                 }
@@ -252,8 +271,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     if (ANY || __uint_as_float(e.y) < t_max) { cur = e.x; break; }   // (any hit: t_max is the ray's own, checked at push time)
                 }
                 if (cur == kDone) {
-                    if (ANY) sink.occluded(ray_idx, false);
-                    else sink.finish(ray_idx, (flags & kFlagFound) != 0u, t_max);
+                    flags |= kFlagFinish;
+                    if (!PB2_DEFER_FINISH) hand_off();
                 }
             }
         }

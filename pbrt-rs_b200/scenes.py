@@ -300,3 +300,41 @@ def furnace_box(L=0.5, kd=0.5):
     lights = [dict(type="area", prim=k, L=(L, L, L), two_sided=True) for k in range(len(idx))]
     return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=[dict(type="matte", kd=(kd, kd, kd))],
                 lights=lights)
+
+
+def _rot_scale(center, axis_angle_deg=(0.0, 0.0, 1.0, 0.0), scale=(1.0, 1.0, 1.0)):
+    """Row-major affine object_to_world = translate(center) * rotate(axis, angle) * scale(s) as float32."""
+    ax = np.asarray(axis_angle_deg[:3], dtype=np.float64)
+    ang = np.radians(axis_angle_deg[3])
+    m = np.eye(4)
+    if np.linalg.norm(ax) > 0 and ang != 0.0:
+        ax = ax / np.linalg.norm(ax)
+        k = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        m[:3, :3] = np.eye(3) + np.sin(ang) * k + (1 - np.cos(ang)) * (k @ k)
+    m[:3, :3] = m[:3, :3] @ np.diag(scale)
+    m[:3, 3] = center
+    return m.astype(np.float32)
+
+
+def scene_spheres(sphere_light=True, partial=True):
+    """Cornell room (no blocks) with ANALYTIC spheres (src/shapes/sphere.rs) instead of tessellated ones: matte, plastic and glass
+    balls, an ellipsoid (rotated, non-uniformly scaled sphere), a partial sphere (z_min / z_max / phi_max, reversed orientation)
+    and — besides the ceiling quad light and a point light — a spherical DiffuseAreaLight.  Sphere primitive ids follow the
+    triangles': len(idx) + k."""
+    room = cornell_box(blocks=False)
+    nt = len(room["idx"])
+    materials = room["materials"] + [dict(type="matte", kd=(0.5, 0.5, 0.8)),
+                                     dict(type="plastic", kd=(0.25, 0.25, 0.25), ks=(0.25, 0.25, 0.25), roughness=0.1, remap=True),
+                                     dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5)]
+    spheres = [dict(center=(140.0, 90.0, 300.0), radius=90.0, material=3),
+               dict(center=(278.0, 130.0, 220.0), radius=90.0, material=4),
+               dict(center=(430.0, 90.0, 280.0), radius=90.0, material=5),
+               dict(o2w=_rot_scale((300.0, 330.0, 420.0), (0.3, 1.0, 0.2, 35.0), (1.6, 0.7, 1.0)), radius=60.0, material=1)]
+    if partial:
+        spheres.append(dict(o2w=_rot_scale((120.0, 300.0, 380.0), (1.0, 0.0, 0.0, -70.0)), radius=70.0, z_min=-40.0, z_max=55.0, phi_max=250.0,
+                            reverse_orientation=True, material=2))
+    lights = room["lights"] + [dict(type="point", p=(278.0, 400.0, 100.0), I=(20000.0, 20000.0, 20000.0))]
+    if sphere_light:
+        spheres.append(dict(center=(460.0, 420.0, 150.0), radius=25.0, material=0))
+        lights.append(dict(type="area", prim=nt + len(spheres) - 1, L=(60.0, 55.0, 40.0), two_sided=False))
+    return dict(verts=room["verts"], idx=room["idx"], tri_material=room["tri_material"], materials=materials, lights=lights, spheres=spheres)

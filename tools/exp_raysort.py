@@ -60,8 +60,22 @@ def spread(v):
 
 morton = (spread(q[:, 2]) << 2) | (spread(q[:, 1]) << 1) | spread(q[:, 0])
 dead = (~live).long() << 40
+pix = torch.arange(n, device=dev)
+px, py = pix % 1024, pix // 1024
+
+
+def tile_key(tw, th):
+    """Rays of one tw x th pixel tile adjacent (tiles row-major, pixels row-major inside a tile): a warp then covers a compact
+    block of the image instead of 32 pixels of one row."""
+    return ((py // th) * (1024 // tw) + (px // tw)) * (tw * th) + (py % th) * tw + (px % tw)
+
+
 orders = {
     "pixel order (as spawned)": None,
+    "8x4 pixel tiles": tile_key(8, 4) + dead,
+    "8x8 pixel tiles": tile_key(8, 8) + dead,
+    "16x16 tiles, octant inside": ((tile_key(16, 16) // 256) << 11) + (octant << 8) + (tile_key(16, 16) % 256) + dead,
+    "pixel morton (z-order)": (spread(py) << 1 | spread(px)) + dead,
     "octant (stable)": octant + dead,
     "octant, morton30(origin)": (octant << 30) + morton + dead,
     "morton30(origin)": morton + dead,
@@ -93,3 +107,16 @@ for name, key in orders.items():
         ref = hits
     same = bool(torch.equal(ref, hits))
     print(f"{name:32s} k_closest_hit {ms:.4f} ms = {n / ms / 1e3:7.1f} Mrays/s   (torch sort + gather {sort_ms:.3f} ms)   results equal: {same}", flush=True)
+
+# the primary (coherent) set under the same pixel-tile orders: does a compact warp footprint help camera rays?
+prim_rays = d_rays.view(torch.float32).view(n, 8)
+for name, key in (("row-major (as generated)", None), ("8x4 pixel tiles", tile_key(8, 4)), ("8x8 pixel tiles", tile_key(8, 8)),
+                  ("pixel morton (z-order)", spread(py) << 1 | spread(px))):
+    if key is None:
+        src = d_rays
+    else:
+        perm = torch.sort(key, stable=True).indices
+        d_sorted.view(torch.float32).view(n, 8).copy_(prim_rays[perm])
+        src = d_sorted
+    ms = timed(lambda: accel.intersect_device(src.data_ptr(), n, d_bh.data_ptr(), None, st))
+    print(f"primary set, {name:28s} k_closest_hit {ms:.4f} ms = {n / ms / 1e3:7.1f} Mrays/s", flush=True)
