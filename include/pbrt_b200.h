@@ -79,6 +79,18 @@ typedef struct pb2_light {
     float falloff_start;/* spot: half-angle where the falloff starts, degrees (spot.rs:39) */
 } pb2_light;
 
+/* src/shapes/sphere.rs:229-248 Sphere::new(object_to_world, world_to_object, reverse_orientation, radius, z_min, z_max, phi_max)
+ * behind a GeometricPrimitive: an analytic sphere (EFloat quadratic, src/core/efloat.rs), optionally cut by z_min / z_max and
+ * phi_max.  object_to_world is a row-major 4x4 AFFINE matrix (last row 0 0 0 1; rotation, non-uniform scale and translation are
+ * fine, a projective row is PB2_ERR_INVALID); world_to_object is its inverse, computed by the library the way Transform::new
+ * does (transform.rs:46-113).  phi_max in degrees.  88 bytes. */
+typedef struct pb2_sphere {
+    float object_to_world[16];
+    float radius, z_min, z_max, phi_max;
+    int32_t reverse_orientation;
+    uint32_t material;          /* index into the scene's materials (ignored for pure ray casting) */
+} pb2_sphere;
+
 /* src/cameras/perspective.rs:34-82 PerspectiveCamera + Transform::look_at. */
 typedef struct pb2_camera {
     float pos[3];
@@ -171,6 +183,12 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
  * (src/shapes/triangle.rs:17-26; 3 / 3 / 2 floats per vertex, world space, NULL = absent), as Triangle::intersect (:251-311),
  * Triangle::get_uvs (:60-72) and Triangle::sample (:338-341) use them.  Call before pb2_scene_build_bvh. */
 int pb2_scene_set_shading_geometry(pb2_scene* scene, const float* normals, const float* tangents, const float* uvs);
+/* Appends n analytic spheres to the scene's primitive list, after the triangles: sphere k of the scene has primitive id
+ * n_tris + k (the id pb2_hit.prim_id reports and pb2_light.prim_id names for a spherical DiffuseAreaLight).  Call before
+ * pb2_scene_build_bvh; SplitMethod::HLBVH (the device build) takes triangles only and refuses a scene with spheres.  A closest
+ * hit on a sphere reports b1 = u = phi / phi_max and b2 = v = (theta - theta_min) / (theta_max - theta_min) (sphere.rs:49-52);
+ * pb2_intersect's optional b0 is 0 there. */
+int pb2_scene_add_spheres(pb2_scene* scene, const pb2_sphere* spheres, uint32_t n);
 int pb2_scene_destroy(pb2_scene* scene);
 /* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
  * node layout + 48-byte triangles, upload to the current device.  split_method (bvh.rs:199-204): 0 = SplitMethod::SAH,

@@ -227,7 +227,9 @@ class Scene:
             self.h = None
 
     def bvh(self):
-        return O.BVHAccel(None, None, _handle=O.lib().orc_scene_bvh(self.h))
+        b = O.BVHAccel(None, None, _handle=O.lib().orc_scene_bvh(self.h))
+        b._scene = self          # the tree lives inside the scene: keep it alive as long as the view
+        return b
 
     def render(self, cam, film, path, mode=1, threads=0, out=None):
         """Returns (xyzw [H,W,4] accumulators, seconds)."""

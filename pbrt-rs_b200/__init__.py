@@ -42,6 +42,30 @@ class Light(C.Structure):
                 ("two_sided", C.c_int32), ("axis", C.c_float * 3), ("total_width", C.c_float), ("falloff_start", C.c_float)]
 
 
+class Sphere(C.Structure):
+    """pb2_sphere: Sphere::new's arguments (src/shapes/sphere.rs:229-248) + the material of its GeometricPrimitive."""
+    _fields_ = [("object_to_world", C.c_float * 16), ("radius", C.c_float), ("z_min", C.c_float), ("z_max", C.c_float),
+                ("phi_max", C.c_float), ("reverse_orientation", C.c_int32), ("material", C.c_uint32)]
+
+
+def sphere_from_dict(d):
+    """dict(o2w=4x4 row-major affine matrix | center=(x, y, z), radius, z_min, z_max, phi_max (degrees), reverse_orientation, material)"""
+    s = Sphere()
+    if "o2w" in d:
+        m = np.asarray(d["o2w"], dtype=np.float32).reshape(4, 4)
+    else:
+        m = np.eye(4, dtype=np.float32)
+        m[:3, 3] = d.get("center", (0, 0, 0))
+    s.object_to_world[:] = [float(v) for v in m.ravel()]
+    s.radius = d["radius"]
+    s.z_min = d.get("z_min", -d["radius"])
+    s.z_max = d.get("z_max", d["radius"])
+    s.phi_max = d.get("phi_max", 360.0)
+    s.reverse_orientation = int(d.get("reverse_orientation", False))
+    s.material = d.get("material", 0)
+    return s
+
+
 class CameraDesc(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
                 ("res_x", C.c_int32), ("res_y", C.c_int32), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
@@ -184,7 +208,7 @@ def lib():
         "pb2_memcpy_h2d": [vp, vp, u64], "pb2_memcpy_d2h": [vp, vp, u64], "pb2_device_synchronize": [],
         "pb2_set_trace_tuning": [i32, i32, i32, i32],
         "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
-        "pb2_scene_set_shading_geometry": [vp, vp, vp, vp],
+        "pb2_scene_set_shading_geometry": [vp, vp, vp, vp], "pb2_scene_add_spheres": [vp, vp, u32],
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
         "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
@@ -277,7 +301,7 @@ class Scene:
     """Triangle list + materials + lights handed to BVHAccel::new (pb2_scene_create); normals / tangents / uvs are
     TriangleMesh's optional per-vertex arrays (src/shapes/triangle.rs:17-26)."""
 
-    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None, normals=None, tangents=None, uvs=None):
+    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None, normals=None, tangents=None, uvs=None, spheres=None):
         verts = _f32(verts).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         self.n_tris = len(idx)
@@ -293,6 +317,10 @@ class Scene:
         if normals is not None or tangents is not None or uvs is not None:
             sg = [None if a is None else _f32(a).reshape(len(verts), k) for a, k in ((normals, 3), (tangents, 3), (uvs, 2))]
             check(lib().pb2_scene_set_shading_geometry(self.h, *[_p(a) for a in sg]))
+        self.n_spheres = len(spheres) if spheres else 0
+        if spheres:                       # analytic spheres: primitive ids n_tris .. n_tris + n_spheres - 1 (pb2_scene_add_spheres)
+            arr = (Sphere * len(spheres))(*spheres)
+            check(lib().pb2_scene_add_spheres(self.h, C.cast(arr, C.c_void_p), len(spheres)))
 
     def destroy(self):
         if self.h:
@@ -444,7 +472,8 @@ def light_from_dict(d):
 def scene_from_dict(sc):
     """Scene from the plain-dict description the generators in scenes.py return."""
     return Scene(sc["verts"], sc["idx"], sc["tri_material"], [material_from_dict(m) for m in sc["materials"]],
-                 [light_from_dict(l) for l in sc["lights"]], normals=sc.get("normals"), tangents=sc.get("tangents"), uvs=sc.get("uvs"))
+                 [light_from_dict(l) for l in sc["lights"]], normals=sc.get("normals"), tangents=sc.get("tangents"), uvs=sc.get("uvs"),
+                 spheres=[sphere_from_dict(d) for d in sc.get("spheres") or []])
 
 
 class Film:

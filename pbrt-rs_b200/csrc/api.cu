@@ -54,6 +54,8 @@ void pb2_scene::free_device() {
     if (d_light_cdf) cudaFree(d_light_cdf);
     if (d_spatial) cudaFree(d_spatial);
     d_spatial = nullptr;
+    if (d_spheres) cudaFree(d_spheres);
+    d_spheres = nullptr;
     path_chain.destroy();
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
@@ -181,8 +183,7 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
             if (tri_material[i] >= n_mats) return set_error(PB2_ERR_INVALID, "triangle %llu references material %u >= %u", (unsigned long long)i, tri_material[i], n_mats);
     }
     for (uint32_t i = 0; i < n_lights; ++i) {
-        if (lights[i].type == PB2_LIGHT_AREA && lights[i].prim_id >= n_tris)
-            return set_error(PB2_ERR_INVALID, "area light %u references triangle %u >= %llu", i, lights[i].prim_id, (unsigned long long)n_tris);
+        // (an area light's prim_id is checked at build time: it may name a sphere added by pb2_scene_add_spheres)
         if (lights[i].type < PB2_LIGHT_POINT || lights[i].type > PB2_LIGHT_DISTANT) return set_error(PB2_ERR_INVALID, "light %u has unknown type %d", i, lights[i].type);
         if (lights[i].type == PB2_LIGHT_DISTANT || lights[i].type == PB2_LIGHT_SPOT) {
             const float* a = lights[i].axis;
@@ -216,6 +217,62 @@ int pb2_scene_set_shading_geometry(pb2_scene* scene, const float* normals, const
     return PB2_OK;
 }
 
+// Sphere::new (sphere.rs:229-248) + Transform::new's inverse (transform.rs:198-206) -> the 128-byte device record and
+// Shape::world_bound (shape.rs:18-20, sphere.rs:31-36, transform.rs:569-606: the eight corners of the object bound).
+static void make_sphere_record(const pb2_sphere& sp, uint32_t prim, DSphere* out, float bounds[6]) {
+    mat4 m;
+    memcpy(m.m, sp.object_to_world, sizeof m.m);
+    const mat4 mi = invert_mat4(m);
+    memcpy(out->m, m.m, 12 * sizeof(float));
+    memcpy(out->mi, mi.m, 12 * sizeof(float));
+    const float r = sp.radius;
+    auto clampf = [](float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    out->radius = r;
+    out->z_min = clampf(fminf(sp.z_min, sp.z_max), -r, r);
+    out->z_max = clampf(fmaxf(sp.z_max, sp.z_min), -r, r);
+    out->theta_min = det_acos(clampf(fminf(sp.z_min, sp.z_max) / r, -1.0f, 1.0f));
+    out->theta_max = det_acos(clampf(fmaxf(sp.z_max, sp.z_min) / r, -1.0f, 1.0f));
+    out->phi_max = PB2_PI / 180.0f * clampf(sp.phi_max, 0.0f, 360.0f);
+    const float (*a)[4] = m.m;                      // pbrt-v3 Transform::SwapsHandedness
+    const float det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                      a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    out->flags = (sp.reverse_orientation ? 1u : 0u) | (det < 0.0f ? 2u : 0u);
+    out->prim = prim;
+    const float lo[3] = {-r, -r, out->z_min}, hi[3] = {r, r, out->z_max};
+    const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 1, 1}};
+    for (int c = 0; c < 8; ++c) {
+        const vec3 p = xf_point(out->m, mk(corner[c][0] ? hi[0] : lo[0], corner[c][1] ? hi[1] : lo[1], corner[c][2] ? hi[2] : lo[2]));
+        const float q[3] = {p.x, p.y, p.z};
+        for (int k = 0; k < 3; ++k) {
+            bounds[k] = c == 0 ? q[k] : fminf(bounds[k], q[k]);
+            bounds[3 + k] = c == 0 ? q[k] : fmaxf(bounds[3 + k], q[k]);
+        }
+    }
+}
+
+int pb2_scene_add_spheres(pb2_scene* scene, const pb2_sphere* spheres, uint32_t n) {
+    if (!scene || (n && !spheres)) return set_error(PB2_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    if (scene->built || scene->built_host) return set_error(PB2_ERR_STATE, "add the spheres before pb2_scene_build_bvh");
+    if (scene->n_primitives() + n >= (1ull << 29)) return set_error(PB2_ERR_LIMIT, "at most 2^29-1 primitives");
+    for (uint32_t i = 0; i < n; ++i) {
+        const pb2_sphere& sp = spheres[i];
+        for (int k = 0; k < 16; ++k)
+            if (!std::isfinite(sp.object_to_world[k])) return set_error(PB2_ERR_INVALID, "sphere %u: object_to_world is not finite", i);
+        const float* m = sp.object_to_world;
+        if (m[12] != 0.0f || m[13] != 0.0f || m[14] != 0.0f || m[15] != 1.0f)
+            return set_error(PB2_ERR_INVALID, "sphere %u: object_to_world must be affine (last row 0 0 0 1)", i);
+        const float det = m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8]);
+        if (det == 0.0f || !std::isfinite(det)) return set_error(PB2_ERR_INVALID, "sphere %u: object_to_world is singular (Matrix4x4::inverse panics, transform.rs:84)", i);
+        if (!(sp.radius > 0.0f) || !std::isfinite(sp.radius)) return set_error(PB2_ERR_INVALID, "sphere %u: radius must be positive and finite", i);
+        if (!std::isfinite(sp.z_min) || !std::isfinite(sp.z_max) || !std::isfinite(sp.phi_max)) return set_error(PB2_ERR_INVALID, "sphere %u: z_min / z_max / phi_max must be finite", i);
+        if (!scene->materials.empty() && sp.material >= scene->materials.size())
+            return set_error(PB2_ERR_INVALID, "sphere %u references material %u >= %zu", i, sp.material, scene->materials.size());
+    }
+    scene->spheres.insert(scene->spheres.end(), spheres, spheres + n);
+    return PB2_OK;
+}
+
 int pb2_scene_destroy(pb2_scene* scene) {
     if (!scene) return PB2_OK;
     scene->free_device();
@@ -238,7 +295,15 @@ static int build_host_locked(pb2_scene* scene, int max_prims_in_node, int split_
     scene->built_host = false;
     const uint64_t n_tris = scene->indices.size() / 3;
     for (double& v : scene->build_ms) v = 0.0;
-    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh, split_method);
+    for (size_t i = 0; i < scene->lights.size(); ++i)
+        if (scene->lights[i].type == PB2_LIGHT_AREA && scene->lights[i].prim_id >= scene->n_primitives())
+            return set_error(PB2_ERR_INVALID, "area light %zu references primitive %u >= %llu", i, scene->lights[i].prim_id, (unsigned long long)scene->n_primitives());
+    const size_t n_sph = scene->spheres.size();
+    scene->sphere_records.resize(n_sph);
+    std::vector<float> sphere_bounds(6 * n_sph);
+    for (size_t i = 0; i < n_sph; ++i) make_sphere_record(scene->spheres[i], (uint32_t)(n_tris + i), &scene->sphere_records[i], &sphere_bounds[6 * i]);
+    build_sah_bvh(scene->verts.data(), scene->verts.size() / 3, scene->indices.data(), n_tris, max_prims_in_node, 0, &scene->bvh, split_method,
+                  sphere_bounds.data(), n_sph);
     if (scene->bvh.max_depth > kStackDepth)
         return set_error(PB2_ERR_LIMIT, "BVH depth %d exceeds the 64-entry traversal stack of BVHAccel::intersect", scene->bvh.max_depth);
     if (scene->bvh.leaf_overflow)
@@ -304,7 +369,10 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     int rc = check_build_args(max_prims_in_node, split_method);
     if (rc) return rc;
     scene->free_device();
-    const uint64_t n_tris = scene->indices.size() / 3;
+    if (split_method == 1 && !scene->spheres.empty())
+        return set_error(PB2_ERR_INVALID, "SplitMethod::HLBVH (the device build) takes triangles only: build a scene with analytic spheres with SAH / Middle / EqualCounts");
+    const uint64_t n_mesh_tris = scene->indices.size() / 3;
+    const uint64_t n_tris = scene->n_primitives();               // every primitive takes one slot of the leaf-order array
     PB2_CUDA(cudaGetDevice(&scene->device));
     SceneView v;
     memset(&v, 0, sizeof v);
@@ -312,7 +380,7 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
     PB2_CUDA(cudaMalloc(&scene->d_counters, pb2_scene::kCounters * sizeof(unsigned long long)));
     PB2_CUDA(cudaMemset(scene->d_counters, 0, pb2_scene::kCounters * sizeof(unsigned long long)));
     // mesh attributes first: the per-triangle "degenerate frame" flag follows the mesh's UVs
-    if (n_tris && (!scene->normals.empty() || !scene->tangents.empty() || !scene->uvs.empty())) {
+    if (n_mesh_tris && (!scene->normals.empty() || !scene->tangents.empty() || !scene->uvs.empty())) {
         auto up = [](void** d, const void* h, size_t bytes) -> cudaError_t {
             cudaError_t e = cudaMalloc(d, bytes);
             return e == cudaSuccess ? cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) : e;
@@ -350,6 +418,11 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
             v.slot_of_prim = (const uint32_t*)scene->d_slot_of_prim;
             v.root_ref = b.root_ref;
             for (int k = 0; k < 3; ++k) { v.root_lo[k] = b.root_bounds[k]; v.root_hi[k] = b.root_bounds[3 + k]; }
+        }
+        if (!scene->sphere_records.empty()) {
+            PB2_CUDA(cudaMalloc(&scene->d_spheres, scene->sphere_records.size() * sizeof(DSphere)));
+            PB2_CUDA(cudaMemcpy(scene->d_spheres, scene->sphere_records.data(), scene->sphere_records.size() * sizeof(DSphere), cudaMemcpyHostToDevice));
+            v.spheres = (const float4*)scene->d_spheres;
         }
         // the device copies are authoritative from here on; drop the host-side device-layout mirrors
         std::vector<PairNode>().swap(b.pairs);

@@ -12,6 +12,7 @@
 #include "bvh_build.hpp"
 #include "kernels.hpp"
 #include "traverse.cuh"
+#include "sphere.cuh"
 
 namespace pb2 {
 
@@ -85,6 +86,12 @@ struct pb2_scene {
     std::vector<pb2_light> lights;
     // TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26), pb2_scene_set_shading_geometry
     std::vector<float> normals, tangents, uvs;
+    // analytic spheres (shapes/sphere.rs), pb2_scene_add_spheres: primitive ids n_tris .. n_tris + spheres.size() - 1
+    std::vector<pb2_sphere> spheres;
+    std::vector<pb2::DSphere> sphere_records;     // device layout (sphere.cuh), filled at build time
+    void* d_spheres = nullptr;
+    uint64_t n_tris() const { return indices.size() / 3; }
+    uint64_t n_primitives() const { return indices.size() / 3 + spheres.size(); }
     void* d_indices = nullptr;
     void* d_normals = nullptr;
     void* d_tangents = nullptr;

@@ -74,8 +74,14 @@ static void make_distribution(const std::vector<float>& func, std::vector<float>
 // Device tables for shading: per-primitive material / area-light ids, materials, lights and both light distributions
 // (lightdistrib.rs:222-232: "uniform" and "power"; integrator.rs:268-277).
 int upload_shading_tables(pb2_scene* scene) {
-    const size_t n_tris = scene->indices.size() / 3;
-    if (scene->tri_material.empty() || n_tris == 0) return PB2_OK;       // ray-casting-only scene
+    const size_t n_mesh = scene->indices.size() / 3;
+    const size_t n_tris = scene->n_primitives();                         // triangles, then analytic spheres
+    if ((n_mesh && scene->tri_material.empty()) || scene->materials.empty() || n_tris == 0) return PB2_OK;       // ray-casting-only scene
+    std::vector<uint32_t> prim_material(scene->tri_material);
+    for (const pb2_sphere& sp : scene->spheres) {
+        if (sp.material >= scene->materials.size()) return set_error(PB2_ERR_INVALID, "a sphere references material %u >= %zu", sp.material, scene->materials.size());
+        prim_material.push_back(sp.material);
+    }
     std::vector<DMaterial> mats(scene->materials.size());
     unsigned class_mask = 0u;
     for (size_t i = 0; i < mats.size(); ++i) {
@@ -110,8 +116,14 @@ int upload_shading_tables(pb2_scene* scene) {
         for (int k = 0; k < 3; ++k) { d.p[k] = l.p[k]; d.l[k] = l.i[k]; }
         d.prim = l.prim_id;
         d.two_sided = l.two_sided;
+        d.sphere = -1;
         rgb3 pw;
-        if (l.type == PB2_LIGHT_AREA) {
+        if (l.type == PB2_LIGHT_AREA && l.prim_id >= n_mesh) {           // DiffuseAreaLight over a Sphere (sphere.rs:100-102)
+            d.sphere = (int)(l.prim_id - n_mesh);
+            d.area = sphere_area(scene->sphere_records[d.sphere]);
+            tri_light[l.prim_id] = (int32_t)i;
+            pw = mkc(l.i[0], l.i[1], l.i[2]) * ((l.two_sided ? 2.0f : 1.0f) * d.area * PB2_PI);      // diffuse.rs:83-85
+        } else if (l.type == PB2_LIGHT_AREA) {
             const uint32_t* ix = &scene->indices[3ull * l.prim_id];
             const float* v = scene->verts.data();
             const vec3 p0 = mk(v[3 * ix[0]], v[3 * ix[0] + 1], v[3 * ix[0] + 2]);
@@ -157,7 +169,7 @@ int upload_shading_tables(pb2_scene* scene) {
     PB2_CUDA(cudaMalloc(&scene->d_materials, mats.size() * sizeof(DMaterial)));
     PB2_CUDA(cudaMalloc(&scene->d_lights, lights.size() * sizeof(DLight)));
     PB2_CUDA(cudaMalloc(&scene->d_light_cdf, (4 * n_lights + 4) * sizeof(float)));
-    PB2_CUDA(cudaMemcpy(scene->d_tri_material, scene->tri_material.data(), n_tris * 4, cudaMemcpyHostToDevice));
+    PB2_CUDA(cudaMemcpy(scene->d_tri_material, prim_material.data(), n_tris * 4, cudaMemcpyHostToDevice));
     PB2_CUDA(cudaMemcpy(scene->d_tri_light, tri_light.data(), n_tris * 4, cudaMemcpyHostToDevice));
     PB2_CUDA(cudaMemcpy(scene->d_materials, mats.data(), mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice));
     PB2_CUDA(cudaMemcpy(scene->d_lights, lights.data(), lights.size() * sizeof(DLight), cudaMemcpyHostToDevice));
@@ -200,7 +212,7 @@ static int ensure_spatial(pb2_scene* scene, cudaStream_t st) {
     PB2_CUDA(cudaMalloc(&scene->d_spatial, bytes));
     for (int i = 0; i < 3; ++i) scene->spatial_nv[i] = nv[i];
     const SpatialView g = spatial_view(scene);
-    spatial_distribution_build(g, (const DLight*)scene->d_lights, (int)n, (float*)g.func, (float*)g.cdf, (float*)g.func_int, st);
+    spatial_distribution_build(g, (const DLight*)scene->d_lights, (int)n, (float*)g.func, (float*)g.cdf, (float*)g.func_int, st, scene->d_spheres);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
@@ -237,7 +249,7 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
 static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* path, const pb2_film_desc* fd, CameraView* cv) {
     if (!scene || !cam || !path) return set_error(PB2_ERR_INVALID, "null argument");
     if (!scene->built) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
-    if (scene->tri_material.empty()) return set_error(PB2_ERR_STATE, "the scene was created without materials");
+    if (!scene->d_tri_material) return set_error(PB2_ERR_STATE, "the scene was created without materials");
     if (path->max_depth < 0 || path->max_depth > 65535) return set_error(PB2_ERR_INVALID, "max_depth out of range");
     if (path->spp <= 0 || path->sample_begin < 0 || path->sample_end > path->spp || path->sample_begin > path->sample_end)
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
@@ -768,7 +780,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
 int pb2_spatial_light_distribution(pb2_scene* scene, int32_t n_voxels[3], float* func, float* cdf, float* func_int) {
     if (!scene || !n_voxels) return set_error(PB2_ERR_INVALID, "null argument");
     if (!scene->built) return set_error(PB2_ERR_STATE, "pb2_scene_build_bvh has not been called");
-    if (scene->tri_material.empty()) return set_error(PB2_ERR_STATE, "the scene was created without materials");
+    if (!scene->d_tri_material) return set_error(PB2_ERR_STATE, "the scene was created without materials");
     std::lock_guard<std::mutex> lock(scene->mu);
     int rc = ensure_spatial(scene, 0);
     if (rc) return rc;

@@ -337,9 +337,11 @@ private:
 }  // namespace
 
 void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
-                   int max_prims_in_node, int threads, HostBVH* out, int split_method) {
+                   int max_prims_in_node, int threads, HostBVH* out, int split_method, const float* extra_bounds, uint64_t n_extra) {
     (void)n_verts;
     *out = HostBVH();
+    const uint64_t n_mesh = n_tris;
+    n_tris += n_extra;                                           // the primitive list: the mesh's triangles, then the extra shapes
     if (n_tris == 0) return;
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     if (threads < 1) threads = 1;
@@ -356,6 +358,14 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
                 if (s >= n_tris) break;
                 uint64_t e = std::min<uint64_t>(n_tris, s + chunk);
                 for (uint64_t t = s; t < e; ++t) {
+                    if (t >= n_mesh) {                           // Shape::world_bound of an analytic shape, handed in by the caller
+                        const float* b = extra_bounds + 6ull * (t - n_mesh);
+                        PrimRef& r = refs[t];
+                        for (int k = 0; k < 3; ++k) { r.lo[k] = b[k]; r.hi[k] = b[3 + k]; r.c[k] = b[k] * 0.5f + b[3 + k] * 0.5f; }
+                        r.id = (uint32_t)t;
+                        r.bucket = 0;
+                        continue;
+                    }
                     const float* p0 = verts + 3ull * indices[3 * t];
                     const float* p1 = verts + 3ull * indices[3 * t + 1];
                     const float* p2 = verts + 3ull * indices[3 * t + 2];
@@ -385,7 +395,7 @@ void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices
     Builder b(refs, max_prims, threads, split_method);
     b.run(out);
     const double t1 = now();
-    repack_device_layout(verts, indices, n_tris, out);
+    repack_device_layout(verts, indices, n_mesh, out, n_extra);
     if (timing) fprintf(stderr, "[pb2] host build: tree %.3f s, device-layout repack %.3f s (%d threads)\n", t1 - t0, now() - t1, threads);
 }
 
@@ -407,7 +417,9 @@ static void parallel_ranges(size_t n, F&& fn) {
 // array is in depth-first order, so the numbering of the device records follows from two prefix counts over it (interior
 // nodes -> pair index; interior nodes at even depth -> quad index, depth-first like the pairs) and every record can then
 // be filled independently of the others.
-void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out) {
+void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out, uint64_t n_extra) {
+    const uint64_t n_mesh = n_tris;
+    n_tris += n_extra;
     const size_t n_nodes = out->nodes.size();
     const std::vector<LinearNode>& nodes = out->nodes;
     std::vector<uint32_t> pair_of(n_nodes, 0), quad_of(n_nodes, 0);
@@ -481,6 +493,14 @@ void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t 
         for (size_t i = lo; i < hi; ++i) {
             const uint32_t t = out->ordered_prims[i];
             PackedTri& pt = out->tris[i];
+            if (t >= n_mesh) {                                   // an analytic sphere: its index in the sphere table rides in v0[0]
+                const uint32_t k = (uint32_t)(t - n_mesh);
+                std::memset(&pt, 0, sizeof pt);
+                std::memcpy(&pt.v0[0], &k, 4);
+                pt.prim_id = t;
+                pt.pad = kPrimSphere;
+                continue;
+            }
             const float* p0 = verts + 3ull * indices[3ull * t];
             const float* p1 = verts + 3ull * indices[3ull * t + 1];
             const float* p2 = verts + 3ull * indices[3ull * t + 2];

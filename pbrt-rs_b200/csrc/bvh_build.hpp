@@ -82,11 +82,16 @@ struct HostBVH {
 
 // verts: 3 floats per vertex; indices: 3 per triangle.  threads <= 0 -> hardware concurrency.  split_method
 // (bvh.rs:199-204): 0 = SplitMethod::SAH, 2 = ::Middle, 3 = ::EqualCounts (the top-down recursive_build, bvh.rs:273-473).
+// extra_bounds / n_extra: primitives that are not triangles (analytic spheres, shapes/sphere.rs), given by their world bounds
+// (6 floats each: min.xyz, max.xyz = Shape::world_bound); they follow the triangles in the primitive list (ids n_tris ..
+// n_tris + n_extra - 1) and take one PackedTri slot each with pad bit 1 set and v0[0] = bits of their index (kPrimSphere).
 void build_sah_bvh(const float* verts, uint64_t n_verts, const uint32_t* indices, uint64_t n_tris,
-                   int max_prims_in_node, int threads, HostBVH* out, int split_method = 0);
+                   int max_prims_in_node, int threads, HostBVH* out, int split_method = 0, const float* extra_bounds = nullptr,
+                   uint64_t n_extra = 0);
 
 // Fills pairs / quads / tris / root refs / root bounds of `out` from its nodes + ordered_prims.
-void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out);
+void repack_device_layout(const float* verts, const uint32_t* indices, uint64_t n_tris, HostBVH* out, uint64_t n_extra = 0);
+constexpr uint32_t kPrimDegenerate = 1u, kPrimSphere = 2u;      // PackedTri::pad bits
 
 // What a device-side build hands over: the traversal layout already in device memory (ownership passes to the caller,
 // cudaFree each pointer) plus the flattened reference-layout nodes and primitive order, kept on the device and only

@@ -100,6 +100,8 @@ Xf perspective(float fov_deg, float n, float f) {
 
 }  // namespace
 
+mat4 invert_mat4(const mat4& m) { return invert(m); }
+
 // cam9 = pos, look, up
 void camera_setup(const float pos[3], const float look[3], const float up[3], float fov, int res_x, int res_y, CameraView* out) {
     out->res_x = res_x;

@@ -26,6 +26,8 @@ void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_h
                          void* d_out, cudaStream_t st);
 void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st);
 void launch_mark_degenerate(void* d_tris, uint64_t n, const void* d_indices, const void* d_uvs, cudaStream_t st);
+// Matrix4x4::inverse (transform.rs:46-113; camera_host.cpp)
+mat4 invert_mat4(const mat4& m);
 void set_trace_tuning(int refill_below, int node_quorum, int leaf_quorum, int prefetch);
 void launch_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* d_out, cudaStream_t st);
 

@@ -30,6 +30,10 @@ struct BatchSink {
         hits[i] = make_uint4(prim, __float_as_uint(t), __float_as_uint(b1), __float_as_uint(b2));
         if (b0_out) b0_out[i] = b0;
     }
+    PB2_D void accept_sphere(uint32_t i, uint32_t prim, float t, float u, float v) const {
+        hits[i] = make_uint4(prim, __float_as_uint(t), __float_as_uint(u), __float_as_uint(v));
+        if (b0_out) b0_out[i] = 0.0f;
+    }
     PB2_D void finish(uint32_t i, bool found, float t_max) const {
         if (found) return;
         hits[i] = make_uint4(0xFFFFFFFFu, __float_as_uint(t_max), 0u, 0u);
@@ -42,14 +46,28 @@ __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_closest_hit(SceneView s
                                                       unsigned long long* __restrict__ counter, uint4* __restrict__ hits,
                                                       float* __restrict__ b0_out, TraceTuning tune) {
     const BatchSink sink{rays, hits, b0_out, nullptr};
-    trace_persistent<false>(s, n, counter, sink, tune);
+    trace_persistent<false, false>(s, n, counter, sink, tune);
 }
 
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_any_hit(SceneView s, const float4* __restrict__ rays, uint32_t n,
                                                   unsigned long long* __restrict__ counter, uint8_t* __restrict__ out,
                                                   TraceTuning tune) {
     const BatchSink sink{rays, nullptr, nullptr, out};
-    trace_persistent<true>(s, n, counter, sink, tune);
+    trace_persistent<true, false>(s, n, counter, sink, tune);
+}
+
+// The same walks over a scene that holds analytic spheres next to its triangles (sphere.cuh): the EFloat quadratic needs more
+// registers than the triangle-only kernels are allowed, so these are separate kernels and triangle scenes never pay for them.
+__global__ void __launch_bounds__(128, 4) k_closest_hit_spheres(SceneView s, const float4* __restrict__ rays, uint32_t n,
+                                                                unsigned long long* __restrict__ counter, uint4* __restrict__ hits,
+                                                                float* __restrict__ b0_out, TraceTuning tune) {
+    const BatchSink sink{rays, hits, b0_out, nullptr};
+    trace_persistent<false, true>(s, n, counter, sink, tune);
+}
+__global__ void __launch_bounds__(128, 4) k_any_hit_spheres(SceneView s, const float4* __restrict__ rays, uint32_t n,
+                                                            unsigned long long* __restrict__ counter, uint8_t* __restrict__ out, TraceTuning tune) {
+    const BatchSink sink{rays, nullptr, nullptr, out};
+    trace_persistent<true, true>(s, n, counter, sink, tune);
 }
 
 // Scheduling knobs (results do not depend on them).  Defaults tuned on B200 with the C3 workload; the environment
@@ -99,6 +117,7 @@ __global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tr
     if (i >= n) return;
     const float4 a = tris[3ull * i], b = tris[3ull * i + 1];
     float4 c = tris[3ull * i + 2];
+    if (__float_as_uint(c.w) & 2u) return;              // an analytic sphere's slot (bvh_build.hpp: kPrimSphere)
     vec3 du, dv;
     bool ok;
     if (uvs) {
@@ -118,6 +137,10 @@ void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void
                         cudaStream_t st) {
     if (n == 0) return;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
+    if (s.spheres)
+        k_closest_hit_spheres<<<persistent_grid((const void*)k_closest_hit_spheres, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter,
+                                                                                                   (uint4*)d_hits, (float*)d_b0, trace_tuning());
+    else
     k_closest_hit<<<persistent_grid((const void*)k_closest_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter, (uint4*)d_hits,
                                                                                  (float*)d_b0, trace_tuning());
 }
@@ -125,6 +148,10 @@ void launch_closest_hit(const SceneView& s, const void* d_rays, uint64_t n, void
 void launch_any_hit(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, unsigned long long* d_counter, cudaStream_t st) {
     if (n == 0) return;
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st);
+    if (s.spheres)
+        k_any_hit_spheres<<<persistent_grid((const void*)k_any_hit_spheres, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter,
+                                                                                           (uint8_t*)d_out, trace_tuning());
+    else
     k_any_hit<<<persistent_grid((const void*)k_any_hit, n), 128, 0, st>>>(s, (const float4*)d_rays, (uint32_t)n, d_counter, (uint8_t*)d_out, trace_tuning());
 }
 

@@ -20,8 +20,17 @@ struct SpatialSamples {
 // Light::sample_li at a bare point (no normal, no error bounds: lightdistrib.rs:133-140) without its VisibilityTester:
 // point.rs:47-66, spot.rs:71-85, distant.rs:50-67, diffuse.rs:60-81 + shape.rs:38-53 + triangle.rs:330-348.  Same operations,
 // in the same order, as the head of direct_lighting() in wavefront.cu.
-__device__ __forceinline__ rgb3 light_sample_li(const DLight& light, vec3 p, float ul0, float ul1, float* pdf_out) {
+__device__ __forceinline__ rgb3 light_sample_li(const DLight& light, const DSphere* spheres, vec3 p, float ul0, float ul1, float* pdf_out) {
     const rgb3 l_emit = mkc(light.l[0], light.l[1], light.l[2]);
+    if (light.type == 1 && light.sphere >= 0) {                          // DiffuseAreaLight over a Sphere: sphere.rs:127-193 from a bare point
+        vec3 ps, pe, ns;
+        float pdf;
+        sphere_sample2(spheres[light.sphere], p, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), ul0, ul1, &ps, &pe, &ns, &pdf);
+        *pdf_out = pdf;
+        if (pdf == 0.0f || len2(ps - p) == 0.0f) { *pdf_out = 0.0f; return gray(0.0f); }
+        const vec3 wi = unit(ps - p);
+        return (light.two_sided || dot3(ns, -wi) > 0.0f) ? l_emit : gray(0.0f);
+    }
     if (light.type != 1) {                                               // delta lights: point, spot, distant
         *pdf_out = 1.0f;
         if (light.type == 3) return l_emit;
@@ -71,7 +80,7 @@ __device__ __forceinline__ vec3 bounds_lerp(vec3 lo, vec3 hi, vec3 t) {
 
 // compute_distribution (lightdistrib.rs:107-158), the per-light sums: thread = (light, voxel).
 __global__ void __launch_bounds__(128) k_spatial_contrib(SpatialView g, const DLight* __restrict__ lights, int n_lights, SpatialSamples smp,
-                                                         float* __restrict__ func) {
+                                                         float* __restrict__ func, const DSphere* __restrict__ spheres) {
     const size_t n_vox = (size_t)g.nv[0] * g.nv[1] * g.nv[2];
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_vox * (size_t)n_lights) return;
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(SpatialView g, const DL
     for (int i = 0; i < kSpatialSamples; ++i) {
         const vec3 po = bounds_lerp(vlo, vhi, mk(smp.v[0][i], smp.v[1][i], smp.v[2][i]));
         float pdf = 0.0f;
-        const rgb3 li = light_sample_li(light, po, smp.v[3][i], smp.v[4][i], &pdf);
+        const rgb3 li = light_sample_li(light, spheres, po, smp.v[3][i], smp.v[4][i], &pdf);
         if (pdf > 0.0f) contrib = contrib + luminance(li) / pdf;
     }
     func[vox * (size_t)n_lights + (size_t)j] = contrib;
@@ -154,13 +163,13 @@ void spatial_grid_extents(const float wb[6], int max_voxels, int nv[3]) {
 
 // Fills func [n_vox][n_lights], cdf [n_vox][n_lights + 1] and func_int [n_vox] (device arrays) on stream st.
 void spatial_distribution_build(const SpatialView& grid, const DLight* d_lights, int n_lights, float* d_func, float* d_cdf, float* d_func_int,
-                                cudaStream_t st) {
+                                cudaStream_t st, const void* d_spheres) {
     SpatialSamples smp;
     for (int b = 0; b < 5; ++b)
         for (int i = 0; i < kSpatialSamples; ++i) smp.v[b][i] = radical_inverse_small(b, (uint64_t)i);
     const size_t n_vox = (size_t)grid.nv[0] * grid.nv[1] * grid.nv[2];
     const size_t n_pairs = n_vox * (size_t)n_lights;
-    k_spatial_contrib<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(grid, d_lights, n_lights, smp, d_func);
+    k_spatial_contrib<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(grid, d_lights, n_lights, smp, d_func, (const DSphere*)d_spheres);
     k_spatial_distrib<<<(unsigned)((n_vox + 127) / 128), 128, 0, st>>>(n_vox, n_lights, d_func, d_cdf, d_func_int);
 }
 

@@ -197,6 +197,7 @@ struct DLight {
     int has_n, has_uv;      // area: the mesh carries vertex normals / UVs
     float n0[3], n1[3], n2[3];   // vertex normals of the emissive triangle (Triangle::sample, triangle.rs:338-341)
     float uv[6];            // its UVs (Shape::pdf2 -> Triangle::intersect frame check)
+    int sphere;             // area light over an analytic sphere: index into SceneView::spheres, else -1
 };
 
 enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u,

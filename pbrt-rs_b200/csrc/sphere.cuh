@@ -17,6 +17,7 @@
 
 namespace pb2 {
 
+PB2_HD float clamp_f(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }      // pbrt.rs:112-120
 PB2_HD float det_asin(float x) {
     const float a = fabsf(x);
     const bool big = a > 0.5f;

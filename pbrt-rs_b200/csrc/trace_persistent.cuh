@@ -93,9 +93,13 @@ PB2_D RayCtx ctx_of(vec3 o, vec3 inv, vec3 sh, uint32_t flags) {
 //   bool load(uint32_t i, vec3* o, vec3* d, float* t_max)                                — false: slot i carries no ray
 //   void accept(uint32_t i, uint32_t prim, float t, float b0, float b1, float b2)       — closest hit: a candidate was
 //                                                     accepted (called in test order; the last call is the closest hit)
+//   void accept_sphere(uint32_t i, uint32_t prim, float t, float u, float v)            — the same for an analytic sphere (SPH only)
 //   void finish(uint32_t i, bool found, float t_max)                                     — closest hit: walk over
 //   void occluded(uint32_t i, bool occ)                                                  — any hit: walk over
-template <bool ANY, class Sink>
+// SPH: the scene holds analytic spheres (sphere.cuh); a separate instantiation, so that triangle-only scenes keep their
+// register budget.  A sphere test needs the ray's direction itself (the walk carries its inverse only), so it reloads the ray
+// from the sink; a sphere hit is handed to accept() with b0 = t (Sphere::intersect has no barycentrics; b1, b2 = u, v).
+template <bool ANY, bool SPH, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n, unsigned long long* __restrict__ counter,
                                                  const Sink& sink, const TraceTuning tune) {
     uint2 stack[kQuadStackDepth];            // {reference, entry distance bits}
@@ -150,10 +154,13 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                                 // reject a box whose child it accepts; folding two levels relies on "child hit => parent
                                 // hit", so these (rare) rays take the literal one-level walk right here.
                                 HitRec h;
-                                const bool found = traverse<ANY>(s, o, d, t_max, &h);
+                                const bool found = traverse<ANY, SPH>(s, o, d, t_max, &h);
                                 if (ANY) sink.occluded(ray_idx, found);
                                 else {
-                                    if (found) sink.accept(ray_idx, h.prim, h.t, h.b0, h.b1, h.b2);
+                                    if (found) {
+                                        if (SPH && h.sphere) sink.accept_sphere(ray_idx, h.prim, h.t, h.b1, h.b2);
+                                        else sink.accept(ray_idx, h.prim, h.t, h.b0, h.b1, h.b2);
+                                    }
                                     sink.finish(ray_idx, found, found ? h.t : t_max);
                                 }
                             } else
@@ -241,6 +248,18 @@ __device__ __forceinline__ void trace_persistent(const SceneView& s, uint32_t n,
                     const float4 c = ldg4(s.tris + 3ull * slot + 2);
                     const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
                     float t, b0, b1, b2;
+                    if (SPH && (__float_as_uint(c.w) & 2u)) {
+                        vec3 ro, rd, p_hit, od;
+                        float tm, phi;
+                        sink.load(ray_idx, &ro, &rd, &tm);
+                        if (sphere_test(sphere_of(s, a), ro, rd, t_max, &p_hit, &phi, &od, &t)) {
+                            if (ANY) { occluded = true; break; }
+                            const SphereVertex sv = sphere_vertex(sphere_of(s, a), p_hit, phi, od);
+                            t_max = t;
+                            flags |= kFlagFound;
+                            sink.accept_sphere(ray_idx, __float_as_uint(a.w), t, sv.u, sv.v);
+                        }
+                    } else
                     if (tri_test(r, t_max, p0, p1, p2, &t, &b0, &b1, &b2)) {
                         if (ANY) { occluded = true; break; }
                         // c.w: Triangle::intersect bails out on this triangle's degenerate frame (triangle.rs:193-215);

@@ -13,6 +13,7 @@
 // triangles tested equals the reference's.
 #pragma once
 #include "pb2_math.cuh"
+#include "sphere.cuh"
 
 namespace pb2 {
 
@@ -25,8 +26,9 @@ struct SceneView {
     const float4* __restrict__ pairs;   // 4 x float4 per interior node (PairNode): literal one-level walk (traverse())
     const float4* __restrict__ tris;    // 3 x float4 per triangle (PackedTri), BVH leaf order
     const uint32_t* __restrict__ slot_of_prim;   // caller's triangle id -> leaf-order slot
+    const float4* __restrict__ spheres;  // 8 x float4 per analytic sphere (DSphere, sphere.cuh); null when the scene has none
     uint32_t root_ref;
-    uint32_t n_tris;
+    uint32_t n_tris;                     // primitives in the tree (triangles + spheres)
     float root_lo[3];
     float root_hi[3];
 };
@@ -35,6 +37,7 @@ struct HitRec {
     uint32_t prim;      // caller's triangle id
     uint32_t slot;      // position in leaf order (index into tris)
     float t, b0, b1, b2;
+    bool sphere;        // the hit is an analytic sphere: b0 = 0, (b1, b2) = (u, v)
 };
 
 // Per-ray constants: inverse direction, slab selectors and the shear of the watertight test.
@@ -181,7 +184,10 @@ PB2_D void ldg8(const float4* p, float4* a, float4* b) {
 }
 
 // One ray through the BVH.  ANY = intersect_p semantics (first accepted triangle ends the walk).
-template <bool ANY>
+// A sphere's leaf slot (bvh_build.hpp kPrimSphere): c.w bit 1 set, a.x = bits of its index in SceneView::spheres.
+PB2_D const DSphere& sphere_of(const SceneView& s, float4 a) { return reinterpret_cast<const DSphere*>(s.spheres)[__float_as_uint(a.x)]; }
+
+template <bool ANY, bool SPH = false>
 PB2_D bool traverse(const SceneView& s, vec3 o, vec3 d, float ray_t_max, HitRec* hit) {
     if (s.n_tris == 0) return false;
     const RayCtx r = make_ray_ctx(o, d);
@@ -203,6 +209,20 @@ PB2_D bool traverse(const SceneView& s, vec3 o, vec3 d, float ray_t_max, HitRec*
                 const float4 c = ldg4(s.tris + 3ull * slot + 2);
                 const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
                 float t, b0, b1, b2;
+                if (SPH && (__float_as_uint(c.w) & 2u)) {       // GeometricPrimitive(Sphere) (primitive.rs:65-78, sphere.rs:38-98)
+                    vec3 p_hit, od;
+                    float phi;
+                    if (sphere_test(sphere_of(s, a), o, d, t_max, &p_hit, &phi, &od, &t)) {
+                        if (ANY) return true;
+                        const SphereVertex sv = sphere_vertex(sphere_of(s, a), p_hit, phi, od);
+                        t_max = t;
+                        hit->prim = __float_as_uint(a.w);
+                        hit->slot = slot;
+                        hit->t = t; hit->b0 = 0.0f; hit->b1 = sv.u; hit->b2 = sv.v;
+                        hit->sphere = true;
+                        found = true;
+                    }
+                } else
                 if (tri_test(r, t_max, p0, p1, p2, &t, &b0, &b1, &b2)) {
                     if (ANY) return true;
                     if (__float_as_uint(c.w) == 0u) {          // frame not degenerate (k_mark_degenerate, triangle.rs:193-215)
@@ -210,6 +230,7 @@ PB2_D bool traverse(const SceneView& s, vec3 o, vec3 d, float ray_t_max, HitRec*
                         hit->prim = __float_as_uint(a.w);
                         hit->slot = slot;
                         hit->t = t; hit->b0 = b0; hit->b1 = b1; hit->b2 = b2;
+                        hit->sphere = false;
                         found = true;
                     }
                 }

@@ -564,6 +564,10 @@ struct ExtendSink {
         if (i >= n_extend) b.mis_prim[b.q_mis[i - n_extend]] = prim;
         else b.hit[queue[i]] = make_uint4(prim, __float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2));
     }
+    PB2_D void accept_sphere(uint32_t i, uint32_t prim, float t, float u, float v) const {       // hit.y carries t for a sphere
+        if (i >= n_extend) b.mis_prim[b.q_mis[i - n_extend]] = prim;
+        else b.hit[queue[i]] = make_uint4(prim, __float_as_uint(t), __float_as_uint(u), __float_as_uint(v));
+    }
     PB2_D void finish(uint32_t i, bool found, float) const {
         if (i >= n_extend) {
             const uint32_t slot = b.q_mis[i - n_extend];
@@ -584,7 +588,13 @@ struct ExtendSink {
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_extend(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
     const uint32_t n_extend = (uint32_t)b.counters[C_ACTIVE_A + cur], n_mis = (uint32_t)b.counters[C_MIS];   // the previous bounce's MIS rays
     const ExtendSink sink{b, sh, b.q_active[cur], n_extend};
-    trace_persistent<false>(s, n_extend + n_mis, &b.counters[C_WORK_EXTEND], sink, tune);
+    trace_persistent<false, false>(s, n_extend + n_mis, &b.counters[C_WORK_EXTEND], sink, tune);
+}
+// scenes with analytic spheres (sphere.cuh): separate kernels, as in kernels_traverse.cu
+__global__ void __launch_bounds__(128, 4) k_extend_spheres(SceneView s, ShadeView sh, PathBuffers b, int cur, TraceTuning tune) {
+    const uint32_t n_extend = (uint32_t)b.counters[C_ACTIVE_A + cur], n_mis = (uint32_t)b.counters[C_MIS];
+    const ExtendSink sink{b, sh, b.q_active[cur], n_extend};
+    trace_persistent<false, true>(s, n_extend + n_mis, &b.counters[C_WORK_EXTEND], sink, tune);
 }
 
 struct ShadowSink {
@@ -598,6 +608,7 @@ struct ShadowSink {
         return true;
     }
     PB2_D void accept(uint32_t, uint32_t, float, float, float, float) const {}
+    PB2_D void accept_sphere(uint32_t, uint32_t, float, float, float) const {}
     PB2_D void finish(uint32_t, bool, float) const {}
     PB2_D void occluded(uint32_t i, bool occ) const {
         const uint32_t slot = b.q_shadow[i];
@@ -608,7 +619,11 @@ struct ShadowSink {
 };
 __global__ void __launch_bounds__(128, PB2_MIN_BLOCKS) k_shadow(SceneView s, PathBuffers b, TraceTuning tune) {
     const ShadowSink sink{b};
-    trace_persistent<true>(s, (uint32_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
+    trace_persistent<true, false>(s, (uint32_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
+}
+__global__ void __launch_bounds__(128, 4) k_shadow_spheres(SceneView s, PathBuffers b, TraceTuning tune) {
+    const ShadowSink sink{b};
+    trace_persistent<true, true>(s, (uint32_t)b.counters[C_SHADOW], &b.counters[C_WORK_SHADOW], sink, tune);
 }
 
 // ---- shade -----------------------------------------------------------------------------------------------------------------
@@ -617,14 +632,24 @@ __device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]
 struct Vertex {           // SurfaceInteraction subset rebuilt from the hit record (triangle.rs:193-311, D59)
     vec3 p, err, n, dpdu;
     vec3 sn, sdpdu;       // shading.n, shading.dpdu: n and dpdu unless the mesh has vertex normals / tangents
+    vec3 wo;              // SurfaceInteraction::wo: -ray.d for a triangle; normalize(o2w * -ray_obj.d) for a sphere (sphere.rs:79)
 };
 // SG = the mesh carries per-vertex normals, tangents or UVs (compiled out otherwise: k_shade is at its register limit).
+// ro / rd: the ray that hit (a sphere's interaction is rebuilt from the ray and the hit distance, which a sphere hit carries in
+// place of b0; sphere.rs:38-93).
 template <bool SG>
-__device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const ShadeView& sh, uint32_t prim, float b0, float b1, float b2) {
+__device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const ShadeView& sh, uint32_t prim, float b0, float b1, float b2,
+                                                 vec3 ro = mk(0.f, 0.f, 0.f), vec3 rd = mk(0.f, 0.f, 1.f)) {
     const uint32_t slot = __ldg(s.slot_of_prim + prim);
     const float4 a = ldg4(s.tris + 3ull * slot), b = ldg4(s.tris + 3ull * slot + 1), c = ldg4(s.tris + 3ull * slot + 2);
     const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
     Vertex v;
+    v.wo = -rd;
+    if (SG && s.spheres && (__float_as_uint(c.w) & 2u)) {
+        const SphereVertex sv = sphere_vertex_at(sphere_of(s, a), ro, rd, b0);
+        v.p = sv.p; v.err = sv.err; v.n = sv.n; v.dpdu = sv.dpdu; v.sn = sv.sn; v.sdpdu = sv.dpdu; v.wo = sv.wo;
+        return v;
+    }
     const float xs = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x)) + fabsf(b2 * p2.x);
     const float ys = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y)) + fabsf(b2 * p2.y);
     const float zs = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z)) + fabsf(b2 * p2.z);
@@ -632,7 +657,7 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
     v.p = (p0 * b0 + p1 * b1) + p2 * b2;
     v.n = unit(cross3(p0 - p2, p1 - p2));
     vec3 dv;
-    if (!SG) {
+    if (!SG || !sh.indices) {                                  // (SG without mesh attributes: a scene that has analytic spheres)
         tri_frame(p0, p1, p2, &v.dpdu, &dv);
         v.sn = v.n;
         v.sdpdu = v.dpdu;
@@ -701,6 +726,19 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
         sh_o = offset_ray_origin(v.p, v.err, v.n, pl - v.p);             // interaction.rs:146-153
         const vec3 target = offset_ray_origin(pl, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), sh_o - pl);
         sh_d = target - sh_o;
+    } else if (SG && light.sphere >= 0) {                                // diffuse.rs:60-81 + sphere.rs:127-193
+        vec3 ps, pe, ns;
+        float pdf;
+        sphere_sample2(reinterpret_cast<const DSphere*>(s.spheres)[light.sphere], v.p, v.err, v.n, ul0, ul1, &ps, &pe, &ns, &pdf);
+        if (pdf == 0.0f || len2(ps - v.p) == 0.0f) { light_pdf = 0.0f; }
+        else {
+            light_pdf = pdf;
+            wi = unit(ps - v.p);
+            li = (light.two_sided || dot3(ns, -wi) > 0.0f) ? l_emit : gray(0.0f);
+            sh_o = offset_ray_origin(v.p, v.err, v.n, ps - v.p);
+            const vec3 target = offset_ray_origin(ps, pe, ns, sh_o - ps);
+            sh_d = target - sh_o;
+        }
     } else {                                                             // diffuse.rs:60-81, shape.rs:38-53, triangle.rs:330-348
         const float su0 = sqrtf(ul0);
         const float b0 = 1.0f - su0, b1 = ul1 * su0;                     // sampling.rs:275-278
@@ -748,6 +786,31 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
             bool go = true;
             const vec3 ro = offset_ray_origin(v.p, v.err, v.n, wi);      // it.spawn_ray(wi)
             float lb0 = 0.0f, lb1 = 0.0f, lb2 = 0.0f;
+            if (SG && light.sphere >= 0) {
+                // Light::pdf_li -> Sphere::pdf2 (sphere.rs:195-207); then the light's normal where this ray meets the sphere (the
+                // closest hit of the MIS ray is this sphere or the contribution is dropped in k_extend)
+                const DSphere& sp = reinterpret_cast<const DSphere*>(s.spheres)[light.sphere];
+                if (!sampled_specular) {
+                    const float lp = sphere_pdf2(sp, v.p, v.err, v.n, wi);
+                    if (lp == 0.0f) go = false;
+                    else weight = power_heuristic(scattering_pdf, lp);
+                }
+                if (go) {
+                    float t_l;
+                    SphereVertex lv;
+                    if (!sphere_intersect(sp, ro, wi, kInf, &t_l, &lv)) go = false;
+                    else {
+                        const rgb3 lmis = (light.two_sided || dot3(lv.n, -wi) > 0.0f) ? l_emit : gray(0.0f);
+                        if (!black(lmis)) {
+                            pending |= 2u;
+                            t2 = lmis * f * gray(1.0f) * weight / scattering_pdf;
+                            mis_o = ro;
+                            mis_d = wi;
+                        }
+                    }
+                }
+                go = false;                                              // handled
+            } else
             if (!sampled_specular) {
                 // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): the light's own triangle
                 const RayCtx rc = make_ray_ctx(ro, wi);
@@ -818,7 +881,9 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
         const unsigned state = __float_as_uint(Lf.w);
         unsigned bounces = state & 0xFFFFu;
         const bool specular_bounce = (state >> 16) & 1u;
-        const Vertex v = rebuild_vertex<SG>(s, sh, h.x, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w));
+        vec3 ray_o = mk(0.f, 0.f, 0.f);
+        if (SG && s.spheres) { const float4 ro = b.ray_o[slot]; ray_o = mk(ro.x, ro.y, ro.z); }
+        const Vertex v = rebuild_vertex<SG>(s, sh, h.x, __uint_as_float(h.y), __uint_as_float(h.z), __uint_as_float(h.w), ray_o, mk(rd.x, rd.y, rd.z));
         const vec3 wo = -mk(rd.x, rd.y, rd.z);
         if (bounces == 0u || specular_bounce) {                          // path.rs:80-82 + interaction.rs:387-395
             const int li = sh.tri_light[h.x];
@@ -851,7 +916,7 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
                     float ul0, ul1, us0, us1;
                     rng.next2<TABLES>(&ul0, &ul1);
                     rng.next2<TABLES>(&us0, &us1);
-                    queued |= direct_lighting<SG>(s, sh, b, slot, v, wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta) << 3;
+                    queued |= direct_lighting<SG>(s, sh, b, slot, v, SG ? v.wo : wo, bsdf, sh.lights[li], pick_pdf, ul0, ul1, us0, us1, beta) << 3;   // estimate_direct reads it.wo
                 }
             }
             float u0, u1;
@@ -1210,7 +1275,7 @@ void launch_shade_t(Wavefront* wf, const SceneView& sv, const ShadeView& sh, con
 }
 void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map, const FilmView& film,
                   const PathParams& pp, int cur, uint64_t n, cudaStream_t st) {
-    const bool tables = map.smp.kind == 2 || map.smp.kind == 3, sg = sh.indices != nullptr;
+    const bool tables = map.smp.kind == 2 || map.smp.kind == 3, sg = sh.indices != nullptr || sv.spheres != nullptr;   // SG = the general vertex
     if (tables && sg) launch_shade_t<true, true>(wf, sv, sh, b, map, film, pp, cur, n, st);
     else if (tables) launch_shade_t<true, false>(wf, sv, sh, b, map, film, pp, cur, n, st);
     else if (sg) launch_shade_t<false, true>(wf, sv, sh, b, map, film, pp, cur, n, st);
@@ -1222,12 +1287,13 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
                  const PathParams& pp, uint64_t n, cudaStream_t st) {
     PathBuffers& b = wf->b;
     const TraceTuning tune = trace_tuning();
-    const unsigned trace_grid = (unsigned)wf->sm_count * (unsigned)PB2_MIN_BLOCKS;
+    const unsigned trace_grid = (unsigned)wf->sm_count * (unsigned)PB2_MIN_BLOCKS, trace_grid_sph = (unsigned)wf->sm_count * 4u;
     k_raygen<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, cam, b);
     int launches = 1;
     for (int depth = 0; depth <= pp.max_depth; ++depth) {
         const int cur = depth & 1;
-        k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
+        if (sv.spheres) k_extend_spheres<<<trace_grid_sph, 128, 0, st>>>(sv, sh, b, cur, tune);
+        else k_extend<<<trace_grid, 128, 0, st>>>(sv, sh, b, cur, tune);
         // hits -> one queue per shading class (material-sorted shading)
         compact_queues(wf, b.q_active[cur], C_ACTIVE_A + cur, true, b.q_mat[0], C_MAT0, b.q_mat[1], C_MAT1, b.q_mat[2], C_MAT2, st);
         launch_shade(wf, sv, sh, b, map, film, pp, cur, n, st);
@@ -1237,7 +1303,8 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
                        b.q_mis, C_MIS, st);
         launches += 1;
         if (sh.n_lights > 0) {
-            k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
+            if (sv.spheres) k_shadow_spheres<<<trace_grid_sph, 128, 0, st>>>(sv, b, tune);
+            else k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
             launches += 1;
         }
     }

@@ -170,7 +170,7 @@ void pixel_tables_generate(int kind, uint32_t n_pix, int spp, int n_dims, int x_
 // SpatialLightDistribution (light_distrib.cu)
 void spatial_grid_extents(const float wb[6], int max_voxels, int nv[3]);
 void spatial_distribution_build(const SpatialView& grid, const DLight* d_lights, int n_lights, float* d_func, float* d_cdf, float* d_func_int,
-                                cudaStream_t st);
+                                cudaStream_t st, const void* d_spheres = nullptr);
 void film_finish(const FilmView& film, unsigned long long* counters, cudaStream_t st);
 void film_add_samples(const FilmView& film, const float* d_pfilm, const float* d_L, const float* d_w, uint64_t n, cudaStream_t st);
 void film_resolve(const FilmView& film, float scale, float splat_scale, float* d_rgb, cudaStream_t st);

@@ -113,6 +113,21 @@ pub struct pb2_light {
 }
 abi_size!(pb2_light, 56);
 
+/// `Sphere::new` (src/shapes/sphere.rs:229-248) + the material of its `GeometricPrimitive`; `object_to_world` row-major, affine.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct pb2_sphere {
+    pub object_to_world: [f32; 16],
+    pub radius: f32,
+    pub z_min: f32,
+    pub z_max: f32,
+    /// degrees
+    pub phi_max: f32,
+    pub reverse_orientation: i32,
+    pub material: u32,
+}
+abi_size!(pb2_sphere, 88);
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct pb2_camera {
@@ -212,6 +227,7 @@ extern "C" {
                             mats: *const pb2_material, n_mats: u32, lights: *const pb2_light, n_lights: u32,
                             out: *mut *mut pb2_scene) -> c_int;
     pub fn pb2_scene_set_shading_geometry(scene: *mut pb2_scene, normals: *const f32, tangents: *const f32, uvs: *const f32) -> c_int;
+    pub fn pb2_scene_add_spheres(scene: *mut pb2_scene, spheres: *const pb2_sphere, n: u32) -> c_int;
     pub fn pb2_scene_destroy(scene: *mut pb2_scene) -> c_int;
     pub fn pb2_scene_build_bvh(scene: *mut pb2_scene, max_prims_in_node: c_int, split_method: c_int) -> c_int;
     pub fn pb2_scene_build_bvh_host(scene: *mut pb2_scene, max_prims_in_node: c_int, split_method: c_int) -> c_int;
@@ -365,6 +381,7 @@ pub struct B200Accel {
     /// The caller's `GeometricPrimitive`s in triangle order, when given: `intersect` points `si.primitive` at the one that was
     /// hit, so `SurfaceInteraction::compute_scattering_functions` / `le` reach its material and area light (interaction.rs:323-330).
     primitives: Vec<PrimitiveDt>,
+    n_spheres: usize,
 }
 unsafe impl Send for B200Accel {}
 unsafe impl Sync for B200Accel {}
@@ -385,9 +402,16 @@ impl B200Accel {
     /// emissive triangle in `pb2_light::prim_id`).
     pub fn from_mesh(mesh: MeshData, primitives: Vec<PrimitiveDt>, tri_material: Option<&[u32]>, mats: &[pb2_material],
                      lights: &[pb2_light], max_prims_in_node: usize, split_method: SplitMethod) -> Self {
+        Self::from_mesh_and_spheres(mesh, &[], primitives, tri_material, mats, lights, max_prims_in_node, split_method)
+    }
+
+    /// The same with analytic `Sphere`s (src/shapes/sphere.rs) appended to the primitive list: sphere `k` has primitive id
+    /// `n_triangles + k`; `primitives`, when given, lists the triangles' `GeometricPrimitive`s and then the spheres'.
+    pub fn from_mesh_and_spheres(mesh: MeshData, spheres: &[pb2_sphere], primitives: Vec<PrimitiveDt>, tri_material: Option<&[u32]>,
+                                 mats: &[pb2_material], lights: &[pb2_light], max_prims_in_node: usize, split_method: SplitMethod) -> Self {
         assert!(mesh.p.len() % 3 == 0 && mesh.vertex_indices.len() % 3 == 0);
         let n_tris = mesh.vertex_indices.len() / 3;
-        assert!(primitives.is_empty() || primitives.len() == n_tris);
+        assert!(primitives.is_empty() || primitives.len() == n_tris + spheres.len());
         if let Some(tm) = tri_material {
             assert_eq!(tm.len(), n_tris);
         }
@@ -405,9 +429,12 @@ impl B200Accel {
                                                      mesh.s.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()),
                                                      mesh.uv.as_ref().map_or(std::ptr::null(), |v| v.as_ptr())));
             }
+            if !spheres.is_empty() {
+                check(pb2_scene_add_spheres(scene, spheres.as_ptr(), spheres.len() as u32));
+            }
             check(pb2_scene_build_bvh(scene, max_prims_in_node as c_int, split_method as c_int));
         }
-        B200Accel { scene, mesh, primitives }
+        B200Accel { scene, mesh, primitives, n_spheres: spheres.len() }
     }
 
     pub fn raw(&self) -> *mut pb2_scene {
@@ -606,6 +633,17 @@ impl Primitive for B200Accel {
         unsafe { check(pb2_intersect(self.scene, &ray, 1, &mut hit, &mut b0)) };
         if hit.prim_id == PB2_MISS {
             return false;
+        }
+        if hit.prim_id as usize >= self.mesh.vertex_indices.len() / 3 {
+            // an analytic sphere: the device found the closest primitive; its `GeometricPrimitive(Sphere)` rebuilds the
+            // interaction (sphere.rs:38-93) — one CPU sphere test, the same arithmetic the device ran
+            debug_assert!((hit.prim_id as usize) < self.mesh.vertex_indices.len() / 3 + self.n_spheres);
+            let p = self.primitives.get(hit.prim_id as usize).expect("pass the spheres' GeometricPrimitives to from_mesh_and_spheres");
+            let found = p.intersect(r, si);
+            if found {
+                si.primitive = Some(p.clone());
+            }
+            return found;
         }
         if !self.fill_interaction(r, &hit, b0, si) {
             return false;

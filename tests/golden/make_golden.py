@@ -7,6 +7,7 @@ tests check the CUDA path against the same bytes, so the two cannot drift togeth
 
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
     python tests/golden/make_golden.py --round2 # rewrites tests/golden/path_r02.npz only
+    python tests/golden/make_golden.py --sphere # rewrites tests/golden/sphere_r02.npz only (analytic spheres)
 
 Inputs (meshes, rays, (pixel, sample) pairs) are stored in the fixtures, so no generator has to reproduce them bit for bit.
 """
@@ -106,8 +107,52 @@ def make_round2(scenes, OP):
     print("path_r02.npz", os.path.getsize(os.path.join(HERE, "path_r02.npz")), "bytes")
 
 
+def golden_sphere_scene(scenes):
+    """scenes.scene_spheres() (analytic matte / plastic / glass balls, an ellipsoid, a partial reversed sphere, a spherical area
+    light, the quad light and a point light) without the roughness remap (no libm on the path)."""
+    sc = scenes.scene_spheres()
+    sc["materials"] = [dict(m, remap=False) if m["type"] == "plastic" else m for m in sc["materials"]]
+    return sc
+
+
+def make_sphere(scenes, orc, OP):
+    """tests/golden/sphere_r02.npz: closest hits / any hits of rays against the sphere scene, per-sample radiance and film."""
+    sc = golden_sphere_scene(scenes)
+    ref = OP.Scene(sc, 4)
+    bvh = ref.bvh()
+    rng = np.random.default_rng(4242)
+    cam = dict(GOLDEN_CAMERA, res=(64, 64))
+    rays = np.asarray(orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"]), np.float32).reshape(-1, 8)
+    extra = np.zeros((4096, 8), np.float32)
+    extra[:, 0:3] = rng.uniform(10, 540, (4096, 3))
+    extra[:, 3] = np.where(rng.random(4096) < 0.5, np.inf, rng.uniform(50.0, 400.0, 4096)).astype(np.float32)
+    extra[:, 4:7] = rng.normal(size=(4096, 3))
+    extra[::97, 5] = 0.0
+    rays = np.concatenate([rays, extra])
+    hits, b0 = bvh.intersect(rays, want_b0=True)[:2]
+    out = dict(rays=rays, prim_id=hits["prim_id"], t=hits["t"].view(np.uint32), b1=hits["b1"].view(np.uint32), b2=hits["b2"].view(np.uint32),
+               b0=np.asarray(b0, np.float32).view(np.uint32), occluded=np.asarray(bvh.intersect_p(rays)[0], np.uint8),
+               nodes=np.frombuffer(np.ascontiguousarray(bvh.nodes()).tobytes(), np.uint8), ordered_prims=bvh.ordered_prims())
+    fd = OP.film_desc(GOLDEN_CAMERA["res"])
+    n = 2048
+    xy = np.stack([rng.integers(0, 48, n), rng.integers(0, 48, n)], axis=1).astype(np.int32)
+    s = rng.integers(0, 4, n).astype(np.uint32)
+    out["xy"], out["sample"] = xy, s
+    for strat in ("uniform", "power", "spatial"):
+        L, _ = ref.path_li(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy=strat, **GOLDEN_PATH), xy, s)
+        out["L_" + strat] = L.view(np.uint32)
+    film, _ = ref.render(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", **GOLDEN_PATH), mode=1)
+    out["film_power"] = film.view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "sphere_r02.npz"), **out)
+    print("sphere_r02.npz", os.path.getsize(os.path.join(HERE, "sphere_r02.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--round2" in sys.argv:                       # only path_r02.npz (the round-1 fixtures are left untouched)
+    if "--sphere" in sys.argv:                       # only sphere_r02.npz
+        ge.build()
+        from oracle import oracle_path as _OP
+        make_sphere(ge.load_scenes(), ge.load_oracle(), _OP)
+    elif "--round2" in sys.argv:                       # only path_r02.npz (the round-1 fixtures are left untouched)
         ge.build()
         from oracle import oracle_path as _OP
         make_round2(ge.load_scenes(), _OP)

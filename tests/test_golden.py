@@ -20,7 +20,7 @@ def _mk():
 
 @pytest.fixture(scope="module")
 def G():
-    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path", "path_r02")}
+    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path", "path_r02", "sphere_r02")}
 
 
 @pytest.fixture(scope="module")
@@ -126,3 +126,44 @@ def test_gpu_reproduces_path_fixture(gpu, scenes, G):
     assert nv == tuple(int(v) for v in g["spatial_grid"])
     for v, f, c in zip(g["spatial_voxels"], g["spatial_func"], g["spatial_cdf"]):
         assert np.array_equal(u32(func[v[2], v[1], v[0]]), f) and np.array_equal(u32(cdf[v[2], v[1], v[0]]), c)
+
+
+def _check_sphere_hits(g, hits, b0, occ, nodes, prims):
+    assert np.array_equal(hits["prim_id"], g["prim_id"])
+    assert np.array_equal(u32(hits["t"]), g["t"]) and np.array_equal(u32(hits["b1"]), g["b1"]) and np.array_equal(u32(hits["b2"]), g["b2"])
+    assert np.array_equal(u32(np.asarray(b0, np.float32)), g["b0"])
+    assert np.array_equal(np.asarray(occ, np.uint8), g["occluded"])
+    assert np.array_equal(np.frombuffer(np.ascontiguousarray(nodes).tobytes(), np.uint8), g["nodes"]) and np.array_equal(prims, g["ordered_prims"])
+
+
+def test_oracle_reproduces_sphere_fixture(orc, OP, scenes, G):
+    g, mk = G["sphere_r02"], _mk()
+    sc = mk.golden_sphere_scene(scenes)
+    assert (g["prim_id"][g["prim_id"] != 0xFFFFFFFF] >= len(sc["idx"])).sum() > 1000          # analytic spheres are hit
+    ref = OP.Scene(sc, 4)
+    bvh = ref.bvh()
+    hits, b0 = bvh.intersect(g["rays"], want_b0=True)[:2]
+    _check_sphere_hits(g, hits, b0, bvh.intersect_p(g["rays"])[0], bvh.nodes(), bvh.ordered_prims())
+    fd = OP.film_desc(mk.GOLDEN_CAMERA["res"])
+    for strat in ("uniform", "power", "spatial"):
+        L, _ = ref.path_li(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy=strat, **mk.GOLDEN_PATH), g["xy"], g["sample"])
+        assert np.array_equal(u32(L), g["L_" + strat]), strat
+    film, _ = ref.render(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", **mk.GOLDEN_PATH), mode=1)
+    assert np.array_equal(u32(film), g["film_power"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_sphere_fixture(gpu, scenes, G):
+    g, mk = G["sphere_r02"], _mk()
+    cam = mk.GOLDEN_CAMERA
+    accel = gpu.BVHAccel(gpu.scene_from_dict(mk.golden_sphere_scene(scenes)), max_prims_in_node=4)
+    hits, b0 = accel.intersect(g["rays"], want_b0=True)
+    nodes, prims = accel.export()
+    _check_sphere_hits(g, hits, b0, accel.intersect_p(g["rays"]), nodes, prims)
+    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    for strat in ("uniform", "power", "spatial"):
+        L, _ = gpu.PathIntegrator(accel, camera, light_strategy=strat, **mk.GOLDEN_PATH).li(g["xy"], g["sample"])
+        assert np.array_equal(u32(L), g["L_" + strat]), strat
+    film = gpu.Film(cam["res"])
+    gpu.PathIntegrator(accel, camera, light_strategy="power", **mk.GOLDEN_PATH).render(film)
+    assert np.array_equal(u32(film.read_xyzw()), g["film_power"])

@@ -171,7 +171,7 @@ def test_rust_shim_matches_header(pb2, tmp_path):
     declared = sorted(set(re.findall(r"pub fn (pb2_[a-z0-9_]+)\s*\(", block)))
     assert declared == pb2.header_symbols()
     sizes = dict((t, int(n)) for t, n in re.findall(r"abi_size!\((pb2_[a-z_]+), (\d+)\);", src))
-    assert set(sizes) == {"pb2_ray", "pb2_hit", "pb2_material", "pb2_light", "pb2_camera", "pb2_film_desc", "pb2_path_desc"}
+    assert set(sizes) == {"pb2_ray", "pb2_hit", "pb2_material", "pb2_light", "pb2_sphere", "pb2_camera", "pb2_film_desc", "pb2_path_desc"}
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include "pbrt_b200.h"\nint main(void){' +
                     "".join(f'printf("{t} %zu\\n", sizeof({t}));' for t in sorted(sizes)) + "return 0;}\n")
@@ -179,10 +179,35 @@ def test_rust_shim_matches_header(pb2, tmp_path):
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(prog), "-o", str(exe)])
     c_sizes = dict((l.split()[0], int(l.split()[1])) for l in subprocess.check_output([str(exe)], text=True).splitlines())
     assert c_sizes == sizes
-    py = {"pb2_material": pb2.Material, "pb2_light": pb2.Light, "pb2_camera": pb2.CameraDesc, "pb2_film_desc": pb2.FilmDesc,
+    py = {"pb2_material": pb2.Material, "pb2_light": pb2.Light, "pb2_sphere": pb2.Sphere, "pb2_camera": pb2.CameraDesc, "pb2_film_desc": pb2.FilmDesc,
           "pb2_path_desc": pb2.PathDesc}
     for t, cls in py.items():
         assert C.sizeof(cls) == sizes[t], t
     assert sizes["pb2_ray"] == 32 and pb2.HIT_DTYPE.itemsize == sizes["pb2_hit"]      # rays travel as float32[n, 8]
     # the two trait impls the shim exists for are code, not comments
     assert re.search(r"^impl Primitive for B200Accel", src, flags=re.M) and re.search(r"^impl Integrator for B200PathIntegrator", src, flags=re.M)
+
+
+def test_host_build_with_analytic_spheres_equals_oracle(pb2, scenes):
+    """Spheres join the primitive list after the triangles (ids n_tris + k) with Shape::world_bound = object_to_world applied to the
+    eight corners of the object bound (shape.rs:18-20, transform.rs:569-606): node array and primitive order equal the oracle's."""
+    from oracle import oracle_path as OP
+    sc = scenes.scene_spheres()
+    mine = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4, host_only=True)
+    ref = OP.Scene(sc, 4).bvh()
+    nodes, prims = mine.export()
+    assert len(prims) == len(sc["idx"]) + len(sc["spheres"])
+    assert np.array_equal(prims, ref.ordered_prims())
+    assert _same_nodes(nodes, ref.nodes())
+    assert np.array_equal(mine.world_bound(), ref.world_bound())
+    # error paths: a projective matrix, a zero radius, a sphere after the build
+    L = pb2.lib()
+    bad = pb2.sphere_from_dict(dict(center=(0, 0, 0), radius=1.0))
+    bad.object_to_world[12] = 0.5
+    arr = (pb2.Sphere * 1)(bad)
+    s2 = pb2.scene_from_dict(scenes.scene_c2())
+    assert L.pb2_scene_add_spheres(s2.h, C.cast(arr, C.c_void_p), 1) == -1 and b"affine" in L.pb2_last_error()
+    arr = (pb2.Sphere * 1)(pb2.sphere_from_dict(dict(center=(0, 0, 0), radius=0.0)))
+    assert L.pb2_scene_add_spheres(s2.h, C.cast(arr, C.c_void_p), 1) == -1 and b"radius" in L.pb2_last_error()
+    arr = (pb2.Sphere * 1)(pb2.sphere_from_dict(dict(center=(0, 0, 0), radius=1.0)))
+    assert L.pb2_scene_add_spheres(mine.scene.h, C.cast(arr, C.c_void_p), 1) == -3
