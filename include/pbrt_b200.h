@@ -91,6 +91,17 @@ typedef struct pb2_sphere {
     uint32_t material;          /* index into the scene's materials (ignored for pure ray casting) */
 } pb2_sphere;
 
+/* src/media/homogeneous.rs:20-28 HomogeneousMedium::new(sigma_a, sigma_s, g): absorption and scattering coefficients per RGB
+ * channel (per unit length of the scene) and the Henyey-Greenstein asymmetry of its phase function (src/core/medium.rs:34-87). */
+typedef struct pb2_medium {
+    float sigma_a[3];
+    float sigma_s[3];
+    float g;
+} pb2_medium;
+/* tri_material[i] / pb2_sphere.material of a surface that has no material (GeometricPrimitive { material: None }): it only
+ * separates two media, rays pass through it (volpath.rs:127-131).  VolPathIntegrator only. */
+#define PB2_NO_MATERIAL 0xFFFFFFFFu
+
 /* src/cameras/perspective.rs:34-82 PerspectiveCamera + Transform::look_at. */
 typedef struct pb2_camera {
     float pos[3];
@@ -137,6 +148,12 @@ enum { PB2_LIGHTS_UNIFORM = 0, PB2_LIGHTS_POWER = 1, PB2_LIGHTS_SPATIAL = 2 };
  * The reference leaves sample_dimension as todo!() (sobol.rs:56-58) and its sobol_interval_to_index cannot terminate
  * (lowdiscrepancy.rs:529-534); both follow pbrt-v3 here. */
 enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1, PB2_SAMPLER_STRATIFIED = 2, PB2_SAMPLER_ZEROTWO = 3, PB2_SAMPLER_SOBOL = 4 };
+/* PB2_INTEGRATOR_PATH: PathIntegrator (src/integrators/path.rs), the wavefront pipeline.  PB2_INTEGRATOR_VOLPATH:
+ * VolPathIntegrator (src/integrators/volpath.rs:60-244) over HomogeneousMedium — medium sampling, Henyey-Greenstein phase
+ * vertices, next-event estimation with transmittance (VisibilityTester::tr, src/core/light.rs:137-160) and MIS through
+ * Scene::intersect_tr (src/core/scene.rs:48-71), one thread per camera sample (k_volpath); samplers: random, stratified, (0,2)
+ * (the number of dimensions a volumetric path draws is unbounded, which the 1000 / 1024-dimension Halton / Sobol' tables are not). */
+enum { PB2_INTEGRATOR_PATH = 0, PB2_INTEGRATOR_VOLPATH = 1 };
 /* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
 typedef struct pb2_path_desc {
     int32_t max_depth;
@@ -149,6 +166,7 @@ typedef struct pb2_path_desc {
     int32_t n_sampled_dimensions; /* stratified, (0,2): PixelSampler::new (sampler.rs:268); pbrt's default is 4 */
     int32_t x_samples, y_samples; /* stratified: StratifiedSampler::new (stratified.rs:23-39); spp must equal x_samples * y_samples */
     int32_t jitter;             /* stratified: jitter_samples */
+    int32_t integrator;         /* PB2_INTEGRATOR_* */
 } pb2_path_desc;
 
 typedef struct pb2_scene pb2_scene;
@@ -189,6 +207,13 @@ int pb2_scene_set_shading_geometry(pb2_scene* scene, const float* normals, const
  * hit on a sphere reports b1 = u = phi / phi_max and b2 = v = (theta - theta_min) / (theta_max - theta_min) (sphere.rs:49-52);
  * pb2_intersect's optional b0 is 0 there. */
 int pb2_scene_add_spheres(pb2_scene* scene, const pb2_sphere* spheres, uint32_t n);
+/* Participating media.  media[n_media]: the scene's HomogeneousMedium list.  prim_inside / prim_outside: per primitive
+ * (triangles, then spheres) the MediumInterface of its GeometricPrimitive (src/core/primitive.rs:33-38, src/core/medium.rs:
+ * 90-115) as indices into media, -1 = no medium; either may be NULL (= all -1).  A primitive whose two sides are equal is not a
+ * medium transition: a ray that hits it keeps its own medium on both sides (primitive.rs:72-76).  camera_medium: the medium
+ * camera rays start in (src/cameras/perspective.rs:109), -1 = none.  Call before pb2_scene_build_bvh. */
+int pb2_scene_set_media(pb2_scene* scene, const pb2_medium* media, uint32_t n_media, const int32_t* prim_inside,
+                        const int32_t* prim_outside, int32_t camera_medium);
 int pb2_scene_destroy(pb2_scene* scene);
 /* Host SAH build (bvh.rs:273-473 recursive_build, :774-811 flatten_bvh_tree), repack to the 64-byte child-pair
  * node layout + 48-byte triangles, upload to the current device.  split_method (bvh.rs:199-204): 0 = SplitMethod::SAH,

@@ -79,6 +79,11 @@ def _bind_path(L):
     L.orc_acos.argtypes = [C.c_float]
     L.orc_atan2.restype = C.c_float
     L.orc_atan2.argtypes = [C.c_float, C.c_float]
+    L.orc_scene_set_media.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_int32]
+    L.orc_exp.restype = C.c_float
+    L.orc_exp.argtypes = [C.c_float]
+    L.orc_log.restype = C.c_float
+    L.orc_log.argtypes = [C.c_float]
     L.orc_scene_free.argtypes = [vp]
     L.orc_scene_bvh.restype = vp
     L.orc_scene_bvh.argtypes = [vp]

@@ -102,7 +102,15 @@ struct PathDesc {
     int32_t n_sampled_dimensions;   // PixelSampler::new (sampler.rs:268-284): tabulated 1D and 2D dimensions (kinds 2, 3)
     int32_t x_samples, y_samples;   // StratifiedSampler::new (stratified.rs:23-39); spp == x_samples * y_samples
     int32_t jitter;
+    int32_t integrator;       // 0 = PathIntegrator (integrators/path.rs), 1 = VolPathIntegrator (integrators/volpath.rs)
 };
+
+// src/media/homogeneous.rs HomogeneousMedium::new(sigma_a, sigma_s, g)
+struct MediumDesc {
+    Float sigma_a[3], sigma_s[3];
+    Float g;
+};
+static constexpr uint32_t kNoMaterial = 0xFFFFFFFFu;   // GeometricPrimitive { material: None }: a surface that only separates media
 
 // ---------------------------------------------------------------- sampling.rs:68-154 Distribution1D (D29 FIX, D57 KEEP, D58)
 struct Distribution1D {
@@ -628,6 +636,20 @@ public:
     std::vector<int32_t> tri_light;
     Distribution1D light_distrib;
     std::vector<V3> vn, vs;                  // TriangleMesh::n / ::s (triangle.rs:19-20), one per vertex, empty = absent
+    // participating media (media/homogeneous.rs) and each primitive's MediumInterface {inside, outside} as indices (-1 = none);
+    // camera_medium = the medium camera rays start in (perspective.rs:109)
+    std::vector<MediumDesc> media;
+    std::vector<int32_t> prim_inside, prim_outside;
+    int32_t camera_medium = -1;
+    void set_media(const MediumDesc* m, uint32_t n, const int32_t* inside, const int32_t* outside, int32_t cam_medium) {
+        media.assign(m, m + n);
+        const size_t np = tri_material.size();
+        prim_inside.assign(np, -1);
+        prim_outside.assign(np, -1);
+        if (inside) prim_inside.assign(inside, inside + np);
+        if (outside) prim_outside.assign(outside, outside + np);
+        camera_medium = cam_medium;
+    }
 
     // TriangleMesh's optional per-vertex normals, tangents and UVs (world space, as given); call after init()
     void set_shading_geometry(const Float* normals, const Float* tangents, const Float* uv) {
@@ -663,6 +685,8 @@ public:
         for (uint32_t i = 0; i < n_spheres; ++i) tri_material.push_back(sph[i].material);
         const uint64_t n_prims = nt + n_spheres;
         materials.resize(n_mats);
+        prim_inside.assign(n_prims, -1);
+        prim_outside.assign(n_prims, -1);
         for (uint32_t i = 0; i < n_mats; ++i) {
             materials[i].d = mats[i];
             materials[i].alpha = mats[i].remap_roughness ? roughness_to_alpha(mats[i].roughness) : mats[i].roughness;
@@ -1378,6 +1402,351 @@ inline RGB path_li(const Scene& scene, Ray ray, Sampler& s, int max_depth, Float
     return l;
 }
 
+// ---------------------------------------------------------------- src/integrators/volpath.rs + src/media/homogeneous.rs
+// VolPathIntegrator over HomogeneousMedium.  KEEP/FIX ledger (pbrt-v3 where the Rust code cannot work):
+//   D69 FIX  interaction.rs:132-153  spawn_ray / spawn_ray_to hand the new ray `None` as its medium          -> GetMedium(d): outside if
+//                                    dot(d, n) > 0 else inside (pbrt-v3 Interaction::GetMedium)
+//   D70 FIX  volpath.rs:127-131      `bounces -= 1; continue` skips the loop's `bounces += 1` (and underflows usize at 0)
+//                                    -> a material-less surface does not count as a bounce (pbrt-v3's for-loop)
+//   D71 FIX  homogeneous.rs:36-38    tr: `.max(Float::MAX)`                                                  -> min
+//   D72 FIX  homogeneous.rs:45       sample: t = -(dist / |d|).min(t_max)                                    -> min(dist / |d|, t_max)
+//   D73 FIX  homogeneous.rs:56       sample: tr = -sigma_t * min(t, MAX) * |d| without the exponential      -> exp(..)
+//   D74 FIX  light.rs:151 / scene.rs:62  the VisibilityTester / intersect_tr loops continue with rays that lost their medium
+//                                    (D69) and t_max                                                         -> pbrt-v3
+//   KEEP     volpath.rs:96-113       the phase function is sampled (sampler.get_2d) BEFORE uniform_sample_one_light draws its
+//                                    three values (pbrt-v3 draws them in the other order)
+//   KEEP     volpath.rs:236          Russian roulette q = max(1 - max_component, 0.05) (path.rs has min: D27)
+//   KEEP     medium.rs:75-87         HenyeyGreenstein::sample_p as written (= pbrt-v3)
+// exp / ln: f32::exp / f32::ln are platform libm; the numerics contract fixes Cephes expf / logf with every operation one
+// rounded f32 op (exp_c, log_c), shared with the kernels like sin / cos / acos / atan2.
+inline Float exp_c(Float x) {
+    if (x > 88.0f) return kInfinity;
+    if (x < -87.0f) return 0.0f;                               // below the normal range: flushed (both sides)
+    Float z = std::floor(1.44269504088896341f * x + 0.5f);
+    x = x - z * 0.693359375f;
+    x = x - z * -2.12194440e-4f;
+    const int n = (int)z;
+    z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    return z * bits_to_float((uint32_t)(n + 127) << 23);       // n in [-126, 127] for |x| <= 88
+}
+inline Float log_c(Float x) {                                   // x > 0, normal
+    if (x <= 0.0f) return -kInfinity;
+    const uint32_t u = float_to_bits(x);
+    int e = (int)(u >> 23) - 126;
+    Float m = bits_to_float((u & 0x007FFFFFu) | 0x3F000000u);  // frexp: m in [0.5, 1)
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; }
+    else m = m - 1.0f;
+    const Float z = m * m;
+    Float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m - 1.6668057665e-1f) * m +
+                 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    const Float fe = (Float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y + -0.5f * z;
+    Float r = m + y;
+    r = r + 0.693359375f * fe;
+    return r;
+}
+
+// media/homogeneous.rs:36-38 (D71)
+inline RGB medium_tr(const MediumDesc& m, Float t_max, V3 d) {
+    const Float s = fmin_(t_max * length(d), 3.402823466e+38f);
+    return RGB{exp_c(-((m.sigma_s[0] + m.sigma_a[0]) * s)), exp_c(-((m.sigma_s[1] + m.sigma_a[1]) * s)), exp_c(-((m.sigma_s[2] + m.sigma_a[2]) * s))};
+}
+// medium.rs:34-37
+inline Float phase_hg(Float cos_theta, Float g) {
+    const Float denom = 1.0f + g * g + 2.0f * g * cos_theta;
+    return (1.0f / kPi / 4.0f) * (1.0f - g * g) / (denom * std::sqrt(denom));        // INV_4_PI = INV_PI / 4 (pbrt.rs:19-21)
+}
+// medium.rs:71-87
+inline Float hg_sample_p(Float g, V3 wo, V3* wi, Float u0, Float u1) {
+    Float cos_theta;
+    if (std::fabs(g) < 1e-3f) cos_theta = 1.0f - 2.0f * u0;
+    else {
+        const Float sqr_term = (1.0f - g * g) / (1.0f + g - 2.0f * g * u0);
+        cos_theta = -(1.0f + g * g - sqr_term * sqr_term) / (2.0f * g);
+    }
+    const Float sin_theta = std::sqrt(fmax_(1.0f - cos_theta * cos_theta, 0.0f));
+    const Float phi = 2.0f * kPi * u1;
+    V3 v1, v2;
+    coordinate_system(wo, &v1, &v2);
+    Float sp, cp;
+    sincos_contract(phi, &sp, &cp);
+    *wi = (v1 * sin_theta * cp + v2 * sin_theta * sp) + wo * cos_theta;                 // geometry.rs:1156-1165
+    return phase_hg(cos_theta, g);
+}
+// media/homogeneous.rs:40-74 (D72, D73): returns the throughput factor; *sampled = a medium interaction at *p_out
+inline RGB medium_sample(const MediumDesc& m, const Ray& ray, Sampler& s, bool* sampled, V3* p_out) {
+    const Float sig_t[3] = {m.sigma_s[0] + m.sigma_a[0], m.sigma_s[1] + m.sigma_a[1], m.sigma_s[2] + m.sigma_a[2]};
+    const Float uc = s.get_1d() * 3.0f;
+    const int channel = std::min(std::isnan(uc) || uc <= 0.0f ? 0 : (int)uc, 2);
+    const Float dist = -log_c(1.0f - s.get_1d()) / sig_t[channel];
+    const Float len = length(ray.d);
+    const Float t = fmin_(dist / len, ray.t_max);
+    *sampled = t < ray.t_max;
+    if (*sampled) *p_out = ray.o + ray.d * t;
+    const Float tt = fmin_(t, 3.402823466e+38f);
+    const RGB tr{exp_c(-sig_t[0] * tt * len), exp_c(-sig_t[1] * tt * len), exp_c(-sig_t[2] * tt * len)};
+    const RGB density = *sampled ? RGB{sig_t[0] * tr.r, sig_t[1] * tr.g, sig_t[2] * tr.b} : tr;
+    Float pdf = 0.0f;
+    pdf += density.r; pdf += density.g; pdf += density.b;
+    pdf *= 1.0f / 3.0f;
+    if (pdf == 0.0f) pdf = 1.0f;
+    return *sampled ? (tr * RGB{m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]}) / pdf : tr / pdf;
+}
+
+// The scattering point handed to uniform_sample_one_light: a surface (bsdf != null) or a medium interaction (phase g).
+struct VolVertex {
+    V3 p, error, n, wo;
+    const BSDF* bsdf;       // null: medium interaction
+    Float g;
+    int med_inside, med_outside;                                // MediumInterface of the interaction
+    int medium_towards(V3 w) const { return dot(w, n) > 0.0f ? med_outside : med_inside; }       // D69
+};
+// primitive.rs:72-76: a hit takes the primitive's interface when that is a transition, else the ray's medium on both sides
+inline void hit_interface(const Scene& scene, uint32_t prim, int ray_medium, int* inside, int* outside) {
+    const int pi = scene.prim_inside[prim], po = scene.prim_outside[prim];
+    if (pi != po) { *inside = pi; *outside = po; }
+    else { *inside = ray_medium; *outside = ray_medium; }
+}
+// VisibilityTester::tr (light.rs:137-160, D74): transmittance from `from` towards the point (p1, p1_err, p1_n); black when a
+// surface with a material is in the way
+inline RGB visibility_tr(const Scene& scene, const VolVertex& from, V3 p1, V3 p1_err, V3 p1_n) {
+    Interaction cur{from.p, from.error, from.n};
+    int cur_in = from.med_inside, cur_out = from.med_outside;
+    RGB tr = rgb(1.0f);
+    for (;;) {
+        const V3 origin = offset_ray_origin(cur.p, cur.error, cur.n, p1 - cur.p);          // spawn_ray_to(&BaseInteraction), interaction.rs:146-153
+        const V3 target = offset_ray_origin(p1, p1_err, p1_n, origin - p1);
+        Ray ray{origin, 1.0f - kShadowEpsilon, target - origin, 0.0f};
+        const int medium = dot(ray.d, cur.n) > 0.0f ? cur_out : cur_in;
+        SurfaceInteraction isect;
+        PathCounters* pc = tl_path_counters;
+        tl_ray_kind = 1;
+        const bool hit = scene.intersect(ray, &isect);
+        tl_ray_kind = 0;
+        (void)pc;
+        if (hit && scene.tri_material[isect.prim] != kNoMaterial) return rgb(0);
+        if (medium >= 0) tr = tr * medium_tr(scene.media[medium], ray.t_max, ray.d);
+        if (!hit) break;
+        hit_interface(scene, isect.prim, medium, &cur_in, &cur_out);
+        cur = Interaction{isect.p, isect.error, isect.n};
+    }
+    return tr;
+}
+// Scene::intersect_tr (scene.rs:48-71, D74)
+inline bool intersect_tr(const Scene& scene, Ray ray, int medium, SurfaceInteraction* isect, RGB* tr) {
+    *tr = rgb(1.0f);
+    for (;;) {
+        tl_ray_kind = 2;
+        const bool hit = scene.intersect(ray, isect);
+        tl_ray_kind = 0;
+        if (medium >= 0) *tr = *tr * medium_tr(scene.media[medium], ray.t_max, ray.d);
+        if (!hit) return false;
+        if (scene.tri_material[isect->prim] != kNoMaterial) return true;
+        int in, out;
+        hit_interface(scene, isect->prim, medium, &in, &out);
+        const V3 d = ray.d;
+        ray = spawn_ray(Interaction{isect->p, isect->error, isect->n}, d);
+        medium = dot(d, isect->n) > 0.0f ? out : in;
+    }
+}
+
+// estimate_direct (integrator.rs:136-266) with handle_media = true, for a surface or a medium interaction
+inline RGB estimate_direct_vol(const Scene& scene, const VolVertex& it, Float us0, Float us1, const LightRt& light, uint32_t light_index, Float ul0,
+                               Float ul1) {
+    const uint8_t flags = BSDF_ALL & ~BSDF_SPECULAR;
+    RGB ld = rgb(0);
+    V3 wi{0, 0, 0};
+    Float light_pdf = 0.0f, scattering_pdf = 0.0f;
+    RGB li = rgb(0);
+    V3 p1{0, 0, 0}, p1_err{0, 0, 0}, p1_n{0, 0, 0};
+    // ---- Light::sample_li (as in estimate_direct above) ----
+    if (light.is_delta()) {
+        V3 pl{light.d.p[0], light.d.p[1], light.d.p[2]};
+        light_pdf = 1.0f;
+        if (light.d.type == LIGHT_DISTANT) {
+            wi = light.w_light;
+            pl = it.p + light.w_light * (2.0f * light.world_radius);
+            li = light.l();
+        } else {
+            wi = normalize(pl - it.p);
+            if (light.d.type == LIGHT_SPOT) li = light.l() * light.falloff(-wi) / length_squared(pl - it.p);
+            else li = light.l() / length_squared(pl - it.p);
+        }
+        p1 = pl;
+    } else {
+        V3 ps, pe, ns;
+        Float pdf;
+        if (light.sphere) light.sphere->sample2(it.p, it.error, it.n, ul0, ul1, &ps, &pe, &ns, &pdf);
+        else {
+            Float su0 = std::sqrt(ul0);
+            Float b0 = 1.0f - su0, b1 = ul1 * su0;
+            ps = (light.p0 * b0 + light.p1 * b1) + light.p2 * ((1.0f - b0) - b1);
+            ns = normalize(cross(light.p1 - light.p0, light.p2 - light.p0));
+            if (light.has_n) ns = faceforward(ns, (light.n0 * b0 + light.n1 * b1) + light.n2 * ((1.0f - b0) - b1));
+            pe = ((vabs(light.p0 * b0) + vabs(light.p1 * b1)) + vabs(light.p2 * ((1.0f - b0) - b1))) * gamma(6.0f);
+            pdf = 1.0f / light.area;
+            V3 w = ps - it.p;
+            if (length_squared(w) == 0.0f) pdf = 0.0f;
+            else {
+                w = normalize(w);
+                pdf *= length_squared(it.p - ps) / std::fabs(dot(ns, -w));
+                if (std::isinf(pdf)) pdf = 0.0f;
+            }
+        }
+        light_pdf = pdf;
+        if (pdf == 0.0f || length_squared(ps - it.p) == 0.0f) { light_pdf = 0.0f; li = rgb(0); }
+        else {
+            wi = normalize(ps - it.p);
+            li = (light.d.two_sided || dot(ns, -wi) > 0.0f) ? light.l() : rgb(0);
+            p1 = ps; p1_err = pe; p1_n = ns;
+        }
+    }
+    if (light_pdf > 0.0f && !is_black(li)) {
+        RGB f;
+        if (it.bsdf) {
+            scattering_pdf = it.bsdf->pdf(it.wo, wi, flags);
+            f = it.bsdf->f(it.wo, wi, flags) * std::fabs(dot(wi, it.bsdf->ns));
+        } else {
+            const Float p = phase_hg(dot(it.wo, wi), it.g);
+            scattering_pdf = p;
+            f = rgb(p);
+        }
+        if (!is_black(f)) {
+            if (tl_path_counters) tl_path_counters->rays[1]++;
+            li = li * visibility_tr(scene, it, p1, p1_err, p1_n);
+            if (!is_black(li)) {
+                if (light.is_delta()) ld = ld + li * f / light_pdf;
+                else ld = ld + li * f * power_heuristic(light_pdf, scattering_pdf) / light_pdf;
+            }
+        }
+    }
+    if (!light.is_delta()) {
+        bool sampled_specular = false;
+        RGB f;
+        if (it.bsdf) {
+            uint8_t sampled = 0;
+            f = it.bsdf->sample_f(it.wo, &wi, us0, us1, &scattering_pdf, flags, &sampled);
+            f = f * std::fabs(dot(wi, it.bsdf->ns));
+            sampled_specular = (sampled & BSDF_SPECULAR) != 0;
+        } else {
+            const Float p = hg_sample_p(it.g, it.wo, &wi, us0, us1);
+            scattering_pdf = p;
+            f = rgb(p);
+        }
+        if (!is_black(f) && scattering_pdf > 0.0f) {
+            Float weight = 1.0f;
+            Interaction base{it.p, it.error, it.n};
+            if (!sampled_specular) {
+                if (light.sphere) light_pdf = light.sphere->pdf2(it.p, it.error, it.n, wi);
+                else {
+                    Ray r = spawn_ray(base, wi);
+                    TriHit th = triangle_intersect_test(light.p0, light.p1, light.p2, r);
+                    V3 du, dv;
+                    if (!th.hit || !triangle_frame(light.p0, light.p1, light.p2, &du, &dv, light.has_uv ? light.uv : nullptr)) return ld;
+                    Interaction li_it = triangle_interaction(light.p0, light.p1, light.p2, th.b0, th.b1, th.b2);
+                    Float lp = length_squared(it.p - li_it.p) / (std::fabs(dot(li_it.n, -wi)) * light.area);
+                    if (std::isinf(lp)) lp = 0.0f;
+                    light_pdf = lp;
+                }
+                if (light_pdf == 0.0f) return ld;
+                weight = power_heuristic(scattering_pdf, light_pdf);
+            }
+            Ray ray = spawn_ray(base, wi);
+            SurfaceInteraction light_isect;
+            RGB tr;
+            RGB lmis = rgb(0);
+            if (intersect_tr(scene, ray, it.medium_towards(wi), &light_isect, &tr)) {
+                if (scene.tri_light[light_isect.prim] == (int32_t)light_index) lmis = scene.le(light_isect, -wi);
+            }
+            if (!is_black(lmis)) ld = ld + lmis * f * tr * weight / scattering_pdf;
+        }
+    }
+    return ld;
+}
+inline RGB uniform_sample_one_light_vol(const Scene& scene, const VolVertex& it, Sampler& s) {
+    if (scene.lights.empty()) return rgb(0);
+    Float light_pdf;
+    size_t num = scene.lookup(it.p).sample_discrete(s.get_1d(), &light_pdf);
+    if (light_pdf == 0.0f) return rgb(0);
+    Float ul0, ul1, us0, us1;
+    s.get_2d(&ul0, &ul1);
+    s.get_2d(&us0, &us1);
+    return estimate_direct_vol(scene, it, us0, us1, scene.lights[num], (uint32_t)num, ul0, ul1) / light_pdf;
+}
+
+// volpath.rs:60-244 VolPathIntegrator::li (BSSRDF branch dead: no subsurface material exists)
+inline RGB volpath_li(const Scene& scene, Ray ray, int ray_medium, Sampler& s, int max_depth, Float rr_threshold) {
+    RGB l = rgb(0), beta = rgb(1);
+    bool specular_bounce = false;
+    int bounces = 0;
+    Float eta_scale = 1.0f;
+    if (tl_path_counters) tl_path_counters->camera_samples++;
+    for (;;) {
+        SurfaceInteraction isect;
+        const V3 o0 = ray.o;
+        (void)o0;
+        bool found = scene.intersect(ray, &isect);
+        bool in_medium = false;
+        V3 mp{0, 0, 0};
+        if (ray_medium >= 0) beta = beta * medium_sample(scene.media[ray_medium], ray, s, &in_medium, &mp);
+        if (is_black(beta)) break;
+        if (in_medium) {
+            if (bounces >= max_depth) break;
+            if (tl_path_counters) tl_path_counters->vertices++;
+            const MediumDesc& m = scene.media[ray_medium];
+            const V3 wo = -ray.d;
+            V3 wi{0, 0, 0};
+            Float u0, u1;
+            s.get_2d(&u0, &u1);
+            hg_sample_p(m.g, wo, &wi, u0, u1);                                                  // KEEP: sampled before the light
+            VolVertex v{mp, V3{0, 0, 0}, V3{0, 0, 0}, wo, nullptr, m.g, ray_medium, ray_medium};
+            ray = Ray{mp, kInfinity, wi, 0.0f};                                                 // mi.spawn_ray(wi): n = 0, no offset; same medium
+            specular_bounce = false;
+            l = l + beta * uniform_sample_one_light_vol(scene, v, s);
+        } else {
+            if (bounces == 0 || specular_bounce)
+                if (found) l = l + beta * scene.le(isect, -ray.d);
+            if (!found || bounces >= max_depth) break;
+            int in, out;
+            hit_interface(scene, isect.prim, ray_medium, &in, &out);
+            if (scene.tri_material[isect.prim] == kNoMaterial) {                                // volpath.rs:127-131 (D70)
+                const V3 d = ray.d;
+                ray = spawn_ray(Interaction{isect.p, isect.error, isect.n}, d);
+                ray_medium = dot(d, isect.n) > 0.0f ? out : in;
+                continue;
+            }
+            if (tl_path_counters) tl_path_counters->vertices++;
+            BSDF bsdf = scene.make_bsdf(isect);
+            VolVertex v{isect.p, isect.error, isect.n, isect.wo, &bsdf, 0.0f, in, out};
+            l = l + beta * uniform_sample_one_light_vol(scene, v, s);
+            V3 wo = -ray.d, wi{0, 0, 0};
+            Float pdf = 0.0f, u0, u1;
+            uint8_t flags = 0;
+            s.get_2d(&u0, &u1);
+            RGB f = bsdf.sample_f(wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
+            if (is_black(f) || pdf == 0.0f) break;
+            beta = beta * (f * (std::fabs(dot(wi, bsdf.ns)) / pdf));
+            specular_bounce = (flags & BSDF_SPECULAR) != 0;
+            if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+                Float eta = bsdf.eta;
+                eta_scale *= (dot(wo, isect.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta);
+            }
+            ray = spawn_ray(Interaction{isect.p, isect.error, isect.n}, wi);
+            ray_medium = v.medium_towards(wi);
+        }
+        RGB rr_beta = beta * eta_scale;
+        if (max_component_value(rr_beta) < rr_threshold && bounces > 3) {
+            Float q = fmax_(1.0f - max_component_value(rr_beta), 0.05f);                        // volpath.rs:236
+            if (s.get_1d() < q) break;
+            beta = beta / (1.0f - q);
+        }
+        bounces += 1;
+    }
+    return l;
+}
+
 // ---------------------------------------------------------------- film.rs
 struct Film {
     FilmDesc d;
@@ -1543,7 +1912,8 @@ inline double render(const Scene& scene, const CameraDesc& cd, const FilmDesc& f
                         (void)ut;
                         Float pfx = (Float)x + u0, pfy = (Float)y + u1;
                         Ray ray = cam.generate_ray(pfx, pfy, l0, l1);
-                        RGB L = path_li(scene, ray, smp, pd.max_depth, pd.rr_threshold);
+                        RGB L = pd.integrator == 1 ? volpath_li(scene, ray, scene.camera_medium, smp, pd.max_depth, pd.rr_threshold)
+                                                   : path_li(scene, ray, smp, pd.max_depth, pd.rr_threshold);
                         if (has_nans(L) || y_value(L) < -1e-5f || std::isinf(y_value(L))) L = rgb(0);   // D22 FIX
                         L = film.clamp_luminance(L);
                         film.footprint(pfx, pfy, [&](int px, int py, Float fw) {

@@ -35,7 +35,24 @@ class FilmDesc(C.Structure):
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
                 ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32),
-                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
+                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32),
+                ("integrator", C.c_int32)]
+
+
+class Medium(C.Structure):
+    """HomogeneousMedium::new(sigma_a, sigma_s, g) (src/media/homogeneous.rs:20-28)"""
+    _fields_ = [("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("g", C.c_float)]
+
+
+NO_MATERIAL = 0xFFFFFFFF       # tri_material / sphere material of a surface that only separates media (GeometricPrimitive.material = None)
+
+
+def medium(d):
+    m = Medium()
+    m.sigma_a[:] = d["sigma_a"]
+    m.sigma_s[:] = d["sigma_s"]
+    m.g = d.get("g", 0.0)
+    return m
 
 
 class Sphere(C.Structure):
@@ -149,8 +166,9 @@ def film_shape(film):
 
 
 def path_desc(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sample_begin=0, sample_end=None, sampler="random",
-              n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True):
+              n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True, integrator="path"):
     p = PathDesc()
+    p.integrator = {"path": 0, "volpath": 1}[integrator]
     p.max_depth = max_depth
     p.rr_threshold = rr_threshold
     p.light_strategy = _STRAT[light_strategy]
@@ -216,6 +234,16 @@ class Scene:
         self.h = L.orc_scene_create2(_p(self.verts), len(self.verts), _p(self.idx), len(self.idx), _p(tm),
                                      C.cast(mats, C.c_void_p), len(sc["materials"]), C.cast(lts, C.c_void_p),
                                      len(sc["lights"]), max_prims_in_node, C.cast(sphs, C.c_void_p), len(sph))
+        # participating media: sc["media"] = [dict(sigma_a, sigma_s, g)], sc["prim_inside"] / sc["prim_outside"] = medium index per
+        # primitive (triangles, then spheres; -1 = none), sc["camera_medium"]
+        if sc.get("media"):
+            n_prims = len(self.idx) + len(sph)
+            med = (Medium * len(sc["media"]))(*[medium(d) for d in sc["media"]])
+            self._ins = np.ascontiguousarray(sc.get("prim_inside", np.full(n_prims, -1)), dtype=np.int32)
+            self._outs = np.ascontiguousarray(sc.get("prim_outside", np.full(n_prims, -1)), dtype=np.int32)
+            assert len(self._ins) == n_prims and len(self._outs) == n_prims
+            L.orc_scene_set_media(C.c_void_p(self.h), C.cast(med, C.c_void_p), len(sc["media"]), _p(self._ins), _p(self._outs),
+                                  int(sc.get("camera_medium", -1)))
         # TriangleMesh's optional per-vertex normals / tangents / UVs (triangle.rs:17-26)
         self._sg = [None if sc.get(k) is None else np.ascontiguousarray(sc[k], dtype=np.float32) for k in ("normals", "tangents", "uvs")]
         if any(a is not None for a in self._sg):

@@ -80,7 +80,24 @@ class FilmDesc(C.Structure):
 class PathDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
                 ("spp", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("sampler", C.c_int32),
-                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32)]
+                ("n_sampled_dimensions", C.c_int32), ("x_samples", C.c_int32), ("y_samples", C.c_int32), ("jitter", C.c_int32),
+                ("integrator", C.c_int32)]
+
+
+class Medium(C.Structure):
+    """pb2_medium: HomogeneousMedium::new(sigma_a, sigma_s, g) (src/media/homogeneous.rs:20-28)."""
+    _fields_ = [("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("g", C.c_float)]
+
+
+NO_MATERIAL = 0xFFFFFFFF       # PB2_NO_MATERIAL: a surface that only separates two media
+
+
+def medium_from_dict(d):
+    m = Medium()
+    m.sigma_a[:] = d["sigma_a"]
+    m.sigma_s[:] = d["sigma_s"]
+    m.g = d.get("g", 0.0)
+    return m
 
 
 _SAMPLER = {"random": 0, "halton": 1, "stratified": 2, "zerotwo": 3, "sobol": 4}
@@ -209,6 +226,7 @@ def lib():
         "pb2_set_trace_tuning": [i32, i32, i32, i32],
         "pb2_scene_create": [vp, u64, vp, u64, vp, vp, u32, vp, u32, vp], "pb2_scene_destroy": [vp],
         "pb2_scene_set_shading_geometry": [vp, vp, vp, vp], "pb2_scene_add_spheres": [vp, vp, u32],
+        "pb2_scene_set_media": [vp, vp, u32, vp, vp, C.c_int32],
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
         "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
@@ -301,7 +319,8 @@ class Scene:
     """Triangle list + materials + lights handed to BVHAccel::new (pb2_scene_create); normals / tangents / uvs are
     TriangleMesh's optional per-vertex arrays (src/shapes/triangle.rs:17-26)."""
 
-    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None, normals=None, tangents=None, uvs=None, spheres=None):
+    def __init__(self, verts, idx, tri_material=None, materials=None, lights=None, normals=None, tangents=None, uvs=None, spheres=None,
+                 media=None, prim_inside=None, prim_outside=None, camera_medium=-1):
         verts = _f32(verts).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         self.n_tris = len(idx)
@@ -321,6 +340,11 @@ class Scene:
         if spheres:                       # analytic spheres: primitive ids n_tris .. n_tris + n_spheres - 1 (pb2_scene_add_spheres)
             arr = (Sphere * len(spheres))(*spheres)
             check(lib().pb2_scene_add_spheres(self.h, C.cast(arr, C.c_void_p), len(spheres)))
+        if media:                         # HomogeneousMedium list + every primitive's MediumInterface (pb2_scene_set_media)
+            arr = (Medium * len(media))(*media)
+            ins = None if prim_inside is None else np.ascontiguousarray(prim_inside, dtype=np.int32)
+            outs = None if prim_outside is None else np.ascontiguousarray(prim_outside, dtype=np.int32)
+            check(lib().pb2_scene_set_media(self.h, C.cast(arr, C.c_void_p), len(media), _p(ins), _p(outs), int(camera_medium)))
 
     def destroy(self):
         if self.h:
@@ -473,7 +497,9 @@ def scene_from_dict(sc):
     """Scene from the plain-dict description the generators in scenes.py return."""
     return Scene(sc["verts"], sc["idx"], sc["tri_material"], [material_from_dict(m) for m in sc["materials"]],
                  [light_from_dict(l) for l in sc["lights"]], normals=sc.get("normals"), tangents=sc.get("tangents"), uvs=sc.get("uvs"),
-                 spheres=[sphere_from_dict(d) for d in sc.get("spheres") or []])
+                 spheres=[sphere_from_dict(d) for d in sc.get("spheres") or []],
+                 media=[medium_from_dict(d) for d in sc.get("media") or []], prim_inside=sc.get("prim_inside"),
+                 prim_outside=sc.get("prim_outside"), camera_medium=sc.get("camera_medium", -1))
 
 
 class Film:
@@ -564,7 +590,8 @@ class PathIntegrator:
     "sobol" (SobolSampler::new(spp, sample_bounds), src/samplers/sobol.rs; spp rounded up likewise)."""
 
     def __init__(self, accel, camera, max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=1, sampler="random",
-                 n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True):
+                 n_sampled_dimensions=4, x_samples=0, y_samples=0, jitter=True, integrator="path"):
+        """integrator: "path" = PathIntegrator (wavefront), "volpath" = VolPathIntegrator (src/integrators/volpath.rs; media)."""
         if sampler in ("zerotwo", "sobol"):
             spp = 1 << max(0, int(spp) - 1).bit_length()             # round_up_pow2_i64, zerotwosequence.rs:21, sobol.rs:22-28
         if sampler == "stratified" and x_samples and y_samples:
@@ -579,6 +606,7 @@ class PathIntegrator:
         self.desc.sampler = _SAMPLER[sampler]
         self.desc.n_sampled_dimensions = n_sampled_dimensions
         self.desc.x_samples, self.desc.y_samples, self.desc.jitter = x_samples, y_samples, int(jitter)
+        self.desc.integrator = {"path": 0, "volpath": 1}[integrator]
         self.spp = spp
 
     def render(self, film, sample_begin=0, sample_end=None, stream=None):

@@ -56,6 +56,10 @@ void pb2_scene::free_device() {
     d_spatial = nullptr;
     if (d_spheres) cudaFree(d_spheres);
     d_spheres = nullptr;
+    if (d_media) cudaFree(d_media);
+    if (d_prim_inside) cudaFree(d_prim_inside);
+    if (d_prim_outside) cudaFree(d_prim_outside);
+    d_media = d_prim_inside = d_prim_outside = nullptr;
     path_chain.destroy();
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
@@ -180,7 +184,7 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
     if (tri_material) {
         if (!mats || n_mats == 0) return set_error(PB2_ERR_INVALID, "tri_material given without materials");
         for (uint64_t i = 0; i < n_tris; ++i)
-            if (tri_material[i] >= n_mats) return set_error(PB2_ERR_INVALID, "triangle %llu references material %u >= %u", (unsigned long long)i, tri_material[i], n_mats);
+            if (tri_material[i] >= n_mats && tri_material[i] != PB2_NO_MATERIAL) return set_error(PB2_ERR_INVALID, "triangle %llu references material %u >= %u", (unsigned long long)i, tri_material[i], n_mats);
     }
     for (uint32_t i = 0; i < n_lights; ++i) {
         // (an area light's prim_id is checked at build time: it may name a sphere added by pb2_scene_add_spheres)
@@ -266,10 +270,39 @@ int pb2_scene_add_spheres(pb2_scene* scene, const pb2_sphere* spheres, uint32_t 
         if (det == 0.0f || !std::isfinite(det)) return set_error(PB2_ERR_INVALID, "sphere %u: object_to_world is singular (Matrix4x4::inverse panics, transform.rs:84)", i);
         if (!(sp.radius > 0.0f) || !std::isfinite(sp.radius)) return set_error(PB2_ERR_INVALID, "sphere %u: radius must be positive and finite", i);
         if (!std::isfinite(sp.z_min) || !std::isfinite(sp.z_max) || !std::isfinite(sp.phi_max)) return set_error(PB2_ERR_INVALID, "sphere %u: z_min / z_max / phi_max must be finite", i);
-        if (!scene->materials.empty() && sp.material >= scene->materials.size())
+        if (!scene->materials.empty() && sp.material >= scene->materials.size() && sp.material != PB2_NO_MATERIAL)
             return set_error(PB2_ERR_INVALID, "sphere %u references material %u >= %zu", i, sp.material, scene->materials.size());
     }
     scene->spheres.insert(scene->spheres.end(), spheres, spheres + n);
+    return PB2_OK;
+}
+
+int pb2_scene_set_media(pb2_scene* scene, const pb2_medium* media, uint32_t n_media, const int32_t* prim_inside, const int32_t* prim_outside,
+                        int32_t camera_medium) {
+    if (!scene || (n_media && !media)) return set_error(PB2_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    if (scene->built || scene->built_host) return set_error(PB2_ERR_STATE, "set the media before pb2_scene_build_bvh");
+    for (uint32_t i = 0; i < n_media; ++i)
+        for (int k = 0; k < 3; ++k) {
+            if (!(media[i].sigma_a[k] >= 0.0f) || !(media[i].sigma_s[k] >= 0.0f) || !std::isfinite(media[i].sigma_a[k]) || !std::isfinite(media[i].sigma_s[k]))
+                return set_error(PB2_ERR_INVALID, "medium %u: sigma_a / sigma_s must be finite and >= 0", i);
+            if (!(media[i].sigma_a[k] + media[i].sigma_s[k] > 0.0f))
+                return set_error(PB2_ERR_INVALID, "medium %u: sigma_t is zero in channel %d (HomogeneousMedium::sample divides by it, homogeneous.rs:44)", i, k);
+        }
+    for (uint32_t i = 0; i < n_media; ++i)
+        if (!(std::fabs(media[i].g) < 1.0f)) return set_error(PB2_ERR_INVALID, "medium %u: |g| must be < 1", i);
+    const uint64_t np = scene->n_primitives();
+    for (const int32_t* side : {prim_inside, prim_outside})
+        if (side)
+            for (uint64_t i = 0; i < np; ++i)
+                if (side[i] < -1 || side[i] >= (int32_t)n_media) return set_error(PB2_ERR_INVALID, "primitive %llu names medium %d of %u", (unsigned long long)i, side[i], n_media);
+    if (camera_medium < -1 || camera_medium >= (int32_t)n_media) return set_error(PB2_ERR_INVALID, "camera medium %d of %u", camera_medium, n_media);
+    scene->media.assign(media, media + n_media);
+    scene->prim_inside.assign(np, -1);
+    scene->prim_outside.assign(np, -1);
+    if (prim_inside) scene->prim_inside.assign(prim_inside, prim_inside + np);
+    if (prim_outside) scene->prim_outside.assign(prim_outside, prim_outside + np);
+    scene->camera_medium = camera_medium;
     return PB2_OK;
 }
 

@@ -90,6 +90,14 @@ struct pb2_scene {
     std::vector<pb2_sphere> spheres;
     std::vector<pb2::DSphere> sphere_records;     // device layout (sphere.cuh), filled at build time
     void* d_spheres = nullptr;
+    // participating media (pb2_scene_set_media)
+    std::vector<pb2_medium> media;
+    std::vector<int32_t> prim_inside, prim_outside;
+    int32_t camera_medium = -1;
+    bool has_material_less = false;     // some primitive carries PB2_NO_MATERIAL
+    void* d_media = nullptr;
+    void* d_prim_inside = nullptr;
+    void* d_prim_outside = nullptr;
     uint64_t n_tris() const { return indices.size() / 3; }
     uint64_t n_primitives() const { return indices.size() / 3 + spheres.size(); }
     void* d_indices = nullptr;

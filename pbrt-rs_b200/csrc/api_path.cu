@@ -79,7 +79,7 @@ int upload_shading_tables(pb2_scene* scene) {
     if ((n_mesh && scene->tri_material.empty()) || scene->materials.empty() || n_tris == 0) return PB2_OK;       // ray-casting-only scene
     std::vector<uint32_t> prim_material(scene->tri_material);
     for (const pb2_sphere& sp : scene->spheres) {
-        if (sp.material >= scene->materials.size()) return set_error(PB2_ERR_INVALID, "a sphere references material %u >= %zu", sp.material, scene->materials.size());
+        if (sp.material >= scene->materials.size() && sp.material != PB2_NO_MATERIAL) return set_error(PB2_ERR_INVALID, "a sphere references material %u >= %zu", sp.material, scene->materials.size());
         prim_material.push_back(sp.material);
     }
     std::vector<DMaterial> mats(scene->materials.size());
@@ -104,6 +104,25 @@ int upload_shading_tables(pb2_scene* scene) {
         class_mask |= 1u << d.cls;
     }
     scene->shading_class_mask = class_mask;
+    scene->has_material_less = false;
+    for (uint32_t m : prim_material) scene->has_material_less |= m == PB2_NO_MATERIAL;
+    if (!scene->media.empty()) {                                         // HomogeneousMedium::new: sigma_t = sigma_s + sigma_a (homogeneous.rs:26)
+        if (scene->prim_inside.size() != n_tris) return set_error(PB2_ERR_STATE, "pb2_scene_set_media was called before the last primitives were added");
+        std::vector<DMedium> dm(scene->media.size());
+        for (size_t i = 0; i < dm.size(); ++i)
+            for (int k = 0; k < 3; ++k) {
+                dm[i].sigma_a[k] = scene->media[i].sigma_a[k];
+                dm[i].sigma_s[k] = scene->media[i].sigma_s[k];
+                dm[i].sigma_t[k] = scene->media[i].sigma_s[k] + scene->media[i].sigma_a[k];
+                dm[i].g = scene->media[i].g;
+            }
+        PB2_CUDA(cudaMalloc(&scene->d_media, dm.size() * sizeof(DMedium)));
+        PB2_CUDA(cudaMalloc(&scene->d_prim_inside, n_tris * 4));
+        PB2_CUDA(cudaMalloc(&scene->d_prim_outside, n_tris * 4));
+        PB2_CUDA(cudaMemcpy(scene->d_media, dm.data(), dm.size() * sizeof(DMedium), cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMemcpy(scene->d_prim_inside, scene->prim_inside.data(), n_tris * 4, cudaMemcpyHostToDevice));
+        PB2_CUDA(cudaMemcpy(scene->d_prim_outside, scene->prim_outside.data(), n_tris * 4, cudaMemcpyHostToDevice));
+    }
     const size_t n_lights = scene->lights.size();
     std::vector<DLight> lights(std::max<size_t>(1, n_lights));
     std::vector<int32_t> tri_light(n_tris, -1);
@@ -243,6 +262,10 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
     v.normals = (const float*)s->d_normals;
     v.tangents = (const float*)s->d_tangents;
     v.uvs = (const float2*)s->d_uvs;
+    v.media = (const DMedium*)s->d_media;
+    v.prim_inside = (const int32_t*)s->d_prim_inside;
+    v.prim_outside = (const int32_t*)s->d_prim_outside;
+    v.camera_medium = s->d_media ? s->camera_medium : -1;
     return v;
 }
 
@@ -255,6 +278,12 @@ static int check_path_args(pb2_scene* scene, const pb2_camera* cam, const pb2_pa
         return set_error(PB2_ERR_INVALID, "bad sample range [%d,%d) of %d", path->sample_begin, path->sample_end, path->spp);
     if (path->light_strategy < PB2_LIGHTS_UNIFORM || path->light_strategy > PB2_LIGHTS_SPATIAL)
         return set_error(PB2_ERR_INVALID, "unknown light strategy %d", path->light_strategy);
+    if (path->integrator != PB2_INTEGRATOR_PATH && path->integrator != PB2_INTEGRATOR_VOLPATH)
+        return set_error(PB2_ERR_INVALID, "unknown integrator %d", path->integrator);
+    if (path->integrator == PB2_INTEGRATOR_PATH && scene->has_material_less)
+        return set_error(PB2_ERR_INVALID, "the scene has surfaces without a material (medium interfaces): render it with PB2_INTEGRATOR_VOLPATH");
+    if (path->integrator == PB2_INTEGRATOR_VOLPATH && (path->sampler == PB2_SAMPLER_HALTON || path->sampler == PB2_SAMPLER_SOBOL))
+        return set_error(PB2_ERR_INVALID, "VolPathIntegrator draws an unbounded number of sampler dimensions: use the random, stratified or (0,2) sampler");
     if (path->sampler < PB2_SAMPLER_RANDOM || path->sampler > PB2_SAMPLER_SOBOL)
         return set_error(PB2_ERR_INVALID, "unknown sampler %d", path->sampler);
     if (path->sampler == PB2_SAMPLER_SOBOL) {
@@ -706,7 +735,7 @@ int pb2_render_path(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc
     // may have been cleared / rendered into on another stream: order this call behind the previous uses of both
     PB2_CUDA(scene->path_chain.enter((cudaStream_t)stream));
     PB2_CUDA(film->chain.enter((cudaStream_t)stream));
-    const PathParams pp{path->max_depth, path->rr_threshold};
+    const PathParams pp{path->max_depth, path->rr_threshold, path->integrator};
     SamplerView smp;
     rc = sampler_view(scene, path, fv.sb_x0, fv.sb_y0, fv.sb_w, fv.sb_h, (cudaStream_t)stream, &smp);
     if (rc) return rc;
@@ -765,7 +794,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     if (e == cudaSuccess) e = cudaMemcpy(d_xy, pixel_xy, n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_s, sample_index, n * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        const PathParams pp{path->max_depth, path->rr_threshold};
+        const PathParams pp{path->max_depth, path->rr_threshold, path->integrator};
         wavefront_li(scene->wf, scene->view, shade_view(scene, path->light_strategy), cv, fv, pp, smp, path->spp, d_xy, d_s, n, d_L, d_pf, 0);
         e = cudaGetLastError();
     }

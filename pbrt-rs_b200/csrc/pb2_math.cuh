@@ -156,6 +156,37 @@ PB2_HD void det_sincos(float x, float* s_out, float* c_out) {
 PB2_HD float det_sin(float x) { float s, c; det_sincos(x, &s, &c); return s; }
 PB2_HD float det_cos(float x) { float s, c; det_sincos(x, &s, &c); return c; }
 
+// Deterministic exp / ln for HomogeneousMedium (media/homogeneous.rs: f32::exp / f32::ln = platform libm in the reference):
+// Cephes expf / logf, every operation one rounded f32 op; exp flushes results below the normal range to 0.
+PB2_HD float det_exp(float x) {
+    if (x > 88.0f) return u2f(0x7f800000u);
+    if (x < -87.0f) return 0.0f;
+    float z = floorf(1.44269504088896341f * x + 0.5f);
+    x = x - z * 0.693359375f;
+    x = x - z * -2.12194440e-4f;
+    const int n = (int)z;
+    z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    return z * u2f((uint32_t)(n + 127) << 23);
+}
+PB2_HD float det_log(float x) {
+    if (x <= 0.0f) return -u2f(0x7f800000u);
+    const uint32_t u = f2u(x);
+    int e = (int)(u >> 23) - 126;
+    float m = u2f((u & 0x007FFFFFu) | 0x3F000000u);
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; }
+    else m = m - 1.0f;
+    const float z = m * m;
+    float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m - 1.6668057665e-1f) * m +
+                 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    const float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y + -0.5f * z;
+    float r = m + y;
+    r = r + 0.693359375f * fe;
+    return r;
+}
+
 struct mat4 {
     float m[4][4];
 };

@@ -200,6 +200,12 @@ struct DLight {
     int sphere;             // area light over an analytic sphere: index into SceneView::spheres, else -1
 };
 
+// HomogeneousMedium (media/homogeneous.rs:12-29)
+struct DMedium {
+    float sigma_a[3], sigma_s[3], sigma_t[3];
+    float g;
+};
+
 enum LobeKind : unsigned { kLambert = 0u, kMicrofacet = 1u, kFresnelSpecular = 2u, kOrenNayar = 3u, kSpecularReflection = 4u, kMicrofacetConductor = 5u,
                            kMicrofacetTransmission = 6u, kFresnelBlend = 7u };
 struct Lobe {
@@ -541,6 +547,44 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, 
     }
     return b;
 }
+
+// ---- HenyeyGreenstein (medium.rs:34-87) behind the interface estimate_direct uses for a BSDF ---------------------------------
+PB2_HD float phase_hg(float cos_theta, float g) {
+    const float denom = 1.0f + g * g + 2.0f * g * cos_theta;
+    return (1.0f / PB2_PI / 4.0f) * (1.0f - g * g) / (denom * sqrtf(denom));       // INV_4_PI = INV_PI / 4 (pbrt.rs:19-21)
+}
+struct PhaseHG {
+    float g;
+    vec3 ns;                // unused (a medium interaction has no normal)
+};
+PB2_HD float hg_sample_p(float g, vec3 wo, vec3* wi, float u0, float u1) {
+    float cos_theta;
+    if (fabsf(g) < 1e-3f) cos_theta = 1.0f - 2.0f * u0;
+    else {
+        const float sqr_term = (1.0f - g * g) / (1.0f + g - 2.0f * g * u0);
+        cos_theta = -(1.0f + g * g - sqr_term * sqr_term) / (2.0f * g);
+    }
+    const float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+    const float phi = 2.0f * PB2_PI * u1;
+    vec3 v1, v2;
+    coord_system(wo, &v1, &v2);
+    float sp, cp;
+    det_sincos(phi, &sp, &cp);
+    *wi = (v1 * sin_theta * cp + v2 * sin_theta * sp) + wo * cos_theta;              // geometry.rs:1156-1165
+    return phase_hg(cos_theta, g);
+}
+// estimate_direct's medium-interaction branches (integrator.rs:165-170, 217-226): f = Spectrum(p), pdf = p, no cosine factor
+PB2_HD rgb3 bsdf_f(const PhaseHG& ph, vec3 wo, vec3 wi, unsigned) { return gray(phase_hg(dot3(wo, wi), ph.g)); }
+PB2_HD float bsdf_pdf(const PhaseHG& ph, vec3 wo, vec3 wi, unsigned) { return phase_hg(dot3(wo, wi), ph.g); }
+PB2_HD rgb3 bsdf_sample_f(const PhaseHG& ph, vec3 wo, vec3* wi, float u0, float u1, float* pdf, unsigned, unsigned* sampled) {
+    const float p = hg_sample_p(ph.g, wo, wi, u0, u1);
+    *pdf = p;
+    *sampled = 0u;
+    return gray(p);
+}
+PB2_HD float cos_factor(const PhaseHG&, vec3) { return 1.0f; }                       // (x * 1.0f is exact)
+template <int NL, int CLS>
+PB2_HD float cos_factor(const BsdfT<NL, CLS>& b, vec3 wi) { return fabsf(dot3(wi, b.ns)); }   // wi.abs_dot(&isect.shading.n)
 
 // Distribution1D::sample_discrete (sampling.rs:130-149) over cdf[0..n], func[0..n) — D57 KEEP (cdf < u), D58 signed clamp.
 PB2_HD int sample_discrete(const float* cdf, const float* func, int n, float func_int, float u, float* pdf) {

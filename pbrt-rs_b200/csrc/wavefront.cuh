@@ -52,6 +52,12 @@ struct ShadeView {
     const float* normals;         // 3 per vertex
     const float* tangents;        // 3 per vertex
     const float2* uvs;            // per vertex
+    // participating media (media/homogeneous.rs) and every primitive's MediumInterface as indices into `media` (-1 = none);
+    // all null / -1 unless pb2_scene_set_media was called
+    const DMedium* media;
+    const int32_t* prim_inside;
+    const int32_t* prim_outside;
+    int camera_medium;
 };
 
 // Film geometry: image, sample bounds (film.rs:76-81 with D42), filter radius and its 16x16 table (film.rs:53-63).
@@ -146,6 +152,7 @@ struct PathBuffers {
 struct PathParams {
     int max_depth;
     float rr_threshold;
+    int integrator;               // PB2_INTEGRATOR_PATH (wavefront) / PB2_INTEGRATOR_VOLPATH (k_volpath)
 };
 
 struct Wavefront {

@@ -338,3 +338,49 @@ def scene_spheres(sphere_light=True, partial=True):
         spheres.append(dict(center=(460.0, 420.0, 150.0), radius=25.0, material=0))
         lights.append(dict(type="area", prim=nt + len(spheres) - 1, L=(60.0, 55.0, 40.0), two_sided=False))
     return dict(verts=room["verts"], idx=room["idx"], tri_material=room["tri_material"], materials=materials, lights=lights, spheres=spheres)
+
+
+NO_MATERIAL = 0xFFFFFFFF
+
+
+def _box(lo, hi):
+    """Axis-aligned box as 12 triangles with outward normals."""
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    quads = [((x0, y0, z0), (x0, y1, z0), (x1, y1, z0), (x1, y0, z0)),      # z = z0, normal -z
+             ((x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1)),      # z = z1, normal +z
+             ((x0, y0, z0), (x0, y0, z1), (x0, y1, z1), (x0, y1, z0)),      # x = x0, normal -x
+             ((x1, y0, z0), (x1, y1, z0), (x1, y1, z1), (x1, y0, z1)),      # x = x1, normal +x
+             ((x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1)),      # y = y0, normal -y
+             ((x0, y1, z0), (x0, y1, z1), (x1, y1, z1), (x1, y1, z0))]      # y = y1, normal +y
+    return merge(*[_quad(*q) for q in quads])
+
+
+def scene_media(fog_everywhere=True, g=0.3):
+    """Cornell room for the VolPathIntegrator (src/integrators/volpath.rs, src/media/homogeneous.rs): the camera sits in a thin
+    homogeneous fog that fills the room (medium 0), a material-less box in the middle encloses a dense, forward-scattering
+    coloured smoke (medium 1: the box surface only separates the media), beside a matte block, a glass ball (analytic sphere) and
+    the quad area light + a point light."""
+    room = cornell_box(blocks=False)
+    meshes = [(room["verts"], room["idx"])]
+    tm = list(room["tri_material"])
+    bv, bi = _box((90.0, 60.0, 200.0), (250.0, 260.0, 360.0))
+    meshes.append((bv, bi))
+    n_room = len(room["idx"])
+    tm.extend([NO_MATERIAL] * len(bi))
+    sv, si = _box((330.0, 0.0, 300.0), (450.0, 150.0, 420.0))
+    meshes.append((sv, si))
+    tm.extend([0] * len(si))
+    verts, idx = merge(*meshes)
+    materials = room["materials"] + [dict(type="glass", kr=(1.0, 1.0, 1.0), kt=(1.0, 1.0, 1.0), eta=1.5)]
+    spheres = [dict(center=(400.0, 210.0, 360.0), radius=60.0, material=3)]
+    fog = 0 if fog_everywhere else -1
+    n_prims = len(idx) + len(spheres)
+    inside = np.full(n_prims, fog, dtype=np.int32)
+    outside = np.full(n_prims, fog, dtype=np.int32)
+    inside[n_room:n_room + len(bi)] = 1                 # the smoke box: medium 1 inside, the fog outside
+    media = [dict(sigma_a=(0.0002, 0.0002, 0.0003), sigma_s=(0.0012, 0.0012, 0.0012), g=0.0),
+             dict(sigma_a=(0.002, 0.004, 0.008), sigma_s=(0.02, 0.018, 0.012), g=g)]
+    lights = room["lights"] + [dict(type="point", p=(278.0, 400.0, 100.0), I=(20000.0, 20000.0, 20000.0))]
+    return dict(verts=verts, idx=idx, tri_material=np.array(tm, dtype=np.uint32), materials=materials, lights=lights, spheres=spheres,
+                media=media, prim_inside=inside, prim_outside=outside, camera_medium=fog)

@@ -191,8 +191,24 @@ pub struct pb2_path_desc {
     pub x_samples: i32,
     pub y_samples: i32,
     pub jitter: i32,
+    /// PB2_INTEGRATOR_*
+    pub integrator: i32,
 }
-abi_size!(pb2_path_desc, 44);
+abi_size!(pb2_path_desc, 48);
+pub const PB2_INTEGRATOR_PATH: i32 = 0;
+pub const PB2_INTEGRATOR_VOLPATH: i32 = 1;
+
+/// `HomogeneousMedium::new(sigma_a, sigma_s, g)` (src/media/homogeneous.rs:20-28).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct pb2_medium {
+    pub sigma_a: [f32; 3],
+    pub sigma_s: [f32; 3],
+    pub g: f32,
+}
+abi_size!(pb2_medium, 28);
+/// `tri_material` / `pb2_sphere::material` of a surface without a material (a medium interface only).
+pub const PB2_NO_MATERIAL: u32 = 0xFFFF_FFFF;
 
 pub enum pb2_scene {}
 pub enum pb2_film {}
@@ -228,6 +244,8 @@ extern "C" {
                             out: *mut *mut pb2_scene) -> c_int;
     pub fn pb2_scene_set_shading_geometry(scene: *mut pb2_scene, normals: *const f32, tangents: *const f32, uvs: *const f32) -> c_int;
     pub fn pb2_scene_add_spheres(scene: *mut pb2_scene, spheres: *const pb2_sphere, n: u32) -> c_int;
+    pub fn pb2_scene_set_media(scene: *mut pb2_scene, media: *const pb2_medium, n_media: u32, prim_inside: *const i32, prim_outside: *const i32,
+                               camera_medium: i32) -> c_int;
     pub fn pb2_scene_destroy(scene: *mut pb2_scene) -> c_int;
     pub fn pb2_scene_build_bvh(scene: *mut pb2_scene, max_prims_in_node: c_int, split_method: c_int) -> c_int;
     pub fn pb2_scene_build_bvh_host(scene: *mut pb2_scene, max_prims_in_node: c_int, split_method: c_int) -> c_int;
@@ -845,6 +863,12 @@ impl B200PathIntegrator {
             SamplerKind::Sobol => path.sampler = PB2_SAMPLER_SOBOL,
         }
         B200PathIntegrator { accel, camera, camera_desc, path, film, _pixel_bounds: pixel_bounds }
+    }
+
+    /// `VolPathIntegrator::new` (src/integrators/volpath.rs:32-50) in place of `PathIntegrator::new`: same arguments; the scene's
+    /// media come from `pb2_scene_set_media` on the accelerator's scene.
+    pub fn use_volpath(&mut self) {
+        self.path.integrator = PB2_INTEGRATOR_VOLPATH;
     }
 
     /// One process per GPU: render only sample indices `[begin, end)` of every pixel (the caller reduces the films).

@@ -8,6 +8,7 @@ tests check the CUDA path against the same bytes, so the two cannot drift togeth
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
     python tests/golden/make_golden.py --round2 # rewrites tests/golden/path_r02.npz only
     python tests/golden/make_golden.py --sphere # rewrites tests/golden/sphere_r02.npz only (analytic spheres)
+    python tests/golden/make_golden.py --volpath # rewrites tests/golden/volpath_r02.npz only (VolPathIntegrator + media)
 
 Inputs (meshes, rays, (pixel, sample) pairs) are stored in the fixtures, so no generator has to reproduce them bit for bit.
 """
@@ -147,8 +148,33 @@ def make_sphere(scenes, orc, OP):
     print("sphere_r02.npz", os.path.getsize(os.path.join(HERE, "sphere_r02.npz")), "bytes")
 
 
+def make_volpath(scenes, OP):
+    """tests/golden/volpath_r02.npz: VolPathIntegrator over scenes.scene_media() (fog, smoke box behind a material-less interface,
+    glass sphere): per-sample radiance under two light strategies and a film."""
+    sc = scenes.scene_media()
+    ref = OP.Scene(sc, 4)
+    rng = np.random.default_rng(777)
+    fd = OP.film_desc(GOLDEN_CAMERA["res"])
+    n = 2048
+    xy = np.stack([rng.integers(0, 48, n), rng.integers(0, 48, n)], axis=1).astype(np.int32)
+    s = rng.integers(0, 4, n).astype(np.uint32)
+    out = dict(xy=xy, sample=s)
+    kw = dict(GOLDEN_PATH, max_depth=8)
+    for strat in ("uniform", "power"):
+        L, _ = ref.path_li(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy=strat, integrator="volpath", **kw), xy, s)
+        out["L_" + strat] = L.view(np.uint32)
+    film, _ = ref.render(GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", integrator="volpath", **kw), mode=1)
+    out["film_power"] = film.view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "volpath_r02.npz"), **out)
+    print("volpath_r02.npz", os.path.getsize(os.path.join(HERE, "volpath_r02.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--sphere" in sys.argv:                       # only sphere_r02.npz
+    if "--volpath" in sys.argv:                      # only volpath_r02.npz
+        ge.build()
+        from oracle import oracle_path as _OP
+        make_volpath(ge.load_scenes(), _OP)
+    elif "--sphere" in sys.argv:                       # only sphere_r02.npz
         ge.build()
         from oracle import oracle_path as _OP
         make_sphere(ge.load_scenes(), ge.load_oracle(), _OP)

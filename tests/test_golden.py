@@ -20,7 +20,7 @@ def _mk():
 
 @pytest.fixture(scope="module")
 def G():
-    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path", "path_r02", "sphere_r02")}
+    return {k: np.load(os.path.join(HERE, "golden", k + ".npz")) for k in ("raycast", "path", "path_r02", "sphere_r02", "volpath_r02")}
 
 
 @pytest.fixture(scope="module")
@@ -166,4 +166,31 @@ def test_gpu_reproduces_sphere_fixture(gpu, scenes, G):
         assert np.array_equal(u32(L), g["L_" + strat]), strat
     film = gpu.Film(cam["res"])
     gpu.PathIntegrator(accel, camera, light_strategy="power", **mk.GOLDEN_PATH).render(film)
+    assert np.array_equal(u32(film.read_xyzw()), g["film_power"])
+
+
+def test_oracle_reproduces_volpath_fixture(orc, OP, scenes, G):
+    g, mk = G["volpath_r02"], _mk()
+    ref = OP.Scene(scenes.scene_media(), 4)
+    fd = OP.film_desc(mk.GOLDEN_CAMERA["res"])
+    kw = dict(mk.GOLDEN_PATH, max_depth=8)
+    for strat in ("uniform", "power"):
+        L, _ = ref.path_li(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy=strat, integrator="volpath", **kw), g["xy"], g["sample"])
+        assert np.array_equal(u32(L), g["L_" + strat]), strat
+    film, _ = ref.render(mk.GOLDEN_CAMERA, fd, OP.path_desc(light_strategy="power", integrator="volpath", **kw), mode=1)
+    assert np.array_equal(u32(film), g["film_power"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_volpath_fixture(gpu, scenes, G):
+    g, mk = G["volpath_r02"], _mk()
+    cam = mk.GOLDEN_CAMERA
+    accel = gpu.BVHAccel(gpu.scene_from_dict(scenes.scene_media()), max_prims_in_node=4)
+    camera = gpu.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+    kw = dict(mk.GOLDEN_PATH, max_depth=8)
+    for strat in ("uniform", "power"):
+        L, _ = gpu.PathIntegrator(accel, camera, light_strategy=strat, integrator="volpath", **kw).li(g["xy"], g["sample"])
+        assert np.array_equal(u32(L), g["L_" + strat]), strat
+    film = gpu.Film(cam["res"])
+    gpu.PathIntegrator(accel, camera, light_strategy="power", integrator="volpath", **kw).render(film)
     assert np.array_equal(u32(film.read_xyzw()), g["film_power"])

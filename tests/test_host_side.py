@@ -171,7 +171,7 @@ def test_rust_shim_matches_header(pb2, tmp_path):
     declared = sorted(set(re.findall(r"pub fn (pb2_[a-z0-9_]+)\s*\(", block)))
     assert declared == pb2.header_symbols()
     sizes = dict((t, int(n)) for t, n in re.findall(r"abi_size!\((pb2_[a-z_]+), (\d+)\);", src))
-    assert set(sizes) == {"pb2_ray", "pb2_hit", "pb2_material", "pb2_light", "pb2_sphere", "pb2_camera", "pb2_film_desc", "pb2_path_desc"}
+    assert set(sizes) == {"pb2_ray", "pb2_hit", "pb2_material", "pb2_light", "pb2_sphere", "pb2_medium", "pb2_camera", "pb2_film_desc", "pb2_path_desc"}
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include "pbrt_b200.h"\nint main(void){' +
                     "".join(f'printf("{t} %zu\\n", sizeof({t}));' for t in sorted(sizes)) + "return 0;}\n")
@@ -179,7 +179,7 @@ def test_rust_shim_matches_header(pb2, tmp_path):
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(prog), "-o", str(exe)])
     c_sizes = dict((l.split()[0], int(l.split()[1])) for l in subprocess.check_output([str(exe)], text=True).splitlines())
     assert c_sizes == sizes
-    py = {"pb2_material": pb2.Material, "pb2_light": pb2.Light, "pb2_sphere": pb2.Sphere, "pb2_camera": pb2.CameraDesc, "pb2_film_desc": pb2.FilmDesc,
+    py = {"pb2_material": pb2.Material, "pb2_light": pb2.Light, "pb2_sphere": pb2.Sphere, "pb2_medium": pb2.Medium, "pb2_camera": pb2.CameraDesc, "pb2_film_desc": pb2.FilmDesc,
           "pb2_path_desc": pb2.PathDesc}
     for t, cls in py.items():
         assert C.sizeof(cls) == sizes[t], t
