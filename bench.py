@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--grid-n", type=int, default=2237, help="quads per side of the C3 grid (2237 -> 10,008,338 triangles)")
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--write-c5-anchor", action="store_true", help="N = 1 only: write profiles/c5_n1_anchor.json from this run's C5 frame")
     ap.add_argument("--no-path", action="store_true", help="tuning / profiling runs: C3 traversal only (the default line carries C2, C4 and C5 too)")
     ap.add_argument("--cpu-stride", type=int, default=1, help="cpu sample = every k-th ray of each ray set")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat the sample until this much traversal time")
@@ -438,6 +439,58 @@ def bench_path_c5(pb2, scenes, torch, args, dist, rank, world):
     return out
 
 
+def bench_path_extras(pb2, scenes, torch, rank, no_cpu):
+    """The two shapes / integrators added after the BASELINE configs, so that they have measured numbers
+    too: the Cornell room with ANALYTIC spheres (shapes/sphere.rs: EFloat quadratic in k_extend_spheres / k_shadow_spheres, a
+    spherical area light) under the wavefront PathIntegrator, and the fog + smoke scene under the VolPathIntegrator
+    (integrators/volpath.rs, media/homogeneous.rs: k_volpath, one thread per camera sample).  Each with a bit-for-bit parity
+    check of sample index 0 of every pixel against the oracle."""
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    for key, sc, kw, res, spp in (("spheres", scenes.scene_spheres(), dict(max_depth=5, rr_threshold=1.0, light_strategy="power"), (1024, 1024), 16),
+                                  ("volpath", scenes.scene_media(), dict(max_depth=8, rr_threshold=1.0, light_strategy="power", integrator="volpath"), (512, 512), 16)):
+        cam = dict(scenes.C2_CAMERA, res=res)
+        accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4)
+        camera = pb2.PerspectiveCamera(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
+        integ = pb2.PathIntegrator(accel, camera, spp=spp, **kw)
+        film = pb2.Film(cam["res"])
+        integ.render(film, 0, 2, stream=stream)
+        torch.cuda.synchronize()
+        c0 = integ.counters()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        film.clear()
+        a.record()
+        integ.render(film, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        c1 = integ.counters()
+        ms = a.elapsed_time(b)
+        n = res[0] * res[1] * spp
+        rays = {k: int(c1[k] - c0[k]) for k in ("extend_rays", "shadow_rays", "mis_rays")}
+        e = {"workload": {"spheres": f"Cornell room, {len(sc['spheres'])} analytic spheres (matte / plastic / glass, ellipsoid, partial sphere, spherical area light), "
+                                     f"PathIntegrator maxdepth 5, {res[0]}x{res[1]} @ {spp} spp",
+                          "volpath": f"fog-filled Cornell room + smoke box behind a material-less interface + glass sphere, VolPathIntegrator maxdepth 8, "
+                                     f"{res[0]}x{res[1]} @ {spp} spp"}[key],
+             "unit": "Msamples/s", "value": n / (ms * 1e-3) / 1e6, "ms_per_frame": ms, "rays_per_frame": rays,
+             "mrays_per_s": sum(rays.values()) / (ms * 1e-3) / 1e6}
+        if rank == 0 and not no_cpu:
+            from oracle import oracle_path as OP
+            okw = dict(kw)
+            ref = OP.Scene(sc, 4)
+            want, dt = ref.render(cam, OP.film_desc(cam["res"]), OP.path_desc(spp=spp, sample_begin=0, sample_end=1, **okw), mode=1)
+            film.clear()
+            integ.render(film, 0, 1)
+            got = film.read_xyzw()
+            cores, model = host_info()
+            e["cpu_baseline"] = {"value": res[0] * res[1] / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": model,
+                                 "sample": f"sample index 0 of every pixel ({res[0] * res[1]:,} camera samples), render time only"}
+            e["parity"] = {"pixels_checked": int(got.shape[0] * got.shape[1]),
+                           "pixels_differing": int((got.view(np.uint32) != want.view(np.uint32)).any(axis=2).sum()),
+                           "checked_against": "oracle SamplerIntegrator::render, sample index 0, bitwise"}
+        out[key] = e
+    return out
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference hot path (oracle/; the Rust crate cannot be built —
     no rustc/cargo in the image), all host threads, on a bounded sample of the C3 pass."""
@@ -616,13 +669,14 @@ def main():
 
     # ---- path tracing (second half of the BASELINE metric) ----
     dist_mod = dist if world > 1 else None
-    path_c2 = path_c4 = path_c5 = None
+    path_c2 = path_c4 = path_c5 = path_extras = None
     path_launches = 0
     if not args.no_path:
         path_c2, path_keep = bench_path_c2(pb2, scenes, torch, args, dist_mod, world)
         path_c4, path_c4_keep = bench_path_c4(pb2, scenes, torch, args, dist_mod, world)
         path_c5 = bench_path_c5(pb2, scenes, torch, args, dist_mod, rank, world)
         path_launches = int(path_c2["kernel_launches_per_frame"] * path_steps(args)[0] + path_c4["kernel_launches_per_step"] * 2)
+        path_extras = bench_path_extras(pb2, scenes, torch, rank, args.no_cpu_baseline) if rank == 0 else None
 
     # ---- BVH build: SplitMethod::HLBVH built on the GPU next to the host SAH build, and what the C3
     # ray sets cost on that tree (same rays, same hits: tests/ compare ids and t bits)
@@ -766,9 +820,13 @@ def main():
                     "link_bound_mrays_s": world * rays_per_step / (3 * n * 32 / (pcie["h2d_gbs"] * 1e9)) / 1e6},
             "gpu_launches": launches_per_step * args.steps + path_launches,
             "clocks": clock_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "path": path_c2, "path_c4": path_c4, "path_multi_gpu": path_c5, "bvh_build": bvh_build,
+            "path": path_c2, "path_c4": path_c4, "path_multi_gpu": path_c5, "path_extras": path_extras, "bvh_build": bvh_build,
         }
         print(json.dumps(line), flush=True)
+        if args.write_c5_anchor and world == 1 and path_c5:
+            json.dump({"msamples_s": path_c5["value"], "ms_per_frame": path_c5["ms_per_frame"], "samples_per_frame": path_c5["samples_per_frame"],
+                       "measured_by": "python bench.py --gpus 1 --write-c5-anchor (one B200, whole 3840x2160 @ 1024 spp frame)"},
+                      open(os.path.join(ROOT, "profiles", "c5_n1_anchor.json"), "w"), indent=1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -3,6 +3,7 @@
 #include "api_internal.hpp"
 
 #include <cmath>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 
@@ -47,6 +48,8 @@ void pb2_scene::free_device() {
     d_lin_nodes = d_lin_prims = nullptr;
     if (d_tris) cudaFree(d_tris);
     if (d_slot_of_prim) cudaFree(d_slot_of_prim);
+    if (d_tris_prim) cudaFree(d_tris_prim);
+    d_tris_prim = nullptr;
     if (d_tri_material) cudaFree(d_tri_material);
     if (d_tri_light) cudaFree(d_tri_light);
     if (d_materials) cudaFree(d_materials);
@@ -99,6 +102,34 @@ void pb2_scene::free_device() {
     d_tab1 = d_tab2 = nullptr;
 }
 
+// fn(begin, end) over [0, n) on the host's hardware threads (one range per thread; small inputs stay on the caller's thread).
+template <class F>
+static void parallel_chunks(uint64_t n, F&& fn) {
+    const uint64_t t = std::max<uint64_t>(1, std::min<uint64_t>(std::thread::hardware_concurrency(), n / (1u << 20) + 1));
+    if (t == 1) { fn((uint64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const uint64_t step = (n + t - 1) / t;
+    for (uint64_t k = 0; k < t; ++k) {
+        const uint64_t lo = k * step, hi = std::min(n, lo + step);
+        if (lo < hi) pool.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
+// The smallest i in [0, n) with pred(i), or UINT64_MAX.
+template <class P>
+static uint64_t first_index_where(uint64_t n, P&& pred) {
+    std::atomic<uint64_t> first{UINT64_MAX};
+    parallel_chunks(n, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i)
+            if (pred(i)) {
+                uint64_t cur = first.load();
+                while (i < cur && !first.compare_exchange_weak(cur, i)) {}
+                return;
+            }
+    });
+    return first.load();
+}
+
 extern "C" {
 
 const char* pb2_last_error(void) { return g_err; }
@@ -141,7 +172,10 @@ int pb2_shutdown(void) {
 
 int pb2_host_alloc(uint64_t bytes, void** out) {
     if (!out) return set_error(PB2_ERR_INVALID, "null out");
-    PB2_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    // PB2_HOST_ALLOC_WC=1 (tuning runs only): write-combined pinned memory — faster for the device to read over PCIe on some
+    // hosts, very slow for the CPU to read back, so only for buffers the host writes and the device reads (ray batches)
+    static const bool wc = getenv("PB2_HOST_ALLOC_WC") && atoi(getenv("PB2_HOST_ALLOC_WC")) != 0;
+    PB2_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     return PB2_OK;
 }
 int pb2_host_free(void* p) {
@@ -177,10 +211,14 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
     *out = nullptr;
     if ((n_verts && !verts) || (n_tris && !indices)) return set_error(PB2_ERR_INVALID, "null mesh arrays");
     if (n_tris >= (1ull << 29)) return set_error(PB2_ERR_LIMIT, "at most 2^29-1 triangles (29-bit references in the device BVH records)");
-    for (uint64_t i = 0; i < 3 * n_verts; ++i)
-        if (!std::isfinite(verts[i])) return set_error(PB2_ERR_INVALID, "vertex %llu has a non-finite coordinate", (unsigned long long)(i / 3));
-    for (uint64_t i = 0; i < 3 * n_tris; ++i)
-        if (indices[i] >= n_verts) return set_error(PB2_ERR_INVALID, "triangle %llu references vertex %u >= %llu", (unsigned long long)(i / 3), indices[i], (unsigned long long)n_verts);
+    // validation and the two copies below run on the host's threads: a 10 M-triangle mesh is 180 MB, 0.1 s on one core
+    {
+        const uint64_t bad_v = first_index_where(3 * n_verts, [&](uint64_t i) { return !std::isfinite(verts[i]); });
+        if (bad_v != UINT64_MAX) return set_error(PB2_ERR_INVALID, "vertex %llu has a non-finite coordinate", (unsigned long long)(bad_v / 3));
+        const uint64_t bad_i = first_index_where(3 * n_tris, [&](uint64_t i) { return indices[i] >= n_verts; });
+        if (bad_i != UINT64_MAX)
+            return set_error(PB2_ERR_INVALID, "triangle %llu references vertex %u >= %llu", (unsigned long long)(bad_i / 3), indices[bad_i], (unsigned long long)n_verts);
+    }
     if (tri_material) {
         if (!mats || n_mats == 0) return set_error(PB2_ERR_INVALID, "tri_material given without materials");
         for (uint64_t i = 0; i < n_tris; ++i)
@@ -196,8 +234,10 @@ int pb2_scene_create(const float* verts, uint64_t n_verts, const uint32_t* indic
         }
     }
     pb2_scene* s = new pb2_scene();
-    s->verts.assign(verts, verts + 3 * n_verts);
-    s->indices.assign(indices, indices + 3 * n_tris);
+    s->verts.resize(3 * n_verts);
+    s->indices.resize(3 * n_tris);
+    parallel_chunks(3 * n_verts, [&](uint64_t lo, uint64_t hi) { memcpy(s->verts.data() + lo, verts + lo, (hi - lo) * sizeof(float)); });
+    parallel_chunks(3 * n_tris, [&](uint64_t lo, uint64_t hi) { memcpy(s->indices.data() + lo, indices + lo, (hi - lo) * sizeof(uint32_t)); });
     if (tri_material) s->tri_material.assign(tri_material, tri_material + n_tris);
     if (mats) s->materials.assign(mats, mats + n_mats);
     if (lights) s->lights.assign(lights, lights + n_lights);
@@ -461,6 +501,14 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
         std::vector<PairNode>().swap(b.pairs);
         std::vector<QuadNode>().swap(b.quads);
         std::vector<PackedTri>().swap(b.tris);
+    }
+    // shading scenes: the triangle records once more, in primitive order (k_shade rebuilds a vertex from hit.prim directly)
+    if (n_tris && !scene->materials.empty() && (n_mesh_tris == 0 || !scene->tri_material.empty())) {
+        PB2_CUDA(cudaMalloc(&scene->d_tris_prim, n_tris * sizeof(PackedTri)));
+        launch_tris_by_prim(scene->d_tris, n_tris, scene->d_tris_prim, 0);
+        PB2_CUDA(cudaGetLastError());
+        PB2_CUDA(cudaDeviceSynchronize());
+        v.tris_prim = (const float4*)scene->d_tris_prim;
     }
     scene->view = v;
     rc = upload_shading_tables(scene);

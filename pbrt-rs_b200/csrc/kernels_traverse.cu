@@ -128,6 +128,19 @@ __global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tr
     c.w = __uint_as_float(ok ? 0u : 1u);
     tris[3ull * i + 2] = c;
 }
+// tris_prim[prim] = tris[slot of prim]: the leaf-order records regrouped in the caller's primitive order (SceneView::tris_prim).
+__global__ void __launch_bounds__(256) k_tris_by_prim(const float4* __restrict__ tris, uint32_t n, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = tris[3ull * i], b = tris[3ull * i + 1], c = tris[3ull * i + 2];
+    const uint32_t prim = __float_as_uint(a.w);
+    out[3ull * prim] = a;
+    out[3ull * prim + 1] = b;
+    out[3ull * prim + 2] = c;
+}
+void launch_tris_by_prim(const void* d_tris, uint64_t n, void* d_out, cudaStream_t st) {
+    if (n) k_tris_by_prim<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)d_tris, (uint32_t)n, (float4*)d_out);
+}
 void launch_mark_degenerate(void* d_tris, uint64_t n, const void* d_indices, const void* d_uvs, cudaStream_t st) {
     if (n == 0) return;
     k_mark_degenerate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((float4*)d_tris, (uint32_t)n, (const uint32_t*)d_indices, (const float2*)d_uvs);

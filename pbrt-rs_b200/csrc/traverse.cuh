@@ -26,6 +26,8 @@ struct SceneView {
     const float4* __restrict__ pairs;   // 4 x float4 per interior node (PairNode): literal one-level walk (traverse())
     const float4* __restrict__ tris;    // 3 x float4 per triangle (PackedTri), BVH leaf order
     const uint32_t* __restrict__ slot_of_prim;   // caller's triangle id -> leaf-order slot
+    const float4* __restrict__ tris_prim; // the same 3 x float4 records in the CALLER's primitive order (shading scenes only): a
+                                          // path vertex is rebuilt from hit.prim with one fetch less than through slot_of_prim
     const float4* __restrict__ spheres;  // 8 x float4 per analytic sphere (DSphere, sphere.cuh); null when the scene has none
     uint32_t root_ref;
     uint32_t n_tris;                     // primitives in the tree (triangles + spheres)

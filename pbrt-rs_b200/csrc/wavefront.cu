@@ -640,8 +640,11 @@ struct Vertex {           // SurfaceInteraction subset rebuilt from the hit reco
 template <bool SG>
 __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const ShadeView& sh, uint32_t prim, float b0, float b1, float b2,
                                                  vec3 ro = mk(0.f, 0.f, 0.f), vec3 rd = mk(0.f, 0.f, 1.f)) {
-    const uint32_t slot = __ldg(s.slot_of_prim + prim);
-    const float4 a = ldg4(s.tris + 3ull * slot), b = ldg4(s.tris + 3ull * slot + 1), c = ldg4(s.tris + 3ull * slot + 2);
+#ifndef PB2_TRIS_BY_PRIM
+#define PB2_TRIS_BY_PRIM 1     /* 0: triangle through slot_of_prim (one more dependent fetch; tuning builds) */
+#endif
+    const float4* tp = PB2_TRIS_BY_PRIM ? s.tris_prim + 3ull * prim : s.tris + 3ull * __ldg(s.slot_of_prim + prim);
+    const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
     const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
     Vertex v;
     v.wo = -rd;
@@ -894,9 +897,32 @@ template <int MAT, bool TABLES, bool SG>
 __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
     const uint64_t n = b.counters[C_MAT0 + MAT];
     const uint32_t* queue = b.q_mat[MAT];
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t slot = queue[i];
-        const uint4 h = b.hit[slot];
+#ifndef PB2_SHADE_PIPE
+#define PB2_SHADE_PIPE 1        /* 0: load the queue entry and the hit record where they are used (the round-1 loop; tuning builds) */
+#endif
+    // The head of an iteration is a chain of dependent loads — queue entry -> hit record -> leaf slot -> triangle — that held
+    // 22 % of the kernel's stall samples on its first two links alone (profiles/r02_tuning.md); they are issued two / one
+    // iteration ahead, so their latency runs under the previous vertices' arithmetic.
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot_n = 0, slot_nn = 0;
+    uint4 h_n = make_uint4(0u, 0u, 0u, 0u);
+    if (PB2_SHADE_PIPE) {
+        if (i0 < n) { slot_n = queue[i0]; h_n = b.hit[slot_n]; }
+        if (i0 + stride < n) slot_nn = queue[i0 + stride];
+    }
+    for (uint64_t i = i0; i < n; i += stride) {
+        uint32_t slot;
+        uint4 h;
+        if (PB2_SHADE_PIPE) {
+            slot = slot_n;
+            h = h_n;
+            slot_n = slot_nn;
+            if (i + stride < n) h_n = b.hit[slot_n];
+            if (i + 2 * stride < n) slot_nn = queue[i + 2 * stride];
+        } else {
+            slot = queue[i];
+            h = b.hit[slot];
+        }
         const float4 rd = b.ray_d[slot];
         float4 Lf = b.L[slot];
         float4 bt = b.beta[slot];
