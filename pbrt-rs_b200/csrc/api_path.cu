@@ -84,6 +84,7 @@ int upload_shading_tables(pb2_scene* scene) {
     }
     std::vector<DMaterial> mats(scene->materials.size());
     unsigned class_mask = 0u;
+    bool class1_all_plastic = true;
     for (size_t i = 0; i < mats.size(); ++i) {
         const pb2_material& m = scene->materials[i];
         if (m.type < PB2_MAT_MATTE || m.type > PB2_MAT_SUBSTRATE) return set_error(PB2_ERR_INVALID, "material %zu has unknown type %d", i, m.type);
@@ -102,7 +103,14 @@ int upload_shading_tables(pb2_scene* scene) {
         // shading class (shade.cuh: make_bsdf<CLS>)
         d.cls = (m.type == PB2_MAT_MATTE && m.sigma == 0.0f) ? 0 : (((m.type == PB2_MAT_GLASS && m.roughness == 0.0f) || m.type == PB2_MAT_MIRROR) ? 2 : 1);
         class_mask |= 1u << d.cls;
+        if (d.cls == 1) {
+            const bool two_lobe_plastic = m.type == PB2_MAT_PLASTIC && (m.kd[0] != 0.0f || m.kd[1] != 0.0f || m.kd[2] != 0.0f) &&
+                                          (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f);
+            class1_all_plastic = class1_all_plastic && two_lobe_plastic;
+        }
     }
+    // bit 3: every class-1 material is a PlasticMaterial with both lobes -> k_shade<3> (the plastic-only kernel) shades queue 1
+    if ((class_mask & 2u) && class1_all_plastic && !(getenv("PB2_GENERAL_CLASS1") && atoi(getenv("PB2_GENERAL_CLASS1")) != 0)) class_mask |= 8u;
     scene->shading_class_mask = class_mask;
     scene->has_material_less = false;
     for (uint32_t m : prim_material) scene->has_material_less |= m == PB2_NO_MATERIAL;

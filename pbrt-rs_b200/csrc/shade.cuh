@@ -236,11 +236,16 @@ PB2_HD float fresnel_conductor1(float ci, float eta_i, float eta_t, float k) {
 PB2_HD bool lobe_matches(const Lobe& l, unsigned flags) { return (l.type & flags) == l.type; }       // D33 FIX
 
 // Lobe kinds a shading class can hold (make_bsdf<CLS>): the branches of the other kinds drop out of that class's kernel.
+// CLS 3 is not a queue of its own: it is class 1 compiled for scenes whose class-1 materials are all PlasticMaterial with
+// non-black Kd and Ks — lobes[0] = Lambertian, lobes[1] = dielectric microfacet, both kinds compile-time constants.  The general
+// class-1 kernel carries six lobe kinds through fourteen inlined lobe evaluations: 43,800 SASS instructions, 66 % of its stall
+// samples waiting for the instruction cache (profiles/r02_tuning.md).
 template <int CLS>
 PB2_HD constexpr bool may_be(unsigned kind) {
     return CLS < 0 || (CLS == 0 && kind == kLambert) ||
            (CLS == 1 && (kind == kLambert || kind == kMicrofacet || kind == kOrenNayar || kind == kMicrofacetConductor || kind == kMicrofacetTransmission || kind == kFresnelBlend)) ||
-           (CLS == 2 && (kind == kFresnelSpecular || kind == kSpecularReflection));
+           (CLS == 2 && (kind == kFresnelSpecular || kind == kSpecularReflection)) ||
+           (CLS == 3 && (kind == kLambert || kind == kMicrofacet));
 }
 template <int CLS>
 PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
@@ -257,7 +262,7 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
         else { sin_alpha = sti; tan_beta = sto / abs_cos_t(wo); }
         return l.r * (1.0f / PB2_PI) * (l.eta_a + ((l.eta_b * max_cos) * sin_alpha) * tan_beta);
     }
-    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || (may_be<CLS>(kMicrofacetConductor) && l.kind == kMicrofacetConductor))) {
         const float co = abs_cos_t(wo), ci = abs_cos_t(wi);
         vec3 wh = wi + wo;
         if (ci == 0.0f || co == 0.0f) return gray(0.0f);
@@ -265,7 +270,7 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
         wh = unit(wh);
         const float c = dot3(wi, face_toward(wh, mk(0.0f, 0.0f, 1.0f)));                                            // D6 FIX
         rgb3 fr;
-        if (l.kind == kMicrofacetConductor) {                    // FresnelConductor::evaluate(|cos|), reflection.rs:583-587
+        if (may_be<CLS>(kMicrofacetConductor) && l.kind == kMicrofacetConductor) {                    // FresnelConductor::evaluate(|cos|), reflection.rs:583-587
             const float ac = fabsf(c);
             fr = mkc(fresnel_conductor1(ac, 1.0f, l.t.r, l.k.r), fresnel_conductor1(ac, 1.0f, l.t.g, l.k.g), fresnel_conductor1(ac, 1.0f, l.t.b, l.k.b));
         } else fr = gray(fresnel_dielectric(c, l.eta_a, l.eta_b));
@@ -302,8 +307,8 @@ PB2_HD rgb3 lobe_f(const Lobe& l, vec3 wo, vec3 wi) {
 }
 template <int CLS>
 PB2_HD float lobe_pdf(const Lobe& l, vec3 wo, vec3 wi) {
-    if (may_be<CLS>(kLambert) && (l.kind == kLambert || l.kind == kOrenNayar)) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
-    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
+    if (may_be<CLS>(kLambert) && (l.kind == kLambert || (may_be<CLS>(kOrenNayar) && l.kind == kOrenNayar))) return same_side(wo, wi) ? abs_cos_t(wi) * (1.0f / PB2_PI) : 0.0f;
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || (may_be<CLS>(kMicrofacetConductor) && l.kind == kMicrofacetConductor))) {
         if (!same_side(wo, wi)) return 0.0f;
         const vec3 wh = unit(wo + wi);
         return tr_pdf(l.alpha, wo, wh) / (4.0f * dot3(wo, wh));
@@ -332,13 +337,13 @@ PB2_HD rgb3 lobe_sample_f(const Lobe& l, vec3 wo, vec3* wi, float u0, float u1, 
         *pdf = 1.0f;
         return l.r * gray(1.0f) / abs_cos_t(*wi);
     }
-    if (may_be<CLS>(kLambert) && (l.kind == kLambert || l.kind == kOrenNayar)) {
+    if (may_be<CLS>(kLambert) && (l.kind == kLambert || (may_be<CLS>(kOrenNayar) && l.kind == kOrenNayar))) {
         *wi = cosine_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi->z = wi->z * -1.0f;
         *pdf = lobe_pdf<CLS>(l, wo, *wi);
         return lobe_f<CLS>(l, wo, *wi);
     }
-    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || l.kind == kMicrofacetConductor)) {
+    if (may_be<CLS>(kMicrofacet) && (l.kind == kMicrofacet || (may_be<CLS>(kMicrofacetConductor) && l.kind == kMicrofacetConductor))) {
         if (wo.z == 0.0f) return gray(0.0f);
         const vec3 wh = tr_sample_wh(l.alpha, wo, u0, u1);
         if (dot3(wo, wh) < 0.0f) return gray(0.0f);
@@ -487,7 +492,7 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL, CLS>& b, vec3 wo_w, vec3* wi_w, float 
 template <int CLS = -1>
 PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
     BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> b;
-    const int type = CLS == 0 ? 0 : m.type;
+    const int type = CLS == 0 ? 0 : (CLS == 3 ? 1 : m.type);
     b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = ns;
     b.ng = ng;
@@ -499,7 +504,13 @@ PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, 
     const rgb3 zero = gray(0.0f);
     // (the first lobe of every material is written to lobes[0] by constant index: a `lobes[b.n++]` whose index the compiler
     // cannot fold moves the whole lobe array to local memory)
-    if (type == 0 || type == 1) {
+    if (CLS == 3) {                                            // PlasticMaterial, Kd and Ks non-black (checked when the scene is uploaded)
+        b.n = 2;
+        Lobe& l0 = b.lobes[0];
+        l0.kind = kLambert; l0.type = kReflection | kDiffuse; l0.r = kd; l0.t = zero; l0.alpha = 0.0f; l0.eta_a = 1.0f; l0.eta_b = 1.0f; l0.k = zero;
+        Lobe& l1 = b.lobes[1];
+        l1.kind = kMicrofacet; l1.type = kReflection | kGlossy; l1.r = ks; l1.t = zero; l1.alpha = m.alpha; l1.eta_a = 1.5f; l1.eta_b = 1.0f; l1.k = zero;
+    } else if (type == 0 || type == 1) {
         if (!black(kd)) {
             Lobe& l = b.lobes[0];
             b.n = 1;

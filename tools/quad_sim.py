@@ -31,6 +31,14 @@ def run(name, verts, idx, rays):
     print(f"{name}: rays {n} binary nodes/ray {st[0]/n:.2f} tris/ray {st[1]/n:.3f} | quad steps/ray {st[2]/n:.2f} boxes/ray {st[3]/n:.2f} "
           f"tris/ray {st[4]/n:.3f} | mismatches {st[5]} nonplain {st[6]} quads {int(st[7]) >> 8} max_sp {int(st[7]) & 255}")
     assert st[5] == 0 and st[1] == st[4]
+    w = np.zeros(13, np.uint64)
+    L.wide_sim(verts.ctypes.data_as(vp), C.c_uint64(len(verts)), idx.ctypes.data_as(vp), C.c_uint64(len(idx)), 4,
+               rays.ctypes.data_as(vp), C.c_uint64(len(rays)), w.ctypes.data_as(vp))
+    for lv, o in ((2, 0), (3, 6)):
+        print(f"   {lv}-level record ({1 << lv}-wide): steps/ray {w[o]/n:.2f} boxes/ray {w[o+1]/n:.2f} tris/ray {w[o+2]/n:.3f} pushes/ray {w[o+3]/n:.2f} "
+              f"pops/ray {w[o+4]/n:.2f} leaf visits/ray {w[o+5]/n:.2f}")
+    print(f"   3-level / 2-level: steps x{w[6]/w[0]:.3f} boxes x{w[7]/w[1]:.3f} tris x{w[8]/max(1, w[2]):.3f}; mismatches vs binary {w[12]}")
+    assert w[12] == 0
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c1"
@@ -42,6 +50,8 @@ elif which == "c3":
     cam = dict(scenes.C3_CAMERA, res=(1024, 1024))
 elif which == "c2":
     sc = scenes.scene_c2(); v, i = sc["verts"], sc["idx"]; cam = scenes.C2_CAMERA
+elif which == "c4":
+    sc = scenes.scene_c4(); v, i = sc["verts"], sc["idx"]; cam = dict(scenes.C4_CAMERA, res=(960, 540))
 elif which == "soup":
     v, i = scenes.random_soup(20000, seed=3); cam = scenes.C1_CAMERA
 rays = orc.camera_primary_rays(cam["pos"], cam["look"], cam["up"], cam["fov"], cam["res"])
