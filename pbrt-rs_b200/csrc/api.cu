@@ -502,9 +502,10 @@ int pb2_scene_build_bvh(pb2_scene* scene, int max_prims_in_node, int split_metho
         std::vector<QuadNode>().swap(b.quads);
         std::vector<PackedTri>().swap(b.tris);
     }
-    // shading scenes: the triangle records once more, in primitive order (k_shade rebuilds a vertex from hit.prim directly)
+    // shading scenes: the triangle records once more, in primitive order, each with its shading frame (k_shade rebuilds a vertex
+    // from hit.prim directly)
     if (n_tris && !scene->materials.empty() && (n_mesh_tris == 0 || !scene->tri_material.empty())) {
-        PB2_CUDA(cudaMalloc(&scene->d_tris_prim, n_tris * sizeof(PackedTri)));
+        PB2_CUDA(cudaMalloc(&scene->d_tris_prim, n_tris * 2 * sizeof(PackedTri)));      // record + shading frame (k_tris_by_prim)
         launch_tris_by_prim(scene->d_tris, n_tris, scene->d_tris_prim, 0);
         PB2_CUDA(cudaGetLastError());
         PB2_CUDA(cudaDeviceSynchronize());

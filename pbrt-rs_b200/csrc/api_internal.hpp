@@ -121,7 +121,7 @@ struct pb2_scene {
     void* d_quads = nullptr;
     void* d_tris = nullptr;
     void* d_slot_of_prim = nullptr;
-    void* d_tris_prim = nullptr;     // PackedTri records in primitive order (shading scenes; SceneView::tris_prim)
+    void* d_tris_prim = nullptr;     // PackedTri + shading frame in primitive order (shading scenes; SceneView::tris_prim)
     void* d_tri_material = nullptr;
     void* d_tri_light = nullptr;
     void* d_materials = nullptr;

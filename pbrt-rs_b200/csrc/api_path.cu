@@ -166,6 +166,15 @@ int upload_shading_tables(pb2_scene* scene) {
                 if (d.has_n) { d.n0[c] = scene->normals[3 * ix[0] + c]; d.n1[c] = scene->normals[3 * ix[1] + c]; d.n2[c] = scene->normals[3 * ix[2] + c]; }
                 if (d.has_uv && c < 2) { d.uv[c] = scene->uvs[2 * ix[0] + c]; d.uv[2 + c] = scene->uvs[2 * ix[1] + c]; d.uv[4 + c] = scene->uvs[2 * ix[2] + c]; }
             }
+            {
+                const vec3 ns = unit(cross3(p1 - p0, p2 - p0)), nh = unit(cross3(p0 - p2, p1 - p2));
+                d.ns_sample[0] = ns.x; d.ns_sample[1] = ns.y; d.ns_sample[2] = ns.z;
+                d.n_hit[0] = nh.x; d.n_hit[1] = nh.y; d.n_hit[2] = nh.z;
+                d.inv_area = 1.0f / d.area;
+                vec3 du, dv;
+                d.frame_ok = (d.has_uv ? tri_frame_uv(p0, p1, p2, make_float2(d.uv[0], d.uv[1]), make_float2(d.uv[2], d.uv[3]), make_float2(d.uv[4], d.uv[5]), &du, &dv)
+                                       : tri_frame(p0, p1, p2, &du, &dv)) ? 1 : 0;
+            }
             tri_light[l.prim_id] = (int32_t)i;
             pw = mkc(l.i[0], l.i[1], l.i[2]) * ((l.two_sided ? 2.0f : 1.0f) * d.area * PB2_PI);      // diffuse.rs:83-85
         } else if (l.type == PB2_LIGHT_SPOT) {                           // spot.rs:30-49

@@ -128,15 +128,31 @@ __global__ void __launch_bounds__(256) k_mark_degenerate(float4* __restrict__ tr
     c.w = __uint_as_float(ok ? 0u : 1u);
     tris[3ull * i + 2] = c;
 }
-// tris_prim[prim] = tris[slot of prim]: the leaf-order records regrouped in the caller's primitive order (SceneView::tris_prim).
+// tris_prim[prim] = tris[slot of prim] + the primitive's shading frame: the leaf-order records regrouped in the caller's primitive
+// order (SceneView::tris_prim, 6 x float4 per primitive), followed by what Triangle::intersect and BSDF::new derive from the three
+// vertices of a plain triangle — n = normalize(cross(dp02, dp12)) (triangle.rs:234-236), ss = normalize(dpdu) with the default
+// UVs (triangle.rs:193-215), ts = cross(n, ss) (reflection.rs:220-234) — computed here once with the functions k_shade used per vertex.
 __global__ void __launch_bounds__(256) k_tris_by_prim(const float4* __restrict__ tris, uint32_t n, float4* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 a = tris[3ull * i], b = tris[3ull * i + 1], c = tris[3ull * i + 2];
     const uint32_t prim = __float_as_uint(a.w);
-    out[3ull * prim] = a;
-    out[3ull * prim + 1] = b;
-    out[3ull * prim + 2] = c;
+    float4* o = out + 6ull * prim;
+    o[0] = a;
+    o[1] = b;
+    o[2] = c;
+    vec3 nn = mk(0.f, 0.f, 0.f), ss = nn, ts = nn;
+    if (!(__float_as_uint(c.w) & 2u)) {                        // (an analytic sphere's interaction is rebuilt from the ray)
+        const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
+        vec3 dpdu, dv;
+        nn = unit(cross3(p0 - p2, p1 - p2));
+        tri_frame(p0, p1, p2, &dpdu, &dv);
+        ss = unit(dpdu);
+        ts = cross3(nn, ss);
+    }
+    o[3] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+    o[4] = make_float4(ss.x, ss.y, ss.z, 0.0f);
+    o[5] = make_float4(ts.x, ts.y, ts.z, 0.0f);
 }
 void launch_tris_by_prim(const void* d_tris, uint64_t n, void* d_out, cudaStream_t st) {
     if (n) k_tris_by_prim<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)d_tris, (uint32_t)n, (float4*)d_out);

@@ -198,6 +198,13 @@ struct DLight {
     float n0[3], n1[3], n2[3];   // vertex normals of the emissive triangle (Triangle::sample, triangle.rs:338-341)
     float uv[6];            // its UVs (Shape::pdf2 -> Triangle::intersect frame check)
     int sphere;             // area light over an analytic sphere: index into SceneView::spheres, else -1
+    // what estimate_direct derives from the emissive triangle's vertices alone, computed once when the scene is uploaded
+    // (api_path.cu, same functions): Triangle::sample's normal normalize(cross(p1 - p0, p2 - p0)) (triangle.rs:336), the
+    // interaction normal normalize(cross(dp02, dp12)) of a hit on it (triangle.rs:234-236), 1 / area (shape.rs:43) and whether
+    // Triangle::intersect accepts the triangle's frame at all (triangle.rs:193-215)
+    float ns_sample[3], n_hit[3];
+    float inv_area;
+    int frame_ok;
 };
 
 // HomogeneousMedium (media/homogeneous.rs:12-29)
@@ -490,14 +497,14 @@ PB2_HD rgb3 bsdf_sample_f(const BsdfT<NL, CLS>& b, vec3 wo_w, vec3* wi_w, float 
 // compile-time constant: the kernel that carries C2 / C4), 1 = general (plastic, metal, Oren-Nayar matte; up to two lobes),
 // 2 = specular (glass, mirror; one lobe); CLS < 0 reads everything at run time.
 template <int CLS = -1>
-PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 sdpdu) {
+PB2_HD BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> make_bsdf(const DMaterial& m, vec3 ng, vec3 ns, vec3 ss, vec3 ts) {
     BsdfT<(CLS == 0 || CLS == 2) ? 1 : 2, CLS> b;
     const int type = CLS == 0 ? 0 : (CLS == 3 ? 1 : m.type);
     b.eta = type == 2 ? m.eta : 1.0f;
     b.ns = ns;
     b.ng = ng;
-    b.ss = unit(sdpdu);                                        // reflection.rs:220-234
-    b.ts = cross3(b.ns, b.ss);
+    b.ss = ss;                                                 // reflection.rs:220-234: ss = normalize(shading.dpdu), ts = cross(ns, ss)
+    b.ts = ts;                                                 // (rebuild_vertex: per primitive for a plain mesh)
     b.n = 0;
     const rgb3 kd = mkc(m.kd[0], m.kd[1], m.kd[2]), ks = mkc(m.ks[0], m.ks[1], m.ks[2]);
     const rgb3 kr = mkc(m.kr[0], m.kr[1], m.kr[2]), kt = mkc(m.kt[0], m.kt[1], m.kt[2]);

@@ -26,8 +26,8 @@ struct SceneView {
     const float4* __restrict__ pairs;   // 4 x float4 per interior node (PairNode): literal one-level walk (traverse())
     const float4* __restrict__ tris;    // 3 x float4 per triangle (PackedTri), BVH leaf order
     const uint32_t* __restrict__ slot_of_prim;   // caller's triangle id -> leaf-order slot
-    const float4* __restrict__ tris_prim; // the same 3 x float4 records in the CALLER's primitive order (shading scenes only): a
-                                          // path vertex is rebuilt from hit.prim with one fetch less than through slot_of_prim
+    const float4* __restrict__ tris_prim; // shading scenes only, 6 x float4 per primitive in the CALLER's primitive order: the PackedTri and
+                                          // the plain triangle's n, ss, ts (k_tris_by_prim) — a path vertex is rebuilt from hit.prim directly
     const float4* __restrict__ spheres;  // 8 x float4 per analytic sphere (DSphere, sphere.cuh); null when the scene has none
     uint32_t root_ref;
     uint32_t n_tris;                     // primitives in the tree (triangles + spheres)
@@ -139,7 +139,7 @@ PB2_D bool tri_test(const RayCtx& r, float ray_t_max, vec3 p0, vec3 p1, vec3 p2,
 
 // triangle.rs:193-215: dpdu, dpdv from the triangle's UVs (Triangle::get_uvs, :60-72; uv0/uv1/uv2, default (0,0),(1,0),(1,1));
 // false when Triangle::intersect bails out on a degenerate frame (closest-hit only — intersect_p never runs this).
-PB2_D bool tri_frame_uv(vec3 p0, vec3 p1, vec3 p2, float2 uv0, float2 uv1, float2 uv2, vec3* dpdu, vec3* dpdv) {
+PB2_HD bool tri_frame_uv(vec3 p0, vec3 p1, vec3 p2, float2 uv0, float2 uv1, float2 uv2, vec3* dpdu, vec3* dpdv) {
     const vec3 dp02 = p0 - p2, dp12 = p1 - p2;
     const float duv02x = uv0.x - uv2.x, duv02y = uv0.y - uv2.y, duv12x = uv1.x - uv2.x, duv12y = uv1.y - uv2.y;
     const float determinant = duv02x * duv12y - duv02y * duv12x;
@@ -159,7 +159,7 @@ PB2_D bool tri_frame_uv(vec3 p0, vec3 p1, vec3 p2, float2 uv0, float2 uv1, float
     *dpdv = dv;
     return true;
 }
-PB2_D bool tri_frame(vec3 p0, vec3 p1, vec3 p2, vec3* dpdu, vec3* dpdv) {
+PB2_HD bool tri_frame(vec3 p0, vec3 p1, vec3 p2, vec3* dpdu, vec3* dpdv) {
     const vec3 dp02 = p0 - p2, dp12 = p1 - p2;
     const float duv02x = 0.0f - 1.0f, duv02y = 0.0f - 1.0f, duv12x = 1.0f - 1.0f, duv12y = 0.0f - 1.0f;
     const float determinant = duv02x * duv12y - duv02y * duv12x;

@@ -236,27 +236,30 @@ struct PathSampler {
 __device__ __forceinline__ vec3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
 
 struct Vertex {           // SurfaceInteraction subset rebuilt from the hit record (triangle.rs:193-311, D59)
-    vec3 p, err, n, dpdu;
-    vec3 sn, sdpdu;       // shading.n, shading.dpdu: n and dpdu unless the mesh has vertex normals / tangents
+    vec3 p, err, n;
+    vec3 sn;              // shading.n: n unless the mesh has vertex normals / tangents
+    vec3 ss, ts;          // the BSDF's frame (reflection.rs:220-234): ss = normalize(shading.dpdu), ts = cross(shading.n, ss)
     vec3 wo;              // SurfaceInteraction::wo: -ray.d for a triangle; normalize(o2w * -ray_obj.d) for a sphere (sphere.rs:79)
 };
 // SG = the mesh carries per-vertex normals, tangents or UVs (compiled out otherwise: k_shade is at its register limit).
 // ro / rd: the ray that hit (a sphere's interaction is rebuilt from the ray and the hit distance, which a sphere hit carries in
 // place of b0; sphere.rs:38-93).
+// A primitive's record in SceneView::tris_prim is 6 x float4: the PackedTri (3 x float4) and, for a plain triangle, what
+// Triangle::intersect + BSDF::new derive from the three vertices alone — n, ss, ts (k_tris_by_prim) — so that the plain-mesh
+// vertex costs three more loads instead of two normalisations, tri_frame and a cross product (11 % of k_shade<0>'s instructions).
 template <bool SG>
 __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const ShadeView& sh, uint32_t prim, float b0, float b1, float b2,
                                                  vec3 ro = mk(0.f, 0.f, 0.f), vec3 rd = mk(0.f, 0.f, 1.f)) {
-#ifndef PB2_TRIS_BY_PRIM
-#define PB2_TRIS_BY_PRIM 1     /* 0: triangle through slot_of_prim (one more dependent fetch; tuning builds) */
-#endif
-    const float4* tp = PB2_TRIS_BY_PRIM ? s.tris_prim + 3ull * prim : s.tris + 3ull * __ldg(s.slot_of_prim + prim);
+    const float4* tp = s.tris_prim + 6ull * prim;
     const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
     const vec3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
     Vertex v;
     v.wo = -rd;
     if (SG && s.spheres && (__float_as_uint(c.w) & 2u)) {
         const SphereVertex sv = sphere_vertex_at(sphere_of(s, a), ro, rd, b0);
-        v.p = sv.p; v.err = sv.err; v.n = sv.n; v.dpdu = sv.dpdu; v.sn = sv.sn; v.sdpdu = sv.dpdu; v.wo = sv.wo;
+        v.p = sv.p; v.err = sv.err; v.n = sv.n; v.sn = sv.sn; v.wo = sv.wo;
+        v.ss = unit(sv.dpdu);
+        v.ts = cross3(v.sn, v.ss);
         return v;
     }
     const float xs = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x)) + fabsf(b2 * p2.x);
@@ -264,26 +267,35 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
     const float zs = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z)) + fabsf(b2 * p2.z);
     v.err = mk(xs, ys, zs) * gammaf_(7.0f);
     v.p = (p0 * b0 + p1 * b1) + p2 * b2;
-    v.n = unit(cross3(p0 - p2, p1 - p2));
-    vec3 dv;
-    if (!SG || !sh.indices) {                                  // (SG without mesh attributes: a scene that has analytic spheres)
-        tri_frame(p0, p1, p2, &v.dpdu, &dv);
+    if (!SG) {                                                 // plain mesh: the per-primitive frame
+        const float4 fn = ldg4(tp + 3), fs = ldg4(tp + 4), ft = ldg4(tp + 5);
+        v.n = mk(fn.x, fn.y, fn.z);
         v.sn = v.n;
-        v.sdpdu = v.dpdu;
+        v.ss = mk(fs.x, fs.y, fs.z);
+        v.ts = mk(ft.x, ft.y, ft.z);
+        return v;
+    }
+    v.n = unit(cross3(p0 - p2, p1 - p2));
+    vec3 dpdu, dv;
+    if (!sh.indices) {                                         // (SG without mesh attributes: a scene that has analytic spheres)
+        tri_frame(p0, p1, p2, &dpdu, &dv);
+        v.sn = v.n;
+        v.ss = unit(dpdu);
+        v.ts = cross3(v.sn, v.ss);
         return v;
     }
     const uint32_t i0 = __ldg(sh.indices + 3ull * prim), i1 = __ldg(sh.indices + 3ull * prim + 1), i2 = __ldg(sh.indices + 3ull * prim + 2);
-    if (sh.uvs) tri_frame_uv(p0, p1, p2, __ldg(sh.uvs + i0), __ldg(sh.uvs + i1), __ldg(sh.uvs + i2), &v.dpdu, &dv);   // Triangle::get_uvs
-    else tri_frame(p0, p1, p2, &v.dpdu, &dv);
+    if (sh.uvs) tri_frame_uv(p0, p1, p2, __ldg(sh.uvs + i0), __ldg(sh.uvs + i1), __ldg(sh.uvs + i2), &dpdu, &dv);   // Triangle::get_uvs
+    else tri_frame(p0, p1, p2, &dpdu, &dv);
     v.sn = v.n;
-    v.sdpdu = v.dpdu;
+    vec3 sdpdu = dpdu;
     if (sh.normals || sh.tangents) {                                     // triangle.rs:251-311
         vec3 ns = v.n;
         if (sh.normals) {
             ns = (ld3(sh.normals + 3ull * i0) * b0 + ld3(sh.normals + 3ull * i1) * b1) + ld3(sh.normals + 3ull * i2) * b2;
             ns = len2(ns) > 0.0f ? unit(ns) : v.n;
         }
-        vec3 ss = unit(v.dpdu);
+        vec3 ss = unit(dpdu);
         if (sh.tangents) {
             const vec3 st = (ld3(sh.tangents + 3ull * i0) * b0 + ld3(sh.tangents + 3ull * i1) * b1) + ld3(sh.tangents + 3ull * i2) * b2;
             if (len2(st) > 0.0f) ss = unit(st);
@@ -294,8 +306,10 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
         // SurfaceInteraction::set_shading_geometry(ss, ts, .., true) (interaction.rs:297-316)
         v.sn = unit(cross3(ss, ts));
         v.n = face_toward(v.n, v.sn);                                    // D6 FIX
-        v.sdpdu = ss;
+        sdpdu = ss;
     }
+    v.ss = unit(sdpdu);                                                  // BSDF::new (reflection.rs:220-234)
+    v.ts = cross3(v.sn, v.ss);
     return v;
 }
 // estimate_direct (integrator.rs:136-266) up to the two visibility queries: fills the NEE record of `slot`.
@@ -367,10 +381,10 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
         const float b0 = 1.0f - su0, b1 = ul1 * su0;                     // sampling.rs:275-278
         const float b2 = (1.0f - b0) - b1;
         const vec3 ps = (lp0 * b0 + lp1 * b1) + lp2 * b2;
-        vec3 ns = unit(cross3(lp1 - lp0, lp2 - lp0));
+        vec3 ns = ld3(light.ns_sample);                                    // normalize(cross(p1 - p0, p2 - p0)), triangle.rs:336
         if (light.has_n) ns = face_toward(ns, (ld3(light.n0) * b0 + ld3(light.n1) * b1) + ld3(light.n2) * b2);     // triangle.rs:338-341, D6 FIX
         const vec3 pe = ((abs3(lp0 * b0) + abs3(lp1 * b1)) + abs3(lp2 * b2)) * gammaf_(6.0f);
-        float pdf = 1.0f / light.area;
+        float pdf = light.inv_area;                                        // 1 / area (shape.rs:43)
         vec3 w = ps - v.p;
         if (len2(w) == 0.0f) pdf = 0.0f;
         else {
@@ -441,14 +455,11 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
                 // Light::pdf_li -> Shape::pdf2 (shape.rs:54-69): the light's own triangle
                 const RayCtx rc = make_ray_ctx(ro, wi);
                 float t;
-                vec3 du, dv;
-                const bool frame_ok = light.has_uv ? tri_frame_uv(lp0, lp1, lp2, make_float2(light.uv[0], light.uv[1]), make_float2(light.uv[2], light.uv[3]),
-                                                                   make_float2(light.uv[4], light.uv[5]), &du, &dv)
-                                                   : tri_frame(lp0, lp1, lp2, &du, &dv);
+                const bool frame_ok = light.frame_ok != 0;               // Triangle::intersect's degenerate-frame exit, per triangle
                 if (!tri_test(rc, kInf, lp0, lp1, lp2, &t, &lb0, &lb1, &lb2) || !frame_ok) go = false;
                 else {
                     const vec3 p_l = (lp0 * lb0 + lp1 * lb1) + lp2 * lb2;
-                    const vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                    const vec3 n_l = ld3(light.n_hit);
                     float lp = len2(v.p - p_l) / (fabsf(dot3(n_l, -wi)) * light.area);
                     if (isinf(lp)) lp = 0.0f;
                     if (lp == 0.0f) go = false;
@@ -459,7 +470,7 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
                 // li = light_isect.le(-wi) if the closest hit is this light's triangle (D56 FIX); its normal is known here:
                 // the geometric one, or — on a mesh with vertex normals / tangents — the one Triangle::intersect leaves in the
                 // interaction at these barycentrics (flipped towards the shading normal, set_shading_geometry)
-                vec3 n_l = unit(cross3(lp0 - lp2, lp1 - lp2));
+                vec3 n_l = ld3(light.n_hit);
                 if (SG && !sampled_specular) n_l = rebuild_vertex<true>(s, sh, light.prim, lb0, lb1, lb2).n;
                 const rgb3 lmis = (light.two_sided || dot3(n_l, -wi) > 0.0f) ? l_emit : gray(0.0f);
                 if (!black(lmis)) {

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
         bool alive = bounces < (unsigned)pp.max_depth;                   // path.rs:90-92
         unsigned queued = (unsigned)Q;                                 // b.state[slot]: class | continues << 2 | NEE rays << 3
         if (alive) {
-            const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.sn, v.sdpdu);
+            const auto bsdf = make_bsdf<MAT>(sh.mats[sh.tri_material[h.x]], v.n, v.sn, v.ss, v.ts);
             PathSampler rng;
             rng.resume(map.smp, slot_info(map, film, slot), b.rng[slot], TABLES ? (state >> 17) & 0x3FFFu : 0u);
             // (class 2 holds specular lobes only — FresnelSpecular, SpecularReflection — so estimate_direct is never reached there)

@@ -112,7 +112,7 @@ __device__ __forceinline__ bool vol_surface(const SceneView& s, const ShadeView&
                                             int med_out, PathSampler& smp, rgb3* L, rgb3* beta, float* eta_scale, bool* specular, vec3* wi_out,
                                             unsigned long long* n_shadow, unsigned long long* n_mis) {
     const Vertex& v = hit.v;
-    const auto bsdf = make_bsdf<CLS>(sh.mats[sh.tri_material[hit.h.prim]], v.n, v.sn, v.sdpdu);
+    const auto bsdf = make_bsdf<CLS>(sh.mats[sh.tri_material[hit.h.prim]], v.n, v.sn, v.ss, v.ts);
     *L = *L + *beta * vol_sample_one_light(s, sh, b, v, v.wo, bsdf, med_in, med_out, smp, n_shadow, n_mis);      // at every surface vertex (volpath.rs:137-146)
     const vec3 wo = -ray_d;
     float u0, u1, pdf = 0.0f;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) k_volpath(uint64_t n, SceneView s, ShadeV
                 smp.next2(&p0, &p1);
                 hg_sample_p(m.g, wo, &wi, p0, p1);                       // volpath.rs:96-103: sampled before the light (KEEP)
                 Vertex v;
-                v.p = mp; v.err = mk(0.f, 0.f, 0.f); v.n = mk(0.f, 0.f, 0.f); v.dpdu = mk(0.f, 0.f, 0.f); v.sn = v.n; v.sdpdu = v.dpdu; v.wo = wo;
+                v.p = mp; v.err = mk(0.f, 0.f, 0.f); v.n = mk(0.f, 0.f, 0.f); v.sn = v.n; v.ss = v.n; v.ts = v.n; v.wo = wo;
                 const PhaseHG ph{m.g, mk(0.f, 0.f, 0.f)};
                 o = mp;                                                  // mi.spawn_ray(wi): no normal, no offset; the medium stays
                 d = wi;

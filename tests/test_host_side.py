@@ -211,3 +211,16 @@ def test_host_build_with_analytic_spheres_equals_oracle(pb2, scenes):
     assert L.pb2_scene_add_spheres(s2.h, C.cast(arr, C.c_void_p), 1) == -1 and b"radius" in L.pb2_last_error()
     arr = (pb2.Sphere * 1)(pb2.sphere_from_dict(dict(center=(0, 0, 0), radius=1.0)))
     assert L.pb2_scene_add_spheres(mine.scene.h, C.cast(arr, C.c_void_p), 1) == -3
+
+
+def test_nudge_equals_next_float_up_down(tmp_path):
+    """offset_ray_origin's branch-free step (pb2_math.cuh nudge) == next_float_up / next_float_down (pbrt.rs:43-77, geometry.rs:1146-1152)
+    on every 251st binary32 value and the special values; `tools/nudge_check.cpp` without an argument is the exhaustive run."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "nudge_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-o", exe, os.path.join(root, "tools", "nudge_check.cpp")])
+    out = subprocess.run([exe, "251"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 differences" in out.stdout
