@@ -283,6 +283,7 @@ static ShadeView shade_view(const pb2_scene* s, int strategy) {
     v.prim_inside = (const int32_t*)s->d_prim_inside;
     v.prim_outside = (const int32_t*)s->d_prim_outside;
     v.camera_medium = s->d_media ? s->camera_medium : -1;
+    v.has_interfaces = s->has_material_less ? 1 : 0;
     return v;
 }
 

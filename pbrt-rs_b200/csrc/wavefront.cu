@@ -712,10 +712,10 @@ unsigned grid_for(const Wavefront* wf, uint64_t n, int per_sm = 8) {
 
 // Stable three-way select of the active queue `in` by the paths' state bytes (see SelectJob); counts stay on the device.
 void compact_queues(Wavefront* wf, const uint32_t* in, int n_in, bool by_class, uint32_t* o0, int c0, uint32_t* o1, int c1, uint32_t* o2, int c2,
-                    cudaStream_t st) {
+                    cudaStream_t st, const uint8_t* state = nullptr) {
     const PathBuffers& b = wf->b;
     SelectJob j;
-    j.in = in; j.n_in = b.counters + n_in; j.state = b.state; j.by_class = by_class ? 1 : 0;
+    j.in = in; j.n_in = b.counters + n_in; j.state = state ? state : b.state; j.by_class = by_class ? 1 : 0;
     j.out[0] = o0; j.out[1] = o1; j.out[2] = o2;
     j.n_out[0] = b.counters + c0; j.n_out[1] = b.counters + c1; j.n_out[2] = b.counters + c2;
     j.status = b.select_status;
@@ -741,9 +741,12 @@ void launch_shade(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const
 void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film, const PathMap& map,
                  const PathParams& pp, uint64_t n, cudaStream_t st) {
     PathBuffers& b = wf->b;
-    if (pp.integrator == 1) {                                            // VolPathIntegrator: one kernel carries whole paths
-        launch_volpath(wf, grid_for(wf, n), n, sv, sh, b, map, film, cam, pp, st);
-        wf->totals[4] += 1;
+    if (pp.integrator == 1) {                                            // VolPathIntegrator (wavefront_volpath.cu)
+        static const bool mega = [] { const char* e = getenv("PB2_VOLPATH_MEGAKERNEL"); return e && atoi(e) != 0; }();
+        if (mega) {                                                      // one thread carries a whole path (the first device version; kept for comparison)
+            launch_volpath(wf, grid_for(wf, n), n, sv, sh, b, map, film, cam, pp, st);
+            wf->totals[4] += 1;
+        } else trace_batch_vol(wf, sv, sh, cam, film, map, pp, n, st);
         return;
     }
     const TraceTuning tune = trace_tuning();
@@ -772,6 +775,15 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
 }
 
 }  // namespace
+
+// the queue select and ray generation for the other translation units (wavefront_volpath.cu)
+void select_queues(Wavefront* wf, const uint32_t* in, int n_in, bool by_class, uint32_t* o0, int c0, uint32_t* o1, int c1, uint32_t* o2, int c2,
+                   cudaStream_t st, const uint8_t* state) {
+    compact_queues(wf, in, n_in, by_class, o0, c0, o1, c1, o2, c2, st, state);
+}
+void launch_raygen(Wavefront* wf, uint64_t n, const PathMap& map, const FilmView& film, const CameraView& cam, cudaStream_t st) {
+    k_raygen<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, cam, wf->b);
+}
 
 int wavefront_create(uint64_t capacity, Wavefront** out) {
     Wavefront* wf = new Wavefront();
@@ -806,6 +818,7 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
     b.q_mis = (uint32_t*)take(capacity * 4);
     b.counters = (unsigned long long*)take(C_COUNT * 8);
     cudaMemset(b.counters, 0, C_COUNT * 8);
+    cudaMallocHost((void**)&wf->h_counters, C_COUNT * 8);
     *out = wf;
     return 0;
 }
@@ -813,6 +826,8 @@ int wavefront_create(uint64_t capacity, Wavefront** out) {
 void wavefront_destroy(Wavefront* wf) {
     if (!wf) return;
     if (wf->arena) cudaFree(wf->arena);
+    if (wf->vol_arena) cudaFree(wf->vol_arena);
+    if (wf->h_counters) cudaFreeHost(wf->h_counters);
     delete wf;
 }
 

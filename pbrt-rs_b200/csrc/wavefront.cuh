@@ -58,6 +58,7 @@ struct ShadeView {
     const int32_t* prim_inside;
     const int32_t* prim_outside;
     int camera_medium;
+    int has_interfaces;           // some primitive has no material (a medium interface): paths and transmittance rays cross it
 };
 
 // Film geometry: image, sample bounds (film.rs:76-81 with D42), filter radius and its 16x16 table (film.rs:53-63).
@@ -117,7 +118,9 @@ struct PathMap {
 enum Counter : int {
     C_ACTIVE_A = 0, C_ACTIVE_B = 1, C_MAT0 = 2, C_MAT1 = 3, C_MAT2 = 4, C_SHADOW = 5, C_MIS = 6, C_MIS_PREV = 7,
     C_WORK_EXTEND = 8, C_WORK_SHADOW = 9, C_WORK_MIS = 10, C_STRAYS = 11, C_STRAY_OVERFLOW = 12,
-    T_CAMERA = 16, T_EXTEND = 17, T_SHADOW = 18, T_MIS = 19, T_LAUNCHES = 20, C_COUNT = 24
+    T_CAMERA = 16, T_EXTEND = 17, T_SHADOW = 18, T_MIS = 19, T_LAUNCHES = 20,
+    // wavefront VolPathIntegrator: the transmittance rays that cross an interface and go on (two buffers each), unused select outputs
+    C_VOL_S_ALT = 24, C_VOL_M_ALT = 25, C_VOL_SCRATCH = 26, C_COUNT = 32
 };
 
 struct PathBuffers {
@@ -149,6 +152,28 @@ struct PathBuffers {
     unsigned* select_tickets;              // two tile counters, used by alternate launches
 };
 
+// What the wavefront VolPathIntegrator (wavefront_volpath.cu) keeps per path slot beside PathBuffers; allocated at its first use.
+// In that mode the NEE record holds the factors of estimate_direct's two terms unmultiplied (the transmittance enters the
+// product before f, integrator.rs:172-173, 259-261): t1 = {li, w1}, f1 = {f |cos|, light_pdf (negated: delta light)},
+// t2 = {lmis * f2, light primitive}, mis_o.w = scattering_pdf, mis_d.w = w2, sh_d.w = pick pdf, beta_nee = beta at the vertex.
+struct VolBuffers {
+    int32_t* med;         // medium of the path ray (-1 = vacuum)
+    float* t_path;        // where the path ray's walk ended: the closest hit's distance, or the ray's own t_max
+    float4* f1;
+    float4* p1;           // VisibilityTester's far end (light.rs:137-160): every segment of the shadow ray is re-aimed at it
+    float4* p1_err;
+    float4* p1_n;
+    float4* tr_s;         // transmittance gathered by the shadow ray so far (rgb)
+    float4* tr_m;         // ... by the MIS ray (Scene::intersect_tr, scene.rs:48-71); w = 1: it ended on a surface with a material
+    int2* ray_med;        // medium of the current segment: x shadow ray, y MIS ray
+    uint4* hit_s;         // closest hit of the current segment (prim, b0 | t for a sphere, b1, b2)
+    uint4* hit_m;
+    float* t_s;
+    float* t_m;
+    uint8_t* st_s;        // after the walk: 1 = a hit; after k_vol_tr_post: 0 = another segment follows, 3 = done
+    uint8_t* st_m;
+};
+
 struct PathParams {
     int max_depth;
     float rr_threshold;
@@ -161,6 +186,9 @@ struct Wavefront {
     void* arena = nullptr;
     int sm_count = 0;
     unsigned select_launches = 0;          // k_select3 launches so far: picks the ticket counter and the epoch
+    VolBuffers vol{};                      // wavefront VolPathIntegrator state (vol_arena; null until the first volpath render)
+    void* vol_arena = nullptr;
+    unsigned long long* h_counters = nullptr;   // pinned: queue counts read back between volpath iterations (interface scenes only)
     uint64_t totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 

@@ -33,6 +33,14 @@ template <> void launch_shade_t<true, true>(Wavefront* wf, const SceneView& sv, 
 void launch_volpath(Wavefront* wf, unsigned grid, uint64_t n, const SceneView& sv, const ShadeView& sh, const PathBuffers& b, const PathMap& map,
                     const FilmView& film, const CameraView& cam, const PathParams& pp, cudaStream_t st);
 
+// the wavefront VolPathIntegrator: all iterations of one batch of n path slots (wavefront_volpath.cu)
+void trace_batch_vol(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const CameraView& cam, const FilmView& film, const PathMap& map,
+                     const PathParams& pp, uint64_t n, cudaStream_t st);
+// wavefront.cu: the stable three-way queue select (k_select3) over `state` (null: PathBuffers::state) and k_raygen
+void select_queues(Wavefront* wf, const uint32_t* in, int n_in, bool by_class, uint32_t* o0, int c0, uint32_t* o1, int c1, uint32_t* o2, int c2,
+                   cudaStream_t st, const uint8_t* state = nullptr);
+void launch_raygen(Wavefront* wf, uint64_t n, const PathMap& map, const FilmView& film, const CameraView& cam, cudaStream_t st);
+
 namespace {
 
 constexpr float kInf = __builtin_huge_valf();
@@ -323,6 +331,7 @@ struct NeeOut {
     rgb3 lmis, f2;          // BSDF / phase sample: the light's radiance towards the vertex and f (* |cos|)
     float w2, scattering_pdf;
     vec3 mis_o, mis_d;
+    vec3 sh_o, sh_d;        // the first segment of the shadow ray (spawn_ray_to, interaction.rs:146-153)
     unsigned light_prim;
 };
 template <bool SG, class BsdfType>
@@ -487,6 +496,8 @@ __device__ __forceinline__ unsigned direct_lighting(const SceneView& s, const Sh
     if (out) {
         out->mis_o = mis_o;
         out->mis_d = mis_d;
+        out->sh_o = sh_o;
+        out->sh_d = sh_d;
         out->light_prim = light.prim;
         return pending;
     }
