@@ -443,7 +443,7 @@ def bench_path_extras(pb2, scenes, torch, rank, no_cpu):
     """The two shapes / integrators added after the BASELINE configs, so that they have measured numbers
     too: the Cornell room with ANALYTIC spheres (shapes/sphere.rs: EFloat quadratic in k_extend_spheres / k_shadow_spheres, a
     spherical area light) under the wavefront PathIntegrator, and the fog + smoke scene under the VolPathIntegrator
-    (integrators/volpath.rs, media/homogeneous.rs: k_volpath, one thread per camera sample).  Each with a bit-for-bit parity
+    (integrators/volpath.rs, media/homogeneous.rs: the wavefront stages of wavefront_volpath.cu).  Each with a bit-for-bit parity
     check of sample index 0 of every pixel against the oracle."""
     out = {}
     stream = torch.cuda.current_stream().cuda_stream

@@ -151,8 +151,11 @@ enum { PB2_SAMPLER_RANDOM = 0, PB2_SAMPLER_HALTON = 1, PB2_SAMPLER_STRATIFIED = 
 /* PB2_INTEGRATOR_PATH: PathIntegrator (src/integrators/path.rs), the wavefront pipeline.  PB2_INTEGRATOR_VOLPATH:
  * VolPathIntegrator (src/integrators/volpath.rs:60-244) over HomogeneousMedium — medium sampling, Henyey-Greenstein phase
  * vertices, next-event estimation with transmittance (VisibilityTester::tr, src/core/light.rs:137-160) and MIS through
- * Scene::intersect_tr (src/core/scene.rs:48-71), one thread per camera sample (k_volpath); samplers: random, stratified, (0,2)
- * (the number of dimensions a volumetric path draws is unbounded, which the 1000 / 1024-dimension Halton / Sobol' tables are not). */
+ * Scene::intersect_tr (src/core/scene.rs:48-71), as wavefront stages of their own (wavefront_volpath.cu); samplers: random,
+ * stratified, (0,2) (the number of dimensions a volumetric path draws is unbounded, which the 1000 / 1024-dimension Halton /
+ * Sobol' tables are not).  A scene with material-less interface surfaces is rendered with host read-backs of queue counts between
+ * stages (crossing an interface is not a bounce, so the number of iterations is not known in advance): pb2_render_path then
+ * returns when the frame is done instead of when it is enqueued. */
 enum { PB2_INTEGRATOR_PATH = 0, PB2_INTEGRATOR_VOLPATH = 1 };
 /* src/integrators/path.rs:31-46 PathIntegrator::new + src/samplers/random.rs:17-27 RandomSampler::new */
 typedef struct pb2_path_desc {

@@ -850,6 +850,11 @@ int pb2_render_counters(pb2_scene* scene, uint64_t out[8]) {
     out[0] = c[T_CAMERA]; out[1] = c[T_EXTEND]; out[2] = c[T_SHADOW]; out[3] = c[T_MIS];
     out[4] = scene->wf->totals[4];
     out[5] = c[C_STRAY_OVERFLOW];
+    if (scene->wf->peer) {                                 // the second wavefront of frames rendered two batches at a time
+        PB2_CUDA(cudaMemcpy(c, scene->wf->peer->b.counters, sizeof c, cudaMemcpyDeviceToHost));
+        out[0] += c[T_CAMERA]; out[1] += c[T_EXTEND]; out[2] += c[T_SHADOW]; out[3] += c[T_MIS];
+        out[4] += scene->wf->peer->totals[4];
+    }
     return PB2_OK;
 }
 

@@ -189,6 +189,12 @@ struct Wavefront {
     VolBuffers vol{};                      // wavefront VolPathIntegrator state (vol_arena; null until the first volpath render)
     void* vol_arena = nullptr;
     unsigned long long* h_counters = nullptr;   // pinned: queue counts read back between volpath iterations (interface scenes only)
+    // A frame of several batches alternates them between this wavefront on the caller's stream and `peer` (a second arena of the
+    // same size, created at the first such frame) on `aux_stream`, so that one batch's launches fill the ramps and tails of the
+    // other's persistent kernels; the film accumulation of the batches stays in batch order (ev_acc).
+    Wavefront* peer = nullptr;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc[2] = {nullptr, nullptr};
     uint64_t totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 

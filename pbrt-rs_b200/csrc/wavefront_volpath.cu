@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128) k_volpath(uint64_t n, SceneView s, ShadeV
 //                  (queues re-selected, counts read back) while a ray has a segment left; scenes without interfaces take one round
 //   k_vol_resolve  l += beta * ld / pick_pdf for the iteration's NEE records, in the reference's order of terms
 // A path's additions to L happen in the order of volpath.rs (Le at a vertex, then that vertex's direct light, then the next
-// vertex), and every path draws its sampler in that order too, so the radiance equals k_volpath's and the oracle's bit for bit.
+// vertex), and every path draws its sampler in that order too, so the radiance equals k_volpath's bit for bit.
 constexpr uint8_t kTrDone = 3, kTrAgain = 0;       // VolBuffers::st_s / st_m after k_vol_tr_post (the select's class predicate)
 
 __device__ __forceinline__ uint32_t pack_path_word(unsigned bounces, bool spec, unsigned extra) { return bounces | ((spec ? 1u : 0u) << 16) | (extra << 17); }
