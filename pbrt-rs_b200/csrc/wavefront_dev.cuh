@@ -275,7 +275,7 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
     const float zs = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z)) + fabsf(b2 * p2.z);
     v.err = mk(xs, ys, zs) * gammaf_(7.0f);
     v.p = (p0 * b0 + p1 * b1) + p2 * b2;
-    if (!SG) {                                                 // plain mesh: the per-primitive frame
+    if (!SG || !sh.indices) {                                  // plain triangle (also in a scene with analytic spheres): the per-primitive frame
         const float4 fn = ldg4(tp + 3), fs = ldg4(tp + 4), ft = ldg4(tp + 5);
         v.n = mk(fn.x, fn.y, fn.z);
         v.sn = v.n;
@@ -285,13 +285,6 @@ __device__ __forceinline__ Vertex rebuild_vertex(const SceneView& s, const Shade
     }
     v.n = unit(cross3(p0 - p2, p1 - p2));
     vec3 dpdu, dv;
-    if (!sh.indices) {                                         // (SG without mesh attributes: a scene that has analytic spheres)
-        tri_frame(p0, p1, p2, &dpdu, &dv);
-        v.sn = v.n;
-        v.ss = unit(dpdu);
-        v.ts = cross3(v.sn, v.ss);
-        return v;
-    }
     const uint32_t i0 = __ldg(sh.indices + 3ull * prim), i1 = __ldg(sh.indices + 3ull * prim + 1), i2 = __ldg(sh.indices + 3ull * prim + 2);
     if (sh.uvs) tri_frame_uv(p0, p1, p2, __ldg(sh.uvs + i0), __ldg(sh.uvs + i1), __ldg(sh.uvs + i2), &dpdu, &dv);   // Triangle::get_uvs
     else tri_frame(p0, p1, p2, &dpdu, &dv);

@@ -10,7 +10,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scene", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--scene", default="c2", choices=["c2", "c4", "spheres", "media"])
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1)
     args = ap.parse_args()
@@ -18,6 +18,11 @@ def main():
     pb2.init(0)
     if args.scene == "c2":
         sc, cam, pk = scenes.scene_c2(), scenes.C2_CAMERA, dict(scenes.C2_PATH, spp=args.spp)
+    elif args.scene == "spheres":      # bench.py path_extras.spheres
+        sc, cam, pk = scenes.scene_spheres(), dict(scenes.C2_CAMERA, res=(1024, 1024)), dict(max_depth=5, rr_threshold=1.0, light_strategy="power", spp=args.spp)
+    elif args.scene == "media":        # bench.py path_extras.volpath
+        sc, cam = scenes.scene_media(), dict(scenes.C2_CAMERA, res=(512, 512))
+        pk = dict(max_depth=8, rr_threshold=1.0, light_strategy="power", integrator="volpath", spp=args.spp)
     else:
         sc, cam, pk = scenes.scene_c4(), scenes.C4_CAMERA, dict(scenes.C4_PATH, spp=args.spp)
     accel = pb2.BVHAccel(pb2.scene_from_dict(sc), max_prims_in_node=4)
