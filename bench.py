@@ -580,14 +580,13 @@ def main():
         mark(1)
         accel.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), d_b0.data_ptr(), stream)
         mark(2)
-        accel.spawn_shadow_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, scenes.C3_POINT_LIGHT, d_srays.data_ptr(), stream)
-        accel.spawn_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_brays.data_ptr(), stream)
+        accel.spawn_shadow_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, scenes.C3_POINT_LIGHT, d_srays.data_ptr(), d_brays.data_ptr(), stream)
         mark(3)
         accel.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), stream)
         mark(4)
         accel.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
         mark(5)
-    launches_per_step = 6
+    launches_per_step = 5
 
     def barrier():
         if world > 1:

@@ -271,6 +271,10 @@ int pb2_spawn_shadow_rays_device(pb2_scene* scene, const void* d_rays, const voi
  * (src/core/sampling.rs:289-294) drawn from PCG32 stream `i` (src/core/rng.rs). */
 int pb2_spawn_bounce_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n,
                                  void* d_out_rays, void* stream);
+/* Both of the above from one pass over the hits (each hit's triangle is gathered and its interaction rebuilt once); the two
+ * outputs equal those of the separate calls bit for bit. */
+int pb2_spawn_shadow_bounce_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n, const float light_pos[3],
+                                        void* d_out_shadow_rays, void* d_out_bounce_rays, void* stream);
 
 /* ---- RNG (src/core/rng.rs:14-48) — parity hook --------------------------------------------------------- */
 /* out[s*n_per + k] = k-th uniform_float() of RNG::new(first_sequence + s). */

@@ -236,6 +236,7 @@ def lib():
         "pb2_camera_matrices": [vp, vp, vp],
         "pb2_spawn_shadow_rays_device": [vp, vp, vp, u64, vp, vp, vp],
         "pb2_spawn_bounce_rays_device": [vp, vp, vp, u64, vp, vp],
+        "pb2_spawn_shadow_bounce_rays_device": [vp, vp, vp, u64, vp, vp, vp, vp],
         "pb2_rng_uniform_floats": [u64, u32, u32, vp], "pb2_film_bounds": [vp, vp, vp],
         "pb2_film_create": [vp, vp], "pb2_film_destroy": [vp], "pb2_film_clear": [vp],
         "pb2_film_add_samples": [vp, vp, vp, vp, u64], "pb2_film_read_xyzw": [vp, vp],
@@ -437,6 +438,10 @@ class BVHAccel:
 
     def spawn_bounce_rays_device(self, d_rays, d_hits, n, d_out, stream=None):
         check(lib().pb2_spawn_bounce_rays_device(self.h, d_rays, d_hits, n, d_out, stream))
+
+    def spawn_shadow_bounce_rays_device(self, d_rays, d_hits, n, light_pos, d_out_shadow, d_out_bounce, stream=None):
+        lp = np.asarray(light_pos, dtype=np.float32)
+        check(lib().pb2_spawn_shadow_bounce_rays_device(self.h, d_rays, d_hits, n, _p(lp), d_out_shadow, d_out_bounce, stream))
 
 
 class PerspectiveCamera:

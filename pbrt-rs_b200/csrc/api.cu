@@ -765,6 +765,16 @@ int pb2_spawn_bounce_rays_device(pb2_scene* scene, const void* d_rays, const voi
     return PB2_OK;
 }
 
+int pb2_spawn_shadow_bounce_rays_device(pb2_scene* scene, const void* d_rays, const void* d_hits, uint64_t n, const float light_pos[3],
+                                        void* d_out_shadow_rays, void* d_out_bounce_rays, void* stream) {
+    int rc = check_ready(scene);
+    if (rc) return rc;
+    if (!light_pos) return set_error(PB2_ERR_INVALID, "null light position");
+    launch_spawn_shadow_bounce(scene->view, d_rays, d_hits, n, light_pos, d_out_shadow_rays, d_out_bounce_rays, (cudaStream_t)stream);
+    PB2_CUDA(cudaGetLastError());
+    return PB2_OK;
+}
+
 // ---- RNG parity hook ----------------------------------------------------------------------------------------
 int pb2_rng_uniform_floats(uint64_t first_sequence, uint32_t n_sequences, uint32_t n_per, float* out) {
     const uint64_t total = (uint64_t)n_sequences * n_per;

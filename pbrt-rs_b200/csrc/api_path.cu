@@ -460,12 +460,14 @@ static int sampler_view(pb2_scene* scene, const pb2_path_desc* path, int sb_x0, 
 // Path slots of the wavefront (233 B each).  A frame is rendered in batches of floor(slots / pixels) samples per pixel and every
 // batch costs ~7 launches per bounce with their ramp-up and tail, so a batch should hold several samples of every pixel: C4
 // (2.07 M pixels, 32 spp) takes 173.9 / 152.0 / 143.8 / 141.3 ms with 2^22 / 2^23 / 2^24 / 2^25 slots, C2 (262 K pixels, 64 spp)
-// 32.2 / 31.8 / 33.4 / 33.3 ms (gpurun_out/tune_slots.log).  Default: 8 samples of every pixel, at least 2^23 and at most 2^26 slots
-// (15.6 GB); PB2_WAVEFRONT_LOG2_SLOTS overrides it for sweeps.
+// 32.2 / 31.8 / 33.4 / 33.3 ms (gpurun_out/tune_slots.log).  With two batches in flight (Wavefront::peer) C4 @ 32 spp takes 104.6 /
+// 96.5 / 93.1 / 91.3 ms with 2^22..2^25 slots per arena and C2 @ 64 spp 17.7 / 17.5 / 18.0 / 18.1 ms (profiles/r02_slots.log).
+// Default: 16 samples of every pixel, at least 2^23 and at most 2^26 slots (15.6 GB; a frame of several batches holds two such
+// arenas); PB2_WAVEFRONT_LOG2_SLOTS overrides it for sweeps.
 static uint64_t wavefront_slots(uint64_t n_pix) {
     static const int forced = [] { const char* e = getenv("PB2_WAVEFRONT_LOG2_SLOTS"); return e ? std::min(std::max(atoi(e), 16), 28) : 0; }();
     if (forced) return 1ull << forced;
-    return std::min<uint64_t>(std::max<uint64_t>(8 * n_pix, 1ull << 23), 1ull << 26);
+    return std::min<uint64_t>(std::max<uint64_t>(16 * n_pix, 1ull << 23), 1ull << 26);
 }
 static int ensure_wavefront(pb2_scene* scene, uint64_t min_capacity) {
     const uint64_t want = std::max<uint64_t>(min_capacity, wavefront_slots(min_capacity));

@@ -25,6 +25,8 @@ void launch_camera_rays(const CameraView& cam, const void* d_pfilm, const void* 
 void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
                          void* d_out, cudaStream_t st);
 void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st);
+void launch_spawn_shadow_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3], void* d_out_shadow,
+                                void* d_out_bounce, cudaStream_t st);
 void launch_tris_by_prim(const void* d_tris, uint64_t n, void* d_out, cudaStream_t st);
 void launch_mark_degenerate(void* d_tris, uint64_t n, const void* d_indices, const void* d_uvs, cudaStream_t st);
 // Matrix4x4::inverse (transform.rs:46-113; camera_host.cpp)

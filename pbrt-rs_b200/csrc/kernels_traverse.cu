@@ -292,6 +292,48 @@ __global__ void __launch_bounds__(256) k_spawn_bounce(SceneView s, const float4*
     out[2 * i + 1] = d4;
 }
 
+// Both ray sets of the C3 workload from one pass over the hits: the hit's triangle is fetched (a scattered gather in a
+// 10 M-triangle scene) and its interaction rebuilt once instead of once per builder; outputs equal the two kernels above.
+__global__ void __launch_bounds__(256) k_spawn_shadow_bounce(SceneView s, const float4* __restrict__ rays, const uint4* __restrict__ hits,
+                                                              uint64_t n, float lx, float ly, float lz, float4* __restrict__ out_shadow,
+                                                              float4* __restrict__ out_bounce) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 h = hits[i];
+    float4 so = make_float4(0.f, 0.f, 0.f, -1.0f), sd = make_float4(0.f, 0.f, 1.f, 0.f), bo = so, bd = sd;
+    if (h.x != 0xFFFFFFFFu) {
+        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+        SurfPoint sp;
+        const vec3 d_in = mk(rd.x, rd.y, rd.z);
+        if (rebuild_hit(s, mk(ro.x, ro.y, ro.z), d_in, __ldg(s.slot_of_prim + h.x), &sp)) {
+            {
+                const vec3 target = mk(lx, ly, lz);
+                const vec3 d = target - sp.p;
+                const vec3 o = offset_ray_origin(sp.p, sp.p_err, sp.n, d);
+                so = make_float4(o.x, o.y, o.z, 1.0f - PB2_SHADOW_EPS);
+                sd = make_float4(d.x, d.y, d.z, 0.0f);
+            }
+            vec3 nn = sp.n;
+            if (dot3(nn, d_in) > 0.0f) nn = -nn;
+            Pcg32 rng;
+            rng.set_sequence(i);
+            const float u0 = rng.next_float();
+            const float u1 = rng.next_float();
+            const vec3 l = cosine_hemisphere(u0, u1);
+            vec3 sdir, tdir;
+            coord_system(nn, &sdir, &tdir);
+            const vec3 wi = (sdir * l.x + tdir * l.y) + nn * l.z;
+            const vec3 o = offset_ray_origin(sp.p, sp.p_err, sp.n, wi);
+            bo = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+            bd = make_float4(wi.x, wi.y, wi.z, 0.0f);
+        }
+    }
+    out_shadow[2 * i] = so;
+    out_shadow[2 * i + 1] = sd;
+    out_bounce[2 * i] = bo;
+    out_bounce[2 * i + 1] = bd;
+}
+
 void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3],
                          void* d_out, cudaStream_t st) {
     if (n == 0) return;
@@ -302,6 +344,13 @@ void launch_spawn_shadow(const SceneView& s, const void* d_rays, const void* d_h
 void launch_spawn_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, void* d_out, cudaStream_t st) {
     if (n == 0) return;
     k_spawn_bounce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, (const float4*)d_rays, (const uint4*)d_hits, n, (float4*)d_out);
+}
+
+void launch_spawn_shadow_bounce(const SceneView& s, const void* d_rays, const void* d_hits, uint64_t n, const float light[3], void* d_out_shadow,
+                                void* d_out_bounce, cudaStream_t st) {
+    if (n == 0) return;
+    k_spawn_shadow_bounce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, (const float4*)d_rays, (const uint4*)d_hits, n, light[0], light[1], light[2],
+                                                                         (float4*)d_out_shadow, (float4*)d_out_bounce);
 }
 
 __global__ void __launch_bounds__(256) k_rng_floats(uint64_t first_seq, uint32_t n_seq, uint32_t n_per, float* __restrict__ out) {

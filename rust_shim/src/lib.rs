@@ -271,6 +271,9 @@ extern "C" {
                                         light_pos: *const f32, d_out_rays: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn pb2_spawn_bounce_rays_device(scene: *mut pb2_scene, d_rays: *const c_void, d_hits: *const c_void, n: u64,
                                         d_out_rays: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn pb2_spawn_shadow_bounce_rays_device(scene: *mut pb2_scene, d_rays: *const c_void, d_hits: *const c_void, n: u64,
+                                               light_pos: *const f32, d_out_shadow_rays: *mut c_void, d_out_bounce_rays: *mut c_void,
+                                               stream: *mut c_void) -> c_int;
     // RNG parity hook
     pub fn pb2_rng_uniform_floats(first_sequence: u64, n_sequences: u32, n_per: u32, out: *mut f32) -> c_int;
     // Film

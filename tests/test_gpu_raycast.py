@@ -173,7 +173,12 @@ def _c3_pass(gpu, accel, camera, n, light):
     accel.spawn_bounce_rays_device(d_rays.ptr, d_hits.ptr, n, d_brays.ptr)
     accel.intersect_p_device(d_srays.ptr, n, d_occ.ptr)
     accel.intersect_device(d_brays.ptr, n, d_bhits.ptr)
+    # the one-pass builder (bench.py) writes the same two ray sets
+    d_s2, d_b2 = gpu.DeviceBuffer(n * 32), gpu.DeviceBuffer(n * 32)
+    accel.spawn_shadow_bounce_rays_device(d_rays.ptr, d_hits.ptr, n, light, d_s2.ptr, d_b2.ptr)
     gpu.check(gpu.lib().pb2_device_synchronize())
+    assert np.array_equal(d_s2.download(np.uint32, n * 8), d_srays.download(np.uint32, n * 8))
+    assert np.array_equal(d_b2.download(np.uint32, n * 8), d_brays.download(np.uint32, n * 8))
     return dict(rays=d_rays.download(np.float32, n * 8).reshape(-1, 8), hits=d_hits.download(gpu.HIT_DTYPE, n),
                 b0=d_b0.download(np.float32, n), srays=d_srays.download(np.float32, n * 8).reshape(-1, 8),
                 brays=d_brays.download(np.float32, n * 8).reshape(-1, 8), occ=d_occ.download(np.uint8, n),
