@@ -249,6 +249,10 @@ int pb2_intersect_p(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* 
 int pb2_intersect_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, pb2_hit* hits, float* b0);
 int pb2_intersect_p_async(pb2_scene* scene, const pb2_ray* rays, uint64_t n, uint8_t* out);
 int pb2_scene_wait(pb2_scene* scene);
+/* Returns when all but the `in_flight` most recently enqueued _async batches have their results in the caller's buffers
+ * (in_flight = 0: pb2_scene_wait).  A caller that produces batches continuously keeps a few in flight — enqueue the next
+ * ones, then wait for the older ones — so that the ring never drains between them. */
+int pb2_scene_wait_until(pb2_scene* scene, uint32_t in_flight);
 /* Device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`). */
 int pb2_intersect_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_hits, void* d_b0, void* stream);
 int pb2_intersect_p_device(pb2_scene* scene, const void* d_rays, uint64_t n, void* d_out, void* stream);

@@ -230,7 +230,7 @@ def lib():
         "pb2_scene_build_bvh": [vp, i32, i32], "pb2_scene_build_bvh_host": [vp, i32, i32], "pb2_world_bound": [vp, vp], "pb2_bvh_info": [vp, vp, vp, vp],
         "pb2_bvh_export": [vp, vp, vp], "pb2_bvh_build_stats": [vp, vp],
         "pb2_intersect": [vp, vp, u64, vp, vp], "pb2_intersect_p": [vp, vp, u64, vp],
-        "pb2_intersect_async": [vp, vp, u64, vp, vp], "pb2_intersect_p_async": [vp, vp, u64, vp], "pb2_scene_wait": [vp],
+        "pb2_intersect_async": [vp, vp, u64, vp, vp], "pb2_intersect_p_async": [vp, vp, u64, vp], "pb2_scene_wait": [vp], "pb2_scene_wait_until": [vp, C.c_uint32],
         "pb2_intersect_device": [vp, vp, u64, vp, vp, vp], "pb2_intersect_p_device": [vp, vp, u64, vp, vp],
         "pb2_camera_generate_rays": [vp, vp, vp, u64, vp], "pb2_camera_primary_rays_device": [vp, vp, vp],
         "pb2_camera_matrices": [vp, vp, vp],

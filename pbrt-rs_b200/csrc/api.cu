@@ -76,6 +76,8 @@ void pb2_scene::free_device() {
     if (pipe.pending && pipe.d2h) cudaStreamSynchronize(pipe.d2h);      // _async batches still in flight
     pipe.pending = false;
     pipe.chunks = 0;
+    pipe.batches = 0;
+    for (cudaEvent_t& e : pipe.batch_done) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (int i = 0; i < kStages; ++i) {
         Stage& st = pipe.slot[i];
         if (st.d_in) cudaFree(st.d_in);
@@ -642,7 +644,15 @@ static int run_pipe(pb2_scene* scene, const pb2_ray* rays, uint64_t n, size_t ou
         if (b0) PB2_CUDA(cudaMemcpyAsync(b0 + off, st.d_aux, m * 4, cudaMemcpyDeviceToHost, p.d2h));
         PB2_CUDA(cudaEventRecord(st.drained, p.d2h));
     }
-    if (!wait) { p.pending = true; return PB2_OK; }
+    if (!wait) {
+        cudaEvent_t& ev = p.batch_done[p.batches % Pipe::kBatchRing];
+        if (!ev) PB2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else if (p.batches >= (uint64_t)Pipe::kBatchRing) PB2_CUDA(cudaEventSynchronize(ev));     // (the batch that used it 64 batches ago)
+        PB2_CUDA(cudaEventRecord(ev, p.d2h));
+        ++p.batches;
+        p.pending = true;
+        return PB2_OK;
+    }
     PB2_CUDA(cudaStreamSynchronize(p.d2h));               // in-order stream: earlier _async batches are out as well
     p.pending = false;
     return PB2_OK;
@@ -682,6 +692,23 @@ int pb2_scene_wait(pb2_scene* scene) {
     PB2_CUDA(cudaSetDevice(scene->device));
     PB2_CUDA(cudaStreamSynchronize(scene->pipe.d2h));
     scene->pipe.pending = false;
+    return PB2_OK;
+}
+
+int pb2_scene_wait_until(pb2_scene* scene, uint32_t in_flight) {
+    if (!scene) return set_error(PB2_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    Pipe& p = scene->pipe;
+    if (!p.pending || p.batches <= (uint64_t)in_flight) return PB2_OK;
+    PB2_CUDA(cudaSetDevice(scene->device));
+    if (in_flight == 0) {
+        PB2_CUDA(cudaStreamSynchronize(p.d2h));
+        p.pending = false;
+        return PB2_OK;
+    }
+    if (in_flight >= (uint32_t)Pipe::kBatchRing) return PB2_OK;      // (older batches were waited for when their events were reused)
+    const uint64_t last = p.batches - 1 - in_flight;                   // the newest batch that must be complete; the d2h stream is in order
+    PB2_CUDA(cudaEventSynchronize(p.batch_done[last % Pipe::kBatchRing]));
     return PB2_OK;
 }
 

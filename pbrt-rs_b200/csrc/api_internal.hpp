@@ -44,6 +44,11 @@ struct Pipe {
     Stage slot[kStages];
     uint64_t chunks = 0;                // chunks enqueued so far, over all calls: picks the slot and the compute stream
     bool pending = false;               // work enqueued by an _async entry point that pb2_scene_wait has not yet waited for
+    // one event per _async batch, recorded behind its last D2H copy (pb2_scene_wait_until); a ring: before an event is reused
+    // its previous batch is waited for, so at most kBatchRing batches are ever un-waited
+    static constexpr int kBatchRing = 64;
+    cudaEvent_t batch_done[kBatchRing] = {};
+    uint64_t batches = 0;               // _async batches enqueued so far
 };
 
 struct Wavefront;

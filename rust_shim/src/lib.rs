@@ -259,6 +259,7 @@ extern "C" {
     pub fn pb2_intersect_async(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, hits: *mut pb2_hit, b0: *mut f32) -> c_int;
     pub fn pb2_intersect_p_async(scene: *mut pb2_scene, rays: *const pb2_ray, n: u64, out: *mut u8) -> c_int;
     pub fn pb2_scene_wait(scene: *mut pb2_scene) -> c_int;
+    pub fn pb2_scene_wait_until(scene: *mut pb2_scene, in_flight: u32) -> c_int;
     pub fn pb2_intersect_device(scene: *mut pb2_scene, d_rays: *const c_void, n: u64, d_hits: *mut c_void, d_b0: *mut c_void,
                                 stream: *mut c_void) -> c_int;
     pub fn pb2_intersect_p_device(scene: *mut pb2_scene, d_rays: *const c_void, n: u64, d_out: *mut c_void, stream: *mut c_void) -> c_int;
@@ -500,6 +501,15 @@ impl B200Accel {
     pub fn wait(&self, pending: Vec<PendingBatch<'_>>) {
         unsafe { check(pb2_scene_wait(self.scene)) };
         drop(pending);
+    }
+
+    /// Blocks until all but the `keep` newest batches are complete (`pb2_scene_wait_until`) and hands those back: a producer of
+    /// batches (one per tile) enqueues ahead and retires the older ones, so the copy ring never drains between batches.
+    pub fn wait_until<'a>(&self, mut pending: Vec<PendingBatch<'a>>, keep: usize) -> Vec<PendingBatch<'a>> {
+        unsafe { check(pb2_scene_wait_until(self.scene, keep as u32)) };
+        let done = pending.len().saturating_sub(keep);
+        pending.drain(..done);
+        pending
     }
 
     /// `(n_nodes, n_prims, max_depth)` of the flattened tree (`pb2_bvh_info`).

@@ -460,6 +460,18 @@ def test_async_entry_points_match_the_synchronous_ones(gpu, orc, scenes):
             C.memset(p_h, 0xFF, n * 16)
             C.memset(p_o, 0xFF, n)
     gpu.check(L.pb2_scene_wait(accel.h))          # nothing pending: returns at once
+    # pb2_scene_wait_until(k): all but the k newest batches are complete when it returns (the ring is in order)
+    for k, (n, rays, p_r, p_h, p_b, p_o) in enumerate(batches):
+        gpu.check(L.pb2_intersect_async(accel.h, p_r, n, p_h, None))
+    gpu.check(L.pb2_scene_wait_until(accel.h, 2))
+    for k, (n, rays, p_r, p_h, p_b, p_o) in enumerate(batches[:-2]):
+        if n:
+            hits = np.frombuffer((C.c_char * (n * 16)).from_address(p_h.value), dtype=gpu.HIT_DTYPE).copy()
+            assert_hits_equal(hits, ref.intersect(rays)[0])
+    gpu.check(L.pb2_scene_wait_until(accel.h, 100))    # more than were ever enqueued: nothing to wait for
+    gpu.check(L.pb2_scene_wait_until(accel.h, 0))
+    n, rays, _, p_h, _, _ = batches[-1]
+    assert_hits_equal(np.frombuffer((C.c_char * (n * 16)).from_address(p_h.value), dtype=gpu.HIT_DTYPE).copy(), ref.intersect(rays)[0])
     for _, _, p_r, p_h, p_b, p_o in batches:
         for p in (p_r, p_h, p_b, p_o):
             gpu.check(L.pb2_host_free(p))
