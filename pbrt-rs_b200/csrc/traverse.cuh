@@ -92,6 +92,13 @@ PB2_D bool slab_entry(const RayCtx& r, float lx, float ly, float lz, float hx, f
 }
 
 PB2_D vec3 permute3(vec3 v, int kx, int ky, int kz) { return mk(comp(v, kx), comp(v, ky), comp(v, kz)); }
+// permute3(v, kx, ky, kz) for the triple Triangle::intersect_test builds (triangle.rs:84-92: kz = max dimension of |d|,
+// kx = kz + 1, ky = kx + 1, both mod 3): always a rotation, selected by two predicates the caller evaluates once — (y, z, x) for
+// kz = 0, (z, x, y) for kz = 1, v itself for kz = 2.  Six selects per vertex; the three index-driven comp() calls cost k_extend
+// 46 instructions per triangle test, 10 % of its warp instructions (profiles/r02_tuning.md).
+PB2_D vec3 rotate3(vec3 v, bool kz0, bool kz1) {
+    return mk(kz0 ? v.y : (kz1 ? v.z : v.x), kz0 ? v.z : (kz1 ? v.x : v.y), kz0 ? v.x : (kz1 ? v.y : v.z));
+}
 
 // (f32)((f64)a*(f64)b - (f64)c*(f64)d): both products are exact in binary64, so one fused multiply-subtract
 // rounds exactly like the reference's f64 subtract (triangle.rs:109-111); then one f64 -> f32 rounding.
@@ -101,9 +108,10 @@ PB2_D float edge_fn(float a, float b, float c, float d) {
 
 // Triangle::intersect_test (triangle.rs:74-158; D7, D8 fixed; D9, D10 kept).
 PB2_D bool tri_test(const RayCtx& r, float ray_t_max, vec3 p0, vec3 p1, vec3 p2, float* t_out, float* b0, float* b1, float* b2) {
-    vec3 p0t = permute3(p0 - r.o, r.kx, r.ky, r.kz);
-    vec3 p1t = permute3(p1 - r.o, r.kx, r.ky, r.kz);
-    vec3 p2t = permute3(p2 - r.o, r.kx, r.ky, r.kz);
+    const bool kz0 = r.kz == 0, kz1 = r.kz == 1;
+    vec3 p0t = rotate3(p0 - r.o, kz0, kz1);
+    vec3 p1t = rotate3(p1 - r.o, kz0, kz1);
+    vec3 p2t = rotate3(p2 - r.o, kz0, kz1);
     p0t.x = p0t.x + r.sx * p0t.z;  p0t.y = p0t.y + r.sy * p0t.z;
     p1t.x = p1t.x + r.sx * p1t.z;  p1t.y = p1t.y + r.sy * p1t.z;
     p2t.x = p2t.x + r.sx * p2t.z;  p2t.y = p2t.y + r.sy * p2t.z;
