@@ -18,6 +18,16 @@ namespace {
 #ifndef PB2_SHADE_THREADS
 #define PB2_SHADE_THREADS 256
 #endif
+#ifndef PB2_SHADE_PREFETCH
+#define PB2_SHADE_PREFETCH 1    /* 0: no prefetch of the next vertex's path state; 2: into L1 (tuning builds) */
+#endif
+__device__ __forceinline__ void prefetch_state(const void* p) {
+#if PB2_SHADE_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 template <int MAT, bool TABLES, bool SG>
 __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(SceneView s, ShadeView sh, PathBuffers b, PathMap map, FilmView film, PathParams pp, int cur) {
     constexpr int Q = MAT == 3 ? 1 : MAT;       // MAT 3 = the class-1 queue shaded by the plastic-only kernel (shade.cuh: may_be<3>)
@@ -43,7 +53,19 @@ __global__ void __launch_bounds__(PB2_SHADE_THREADS, PB2_SHADE_BLOCKS) k_shade(S
             slot = slot_n;
             h = h_n;
             slot_n = slot_nn;
-            if (i + stride < n) h_n = b.hit[slot_n];
+            if (i + stride < n) {
+                h_n = b.hit[slot_n];
+#if PB2_SHADE_PREFETCH
+                // the next vertex's path state (its slot has been in a register since the previous iteration): four lines on
+                // their way into L2 / L1 while this vertex is shaded — the head-of-iteration loads of ray_d, L, beta and rng
+                // held 18 % of the kernel's stall samples (profiles/r02_tuning.md; prefetching the next triangle record from
+                // the middle of the iteration as well measured slower and is not done)
+                prefetch_state(b.ray_d + slot_n);
+                prefetch_state(b.L + slot_n);
+                prefetch_state(b.beta + slot_n);
+                prefetch_state(b.rng + slot_n);
+#endif
+            }
             if (i + 2 * stride < n) slot_nn = queue[i + 2 * stride];
         } else {
             slot = queue[i];
