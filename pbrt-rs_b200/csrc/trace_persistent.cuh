@@ -58,7 +58,14 @@ PB2_D float quad_child_entry(float nx, float ny, float nz, float fx, float fy, f
     const float widen = 1.0f + 2.0f * gammaf_(3.0f);
     const float tn = fmaxf(fmaxf((nx - o.x) * inv.x, (ny - o.y) * inv.y), (nz - o.z) * inv.z);
     const float tf = fminf(fminf((fx - o.x) * inv.x, (fy - o.y) * inv.y), (fz - o.z) * inv.z) * widen;
-    return (tn <= tf && tf > 0.0f && tn < t_max) ? tn : __int_as_float(0x7f800000);
+    // one select on the conjunction of the three ordered comparisons (the compiler's own code selects +inf once per comparison:
+    // 6 instead of 4 instructions per box, 8 more per QuadNode step)
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\tsetp.gt.and.f32 p, %2, 0f00000000, p;\n\tsetp.lt.and.f32 p, %1, %3, p;\n\t"
+        "selp.f32 %0, %1, 0f7F800000, p;\n\t}"
+        : "=f"(r)
+        : "f"(tn), "f"(tf), "f"(t_max));
+    return r;
 }
 PB2_D void swap_if(bool c, uint32_t& ra, float& ta, uint32_t& rb, float& tb) {
     const uint32_t r = c ? rb : ra; rb = c ? ra : rb; ra = r;
