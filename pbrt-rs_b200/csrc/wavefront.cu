@@ -127,39 +127,27 @@ __global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= n_tiles) return;
-        // ---- load kSelItems consecutive entries per thread (blocked: the select is stable) ----
-        const unsigned long long i0 = (unsigned long long)tile * kSelTile + (unsigned long long)threadIdx.x * kSelItems;
+        // ---- warp-striped tile: warp w owns entries [w * 32 * kSelItems, (w + 1) * 32 * kSelItems) of the tile, lane l its rows
+        // k * 32 + l, so every load, every state-byte gather (the queue is sorted by slot) and every store of a warp instruction
+        // falls on neighbouring addresses.  (First version: kSelItems consecutive entries per thread — a warp instruction then
+        // spanned 2 KB of the queue and 32 separate runs of the outputs; ncu saw 4x the L2 traffic the select needs.) ----
+        const unsigned long long w0 = (unsigned long long)tile * kSelTile + (unsigned long long)warp * (32u * kSelItems) + lane;
         uint32_t slot[kSelItems];
-        if (i0 + kSelItems <= n) {
 #pragma unroll
-            for (int k = 0; k < kSelItems; k += 4) {
-                const uint4 a = *reinterpret_cast<const uint4*>(j.in + i0 + k);
-                slot[k] = a.x; slot[k + 1] = a.y; slot[k + 2] = a.z; slot[k + 3] = a.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kSelItems; ++k) slot[k] = i0 + k < n ? j.in[i0 + k] : 0u;
-        }
-        unsigned bits[3] = {0u, 0u, 0u};           // bit k of bits[q]: entry k goes to output q
+        for (int k = 0; k < kSelItems; ++k) slot[k] = w0 + 32u * k < n ? j.in[w0 + 32u * k] : 0u;
+        unsigned bits[3] = {0u, 0u, 0u};           // bit k of bits[q]: row k of this lane goes to output q
 #pragma unroll
         for (int k = 0; k < kSelItems; ++k) {
-            const unsigned st = i0 + k < n ? j.state[slot[k]] : (j.by_class ? kStateDead : 0u);
+            const unsigned st = w0 + 32u * k < n ? j.state[slot[k]] : (j.by_class ? kStateDead : 0u);
 #pragma unroll
             for (int q = 0; q < 3; ++q) bits[q] |= (select_pred(j.by_class, st, q) ? 1u : 0u) << k;
         }
-        unsigned cnt[3], inc[3];
+        // warp totals per output
 #pragma unroll
-        for (int q = 0; q < 3; ++q) inc[q] = cnt[q] = (unsigned)__popc(bits[q]);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, inc[q], o);
-                if (lane >= (unsigned)o) inc[q] += v;
-            }
-        if (lane == 31u)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) s_warp[q][warp] = inc[q];
+        for (int q = 0; q < 3; ++q) {
+            const unsigned t = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(bits[q]));
+            if (lane == 0u) s_warp[q][warp] = t;
+        }
         __syncthreads();
         // ---- warps 0-2: tile total of output `warp`, publish it, look back ----
         if (warp < 3u) {
@@ -177,27 +165,30 @@ __global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
             }
         }
         __syncthreads();
-        // ---- scatter ----
+        // ---- scatter: rows in order, lanes in order inside a row (stable) ----
+        const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            unsigned before = 0u;
+            unsigned pos = s_base[q];
 #pragma unroll
-            for (int w = 0; w < kSelThreads / 32; ++w) before += (unsigned)w < warp ? s_warp[q][w] : 0u;
-            unsigned pos = s_base[q] + before + inc[q] - cnt[q];
+            for (int w = 0; w < kSelThreads / 32; ++w) pos += (unsigned)w < warp ? s_warp[q][w] : 0u;
             uint32_t* out = j.out[q];
 #pragma unroll
-            for (int k = 0; k < kSelItems; ++k)
-                if ((bits[q] >> k) & 1u) out[pos++] = slot[k];
+            for (int k = 0; k < kSelItems; ++k) {
+                const bool mine = (bits[q] >> k) & 1u;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+                if (mine) out[pos + __popc(m & lt)] = slot[k];
+                pos += __popc(m);
+            }
         }
-        if (tile == n_tiles - 1u && threadIdx.x == kSelThreads - 1) {
-            // (the last thread of the last tile: its inclusive position is the total)
+        if (tile == n_tiles - 1u && threadIdx.x == 0) {
             unsigned long long tot[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                unsigned before = 0u;
+                unsigned all = 0u;
 #pragma unroll
-                for (int w = 0; w < kSelThreads / 32; ++w) before += (unsigned)w < warp ? s_warp[q][w] : 0u;
-                tot[q] = (unsigned long long)s_base[q] + before + inc[q];
+                for (int w = 0; w < kSelThreads / 32; ++w) all += s_warp[q][w];
+                tot[q] = (unsigned long long)s_base[q] + all;
             }
             select_finish(j, tot[0], tot[1], tot[2]);
         }
