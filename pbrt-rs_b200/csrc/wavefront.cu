@@ -108,7 +108,7 @@ __device__ __forceinline__ unsigned select_look_back(const unsigned long long* s
     }
     return excl;
 }
-__global__ void __launch_bounds__(kSelThreads) k_select3(SelectJob j) {
+__global__ void __launch_bounds__(kSelThreads, 4) k_select3(SelectJob j) {
     __shared__ unsigned s_tile;
     __shared__ unsigned s_warp[3][kSelThreads / 32];
     __shared__ unsigned s_base[3];
