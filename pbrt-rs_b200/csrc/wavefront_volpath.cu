@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(128) k_volpath(uint64_t n, SceneView s, ShadeV
 //   k_vol_resolve  l += beta * ld / pick_pdf for the iteration's NEE records, in the reference's order of terms
 // A path's additions to L happen in the order of volpath.rs (Le at a vertex, then that vertex's direct light, then the next
 // vertex), and every path draws its sampler in that order too, so the radiance equals k_volpath's bit for bit.
+#ifndef PB2_VOL_BLOCKS
+#define PB2_VOL_BLOCKS 4        /* CTAs of 128 threads per SM of k_vol_medium / k_vol_surface: 128 registers with 200-440 B of spills beat the 156-195 registers / 3 CTAs the compiler takes freely (18.22 -> 17.54 ms on the fog + smoke frame) */
+#endif
 constexpr uint8_t kTrDone = 3, kTrAgain = 0;       // VolBuffers::st_s / st_m after k_vol_tr_post (the select's class predicate)
 
 __device__ __forceinline__ uint32_t pack_path_word(unsigned bounces, bool spec, unsigned extra) { return bounces | ((spec ? 1u : 0u) << 16) | (extra << 17); }
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(kThreads) k_vol_resolve(PathBuffers b, VolBuff
 }
 
 // ---- the medium stage: volpath.rs:76-131 for every active path -----------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vol_medium(SceneView s, ShadeView sh, PathBuffers b, VolBuffers vb, PathMap map, FilmView film, PathParams pp, int cur) {
+__global__ void __launch_bounds__(128, PB2_VOL_BLOCKS) k_vol_medium(SceneView s, ShadeView sh, PathBuffers b, VolBuffers vb, PathMap map, FilmView film, PathParams pp, int cur) {
     const uint64_t n = b.counters[C_ACTIVE_A + cur];
     const uint32_t* queue = b.q_active[cur];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(128) k_vol_medium(SceneView s, ShadeView sh, P
 
 // ---- the surface vertex of volpath.rs:133-187 for the hits of shading class CLS ----------------------------------------------------
 template <int CLS>
-__global__ void __launch_bounds__(128) k_vol_surface(SceneView s, ShadeView sh, PathBuffers b, VolBuffers vb, PathMap map, FilmView film, PathParams pp) {
+__global__ void __launch_bounds__(128, PB2_VOL_BLOCKS) k_vol_surface(SceneView s, ShadeView sh, PathBuffers b, VolBuffers vb, PathMap map, FilmView film, PathParams pp) {
     const uint64_t n = b.counters[C_MAT0 + CLS];
     const uint32_t* queue = b.q_mat[CLS];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
