@@ -242,9 +242,15 @@ static int ensure_spatial(pb2_scene* scene, cudaStream_t st) {
     spatial_grid_extents(scene->root_bounds, 64, nv);
     const uint64_t n_vox = (uint64_t)nv[0] * nv[1] * nv[2];
     const uint64_t bytes = (n_vox * n + n_vox * (n + 1) + n_vox) * sizeof(float);
-    if (bytes > kSpatialMaxBytes)
-        return set_error(PB2_ERR_INVALID, "spatial light distribution: %llu voxels x %zu lights need %.1f GB of tables (limit %.0f GB); use \"power\"",
-                         (unsigned long long)n_vox, n, bytes / 1e9, kSpatialMaxBytes / 1e9);
+    // The reference fills a voxel at its first lookup (lightdistrib.rs:165-220); here the whole grid is filled eagerly, every
+    // emissive triangle being one light, so the tables are bounded by what the device can hold beside the wavefront arenas:
+    // half of the free memory, at most kSpatialMaxBytes.
+    size_t free_b = 0, total_b = 0;
+    PB2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t limit = std::min<uint64_t>(kSpatialMaxBytes, (uint64_t)free_b / 2);
+    if (bytes > limit)
+        return set_error(PB2_ERR_LIMIT, "spatial light distribution: %llu voxels x %zu lights need %.1f GB of tables (limit %.1f GB: half of the free "
+                         "device memory, at most %.0f GB); use \"power\"", (unsigned long long)n_vox, n, bytes / 1e9, limit / 1e9, kSpatialMaxBytes / 1e9);
     PB2_CUDA(cudaMalloc(&scene->d_spatial, bytes));
     for (int i = 0; i < 3; ++i) scene->spatial_nv[i] = nv[i];
     const SpatialView g = spatial_view(scene);

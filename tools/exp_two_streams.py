@@ -26,9 +26,10 @@ def setup():
     return accel, camera, pb2.PathIntegrator(accel, camera, **dict(pk, spp=SPP)), pb2.Film(cam["res"])
 
 
-A, B = setup(), setup()
-s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-for w, s in ((A, s1), (B, s2)):
+NC = int(os.environ.get("EXP_COPIES", "2"))
+W = [setup() for _ in range(NC)]
+S = [torch.cuda.Stream() for _ in range(NC)]
+for w, s in zip(W, S):
     w[2].render(w[3], stream=s.cuda_stream)
 torch.cuda.synchronize()
 
@@ -36,19 +37,21 @@ torch.cuda.synchronize()
 def run(concurrent):
     ts = []
     for _ in range(5):
-        A[3].clear(); B[3].clear()
+        for w in W:
+            w[3].clear()
         torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(s1)
-        s2.wait_event(e0)
-        A[2].render(A[3], stream=s1.cuda_stream)
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e0.record(S[0])
+        for s in S[1:]:
+            s.wait_event(e0)
+        for w, s in zip(W, S):
+            w[2].render(w[3], stream=(s if concurrent else S[0]).cuda_stream)
         if concurrent:
-            B[2].render(B[3], stream=s2.cuda_stream)
-            e2.record(s2)
-            s1.wait_event(e2)
-        else:
-            B[2].render(B[3], stream=s1.cuda_stream)
-        e1.record(s1)
+            for s in S[1:]:
+                e = torch.cuda.Event()
+                e.record(s)
+                S[0].wait_event(e)
+        e1.record(S[0])
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.mean(ts[1:]))
@@ -56,5 +59,5 @@ def run(concurrent):
 
 for rep in range(2):
     seq, con = run(False), run(True)
-    print(f"{which} 2 x {SPP} spp: one stream {seq:.3f} ms, two streams {con:.3f} ms ({(con / seq - 1) * 100:+.1f} %)  "
-          f"rgb {A[3].resolve_rgb().mean():.6f} {B[3].resolve_rgb().mean():.6f}", flush=True)
+    print(f"{which} {NC} x {SPP} spp: one stream {seq:.3f} ms, {NC} streams {con:.3f} ms ({(con / seq - 1) * 100:+.1f} %)  "
+          f"rgb {W[0][3].resolve_rgb().mean():.6f} {W[-1][3].resolve_rgb().mean():.6f}", flush=True)
