@@ -7,8 +7,9 @@ cosine-bounce rays (incoherent closest hit) spawned from the hits -> both traced
 
   value     = rays traced / device time, inputs resident in HBM (CUDA events on the launching stream)
   e2e       = the same three batches through the host-buffer C ABI from pinned host memory, H2D + D2H inside the timed
-              region: enqueued back to back (pb2_intersect_async / pb2_intersect_p_async) and waited for once per step;
-              the synchronous calls (pb2_intersect / pb2_intersect_p, one drain per batch) are timed beside it
+              region of every step: enqueued back to back (pb2_intersect_async / pb2_intersect_p_async), one step kept in
+              flight while the previous step's results are retired (pb2_scene_wait_until), the last step waited for in
+              full; the synchronous calls (pb2_intersect / pb2_intersect_p, one drain per batch) are timed beside it
   roofline  = algorithmic bytes of the incoherent closest-hit launch (oracle-counted nodes/triangles in reference order,
               SURVEY §8d) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference = the CPU restatement of the reference (oracle/, all host threads) on a bounded sample
