@@ -717,22 +717,24 @@ def test_many_small_batches_on_two_streams_bit_exact(gpu, OP, scenes, tmp_path):
     """A frame of several batches alternates between the scene's wavefront and a second arena on an internal stream, with the film
     accumulation ordered by events (wavefront_render).  Forced here with a 2^16-slot wavefront (PB2_WAVEFRONT_LOG2_SLOTS, read once
     per process: subprocesses): 128x128 @ 16 spp = four batches, PathIntegrator and VolPathIntegrator, with the second stream and
-    without (PB2_TWO_STREAMS=0) — both films equal the oracle's bits."""
+    without (PB2_TWO_STREAMS=0), and the VolPathIntegrator also as k_volpath (PB2_VOLPATH_MEGAKERNEL=1) — every film equals the oracle's bits."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     films = {}
-    for two in ("1", "0"):
+    for two in ("1", "0", "mega"):
         npz = str(tmp_path / f"films_{two}.npz")
-        env = dict(os.environ, PB2_WAVEFRONT_LOG2_SLOTS="16", PB2_TWO_STREAMS=two)
+        env = dict(os.environ, PB2_WAVEFRONT_LOG2_SLOTS="16", PB2_TWO_STREAMS="1" if two == "mega" else two)
+        if two == "mega":                          # the one-thread-per-path form of the VolPathIntegrator (kept for comparison)
+            env["PB2_VOLPATH_MEGAKERNEL"] = "1"
         subprocess.run([sys.executable, "-c", _BATCH_SNIPPET.format(root=root, npz=npz)], check=True, env=env, timeout=600)
         films[two] = np.load(npz)
     cam = dict(scenes.C2_CAMERA, res=(128, 128))
     for name, sc, kw in (("path", scenes.scene_c2(), dict(max_depth=5, rr_threshold=1.0, light_strategy="uniform", spp=16)),
                          ("volpath", scenes.scene_media(), dict(max_depth=6, rr_threshold=1.0, light_strategy="power", spp=16, integrator="volpath"))):
         want, _ = OP.Scene(sc, 4).render(cam, OP.film_desc(cam["res"]), OP.path_desc(**kw), mode=1)
-        for two in ("1", "0"):
+        for two in ("1", "0", "mega"):
             got = films[two][name]
             assert np.array_equal(bits(got), bits(want)), f"{name}, PB2_TWO_STREAMS={two}: {(bits(got) != bits(want)).any(axis=2).sum()} pixels differ"
         assert films["1"][name + "_launches"][0] > 4 * 20          # four batches' worth of launches
