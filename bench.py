@@ -5,7 +5,8 @@ A "step" is one C3 pass (BASELINE config 2): 1024x1024 primary r
 closest hit against the 10,008,338-triangle displaced grid -> shadow rays to the point light (any-hit) and
 cosine-bounce rays (incoherent closest hit) spawned from the hits -> both traced.  3 x 1,048,576 rays per step.
 
-  value     = rays traced / device time, inputs resident in HBM (CUDA events on the launching stream)
+  value     = rays traced / device time, inputs resident in HBM (CUDA events on the launching stream); the shadow and the
+              bounce batch of a step are independent and go out on two streams (joined before the step's end event)
   e2e       = the same three batches through the host-buffer C ABI from pinned host memory, H2D + D2H inside the timed
               region of every step: enqueued back to back (pb2_intersect_async / pb2_intersect_p_async), one step kept in
               flight while the previous step's results are retired (pb2_scene_wait_until), the last step waited for in
@@ -572,7 +573,13 @@ def main():
 
     names = ["raygen", "closest_primary", "spawn", "any_shadow", "closest_bounce"]
 
-    def device_step(events=None):
+    side = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+
+    def device_step(events=None, overlap=True):
+        # overlap: the shadow batch and the bounce batch do not depend on each other, so they go out on two streams (the
+        # `stream` argument of the C ABI) and the tail of each persistent launch is filled by the other; overlap=False runs
+        # the five launches one after the other, which is what the per-kernel times (kernel_ms, roofline) are taken from.
         def mark(i):
             if events is not None:
                 events[i].record()
@@ -583,9 +590,18 @@ def main():
         mark(2)
         accel.spawn_shadow_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, scenes.C3_POINT_LIGHT, d_srays.data_ptr(), d_brays.data_ptr(), stream)
         mark(3)
-        accel.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), stream)
-        mark(4)
-        accel.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
+        if overlap:
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main_stream)
+            side.wait_event(fork)
+            accel.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), side.cuda_stream)
+            accel.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
+            join.record(side)
+            main_stream.wait_event(join)
+        else:
+            accel.intersect_p_device(d_srays.data_ptr(), n, d_occ.data_ptr(), stream)
+            mark(4)
+            accel.intersect_device(d_brays.data_ptr(), n, d_bhits.data_ptr(), None, stream)
         mark(5)
     launches_per_step = 5
 
@@ -607,8 +623,15 @@ def main():
         flush.zero_()                       # L2 flush between timed iterations (outside the event pairs)
     barrier()
     step_ms = [ev[0].elapsed_time(ev[5]) for ev in all_events]
-    kernel_ms = {names[i]: float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in all_events])) for i in range(5)}
     total_ms = float(sum(step_ms))
+    # per-kernel times: the same steps once more with the five launches strictly one after the other (not part of `value`)
+    serial_events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        device_step(serial_events[s], overlap=False)
+        flush.zero_()
+    barrier()
+    kernel_ms = {names[i]: float(np.mean([ev[i].elapsed_time(ev[i + 1]) for ev in serial_events])) for i in range(5)}
+    serial_step_ms = float(np.mean([ev[0].elapsed_time(ev[5]) for ev in serial_events]))
 
     # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region ----
     h_rays = torch.empty(n * 8, dtype=torch.float32).pin_memory()
@@ -821,7 +844,9 @@ def main():
             "config": bench_config(n_prims, args.res),
             "scene": {"bvh_nodes": n_nodes, "bvh_depth": depth, "scene_gen_s": t_gen, "bvh_build_upload_s": t_build,
                       "l2": "BVH+triangles (~1 GB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps"},
-            "kernel_ms": kernel_ms, "hits_crc32": hits_crc,
+            "kernel_ms": kernel_ms, "kernel_ms_note": "each launch alone on the device (the same steps repeated with the five launches in series, "
+                                                      "outside the timed region); in the timed steps the shadow and bounce batches share the device on two streams",
+            "serial_ms_per_step": serial_step_ms, "hits_crc32": hits_crc,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": n * 16 + n + n * 16,
                     "api": "pb2_intersect_async x2 + pb2_intersect_p_async per step, pb2_scene_wait_until(3): one step stays in flight while the previous one is retired; pinned host buffers",
                     "synchronous_calls_mrays_s": world * rays_per_step * args.steps / e2e_sync_s / 1e6,
