@@ -18,6 +18,31 @@ def test_white_furnace_converges_to_closed_form(OP, scenes):
     assert abs(OP.resolve_rgb(xyzw).mean() - 1.0) < 0.01
 
 
+def test_glass_in_a_furnace_preserves_radiance(OP, scenes):
+    """External pin for FresnelSpecular + refract + the eta^2 radiance scaling (reflection.rs:733-819, :145-156): inside a closed
+    box whose black walls all emit L = 1, a lossless dielectric (Kr = Kt = 1, eta = 1.5) changes nothing — every specular path
+    carries throughput 1 when it leaves the glass again (F / F on reflection, (1 - F) eta_i^2 / eta_t^2 / (1 - F) in and the
+    inverse out) and ends on an emitter, so every sample is 1 up to rounding, whether it sees the sphere or not; only paths still
+    inside the glass at max_depth (total internal reflection) are lost."""
+    box = scenes.furnace_box(L=1.0, kd=0.0)
+    sv, si = scenes.uv_sphere(radius=0.45, center=(0.0, 0.0, 0.3), n_theta=24, n_phi=48)
+    verts, idx = scenes.merge((box["verts"], box["idx"]), (sv, si))
+    n_box = len(box["idx"])
+    sc = dict(verts=verts, idx=idx, tri_material=np.concatenate([box["tri_material"], np.ones(len(si), np.uint32)]),
+              materials=box["materials"] + [dict(type="glass", kr=(1, 1, 1), kt=(1, 1, 1), eta=1.5)], lights=box["lights"])
+    assert all(l["prim"] < n_box for l in sc["lights"])
+    cam = dict(pos=(0, 0, -0.9), look=(0, 0, 1), up=(0, 1, 0), fov=70.0, res=(32, 32))
+    xyzw, _ = OP.Scene(sc).render(cam, OP.film_desc((32, 32)), OP.path_desc(max_depth=60, rr_threshold=0.0, spp=16))
+    rgb = OP.resolve_rgb(xyzw)
+    assert rgb.max() < 1.0 + 1e-4
+    # every one of the 16 samples of a pixel returns exactly 1 (rounding aside) or — a grazing path caught in total internal
+    # reflection until max_depth, on the sphere's silhouette only — 0
+    assert np.abs(rgb * 16.0 - np.round(rgb * 16.0)).max() < 2e-3
+    assert (np.abs(rgb - 1.0) < 1e-4).all(axis=2).mean() > 0.95
+    assert (np.abs(rgb[12:20, 12:20] - 1.0) < 1e-4).all()   # straight through the middle of the sphere
+    assert rgb.mean() > 0.995, rgb.mean()
+
+
 def test_sample_ranges_add_up_exactly(OP, scenes):
     sc = OP.Scene(scenes.scene_c2())
     cam = dict(scenes.C2_CAMERA, res=(32, 32))
