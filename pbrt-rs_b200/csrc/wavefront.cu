@@ -743,6 +743,13 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
     }
     const TraceTuning tune = trace_tuning();
     const unsigned trace_grid = (unsigned)wf->sm_count * (unsigned)PB2_MIN_BLOCKS, trace_grid_sph = (unsigned)wf->sm_count * 4u;
+    // k_shadow (any hit: no candidate bookkeeping) needs fewer registers than k_extend and fits one CTA per SM more
+    static const int shadow_per_sm = [] {
+        int v = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, (const void*)k_shadow, 128, 0);
+        return std::max(v, PB2_MIN_BLOCKS);
+    }();
+    const unsigned trace_grid_shadow = (unsigned)wf->sm_count * (unsigned)shadow_per_sm;
     k_raygen<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, cam, b);
     int launches = 1;
     for (int depth = 0; depth <= pp.max_depth; ++depth) {
@@ -759,7 +766,7 @@ void trace_batch(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
         launches += 1;
         if (sh.n_lights > 0) {
             if (sv.spheres) k_shadow_spheres<<<trace_grid_sph, 128, 0, st>>>(sv, b, tune);
-            else k_shadow<<<trace_grid, 128, 0, st>>>(sv, b, tune);           // (the MIS rays ride in the next bounce's k_extend)
+            else k_shadow<<<trace_grid_shadow, 128, 0, st>>>(sv, b, tune);    // (the MIS rays ride in the next bounce's k_extend)
             launches += 1;
         }
     }
