@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(128) k_volpath(uint64_t n, SceneView s, ShadeV
 //   k_vol_resolve  l += beta * ld / pick_pdf for the iteration's NEE records, in the reference's order of terms
 // A path's additions to L happen in the order of volpath.rs (Le at a vertex, then that vertex's direct light, then the next
 // vertex), and every path draws its sampler in that order too, so the radiance equals k_volpath's bit for bit.
+#ifndef PB2_VOL_BLIND_ROUNDS
+#define PB2_VOL_BLIND_ROUNDS 1  /* transmittance rounds run without a read-back of the pending-ray counts (interface scenes) */
+#endif
 #ifndef PB2_VOL_BLOCKS
 #define PB2_VOL_BLOCKS 4        /* CTAs of 128 threads per SM of k_vol_medium / k_vol_surface: 128 registers with 200-440 B of spills beat the 156-195 registers / 3 CTAs the compiler takes freely (18.22 -> 17.54 ms on the fog + smoke frame) */
 #endif
@@ -715,6 +718,7 @@ void trace_batch_vol(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
     uint64_t launches = 2;
     for (int it = 0;; ++it) {
         const int cur = it & 1;
+        bool counts_fresh = false;                         // h_counters read back after this iteration's queue select
         if (sv.spheres) k_vol_extend_spheres<<<trace_grid_sph, 128, 0, st>>>(sv, b, vb, cur, tune);
         else k_vol_extend<<<trace_grid, 128, 0, st>>>(sv, b, vb, cur, tune);
         k_vol_medium<<<stage, 128, 0, st>>>(sv, sh, b, vb, map, film, pp, cur);
@@ -740,8 +744,13 @@ void trace_batch_vol(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
                 select_queues(wf, qs, cs, true, qs_alt, cs_alt, b.q_mat[2], C_VOL_SCRATCH, b.q_mat[2], C_VOL_SCRATCH, st, vb.st_s);
                 select_queues(wf, qm, cm, true, qm_alt, cm_alt, b.q_mat[2], C_VOL_SCRATCH, b.q_mat[2], C_VOL_SCRATCH, st, vb.st_m);
                 launches += 2;
-                read_counts();
-                if (wf->h_counters[cs_alt] == 0 && wf->h_counters[cm_alt] == 0) break;
+                // (round 0 of PB2_VOL_BLIND_ROUNDS is followed by the next one without asking: a scene with interfaces usually has
+                // rays that cross one, and an empty round costs less than the read-back it saves)
+                if (round >= PB2_VOL_BLIND_ROUNDS) {
+                    read_counts();
+                    counts_fresh = true;
+                    if (wf->h_counters[cs_alt] == 0 && wf->h_counters[cm_alt] == 0) break;
+                }
                 std::swap(qs, qs_alt);
                 std::swap(qm, qm_alt);
                 std::swap(cs, cs_alt);
@@ -750,8 +759,11 @@ void trace_batch_vol(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
             k_vol_resolve<<<wide, kThreads, 0, st>>>(b, vb, cur);
             launches += 1;
         }
-        if (sh.has_interfaces) {                                         // crossing an interface is not a bounce: go on while a path is alive
-            read_counts();
+        // crossing an interface is not a bounce: go on while a path is alive.  Before iteration max_depth some path is (nothing
+        // counts down faster than one bounce per iteration), and the count of the next active queue was fixed by the select above:
+        // a read-back of the transmittance rounds already holds it.
+        if (sh.has_interfaces && it >= pp.max_depth) {
+            if (!counts_fresh) read_counts();
             if (wf->h_counters[C_ACTIVE_A + (cur ^ 1)] == 0) break;
         }
     }
