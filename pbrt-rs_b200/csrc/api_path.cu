@@ -42,6 +42,7 @@ static FilmView film_view(const pb2_film* f) {
     v.px0 = f->px0; v.py0 = f->py0; v.px1 = f->px1; v.py1 = f->py1;
     v.max_lum = f->desc.max_sample_luminance > 0.0f ? f->desc.max_sample_luminance : __builtin_huge_valf();
     v.sb_x0 = f->sb_x0; v.sb_y0 = f->sb_y0; v.sb_w = f->sb_x1 - f->sb_x0; v.sb_h = f->sb_y1 - f->sb_y0;
+    v.sb_w_magic = fast_div_magic((uint32_t)v.sb_w);
     v.radius_x = f->desc.radius_x; v.radius_y = f->desc.radius_y;
     v.exact = (f->desc.filter == PB2_FILTER_BOX && f->desc.radius_x == 0.5f && f->desc.radius_y == 0.5f) ? 1 : 0;
     v.table = f->d_table;
@@ -802,6 +803,7 @@ int pb2_path_li(pb2_scene* scene, const pb2_camera* cam, const pb2_path_desc* pa
     FilmView fv;
     memset(&fv, 0, sizeof fv);
     fv.px1 = cam->res_x; fv.py1 = cam->res_y; fv.sb_w = cam->res_x; fv.sb_h = cam->res_y; fv.radius_x = fv.radius_y = 0.5f;
+    fv.sb_w_magic = fast_div_magic((uint32_t)fv.sb_w);
     fv.max_lum = __builtin_huge_valf();
     int32_t* d_xy = nullptr;
     uint32_t* d_s = nullptr;

@@ -465,7 +465,8 @@ __device__ __forceinline__ void film_stray(const FilmView& f, unsigned long long
 // (stray_counters: the frame's stray list is shared by the two wavefronts that alternate its batches)
 __global__ void __launch_bounds__(kThreads) k_film_accumulate_exact(PathMap map, FilmView f, PathBuffers b, int n_samples, unsigned long long* stray_counters) {
     for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < map.n_pix; pix += gridDim.x * blockDim.x) {
-        const int x = f.sb_x0 + (int)(pix % (uint32_t)f.sb_w), y = f.sb_y0 + (int)(pix / (uint32_t)f.sb_w);
+        const uint32_t row = fast_div(pix, f.sb_w_magic);
+        const int x = f.sb_x0 + (int)(pix - row * (uint32_t)f.sb_w), y = f.sb_y0 + (int)row;
         const bool inside = x >= f.px0 && y >= f.py0 && x < f.px1 && y < f.py1;
         float4 acc = inside ? f.acc[f.index(x, y)] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < n_samples; ++s) {
@@ -875,7 +876,7 @@ int wavefront_render(Wavefront* wf, const SceneView& sv, const ShadeView& sh, co
     int k = 0;
     for (int s0 = sample_begin; s0 < sample_end; s0 += per_batch, ++k) {
         const int ns = std::min(per_batch, sample_end - s0);
-        PathMap map{(uint32_t)n_pix, spp, s0, nullptr, nullptr, smp};
+        PathMap map{(uint32_t)n_pix, spp, s0, nullptr, nullptr, smp, fast_div_magic((uint32_t)n_pix)};
         const uint64_t n = n_pix * (uint64_t)ns;
         Wavefront* w = overlap && (k & 1) ? wf->peer : wf;
         cudaStream_t ws = overlap && (k & 1) ? wf->aux_stream : st;
@@ -905,7 +906,7 @@ int wavefront_li(Wavefront* wf, const SceneView& sv, const ShadeView& sh, const 
                  const PathParams& pp, const SamplerView& smp, int spp, const int32_t* d_xy, const uint32_t* d_s, uint64_t n, float* d_L,
                  float* d_pfilm, cudaStream_t st) {
     if (n == 0) return 0;
-    PathMap map{(uint32_t)std::max<uint64_t>(1, n), spp, 0, d_xy, d_s, smp};
+    PathMap map{(uint32_t)std::max<uint64_t>(1, n), spp, 0, d_xy, d_s, smp, fast_div_magic((uint32_t)std::max<uint64_t>(1, n))};
     trace_batch(wf, sv, sh, cam, film, map, pp, n, st);
     k_copy_li<<<grid_for(wf, n), kThreads, 0, st>>>(n, map, film, wf->b, d_L, d_pfilm);
     return 0;

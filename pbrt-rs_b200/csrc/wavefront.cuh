@@ -65,6 +65,7 @@ struct ShadeView {
 struct FilmView {
     int px0, py0, px1, py1;       // cropped_pixel_bounds (film.rs:41-50): the pixels the film stores, row-major
     int sb_x0, sb_y0, sb_w, sb_h;
+    unsigned long long sb_w_magic;   // fast_div_magic(sb_w): pixel -> row without a 32-bit division (slot_info runs per path vertex)
     float max_lum;                // max_sample_luminance (film.rs:259-261), +inf when unset
     float radius_x, radius_y;
     int exact;                    // box filter, r = 0.5: ordered accumulation (bit-reproducible)
@@ -105,6 +106,15 @@ struct SamplerView {
     int sobol_resolution, sobol_log2_resolution;
 };
 
+// Exact n / d for 32-bit n, d through one 64 x 64 -> high 64 multiply: m = ceil(2^64 / d), n / d = hi64(n * m) (the error term
+// n * (m d - 2^64) / (d 2^64) is below 2^-32 <= 1 / d, so the floor is unchanged); d = 1 has no 64-bit m and is flagged by m = 0.
+inline unsigned long long fast_div_magic(uint32_t d) { return d <= 1u ? 0ull : 0xFFFFFFFFFFFFFFFFull / d + 1ull; }
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, unsigned long long magic) {
+    return magic ? (uint32_t)__umul64hi((unsigned long long)n, magic) : n;
+}
+#endif
+
 // slot -> (pixel, sample index)
 struct PathMap {
     uint32_t n_pix;               // sample-bounds pixels per sample index
@@ -113,6 +123,7 @@ struct PathMap {
     const int32_t* explicit_xy;   // pb2_path_li: explicit pixel coordinates, else null
     const uint32_t* explicit_s;
     SamplerView smp;
+    unsigned long long n_pix_magic;   // fast_div_magic(n_pix)
 };
 
 enum Counter : int {

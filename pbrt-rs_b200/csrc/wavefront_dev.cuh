@@ -69,10 +69,10 @@ __device__ __forceinline__ SlotInfo slot_info(const PathMap& m, const FilmView& 
         s.sample = m.explicit_s[slot];
         s.pix = (uint32_t)(s.y - f.sb_y0) * (uint32_t)f.sb_w + (uint32_t)(s.x - f.sb_x0);
     } else {
-        const uint32_t s_local = slot / m.n_pix;
+        const uint32_t s_local = fast_div(slot, m.n_pix_magic);
         s.pix = slot - s_local * m.n_pix;
         s.sample = (uint32_t)m.sample0 + s_local;
-        const uint32_t row = s.pix / (uint32_t)f.sb_w;
+        const uint32_t row = fast_div(s.pix, f.sb_w_magic);
         s.x = f.sb_x0 + (int)(s.pix - row * (uint32_t)f.sb_w);
         s.y = f.sb_y0 + (int)row;
     }
