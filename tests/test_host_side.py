@@ -224,3 +224,16 @@ def test_nudge_equals_next_float_up_down(tmp_path):
     out = subprocess.run([exe, "251"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert " 0 differences" in out.stdout
+
+
+def test_fast_div_is_exact(tmp_path):
+    """slot -> (sample, pixel, row, column) uses n / d = hi64(n * ceil(2^64 / d)) instead of two 32-bit divisions (wavefront.cuh
+    fast_div): equal to n / d on 104 M (n, d) pairs — film widths, powers of two, multiples +- 2, the top of the range, random."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fast_div_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tools", "fast_div_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 differences" in out.stdout
